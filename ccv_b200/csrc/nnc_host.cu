@@ -1,0 +1,673 @@
+// nnc_host.cu -- group (B) of include/ccv_nnc_sm100.h: a minimal stand-alone host for the backend, with the
+// reference's names and semantics (ccv_nnc_init / ccv_nnc_cmd / ccv_nnc_cmd_exec / tensors / stream contexts),
+// so that the backend can be driven without libccv.  When the backend is linked under lib/nnc these symbols are
+// ccv's own and this file is left out.
+//
+// Reference being mirrored: lib/nnc/ccv_nnc_cmd.c:27-30,117-131,307-328,651-693 (init, ok, find_backend, exec),
+// lib/nnc/ccv_nnc_tensor.c:13-110 (tensor new/free/view), lib/nnc/ccv_nnc_stream.c:27-161,289-294 and
+// lib/nnc/gpu/ccv_nnc_compat.cu:255-511 (stream contexts, grow-only workspace), lib/nnc/ccv_nnc_graph_run.c:911-979.
+#include "../../include/ccv_nnc_sm100.h"
+#include "sm100_contract.h"
+#include <cuda_runtime.h>
+#include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unordered_map>
+#include <vector>
+
+struct ccv_nnc_stream_context_s {
+	int type;
+	int device;
+	cudaStream_t stream;
+	void* gpu_workspace;
+	size_t gpu_workspace_size;
+	void* cpu_workspace;
+	size_t cpu_workspace_size;
+	ccv_nnc_stream_context_neighbor_discovery_f neighbor_discovery;
+	void* neighbor_discovery_context;
+};
+
+namespace {
+
+// dispatch table: cmd id -> registry record of the (single) GPU_SM100 backend
+std::unordered_map<uint32_t, ccv_nnc_cmd_backend_registry_t> g_registry;
+std::once_flag g_init_once;
+
+enum { MATRIX_DENSE = 0x00100000, UNMANAGED = 0x20000000, NO_DATA_ALLOC = 0x10000000 };
+
+size_t datatype_size(const int datatype)
+{
+	switch (CCV_GET_DATA_TYPE(datatype))
+	{
+		case CCV_8U: return 1;
+		case CCV_32S: case CCV_32F: return 4;
+		case CCV_64S: case CCV_64F: return 8;
+		case CCV_16F: case CCV_16BF: return 2;
+		case CCV_QX: return 1;
+	}
+	return 0;
+}
+
+int tensor_nd(const int* const dim)
+{
+	int i;
+	for (i = 0; i < CCV_NNC_MAX_DIM_ALLOC; i++)
+		if (dim[i] == 0)
+			return i;
+	return CCV_NNC_MAX_DIM_ALLOC;
+}
+
+// per-thread default stream contexts, one per device (lib/nnc/gpu/ccv_nnc_compat.cu:342-350)
+thread_local ccv_nnc_stream_context_t* t_default_streams[64] = { 0 };
+
+ccv_nnc_stream_context_t* default_stream(const int device)
+{
+	const int d = device < 0 ? 0 : device & 63;
+	if (!t_default_streams[d])
+	{
+		int type = CCV_STREAM_CONTEXT_GPU;
+		CCV_STREAM_SET_DEVICE_ID(type, d);
+		t_default_streams[d] = ccv_nnc_stream_context_new(type);
+	}
+	return t_default_streams[d];
+}
+
+int device_of(ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size)
+{
+	int i;
+	for (i = 0; i < output_size; i++)
+		if (outputs[i] && CCV_TENSOR_GET_MEMORY(outputs[i]->info.type) == CCV_TENSOR_GPU_MEMORY)
+			return CCV_TENSOR_GET_DEVICE_ID(outputs[i]->info.type);
+	for (i = 0; i < input_size; i++)
+		if (inputs[i] && CCV_TENSOR_GET_MEMORY(inputs[i]->info.type) == CCV_TENSOR_GPU_MEMORY)
+			return CCV_TENSOR_GET_DEVICE_ID(inputs[i]->info.type);
+	return -1;
+}
+
+} // namespace
+
+extern "C" {
+
+void ccv_nnc_init(void)
+{
+	std::call_once(g_init_once, []() {
+#define CCV_SM100_CALL_REGISTER(cmd) { ccv_nnc_cmd_backend_registry_t r; memset(&r, 0, sizeof(r)); _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(&r); g_registry[(uint32_t)cmd] = r; }
+		CCV_NNC_SM100_COMMANDS(CCV_SM100_CALL_REGISTER)
+#undef CCV_SM100_CALL_REGISTER
+	});
+}
+
+ccv_nnc_cmd_t ccv_nnc_cmd(const uint32_t cmd, ccv_nnc_cmd_vtab_t* const isa, const ccv_nnc_cmd_param_t params, const int flags)
+{
+	ccv_nnc_cmd_t c;
+	memset(&c, 0, sizeof(c));
+	c.cmd = cmd;
+	c.backend = CCV_NNC_NO_BACKEND;
+	c.algorithm = -1;
+	c.info = params;
+	c.isa = isa;
+	return c;
+}
+
+int ccv_nnc_cmd_ok(const uint32_t cmd, const uint32_t backend)
+{
+	if (cmd == CCV_NNC_NOOP)
+		return 1;
+	if (backend != CCV_NNC_BACKEND_GPU_SM100 && backend != CCV_NNC_NO_BACKEND)
+		return 0;
+	ccv_nnc_init();
+	auto it = g_registry.find(cmd);
+	return it != g_registry.end() && it->second.exec != 0;
+}
+
+uint32_t ccv_nnc_cmd_find_backend(const ccv_nnc_cmd_t cmd, const int tensor_memory, const int tensor_formats, const int tensor_datatypes)
+{
+	if (cmd.cmd == CCV_NNC_NOOP || cmd.cmd == CCV_NNC_CUSTOM_FORWARD || cmd.cmd == CCV_NNC_CUSTOM_BACKWARD)
+		return cmd.backend;
+	ccv_nnc_init();
+	auto it = g_registry.find(cmd.cmd);
+	if (it == g_registry.end())
+		return cmd.backend;
+	const ccv_nnc_cmd_backend_registry_t& r = it->second;
+	if (r.exec && (r.tensor_memory & tensor_memory) == tensor_memory && (r.tensor_formats & tensor_formats) == tensor_formats && (r.tensor_datatypes & tensor_datatypes) == tensor_datatypes)
+		return CCV_NNC_BACKEND_GPU_SM100;
+	return cmd.backend;
+}
+
+uint64_t ccv_nnc_cmd_mono_time(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1000000000ULL + ts.tv_nsec;
+}
+
+int ccv_nnc_cmd_exec(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (cmd.cmd == CCV_NNC_NOOP)
+		return CCV_NNC_EXEC_SUCCESS;
+	ccv_nnc_init();
+	if (!stream_context)
+	{
+		const int device = device_of(inputs, input_size, outputs, output_size);
+		if (device >= 0)
+			cudaSetDevice(device);
+	}
+	if (cmd.cmd == CCV_NNC_CUSTOM_FORWARD || cmd.cmd == CCV_NNC_CUSTOM_BACKWARD)
+		return CCV_NNC_EXEC_NO_KERNEL; // custom vtabs live above this slice of the API
+	uint32_t backend = cmd.backend;
+	if (backend == CCV_NNC_NO_BACKEND)
+	{
+		int tensor_memory = 0, tensor_formats = 0, tensor_datatypes = 0, i;
+		for (i = 0; i < input_size; i++)
+			if (inputs[i])
+				tensor_memory |= CCV_TENSOR_GET_MEMORY(inputs[i]->info.type), tensor_formats |= inputs[i]->info.format, tensor_datatypes |= CCV_GET_DATA_TYPE(inputs[i]->info.datatype);
+		for (i = 0; i < output_size; i++)
+			if (outputs[i])
+				tensor_memory |= CCV_TENSOR_GET_MEMORY(outputs[i]->info.type), tensor_formats |= outputs[i]->info.format, tensor_datatypes |= CCV_GET_DATA_TYPE(outputs[i]->info.datatype);
+		backend = ccv_nnc_cmd_find_backend(cmd, tensor_memory, tensor_formats, tensor_datatypes);
+	}
+	if (backend != CCV_NNC_BACKEND_GPU_SM100)
+		return CCV_NNC_EXEC_NO_KERNEL; // there is deliberately no CPU fallback in this library
+	auto it = g_registry.find(cmd.cmd);
+	if (it == g_registry.end() || !it->second.exec)
+		return CCV_NNC_EXEC_NO_KERNEL;
+	const int ret = it->second.exec(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	if (!stream_context)
+	{
+		// the synchronous form: results are visible (and the per-thread workspace released) on return
+		const int device = device_of(inputs, input_size, outputs, output_size);
+		ccv_nnc_stream_context_t* const s = default_stream(device);
+		ccv_nnc_stream_context_wait(s);
+		ccv_nnc_stream_context_drain(s);
+	}
+	return ret;
+}
+
+ccv_nnc_hint_t ccv_nnc_hint_auto(const ccv_nnc_cmd_param_t cmd, const ccv_nnc_tensor_param_t a, const ccv_nnc_tensor_param_t b)
+{
+	// lib/nnc/ccv_nnc_cmd.c:204-250: for each spatial axis, stride = ceil(a / b)-ish guess and symmetric-as-possible border
+	ccv_nnc_hint_t hint;
+	memset(&hint, 0, sizeof(hint));
+	const int a_nd = tensor_nd(a.dim), b_nd = tensor_nd(b.dim);
+	if (a_nd != b_nd || (a_nd != CCV_NNC_MAX_DIM + 1 && a_nd != CCV_NNC_MAX_DIM + 2))
+		return hint;
+	const int hw_a = (a.format == CCV_TENSOR_FORMAT_NHWC) ? (a_nd == CCV_NNC_MAX_DIM + 1 ? 0 : 1) : (a.format == CCV_TENSOR_FORMAT_NCHW ? (a_nd == CCV_NNC_MAX_DIM + 1 ? 1 : 2) : 0);
+	int i;
+	for (i = 0; i < CCV_NNC_MAX_DIM; i++)
+	{
+		const int ad = a.dim[i + hw_a], bd = b.dim[i + hw_a];
+		if (bd <= 0)
+			continue;
+		const int stride = (ad + bd / 2) / bd > 0 ? (ad + bd / 2) / bd : 1;
+		hint.stride.dim[i] = stride;
+		const int border = cmd.size.dim[i] - (ad - stride * (bd - 1));
+		hint.border.begin[i] = (border + 1) / 2 > 0 ? (border + 1) / 2 : 0;
+		hint.border.end[i] = border - hint.border.begin[i] > 0 ? border - hint.border.begin[i] : 0;
+	}
+	return hint;
+}
+
+size_t ccv_nnc_tensor_data_size(const ccv_nnc_tensor_param_t params)
+{
+	size_t count = 1;
+	int i;
+	for (i = 0; i < CCV_NNC_MAX_DIM_ALLOC && params.dim[i] > 0; i++)
+		count *= (size_t)params.dim[i];
+	const size_t size = count * datatype_size(params.datatype);
+	return (size + 63) & ~(size_t)63;
+}
+
+ccv_nnc_tensor_t* ccv_nnc_tensor_new(const void* const ptr, const ccv_nnc_tensor_param_t params, const int flags)
+{
+	ccv_nnc_tensor_t* tensor = (ccv_nnc_tensor_t*)calloc(1, sizeof(ccv_nnc_tensor_t));
+	tensor->refcount = 1;
+	tensor->info = params;
+	if (ptr)
+	{
+		tensor->type = NO_DATA_ALLOC | MATRIX_DENSE | CCV_GET_DATA_TYPE(params.datatype);
+		tensor->data.u8 = (unsigned char*)ptr;
+		return tensor;
+	}
+	const size_t size = ccv_nnc_tensor_data_size(params);
+	tensor->data_size = size;
+	tensor->type = UNMANAGED | MATRIX_DENSE | CCV_GET_DATA_TYPE(params.datatype);
+	if (size == 0)
+		return tensor;
+	if (CCV_TENSOR_GET_MEMORY(params.type) == CCV_TENSOR_GPU_MEMORY)
+	{
+		cudaSetDevice(CCV_TENSOR_GET_DEVICE_ID(params.type));
+		void* p = 0;
+		const cudaError_t e = cudaMalloc(&p, size);
+		if (e != cudaSuccess)
+		{
+			sm100::set_last_error("cudaMalloc(tensor)", e);
+			free(tensor);
+			return 0;
+		}
+		tensor->data.u8 = (unsigned char*)p;
+	} else {
+		void* p = 0;
+		if (posix_memalign(&p, 64, size))
+		{
+			free(tensor);
+			return 0;
+		}
+		tensor->data.u8 = (unsigned char*)p;
+	}
+	return tensor;
+}
+
+int ccv_nnc_tensor_pin_memory(ccv_nnc_tensor_t* const tensor)
+{
+	if (CCV_TENSOR_GET_MEMORY(tensor->info.type) != CCV_TENSOR_CPU_MEMORY || (tensor->type & CCV_TENSOR_PINNED_MEM) || !tensor->data.u8)
+		return 0;
+	const size_t size = tensor->data_size ? tensor->data_size : ccv_nnc_tensor_data_size(tensor->info);
+	if (cudaHostRegister(tensor->data.u8, size, cudaHostRegisterPortable) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return -1;
+	}
+	tensor->type |= CCV_TENSOR_PINNED_MEM;
+	return 0;
+}
+
+void ccv_nnc_tensor_free(ccv_nnc_tensor_t* const tensor)
+{
+	if (!tensor)
+		return;
+	if (!(tensor->type & NO_DATA_ALLOC) && !CCV_IS_TENSOR_VIEW(tensor) && tensor->data.u8)
+	{
+		if (CCV_TENSOR_GET_MEMORY(tensor->info.type) == CCV_TENSOR_GPU_MEMORY)
+			cudaFree(tensor->data.u8);
+		else {
+			if (tensor->type & CCV_TENSOR_PINNED_MEM)
+				cudaHostUnregister(tensor->data.u8);
+			free(tensor->data.u8);
+		}
+	}
+	free(tensor);
+}
+
+ccv_nnc_tensor_view_t* ccv_nnc_tensor_view_new(const ccv_nnc_tensor_t* const tensor, const ccv_nnc_tensor_param_t params, const int ofs[CCV_NNC_MAX_DIM_ALLOC], const int stride[CCV_NNC_MAX_DIM_ALLOC])
+{
+	// lib/nnc/ccv_nnc_tensor.c:247-310: data already includes the view offset; contiguous iff strides are the packed ones
+	ccv_nnc_tensor_view_t* tv = (ccv_nnc_tensor_view_t*)calloc(1, sizeof(ccv_nnc_tensor_view_t));
+	tv->type = (tensor->type & ~0xfff) | CCV_TENSOR_VIEW | NO_DATA_ALLOC;
+	tv->refcount = 1;
+	tv->info = params;
+	tv->alias_ref = (uintptr_t)tensor;
+	const int nd = tensor_nd(params.dim);
+	size_t off = 0;
+	int i;
+	for (i = 0; i < nd; i++)
+		off += (size_t)ofs[i] * stride[i];
+	off *= datatype_size(params.datatype);
+	tv->off = (off_t)off;
+	tv->data.u8 = tensor->data.u8 + off;
+	tv->dataof = tensor->dataof;
+	memcpy(tv->stride, stride, sizeof(int) * CCV_NNC_MAX_DIM_ALLOC);
+	int packed = 1, contiguous = 1;
+	for (i = nd - 1; i >= 0; i--)
+	{
+		if (stride[i] != packed)
+			contiguous = 0;
+		packed *= params.dim[i];
+	}
+	tv->contiguous = contiguous;
+	return tv;
+}
+
+void ccv_nnc_tensor_view_free(ccv_nnc_tensor_view_t* const tensor_view)
+{
+	free(tensor_view);
+}
+
+// ---------------------------------------------------------------------------------------------------- streams
+ccv_nnc_stream_context_t* ccv_nnc_stream_context_new(const int type)
+{
+	ccv_nnc_stream_context_t* s = (ccv_nnc_stream_context_t*)calloc(1, sizeof(ccv_nnc_stream_context_t));
+	s->type = type;
+	s->device = CCV_STREAM_GET_DEVICE_ID(type);
+	if (CCV_STREAM_GET_CONTEXT(type) == CCV_STREAM_CONTEXT_GPU)
+	{
+		cudaSetDevice(s->device);
+		const cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+		if (e != cudaSuccess)
+		{
+			sm100::set_last_error("cudaStreamCreate", e);
+			free(s);
+			return 0;
+		}
+	}
+	return s;
+}
+
+int ccv_nnc_stream_context_type(const ccv_nnc_stream_context_t* const stream_context)
+{
+	return stream_context->type;
+}
+
+void* ccv_nnc_stream_context_get_stream(const ccv_nnc_stream_context_t* const stream_context)
+{
+	if (!stream_context)
+	{
+		int device = 0;
+		cudaGetDevice(&device);
+		return (void*)default_stream(device)->stream;
+	}
+	return (void*)stream_context->stream;
+}
+
+int ccv_nnc_stream_context_get_device(const ccv_nnc_stream_context_t* const stream_context)
+{
+	if (!stream_context)
+	{
+		int device = 0;
+		cudaGetDevice(&device);
+		return device;
+	}
+	return stream_context->device;
+}
+
+void* ccv_nnc_stream_context_get_workspace(ccv_nnc_stream_context_t* const stream_context, const size_t workspace_size, const int mem)
+{
+	// a single grow-only buffer per (stream, device): one op's scratch is invalidated by the next request on the same
+	// stream, which is safe because work on a stream is ordered (lib/nnc/gpu/ccv_nnc_compat.cu:438-471)
+	ccv_nnc_stream_context_t* s = stream_context;
+	if (!s)
+	{
+		int device = 0;
+		cudaGetDevice(&device);
+		s = default_stream(device);
+	}
+	if (mem == CCV_TENSOR_CPU_MEMORY)
+	{
+		if (s->cpu_workspace_size < workspace_size)
+		{
+			free(s->cpu_workspace);
+			s->cpu_workspace = 0;
+			s->cpu_workspace_size = 0;
+			if (posix_memalign(&s->cpu_workspace, 64, workspace_size))
+				return 0;
+			s->cpu_workspace_size = workspace_size;
+		}
+		return s->cpu_workspace;
+	}
+	if (s->gpu_workspace_size < workspace_size)
+	{
+		if (s->gpu_workspace)
+		{
+			// kernels already enqueued may still be using the old buffer
+			cudaStreamSynchronize(s->stream);
+			cudaFree(s->gpu_workspace);
+		}
+		s->gpu_workspace = 0;
+		s->gpu_workspace_size = 0;
+		const size_t rounded = (workspace_size + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
+		const cudaError_t e = cudaMalloc(&s->gpu_workspace, rounded);
+		if (e != cudaSuccess)
+		{
+			sm100::set_last_error("cudaMalloc(workspace)", e);
+			return 0;
+		}
+		s->gpu_workspace_size = rounded;
+	}
+	return s->gpu_workspace;
+}
+
+void ccv_nnc_stream_context_drain(ccv_nnc_stream_context_t* const stream_context)
+{
+	if (!stream_context)
+		return;
+	if (stream_context->gpu_workspace)
+	{
+		cudaStreamSynchronize(stream_context->stream);
+		cudaFree(stream_context->gpu_workspace);
+		stream_context->gpu_workspace = 0;
+		stream_context->gpu_workspace_size = 0;
+	}
+	free(stream_context->cpu_workspace);
+	stream_context->cpu_workspace = 0;
+	stream_context->cpu_workspace_size = 0;
+}
+
+void ccv_nnc_stream_context_wait(const ccv_nnc_stream_context_t* const stream_context)
+{
+	if (!stream_context)
+	{
+		int device = 0;
+		cudaGetDevice(&device);
+		cudaStreamSynchronize(default_stream(device)->stream);
+		return;
+	}
+	if (CCV_STREAM_GET_CONTEXT(stream_context->type) == CCV_STREAM_CONTEXT_GPU)
+	{
+		const cudaError_t e = cudaStreamSynchronize(stream_context->stream);
+		if (e != cudaSuccess)
+			sm100::set_last_error("cudaStreamSynchronize", e);
+	}
+}
+
+void ccv_nnc_stream_context_free(ccv_nnc_stream_context_t* const stream_context)
+{
+	if (!stream_context)
+		return;
+	ccv_nnc_stream_context_drain(stream_context);
+	if (stream_context->stream)
+		cudaStreamDestroy(stream_context->stream);
+	free(stream_context);
+}
+
+int ccv_nnc_device_count(const int type)
+{
+	if (CCV_STREAM_GET_CONTEXT(type) != CCV_STREAM_CONTEXT_GPU)
+		return 1;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
+	return count;
+}
+
+void ccv_nnc_stream_context_set_neighbor_discovery(ccv_nnc_stream_context_t* const stream_context, ccv_nnc_stream_context_neighbor_discovery_f discovery, void* const context)
+{
+	stream_context->neighbor_discovery = discovery;
+	stream_context->neighbor_discovery_context = context;
+}
+
+ccv_nnc_stream_context_t* ccv_nnc_stream_context_find_neighbor(ccv_nnc_stream_context_t* const stream_context, const int device_id)
+{
+	if (stream_context->device == device_id)
+		return stream_context;
+	if (stream_context->neighbor_discovery)
+		return stream_context->neighbor_discovery(device_id, stream_context->neighbor_discovery_context);
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- FFI helpers
+int ccv_nnc_sm100_cmd_exec(const uint32_t cmd, const uint32_t backend, const int algorithm, const ccv_nnc_cmd_param_t* const info, const ccv_nnc_hint_t* const hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	ccv_nnc_cmd_t c = ccv_nnc_cmd(cmd, 0, *info, 0);
+	c.backend = backend;
+	c.algorithm = algorithm;
+	return ccv_nnc_cmd_exec(c, *hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
+ccv_nnc_tensor_t* ccv_nnc_sm100_tensor_new(const void* const ptr, const ccv_nnc_tensor_param_t* const params)
+{
+	return ccv_nnc_tensor_new(ptr, *params, 0);
+}
+
+ccv_nnc_tensor_view_t* ccv_nnc_sm100_tensor_view_new(const ccv_nnc_tensor_t* const tensor, const ccv_nnc_tensor_param_t* const params, const int* const ofs, const int* const stride)
+{
+	return ccv_nnc_tensor_view_new(tensor, *params, ofs, stride);
+}
+
+void ccv_nnc_sm100_hint_auto(const ccv_nnc_cmd_param_t* const info, const ccv_nnc_tensor_param_t* const a, const ccv_nnc_tensor_param_t* const b, ccv_nnc_hint_t* const hint)
+{
+	*hint = ccv_nnc_hint_auto(*info, *a, *b);
+}
+
+int ccv_nnc_sm100_memcpy_h2d(void* const dst_device, const void* const src_host, const size_t bytes, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t stream = (cudaStream_t)ccv_nnc_stream_context_get_stream(stream_context);
+	cudaError_t e = cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(stream);
+	if (e != cudaSuccess)
+	{
+		sm100::set_last_error("memcpy_h2d", e);
+		return -1;
+	}
+	return 0;
+}
+
+int ccv_nnc_sm100_memcpy_d2h(void* const dst_host, const void* const src_device, const size_t bytes, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t stream = (cudaStream_t)ccv_nnc_stream_context_get_stream(stream_context);
+	cudaError_t e = cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(stream);
+	if (e != cudaSuccess)
+	{
+		sm100::set_last_error("memcpy_d2h", e);
+		return -1;
+	}
+	return 0;
+}
+
+uint64_t ccv_nnc_sm100_launch_count(void)
+{
+	return (uint64_t)sm100::launch_count();
+}
+
+const char* ccv_nnc_sm100_last_error(void)
+{
+	return sm100::last_error();
+}
+
+// ---------------------------------------------------------------------------------------------------- flat graph
+} // extern "C"
+
+struct ccv_nnc_sm100_graph_node_t {
+	ccv_nnc_cmd_t cmd;
+	ccv_nnc_hint_t hint;
+	int flags;
+	std::vector<ccv_nnc_tensor_t*> inputs, outputs;
+};
+
+struct ccv_nnc_sm100_graph_s {
+	std::vector<ccv_nnc_sm100_graph_node_t> nodes;
+	std::vector<cudaGraphExec_t> captures;
+};
+
+extern "C" {
+
+ccv_nnc_sm100_graph_t* ccv_nnc_sm100_graph_new(void)
+{
+	return new ccv_nnc_sm100_graph_s();
+}
+
+int ccv_nnc_sm100_graph_exec_new(ccv_nnc_sm100_graph_t* const graph, const uint32_t cmd, const uint32_t backend, const int algorithm, const ccv_nnc_cmd_param_t* const info, const ccv_nnc_hint_t* const hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size)
+{
+	ccv_nnc_sm100_graph_node_t node;
+	node.cmd = ccv_nnc_cmd(cmd, 0, *info, 0);
+	node.cmd.backend = backend;
+	node.cmd.algorithm = algorithm;
+	node.hint = *hint;
+	node.flags = flags;
+	node.inputs.assign(inputs, inputs + input_size);
+	node.outputs.assign(outputs, outputs + output_size);
+	graph->nodes.push_back(node);
+	return (int)graph->nodes.size() - 1;
+}
+
+int ccv_nnc_sm100_graph_size(const ccv_nnc_sm100_graph_t* const graph)
+{
+	return (int)graph->nodes.size();
+}
+
+int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin, const int end, ccv_nnc_stream_context_t* const stream_context)
+{
+	// lib/nnc/ccv_nnc_graph_run.c:911-979: for each exec in topological order: ccv_nnc_cmd_exec(...); non-zero is reported, not fatal
+	int status = 0, i;
+	const int last = end < 0 || end > (int)graph->nodes.size() ? (int)graph->nodes.size() : end;
+	for (i = begin < 0 ? 0 : begin; i < last; i++)
+	{
+		ccv_nnc_sm100_graph_node_t& n = graph->nodes[i];
+		const int ret = ccv_nnc_cmd_exec(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), stream_context);
+		if (ret != 0 && status == 0)
+		{
+			fprintf(stderr, "[ccv_nnc_sm100] graph node %d (cmd 0x%08x) returned %d\n", i, n.cmd.cmd, ret);
+			status = ret;
+		}
+	}
+	return status;
+}
+
+int ccv_nnc_sm100_graph_capture(ccv_nnc_sm100_graph_t* const graph, const int begin, const int end, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (!stream_context)
+		return -1;
+	cudaStream_t stream = stream_context->stream;
+	// one eager pass first: sizes the workspace (allocation is illegal during capture) and loads kernels
+	int status = ccv_nnc_sm100_graph_run(graph, begin, end, stream_context);
+	if (status != 0)
+		return -1;
+	if (cudaStreamSynchronize(stream) != cudaSuccess)
+		return -1;
+	cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+	if (e != cudaSuccess)
+	{
+		sm100::set_last_error("cudaStreamBeginCapture", e);
+		return -1;
+	}
+	status = ccv_nnc_sm100_graph_run(graph, begin, end, stream_context);
+	cudaGraph_t g = 0;
+	e = cudaStreamEndCapture(stream, &g);
+	if (e != cudaSuccess || status != 0 || !g)
+	{
+		sm100::set_last_error("cudaStreamEndCapture", e);
+		if (g)
+			cudaGraphDestroy(g);
+		return -1;
+	}
+	cudaGraphExec_t ge = 0;
+	e = cudaGraphInstantiate(&ge, g, 0);
+	cudaGraphDestroy(g);
+	if (e != cudaSuccess)
+	{
+		sm100::set_last_error("cudaGraphInstantiate", e);
+		return -1;
+	}
+	graph->captures.push_back(ge);
+	return (int)graph->captures.size() - 1;
+}
+
+int ccv_nnc_sm100_graph_replay(ccv_nnc_sm100_graph_t* const graph, const int capture_id, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (capture_id < 0 || capture_id >= (int)graph->captures.size() || !stream_context)
+		return -1;
+	const cudaError_t e = cudaGraphLaunch(graph->captures[capture_id], stream_context->stream);
+	if (e != cudaSuccess)
+	{
+		sm100::set_last_error("cudaGraphLaunch", e);
+		return -1;
+	}
+	return 0;
+}
+
+void ccv_nnc_sm100_graph_free(ccv_nnc_sm100_graph_t* const graph)
+{
+	if (!graph)
+		return;
+	for (cudaGraphExec_t ge : graph->captures)
+		cudaGraphExecDestroy(ge);
+	delete graph;
+}
+
+} // extern "C"

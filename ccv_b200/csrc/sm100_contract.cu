@@ -1,0 +1,476 @@
+// sm100_contract.cu -- host-side launchers for the tcgen05/TMA contraction kernel (sm100_umma_gemm.cuh):
+// tensor-map encoding (tile and im2col mode) and the mapping of GEMM / convolution fprop / dgrad / wgrad
+// onto its operand modes.  Reference semantics being reproduced: lib/nnc/cmd/blas/ccv_nnc_gemm_cpu_ref.c:110-448,
+// lib/nnc/cmd/convolution/ccv_nnc_conv_cpu_ref.c:13-345 (NHWC).
+#include "sm100_contract.h"
+#include "sm100_umma_gemm.cuh"
+#include <atomic>
+#include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace sm100 {
+
+// ------------------------------------------------------------------------------------------------ bookkeeping
+static std::atomic<unsigned long long> g_launches(0);
+static char g_last_error[256] = "";
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void set_last_error(const char* what, cudaError_t err)
+{
+	snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(err));
+	fprintf(stderr, "[ccv_nnc_sm100] %s\n", g_last_error);
+}
+const char* last_error() { return g_last_error; }
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*encode_tiled_f)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*encode_im2col_f)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_f g_encode_tiled = 0;
+static encode_im2col_f g_encode_im2col = 0;
+static int g_driver_version = 0;
+static int g_tma_dtype = -1; // CUtensorMapDataType used for fp32 operands
+
+static bool tma_api_init()
+{
+	static std::once_flag once;
+	std::call_once(once, []() {
+		void* fn = 0;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+			g_encode_tiled = (encode_tiled_f)fn;
+		fn = 0;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+			g_encode_im2col = (encode_im2col_f)fn;
+		cudaDriverGetVersion(&g_driver_version);
+		// TFLOAT32 makes the TMA unit write round-to-nearest TF32 values into shared memory, so the tensor core's
+		// implicit truncation of the low 13 mantissa bits becomes a no-op (unbiased error instead of a 2^-11 bias).
+		const char* e = getenv("CCV_NNC_SM100_TMA_DTYPE");
+		g_tma_dtype = e ? atoi(e) : (int)CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+	});
+	return g_encode_tiled != 0 && g_encode_im2col != 0;
+}
+
+// fp32 2-D row-major [rows, cols] with row pitch `ld` elements; box = {box_cols (<= 32), box_rows}
+static bool make_map_2d(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool mn_major = false)
+{
+	if ((((uintptr_t)ptr) & 15) || ((ld * 4) & 15) || ld * 4 >= (1ll << 40))
+		return false;
+	cuuint64_t dims[2] = { (cuuint64_t)cols, (cuuint64_t)rows };
+	cuuint64_t strides[1] = { (cuuint64_t)ld * 4 };
+	cuuint32_t box[2] = { (cuuint32_t)box_cols, (cuuint32_t)box_rows };
+	cuuint32_t estr[2] = { 1, 1 };
+	CUresult r = g_encode_tiled(map, (CUtensorMapDataType)g_tma_dtype, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS;
+}
+
+// fp32 NHWC tensor {C, W, H, N} in im2col mode. Base pixels run over [lower, dim + upper) per spatial axis with the
+// given traversal stride; each load fetches `pixels` base pixels x `channels` channels at base + tap offset.
+static bool make_map_im2col(CUtensorMap* map, const float* ptr, int N, int H, int W, int C, long long sn, long long sh, long long sw, int lower_h, int lower_w, int upper_h, int upper_w, int trav_h, int trav_w, int channels, int pixels, bool mn_major = false)
+{
+	if ((((uintptr_t)ptr) & 15) || ((sw * 4) & 15) || ((sh * 4) & 15) || ((sn * 4) & 15))
+		return false;
+	if (lower_h < -128 || lower_h > 127 || lower_w < -128 || lower_w > 127 || upper_h < -128 || upper_h > 127 || upper_w < -128 || upper_w > 127)
+		return false;
+	if (trav_h < 1 || trav_h > 8 || trav_w < 1 || trav_w > 8)
+		return false;
+	cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N };
+	cuuint64_t strides[3] = { (cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4 };
+	int lower[2] = { lower_w, lower_h };
+	int upper[2] = { upper_w, upper_h };
+	cuuint32_t estr[4] = { 1, (cuuint32_t)trav_w, (cuuint32_t)trav_h, 1 };
+	CUresult r = g_encode_im2col(map, (CUtensorMapDataType)g_tma_dtype, 4, (void*)ptr, dims, strides, lower, upper, (cuuint32_t)channels, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS)
+		return false;
+	// Same driver workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): for tensors under 128 KiB, drivers
+	// <= 13.1 set a descriptor bit that makes im2col loads fault.
+	if (g_driver_version <= 13010 && (long long)N * sn * 4 < 131072)
+		reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------ launch
+static int g_num_sms = 0;
+static int num_sms()
+{
+	if (!g_num_sms)
+	{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+		if (g_num_sms <= 0)
+			g_num_sms = 148;
+	}
+	return g_num_sms;
+}
+
+template <int AMODE, int BMODE, int BN, int STAGES>
+static int launch_umma(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p, int grid_x, int grid_y)
+{
+	using S = UmmaSmem<BN, STAGES>;
+	auto kern = umma_gemm_kernel<AMODE, BMODE, BN, STAGES>;
+	static bool configured = false;
+	if (!configured)
+	{
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+		if (e != cudaSuccess)
+		{
+			set_last_error("cudaFuncSetAttribute(umma_gemm_kernel)", e);
+			return -1;
+		}
+		configured = true;
+	}
+	dim3 grid(grid_x, grid_y, p.grid_taps * p.splits);
+	kern<<<grid, 192, S::TOTAL, stream>>>(tmA, tmB, p);
+	count_launch();
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error("umma_gemm_kernel launch", e);
+		return -1;
+	}
+	return 0;
+}
+
+// BN = 128 with 3 stages (2 CTAs/SM) is the default shape; BN = 64 keeps small-N problems from wasting MMA columns.
+template <int AMODE, int BMODE>
+static int launch_umma_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p, int bn)
+{
+	const int gx = (p.M + UMMA_BLOCK_M - 1) / UMMA_BLOCK_M;
+	const int gy = (p.N + bn - 1) / bn;
+	if (bn == 64)
+		return launch_umma<AMODE, BMODE, 64, 4>(stream, tmA, tmB, p, gx, gy);
+	return launch_umma<AMODE, BMODE, 128, 3>(stream, tmA, tmB, p, gx, gy);
+}
+
+static int pick_bn(int N)
+{
+	const char* e = getenv("CCV_NNC_SM100_BN");
+	if (e)
+		return atoi(e) == 64 ? 64 : 128;
+	return N <= 64 ? 64 : 128;
+}
+
+static void init_params(UmmaGemmParams& p)
+{
+	memset(&p, 0, sizeof(p));
+	p.splits = 1;
+	p.grid_taps = 1;
+	p.alpha = 1.f;
+	p.stride_h = p.stride_w = 1;
+	p.P = p.Q = 1;
+	static int lbo = -1, sbo = -1, layout = -1;
+	if (lbo < 0)
+	{
+		const char* e;
+		lbo = (e = getenv("CCV_NNC_SM100_MN_LBO")) ? atoi(e) : 4096;
+		sbo = (e = getenv("CCV_NNC_SM100_MN_SBO")) ? atoi(e) : 512;
+		layout = (e = getenv("CCV_NNC_SM100_MN_LAYOUT")) ? atoi(e) : 1;
+	}
+	p.mn_lbo = lbo, p.mn_sbo = sbo, p.mn_layout = layout;
+}
+
+static int pick_splits(long long tiles, int k_iters, int min_iters_per_split)
+{
+	// aim for ~2 CTAs per SM in flight; never split finer than `min_iters_per_split` k-iterations
+	const long long target = 2ll * num_sms();
+	if (tiles >= target)
+		return 1;
+	long long s = (target + tiles - 1) / tiles;
+	const long long max_s = k_iters / min_iters_per_split;
+	if (s > max_s)
+		s = max_s;
+	if (s < 1)
+		s = 1;
+	// no empty splits: per = ceil(k/s) must leave the last split non-empty
+	while (s > 1 && (long long)((k_iters + s - 1) / s) * (s - 1) >= k_iters)
+		s--;
+	return (int)s;
+}
+
+int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long long lda, int trans_a, const float* b, long long ldb, int trans_b, float* c, long long ldc, const float* bias, int accumulate)
+{
+	if (!tma_api_init() || M <= 0 || N <= 0 || K <= 0)
+		return 1;
+	const int bn = pick_bn(N);
+	CUtensorMap tmA, tmB;
+	bool ok;
+	if (!trans_a)
+		ok = make_map_2d(&tmA, a, M, K, lda, 32, UMMA_BLOCK_M);
+	else
+		ok = make_map_2d(&tmA, a, K, M, lda, 32, UMMA_BLOCK_K, true);
+	if (!ok)
+		return 1;
+	if (trans_b) // stored [N, K]: K-major
+		ok = make_map_2d(&tmB, b, N, K, ldb, 32, bn);
+	else // stored [K, N]: N contiguous
+		ok = make_map_2d(&tmB, b, K, N, ldb, 32, UMMA_BLOCK_K, true);
+	if (!ok)
+		return 1;
+	UmmaGemmParams p;
+	init_params(p);
+	p.M = M, p.N = N;
+	p.k_iters = (K + UMMA_BLOCK_K - 1) / UMMA_BLOCK_K;
+	p.chunks_per_tap = p.k_iters;
+	p.out = c, p.bias = bias, p.accumulate = accumulate;
+	p.rowmap.mode = 0, p.rowmap.ld = ldc;
+	p.idesc = umma_instr_desc(2, trans_a, !trans_b, UMMA_BLOCK_M, bn);
+	const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn);
+	p.splits = pick_splits(tiles, p.k_iters, 8);
+	if (p.splits > 1 && !accumulate)
+	{
+		// split-K partial sums are combined with red.add: start from zero
+		cudaError_t e = cudaMemset2DAsync(c, ldc * 4, 0, (size_t)N * 4, M, stream);
+		if (e != cudaSuccess)
+		{
+			set_last_error("memset(split-K)", e);
+			return -1;
+		}
+	}
+	if (!trans_a && trans_b)
+		return launch_umma_bn<OP_K2D, OP_K2D>(stream, tmA, tmB, p, bn);
+	if (!trans_a && !trans_b)
+		return launch_umma_bn<OP_K2D, OP_MN2D>(stream, tmA, tmB, p, bn);
+	if (trans_a && trans_b)
+		return launch_umma_bn<OP_MN2D, OP_K2D>(stream, tmA, tmB, p, bn);
+	return launch_umma_bn<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn);
+}
+
+static bool conv_is_pointwise(const ConvGeom& g)
+{
+	return g.R == 1 && g.S == 1 && g.stride_h == 1 && g.stride_w == 1 && g.pad_h0 == 0 && g.pad_h1 == 0 && g.pad_w0 == 0 && g.pad_w1 == 0 &&
+		g.aw == g.C && g.ah == (long long)g.W * g.C && g.an == (long long)g.H * g.W * g.C && g.bw == g.K && g.bh == (long long)g.Q * g.K && g.bn == (long long)g.P * g.Q * g.K;
+}
+
+static bool conv_out_contiguous(const ConvGeom& g)
+{
+	return g.bw == g.K && g.bh == (long long)g.Q * g.K && g.bn == (long long)g.P * g.Q * g.K;
+}
+
+static bool conv_in_contiguous(const ConvGeom& g)
+{
+	return g.aw == g.C && g.ah == (long long)g.W * g.C && g.an == (long long)g.H * g.W * g.C;
+}
+
+static bool conv_shape_consistent(const ConvGeom& g)
+{
+	const int eff_r = (g.R - 1) * g.dil_h + 1, eff_s = (g.S - 1) * g.dil_w + 1;
+	return (g.H + g.pad_h0 + g.pad_h1 - eff_r) / g.stride_h + 1 == g.P && (g.W + g.pad_w0 + g.pad_w1 - eff_s) / g.stride_w + 1 == g.Q &&
+		g.R * g.S <= UMMA_MAX_TAPS && g.C % 4 == 0 && g.K % 4 == 0;
+}
+
+int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b)
+{
+	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g))
+		return 1;
+	const long long M = (long long)g.N * g.P * g.Q;
+	if (M > 0x7fffffffll)
+		return 1;
+	if (conv_is_pointwise(g)) // a plain [NHW, C] x [K, C]^T GEMM
+		return gemm_tf32(stream, (int)M, g.K, g.C, a, g.C, 0, w, g.C, 1, b, g.K, bias, 0);
+	const int bn = pick_bn(g.K);
+	CUtensorMap tmA, tmB;
+	if (!make_map_im2col(&tmA, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, 32, UMMA_BLOCK_M))
+		return 1;
+	const long long rsc = (long long)g.R * g.S * g.C;
+	if (!make_map_2d(&tmB, w, g.K, rsc, rsc, 32, bn))
+		return 1;
+	UmmaGemmParams p;
+	init_params(p);
+	p.M = (int)M, p.N = g.K;
+	p.chunks_per_tap = (g.C + 31) / 32;
+	p.k_iters = g.R * g.S * p.chunks_per_tap;
+	p.P = g.P, p.Q = g.Q;
+	p.stride_h = g.stride_h, p.stride_w = g.stride_w;
+	p.base_h = -g.pad_h0, p.base_w = -g.pad_w0;
+	for (int r = 0; r < g.R; r++)
+		for (int s = 0; s < g.S; s++)
+		{
+			const int t = r * g.S + s;
+			p.tap_off_h[t] = (unsigned short)(r * g.dil_h);
+			p.tap_off_w[t] = (unsigned short)(s * g.dil_w);
+			p.tap_b_col[t] = t * g.C;
+		}
+	p.out = b, p.bias = bias;
+	p.rowmap.mode = 0, p.rowmap.ld = g.K;
+	p.idesc = umma_instr_desc(2, 0, 0, UMMA_BLOCK_M, bn);
+	return launch_umma_bn<OP_IM2COL, OP_K2D>(stream, tmA, tmB, p, bn);
+}
+
+int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a)
+{
+	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g) || !conv_in_contiguous(g))
+		return 1;
+	if (conv_is_pointwise(g)) // dA[NHW, C] = dB[NHW, K] x W[K, C]
+		return gemm_tf32(stream, g.N * g.H * g.W, g.C, g.K, grad_b, g.K, 0, w, g.C, 0, grad_a, g.C, 0, 0);
+	const int bn = pick_bn(g.C);
+	const long long rsc = (long long)g.R * g.S * g.C;
+	CUtensorMap tmB;
+	if (!make_map_2d(&tmB, w, g.K, rsc, rsc, 32, UMMA_BLOCK_K, true))
+		return 1;
+	// Decompose by output-pixel residue class (ah, aw) modulo the stride: within a class, pixel h = i * stride + ah
+	// receives from filter row r iff (ah + pad - r * dil) % stride == 0, reading grad_b row i + (ah + pad - r * dil) / stride.
+	bool need_zero = false;
+	struct ClassPlan {
+		int ntaps_h, ntaps_w;
+		int e_h[UMMA_MAX_TAPS], r_h[UMMA_MAX_TAPS], e_w[UMMA_MAX_TAPS], s_w[UMMA_MAX_TAPS];
+	};
+	for (int ah = 0; ah < g.stride_h; ah++)
+		for (int aw = 0; aw < g.stride_w; aw++)
+		{
+			ClassPlan cp;
+			cp.ntaps_h = cp.ntaps_w = 0;
+			for (int r = 0; r < g.R; r++)
+			{
+				const int num = ah + g.pad_h0 - r * g.dil_h;
+				if (((num % g.stride_h) + g.stride_h) % g.stride_h == 0)
+					cp.e_h[cp.ntaps_h] = (num >= 0 ? num / g.stride_h : -((-num) / g.stride_h)), cp.r_h[cp.ntaps_h++] = r;
+			}
+			for (int s = 0; s < g.S; s++)
+			{
+				const int num = aw + g.pad_w0 - s * g.dil_w;
+				if (((num % g.stride_w) + g.stride_w) % g.stride_w == 0)
+					cp.e_w[cp.ntaps_w] = (num >= 0 ? num / g.stride_w : -((-num) / g.stride_w)), cp.s_w[cp.ntaps_w++] = s;
+			}
+			const int Hc = (g.H - ah + g.stride_h - 1) / g.stride_h, Wc = (g.W - aw + g.stride_w - 1) / g.stride_w;
+			if (Hc <= 0 || Wc <= 0)
+				continue;
+			if (cp.ntaps_h == 0 || cp.ntaps_w == 0)
+			{
+				need_zero = true;
+				continue;
+			}
+		}
+	if (need_zero)
+	{
+		cudaError_t e = cudaMemsetAsync(grad_a, 0, (size_t)g.N * g.H * g.W * g.C * 4, stream);
+		if (e != cudaSuccess)
+		{
+			set_last_error("memset(dgrad)", e);
+			return -1;
+		}
+	}
+	for (int ah = 0; ah < g.stride_h; ah++)
+		for (int aw = 0; aw < g.stride_w; aw++)
+		{
+			ClassPlan cp;
+			cp.ntaps_h = cp.ntaps_w = 0;
+			int lo_h = 1 << 30, lo_w = 1 << 30;
+			for (int r = 0; r < g.R; r++)
+			{
+				const int num = ah + g.pad_h0 - r * g.dil_h;
+				if (((num % g.stride_h) + g.stride_h) % g.stride_h == 0)
+				{
+					const int e = num >= 0 ? num / g.stride_h : -((-num) / g.stride_h);
+					cp.e_h[cp.ntaps_h] = e, cp.r_h[cp.ntaps_h++] = r;
+					if (e < lo_h)
+						lo_h = e;
+				}
+			}
+			for (int s = 0; s < g.S; s++)
+			{
+				const int num = aw + g.pad_w0 - s * g.dil_w;
+				if (((num % g.stride_w) + g.stride_w) % g.stride_w == 0)
+				{
+					const int e = num >= 0 ? num / g.stride_w : -((-num) / g.stride_w);
+					cp.e_w[cp.ntaps_w] = e, cp.s_w[cp.ntaps_w++] = s;
+					if (e < lo_w)
+						lo_w = e;
+				}
+			}
+			const int Hc = (g.H - ah + g.stride_h - 1) / g.stride_h, Wc = (g.W - aw + g.stride_w - 1) / g.stride_w;
+			if (Hc <= 0 || Wc <= 0 || cp.ntaps_h == 0 || cp.ntaps_w == 0)
+				continue;
+			CUtensorMap tmA;
+			// base pixels i in [0, Hc) map to grad_b rows i + lo_h + offset: bounding box [lo_h, P + (Hc - P + lo_h))
+			if (!make_map_im2col(&tmA, grad_b, g.N, g.P, g.Q, g.K, g.bn, g.bh, g.bw, lo_h, lo_w, Hc - g.P + lo_h, Wc - g.Q + lo_w, 1, 1, 32, UMMA_BLOCK_M))
+				return 1;
+			UmmaGemmParams p;
+			init_params(p);
+			p.M = g.N * Hc * Wc, p.N = g.C;
+			p.chunks_per_tap = (g.K + 31) / 32;
+			p.k_iters = cp.ntaps_h * cp.ntaps_w * p.chunks_per_tap;
+			p.P = Hc, p.Q = Wc;
+			p.base_h = lo_h, p.base_w = lo_w;
+			for (int i = 0; i < cp.ntaps_h; i++)
+				for (int j = 0; j < cp.ntaps_w; j++)
+				{
+					const int t = i * cp.ntaps_w + j;
+					p.tap_off_h[t] = (unsigned short)(cp.e_h[i] - lo_h);
+					p.tap_off_w[t] = (unsigned short)(cp.e_w[j] - lo_w);
+					p.tap_b_col[t] = (cp.r_h[i] * g.S + cp.s_w[j]) * g.C;
+				}
+			p.out = grad_a + ((long long)ah * g.W + aw) * g.C;
+			p.rowmap.mode = 1;
+			p.rowmap.Pc = Hc, p.rowmap.Qc = Wc;
+			p.rowmap.n_stride = (long long)g.H * g.W * g.C;
+			p.rowmap.h_stride = (long long)g.stride_h * g.W * g.C;
+			p.rowmap.w_stride = (long long)g.stride_w * g.C;
+			p.idesc = umma_instr_desc(2, 0, 1, UMMA_BLOCK_M, bn);
+			const int rc = launch_umma_bn<OP_IM2COL, OP_MN2D>(stream, tmA, tmB, p, bn);
+			if (rc)
+				return rc;
+		}
+	return 0;
+}
+
+int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate)
+{
+	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g))
+		return 1;
+	const long long npq = (long long)g.N * g.P * g.Q;
+	if (npq > 0x7fffffffll)
+		return 1;
+	const int bn = pick_bn(g.C);
+	const long long rsc = (long long)g.R * g.S * g.C;
+	CUtensorMap tmA, tmB;
+	// A = grad_b^T: [K, NPQ] read from the [NPQ, K] tensor as an MN-major operand
+	if (!make_map_2d(&tmA, grad_b, npq, g.K, g.K, 32, UMMA_BLOCK_K, true))
+		return 1;
+	UmmaGemmParams p;
+	init_params(p);
+	p.M = g.K, p.N = g.C;
+	p.k_iters = (int)((npq + UMMA_BLOCK_K - 1) / UMMA_BLOCK_K);
+	p.chunks_per_tap = p.k_iters;
+	p.out = grad_w;
+	p.rowmap.mode = 0, p.rowmap.ld = rsc;
+	p.idesc = umma_instr_desc(2, 1, 1, UMMA_BLOCK_M, bn);
+	const long long tiles = (long long)((g.K + 127) / 128) * ((g.C + bn - 1) / bn) * g.R * g.S;
+	p.splits = pick_splits(tiles, p.k_iters, 16);
+	if (p.splits > 1 && !accumulate)
+	{
+		cudaError_t e = cudaMemsetAsync(grad_w, 0, (size_t)g.K * rsc * 4, stream);
+		if (e != cudaSuccess)
+		{
+			set_last_error("memset(wgrad)", e);
+			return -1;
+		}
+	}
+	p.accumulate = accumulate;
+	if (conv_is_pointwise(g))
+	{
+		// B = a: [NHW, C], also MN-major
+		if (!make_map_2d(&tmB, a, npq, g.C, g.C, 32, UMMA_BLOCK_K, true))
+			return 1;
+		return launch_umma_bn<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn);
+	}
+	if (!make_map_im2col(&tmB, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, 32, UMMA_BLOCK_K, true))
+		return 1;
+	p.grid_taps = g.R * g.S;
+	p.grid_tap_out_stride = g.C;
+	p.P = g.P, p.Q = g.Q;
+	p.stride_h = g.stride_h, p.stride_w = g.stride_w;
+	p.base_h = -g.pad_h0, p.base_w = -g.pad_w0;
+	for (int r = 0; r < g.R; r++)
+		for (int s = 0; s < g.S; s++)
+		{
+			const int t = r * g.S + s;
+			p.tap_off_h[t] = (unsigned short)(r * g.dil_h);
+			p.tap_off_w[t] = (unsigned short)(s * g.dil_w);
+		}
+	return launch_umma_bn<OP_MN2D, OP_IM2COL>(stream, tmA, tmB, p, bn);
+}
+
+} // namespace sm100

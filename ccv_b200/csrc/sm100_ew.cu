@@ -1,0 +1,1274 @@
+// sm100_ew.cu -- the HBM-bound kernels: elementwise, pooling, batch norm, softmax, losses, SGD, dtype / layout moves.
+// All are coalesced, 128-bit vectorised where the shape allows, grid-stride with the grid sized as a multiple of the
+// SM count; reductions use warp shuffles and one atomic per block.  Semantics follow CCV_NNC_BACKEND_CPU_REF
+// (file:line cited per kernel, relative to /root/reference/lib/nnc/cmd).
+#include "sm100_ew.h"
+#include "sm100_contract.h"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <float.h>
+
+namespace sm100 {
+
+static int g_sms = 0;
+static int sms()
+{
+	if (!g_sms)
+	{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+		if (g_sms <= 0)
+			g_sms = 148;
+	}
+	return g_sms;
+}
+
+static int grid_for(size_t work_items, int threads, int max_waves = 8)
+{
+	size_t blocks = (work_items + threads - 1) / threads;
+	const size_t cap = (size_t)sms() * max_waves;
+	if (blocks > cap)
+		blocks = cap;
+	if (blocks < 1)
+		blocks = 1;
+	return (int)blocks;
+}
+
+static int check(const char* what)
+{
+	count_launch();
+	const cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error(what, e);
+		return -1;
+	}
+	return 0;
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xffffffff, v, o);
+	return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v = fmaxf(v, __shfl_xor_sync(0xffffffff, v, o));
+	return v;
+}
+// block-wide reductions for blockDim.x <= 1024 (result valid in every thread)
+__device__ __forceinline__ float block_sum(float v, float* sh)
+{
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	v = warp_sum(v);
+	__syncthreads();
+	if (lane == 0)
+		sh[w] = v;
+	__syncthreads();
+	v = lane < nw ? sh[lane] : 0.f;
+	return warp_sum(v);
+}
+__device__ __forceinline__ float block_max(float v, float* sh)
+{
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	v = warp_max(v);
+	__syncthreads();
+	if (lane == 0)
+		sh[w] = v;
+	__syncthreads();
+	v = lane < nw ? sh[lane] : -FLT_MAX;
+	return warp_max(v);
+}
+
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+// =============================================================================================== set / sum / axpby
+__global__ void set_f32_kernel(float* __restrict__ p, const size_t n, const float v)
+{
+	const size_t n4 = n >> 2;
+	const float4 v4 = make_float4(v, v, v, v);
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+		reinterpret_cast<float4*>(p)[i] = v4;
+	for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		p[i] = v;
+}
+__global__ void set_f32_scalar_kernel(float* __restrict__ p, const size_t n, const float v)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		p[i] = v;
+}
+// util/ccv_nnc_util_cpu_ref.c:596-640 (SET)
+int ew_set_f32(cudaStream_t s, float* p, size_t n, float v)
+{
+	if (n == 0)
+		return 0;
+	if (aligned16(p))
+		set_f32_kernel<<<grid_for((n >> 2) + 1, 256), 256, 0, s>>>(p, n, v);
+	else
+		set_f32_scalar_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, v);
+	return check("set_f32");
+}
+__global__ void set_u16_kernel(uint16_t* __restrict__ p, const size_t n, const uint16_t v)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		p[i] = v;
+}
+int ew_set_u16(cudaStream_t s, uint16_t* p, size_t n, uint16_t v)
+{
+	if (n == 0)
+		return 0;
+	set_u16_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, v);
+	return check("set_u16");
+}
+
+struct SumArgs {
+	const float* in[8];
+	int k;
+};
+template <int VEC>
+__global__ void sum_kernel(const SumArgs a, float* __restrict__ out, const size_t n, const int accumulate)
+{
+	if (VEC == 4)
+	{
+		const size_t n4 = n >> 2;
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+		{
+			float4 acc = accumulate ? reinterpret_cast<const float4*>(out)[i] : make_float4(0, 0, 0, 0);
+#pragma unroll 8
+			for (int j = 0; j < a.k; j++)
+			{
+				const float4 v = reinterpret_cast<const float4*>(a.in[j])[i];
+				acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+			}
+			reinterpret_cast<float4*>(out)[i] = acc;
+		}
+		for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		{
+			float acc = accumulate ? out[i] : 0.f;
+			for (int j = 0; j < a.k; j++)
+				acc += a.in[j][i];
+			out[i] = acc;
+		}
+	} else {
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		{
+			float acc = accumulate ? out[i] : 0.f;
+			for (int j = 0; j < a.k; j++)
+				acc += a.in[j][i];
+			out[i] = acc;
+		}
+	}
+}
+// ew/ccv_nnc_ew_cpu_ref.c:15-110 (EWSUM): c = a0 + a1 + ...; evaluated left to right like the reference
+int ew_sum_f32(cudaStream_t s, const float* const* inputs, int k, float* out, size_t n)
+{
+	if (n == 0 || k <= 0)
+		return 0;
+	int done = 0;
+	while (done < k)
+	{
+		SumArgs a;
+		a.k = (k - done) > 8 ? 8 : (k - done);
+		bool vec = aligned16(out);
+		for (int j = 0; j < a.k; j++)
+		{
+			a.in[j] = inputs[done + j];
+			vec = vec && aligned16(a.in[j]);
+		}
+		if (vec)
+			sum_kernel<4><<<grid_for((n >> 2) + 1, 256), 256, 0, s>>>(a, out, n, done > 0);
+		else
+			sum_kernel<1><<<grid_for(n, 256), 256, 0, s>>>(a, out, n, done > 0);
+		if (check("ew_sum"))
+			return -1;
+		done += a.k;
+	}
+	return 0;
+}
+
+__global__ void axpby_kernel(const float p, const float* __restrict__ a, const float q, const float* __restrict__ b, float* __restrict__ c, const size_t n, const int vec)
+{
+	if (vec)
+	{
+		const size_t n4 = n >> 2;
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const float4 x = reinterpret_cast<const float4*>(a)[i];
+			float4 r = make_float4(p * x.x, p * x.y, p * x.z, p * x.w);
+			if (b)
+			{
+				const float4 y = reinterpret_cast<const float4*>(b)[i];
+				r.x += q * y.x, r.y += q * y.y, r.z += q * y.z, r.w += q * y.w;
+			}
+			reinterpret_cast<float4*>(c)[i] = r;
+		}
+		for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+			c[i] = b ? p * a[i] + q * b[i] : p * a[i];
+	} else
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+			c[i] = b ? p * a[i] + q * b[i] : p * a[i];
+}
+// blas/ccv_nnc_add_cpu_ref.c (ADD: c = p * a + q * b), blas/ccv_nnc_mul_cpu_ref.c (SCALAR_MUL: c = p * a)
+int ew_axpby_f32(cudaStream_t s, float p, const float* a, float q, const float* b, float* c, size_t n)
+{
+	if (n == 0)
+		return 0;
+	const int vec = aligned16(a) && aligned16(c) && (!b || aligned16(b));
+	axpby_kernel<<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(p, a, q, b, c, n, vec);
+	return check("ew_axpby");
+}
+
+struct Bcast4 {
+	int dim[4];
+	int as[4], bs[4], cs[4];
+};
+template <int OP>
+__global__ void bcast_kernel(const float p, const float* __restrict__ a, const float q, const float* __restrict__ b, float* __restrict__ c, const Bcast4 d, const size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	{
+		size_t r = i;
+		const int i3 = r % d.dim[3];
+		r /= d.dim[3];
+		const int i2 = r % d.dim[2];
+		r /= d.dim[2];
+		const int i1 = r % d.dim[1];
+		const int i0 = (int)(r / d.dim[1]);
+		const float av = a[(size_t)i0 * d.as[0] + (size_t)i1 * d.as[1] + (size_t)i2 * d.as[2] + (size_t)i3 * d.as[3]];
+		const size_t co = (size_t)i0 * d.cs[0] + (size_t)i1 * d.cs[1] + (size_t)i2 * d.cs[2] + (size_t)i3 * d.cs[3];
+		if (OP == 0)
+			c[co] = b ? p * av + q * b[(size_t)i0 * d.bs[0] + (size_t)i1 * d.bs[1] + (size_t)i2 * d.bs[2] + (size_t)i3 * d.bs[3]] : p * av;
+		else
+			c[co] = p * av * b[(size_t)i0 * d.bs[0] + (size_t)i1 * d.bs[1] + (size_t)i2 * d.bs[2] + (size_t)i3 * d.bs[3]];
+	}
+}
+static Bcast4 make_bcast(const int* as, const int* bs, const int* cs, const int* dim)
+{
+	Bcast4 d;
+	for (int i = 0; i < 4; i++)
+		d.dim[i] = dim[i] > 0 ? dim[i] : 1, d.as[i] = as[i], d.bs[i] = bs ? bs[i] : 0, d.cs[i] = cs[i];
+	return d;
+}
+int ew_axpby_bcast_f32(cudaStream_t s, float p, const float* a, const int* astride, float q, const float* b, const int* bstride, float* c, const int* cstride, const int* dim)
+{
+	const Bcast4 d = make_bcast(astride, bstride, cstride, dim);
+	const size_t n = (size_t)d.dim[0] * d.dim[1] * d.dim[2] * d.dim[3];
+	if (n == 0)
+		return 0;
+	bcast_kernel<0><<<grid_for(n, 256), 256, 0, s>>>(p, a, q, b, c, d, n);
+	return check("ew_axpby_bcast");
+}
+int ew_mul_bcast_f32(cudaStream_t s, float p, const float* a, const int* astride, const float* b, const int* bstride, float* c, const int* cstride, const int* dim)
+{
+	const Bcast4 d = make_bcast(astride, bstride, cstride, dim);
+	const size_t n = (size_t)d.dim[0] * d.dim[1] * d.dim[2] * d.dim[3];
+	if (n == 0)
+		return 0;
+	bcast_kernel<1><<<grid_for(n, 256), 256, 0, s>>>(p, a, 0.f, b, c, d, n);
+	return check("ew_mul_bcast");
+}
+
+// =============================================================================================== relu
+__global__ void relu_fwd_kernel(const float* __restrict__ a, float* __restrict__ b, const size_t n, const int vec)
+{
+	if (vec)
+	{
+		const size_t n4 = n >> 2;
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const float4 x = reinterpret_cast<const float4*>(a)[i];
+			reinterpret_cast<float4*>(b)[i] = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
+		}
+		for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+			b[i] = fmaxf(a[i], 0.f);
+	} else
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+			b[i] = fmaxf(a[i], 0.f);
+}
+// relu/ccv_nnc_relu_cpu_ref.c:13-31
+int ew_relu_fwd_f32(cudaStream_t s, const float* a, float* b, size_t n)
+{
+	if (n == 0)
+		return 0;
+	const int vec = aligned16(a) && aligned16(b);
+	relu_fwd_kernel<<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, n, vec);
+	return check("relu_fwd");
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ h, const size_t n, const int vec)
+{
+	if (vec)
+	{
+		const size_t n4 = n >> 2;
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const float4 x = reinterpret_cast<const float4*>(b)[i];
+			const float4 y = reinterpret_cast<const float4*>(g)[i];
+			reinterpret_cast<float4*>(h)[i] = make_float4(x.x > 0 ? y.x : 0.f, x.y > 0 ? y.y : 0.f, x.z > 0 ? y.z : 0.f, x.w > 0 ? y.w : 0.f);
+		}
+		for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+			h[i] = b[i] > 0 ? g[i] : 0.f;
+	} else
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+			h[i] = b[i] > 0 ? g[i] : 0.f;
+}
+// relu/ccv_nnc_relu_cpu_ref.c:33-55: the mask is the forward OUTPUT b > 0
+int ew_relu_bwd_f32(cudaStream_t s, const float* g, const float* b, float* h, size_t n)
+{
+	if (n == 0)
+		return 0;
+	const int vec = aligned16(g) && aligned16(b) && aligned16(h);
+	relu_bwd_kernel<<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(g, b, h, n, vec);
+	return check("relu_bwd");
+}
+
+// =============================================================================================== column sums
+// Each block owns a slab of rows; threads are laid out (column, row-lane); per-column partials are combined across
+// the block in shared memory and added to the output with one atomic per (block, column).
+__global__ void colsum_kernel(const float* __restrict__ g, const size_t rows, const int cols, const long long ld, float* __restrict__ out, const int cpb)
+{
+	extern __shared__ float sh[];
+	const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb, rpi = blockDim.x / cpb;
+	const int col = blockIdx.x * cpb + tx;
+	float acc = 0.f;
+	if (ty < rpi && col < cols)
+		for (size_t r = (size_t)blockIdx.y * rpi + ty; r < rows; r += (size_t)gridDim.y * rpi)
+			acc += g[r * ld + col];
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	if (ty == 0 && col < cols)
+	{
+		for (int j = 1; j < rpi; j++)
+			acc += sh[j * cpb + tx];
+		atomicAdd(out + col, acc);
+	}
+}
+int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long ld, float* out, int accumulate)
+{
+	if (cols <= 0)
+		return 0;
+	if (!accumulate)
+	{
+		const cudaError_t e = cudaMemsetAsync(out, 0, (size_t)cols * 4, s);
+		if (e != cudaSuccess)
+		{
+			set_last_error("memset(colsum)", e);
+			return -1;
+		}
+	}
+	if (rows == 0)
+		return 0;
+	const int cpb = cols >= 256 ? 256 : (cols >= 128 ? 128 : (cols >= 64 ? 64 : 32));
+	const int rpi = 256 / cpb;
+	const int gx = (cols + cpb - 1) / cpb;
+	size_t gy = (rows + rpi * 8 - 1) / ((size_t)rpi * 8);
+	const size_t cap = (size_t)(sms() * 4 + gx - 1) / gx;
+	if (gy > cap)
+		gy = cap;
+	if (gy < 1)
+		gy = 1;
+	colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 256 * sizeof(float), s>>>(g, rows, cols, ld, out, cpb);
+	return check("colsum");
+}
+
+// generic <= 4-d reduction to a broadcast shape: one thread block per output element (small outputs only)
+struct Reduce4 {
+	int adim[4], astride[4], rdim[4];
+};
+__global__ void reduce_sum_kernel(const float* __restrict__ a, float* __restrict__ out, const Reduce4 d, const float scale, const int accumulate)
+{
+	__shared__ float sh[32];
+	// output index -> (o0, o1, o2, o3)
+	int o = blockIdx.x;
+	int oi[4];
+	for (int k = 3; k >= 0; k--)
+		oi[k] = o % d.rdim[k], o /= d.rdim[k];
+	int ext[4];
+	size_t total = 1;
+	for (int k = 0; k < 4; k++)
+		ext[k] = d.rdim[k] == 1 ? d.adim[k] : 1, total *= ext[k];
+	float acc = 0.f;
+	for (size_t i = threadIdx.x; i < total; i += blockDim.x)
+	{
+		size_t r = i;
+		size_t off = 0;
+		for (int k = 3; k >= 0; k--)
+		{
+			const int ik = (int)(r % ext[k]);
+			r /= ext[k];
+			off += (size_t)(d.rdim[k] == 1 ? ik : oi[k]) * d.astride[k];
+		}
+		acc += a[off];
+	}
+	acc = block_sum(acc, sh);
+	if (threadIdx.x == 0)
+		out[blockIdx.x] = accumulate ? out[blockIdx.x] + acc * scale : acc * scale;
+}
+int reduce_sum_bcast_f32(cudaStream_t s, const float* a, const int* adim, const int* astride, float* out, const int* rdim, float scale, int accumulate)
+{
+	Reduce4 d;
+	size_t outs = 1;
+	for (int i = 0; i < 4; i++)
+		d.adim[i] = adim[i] > 0 ? adim[i] : 1, d.astride[i] = astride[i], d.rdim[i] = rdim[i] > 0 ? rdim[i] : 1, outs *= d.rdim[i];
+	if (outs > 0x7fffffff)
+		return 1;
+	reduce_sum_kernel<<<(unsigned)outs, 256, 0, s>>>(a, out, d, scale, accumulate);
+	return check("reduce_sum");
+}
+
+// =============================================================================================== pooling (NHWC)
+// pool/ccv_nnc_max_pool_cpu_ref.c:13-59, pool/ccv_nnc_avg_pool_cpu_ref.c:13-58: the window is clipped to the input
+// (SET_BORDER_OFFSET_SIZE_FOR, ccv_nnc_internal.h:209-213); the average divides by the clipped window size.
+template <int VEC, int IS_MAX>
+__global__ void pool_fwd_kernel(const PoolGeom g, const float* __restrict__ a, float* __restrict__ b)
+{
+	const int CV = g.C / VEC;
+	const size_t total = (size_t)g.N * g.P * g.Q * CV;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const int c = (int)(i % CV) * VEC;
+		size_t r = i / CV;
+		const int q = (int)(r % g.Q);
+		r /= g.Q;
+		const int p = (int)(r % g.P);
+		const int n = (int)(r / g.P);
+		const int h0 = max(p * g.stride_h - g.pad_h, 0), h1 = min(p * g.stride_h - g.pad_h + g.R, g.H);
+		const int w0 = max(q * g.stride_w - g.pad_w, 0), w1 = min(q * g.stride_w - g.pad_w + g.S, g.W);
+		float v[VEC];
+#pragma unroll
+		for (int k = 0; k < VEC; k++)
+			v[k] = IS_MAX ? -FLT_MAX : 0.f;
+		for (int h = h0; h < h1; h++)
+			for (int w = w0; w < w1; w++)
+			{
+				const float* ap = a + n * g.an + h * g.ah + w * g.aw + c;
+				float x[VEC];
+				if (VEC == 4)
+				{
+					const float4 t = *reinterpret_cast<const float4*>(ap);
+					x[0] = t.x, x[1 % VEC] = t.y, x[2 % VEC] = t.z, x[3 % VEC] = t.w;
+				} else
+					x[0] = *ap;
+#pragma unroll
+				for (int k = 0; k < VEC; k++)
+					v[k] = IS_MAX ? fmaxf(v[k], x[k]) : v[k] + x[k];
+			}
+		if (!IS_MAX)
+		{
+			const float inv = (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+			for (int k = 0; k < VEC; k++)
+				v[k] = v[k] / inv;
+		}
+		float* bp = b + n * g.bn + p * g.bh + q * g.bw + c;
+		if (VEC == 4)
+			*reinterpret_cast<float4*>(bp) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+		else
+			bp[0] = v[0];
+	}
+}
+static bool pool_vec_ok(const PoolGeom& g, const void* a, const void* b)
+{
+	return g.C % 4 == 0 && aligned16(a) && aligned16(b) && g.aw % 4 == 0 && g.ah % 4 == 0 && g.an % 4 == 0 && g.bw % 4 == 0 && g.bh % 4 == 0 && g.bn % 4 == 0;
+}
+int pool_max_fwd_f32(cudaStream_t s, const PoolGeom& g, const float* a, float* b)
+{
+	const size_t total = (size_t)g.N * g.P * g.Q * g.C;
+	if (total == 0)
+		return 0;
+	if (pool_vec_ok(g, a, b))
+		pool_fwd_kernel<4, 1><<<grid_for(total / 4, 256), 256, 0, s>>>(g, a, b);
+	else
+		pool_fwd_kernel<1, 1><<<grid_for(total, 256), 256, 0, s>>>(g, a, b);
+	return check("pool_max_fwd");
+}
+int pool_avg_fwd_f32(cudaStream_t s, const PoolGeom& g, const float* a, float* b)
+{
+	const size_t total = (size_t)g.N * g.P * g.Q * g.C;
+	if (total == 0)
+		return 0;
+	if (pool_vec_ok(g, a, b))
+		pool_fwd_kernel<4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(g, a, b);
+	else
+		pool_fwd_kernel<1, 0><<<grid_for(total, 256), 256, 0, s>>>(g, a, b);
+	return check("pool_avg_fwd");
+}
+// Backward as a gather over input positions (no atomics): input (h, w) collects from every window that covers it.
+// max: pool/ccv_nnc_max_pool_cpu_ref.c:61-139 -- every position equal to the window max receives the gradient.
+// avg: pool/ccv_nnc_avg_pool_cpu_ref.c:60-110 -- gradient / clipped window size.
+template <int VEC, int IS_MAX>
+__global__ void pool_bwd_kernel(const PoolGeom g, const float* __restrict__ gb, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ ga)
+{
+	const int CV = g.C / VEC;
+	const size_t total = (size_t)g.N * g.H * g.W * CV;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const int c = (int)(i % CV) * VEC;
+		size_t r = i / CV;
+		const int w = (int)(r % g.W);
+		r /= g.W;
+		const int h = (int)(r % g.H);
+		const int n = (int)(r / g.H);
+		// windows p with p * stride - pad <= h < p * stride - pad + R
+		const int p_lo = max((h + g.pad_h - g.R + g.stride_h) / g.stride_h, 0), p_hi = min((h + g.pad_h) / g.stride_h, g.P - 1);
+		const int q_lo = max((w + g.pad_w - g.S + g.stride_w) / g.stride_w, 0), q_hi = min((w + g.pad_w) / g.stride_w, g.Q - 1);
+		float x[VEC], acc[VEC];
+#pragma unroll
+		for (int k = 0; k < VEC; k++)
+			acc[k] = 0.f, x[k] = 0.f;
+		if (IS_MAX)
+		{
+			const float* ap = a + n * g.an + h * g.ah + w * g.aw + c;
+			if (VEC == 4)
+			{
+				const float4 t = *reinterpret_cast<const float4*>(ap);
+				x[0] = t.x, x[1 % VEC] = t.y, x[2 % VEC] = t.z, x[3 % VEC] = t.w;
+			} else
+				x[0] = *ap;
+		}
+		for (int p = p_lo; p <= p_hi; p++)
+		{
+			if (h + g.pad_h - g.R >= p * g.stride_h) // (h + pad - R + stride) / stride rounds toward zero for negatives
+				continue;
+			const int h0 = max(p * g.stride_h - g.pad_h, 0), h1 = min(p * g.stride_h - g.pad_h + g.R, g.H);
+			for (int q = q_lo; q <= q_hi; q++)
+			{
+				if (w + g.pad_w - g.S >= q * g.stride_w)
+					continue;
+				const size_t o = n * g.bn + p * g.bh + q * g.bw + c;
+				float gv[VEC], bv[VEC];
+				if (VEC == 4)
+				{
+					const float4 t = *reinterpret_cast<const float4*>(gb + o);
+					gv[0] = t.x, gv[1 % VEC] = t.y, gv[2 % VEC] = t.z, gv[3 % VEC] = t.w;
+					if (IS_MAX)
+					{
+						const float4 u = *reinterpret_cast<const float4*>(b + o);
+						bv[0] = u.x, bv[1 % VEC] = u.y, bv[2 % VEC] = u.z, bv[3 % VEC] = u.w;
+					}
+				} else {
+					gv[0] = gb[o];
+					if (IS_MAX)
+						bv[0] = b[o];
+				}
+				if (IS_MAX)
+				{
+#pragma unroll
+					for (int k = 0; k < VEC; k++)
+						if (x[k] == bv[k])
+							acc[k] += gv[k];
+				} else {
+					const int w0 = max(q * g.stride_w - g.pad_w, 0), w1 = min(q * g.stride_w - g.pad_w + g.S, g.W);
+					const float inv = (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+					for (int k = 0; k < VEC; k++)
+						acc[k] += gv[k] / inv;
+				}
+			}
+		}
+		float* hp = ga + n * g.an + h * g.ah + w * g.aw + c;
+		if (VEC == 4)
+			*reinterpret_cast<float4*>(hp) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+		else
+			hp[0] = acc[0];
+	}
+}
+int pool_max_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, const float* a, const float* b, float* grad_a)
+{
+	const size_t total = (size_t)g.N * g.H * g.W * g.C;
+	if (total == 0)
+		return 0;
+	if (pool_vec_ok(g, a, b) && aligned16(grad_b) && aligned16(grad_a))
+		pool_bwd_kernel<4, 1><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
+	else
+		pool_bwd_kernel<1, 1><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
+	return check("pool_max_bwd");
+}
+int pool_avg_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, float* grad_a)
+{
+	const size_t total = (size_t)g.N * g.H * g.W * g.C;
+	if (total == 0)
+		return 0;
+	if (pool_vec_ok(g, grad_a, grad_b))
+		pool_bwd_kernel<4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, 0, 0, grad_a);
+	else
+		pool_bwd_kernel<1, 0><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, 0, 0, grad_a);
+	return check("pool_avg_bwd");
+}
+
+// =============================================================================================== batch norm
+// norm/ccv_nnc_batch_norm_cpu_ref.c:16-250 (forward), :312-470 (backward).  Statistics are biased (divide by count);
+// running = momentum * running + (1 - momentum) * batch.  Layout [outer, C, inner].
+//
+// Pass 1 accumulates, per channel, sum(x - k) and sum((x - k)^2) with the per-channel shift k = x[0, c] (keeps the
+// one-pass variance formula well conditioned); block partials go to a double-precision workspace with atomics.
+// workspace (doubles): [0, C) first moment, [C, 2C) second moment.
+size_t bn_workspace_bytes(int C) { return (size_t)C * 2 * sizeof(double); }
+
+// inner == 1 (NHWC): threads (column-vector, row-lane); VEC = 4 uses 128-bit loads along C
+template <int VEC, int MODE> // MODE 0: stats of x. MODE 1: backward sums (g, g * xhat)
+__global__ void bn_reduce_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ inv_std, const size_t rows, const int C, double* __restrict__ ws, const int cpb)
+{
+	extern __shared__ float sh[]; // [2][blockDim.x][VEC]
+	const int CV = C / VEC;
+	const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb, rpi = blockDim.x / cpb;
+	const int cv = blockIdx.x * cpb + tx;
+	float s1[VEC], s2[VEC], k[VEC], k2[VEC];
+#pragma unroll
+	for (int j = 0; j < VEC; j++)
+		s1[j] = s2[j] = 0.f;
+	const bool active = ty < rpi && cv < CV;
+	if (active)
+	{
+#pragma unroll
+		for (int j = 0; j < VEC; j++)
+		{
+			if (MODE == 0)
+				k[j] = x[cv * VEC + j], k2[j] = 0.f;
+			else
+				k[j] = mean[cv * VEC + j], k2[j] = inv_std[cv * VEC + j];
+		}
+		for (size_t r = (size_t)blockIdx.y * rpi + ty; r < rows; r += (size_t)gridDim.y * rpi)
+		{
+			float xv[VEC], gv[VEC];
+			if (VEC == 4)
+			{
+				const float4 t = reinterpret_cast<const float4*>(x + r * C)[cv];
+				xv[0] = t.x, xv[1 % VEC] = t.y, xv[2 % VEC] = t.z, xv[3 % VEC] = t.w;
+				if (MODE == 1)
+				{
+					const float4 u = reinterpret_cast<const float4*>(g + r * C)[cv];
+					gv[0] = u.x, gv[1 % VEC] = u.y, gv[2 % VEC] = u.z, gv[3 % VEC] = u.w;
+				}
+			} else {
+				xv[0] = x[r * C + cv];
+				if (MODE == 1)
+					gv[0] = g[r * C + cv];
+			}
+#pragma unroll
+			for (int j = 0; j < VEC; j++)
+			{
+				if (MODE == 0)
+				{
+					const float d = xv[j] - k[j];
+					s1[j] += d, s2[j] += d * d;
+				} else {
+					s1[j] += gv[j], s2[j] += gv[j] * (xv[j] - k[j]) * k2[j];
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < VEC; j++)
+		sh[threadIdx.x * VEC + j] = s1[j], sh[(blockDim.x + threadIdx.x) * VEC + j] = s2[j];
+	__syncthreads();
+	if (ty == 0 && cv < CV)
+	{
+		for (int t = 1; t < rpi; t++)
+#pragma unroll
+			for (int j = 0; j < VEC; j++)
+				s1[j] += sh[(t * cpb + tx) * VEC + j], s2[j] += sh[(blockDim.x + t * cpb + tx) * VEC + j];
+#pragma unroll
+		for (int j = 0; j < VEC; j++)
+		{
+			atomicAdd(ws + cv * VEC + j, (double)s1[j]);
+			atomicAdd(ws + C + cv * VEC + j, (double)s2[j]);
+		}
+	}
+}
+// inner > 1 (NCHW): one block per channel
+template <int MODE>
+__global__ void bn_reduce_generic_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ inv_std, const size_t outer, const int C, const size_t inner, double* __restrict__ ws)
+{
+	__shared__ float sh[32];
+	const int c = blockIdx.x;
+	const float k = MODE == 0 ? x[(size_t)c * inner] : mean[c];
+	const float k2 = MODE == 0 ? 0.f : inv_std[c];
+	float s1 = 0.f, s2 = 0.f;
+	const size_t total = outer * inner;
+	for (size_t i = threadIdx.x; i < total; i += blockDim.x)
+	{
+		const size_t o = i / inner, in = i - o * inner;
+		const size_t idx = (o * C + c) * inner + in;
+		if (MODE == 0)
+		{
+			const float d = x[idx] - k;
+			s1 += d, s2 += d * d;
+		} else {
+			const float gv = g[idx];
+			s1 += gv, s2 += gv * (x[idx] - k) * k2;
+		}
+	}
+	s1 = block_sum(s1, sh);
+	s2 = block_sum(s2, sh);
+	if (threadIdx.x == 0)
+		ws[c] = (double)s1, ws[C + c] = (double)s2;
+}
+__global__ void bn_finalize_kernel(const float* __restrict__ x, const size_t shift_stride, const double* __restrict__ ws, const int C, const double count, const float epsilon, const float momentum, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C)
+		return;
+	const double k = (double)x[(size_t)c * shift_stride];
+	const double s1 = ws[c], s2 = ws[C + c];
+	const double mean = k + s1 / count;
+	double var = (s2 - s1 * s1 / count) / count;
+	if (var < 0)
+		var = 0;
+	const float meanf = (float)mean, varf = (float)var;
+	saved_mean[c] = meanf;
+	saved_inv_std[c] = 1.f / sqrtf(varf + epsilon);
+	running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * meanf;
+	running_var[c] = momentum * running_var[c] + (1.f - momentum) * varf;
+}
+// y = (x - mean) * inv_std * scale + bias, evaluated as x * a + b with a = scale * inv_std, b = bias - mean * a
+// (the non-ZERO_MEMORY_ALLOC path of the reference, batch_norm_cpu_ref.c:176-249).  IS_TEST uses 1 / (sqrt(var) + eps).
+template <int VEC, int IS_TEST>
+__global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ var_or_inv_std, const size_t total_vec, const int C, const size_t inner, const float epsilon)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x)
+	{
+		float xv[VEC];
+		int c[VEC];
+		if (VEC == 4)
+		{
+			const float4 t = reinterpret_cast<const float4*>(x)[i];
+			xv[0] = t.x, xv[1 % VEC] = t.y, xv[2 % VEC] = t.z, xv[3 % VEC] = t.w;
+			const int c0 = (int)((i * 4) % C); // inner == 1 on the vector path
+#pragma unroll
+			for (int j = 0; j < VEC; j++)
+				c[j] = c0 + j;
+		} else {
+			xv[0] = x[i];
+			c[0] = (int)((i / inner) % C);
+		}
+		float o[VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++)
+		{
+			const float istd = IS_TEST ? 1.f / (sqrtf(var_or_inv_std[c[j]]) + epsilon) : var_or_inv_std[c[j]];
+			const float a = scale[c[j]] * istd;
+			const float b = bias[c[j]] - mean[c[j]] * a;
+			o[j] = xv[j] * a + b;
+		}
+		if (VEC == 4)
+			reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+		else
+			y[i] = o[0];
+	}
+}
+static void bn_reduce_config(size_t rows, int CV, int& cpb, dim3& grid)
+{
+	cpb = CV >= 256 ? 256 : CV;
+	// largest divisor-friendly column count: threads beyond rpi * cpb idle
+	const int rpi = 256 / cpb;
+	const int gx = (CV + cpb - 1) / cpb;
+	size_t gy = (rows + (size_t)rpi * 16 - 1) / ((size_t)rpi * 16);
+	const size_t cap = (size_t)(sms() * 4 + gx - 1) / gx;
+	if (gy > cap)
+		gy = cap;
+	if (gy < 1)
+		gy = 1;
+	grid = dim3(gx, (unsigned)gy);
+}
+int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace)
+{
+	double* ws = (double*)workspace;
+	const size_t total = outer * C * inner;
+	if (total == 0)
+		return 0;
+	if (inner == 1)
+	{
+		cudaError_t e = cudaMemsetAsync(ws, 0, bn_workspace_bytes(C), s);
+		if (e != cudaSuccess)
+		{
+			set_last_error("memset(bn)", e);
+			return -1;
+		}
+		const bool vec = C % 4 == 0 && aligned16(x);
+		int cpb;
+		dim3 grid;
+		if (vec)
+		{
+			bn_reduce_config(outer, C / 4, cpb, grid);
+			bn_reduce_nhwc_kernel<4, 0><<<grid, 256, 2 * 256 * 4 * sizeof(float), s>>>(x, 0, 0, 0, outer, C, ws, cpb);
+		} else {
+			bn_reduce_config(outer, C, cpb, grid);
+			bn_reduce_nhwc_kernel<1, 0><<<grid, 256, 2 * 256 * sizeof(float), s>>>(x, 0, 0, 0, outer, C, ws, cpb);
+		}
+		if (check("bn_reduce"))
+			return -1;
+	} else {
+		bn_reduce_generic_kernel<0><<<C, 512, 0, s>>>(x, 0, 0, 0, outer, C, inner, ws);
+		if (check("bn_reduce_generic"))
+			return -1;
+	}
+	bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, inner, ws, C, (double)outer * (double)inner, epsilon, momentum, running_mean, running_var, saved_mean, saved_inv_std);
+	if (check("bn_finalize"))
+		return -1;
+	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(y))
+		bn_apply_kernel<4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(x, y, scale, bias, saved_mean, saved_inv_std, total / 4, C, 1, epsilon);
+	else
+		bn_apply_kernel<1, 0><<<grid_for(total, 256), 256, 0, s>>>(x, y, scale, bias, saved_mean, saved_inv_std, total, C, inner, epsilon);
+	return check("bn_apply");
+}
+int bn_fwd_test_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, const float* mean, const float* var, size_t outer, int C, size_t inner, float epsilon)
+{
+	const size_t total = outer * C * inner;
+	if (total == 0)
+		return 0;
+	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(y))
+		bn_apply_kernel<4, 1><<<grid_for(total / 4, 256), 256, 0, s>>>(x, y, scale, bias, mean, var, total / 4, C, 1, epsilon);
+	else
+		bn_apply_kernel<1, 1><<<grid_for(total, 256), 256, 0, s>>>(x, y, scale, bias, mean, var, total, C, inner, epsilon);
+	return check("bn_apply_test");
+}
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, const int C, float* __restrict__ dscale, float* __restrict__ dbias)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C)
+		return;
+	if (dbias)
+		dbias[c] = (float)ws[c];
+	if (dscale)
+		dscale[c] = (float)ws[C + c];
+}
+// h = scale * inv_std / count * (count * g - dbias - xhat * dscale)   (batch_norm_cpu_ref.c:430-466)
+template <int VEC>
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ mean, const float* __restrict__ inv_std, const double* __restrict__ ws, float* __restrict__ dx, const size_t total_vec, const int C, const size_t inner, const float count)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x)
+	{
+		float xv[VEC], gv[VEC];
+		int c[VEC];
+		if (VEC == 4)
+		{
+			const float4 t = reinterpret_cast<const float4*>(x)[i];
+			const float4 u = reinterpret_cast<const float4*>(g)[i];
+			xv[0] = t.x, xv[1 % VEC] = t.y, xv[2 % VEC] = t.z, xv[3 % VEC] = t.w;
+			gv[0] = u.x, gv[1 % VEC] = u.y, gv[2 % VEC] = u.z, gv[3 % VEC] = u.w;
+			const int c0 = (int)((i * 4) % C);
+#pragma unroll
+			for (int j = 0; j < VEC; j++)
+				c[j] = c0 + j;
+		} else {
+			xv[0] = x[i], gv[0] = g[i];
+			c[0] = (int)((i / inner) % C);
+		}
+		float o[VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++)
+		{
+			const float istd = inv_std[c[j]];
+			const float xhat = (xv[j] - mean[c[j]]) * istd;
+			const float sisb = scale[c[j]] * istd / count;
+			o[j] = sisb * (count * gv[j] - (float)ws[c[j]] - xhat * (float)ws[C + c[j]]);
+		}
+		if (VEC == 4)
+			reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+		else
+			dx[i] = o[0];
+	}
+}
+int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* saved_mean, const float* saved_inv_std, float* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace)
+{
+	double* ws = (double*)workspace;
+	const size_t total = outer * C * inner;
+	if (total == 0)
+		return 0;
+	if (inner == 1)
+	{
+		cudaError_t e = cudaMemsetAsync(ws, 0, bn_workspace_bytes(C), s);
+		if (e != cudaSuccess)
+		{
+			set_last_error("memset(bn_bwd)", e);
+			return -1;
+		}
+		const bool vec = C % 4 == 0 && aligned16(x) && aligned16(g);
+		int cpb;
+		dim3 grid;
+		if (vec)
+		{
+			bn_reduce_config(outer, C / 4, cpb, grid);
+			bn_reduce_nhwc_kernel<4, 1><<<grid, 256, 2 * 256 * 4 * sizeof(float), s>>>(x, g, saved_mean, saved_inv_std, outer, C, ws, cpb);
+		} else {
+			bn_reduce_config(outer, C, cpb, grid);
+			bn_reduce_nhwc_kernel<1, 1><<<grid, 256, 2 * 256 * sizeof(float), s>>>(x, g, saved_mean, saved_inv_std, outer, C, ws, cpb);
+		}
+		if (check("bn_bwd_reduce"))
+			return -1;
+	} else {
+		bn_reduce_generic_kernel<1><<<C, 512, 0, s>>>(x, g, saved_mean, saved_inv_std, outer, C, inner, ws);
+		if (check("bn_bwd_reduce_generic"))
+			return -1;
+	}
+	if (dscale || dbias)
+	{
+		bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(ws, C, dscale, dbias);
+		if (check("bn_bwd_finalize"))
+			return -1;
+	}
+	if (!dx)
+		return 0;
+	const float count = (float)((double)outer * (double)inner);
+	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(g) && aligned16(dx))
+		bn_bwd_apply_kernel<4><<<grid_for(total / 4, 256), 256, 0, s>>>(g, x, scale, saved_mean, saved_inv_std, ws, dx, total / 4, C, 1, count);
+	else
+		bn_bwd_apply_kernel<1><<<grid_for(total, 256), 256, 0, s>>>(g, x, scale, saved_mean, saved_inv_std, ws, dx, total, C, inner, count);
+	return check("bn_bwd_apply");
+}
+
+// =============================================================================================== softmax / losses
+// softmax/ccv_nnc_softmax_cpu_ref.c:13-40: per row, b = exp(a - max) / sum; one block per row
+__global__ void softmax_fwd_kernel(const float* __restrict__ a, float* __restrict__ b, const int count)
+{
+	__shared__ float sh[32];
+	const float* ap = a + (size_t)blockIdx.x * count;
+	float* bp = b + (size_t)blockIdx.x * count;
+	float m = -FLT_MAX;
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+		m = fmaxf(m, ap[j]);
+	m = block_max(m, sh);
+	float sum = 0.f;
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+	{
+		const float e = expf(ap[j] - m);
+		bp[j] = e;
+		sum += e;
+	}
+	sum = block_sum(sum, sh);
+	const float inv = 1.f / sum;
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+		bp[j] *= inv;
+}
+static int softmax_threads(int count) { return count >= 1024 ? 256 : (count >= 256 ? 128 : (count >= 64 ? 64 : 32)); }
+int softmax_fwd_f32(cudaStream_t s, const float* a, float* b, int batch, int count)
+{
+	if (batch <= 0 || count <= 0)
+		return 0;
+	softmax_fwd_kernel<<<batch, softmax_threads(count), 0, s>>>(a, b, count);
+	return check("softmax_fwd");
+}
+// softmax/ccv_nnc_softmax_cpu_ref.c:42-75: h = (g - sum(g * b)) * b
+__global__ void softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ h, const int count)
+{
+	__shared__ float sh[32];
+	const size_t o = (size_t)blockIdx.x * count;
+	float sum = 0.f;
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+		sum += g[o + j] * b[o + j];
+	sum = block_sum(sum, sh);
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+		h[o + j] = (g[o + j] - sum) * b[o + j];
+}
+int softmax_bwd_f32(cudaStream_t s, const float* g, const float* b, float* h, int batch, int count)
+{
+	if (batch <= 0 || count <= 0)
+		return 0;
+	softmax_bwd_kernel<<<batch, softmax_threads(count), 0, s>>>(g, b, h, count);
+	return check("softmax_bwd");
+}
+__device__ __forceinline__ int label_of(const void* label, const int kind, const int i)
+{
+	return kind == 1 ? reinterpret_cast<const int*>(label)[i] : (int)(reinterpret_cast<const float*>(label)[i] + 0.5f);
+}
+// loss/ccv_nnc_categorical_crossentropy_cpu_ref.c:13-105
+__global__ void cce_fwd_kernel(const float* __restrict__ a, const void* __restrict__ label, const int kind, float* __restrict__ c, const int count, const float trim0, const float trim1)
+{
+	__shared__ float sh[32];
+	const int i = blockIdx.x;
+	const float* ap = a + (size_t)i * count;
+	float p = 0.f;
+	if (kind == 2)
+	{
+		const float* bp = reinterpret_cast<const float*>(label) + (size_t)i * count;
+		for (int j = threadIdx.x; j < count; j += blockDim.x)
+			p += -bp[j] * logf(ap[j]);
+	} else {
+		const int l = label_of(label, kind, i);
+		if (trim0 == 0.f && trim1 == 1.f)
+		{
+			if (threadIdx.x == 0)
+				c[i] = -logf(ap[l]);
+			return;
+		}
+		for (int j = threadIdx.x; j < count; j += blockDim.x)
+			p += -(j == l ? trim1 : trim0) * logf(ap[j]);
+	}
+	p = block_sum(p, sh);
+	if (threadIdx.x == 0)
+		c[i] = p;
+}
+int cce_fwd_f32(cudaStream_t s, const float* a, const void* label, int label_kind, float* c, int batch, int count, float trim0, float trim1)
+{
+	if (batch <= 0 || count <= 0)
+		return 0;
+	cce_fwd_kernel<<<batch, softmax_threads(count), 0, s>>>(a, label, label_kind, c, count, trim0, trim1);
+	return check("cce_fwd");
+}
+// loss/ccv_nnc_categorical_crossentropy_cpu_ref.c:107-300: h = -g * t / a (g == NULL means 1)
+__global__ void cce_bwd_kernel(const float* __restrict__ g, const float* __restrict__ a, const void* __restrict__ label, const int kind, float* __restrict__ h, const int count, const float trim0, const float trim1)
+{
+	const int i = blockIdx.x;
+	const float gp = g ? g[i] : 1.f;
+	const float* ap = a + (size_t)i * count;
+	float* hp = h + (size_t)i * count;
+	if (kind == 2)
+	{
+		const float* bp = reinterpret_cast<const float*>(label) + (size_t)i * count;
+		for (int j = threadIdx.x; j < count; j += blockDim.x)
+			hp[j] = -gp * bp[j] / ap[j];
+		return;
+	}
+	const int l = label_of(label, kind, i);
+	if (trim0 == 0.f && trim1 == 1.f)
+	{
+		for (int j = threadIdx.x; j < count; j += blockDim.x)
+			hp[j] = j == l ? -gp / ap[j] : 0.f;
+	} else {
+		for (int j = threadIdx.x; j < count; j += blockDim.x)
+			hp[j] = -gp * (j == l ? trim1 : trim0) / ap[j];
+	}
+}
+int cce_bwd_f32(cudaStream_t s, const float* g, const float* a, const void* label, int label_kind, float* h, int batch, int count, float trim0, float trim1)
+{
+	if (batch <= 0 || count <= 0)
+		return 0;
+	cce_bwd_kernel<<<batch, softmax_threads(count), 0, s>>>(g, a, label, label_kind, h, count, trim0, trim1);
+	return check("cce_bwd");
+}
+// softmax_loss/ccv_nnc_softmax_crossentropy_cpu_ref.c:13-170: d = softmax(a); c = sum_j t_j * (max - a_j).
+// (The reference's "loss" deliberately leaves out log(sum exp): it is assigned before the exponentials, :46,:71,:98.)
+__global__ void softmax_cce_fwd_kernel(const float* __restrict__ a, const void* __restrict__ label, const int kind, float* __restrict__ c, float* __restrict__ d, const int count, const float trim0, const float trim1)
+{
+	__shared__ float sh[32];
+	const int i = blockIdx.x;
+	const float* ap = a + (size_t)i * count;
+	float* dp = d + (size_t)i * count;
+	float m = -FLT_MAX;
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+		m = fmaxf(m, ap[j]);
+	m = block_max(m, sh);
+	float sum = 0.f;
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+	{
+		const float e = expf(ap[j] - m);
+		dp[j] = e;
+		sum += e;
+	}
+	sum = block_sum(sum, sh);
+	const float inv = 1.f / sum;
+	const int l = kind == 2 ? -1 : label_of(label, kind, i);
+	const float* bp = kind == 2 ? reinterpret_cast<const float*>(label) + (size_t)i * count : 0;
+	float p = 0.f;
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+	{
+		dp[j] *= inv;
+		if (c)
+		{
+			const float t = kind == 2 ? bp[j] : (j == l ? trim1 : trim0);
+			if (t != 0.f)
+				p += t * (m - ap[j]);
+		}
+	}
+	if (c)
+	{
+		p = block_sum(p, sh);
+		if (threadIdx.x == 0)
+			c[i] = p;
+	}
+}
+int softmax_cce_fwd_f32(cudaStream_t s, const float* a, const void* label, int label_kind, float* c, float* d, int batch, int count, float trim0, float trim1)
+{
+	if (batch <= 0 || count <= 0)
+		return 0;
+	softmax_cce_fwd_kernel<<<batch, softmax_threads(count), 0, s>>>(a, label, label_kind, c, d, count, trim0, trim1);
+	return check("softmax_cce_fwd");
+}
+// softmax_loss/ccv_nnc_softmax_crossentropy_cpu_ref.c:172-340: h = g * (d - t); g == NULL means 1
+__global__ void softmax_cce_bwd_kernel(const float* __restrict__ g, const void* __restrict__ label, const int kind, const float* __restrict__ d, float* __restrict__ h, const int count, const float trim0, const float trim1)
+{
+	const int i = blockIdx.x;
+	const float gp = g ? g[i] : 1.f;
+	const float* dp = d + (size_t)i * count;
+	float* hp = h + (size_t)i * count;
+	if (kind == 2)
+	{
+		const float* bp = reinterpret_cast<const float*>(label) + (size_t)i * count;
+		for (int j = threadIdx.x; j < count; j += blockDim.x)
+			hp[j] = gp * (dp[j] - bp[j]);
+		return;
+	}
+	const int l = label_of(label, kind, i);
+	for (int j = threadIdx.x; j < count; j += blockDim.x)
+		hp[j] = gp * (dp[j] - (j == l ? trim1 : trim0));
+}
+int softmax_cce_bwd_f32(cudaStream_t s, const float* g, const void* label, int label_kind, const float* d, float* h, int batch, int count, float trim0, float trim1)
+{
+	if (batch <= 0 || count <= 0)
+		return 0;
+	softmax_cce_bwd_kernel<<<batch, softmax_threads(count), 0, s>>>(g, label, label_kind, d, h, count, trim0, trim1);
+	return check("softmax_cce_bwd");
+}
+
+// =============================================================================================== SGD
+// sgd/ccv_nnc_sgd_cpu_ref.c:16-126
+template <int VEC>
+__global__ void sgd_kernel(const float* __restrict__ g, const float* __restrict__ a, const float* __restrict__ m, float* __restrict__ b, float* __restrict__ n, const size_t count, const int nesterov, const float rate, const float scale, const float decay, const float momentum, const float inv_dampening)
+{
+	const size_t cv = VEC == 4 ? count >> 2 : count;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cv; i += (size_t)gridDim.x * blockDim.x)
+	{
+		float gv[VEC], av[VEC], mv[VEC], bv[VEC], nv[VEC];
+		if (VEC == 4)
+		{
+			const float4 t = reinterpret_cast<const float4*>(g)[i], u = reinterpret_cast<const float4*>(a)[i], w = reinterpret_cast<const float4*>(m)[i];
+			gv[0] = t.x, gv[1 % VEC] = t.y, gv[2 % VEC] = t.z, gv[3 % VEC] = t.w;
+			av[0] = u.x, av[1 % VEC] = u.y, av[2 % VEC] = u.z, av[3 % VEC] = u.w;
+			mv[0] = w.x, mv[1 % VEC] = w.y, mv[2 % VEC] = w.z, mv[3 % VEC] = w.w;
+		} else
+			gv[0] = g[i], av[0] = a[i], mv[0] = m[i];
+#pragma unroll
+		for (int j = 0; j < VEC; j++)
+		{
+			if (nesterov)
+			{
+				float grad = scale * gv[j];
+				const float mom = nv[j] = momentum * mv[j] + grad + decay * av[j];
+				grad += momentum * mom;
+				bv[j] = av[j] - rate * grad;
+			} else {
+				const float mom = nv[j] = momentum * mv[j] + inv_dampening * (scale * gv[j] + decay * av[j]);
+				bv[j] = av[j] - rate * mom;
+			}
+		}
+		if (VEC == 4)
+		{
+			reinterpret_cast<float4*>(b)[i] = make_float4(bv[0], bv[1 % VEC], bv[2 % VEC], bv[3 % VEC]);
+			reinterpret_cast<float4*>(n)[i] = make_float4(nv[0], nv[1 % VEC], nv[2 % VEC], nv[3 % VEC]);
+		} else
+			b[i] = bv[0], n[i] = nv[0];
+	}
+}
+int sgd_f32(cudaStream_t s, const float* g, const float* a, const float* m, float* b, float* n, size_t count, int nesterov, float rate, float scale, float decay, float momentum, float dampening)
+{
+	if (count == 0)
+		return 0;
+	const float inv_dampening = 1.f - dampening;
+	if (count % 4 == 0 && aligned16(g) && aligned16(a) && aligned16(m) && aligned16(b) && aligned16(n))
+		sgd_kernel<4><<<grid_for(count / 4, 256), 256, 0, s>>>(g, a, m, b, n, count, nesterov, rate, scale, decay, momentum, inv_dampening);
+	else
+		sgd_kernel<1><<<grid_for(count, 256), 256, 0, s>>>(g, a, m, b, n, count, nesterov, rate, scale, decay, momentum, inv_dampening);
+	return check("sgd");
+}
+
+// =============================================================================================== dtype conversion
+// f32 -> f16 follows the reference's CPU table method bit for bit (lib/ccv_util.c:1434-1440; van der Zijp's
+// base/shift tables): the mantissa is TRUNCATED, values below 2^-24 flush to signed zero, values >= 2^16 become inf,
+// NaN keeps its top mantissa bits.  This is not __float2half_rn.
+__device__ __forceinline__ uint16_t f32_to_f16_trunc(const float f)
+{
+	const uint32_t u = __float_as_uint(f);
+	const uint32_t sign = (u >> 16) & 0x8000u;
+	const int e = (int)((u >> 23) & 0xff) - 127;
+	const uint32_t m = u & 0x007fffffu;
+	if (e < -24)
+		return (uint16_t)sign;
+	if (e < -14)
+		return (uint16_t)(sign | ((0x0400u >> (-e - 14)) + (m >> (-e - 1))));
+	if (e <= 15)
+		return (uint16_t)(sign | (((uint32_t)(e + 15) << 10) + (m >> 13)));
+	if (e < 128)
+		return (uint16_t)(sign | 0x7c00u);
+	return (uint16_t)(sign | (0x7c00u + (m >> 13)));
+}
+template <int AD, int BD>
+__global__ void convert_kernel(const void* __restrict__ a, void* __restrict__ b, const size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	{
+		if (AD == 0 && BD == 1)
+			reinterpret_cast<uint16_t*>(b)[i] = f32_to_f16_trunc(reinterpret_cast<const float*>(a)[i]);
+		else if (AD == 1 && BD == 0)
+			reinterpret_cast<float*>(b)[i] = __half2float(reinterpret_cast<const __half*>(a)[i]);
+		else if (AD == 0 && BD == 2)
+			reinterpret_cast<double*>(b)[i] = (double)reinterpret_cast<const float*>(a)[i];
+		else if (AD == 2 && BD == 0)
+			reinterpret_cast<float*>(b)[i] = (float)reinterpret_cast<const double*>(a)[i];
+		else if (AD == 0 && BD == 3)
+			reinterpret_cast<__nv_bfloat16*>(b)[i] = __float2bfloat16_rn(reinterpret_cast<const float*>(a)[i]);
+		else if (AD == 3 && BD == 0)
+			reinterpret_cast<float*>(b)[i] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a)[i]);
+		else if (AD == 2 && BD == 1)
+			reinterpret_cast<uint16_t*>(b)[i] = f32_to_f16_trunc((float)reinterpret_cast<const double*>(a)[i]);
+		else if (AD == 1 && BD == 2)
+			reinterpret_cast<double*>(b)[i] = (double)__half2float(reinterpret_cast<const __half*>(a)[i]);
+	}
+}
+int convert_dtype(cudaStream_t s, const void* a, int ad, void* b, int bd, size_t n)
+{
+	if (n == 0)
+		return 0;
+	const int grid = grid_for(n, 256);
+#define CONV_CASE(A, B) if (ad == A && bd == B) { convert_kernel<A, B><<<grid, 256, 0, s>>>(a, b, n); return check("convert_dtype"); }
+	CONV_CASE(0, 1) CONV_CASE(1, 0) CONV_CASE(0, 2) CONV_CASE(2, 0) CONV_CASE(0, 3) CONV_CASE(3, 0) CONV_CASE(2, 1) CONV_CASE(1, 2)
+#undef CONV_CASE
+	return 1;
+}
+
+// =============================================================================================== strided copy
+template <typename T>
+__global__ void copy_strided_kernel(const T* __restrict__ a, T* __restrict__ b, const Bcast4 d, const size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	{
+		size_t r = i;
+		const int i3 = r % d.dim[3];
+		r /= d.dim[3];
+		const int i2 = r % d.dim[2];
+		r /= d.dim[2];
+		const int i1 = r % d.dim[1];
+		const int i0 = (int)(r / d.dim[1]);
+		b[(size_t)i0 * d.cs[0] + (size_t)i1 * d.cs[1] + (size_t)i2 * d.cs[2] + (size_t)i3 * d.cs[3]] = a[(size_t)i0 * d.as[0] + (size_t)i1 * d.as[1] + (size_t)i2 * d.as[2] + (size_t)i3 * d.as[3]];
+	}
+}
+// util/ccv_nnc_util_cpu_ref.c (DATA_TRANSFER / FORMAT_TRANSFORM / TRANSPOSE all reduce to b[index] = a[index] over
+// permuted strides).  The index space is enumerated in the order that makes b's writes coalesced.
+int copy_strided(cudaStream_t s, const void* a, const int* astride, void* b, const int* bstride, const int* dim, int elem_size)
+{
+	Bcast4 d = make_bcast(astride, 0, bstride, dim);
+	// order the four axes by decreasing output stride so that consecutive threads write consecutive addresses
+	int order[4] = { 0, 1, 2, 3 };
+	for (int i = 0; i < 4; i++)
+		for (int j = i + 1; j < 4; j++)
+			if (d.cs[order[j]] > d.cs[order[i]] || (d.cs[order[j]] == d.cs[order[i]] && d.dim[order[j]] < d.dim[order[i]]))
+			{
+				const int t = order[i];
+				order[i] = order[j];
+				order[j] = t;
+			}
+	Bcast4 e;
+	for (int i = 0; i < 4; i++)
+		e.dim[i] = d.dim[order[i]], e.as[i] = d.as[order[i]], e.cs[i] = d.cs[order[i]], e.bs[i] = 0;
+	const size_t n = (size_t)e.dim[0] * e.dim[1] * e.dim[2] * e.dim[3];
+	if (n == 0)
+		return 0;
+	const int grid = grid_for(n, 256);
+	if (elem_size == 4)
+		copy_strided_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)a, (uint32_t*)b, e, n);
+	else if (elem_size == 2)
+		copy_strided_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)a, (uint16_t*)b, e, n);
+	else if (elem_size == 8)
+		copy_strided_kernel<uint64_t><<<grid, 256, 0, s>>>((const uint64_t*)a, (uint64_t*)b, e, n);
+	else if (elem_size == 1)
+		copy_strided_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)a, (uint8_t*)b, e, n);
+	else
+		return 1;
+	return check("copy_strided");
+}
+
+} // namespace sm100

@@ -1,0 +1,177 @@
+// sm100_ptx.cuh -- thin inline-PTX wrappers for the Blackwell (sm_100a) primitives the backend's kernels use:
+// mbarrier, TMA (cp.async.bulk.tensor tile + im2col), tcgen05 (alloc / mma / commit / ld / fences).
+// No CUTLASS: this is the whole dependency surface.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sm100 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t elect_one()
+{
+	uint32_t pred = 0;
+	asm volatile(
+		"{\n\t.reg .pred P;\n\t"
+		"elect.sync _|P, 0xffffffff;\n\t"
+		"selp.u32 %0, 1, 0, P;\n\t}\n"
+		: "=r"(pred));
+	return pred;
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n\t.reg .pred P1;\n\t"
+		"WAIT_LOOP:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+		"@P1 bra DONE;\n\t"
+		"bra WAIT_LOOP;\n\t"
+		"DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+		"r"(parity)
+		: "memory");
+}
+
+// ---------------------------------------------------------------- TMA
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* desc)
+{
+	asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* desc, uint64_t* bar, int c0, int c1)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+		"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+		: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* desc, uint64_t* bar, int c0, int c1, int c2)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+		"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+		: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* desc, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+		"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+		: "memory");
+}
+// im2col mode over an NHWC tensor {C, W, H, N}: loads `pixelsPerColumn` pixels x `channelsPerPixel` channels,
+// walking base pixels from (w, h, n) through the descriptor's bounding box; (off_w, off_h) is the filter-tap offset.
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* desc, uint64_t* bar, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
+		"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+		: "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
+{
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish()
+{
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before()
+{
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after()
+{
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; one thread issues on behalf of the CTA.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+		"l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+		"l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
+{
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+		"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+		"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+		  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+		  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+		  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+		: "r"(taddr)
+		: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait()
+{
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor (64-bit) for tcgen05.mma:
+//   [0,14)  start address >> 4      [16,30) leading byte offset >> 4     [32,46) stride byte offset >> 4
+//   [46,48) version = 1 (Blackwell)  [49,52) base offset = 0
+//   [61,64) layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (128-byte span swizzled in 32-byte atoms,
+//           the layout MN-major 32-bit operands require), 4 = 64B, 6 = 32B, 0 = none
+__host__ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
+{
+	return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+		(1ull << 46) | ((uint64_t)layout_type << 61);
+}
+// Instruction descriptor (32-bit): c_format [4,6) (1 = f32); a/b format [7,10)/[10,13) (0 f16, 1 bf16, 2 tf32);
+// a/b major [15]/[16] (0 = K-major, 1 = MN-major); N>>3 at [17,23); M>>4 at [24,29).
+__host__ __device__ __forceinline__ uint32_t umma_instr_desc(int ab_format, int a_mn_major, int b_mn_major, int m, int n)
+{
+	return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(a_mn_major ? 1 : 0) << 15) |
+		((uint32_t)(b_mn_major ? 1 : 0) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+} // namespace sm100
