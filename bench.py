@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric: ResNet-50 (bin/nnc/imagenet.c v1d) fp32, N=256 per GPU, forward +
+backward (+ the gradient allreduce for N>1, + the SGD commands), images/sec, on CCV_NNC_BACKEND_GPU_SM100.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's arm
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU_REF path on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...         # one process per GPU, batch-sharded (weak scaling)
+
+One JSON line on rank 0.  `value` is device-timed (CUDA events on the launching stream) with inputs resident in HBM;
+`e2e` is the same step driven from pinned HOST buffers through the reference-facing command API (CMD_DATA_TRANSFER of
+the input batch and labels in, the per-sample loss out), also device-timed.  Synthetic data, random-init weights.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "resnet50_fp32_n256_fwd_bwd_images_per_sec"
+UNIT = "images/s"
+
+
+def peaks():
+    p = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
+    try:
+        m = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        p = dict(hbm_gbs=float(m["hbm_gbs"]), bf16_tflops=float(m["bf16_tflops"]), bf16_tflops_sustained=float(m.get("bf16_tflops_sustained", m["bf16_tflops"])), source="measured")
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device):
+        threading.Thread.__init__(self)
+        self.daemon = True
+        self.device, self.samples, self.reasons, self.stop_flag, self.max_mhz = device, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"], timeout=5).decode().strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+def reference_arm(args):
+    """The reference's own implementation of the path: the identical ResNet-50 command list executed by the compiled,
+    unmodified reference (oracle/_ref/libccv_ref.so, CCV_NNC_BACKEND_CPU_REF) on the host cores.  A step is a bounded
+    sample of the workload: batch 1 (CPU_REF's pooling only walks one image per call) at 224x224, the
+    same forward + backward + SGD commands.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref, ref_factory
+    from ccv_b200 import resnet50
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libccv_ref.so not built (make -C oracle)"}))
+        return
+    sample_batch = 1
+    net = resnet50.Net(sample_batch, image=args.image, classes=1000, global_batch=sample_batch, factory=ref_factory.RefFactory())
+    net.input.upload(np.random.RandomState(0).rand(sample_batch, args.image, args.image, 3).astype(np.float32))
+    net.labels.upload(np.zeros((sample_batch,), np.int32))
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+
+    def step():
+        ref_factory.run_nodes(net.fwd)
+        ref_factory.run_nodes(net.bwd)
+        ref_factory.run_nodes(net.opt)
+    for _ in range(warmup):
+        step()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt = (time.time() - t0) / steps
+    v = sample_batch / dt
+    cores = ref.num_threads()
+    sample = "ResNet-50 v1d fwd+bwd+SGD, batch %d of %dx%d, CCV_NNC_BACKEND_CPU_REF, %d OpenMP threads, %d step(s)" % (sample_batch, args.image, args.image, cores, steps)
+    print(json.dumps({"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                      "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c) fp32 NHWC fwd+bwd+SGD; bounded sample: batch 1 per step on the host CPU", "image": args.image},
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def cpu_baseline(image, budget_s=30.0):
+    """Reported next to the GPU number (rank 0, N=1): the same command list on the reference's CPU_REF, batch 1."""
+    try:
+        from oracle import ref, ref_factory
+        from ccv_b200 import resnet50
+        if not ref.available():
+            return None
+        net = resnet50.Net(1, image=image, classes=1000, global_batch=1, factory=ref_factory.RefFactory())
+        net.input.upload(np.random.RandomState(0).rand(1, image, image, 3).astype(np.float32))
+        net.labels.upload(np.zeros((1,), np.int32))
+        t0 = time.time()
+        n = 0
+        while n < 1 or (time.time() - t0 < budget_s / 3 and n < 3):
+            ref_factory.run_nodes(net.fwd), ref_factory.run_nodes(net.bwd), ref_factory.run_nodes(net.opt)
+            n += 1
+        dt = (time.time() - t0) / n
+        return {"value": 1.0 / dt, "unit": UNIT, "cores": ref.num_threads(), "kind": "reference",
+                "sample": "ResNet-50 v1d fwd+bwd+SGD, batch 1 of %dx%d per step, %d step(s), CCV_NNC_BACKEND_CPU_REF compiled from /root/reference (oracle/_ref), OpenMP" % (image, image, n)}
+    except Exception as e:  # the baseline must never take the benchmark down
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sm100")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE: 256)")
+    ap.add_argument("--image", type=int, default=224)
+    ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-op", default="", help="write the per-command profile to this JSON file")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ccv_b200 import nnc, resnet50
+    nnc.init()
+    if nnc.lib().ccv_nnc_device_count(nnc.CCV_STREAM_CONTEXT_GPU) <= 0:
+        raise SystemExit("bench.py: no CUDA device and there is no CPU fallback (use --impl reference for the CPU_REF arm)")
+    device = local_rank
+    stream = nnc.Stream(device)
+    net = resnet50.Net(args.batch, image=args.image, classes=1000, device=device, global_batch=args.batch * world)
+    fb_nodes, opt_nodes = net.fwd + net.bwd, net.opt
+    graph = nnc.Graph()
+    for cmd, hint, flags, ins, outs in fb_nodes + opt_nodes:
+        graph.exec_new(cmd, hint, flags, ins, outs)
+    n_fb, n_all = len(fb_nodes), len(fb_nodes) + len(opt_nodes)
+
+    # synthetic batch in pinned host memory (for the e2e leg) and resident in HBM (for `value`)
+    rs = np.random.RandomState(1234 + rank)
+    host_in = nnc.cpu_tensor([args.batch, args.image, args.image, 3])
+    host_lab = nnc.cpu_tensor([args.batch], datatype=nnc.CCV_32S)
+    host_loss = nnc.cpu_tensor([args.batch])
+    for t in (host_in, host_lab, host_loss):
+        nnc.lib().ccv_nnc_tensor_pin_memory(t.ptr)
+    host_in.upload(rs.rand(args.batch, args.image, args.image, 3).astype(np.float32))
+    host_lab.upload(rs.randint(0, 1000, size=(args.batch,)).astype(np.int32))
+    xfer = nnc.CMD_DATA_TRANSFER_FORWARD()
+    assert nnc.cmd_exec(xfer, None, 0, [host_in, host_lab], [net.input, net.labels], stream) == 0
+    stream.wait()
+
+    # the single gradient exchange: one sum-allreduce over the flat gradient buffer (torch.distributed/NCCL plumbing)
+    allreduce = None
+    if world > 1:
+        import torch
+
+        class _Flat(object):
+            __cuda_array_interface__ = {"shape": (net.flat_count,), "typestr": "<f4", "data": (net.g_flat.data_ptr, False), "version": 2}
+        g_torch = torch.as_tensor(_Flat(), device=torch.device("cuda", device))
+        ext = torch.cuda.ExternalStream(stream.cuda_stream, device=torch.device("cuda", device))
+
+        def allreduce():
+            with torch.cuda.stream(ext):
+                dist.all_reduce(g_torch)
+
+    # eager pass: sizes workspaces, counts launches, checks every command returns success
+    l0 = nnc.launch_count()
+    if graph.run(stream, 0, n_all) != 0:
+        raise SystemExit("bench.py: a command failed: %s" % nnc.lib().ccv_nnc_sm100_last_error())
+    stream.wait()
+    launches_per_step = nnc.launch_count() - l0
+    use_graph = not args.no_cuda_graph
+    if use_graph:
+        cap_fb, cap_opt = graph.capture(stream, 0, n_fb), graph.capture(stream, n_fb, n_all)
+
+    def step():
+        if use_graph:
+            graph.replay(cap_fb, stream)
+        else:
+            graph.run(stream, 0, n_fb)
+        if allreduce:
+            allreduce()
+        if use_graph:
+            graph.replay(cap_opt, stream)
+        else:
+            graph.run(stream, n_fb, n_all)
+
+    def barrier():
+        stream.wait()
+        if dist is not None:
+            dist.barrier()
+        stream.wait()
+
+    def timed(fn, steps):
+        e0, e1 = nnc.Event(), nnc.Event()
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        ms = e0.elapsed_ms(e1)
+        barrier()
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(device)
+    sampler.start()
+    ms = timed(step, args.steps)
+    ms_per_step = ms / args.steps
+
+    def e2e_step():
+        nnc.cmd_exec(xfer, None, 0, [host_in, host_lab], [net.input, net.labels], stream)
+        step()
+        nnc.cmd_exec(xfer, None, 0, [net.loss], [host_loss], stream)
+    e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    sampler.stop_flag = True
+    sampler.join()
+    loss = float(np.mean(host_loss.download()))
+
+    images_per_step = args.batch * world
+    value = images_per_step / (ms_per_step * 1e-3)
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c:17-95) fp32 NHWC, per-GPU batch %d, %dx%d, fwd+bwd + nesterov SGD%s" % (args.batch, args.image, args.image, ", one NCCL sum-allreduce of the flat fp32 gradient buffer" if world > 1 else ""),
+                      "global_batch": images_per_step, "parallelism": "dp%d" % world, "tensor_core_math": "tcgen05 kind::tf32, fp32 accumulate (TMA rounds operands to TF32)",
+                      "cuda_graph": use_graph, "l2": "activations per step (>20 GB) exceed the 126 MB L2: no flush needed", "mean_loss": loss},
+           "e2e": {"value": images_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes + host_lab.nbytes), "d2h_bytes_per_step": int(host_loss.nbytes), "ms_per_step": e2e_ms},
+           "gpu_launches": int(launches_per_step * (args.steps * 2 + args.warmup + 2)), "gpu_launches_per_step": int(launches_per_step), "clocks": sampler.summary()}
+
+    if rank == 0:
+        # per-command profile (eager, CUDA events around every command) -> roofline of the dominant kernel
+        pk = peaks()
+        prof = profile_nodes(nnc, net, stream, pk)
+        out["roofline"] = prof["roofline"]
+        out["per_op"] = prof["summary"]
+        if args.per_op:
+            json.dump(prof, open(args.per_op, "w"), indent=1)
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.image)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def node_cost(cmd, ins, outs):
+    """(kind, algorithmic flops, algorithmic bytes) of one command, from its tensors (SURVEY.md 8d per-unit figures:
+    contractions = 2 * M * N * K flops; everything else = the bytes it must read + write once)."""
+    from ccv_b200 import abi
+    nb = lambda t: 0 if t is None else t.nbytes
+    c = cmd.cmd
+    io = sum(nb(t) for t in ins) + sum(nb(t) for t in outs)
+    if c == abi.CCV_NNC_CONVOLUTION_FORWARD:
+        n, p, q, k = outs[0].dims
+        return "conv_fwd", 2.0 * n * p * q * k * ins[1].count / ins[1].dims[0], io
+    if c == abi.CCV_NNC_CONVOLUTION_BACKWARD:
+        n, p, q, k = ins[0].dims
+        f = 2.0 * n * p * q * k * ins[2].count / ins[2].dims[0]
+        return "conv_bwd", f * (2 if outs[0] is not None else 1), io
+    if c == abi.CCV_NNC_GEMM_FORWARD:
+        return "gemm_fwd", 2.0 * outs[0].count * ins[0].dims[-1], io
+    if c == abi.CCV_NNC_GEMM_BACKWARD:
+        return "gemm_bwd", 4.0 * ins[0].count * ins[1].dims[-1], io
+    names = {abi.CCV_NNC_BATCH_NORM_FORWARD: "bn_fwd", abi.CCV_NNC_BATCH_NORM_BACKWARD: "bn_bwd", abi.CCV_NNC_RELU_FORWARD: "relu_fwd", abi.CCV_NNC_RELU_BACKWARD: "relu_bwd",
+             abi.CCV_NNC_EWSUM_FORWARD: "ewsum", abi.CCV_NNC_MAX_POOL_FORWARD: "maxpool_fwd", abi.CCV_NNC_MAX_POOL_BACKWARD: "maxpool_bwd", abi.CCV_NNC_AVERAGE_POOL_FORWARD: "avgpool_fwd",
+             abi.CCV_NNC_AVERAGE_POOL_BACKWARD: "avgpool_bwd", abi.CCV_NNC_SGD_FORWARD: "sgd", abi.CCV_NNC_SOFTMAX_FORWARD: "softmax", abi.CCV_NNC_SOFTMAX_BACKWARD: "softmax"}
+    return names.get(c, "other"), 0.0, io
+
+
+def profile_nodes(nnc, net, stream, pk):
+    """Run every command of one step eagerly with CUDA events around it (3 repetitions, best taken)."""
+    rows = []
+    e0, e1 = nnc.Event(), nnc.Event()
+    for nodes in (net.fwd, net.bwd, net.opt):
+        for cmd, hint, flags, ins, outs in nodes:
+            kind, flops, nbytes = node_cost(cmd, ins, outs)
+            best = 1e30
+            for _ in range(3):
+                e0.record(stream)
+                nnc.cmd_exec(cmd, hint, flags, ins, outs, stream)
+                e1.record(stream)
+                best = min(best, e0.elapsed_ms(e1))
+            rows.append(dict(kind=kind, ms=best, flops=flops, bytes=nbytes))
+    summary = {}
+    for r in rows:
+        s = summary.setdefault(r["kind"], dict(n=0, ms=0.0, flops=0.0, bytes=0.0))
+        s["n"] += 1
+        s["ms"] += r["ms"]
+        s["flops"] += r["flops"]
+        s["bytes"] += r["bytes"]
+    tf32_peak = pk["bf16_tflops"] / 2.0
+    for k, s in summary.items():
+        if s["flops"] > 0:
+            s["tflops"] = s["flops"] / (s["ms"] * 1e-3) / 1e12
+            s["frac_of_tf32_peak"] = s["tflops"] / tf32_peak
+        s["gbs"] = s["bytes"] / (s["ms"] * 1e-3) / 1e9
+        s["frac_of_hbm_peak"] = s["gbs"] / pk["hbm_gbs"]
+    tc = [r for r in rows if r["flops"] > 0]
+    tc_flops, tc_ms = sum(r["flops"] for r in tc), sum(r["ms"] for r in tc)
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "umma_gemm_kernel (tcgen05 kind::tf32; all convolution + GEMM commands of one step)", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf32_peak, "traffic": None, "peak_source": "%s bf16 cuBLAS burst peak / 2 (TF32 tensor rate is half the bf16 rate)" % pk["source"],
+                "launch_ms_total": tc_ms, "algorithmic_flops_per_step": tc_flops, "total_ms_all_commands": sum(r["ms"] for r in rows)}
+    return dict(roofline=roofline, summary=summary, rows=rows)
+
+
+if __name__ == "__main__":
+    main()

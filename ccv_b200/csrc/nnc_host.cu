@@ -540,6 +540,36 @@ int ccv_nnc_sm100_memcpy_d2h(void* const dst_host, const void* const src_device,
 	return 0;
 }
 
+// CUDA-event timing on a stream context's stream (device time, the way every number in bench.py is taken)
+void* ccv_nnc_sm100_event_new(void)
+{
+	cudaEvent_t e = 0;
+	if (cudaEventCreate(&e) != cudaSuccess)
+		return 0;
+	return (void*)e;
+}
+
+int ccv_nnc_sm100_event_record(void* const event, ccv_nnc_stream_context_t* const stream_context)
+{
+	return cudaEventRecord((cudaEvent_t)event, (cudaStream_t)ccv_nnc_stream_context_get_stream(stream_context)) == cudaSuccess ? 0 : -1;
+}
+
+float ccv_nnc_sm100_event_elapsed_ms(void* const begin, void* const end)
+{
+	float ms = -1.f;
+	if (cudaEventSynchronize((cudaEvent_t)end) != cudaSuccess)
+		return -1.f;
+	if (cudaEventElapsedTime(&ms, (cudaEvent_t)begin, (cudaEvent_t)end) != cudaSuccess)
+		return -1.f;
+	return ms;
+}
+
+void ccv_nnc_sm100_event_free(void* const event)
+{
+	if (event)
+		cudaEventDestroy((cudaEvent_t)event);
+}
+
 uint64_t ccv_nnc_sm100_launch_count(void)
 {
 	return (uint64_t)sm100::launch_count();

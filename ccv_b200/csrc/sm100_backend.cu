@@ -1,0 +1,1204 @@
+// sm100_backend.cu -- group (A) of include/ccv_nnc_sm100.h: the command layer of CCV_NNC_BACKEND_GPU_SM100.
+//
+// One exec function per command, with the reference's signature (lib/nnc/ccv_nnc.h:315) and positional tensor
+// conventions (lib/nnc/ccv_nnc.h:308-314), and one registration function per command spelled exactly as
+// REGISTER_COMMAND_BACKEND(cmd, CCV_NNC_BACKEND_GPU_SM100) would (lib/nnc/ccv_nnc_internal.h:196-202).  An exec only
+// validates shapes, pulls the CUDA stream / workspace from the stream context and enqueues kernels; it never
+// synchronises and there is no CPU path: anything it cannot run returns CCV_NNC_EXEC_INVALID.
+#include "../../include/ccv_nnc_sm100.h"
+#include "sm100_contract.h"
+#include "sm100_ew.h"
+#include <cuda_runtime.h>
+#include <string.h>
+
+using namespace sm100;
+
+namespace {
+
+struct TV {
+	unsigned char* p;
+	int nd;
+	int dim[CCV_NNC_MAX_DIM_ALLOC];
+	int stride[CCV_NNC_MAX_DIM_ALLOC];
+	int contiguous;
+	int datatype;
+	int format;
+	size_t count;
+};
+
+int tensor_nd(const int* const dim)
+{
+	int i;
+	for (i = 0; i < CCV_NNC_MAX_DIM_ALLOC; i++)
+		if (dim[i] == 0)
+			return i;
+	return CCV_NNC_MAX_DIM_ALLOC;
+}
+
+// ccv_nnc_tensor_view_get_stride (lib/nnc/ccv_nnc_easy.h): a view carries its strides, a plain tensor is packed
+TV view_of(const ccv_nnc_tensor_t* const t)
+{
+	TV v;
+	memset(&v, 0, sizeof(v));
+	v.p = t->data.u8;
+	v.nd = tensor_nd(t->info.dim);
+	v.datatype = CCV_GET_DATA_TYPE(t->info.datatype);
+	v.format = t->info.format;
+	v.count = 1;
+	int i;
+	for (i = 0; i < v.nd; i++)
+		v.dim[i] = t->info.dim[i], v.count *= (size_t)t->info.dim[i];
+	if (CCV_IS_TENSOR_VIEW(t))
+	{
+		const ccv_nnc_tensor_view_t* const tv = (const ccv_nnc_tensor_view_t*)t;
+		int packed = 1;
+		v.contiguous = 1;
+		for (i = v.nd - 1; i >= 0; i--)
+		{
+			v.stride[i] = tv->stride[i];
+			if (v.dim[i] != 1 && tv->stride[i] != packed)
+				v.contiguous = 0;
+			packed *= v.dim[i];
+		}
+	} else {
+		int packed = 1;
+		for (i = v.nd - 1; i >= 0; i--)
+			v.stride[i] = packed, packed *= v.dim[i];
+		v.contiguous = 1;
+	}
+	return v;
+}
+
+// ccv_nnc_tensor_view_get_dim: right-align into 4 dims with leading 1s
+void dims4(const TV& v, int dim[4], int stride[4])
+{
+	const int off = 4 - v.nd;
+	int i;
+	for (i = 0; i < 4; i++)
+	{
+		if (i < off)
+			dim[i] = 1, stride[i] = 0;
+		else
+			dim[i] = v.dim[i - off], stride[i] = v.stride[i - off];
+	}
+}
+
+inline cudaStream_t stream_of(ccv_nnc_stream_context_t* const stream_context)
+{
+	return (cudaStream_t)ccv_nnc_stream_context_get_stream(stream_context);
+}
+
+inline bool is_f32(const ccv_nnc_tensor_t* const t) { return CCV_GET_DATA_TYPE(t->info.datatype) == CCV_32F; }
+
+bool same_shape(const TV& a, const TV& b)
+{
+	if (a.nd != b.nd)
+		return false;
+	for (int i = 0; i < a.nd; i++)
+		if (a.dim[i] != b.dim[i])
+			return false;
+	return true;
+}
+
+int dtype_code(const int datatype)
+{
+	switch (CCV_GET_DATA_TYPE(datatype))
+	{
+		case CCV_32F: return 0;
+		case CCV_16F: return 1;
+		case CCV_64F: return 2;
+		case CCV_16BF: return 3;
+	}
+	return -1;
+}
+
+size_t dtype_size(const int datatype)
+{
+	switch (CCV_GET_DATA_TYPE(datatype))
+	{
+		case CCV_8U: return 1;
+		case CCV_16F: case CCV_16BF: return 2;
+		case CCV_32F: case CCV_32S: return 4;
+		case CCV_64F: case CCV_64S: return 8;
+	}
+	return 0;
+}
+
+#define RC(x) do { const int rc_ = (x); if (rc_ < 0) return CCV_NNC_EXEC_INVALID; if (rc_ > 0) return CCV_NNC_EXEC_INVALID; } while (0)
+
+// ================================================================================================ GEMM
+struct Mat {
+	float* p;
+	int batch, rows, cols;
+	long long batch_inc, rs, cs;
+};
+
+// ccv_nnc_tensor_get_matrix_params (lib/nnc/ccv_nnc_easy.h:421-444) for nd <= 3
+bool mat_of(const TV& v, const int transpose[2], Mat& m)
+{
+	if (v.nd < 1 || v.nd > 3)
+		return false;
+	m.p = (float*)v.p;
+	m.batch = v.nd < 3 ? 1 : v.dim[v.nd - 3];
+	m.batch_inc = v.nd < 3 ? 0 : v.stride[v.nd - 3];
+	m.rows = v.nd == 1 ? 1 : v.dim[v.nd - 2];
+	m.rs = v.nd >= 2 ? v.stride[v.nd - 2] : (long long)v.stride[0] * v.dim[0];
+	m.cols = v.dim[v.nd - 1];
+	m.cs = v.stride[v.nd - 1];
+	if (transpose[0] != transpose[1])
+	{
+		const int t = m.rows;
+		m.rows = m.cols, m.cols = t;
+		const long long u = m.rs;
+		m.rs = m.cs, m.cs = u;
+	}
+	return true;
+}
+
+// C[M, N] (+)= A[M, K] * B[K, N] + bias over arbitrary (row, col) element strides
+int gemm_dispatch(cudaStream_t s, const int algorithm, const int M, const int N, const int K, const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c, long long c_rs, long long c_cs, const float* bias, const int accumulate)
+{
+	if (M <= 0 || N <= 0)
+		return 0;
+	if (K <= 0)
+		return 1;
+	if (c_cs != 1 && N > 1)
+	{
+		if (c_rs != 1 && M > 1)
+			return 1;
+		if (bias)
+			return 1;
+		// C^T = B^T A^T
+		return gemm_dispatch(s, algorithm, N, M, K, b, b_cs, b_rs, a, a_cs, a_rs, c, c_cs, 1, 0, accumulate);
+	}
+	if (algorithm != CCV_NNC_SM100_ALGO_FFMA)
+	{
+		int ta = -1, tb = -1;
+		long long lda = 0, ldb = 0;
+		if (a_cs == 1 || K == 1)
+			ta = 0, lda = a_rs;
+		else if (a_rs == 1 || M == 1)
+			ta = 1, lda = a_cs;
+		if (b_cs == 1 || N == 1)
+			tb = 0, ldb = b_rs;
+		else if (b_rs == 1 || K == 1)
+			tb = 1, ldb = b_cs;
+		if (ta >= 0 && tb >= 0)
+		{
+			const int rc = gemm_tf32(s, M, N, K, a, lda, ta, b, ldb, tb, c, c_rs, bias, accumulate);
+			if (rc <= 0)
+				return rc;
+		}
+	}
+	return gemm_ffma(s, M, N, K, a, a_rs, a_cs, b, b_rs, b_cs, c, c_rs, bias, accumulate);
+}
+
+// blas/ccv_nnc_gemm_cpu_ref.c:110-184
+int exec_gemm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	const ccv_nnc_tensor_t* const bias_t = input_size > 2 ? inputs[2] : 0;
+	if (!is_f32(inputs[0]) || !is_f32(inputs[1]) || !is_f32(outputs[0]) || (bias_t && !is_f32(bias_t)))
+		return CCV_NNC_EXEC_INVALID;
+	const int no_transpose[2] = { 0, 0 };
+	Mat a, w, b, bias;
+	if (!mat_of(view_of(inputs[0]), cmd.info.blas.transpose_a, a) || !mat_of(view_of(inputs[1]), cmd.info.blas.transpose_b, w) || !mat_of(view_of(outputs[0]), no_transpose, b))
+		return CCV_NNC_EXEC_INVALID;
+	if (a.rows != b.rows || a.cols != w.rows || w.cols != b.cols)
+		return CCV_NNC_EXEC_INVALID;
+	if ((a.batch != b.batch && a.batch != 1) || (w.batch != b.batch && w.batch != 1))
+		return CCV_NNC_EXEC_INVALID;
+	if (a.batch == 1)
+		a.batch_inc = 0;
+	if (w.batch == 1)
+		w.batch_inc = 0;
+	if (bias_t)
+	{
+		if (!mat_of(view_of(bias_t), no_transpose, bias) || bias.cols != b.cols || bias.cs != 1 || (bias.rows != 1))
+			return CCV_NNC_EXEC_INVALID;
+		if (bias.batch == 1)
+			bias.batch_inc = 0;
+	}
+	cudaStream_t s = stream_of(stream_context);
+	for (int i = 0; i < b.batch; i++)
+		RC(gemm_dispatch(s, cmd.algorithm, b.rows, b.cols, a.cols, a.p + i * a.batch_inc, a.rs, a.cs, w.p + i * w.batch_inc, w.rs, w.cs, b.p + i * b.batch_inc, b.rs, b.cs, bias_t ? bias.p + i * bias.batch_inc : 0, 0));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// blas/ccv_nnc_gemm_cpu_ref.c:318-448: inputs (g, a, w), outputs (h, dw, dbias), each optional
+int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 2 || output_size < 1 || !inputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	const int no_transpose[2] = { 0, 0 };
+	const int accumulate = (flags & CCV_NNC_ACCUMULATE_OUTPUT) ? 1 : 0;
+	Mat g;
+	if (!is_f32(inputs[0]) || !mat_of(view_of(inputs[0]), no_transpose, g))
+		return CCV_NNC_EXEC_INVALID;
+	cudaStream_t s = stream_of(stream_context);
+	ccv_nnc_tensor_t* const dbias_t = output_size > 2 ? outputs[2] : 0;
+	ccv_nnc_tensor_t* const dw_t = output_size > 1 ? outputs[1] : 0;
+	ccv_nnc_tensor_t* const h_t = outputs[0];
+	if (dbias_t)
+	{
+		Mat db;
+		if (!mat_of(view_of(dbias_t), no_transpose, db) || db.cols != g.cols || db.cs != 1 || g.cs != 1 || db.rows != 1)
+			return CCV_NNC_EXEC_INVALID;
+		if (db.batch != 1 && db.batch != g.batch)
+			return CCV_NNC_EXEC_INVALID;
+		for (int i = 0; i < g.batch; i++)
+			RC(colsum_f32(s, g.p + i * g.batch_inc, g.rows, g.cols, g.rs, db.p + (db.batch == 1 ? 0 : i * db.batch_inc), accumulate || (db.batch == 1 && i > 0)));
+	}
+	if (dw_t)
+	{
+		if (!inputs[1])
+			return CCV_NNC_EXEC_INVALID;
+		Mat a, dw;
+		if (!mat_of(view_of(inputs[1]), cmd.info.blas.transpose_a, a) || !mat_of(view_of(dw_t), cmd.info.blas.transpose_b, dw))
+			return CCV_NNC_EXEC_INVALID;
+		if (a.rows != g.rows || a.cols != dw.rows || dw.cols != g.cols)
+			return CCV_NNC_EXEC_INVALID;
+		if (a.batch == 1)
+			a.batch_inc = 0;
+		// dw[K, N] = a^T[K, M] * g[M, N]; a shared dw sums over the batch
+		for (int i = 0; i < g.batch; i++)
+			RC(gemm_dispatch(s, cmd.algorithm, dw.rows, dw.cols, g.rows, a.p + i * a.batch_inc, a.cs, a.rs, g.p + i * g.batch_inc, g.rs, g.cs, dw.p + (dw.batch == 1 ? 0 : i * dw.batch_inc), dw.rs, dw.cs, 0, accumulate || (dw.batch == 1 && i > 0)));
+	}
+	if (h_t)
+	{
+		if (input_size < 3 || !inputs[2])
+			return CCV_NNC_EXEC_INVALID;
+		Mat h, w;
+		if (!mat_of(view_of(h_t), cmd.info.blas.transpose_a, h) || !mat_of(view_of(inputs[2]), cmd.info.blas.transpose_b, w))
+			return CCV_NNC_EXEC_INVALID;
+		if (h.cols != w.rows || w.cols != g.cols || h.rows != g.rows)
+			return CCV_NNC_EXEC_INVALID;
+		if (w.batch == 1)
+			w.batch_inc = 0;
+		// h[M, K] = g[M, N] * w^T[N, K]
+		for (int i = 0; i < g.batch; i++)
+			RC(gemm_dispatch(s, cmd.algorithm, h.rows, h.cols, g.cols, g.p + i * g.batch_inc, g.rs, g.cs, w.p + i * w.batch_inc, w.cs, w.rs, h.p + (h.batch == 1 ? 0 : i * h.batch_inc), h.rs, h.cs, 0, accumulate || (h.batch == 1 && i > 0)));
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ================================================================================================ CONVOLUTION
+// NHWC activations ([N,] H, W, C), filters [K, R, S, C / groups] (convolution/ccv_nnc_conv_cpu_ref.c:47-65)
+bool conv_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, const TV& a, const TV& w, const TV& b, ConvGeom& g)
+{
+	if (a.format != CCV_TENSOR_FORMAT_NHWC || b.format != CCV_TENSOR_FORMAT_NHWC)
+		return false;
+	if ((a.nd != 3 && a.nd != 4) || (b.nd != 3 && b.nd != 4) || w.nd != 4 || !w.contiguous)
+		return false;
+	const int ao = a.nd - 3, bo = b.nd - 3;
+	memset(&g, 0, sizeof(g));
+	g.N = a.nd == 4 ? a.dim[0] : 1;
+	if ((b.nd == 4 ? b.dim[0] : 1) != g.N)
+		return false;
+	g.H = a.dim[ao], g.W = a.dim[ao + 1], g.C = a.dim[ao + 2];
+	g.P = b.dim[bo], g.Q = b.dim[bo + 1], g.K = b.dim[bo + 2];
+	g.R = w.dim[1], g.S = w.dim[2];
+	if (a.stride[ao + 2] != 1 || b.stride[bo + 2] != 1)
+		return false;
+	g.an = a.nd == 4 ? a.stride[0] : (long long)g.H * a.stride[ao];
+	g.ah = a.stride[ao], g.aw = a.stride[ao + 1];
+	g.bn = b.nd == 4 ? b.stride[0] : (long long)g.P * b.stride[bo];
+	g.bh = b.stride[bo], g.bw = b.stride[bo + 1];
+	g.stride_h = hint.stride.dim[0] > 0 ? hint.stride.dim[0] : 1;
+	g.stride_w = hint.stride.dim[1] > 0 ? hint.stride.dim[1] : 1;
+	g.dil_h = cmd.info.convolution.dilation[0] > 1 ? cmd.info.convolution.dilation[0] : 1;
+	g.dil_w = cmd.info.convolution.dilation[1] > 1 ? cmd.info.convolution.dilation[1] : 1;
+	g.pad_h0 = hint.border.begin[0], g.pad_w0 = hint.border.begin[1];
+	// CPU_REF clips the window at the far edge (SET_BORDER_OFFSET_SIZE_FOR), i.e. the effective end padding is whatever
+	// the output extent implies, not hint.border.end
+	g.pad_h1 = (g.P - 1) * g.stride_h + (g.R - 1) * g.dil_h + 1 - g.H - g.pad_h0;
+	g.pad_w1 = (g.Q - 1) * g.stride_w + (g.S - 1) * g.dil_w + 1 - g.W - g.pad_w0;
+	const int groups = cmd.info.convolution.groups > 0 ? cmd.info.convolution.groups : 1;
+	if (w.dim[0] != g.K || g.K != cmd.info.convolution.count || w.dim[3] * groups != g.C || g.K % groups != 0)
+		return false;
+	if (cmd.info.size.dim[0] != g.R || cmd.info.size.dim[1] != g.S)
+		return false;
+	return true;
+}
+
+int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	const ccv_nnc_tensor_t* const bias_t = input_size > 2 ? inputs[2] : 0;
+	if (!is_f32(inputs[0]) || !is_f32(inputs[1]) || !is_f32(outputs[0]) || (bias_t && (!is_f32(bias_t) || CCV_IS_TENSOR_VIEW(bias_t))))
+		return CCV_NNC_EXEC_INVALID;
+	ConvGeom g;
+	if (!conv_geom(cmd, hint, view_of(inputs[0]), view_of(inputs[1]), view_of(outputs[0]), g))
+		return CCV_NNC_EXEC_INVALID;
+	if (bias_t && bias_t->info.dim[0] != g.K)
+		return CCV_NNC_EXEC_INVALID;
+	const int groups = cmd.info.convolution.groups > 0 ? cmd.info.convolution.groups : 1;
+	cudaStream_t s = stream_of(stream_context);
+	const float* a = inputs[0]->data.f32;
+	const float* w = inputs[1]->data.f32;
+	const float* bias = bias_t ? bias_t->data.f32 : 0;
+	float* b = outputs[0]->data.f32;
+	if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
+	{
+		const int rc = conv_fprop_tf32(s, g, a, w, bias, b);
+		if (rc == 0)
+			return CCV_NNC_EXEC_SUCCESS;
+		if (rc < 0)
+			return CCV_NNC_EXEC_INVALID;
+	}
+	RC(conv_fprop_ffma(s, g, groups, a, w, bias, b));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// convolution/ccv_nnc_conv_cpu_ref.c:174-345: inputs (g, a, w), outputs (h, dw, dbias); dw / dbias honour
+// CCV_NNC_ACCUMULATE_OUTPUT, h is always overwritten (:286)
+int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1])
+		return CCV_NNC_EXEC_INVALID;
+	ccv_nnc_tensor_t* const h_t = outputs[0];
+	ccv_nnc_tensor_t* const dw_t = output_size > 1 ? outputs[1] : 0;
+	ccv_nnc_tensor_t* const dbias_t = output_size > 2 ? outputs[2] : 0;
+	const ccv_nnc_tensor_t* const w_t = input_size > 2 ? inputs[2] : 0;
+	const ccv_nnc_tensor_t* const filt = dw_t ? dw_t : w_t;
+	if (!filt || !is_f32(inputs[0]) || !is_f32(inputs[1]))
+		return CCV_NNC_EXEC_INVALID;
+	ConvGeom g;
+	if (!conv_geom(cmd, hint, view_of(inputs[1]), view_of(filt), view_of(inputs[0]), g))
+		return CCV_NNC_EXEC_INVALID;
+	const int groups = cmd.info.convolution.groups > 0 ? cmd.info.convolution.groups : 1;
+	const int accumulate = (flags & CCV_NNC_ACCUMULATE_OUTPUT) ? 1 : 0;
+	cudaStream_t s = stream_of(stream_context);
+	const float* gb = inputs[0]->data.f32;
+	const float* a = inputs[1]->data.f32;
+	if (dbias_t)
+	{
+		if (dbias_t->info.dim[0] != g.K || g.bh != (long long)g.Q * g.bw || g.bn != (long long)g.P * g.bh)
+			return CCV_NNC_EXEC_INVALID;
+		RC(colsum_f32(s, gb, (size_t)g.N * g.P * g.Q, g.K, g.bw, dbias_t->data.f32, accumulate));
+	}
+	if (dw_t)
+	{
+		int rc = 1;
+		if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
+			rc = conv_wgrad_tf32(s, g, gb, a, dw_t->data.f32, accumulate);
+		if (rc < 0)
+			return CCV_NNC_EXEC_INVALID;
+		if (rc > 0)
+			RC(conv_wgrad_ffma(s, g, groups, gb, a, dw_t->data.f32, accumulate));
+	}
+	if (h_t)
+	{
+		if (!w_t || !is_f32(h_t))
+			return CCV_NNC_EXEC_INVALID;
+		ConvGeom gh;
+		if (!conv_geom(cmd, hint, view_of(h_t), view_of(w_t), view_of(inputs[0]), gh))
+			return CCV_NNC_EXEC_INVALID;
+		int rc = 1;
+		if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
+			rc = conv_dgrad_tf32(s, gh, gb, w_t->data.f32, h_t->data.f32);
+		if (rc < 0)
+			return CCV_NNC_EXEC_INVALID;
+		if (rc > 0)
+			RC(conv_dgrad_ffma(s, gh, groups, gb, w_t->data.f32, h_t->data.f32));
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ================================================================================================ BATCH NORM
+// norm/ccv_nnc_batch_norm_cpu_ref.c:16-250.  Supported reduction shapes: per-channel statistics of an NHWC
+// ([.., C], scale dims [1,1,1,C]) or NCHW ([N, C, H, W], scale dims [1,C,1,1]) tensor.
+bool bn_layout(const TV& a, const TV& scale, size_t& outer, int& C, size_t& inner)
+{
+	int ad[4], as[4], rd[4], rs[4];
+	if (a.nd > 4 || scale.nd > 4 || !a.contiguous || !scale.contiguous)
+		return false;
+	dims4(a, ad, as);
+	dims4(scale, rd, rs);
+	int axis = -1;
+	for (int i = 0; i < 4; i++)
+		if (rd[i] != 1)
+		{
+			if (axis >= 0 || rd[i] != ad[i])
+				return false;
+			axis = i;
+		}
+	if (axis < 0)
+		axis = 3; // a single statistic over everything: C = 1
+	if (rd[axis] == 1 && ad[axis] != 1)
+	{
+		// scale has one element but the tensor does not: treat the whole tensor as one channel
+		outer = 1, C = 1, inner = a.count;
+		return true;
+	}
+	outer = 1, inner = 1;
+	for (int i = 0; i < axis; i++)
+		outer *= ad[i];
+	for (int i = axis + 1; i < 4; i++)
+		inner *= ad[i];
+	C = ad[axis];
+	return true;
+}
+
+int exec_bnorm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 5 || output_size < 1)
+		return CCV_NNC_EXEC_INVALID;
+	for (int i = 0; i < 5; i++)
+		if (!inputs[i] || !is_f32(inputs[i]))
+			return CCV_NNC_EXEC_INVALID;
+	if (!outputs[0] || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	const TV a = view_of(inputs[0]), scale = view_of(inputs[1]), b = view_of(outputs[0]);
+	size_t outer, inner;
+	int C;
+	if (!same_shape(a, b) || !b.contiguous || !bn_layout(a, scale, outer, C, inner))
+		return CCV_NNC_EXEC_INVALID;
+	for (int i = 2; i < 5; i++)
+		if (view_of(inputs[i]).count != (size_t)C)
+			return CCV_NNC_EXEC_INVALID;
+	cudaStream_t s = stream_of(stream_context);
+	if (cmd.info.bnorm.is_test)
+	{
+		RC(bn_fwd_test_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, inputs[3]->data.f32, inputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon));
+		return CCV_NNC_EXEC_SUCCESS;
+	}
+	if (output_size != 5 || !outputs[1] || !outputs[2] || !outputs[3] || !outputs[4])
+		return CCV_NNC_EXEC_INVALID;
+	// running mean / var are updated in place (:45-46)
+	if (inputs[3]->data.f32 != outputs[1]->data.f32 || inputs[4]->data.f32 != outputs[2]->data.f32)
+		return CCV_NNC_EXEC_INVALID;
+	if (view_of(outputs[3]).count != (size_t)C || view_of(outputs[4]).count != (size_t)C)
+		return CCV_NNC_EXEC_INVALID;
+	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
+	if (!ws)
+		return CCV_NNC_EXEC_OOM;
+	RC(bn_fwd_train_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, outputs[3]->data.f32, outputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, cmd.info.bnorm.momentum, ws));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// norm/ccv_nnc_batch_norm_cpu_ref.c:312-470: inputs[0] = g, [5] = a, [6] = scale, [13] = saved_mean, [14] = saved_inv_std;
+// outputs (h, dscale, dbias)
+int exec_bnorm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 15 || output_size < 1)
+		return CCV_NNC_EXEC_INVALID;
+	const ccv_nnc_tensor_t* const g_t = inputs[0];
+	const ccv_nnc_tensor_t* const a_t = inputs[5];
+	const ccv_nnc_tensor_t* const scale_t = inputs[6];
+	const ccv_nnc_tensor_t* const mean_t = inputs[13];
+	const ccv_nnc_tensor_t* const istd_t = inputs[14];
+	if (!g_t || !a_t || !scale_t || !mean_t || !istd_t)
+		return CCV_NNC_EXEC_INVALID;
+	ccv_nnc_tensor_t* const h_t = outputs[0];
+	ccv_nnc_tensor_t* const dscale_t = output_size > 1 ? outputs[1] : 0;
+	ccv_nnc_tensor_t* const dbias_t = output_size > 2 ? outputs[2] : 0;
+	const TV a = view_of(a_t), g = view_of(g_t), scale = view_of(scale_t);
+	size_t outer, inner;
+	int C;
+	if (!same_shape(a, g) || !g.contiguous || !bn_layout(a, scale, outer, C, inner))
+		return CCV_NNC_EXEC_INVALID;
+	if (h_t && (!same_shape(view_of(h_t), a) || !view_of(h_t).contiguous))
+		return CCV_NNC_EXEC_INVALID;
+	cudaStream_t s = stream_of(stream_context);
+	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
+	if (!ws)
+		return CCV_NNC_EXEC_OOM;
+	RC(bn_bwd_f32(s, g_t->data.f32, a_t->data.f32, scale_t->data.f32, mean_t->data.f32, istd_t->data.f32, h_t ? h_t->data.f32 : 0, dscale_t ? dscale_t->data.f32 : 0, dbias_t ? dbias_t->data.f32 : 0, outer, C, inner, ws));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ================================================================================================ RELU / EW
+int exec_relu_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	const TV a = view_of(inputs[0]), b = view_of(outputs[0]);
+	if (!a.contiguous || !b.contiguous || a.count != b.count)
+		return CCV_NNC_EXEC_INVALID;
+	RC(ew_relu_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, outputs[0]->data.f32, a.count));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+int exec_relu_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 3 || output_size < 1 || !inputs[0] || !inputs[2] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	const TV g = view_of(inputs[0]), b = view_of(inputs[2]), h = view_of(outputs[0]);
+	if (!g.contiguous || !b.contiguous || !h.contiguous || g.count != b.count || g.count != h.count)
+		return CCV_NNC_EXEC_INVALID;
+	RC(ew_relu_bwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, g.count));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ew/ccv_nnc_ew_cpu_ref.c:15-110,207-214
+int exec_ewsum_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 1 || output_size < 1 || !outputs[0] || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	const TV c = view_of(outputs[0]);
+	if (!c.contiguous || input_size > 64)
+		return CCV_NNC_EXEC_INVALID;
+	const float* ptrs[64];
+	for (int i = 0; i < input_size; i++)
+	{
+		if (!inputs[i] || !is_f32(inputs[i]))
+			return CCV_NNC_EXEC_INVALID;
+		const TV a = view_of(inputs[i]);
+		if (!a.contiguous || a.count != c.count)
+			return CCV_NNC_EXEC_INVALID;
+		ptrs[i] = inputs[i]->data.f32;
+	}
+	cudaStream_t s = stream_of(stream_context);
+	if (input_size == 1)
+	{
+		if (ptrs[0] != outputs[0]->data.f32 && cudaMemcpyAsync(outputs[0]->data.f32, ptrs[0], c.count * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+			return CCV_NNC_EXEC_INVALID;
+		return CCV_NNC_EXEC_SUCCESS;
+	}
+	RC(ew_sum_f32(s, ptrs, input_size, outputs[0]->data.f32, c.count));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ew/ccv_nnc_ew_cpu_ref.c:216-233: every output receives the incoming gradient (or ones if it is absent)
+int exec_ewsum_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t s = stream_of(stream_context);
+	for (int i = 0; i < output_size; i++)
+	{
+		if (!outputs[i])
+			continue;
+		const TV h = view_of(outputs[i]);
+		if (!h.contiguous || !is_f32(outputs[i]))
+			return CCV_NNC_EXEC_INVALID;
+		if (input_size < 1 || !inputs[0])
+			RC(ew_set_f32(s, outputs[i]->data.f32, h.count, 1.f));
+		else if (inputs[0]->data.f32 != outputs[i]->data.f32)
+		{
+			const TV g = view_of(inputs[0]);
+			if (!g.contiguous || g.count != h.count)
+				return CCV_NNC_EXEC_INVALID;
+			if (cudaMemcpyAsync(outputs[i]->data.f32, inputs[0]->data.f32, h.count * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+				return CCV_NNC_EXEC_INVALID;
+		}
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// broadcasting helper: c's 4-d shape drives the loop; an operand dimension of 1 broadcasts (stride 0)
+bool bcast_strides(const TV& c, const TV& x, int xs[4])
+{
+	int cd[4], cs[4], xd[4], xs0[4];
+	if (c.nd > 4 || x.nd > 4)
+		return false;
+	dims4(c, cd, cs);
+	dims4(x, xd, xs0);
+	for (int i = 0; i < 4; i++)
+	{
+		if (xd[i] == cd[i])
+			xs[i] = xd[i] == 1 ? 0 : xs0[i];
+		else if (xd[i] == 1)
+			xs[i] = 0;
+		else
+			return false;
+	}
+	return true;
+}
+
+// blas/ccv_nnc_add_cpu_ref.c:13-198: c = p * a + q * b, b optional, numpy-style broadcast of a and b into c
+int exec_add_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	const ccv_nnc_tensor_t* const b_t = input_size > 1 ? inputs[1] : 0;
+	const float p = cmd.info.blas.a[0], q = cmd.info.blas.a[1];
+	const TV a = view_of(inputs[0]), c = view_of(outputs[0]);
+	cudaStream_t s = stream_of(stream_context);
+	if (a.contiguous && c.contiguous && same_shape(a, c) && (!b_t || (view_of(b_t).contiguous && same_shape(view_of(b_t), c))))
+	{
+		RC(ew_axpby_f32(s, p, inputs[0]->data.f32, q, b_t ? b_t->data.f32 : 0, outputs[0]->data.f32, c.count));
+		return CCV_NNC_EXEC_SUCCESS;
+	}
+	int cd[4], cs[4], as[4], bs[4];
+	if (c.nd > 4)
+		return CCV_NNC_EXEC_INVALID;
+	dims4(c, cd, cs);
+	if (!bcast_strides(c, a, as) || (b_t && !bcast_strides(c, view_of(b_t), bs)))
+		return CCV_NNC_EXEC_INVALID;
+	RC(ew_axpby_bcast_f32(s, p, inputs[0]->data.f32, as, q, b_t ? b_t->data.f32 : 0, b_t ? bs : 0, outputs[0]->data.f32, cs, cd));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// gradient of a broadcast operand: scale * g summed over the broadcast axes
+int reduce_to(cudaStream_t s, const float scale, const ccv_nnc_tensor_t* const g_t, ccv_nnc_tensor_t* const out_t)
+{
+	const TV g = view_of(g_t), o = view_of(out_t);
+	if (!o.contiguous || g.nd > 4 || o.nd > 4)
+		return 1;
+	if (g.contiguous && same_shape(g, o))
+		return ew_axpby_f32(s, scale, g_t->data.f32, 0.f, 0, out_t->data.f32, o.count);
+	int gd[4], gs[4], od[4], os[4];
+	dims4(g, gd, gs);
+	dims4(o, od, os);
+	for (int i = 0; i < 4; i++)
+		if (od[i] != gd[i] && od[i] != 1)
+			return 1;
+	return reduce_sum_bcast_f32(s, g_t->data.f32, gd, gs, out_t->data.f32, od, scale, 0);
+}
+
+// blas/ccv_nnc_add_cpu_ref.c:200-330
+int exec_add_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t s = stream_of(stream_context);
+	const float pq[2] = { cmd.info.blas.a[0], cmd.info.blas.a[1] };
+	for (int i = 0; i < 2 && i < output_size; i++)
+	{
+		if (!outputs[i])
+			continue;
+		if (!is_f32(outputs[i]))
+			return CCV_NNC_EXEC_INVALID;
+		if (input_size < 1 || !inputs[0])
+		{
+			const TV o = view_of(outputs[i]);
+			if (!o.contiguous)
+				return CCV_NNC_EXEC_INVALID;
+			RC(ew_set_f32(s, outputs[i]->data.f32, o.count, pq[i]));
+		} else
+			RC(reduce_to(s, pq[i], inputs[0], outputs[i]));
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// blas/ccv_nnc_mul_cpu_ref.c: MUL c = p * a * b (broadcast); SCALAR_MUL c = p * a
+int exec_mul_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	if (!is_f32(inputs[0]) || !is_f32(inputs[1]) || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	const TV a = view_of(inputs[0]), b = view_of(inputs[1]), c = view_of(outputs[0]);
+	int cd[4], cs[4], as[4], bs[4];
+	if (c.nd > 4)
+		return CCV_NNC_EXEC_INVALID;
+	dims4(c, cd, cs);
+	if (!bcast_strides(c, a, as) || !bcast_strides(c, b, bs))
+		return CCV_NNC_EXEC_INVALID;
+	RC(ew_mul_bcast_f32(stream_of(stream_context), cmd.info.blas.a[0], inputs[0]->data.f32, as, inputs[1]->data.f32, bs, outputs[0]->data.f32, cs, cd));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// d(p a b)/da = p g b, d/db = p g a; only the same-shape (no broadcast) gradient is provided here
+int exec_mul_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 3)
+		return CCV_NNC_EXEC_INVALID;
+	cudaStream_t s = stream_of(stream_context);
+	const float p = cmd.info.blas.a[0];
+	for (int i = 0; i < 2 && i < output_size; i++)
+	{
+		if (!outputs[i])
+			continue;
+		const ccv_nnc_tensor_t* const other = inputs[2 - i]; // ha needs b (inputs[2]), hb needs a (inputs[1])
+		if (!other)
+			return CCV_NNC_EXEC_INVALID;
+		const TV o = view_of(outputs[i]), x = view_of(other);
+		if (!o.contiguous || !x.contiguous || !same_shape(o, x))
+			return CCV_NNC_EXEC_INVALID;
+		if (!inputs[0])
+			RC(ew_axpby_f32(s, p, other->data.f32, 0.f, 0, outputs[i]->data.f32, o.count));
+		else {
+			const TV g = view_of(inputs[0]);
+			if (!g.contiguous || !same_shape(g, o))
+				return CCV_NNC_EXEC_INVALID;
+			int d[4], st[4];
+			dims4(o, d, st);
+			RC(ew_mul_bcast_f32(s, p, inputs[0]->data.f32, st, other->data.f32, st, outputs[i]->data.f32, st, d));
+		}
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+int exec_scalar_mul_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	const TV a = view_of(inputs[0]), c = view_of(outputs[0]);
+	if (!a.contiguous || !c.contiguous || a.count != c.count)
+		return CCV_NNC_EXEC_INVALID;
+	RC(ew_axpby_f32(stream_of(stream_context), cmd.info.blas.a[0], inputs[0]->data.f32, 0.f, 0, outputs[0]->data.f32, c.count));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+int exec_scalar_mul_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (output_size < 1 || !outputs[0] || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	const TV h = view_of(outputs[0]);
+	if (!h.contiguous)
+		return CCV_NNC_EXEC_INVALID;
+	cudaStream_t s = stream_of(stream_context);
+	if (input_size < 1 || !inputs[0])
+		RC(ew_set_f32(s, outputs[0]->data.f32, h.count, cmd.info.blas.a[0]));
+	else {
+		if (!view_of(inputs[0]).contiguous || view_of(inputs[0]).count != h.count)
+			return CCV_NNC_EXEC_INVALID;
+		RC(ew_axpby_f32(s, cmd.info.blas.a[0], inputs[0]->data.f32, 0.f, 0, outputs[0]->data.f32, h.count));
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ================================================================================================ POOLING
+bool pool_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, const TV& a, const TV& b, PoolGeom& g)
+{
+	if (a.format != CCV_TENSOR_FORMAT_NHWC || b.format != CCV_TENSOR_FORMAT_NHWC)
+		return false;
+	if ((a.nd != 3 && a.nd != 4) || a.nd != b.nd)
+		return false;
+	const int ao = a.nd - 3, bo = b.nd - 3;
+	memset(&g, 0, sizeof(g));
+	g.N = a.nd == 4 ? a.dim[0] : 1;
+	if (b.nd == 4 && b.dim[0] != g.N)
+		return false;
+	g.H = a.dim[ao], g.W = a.dim[ao + 1], g.C = a.dim[ao + 2];
+	g.P = b.dim[bo], g.Q = b.dim[bo + 1];
+	if (b.dim[bo + 2] != g.C || a.stride[ao + 2] != 1 || b.stride[bo + 2] != 1)
+		return false;
+	g.an = a.nd == 4 ? a.stride[0] : 0, g.ah = a.stride[ao], g.aw = a.stride[ao + 1];
+	g.bn = b.nd == 4 ? b.stride[0] : 0, g.bh = b.stride[bo], g.bw = b.stride[bo + 1];
+	g.R = cmd.info.size.dim[0], g.S = cmd.info.size.dim[1];
+	g.stride_h = hint.stride.dim[0] > 0 ? hint.stride.dim[0] : 1;
+	g.stride_w = hint.stride.dim[1] > 0 ? hint.stride.dim[1] : 1;
+	g.pad_h = hint.border.begin[0], g.pad_w = hint.border.begin[1];
+	return g.R > 0 && g.S > 0;
+}
+
+// pool/ccv_nnc_max_pool_cpu_ref.c:13-59 / pool/ccv_nnc_avg_pool_cpu_ref.c:13-58 (all N images, unlike CPU_REF which
+// only walks image 0 -- SURVEY.md 0.6)
+template <int IS_MAX>
+int exec_pool_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	PoolGeom g;
+	if (!pool_geom(cmd, hint, view_of(inputs[0]), view_of(outputs[0]), g))
+		return CCV_NNC_EXEC_INVALID;
+	if (IS_MAX)
+		RC(pool_max_fwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, outputs[0]->data.f32));
+	else
+		RC(pool_avg_fwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, outputs[0]->data.f32));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// max: inputs (g, a, b) -> h; avg: inputs (g, ...) -> h
+template <int IS_MAX>
+int exec_pool_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	PoolGeom g;
+	if (!pool_geom(cmd, hint, view_of(outputs[0]), view_of(inputs[0]), g))
+		return CCV_NNC_EXEC_INVALID;
+	if (IS_MAX)
+	{
+		if (input_size < 3 || !inputs[1] || !inputs[2])
+			return CCV_NNC_EXEC_INVALID;
+		const TV a = view_of(inputs[1]), b = view_of(inputs[2]), gv = view_of(inputs[0]), h = view_of(outputs[0]);
+		// the kernel addresses a with h's strides and b with g's strides
+		if (!same_shape(a, h) || !same_shape(b, gv))
+			return CCV_NNC_EXEC_INVALID;
+		for (int i = 0; i < a.nd; i++)
+			if (a.stride[i] != h.stride[i])
+				return CCV_NNC_EXEC_INVALID;
+		for (int i = 0; i < b.nd; i++)
+			if (b.stride[i] != gv.stride[i])
+				return CCV_NNC_EXEC_INVALID;
+		RC(pool_max_bwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32));
+	} else
+		RC(pool_avg_bwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, outputs[0]->data.f32));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ================================================================================================ SOFTMAX / LOSSES
+bool rows_of(const TV& a, int& batch, int& count)
+{
+	if (!a.contiguous || a.nd < 1)
+		return false;
+	batch = a.nd < 2 ? 1 : a.dim[0];
+	count = (int)(a.count / (size_t)batch);
+	return true;
+}
+
+int exec_softmax_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	int batch, count;
+	const TV a = view_of(inputs[0]), b = view_of(outputs[0]);
+	if (!rows_of(a, batch, count) || !b.contiguous || !same_shape(a, b))
+		return CCV_NNC_EXEC_INVALID;
+	RC(softmax_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, outputs[0]->data.f32, batch, count));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+int exec_softmax_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 3 || output_size < 1 || !inputs[0] || !inputs[2] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	int batch, count;
+	const TV g = view_of(inputs[0]), b = view_of(inputs[2]), h = view_of(outputs[0]);
+	if (!rows_of(g, batch, count) || !b.contiguous || !h.contiguous || !same_shape(g, b) || !same_shape(g, h))
+		return CCV_NNC_EXEC_INVALID;
+	RC(softmax_bwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, batch, count));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// label tensor -> kind (0 fp32 index, 1 int32 index, 2 fp32 distribution), following the reference's "range" rule
+// (loss/ccv_nnc_categorical_crossentropy_cpu_ref.c:27-30)
+bool label_kind_of(const ccv_nnc_tensor_t* const b_t, const int batch, int& kind)
+{
+	const TV b = view_of(b_t);
+	if (!b.contiguous)
+		return false;
+	if (CCV_GET_DATA_TYPE(b_t->info.datatype) == CCV_32S)
+	{
+		kind = 1;
+		return true;
+	}
+	if (CCV_GET_DATA_TYPE(b_t->info.datatype) != CCV_32F)
+		return false;
+	int range;
+	if (b.nd > 1)
+		range = b.dim[b.nd - 1]; // ccv_nnc_tensor_get_c for the 2-d [batch, count] case
+	else
+		range = batch == 1 ? b.dim[0] : 1;
+	kind = range == 1 ? 0 : 2;
+	return true;
+}
+
+int exec_cce_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 2 || output_size < 1 || !inputs[0] || !inputs[1] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	int batch, count, kind;
+	if (!is_f32(inputs[0]) || !rows_of(view_of(inputs[0]), batch, count) || !label_kind_of(inputs[1], batch, kind) || !view_of(outputs[0]).contiguous)
+		return CCV_NNC_EXEC_INVALID;
+	RC(cce_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.ptr, kind, outputs[0]->data.f32, batch, count, cmd.info.label_smoothing.trim0, cmd.info.label_smoothing.trim1));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// inputs (g, a, b) -> h
+int exec_cce_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 3 || output_size < 1 || !inputs[1] || !inputs[2] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	int batch, count, kind;
+	if (!is_f32(inputs[1]) || !rows_of(view_of(inputs[1]), batch, count) || !label_kind_of(inputs[2], batch, kind) || !view_of(outputs[0]).contiguous || !same_shape(view_of(inputs[1]), view_of(outputs[0])))
+		return CCV_NNC_EXEC_INVALID;
+	RC(cce_bwd_f32(stream_of(stream_context), inputs[0] ? inputs[0]->data.f32 : 0, inputs[1]->data.f32, inputs[2]->data.ptr, kind, outputs[0]->data.f32, batch, count, cmd.info.label_smoothing.trim0, cmd.info.label_smoothing.trim1));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// softmax_loss/ccv_nnc_softmax_crossentropy_cpu_ref.c:13-170: inputs (a, label) -> outputs (c, d)
+int exec_softmax_cce_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 2 || output_size != 2 || !inputs[0] || !inputs[1] || !outputs[1])
+		return CCV_NNC_EXEC_INVALID;
+	int batch, count, kind;
+	if (!is_f32(inputs[0]) || !rows_of(view_of(inputs[0]), batch, count) || !label_kind_of(inputs[1], batch, kind) || !view_of(outputs[1]).contiguous || !same_shape(view_of(inputs[0]), view_of(outputs[1])))
+		return CCV_NNC_EXEC_INVALID;
+	RC(softmax_cce_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.ptr, kind, outputs[0] ? outputs[0]->data.f32 : 0, outputs[1]->data.f32, batch, count, cmd.info.label_smoothing.trim0, cmd.info.label_smoothing.trim1));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// inputs: [0] = g (may be NULL), [3] = label, [5] = d; outputs[0] = h (:172-181)
+int exec_softmax_cce_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 6 || output_size < 1 || !inputs[3] || !inputs[5] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	int batch, count, kind;
+	if (!is_f32(inputs[5]) || !rows_of(view_of(inputs[5]), batch, count) || !label_kind_of(inputs[3], batch, kind) || !view_of(outputs[0]).contiguous || !same_shape(view_of(inputs[5]), view_of(outputs[0])))
+		return CCV_NNC_EXEC_INVALID;
+	RC(softmax_cce_bwd_f32(stream_of(stream_context), inputs[0] ? inputs[0]->data.f32 : 0, inputs[3]->data.ptr, kind, inputs[5]->data.f32, outputs[0]->data.f32, batch, count, cmd.info.label_smoothing.trim0, cmd.info.label_smoothing.trim1));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ================================================================================================ SGD
+// sgd/ccv_nnc_sgd_cpu_ref.c:16-126: inputs (g, a, m) -> outputs (b, n)
+int exec_sgd_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 3 || output_size != 2)
+		return CCV_NNC_EXEC_INVALID;
+	size_t count = 0;
+	for (int i = 0; i < 3; i++)
+	{
+		if (!inputs[i] || !is_f32(inputs[i]) || !view_of(inputs[i]).contiguous)
+			return CCV_NNC_EXEC_INVALID;
+		if (i == 0)
+			count = view_of(inputs[0]).count;
+		else if (view_of(inputs[i]).count != count)
+			return CCV_NNC_EXEC_INVALID;
+	}
+	for (int i = 0; i < 2; i++)
+		if (!outputs[i] || !is_f32(outputs[i]) || !view_of(outputs[i]).contiguous || view_of(outputs[i]).count != count)
+			return CCV_NNC_EXEC_INVALID;
+	if (cmd.info.sgd.nesterov && cmd.info.sgd.dampening != 0)
+		return CCV_NNC_EXEC_INVALID;
+	RC(sgd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, outputs[1]->data.f32, count, cmd.info.sgd.nesterov, cmd.info.sgd.rate, cmd.info.sgd.scale, cmd.info.sgd.decay, cmd.info.sgd.momentum, cmd.info.sgd.dampening));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+int exec_invalid(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return CCV_NNC_EXEC_INVALID; // e.g. SGD backward (sgd/ccv_nnc_sgd_cpu_ref.c:128-131)
+}
+
+// ================================================================================================ SET / MOVES
+// util/ccv_nnc_util_cpu_ref.c:637-664
+int exec_set_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t s = stream_of(stream_context);
+	const float v = cmd.cmd == CCV_NNC_SET_BACKWARD ? 0.f : cmd.info.blas.a[0];
+	for (int i = 0; i < output_size; i++)
+	{
+		if (!outputs[i])
+			continue;
+		const TV o = view_of(outputs[i]);
+		if (!o.contiguous)
+			return CCV_NNC_EXEC_INVALID;
+		const int dt = CCV_GET_DATA_TYPE(outputs[i]->info.datatype);
+		if (v == 0.f)
+		{
+			if (cudaMemsetAsync(outputs[i]->data.u8, 0, o.count * dtype_size(dt), s) != cudaSuccess)
+				return CCV_NNC_EXEC_INVALID;
+		} else if (dt == CCV_32F)
+			RC(ew_set_f32(s, outputs[i]->data.f32, o.count, v));
+		else if (dt == CCV_32S) {
+			const int iv = (int)v;
+			float fv;
+			memcpy(&fv, &iv, 4);
+			RC(ew_set_f32(s, outputs[i]->data.f32, o.count, fv));
+		} else
+			return CCV_NNC_EXEC_INVALID;
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// copy between two tensors of equal shape and datatype: memcpy when both are packed, strided kernel otherwise
+int copy_tensor(cudaStream_t s, const ccv_nnc_tensor_t* const a_t, ccv_nnc_tensor_t* const b_t)
+{
+	const TV a = view_of(a_t), b = view_of(b_t);
+	if (a.datatype != b.datatype || a.count != b.count)
+		return 1;
+	const size_t es = dtype_size(a.datatype);
+	const int a_gpu = CCV_TENSOR_GET_MEMORY(a_t->info.type) == CCV_TENSOR_GPU_MEMORY, b_gpu = CCV_TENSOR_GET_MEMORY(b_t->info.type) == CCV_TENSOR_GPU_MEMORY;
+	if (a.contiguous && b.contiguous)
+	{
+		const cudaMemcpyKind kind = a_gpu ? (b_gpu ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost) : (b_gpu ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost);
+		const cudaError_t e = cudaMemcpyAsync(b.p, a.p, a.count * es, kind, s);
+		if (e != cudaSuccess)
+		{
+			set_last_error("cudaMemcpyAsync(data transfer)", e);
+			return -1;
+		}
+		count_launch(0);
+		return 0;
+	}
+	if (!a_gpu || !b_gpu || a.nd > 4 || !same_shape(a, b))
+		return 1;
+	int ad[4], as[4], bd[4], bs[4];
+	dims4(a, ad, as);
+	dims4(b, bd, bs);
+	return copy_strided(s, a.p, as, b.p, bs, ad, (int)es);
+}
+
+// util/ccv_nnc_util_cpu_ref.c:596-617
+int exec_data_transfer(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t s = stream_of(stream_context);
+	const int n = input_size < output_size ? input_size : output_size;
+	for (int i = 0; i < n; i++)
+		if (inputs[i] && outputs[i] && inputs[i] != outputs[i])
+			RC(copy_tensor(s, inputs[i], outputs[i]));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// util/ccv_nnc_util_cpu_ref.c:996-1082: same format = copy; NHWC <-> NCHW = copy over permuted strides
+int exec_format_transform(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t s = stream_of(stream_context);
+	for (int i = 0; i < output_size && i < input_size; i++)
+	{
+		if (!inputs[i] || !outputs[i])
+			continue;
+		const TV a = view_of(inputs[i]), b = view_of(outputs[i]);
+		if (a.dim[0] == 0 || b.dim[0] == 0)
+			continue;
+		if (a.format == b.format)
+		{
+			RC(copy_tensor(s, inputs[i], outputs[i]));
+			continue;
+		}
+		if (a.datatype != b.datatype || a.nd != b.nd || (a.nd != 3 && a.nd != 4))
+			return CCV_NNC_EXEC_INVALID;
+		// express both in (n, c, h, w) index order
+		int d[4], as[4], bs[4];
+		const int o = a.nd - 3;
+		auto nchw_of = [&](const TV& t, int dim[4], int st[4]) -> bool {
+			dim[0] = t.nd == 4 ? t.dim[0] : 1, st[0] = t.nd == 4 ? t.stride[0] : 0;
+			if (t.format == CCV_TENSOR_FORMAT_NHWC)
+				dim[1] = t.dim[o + 2], st[1] = t.stride[o + 2], dim[2] = t.dim[o], st[2] = t.stride[o], dim[3] = t.dim[o + 1], st[3] = t.stride[o + 1];
+			else if (t.format == CCV_TENSOR_FORMAT_NCHW)
+				dim[1] = t.dim[o], st[1] = t.stride[o], dim[2] = t.dim[o + 1], st[2] = t.stride[o + 1], dim[3] = t.dim[o + 2], st[3] = t.stride[o + 2];
+			else
+				return false;
+			return true;
+		};
+		int bd[4];
+		if (!nchw_of(a, d, as) || !nchw_of(b, bd, bs))
+			return CCV_NNC_EXEC_INVALID;
+		for (int k = 0; k < 4; k++)
+			if (d[k] != bd[k])
+				return CCV_NNC_EXEC_INVALID;
+		RC(copy_strided(s, a.p, as, b.p, bs, d, (int)dtype_size(a.datatype)));
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// util/ccv_nnc_util_cpu_ref.c:1102-1180: swap two axes
+int exec_transpose(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t s = stream_of(stream_context);
+	for (int i = 0; i < output_size && i < input_size; i++)
+	{
+		if (!inputs[i] || !outputs[i])
+			continue;
+		const TV a = view_of(inputs[i]), b = view_of(outputs[i]);
+		if (a.nd != b.nd || a.nd > 4 || a.datatype != b.datatype)
+			return CCV_NNC_EXEC_INVALID;
+		const int ax0 = cmd.info.transpose.axis[0], ax1 = cmd.info.transpose.axis[1];
+		if (ax0 < 0 || ax1 < 0 || ax0 >= a.nd || ax1 >= a.nd)
+			return CCV_NNC_EXEC_INVALID;
+		int d[4], as[4], bs[4];
+		const int off = 4 - a.nd;
+		for (int k = 0; k < 4; k++)
+		{
+			if (k < off)
+			{
+				d[k] = 1, as[k] = bs[k] = 0;
+				continue;
+			}
+			const int bk = k - off; // index in b
+			const int ak = bk == ax0 ? ax1 : (bk == ax1 ? ax0 : bk);
+			if (b.dim[bk] != a.dim[ak])
+				return CCV_NNC_EXEC_INVALID;
+			d[k] = b.dim[bk], bs[k] = b.stride[bk], as[k] = a.stride[ak];
+		}
+		RC(copy_strided(s, a.p, as, b.p, bs, d, (int)dtype_size(a.datatype)));
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// util/ccv_nnc_util_cpu_ref.c:1200-1260
+int exec_datatype_conversion(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t s = stream_of(stream_context);
+	for (int i = 0; i < output_size && i < input_size; i++)
+	{
+		if (!inputs[i] || !outputs[i])
+			continue;
+		const TV a = view_of(inputs[i]), b = view_of(outputs[i]);
+		if (a.count != b.count)
+			return CCV_NNC_EXEC_INVALID;
+		if (a.datatype == b.datatype)
+		{
+			RC(copy_tensor(s, inputs[i], outputs[i]));
+			continue;
+		}
+		if (!a.contiguous || !b.contiguous || dtype_code(a.datatype) < 0 || dtype_code(b.datatype) < 0)
+			return CCV_NNC_EXEC_INVALID;
+		RC(convert_dtype(s, a.p, dtype_code(a.datatype), b.p, dtype_code(b.datatype), a.count));
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+void fill(ccv_nnc_cmd_backend_registry_t* const registry, const int formats, const int datatypes, const int algorithms, const ccv_nnc_cmd_exec_f exec)
+{
+	registry->tensor_formats = formats;
+	registry->tensor_datatypes = datatypes;
+	registry->tensor_memory = CCV_TENSOR_GPU_MEMORY;
+	registry->algorithms = algorithms;
+	registry->exec = exec;
+	registry->autotune = 0;
+	registry->aux = 0;
+}
+
+const int ALL_FORMATS = CCV_TENSOR_FORMAT_NCHW | CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_CHWN;
+
+} // namespace
+
+// implemented in sm100_backend_ext.cu (attention, layer / rms norm, upsample, allreduce)
+extern "C" {
+int ccv_nnc_sm100_exec_sdpa_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_exec_sdpa_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_exec_lnorm_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_exec_lnorm_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_exec_rmsnorm_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_exec_rmsnorm_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_exec_upsample_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_exec_upsample_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_exec_allreduce(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+}
+
+// ================================================================================================ registration
+#define REGISTER_SM100(cmd) extern "C" void _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(ccv_nnc_cmd_backend_registry_t* const registry)
+
+REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_forw); }
+REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); }
+REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); }
+REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); }
+REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_forw); }
+REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_back); }
+REGISTER_SM100(CCV_NNC_SOFTMAX_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_forw); }
+REGISTER_SM100(CCV_NNC_SOFTMAX_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_back); }
+REGISTER_SM100(CCV_NNC_BATCH_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_bnorm_forw); }
+REGISTER_SM100(CCV_NNC_BATCH_NORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_bnorm_back); }
+REGISTER_SM100(CCV_NNC_LAYER_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_lnorm_forw); }
+REGISTER_SM100(CCV_NNC_LAYER_NORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_lnorm_back); }
+REGISTER_SM100(CCV_NNC_RMSNORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_rmsnorm_forw); }
+REGISTER_SM100(CCV_NNC_RMSNORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_rmsnorm_back); }
+REGISTER_SM100(CCV_NNC_EWSUM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_ewsum_forw); }
+REGISTER_SM100(CCV_NNC_EWSUM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_ewsum_back); }
+REGISTER_SM100(CCV_NNC_ADD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_add_forw); }
+REGISTER_SM100(CCV_NNC_ADD_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_add_back); }
+REGISTER_SM100(CCV_NNC_MUL_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_mul_forw); }
+REGISTER_SM100(CCV_NNC_MUL_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_mul_back); }
+REGISTER_SM100(CCV_NNC_SCALAR_MUL_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_scalar_mul_forw); }
+REGISTER_SM100(CCV_NNC_SCALAR_MUL_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_scalar_mul_back); }
+REGISTER_SM100(CCV_NNC_RELU_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_relu_forw); }
+REGISTER_SM100(CCV_NNC_RELU_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_relu_back); }
+REGISTER_SM100(CCV_NNC_MAX_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, 1, exec_pool_forw<1>); }
+REGISTER_SM100(CCV_NNC_MAX_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, 1, exec_pool_back<1>); }
+REGISTER_SM100(CCV_NNC_AVERAGE_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, 1, exec_pool_forw<0>); }
+REGISTER_SM100(CCV_NNC_AVERAGE_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, 1, exec_pool_back<0>); }
+REGISTER_SM100(CCV_NNC_UPSAMPLE_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, 1, ccv_nnc_sm100_exec_upsample_forw); }
+REGISTER_SM100(CCV_NNC_UPSAMPLE_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, 1, ccv_nnc_sm100_exec_upsample_back); }
+REGISTER_SM100(CCV_NNC_SET_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_set_forw); }
+REGISTER_SM100(CCV_NNC_SET_BACKWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_set_forw); }
+REGISTER_SM100(CCV_NNC_DATA_TRANSFER_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S | CCV_8U, 1, exec_data_transfer); registry->tensor_memory = CCV_TENSOR_CPU_MEMORY | CCV_TENSOR_GPU_MEMORY; }
+REGISTER_SM100(CCV_NNC_DATA_TRANSFER_BACKWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S | CCV_8U, 1, exec_data_transfer); registry->tensor_memory = CCV_TENSOR_CPU_MEMORY | CCV_TENSOR_GPU_MEMORY; }
+REGISTER_SM100(CCV_NNC_FORMAT_TRANSFORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_32S | CCV_16F | CCV_16BF | CCV_8U, 1, exec_format_transform); }
+REGISTER_SM100(CCV_NNC_FORMAT_TRANSFORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_32S | CCV_16F | CCV_16BF | CCV_8U, 1, exec_format_transform); }
+REGISTER_SM100(CCV_NNC_TRANSPOSE_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_transpose); }
+REGISTER_SM100(CCV_NNC_TRANSPOSE_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_transpose); }
+REGISTER_SM100(CCV_NNC_DATATYPE_CONVERSION_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF, 1, exec_datatype_conversion); }
+REGISTER_SM100(CCV_NNC_DATATYPE_CONVERSION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF, 1, exec_datatype_conversion); }
+REGISTER_SM100(CCV_NNC_SGD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_sgd_forw); }
+REGISTER_SM100(CCV_NNC_SGD_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_invalid); }
+REGISTER_SM100(CCV_NNC_CATEGORICAL_CROSSENTROPY_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_cce_forw); }
+REGISTER_SM100(CCV_NNC_CATEGORICAL_CROSSENTROPY_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_cce_back); }
+REGISTER_SM100(CCV_NNC_SOFTMAX_CROSSENTROPY_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_softmax_cce_forw); }
+REGISTER_SM100(CCV_NNC_SOFTMAX_CROSSENTROPY_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_softmax_cce_back); }
+REGISTER_SM100(CCV_NNC_COMM_ALLREDUCE_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_allreduce); }
+REGISTER_SM100(CCV_NNC_COMM_ALLREDUCE_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_allreduce); }

@@ -1,0 +1,279 @@
+"""ResNet-50 (the v1d variant of the reference's trainer, bin/nnc/imagenet.c:17-95) as a flat, topologically ordered
+list of nnc commands on CCV_NNC_BACKEND_GPU_SM100 -- the same command sequence ccv_cnnp_model_fit ends up issuing
+through ccv_nnc_graph_run (lib/nnc/ccv_cnnp_model.c:1533-1570): forward, softmax + categorical cross-entropy,
+backward, and one nesterov-SGD command per parameter (bin/nnc/imagenet.c:314-317).
+
+ccv's symbolic graph, autodiff and memory planner are NOT rebuilt here (out of scope); this module
+is only the driver that exercises the hot path at BASELINE.json's headline configuration.  NHWC, fp32.
+
+Data parallelism: one process per GPU holds one batch shard and a full replica; all gradients live in ONE
+flat buffer so that the exchange step is a single sum-allreduce, after which every replica runs the same SGD commands
+(sgd.scale = 1 / global_batch carries the averaging, bin/nnc/imagenet.c:474-475)."""
+import numpy as np
+
+from . import abi, nnc
+
+
+class GpuFactory(object):
+    """Allocates ccv_nnc_tensor_t on the GPU through the backend library. (The oracle-side twin, used by the tests and by
+    bench.py's cpu_baseline leg to run the identical command list on CCV_NNC_BACKEND_CPU_REF, lives in oracle/.)"""
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def alloc(self, shape, datatype=abi.CCV_32F):
+        return nnc.gpu_tensor(list(shape), abi.CCV_TENSOR_FORMAT_NHWC, datatype, self.device)
+
+    def alias(self, base, elem_offset, shape, datatype=abi.CCV_32F):
+        return nnc.gpu_tensor(list(shape), abi.CCV_TENSOR_FORMAT_NHWC, datatype, self.device, base.data_ptr + elem_offset * 4)
+
+
+class Net(object):
+    def __init__(self, batch, image=224, classes=1000, device=0, global_batch=None, learn_rate=0.04, weight_decay=1e-4, seed=0, algorithm=-1, factory=None):
+        self.batch, self.image, self.classes, self.device = batch, image, classes, device
+        self.factory = factory if factory is not None else GpuFactory(device)
+        self.global_batch = global_batch or batch
+        self.learn_rate, self.weight_decay = learn_rate, weight_decay
+        self.algorithm = algorithm
+        self.rng = np.random.RandomState(seed)
+        self.tensors = []       # everything allocated (for free())
+        self.params = []        # (name, shape, decay) in creation order
+        self.param_init = {}
+        self.fwd, self.bwd, self.opt = [], [], []   # node lists: (cmd, hint, flags, inputs, outputs)
+        self.flops = 0
+        self.bytes_alloc = 0
+        self._pending_params = []
+        self._build()
+
+    # ------------------------------------------------------------------------------------------------ allocation
+    def alloc(self, shape, datatype=abi.CCV_32F):
+        t = self.factory.alloc(shape, datatype)
+        self.tensors.append(t)
+        self.bytes_alloc += int(np.prod(shape)) * 4
+        return t
+
+    def alias(self, base, elem_offset, shape):
+        t = self.factory.alias(base, elem_offset, shape)
+        self.tensors.append(t)
+        return t
+
+    def param(self, name, shape, init, decay):
+        """Parameters, their gradients and momenta are carved out of three flat buffers once all shapes are known."""
+        self._pending_params.append((name, tuple(shape), init, decay))
+        return len(self._pending_params) - 1
+
+    def _materialise_params(self):
+        offs, total = [], 0
+        for _, shape, _, _ in self._pending_params:
+            offs.append(total)
+            n = int(np.prod(shape))
+            total += (n + 63) // 64 * 64  # 256-byte aligned slices: TMA / 128-bit access friendly
+        self.flat_count = total
+        self.w_flat, self.g_flat, self.m_flat = (self.alloc([total]) for _ in range(3))
+        host = np.zeros((total,), np.float32)
+        self.w, self.g, self.m = [], [], []
+        for (name, shape, init, decay), o in zip(self._pending_params, offs):
+            n = int(np.prod(shape))
+            host[o:o + n] = init.reshape(-1)
+            for flat, lst in ((self.w_flat, self.w), (self.g_flat, self.g), (self.m_flat, self.m)):
+                lst.append(self.alias(flat, o, shape))
+            self.params.append((name, shape, decay))
+        self.w_flat.upload(host)
+        self.m_flat.upload(np.zeros((total,), np.float32))
+        self.g_flat.upload(np.zeros((total,), np.float32))
+        self.param_host = host
+        self.param_offsets = offs
+
+    # ------------------------------------------------------------------------------------------------ layers
+    def _conv(self, x, xs, cin, cout, k, stride, pad, bias, name, need_dx=True):
+        """CONVOLUTION_FORWARD / BACKWARD pair. Returns (y, y_shape)."""
+        N, H, W, _ = xs
+        P, Q = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        fan_in = cin * k * k
+        w = self.param(name + ".w", (cout, k, k, cin), (self.rng.standard_normal((cout, k, k, cin)) * np.sqrt(2.0 / fan_in)).astype(np.float32), self.weight_decay)
+        b = self.param(name + ".b", (cout,), np.zeros((cout,), np.float32), 0.0) if bias else None
+        y = self.alloc((N, P, Q, cout))
+        self.flops += 2 * N * P * Q * cout * cin * k * k * (3 if need_dx else 2)
+        rec = dict(kind="conv", x=x, y=y, w=w, b=b, cin=cin, cout=cout, k=k, hint=abi.hint((stride, stride), (pad, pad)), need_dx=need_dx, xs=xs, name=name)
+        self.layers.append(rec)
+        return y, (N, P, Q, cout)
+
+    def _bn(self, x, xs, name, relu):
+        C = xs[-1]
+        scale = self.param(name + ".scale", (1, 1, 1, C), np.ones((1, 1, 1, C), np.float32), 0.0)
+        bias = self.param(name + ".bias", (1, 1, 1, C), np.zeros((1, 1, 1, C), np.float32), 0.0)
+        mean, var = self.alloc((1, 1, 1, C)), self.alloc((1, 1, 1, C))
+        mean.upload(np.zeros((C,), np.float32)), var.upload(np.ones((C,), np.float32))
+        y = self.alloc(xs)
+        rec = dict(kind="bn", x=x, y=y, scale=scale, bias=bias, mean=mean, var=var, sm=self.alloc((1, 1, 1, C)), sis=self.alloc((1, 1, 1, C)), relu=relu, xs=xs, name=name)
+        self.layers.append(rec)
+        return y
+
+    def _block(self, x, xs, filters, expansion, stride, projection, name):
+        N, H, W, C = xs
+        short, short_s = x, xs
+        rec_short = []
+        start = len(self.layers)
+        if projection:
+            if stride > 1:
+                ps = (N, H // stride, W // stride, C)
+                p = self.alloc(ps)
+                self.layers.append(dict(kind="avgpool", x=x, y=p, k=stride, hint=abi.hint((stride, stride), (0, 0)), xs=xs, ys=ps, name=name + ".avgdown"))
+                short, short_s = p, ps
+            short, short_s = self._conv(short, short_s, C, filters * expansion, 1, 1, 0, False, name + ".conv0")
+        branch_end = len(self.layers)
+        o, os_ = self._conv(x, xs, C, filters, 1, 1, 0, True, name + ".conv1")
+        o = self._bn(o, os_, name + ".bn1", True)
+        o, os_ = self._conv(o, os_, filters, filters, 3, stride, 1, True, name + ".conv2")
+        o = self._bn(o, os_, name + ".bn2", True)
+        o, os_ = self._conv(o, os_, filters, filters * expansion, 1, 1, 0, True, name + ".conv3")
+        o = self._bn(o, os_, name + ".bn3", False)
+        y = self.alloc(os_)
+        self.layers.append(dict(kind="block_end", main=o, short=short, y=y, x=x, xs=xs, ys=os_, short_range=(start, branch_end), main_range=(branch_end, len(self.layers)), name=name))
+        return y, os_
+
+    # ------------------------------------------------------------------------------------------------ build
+    def _build(self):
+        N, S = self.batch, self.image
+        self.layers = []
+        self.input = self.alloc((N, S, S, 3))
+        self.labels = self.alloc((N,), datatype=abi.CCV_32S)
+        x, xs = self.input, (N, S, S, 3)
+        # stem: 3x3/2 (3->32), 3x3 (32->32), 3x3 (32->64), each + BN + ReLU, then 3x3/2 max pool (imagenet.c:73-84)
+        for i, (cin, cout, st) in enumerate(((3, 32, 2), (32, 32, 1), (32, 64, 1))):
+            x, xs = self._conv(x, xs, cin, cout, 3, st, 1, False, "stem.conv%d" % i, need_dx=i > 0)
+            x = self._bn(x, xs, "stem.bn%d" % i, True)
+        ps = (N, (xs[1] + 2 - 3) // 2 + 1, (xs[2] + 2 - 3) // 2 + 1, xs[3])
+        p = self.alloc(ps)
+        self.layers.append(dict(kind="maxpool", x=x, y=p, k=3, hint=abi.hint((2, 2), (1, 1)), xs=xs, ys=ps, name="stem.pool"))
+        x, xs = p, ps
+        for li, (filters, stride, blocks) in enumerate(((64, 1, 3), (128, 2, 4), (256, 2, 6), (512, 2, 3))):
+            for bi in range(blocks):
+                x, xs = self._block(x, xs, filters, 4, stride if bi == 0 else 1, bi == 0, "layer%d.block%d" % (li + 1, bi))
+        # global average pool, flatten, dense 1000 (+bias), softmax (imagenet.c:89-93)
+        gs = (N, 1, 1, xs[3])
+        gp = self.alloc(gs)
+        self.layers.append(dict(kind="avgpool", x=x, y=gp, k=xs[1], hint=abi.hint((1, 1), (0, 0)), xs=xs, ys=gs, name="global_pool"))
+        feat = xs[3]
+        # ccv_cnnp_dense: w = [out, in] used with transpose_b (lib/nnc/ccv_cnnp_model_addons.c:1360-1373)
+        dw = self.param("fc.w", (self.classes, feat), (self.rng.standard_normal((self.classes, feat)) * np.sqrt(1.0 / feat)).astype(np.float32), self.weight_decay)
+        db = self.param("fc.b", (self.classes,), np.zeros((self.classes,), np.float32), 0.0)
+        self.flops += 2 * N * feat * self.classes * 3
+        self._materialise_params()
+        self.feat_view = self.alias(gp, 0, (N, feat))  # flatten = alias (ccv_cnnp_flatten)
+        self.logits, self.probs, self.loss = self.alloc((N, self.classes)), self.alloc((N, self.classes)), self.alloc((N,))
+        self._emit(dw, db)
+
+    def _node(self, lst, cmd, hint, flags, inputs, outputs):
+        lst.append((cmd, hint, flags, inputs, outputs))
+
+    def _emit(self, fc_w, fc_b):
+        W, G = self.w, self.g
+        A = self.algorithm
+        f = self.fwd
+        for L in self.layers:
+            k = L["kind"]
+            if k == "conv":
+                ins = [L["x"], W[L["w"]]] + ([W[L["b"]]] if L["b"] is not None else [])
+                self._node(f, nnc.CMD_CONVOLUTION_FORWARD(1, L["cout"], L["k"], L["k"], L["cin"], algorithm=A), L["hint"], 0, ins, [L["y"]])
+            elif k == "bn":
+                self._node(f, nnc.CMD_BATCH_NORM_FORWARD(1e-4, 0, 0.9), None, 0, [L["x"], W[L["scale"]], W[L["bias"]], L["mean"], L["var"]], [L["y"], L["mean"], L["var"], L["sm"], L["sis"]])
+                if L["relu"]:
+                    self._node(f, nnc.CMD_RELU_FORWARD(), None, 0, [L["y"]], [L["y"]])
+            elif k == "avgpool":
+                self._node(f, nnc.CMD_AVERAGE_POOL_FORWARD(L["k"], L["k"]), L["hint"], 0, [L["x"]], [L["y"]])
+            elif k == "maxpool":
+                self._node(f, nnc.CMD_MAX_POOL_FORWARD(L["k"], L["k"]), L["hint"], 0, [L["x"]], [L["y"]])
+            elif k == "block_end":
+                self._node(f, nnc.CMD_EWSUM_FORWARD(), None, 0, [L["main"], L["short"]], [L["y"]])
+                self._node(f, nnc.CMD_RELU_FORWARD(), None, 0, [L["y"]], [L["y"]])
+        self._node(f, nnc.CMD_GEMM_FORWARD((0, 0), (0, 1), algorithm=A), None, 0, [self.feat_view, W[fc_w], W[fc_b]], [self.logits])
+        self._node(f, nnc.CMD_SOFTMAX_FORWARD(), None, 0, [self.logits], [self.probs])
+        self._node(f, nnc.CMD_CATEGORICAL_CROSSENTROPY_FORWARD(), None, 0, [self.probs, self.labels], [self.loss])
+        # ---------------------------------------------------------------- backward (reverse topological order)
+        b = self.bwd
+        g_probs, g_logits = self.alloc((self.batch, self.classes)), self.alloc((self.batch, self.classes))
+        self._node(b, nnc.CMD_CATEGORICAL_CROSSENTROPY_BACKWARD(), None, 0, [None, self.probs, self.labels], [g_probs])
+        self._node(b, nnc.CMD_SOFTMAX_BACKWARD(), None, 0, [g_probs, None, self.probs], [g_logits])
+        g_feat = self.alloc(self.layers[-1]["ys"])
+        g_feat_view = self.alias(g_feat, 0, (self.batch, self.layers[-1]["ys"][3]))
+        self._node(b, nnc.CMD_GEMM_BACKWARD((0, 0), (0, 1), algorithm=A), None, 0, [g_logits, self.feat_view, W[fc_w]], [g_feat_view, G[fc_w], G[fc_b]])
+        grad = {id(self.layers[-1]["y"]): g_feat}   # gradient tensor of each activation, keyed by the activation
+
+        def grad_of(t):
+            return grad[id(t)]
+
+        def set_grad(t, shape):
+            gt = self.alloc(shape)
+            grad[id(t)] = gt
+            return gt
+
+        def back_layer(L):
+            k = L["kind"]
+            if k == "conv":
+                gy = grad_of(L["y"])
+                gx = set_grad(L["x"], L["xs"]) if L["need_dx"] else None
+                outs = [gx, G[L["w"]]] + ([G[L["b"]]] if L["b"] is not None else [])
+                self._node(b, nnc.CMD_CONVOLUTION_BACKWARD(1, L["cout"], L["k"], L["k"], L["cin"], algorithm=A), L["hint"], 0, [gy, L["x"], W[L["w"]]], outs)
+            elif k == "bn":
+                gy = grad_of(L["y"])
+                if L["relu"]:
+                    self._node(b, nnc.CMD_RELU_BACKWARD(), None, 0, [gy, None, L["y"]], [gy])
+                gx = set_grad(L["x"], L["xs"])
+                ins = [gy] + [None] * 4 + [L["x"], W[L["scale"]]] + [None] * 6 + [L["sm"], L["sis"]]
+                self._node(b, nnc.CMD_BATCH_NORM_BACKWARD(1e-4, 0, 0.9), None, 0, ins, [gx, G[L["scale"]], G[L["bias"]]])
+            elif k == "avgpool":
+                gx = set_grad(L["x"], L["xs"])
+                self._node(b, nnc.CMD_AVERAGE_POOL_BACKWARD(L["k"], L["k"]), L["hint"], 0, [grad_of(L["y"])], [gx])
+            elif k == "maxpool":
+                gx = set_grad(L["x"], L["xs"])
+                self._node(b, nnc.CMD_MAX_POOL_BACKWARD(L["k"], L["k"]), L["hint"], 0, [grad_of(L["y"]), L["x"], L["y"]], [gx])
+
+        i = len(self.layers) - 1
+        while i >= 0:
+            L = self.layers[i]
+            if L["kind"] != "block_end":
+                back_layer(L)
+                i -= 1
+                continue
+            gy = grad_of(L["y"])
+            self._node(b, nnc.CMD_RELU_BACKWARD(), None, 0, [gy, None, L["y"]], [gy])
+            # EWSUM backward hands the same gradient to both branches (ew/ccv_nnc_ew_cpu_ref.c:216-233): alias, no copy
+            grad[id(L["main"])] = gy
+            grad[id(L["short"])] = gy
+            m0, m1 = L["main_range"]
+            for j in range(m1 - 1, m0 - 1, -1):
+                back_layer(self.layers[j])
+            g_main = grad_of(L["x"])
+            s0, s1 = L["short_range"]
+            if s1 > s0:
+                del grad[id(L["x"])]
+                for j in range(s1 - 1, s0 - 1, -1):
+                    back_layer(self.layers[j])
+                g_short = grad_of(L["x"])
+            else:
+                g_short = gy
+            # the block input feeds both branches: its gradient is their sum
+            self._node(b, nnc.CMD_EWSUM_FORWARD(), None, 0, [g_main, g_short], [g_main])
+            grad[id(L["x"])] = g_main
+            i = s0 - 1
+        # ---------------------------------------------------------------- optimizer: one SGD command per parameter
+        for idx, (name, shape, decay) in enumerate(self.params):
+            cmd = nnc.CMD_SGD_FORWARD(1, self.learn_rate, 1.0 / self.global_batch, decay, 0.9, 0.0)
+            self._node(self.opt, cmd, None, 0, [G[idx], W[idx], self.m[idx]], [W[idx], self.m[idx]])
+
+    # ------------------------------------------------------------------------------------------------ execution
+    def graphs(self):
+        """Three flat graphs (forward, backward, optimizer) over the node lists."""
+        out = []
+        for nodes in (self.fwd, self.bwd, self.opt):
+            gph = nnc.Graph()
+            for cmd, hint, flags, ins, outs in nodes:
+                gph.exec_new(cmd, hint, flags, ins, outs)
+            out.append(gph)
+        return out
+
+    def free(self):
+        for t in self.tensors:
+            t.free()
+        self.tensors = []

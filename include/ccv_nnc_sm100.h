@@ -476,6 +476,11 @@ void ccv_nnc_sm100_hint_auto(const ccv_nnc_cmd_param_t* const info, const ccv_nn
 /* blocking copies between host memory and a GPU tensor's storage (what tests use to stage data) */
 int ccv_nnc_sm100_memcpy_h2d(void* const dst_device, const void* const src_host, const size_t bytes, ccv_nnc_stream_context_t* const stream_context);
 int ccv_nnc_sm100_memcpy_d2h(void* const dst_host, const void* const src_device, const size_t bytes, ccv_nnc_stream_context_t* const stream_context);
+/* CUDA events on a stream context's stream, for device-side timing */
+void* ccv_nnc_sm100_event_new(void);
+int ccv_nnc_sm100_event_record(void* const event, ccv_nnc_stream_context_t* const stream_context);
+float ccv_nnc_sm100_event_elapsed_ms(void* const begin, void* const end);
+void ccv_nnc_sm100_event_free(void* const event);
 /* number of kernels this backend has launched since process start (bench.py's gpu_launches) */
 uint64_t ccv_nnc_sm100_launch_count(void);
 /* last CUDA error string seen by the backend (empty if none) */

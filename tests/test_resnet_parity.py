@@ -1,0 +1,56 @@
+"""Whole-model parity: the identical ResNet-50 v1d command list (ccv_b200/resnet50.py, after bin/nnc/imagenet.c:17-95)
+on CCV_NNC_BACKEND_GPU_SM100 and on the reference's CPU_REF.  Batch 1 because CPU_REF's pooling only walks image 0 of a
+batch.  Also the CUDA-graph replay must reproduce the eager result."""
+import numpy as np
+import pytest
+
+from ccv_b200 import resnet50
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_gpu(nnc, net, stream):
+    g = nnc.Graph()
+    for cmd, hint, flags, ins, outs in net.fwd + net.bwd:
+        g.exec_new(cmd, hint, flags, ins, outs)
+    assert g.run(stream) == 0
+    stream.wait()
+    return g
+
+
+@pytest.mark.ref
+def test_resnet50_forward_backward_matches_cpu_ref(gpu, ref):
+    from oracle import ref_factory
+    nnc = gpu
+    image, classes = 64, 10
+    x = np.random.RandomState(0).rand(1, image, image, 3).astype(np.float32)
+    lab = np.array([3], np.int32)
+    cpu = resnet50.Net(1, image=image, classes=classes, factory=ref_factory.RefFactory(), seed=7)
+    cpu.input.upload(x), cpu.labels.upload(lab)
+    ref_factory.run_nodes(cpu.fwd), ref_factory.run_nodes(cpu.bwd)
+    stream = nnc.Stream(0)
+    net = resnet50.Net(1, image=image, classes=classes, seed=7)
+    net.input.upload(x), net.labels.upload(lab)
+    g = _run_gpu(nnc, net, stream)
+    assert_close(net.logits.download(), cpu.logits.download(), 2e-3, "logits")
+    assert_close(net.probs.download(), cpu.probs.download(), 2e-3, "softmax")
+    assert_close(net.loss.download(), cpu.loss.download(), 2e-3, "loss")
+    # gradients of every parameter: compared per tensor (normalised by that tensor's own largest reference value).
+    # 50 TF32 layers deep, errors compound: 1e-2 on the deepest-path gradients, still far below any training noise.
+    gg, gc = net.g_flat.download(), cpu.g_flat.download()
+    worst = 0.0
+    for (name, shape, _), off in zip(net.params, net.param_offsets):
+        n = int(np.prod(shape))
+        a, b = gg[off:off + n], gc[off:off + n]
+        scale = max(np.abs(b).max(), 1e-6)
+        worst = max(worst, float(np.abs(a - b).max() / scale))
+        assert np.abs(a - b).max() / scale < 3e-2, name
+    print("worst per-parameter normalised gradient error: %.3e" % worst)
+    # CUDA-graph capture + replay is bit-identical in the forward outputs to the eager run
+    eager_logits = net.logits.download()
+    cid = g.capture(stream)
+    assert g.replay(cid, stream) == 0
+    stream.wait()
+    assert np.array_equal(net.logits.download(), eager_logits)
+    g.free(), net.free(), stream.free()

@@ -1,0 +1,74 @@
+"""Shared helpers for the parity tests: run one command on the SM100 backend (through the C ABI) and on the oracle
+(the reference's own CCV_NNC_BACKEND_CPU_REF) from the same numpy inputs."""
+import numpy as np
+
+from ccv_b200 import abi
+
+NHWC = abi.CCV_TENSOR_FORMAT_NHWC
+NCHW = abi.CCV_TENSOR_FORMAT_NCHW
+NP_TO_CCV = {np.dtype(np.float32): abi.CCV_32F, np.dtype(np.int32): abi.CCV_32S, np.dtype(np.float64): abi.CCV_64F, np.dtype(np.float16): abi.CCV_16F, np.dtype(np.uint16): abi.CCV_16F, np.dtype(np.uint8): abi.CCV_8U}
+
+
+def seeded(shape, seed, lo=0.0, hi=1.0, dtype=np.float32):
+    """U(lo, hi] inputs, seeded (the reference's GPU-vs-CPU protocol, test/int/nnc/cudnn.tests.c:38-46, uses dSFMT seed 0)."""
+    r = np.random.RandomState(seed)
+    return (lo + (hi - lo) * (1.0 - r.random_sample(shape))).astype(dtype)
+
+
+def gpu_exec(nnc, cmd, hint, flags, in_arrays, out_arrays, fmt=NHWC, in_fmts=None, out_fmts=None, stream=None):
+    """Upload, ccv_nnc_cmd_exec on CCV_NNC_BACKEND_GPU_SM100, download. The same array object appearing in both lists
+    (or twice) is the same GPU tensor (in-place ops). Returns (status, [output arrays])."""
+    cache = {}
+
+    def tensor_for(a, f):
+        if a is None:
+            return None
+        if id(a) not in cache:
+            t = nnc.gpu_tensor(list(a.shape), f, NP_TO_CCV[a.dtype])
+            t.upload(a.view(np.float16) if a.dtype == np.uint16 else a)
+            cache[id(a)] = t
+        return cache[id(a)]
+
+    ins = [tensor_for(a, in_fmts[i] if in_fmts else fmt) for i, a in enumerate(in_arrays)]
+    outs = [tensor_for(a, out_fmts[i] if out_fmts else fmt) for i, a in enumerate(out_arrays)]
+    status = nnc.cmd_exec(cmd, hint, flags, ins, outs, stream)
+    if stream is not None:
+        stream.wait()
+    results = [None if t is None else t.download() for t in outs]
+    for t in cache.values():
+        t.free()
+    return status, results
+
+
+def ref_exec(ref, cmd, hint, flags, in_arrays, out_arrays, fmt=NHWC, in_fmts=None, out_fmts=None):
+    """Same command on the reference's CPU_REF. out_arrays are modified in place and returned."""
+    cache = {}
+
+    def tensor_for(a, f):
+        if a is None:
+            return None
+        if id(a) not in cache:
+            cache[id(a)] = ref.RefTensor(a, f)
+        return cache[id(a)]
+
+    ins = [tensor_for(a, in_fmts[i] if in_fmts else fmt) for i, a in enumerate(in_arrays)]
+    outs = [tensor_for(a, out_fmts[i] if out_fmts else fmt) for i, a in enumerate(out_arrays)]
+    status = ref.cmd_exec(cmd, hint, flags, ins, outs)
+    for t in cache.values():
+        t.free()
+    return status, out_arrays
+
+
+def rel_err(got, want):
+    """max |got - want| / max(|want|): the normalised error the fp32 tolerance of BASELINE.json (<= 1e-3) is applied to."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    denom = max(np.abs(want).max(), 1e-30)
+    return float(np.abs(got - want).max() / denom)
+
+
+def assert_close(got, want, tol, what=""):
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    assert np.isfinite(got).all(), what + ": non-finite output"
+    e = rel_err(got, want)
+    assert e <= tol, "%s: normalised max error %.3e > %.1e" % (what, e, tol)
