@@ -177,16 +177,8 @@ def main():
     # the single gradient exchange: one sum-allreduce over the flat gradient buffer (torch.distributed/NCCL plumbing)
     allreduce = None
     if world > 1:
-        import torch
-
-        class _Flat(object):
-            __cuda_array_interface__ = {"shape": (net.flat_count,), "typestr": "<f4", "data": (net.g_flat.data_ptr, False), "version": 2}
-        g_torch = torch.as_tensor(_Flat(), device=torch.device("cuda", device))
-        ext = torch.cuda.ExternalStream(stream.cuda_stream, device=torch.device("cuda", device))
-
-        def allreduce():
-            with torch.cuda.stream(ext):
-                dist.all_reduce(g_torch)
+        from ccv_b200 import dp
+        allreduce = dp.FlatAllreduce(net, dist, stream, device)
 
     # eager pass: sizes workspaces, counts launches, checks every command returns success
     l0 = nnc.launch_count()

