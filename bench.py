@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE: 256)")
     ap.add_argument("--image", type=int, default=224)
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="run every reference command as its own kernel sequence (no peephole fusion)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-op", default="", help="write the per-command profile to this JSON file")
     args = ap.parse_args()
@@ -154,12 +155,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device and there is no CPU fallback (use --impl reference for the CPU_REF arm)")
     device = local_rank
     stream = nnc.Stream(device)
-    net = resnet50.Net(args.batch, image=args.image, classes=1000, device=device, global_batch=args.batch * world)
-    fb_nodes, opt_nodes = net.fwd + net.bwd, net.opt
-    graph = nnc.Graph()
-    for cmd, hint, flags, ins, outs in fb_nodes + opt_nodes:
-        graph.exec_new(cmd, hint, flags, ins, outs)
-    n_fb, n_all = len(fb_nodes), len(fb_nodes) + len(opt_nodes)
+    net = resnet50.Net(args.batch, image=args.image, classes=1000, device=device, global_batch=args.batch * world, learn_rate=4e-5)  # 0.4 * 0.0001: the first warm-up rate of bin/nnc/imagenet.c:296-312
+    g_fb, g_opt = nnc.Graph(), nnc.Graph()
+    for cmd, hint, flags, ins, outs in net.fwd + net.bwd:
+        g_fb.exec_new(cmd, hint, flags, ins, outs)
+    for cmd, hint, flags, ins, outs in net.opt:
+        g_opt.exec_new(cmd, hint, flags, ins, outs)
+    n_fused = 0 if args.no_fuse else g_fb.fuse()
 
     # synthetic batch in pinned host memory (for the e2e leg) and resident in HBM (for `value`)
     rs = np.random.RandomState(1234 + rank)
@@ -182,25 +184,26 @@ def main():
 
     # eager pass: sizes workspaces, counts launches, checks every command returns success
     l0 = nnc.launch_count()
-    if graph.run(stream, 0, n_all) != 0:
+    if g_fb.run(stream) != 0 or g_opt.run(stream) != 0:
         raise SystemExit("bench.py: a command failed: %s" % nnc.lib().ccv_nnc_sm100_last_error())
     stream.wait()
     launches_per_step = nnc.launch_count() - l0
+    first_loss = float(np.mean(net.loss.download()))
     use_graph = not args.no_cuda_graph
     if use_graph:
-        cap_fb, cap_opt = graph.capture(stream, 0, n_fb), graph.capture(stream, n_fb, n_all)
+        cap_fb, cap_opt = g_fb.capture(stream), g_opt.capture(stream)
 
     def step():
         if use_graph:
-            graph.replay(cap_fb, stream)
+            g_fb.replay(cap_fb, stream)
         else:
-            graph.run(stream, 0, n_fb)
+            g_fb.run(stream)
         if allreduce:
             allreduce()
         if use_graph:
-            graph.replay(cap_opt, stream)
+            g_opt.replay(cap_opt, stream)
         else:
-            graph.run(stream, n_fb, n_all)
+            g_opt.run(stream)
 
     def barrier():
         stream.wait()
@@ -247,14 +250,14 @@ def main():
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c:17-95) fp32 NHWC, per-GPU batch %d, %dx%d, fwd+bwd + nesterov SGD%s" % (args.batch, args.image, args.image, ", one NCCL sum-allreduce of the flat fp32 gradient buffer" if world > 1 else ""),
                       "global_batch": images_per_step, "parallelism": "dp%d" % world, "tensor_core_math": "tcgen05 kind::tf32, fp32 accumulate (TMA rounds operands to TF32)",
-                      "cuda_graph": use_graph, "l2": "activations per step (>20 GB) exceed the 126 MB L2: no flush needed", "mean_loss": loss},
+                      "cuda_graph": use_graph, "fused_pairs": n_fused, "first_step_loss": first_loss, "l2": "activations per step (>20 GB) exceed the 126 MB L2: no flush needed", "mean_loss": loss},
            "e2e": {"value": images_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes + host_lab.nbytes), "d2h_bytes_per_step": int(host_loss.nbytes), "ms_per_step": e2e_ms},
            "gpu_launches": int(launches_per_step * (args.steps * 2 + args.warmup + 2)), "gpu_launches_per_step": int(launches_per_step), "clocks": sampler.summary()}
 
     if rank == 0:
         # per-command profile (eager, CUDA events around every command) -> roofline of the dominant kernel
         pk = peaks()
-        prof = profile_nodes(nnc, net, stream, pk)
+        prof = profile_nodes(nnc, net, (g_fb, g_opt), stream, pk)
         out["roofline"] = prof["roofline"]
         out["per_op"] = prof["summary"]
         if args.per_op:
@@ -267,13 +270,18 @@ def main():
         dist.destroy_process_group()
 
 
-def node_cost(cmd, ins, outs):
-    """(kind, algorithmic flops, algorithmic bytes) of one command, from its tensors (SURVEY.md 8d per-unit figures:
+FUSED_NAMES = {1: "bn_relu_fwd", 2: "relu_bn_bwd", 3: "add_relu_fwd", 4: "add_relu_bwd"}
+
+
+def node_cost(cmd, fused_kind, ins, outs):
+    """(kind, algorithmic flops, algorithmic bytes) of one node, from its tensors (SURVEY.md 8d per-unit figures:
     contractions = 2 * M * N * K flops; everything else = the bytes it must read + write once)."""
     from ccv_b200 import abi
     nb = lambda t: 0 if t is None else t.nbytes
-    c = cmd.cmd
     io = sum(nb(t) for t in ins) + sum(nb(t) for t in outs)
+    if fused_kind:
+        return FUSED_NAMES[fused_kind], 0.0, io
+    c = cmd
     if c == abi.CCV_NNC_CONVOLUTION_FORWARD:
         n, p, q, k = outs[0].dims
         return "conv_fwd", 2.0 * n * p * q * k * ins[1].count / ins[1].dims[0], io
@@ -291,20 +299,15 @@ def node_cost(cmd, ins, outs):
     return names.get(c, "other"), 0.0, io
 
 
-def profile_nodes(nnc, net, stream, pk):
-    """Run every command of one step eagerly with CUDA events around it (3 repetitions, best taken)."""
+def profile_nodes(nnc, net, graphs, stream, pk):
+    """Every node of one step run on its own with CUDA events around it (best of 3), through the same runner."""
+    by_ptr = dict((t.ptr, t) for t in net.tensors)
     rows = []
-    e0, e1 = nnc.Event(), nnc.Event()
-    for nodes in (net.fwd, net.bwd, net.opt):
-        for cmd, hint, flags, ins, outs in nodes:
-            kind, flops, nbytes = node_cost(cmd, ins, outs)
-            best = 1e30
-            for _ in range(3):
-                e0.record(stream)
-                nnc.cmd_exec(cmd, hint, flags, ins, outs, stream)
-                e1.record(stream)
-                best = min(best, e0.elapsed_ms(e1))
-            rows.append(dict(kind=kind, ms=best, flops=flops, bytes=nbytes))
+    for gph in graphs:
+        ms = gph.profile(stream, 3)
+        for (cmd, fk, ins, outs), t in zip(gph.nodes(), ms):
+            kind, flops, nbytes = node_cost(cmd, fk, [by_ptr.get(p) for p in ins], [by_ptr.get(p) for p in outs])
+            rows.append(dict(kind=kind, ms=t, flops=flops, bytes=nbytes))
     summary = {}
     for r in rows:
         s = summary.setdefault(r["kind"], dict(n=0, ms=0.0, flops=0.0, bytes=0.0))

@@ -588,7 +588,15 @@ struct ccv_nnc_sm100_graph_node_t {
 	ccv_nnc_hint_t hint;
 	int flags;
 	std::vector<ccv_nnc_tensor_t*> inputs, outputs;
+	ccv_nnc_cmd_exec_f fused; // non-NULL: a fused pair installed by ccv_nnc_sm100_graph_fuse, called instead of ccv_nnc_cmd_exec
 };
+
+extern "C" {
+int ccv_nnc_sm100_fused_bn_relu_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_fused_relu_bn_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_fused_add_relu_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+}
 
 struct ccv_nnc_sm100_graph_s {
 	std::vector<ccv_nnc_sm100_graph_node_t> nodes;
@@ -612,6 +620,7 @@ int ccv_nnc_sm100_graph_exec_new(ccv_nnc_sm100_graph_t* const graph, const uint3
 	node.flags = flags;
 	node.inputs.assign(inputs, inputs + input_size);
 	node.outputs.assign(outputs, outputs + output_size);
+	node.fused = 0;
 	graph->nodes.push_back(node);
 	return (int)graph->nodes.size() - 1;
 }
@@ -629,13 +638,154 @@ int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin,
 	for (i = begin < 0 ? 0 : begin; i < last; i++)
 	{
 		ccv_nnc_sm100_graph_node_t& n = graph->nodes[i];
-		const int ret = ccv_nnc_cmd_exec(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), stream_context);
+		const int ret = n.fused ? n.fused(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), stream_context) :
+			ccv_nnc_cmd_exec(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), stream_context);
 		if (ret != 0 && status == 0)
 		{
 			fprintf(stderr, "[ccv_nnc_sm100] graph node %d (cmd 0x%08x) returned %d\n", i, n.cmd.cmd, ret);
 			status = ret;
 		}
 	}
+	return status;
+}
+
+// Peephole fusion over adjacent nodes (the "fusion of adjacent nodes" item of the graph-runner launch path).
+// Every rewrite keeps the tensors the pair would have written, except the in-place intermediate of (b) and (d):
+//  (a) BATCH_NORM_FORWARD(train) ; RELU_FORWARD in place on its output      -> one pass writes relu(bn(x))
+//  (b) RELU_BACKWARD in place on g (mask y) ; BATCH_NORM_BACKWARD(g, x = bn input of y) -> mask recomputed from x; g is left
+//      unmasked, so the rewrite is only applied when no later node reads g
+//  (c) EWSUM(a, b -> y) ; RELU_FORWARD in place on y                          -> y = relu(a + b)
+//  (d) EWSUM(a, b -> a) ; RELU_BACKWARD in place on a (mask y)                -> a = y > 0 ? a + b : 0
+int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
+{
+	std::vector<ccv_nnc_sm100_graph_node_t>& nodes = graph->nodes;
+	if (!graph->captures.empty())
+		return -1;
+	std::vector<ccv_nnc_sm100_graph_node_t> out;
+	int fused = 0;
+	const size_t n = nodes.size();
+	auto is_gpu_sm100 = [](const ccv_nnc_sm100_graph_node_t& x) { return x.fused == 0 && (x.cmd.backend == CCV_NNC_BACKEND_GPU_SM100 || x.cmd.backend == CCV_NNC_NO_BACKEND); };
+	for (size_t i = 0; i < n; i++)
+	{
+		ccv_nnc_sm100_graph_node_t& a = nodes[i];
+		if (i + 1 < n && is_gpu_sm100(a) && is_gpu_sm100(nodes[i + 1]))
+		{
+			ccv_nnc_sm100_graph_node_t& b = nodes[i + 1];
+			// (a)
+			if (a.cmd.cmd == CCV_NNC_BATCH_NORM_FORWARD && !a.cmd.info.bnorm.is_test && a.outputs.size() == 5 && b.cmd.cmd == CCV_NNC_RELU_FORWARD && b.inputs.size() == 1 && b.outputs.size() == 1 &&
+				b.inputs[0] == a.outputs[0] && b.outputs[0] == a.outputs[0])
+			{
+				ccv_nnc_sm100_graph_node_t f = a;
+				f.fused = ccv_nnc_sm100_fused_bn_relu_forw;
+				out.push_back(f);
+				fused++, i++;
+				continue;
+			}
+			// (c)
+			if (a.cmd.cmd == CCV_NNC_EWSUM_FORWARD && a.inputs.size() == 2 && a.outputs.size() == 1 && b.cmd.cmd == CCV_NNC_RELU_FORWARD && b.inputs.size() == 1 && b.inputs[0] == a.outputs[0] && b.outputs[0] == a.outputs[0])
+			{
+				ccv_nnc_sm100_graph_node_t f = a;
+				f.fused = ccv_nnc_sm100_fused_add_relu_forw;
+				out.push_back(f);
+				fused++, i++;
+				continue;
+			}
+			// (d)
+			if (a.cmd.cmd == CCV_NNC_EWSUM_FORWARD && a.inputs.size() == 2 && a.outputs.size() == 1 && a.outputs[0] == a.inputs[0] && b.cmd.cmd == CCV_NNC_RELU_BACKWARD && b.inputs.size() == 3 && b.inputs[0] == a.outputs[0] &&
+				b.outputs.size() == 1 && b.outputs[0] == a.outputs[0] && b.inputs[2])
+			{
+				ccv_nnc_sm100_graph_node_t f = a;
+				f.inputs.push_back(b.inputs[2]);
+				f.fused = ccv_nnc_sm100_fused_add_relu_back;
+				out.push_back(f);
+				fused++, i++;
+				continue;
+			}
+			// (b)
+			if (a.cmd.cmd == CCV_NNC_RELU_BACKWARD && a.inputs.size() == 3 && a.outputs.size() == 1 && a.outputs[0] == a.inputs[0] && a.inputs[2] && b.cmd.cmd == CCV_NNC_BATCH_NORM_BACKWARD && b.inputs.size() == 15 &&
+				b.inputs[0] == a.outputs[0] && b.inputs[5] && !b.inputs[7])
+			{
+				// the forward batch norm that produced the mask tensor from this x supplies the bias
+				ccv_nnc_tensor_t* bias = 0;
+				for (size_t j = 0; j < n && !bias; j++)
+					if (nodes[j].cmd.cmd == CCV_NNC_BATCH_NORM_FORWARD && nodes[j].inputs.size() == 5 && nodes[j].outputs.size() >= 1 && nodes[j].outputs[0] == a.inputs[2] && nodes[j].inputs[0] == b.inputs[5] && nodes[j].inputs[1] == b.inputs[6])
+						bias = nodes[j].inputs[2];
+				bool g_read_later = false;
+				for (size_t j = i + 2; j < n && !g_read_later; j++)
+					for (ccv_nnc_tensor_t* t : nodes[j].inputs)
+						if (t == a.outputs[0])
+						{
+							// a later node that overwrites g before reading it would be fine, but keep the rule simple
+							g_read_later = true;
+							break;
+						}
+				if (bias && !g_read_later)
+				{
+					ccv_nnc_sm100_graph_node_t f = b;
+					f.inputs[7] = bias;
+					f.fused = ccv_nnc_sm100_fused_relu_bn_back;
+					out.push_back(f);
+					fused++, i++;
+					continue;
+				}
+			}
+		}
+		out.push_back(a);
+	}
+	nodes.swap(out);
+	return fused;
+}
+
+// introspection + per-node device timing (CUDA events around each node, best of `reps`), for bench.py's per-command table
+int ccv_nnc_sm100_graph_node(const ccv_nnc_sm100_graph_t* const graph, const int i, uint32_t* const cmd, int* const fused_kind, int* const input_size, int* const output_size)
+{
+	if (i < 0 || i >= (int)graph->nodes.size())
+		return -1;
+	const ccv_nnc_sm100_graph_node_t& n = graph->nodes[i];
+	*cmd = n.cmd.cmd;
+	*fused_kind = n.fused == ccv_nnc_sm100_fused_bn_relu_forw ? 1 : n.fused == ccv_nnc_sm100_fused_relu_bn_back ? 2 : n.fused == ccv_nnc_sm100_fused_add_relu_forw ? 3 : n.fused == ccv_nnc_sm100_fused_add_relu_back ? 4 : 0;
+	*input_size = (int)n.inputs.size();
+	*output_size = (int)n.outputs.size();
+	return 0;
+}
+
+void* ccv_nnc_sm100_graph_node_tensor(const ccv_nnc_sm100_graph_t* const graph, const int i, const int is_output, const int k)
+{
+	if (i < 0 || i >= (int)graph->nodes.size())
+		return 0;
+	const std::vector<ccv_nnc_tensor_t*>& v = is_output ? graph->nodes[i].outputs : graph->nodes[i].inputs;
+	return k >= 0 && k < (int)v.size() ? (void*)v[k] : 0;
+}
+
+int ccv_nnc_sm100_graph_profile(ccv_nnc_sm100_graph_t* const graph, ccv_nnc_stream_context_t* const stream_context, const int reps, float* const ms)
+{
+	if (!stream_context)
+		return -1;
+	cudaEvent_t e0, e1;
+	if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+		return -1;
+	cudaStream_t stream = stream_context->stream;
+	int status = 0;
+	for (int i = 0; i < (int)graph->nodes.size(); i++)
+	{
+		float best = 1e30f;
+		for (int r = 0; r < (reps < 1 ? 1 : reps); r++)
+		{
+			cudaEventRecord(e0, stream);
+			const int ret = ccv_nnc_sm100_graph_run(graph, i, i + 1, stream_context);
+			cudaEventRecord(e1, stream);
+			cudaEventSynchronize(e1);
+			float t = 0;
+			cudaEventElapsedTime(&t, e0, e1);
+			if (t < best)
+				best = t;
+			if (ret != 0)
+				status = ret;
+		}
+		ms[i] = best;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
 	return status;
 }
 

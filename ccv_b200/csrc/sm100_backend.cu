@@ -442,7 +442,7 @@ bool bn_layout(const TV& a, const TV& scale, size_t& outer, int& C, size_t& inne
 	return true;
 }
 
-int exec_bnorm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+int bnorm_forw(const int fuse_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (input_size != 5 || output_size < 1)
 		return CCV_NNC_EXEC_INVALID;
@@ -462,7 +462,12 @@ int exec_bnorm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const in
 	cudaStream_t s = stream_of(stream_context);
 	if (cmd.info.bnorm.is_test)
 	{
-		RC(bn_fwd_test_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, inputs[3]->data.f32, inputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon));
+		if (fuse_relu)
+			return CCV_NNC_EXEC_INVALID;
+		void* const tws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
+		if (!tws)
+			return CCV_NNC_EXEC_OOM;
+		RC(bn_fwd_test_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, inputs[3]->data.f32, inputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, tws));
 		return CCV_NNC_EXEC_SUCCESS;
 	}
 	if (output_size != 5 || !outputs[1] || !outputs[2] || !outputs[3] || !outputs[4])
@@ -475,15 +480,24 @@ int exec_bnorm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const in
 	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
 	if (!ws)
 		return CCV_NNC_EXEC_OOM;
-	RC(bn_fwd_train_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, outputs[3]->data.f32, outputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, cmd.info.bnorm.momentum, ws));
+	RC(bn_fwd_train_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, outputs[3]->data.f32, outputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, cmd.info.bnorm.momentum, ws, fuse_relu));
 	return CCV_NNC_EXEC_SUCCESS;
+}
+
+int exec_bnorm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return bnorm_forw(0, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 
 // norm/ccv_nnc_batch_norm_cpu_ref.c:312-470: inputs[0] = g, [5] = a, [6] = scale, [13] = saved_mean, [14] = saved_inv_std;
 // outputs (h, dscale, dbias)
-int exec_bnorm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+int bnorm_back(const int fused_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (input_size != 15 || output_size < 1)
+		return CCV_NNC_EXEC_INVALID;
+	// the fused form carries the forward bias in slot 7 (unused by BATCH_NORM_BACKWARD, norm/ccv_nnc_norm.c:28-37)
+	const ccv_nnc_tensor_t* const bias_t = fused_relu ? inputs[7] : 0;
+	if (fused_relu && !bias_t)
 		return CCV_NNC_EXEC_INVALID;
 	const ccv_nnc_tensor_t* const g_t = inputs[0];
 	const ccv_nnc_tensor_t* const a_t = inputs[5];
@@ -506,8 +520,13 @@ int exec_bnorm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const in
 	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
 	if (!ws)
 		return CCV_NNC_EXEC_OOM;
-	RC(bn_bwd_f32(s, g_t->data.f32, a_t->data.f32, scale_t->data.f32, mean_t->data.f32, istd_t->data.f32, h_t ? h_t->data.f32 : 0, dscale_t ? dscale_t->data.f32 : 0, dbias_t ? dbias_t->data.f32 : 0, outer, C, inner, ws));
+	RC(bn_bwd_f32(s, g_t->data.f32, a_t->data.f32, scale_t->data.f32, bias_t ? bias_t->data.f32 : 0, mean_t->data.f32, istd_t->data.f32, h_t ? h_t->data.f32 : 0, dscale_t ? dscale_t->data.f32 : 0, dbias_t ? dbias_t->data.f32 : 0, outer, C, inner, ws));
 	return CCV_NNC_EXEC_SUCCESS;
+}
+
+int exec_bnorm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return bnorm_back(0, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 
 // ================================================================================================ RELU / EW
@@ -1149,6 +1168,43 @@ int ccv_nnc_sm100_exec_rmsnorm_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, c
 int ccv_nnc_sm100_exec_upsample_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 int ccv_nnc_sm100_exec_upsample_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 int ccv_nnc_sm100_exec_allreduce(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+}
+
+// ================================================================================================ fused pairs
+// Used by the flat graph runner's peephole pass (ccv_nnc_sm100_graph_fuse): each stands for two adjacent reference
+// commands and produces what the pair would have produced.
+extern "C" int ccv_nnc_sm100_fused_bn_relu_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return bnorm_forw(1, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
+extern "C" int ccv_nnc_sm100_fused_relu_bn_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return bnorm_back(1, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
+// inputs (a, b) -> y = relu(a + b)
+extern "C" int ccv_nnc_sm100_fused_add_relu_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 2 || output_size != 1 || !inputs[0] || !inputs[1] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	const TV a = view_of(inputs[0]), b = view_of(inputs[1]), y = view_of(outputs[0]);
+	if (!a.contiguous || !b.contiguous || !y.contiguous || a.count != y.count || b.count != y.count || !is_f32(inputs[0]) || !is_f32(inputs[1]) || !is_f32(outputs[0]))
+		return CCV_NNC_EXEC_INVALID;
+	RC(ew_add_relu_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, outputs[0]->data.f32, y.count));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// inputs (a, b, y) -> out = y > 0 ? a + b : 0   (EWSUM of two branch gradients followed by RELU_BACKWARD)
+extern "C" int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size != 3 || output_size != 1 || !inputs[0] || !inputs[1] || !inputs[2] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	const TV a = view_of(inputs[0]), b = view_of(inputs[1]), y = view_of(inputs[2]), o = view_of(outputs[0]);
+	if (!a.contiguous || !b.contiguous || !y.contiguous || !o.contiguous || a.count != o.count || b.count != o.count || y.count != o.count)
+		return CCV_NNC_EXEC_INVALID;
+	RC(ew_add_relu_bwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, o.count));
+	return CCV_NNC_EXEC_SUCCESS;
 }
 
 // ================================================================================================ registration

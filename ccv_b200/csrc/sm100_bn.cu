@@ -1,0 +1,450 @@
+// sm100_bn.cu -- batch normalisation (training / inference forward, backward), optionally fused with the ReLU that
+// follows it in a ResNet block, and the two fused residual-add kernels.  All HBM-bound: every pass streams each tensor
+// once with 128-bit accesses and several independent loads in flight per thread.
+//
+// Semantics: norm/ccv_nnc_batch_norm_cpu_ref.c:16-250 (forward), :312-470 (backward); relu/ccv_nnc_relu_cpu_ref.c:13-55;
+// ew/ccv_nnc_ew_cpu_ref.c:15-110 (paths relative to /root/reference/lib/nnc/cmd).  Statistics are biased; running =
+// momentum * running + (1 - momentum) * batch.  Layout [outer, C, inner] (NHWC: inner = 1).
+//
+// Workspace (bn_workspace_bytes): double s[2C] (cross-block sums) followed by float coef[4C] (per-channel a, b, p, q).
+#include "sm100_ew.h"
+#include "sm100_contract.h"
+
+namespace sm100 {
+
+static int g_sms_bn = 0;
+static int sms()
+{
+	if (!g_sms_bn)
+	{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&g_sms_bn, cudaDevAttrMultiProcessorCount, dev);
+		if (g_sms_bn <= 0)
+			g_sms_bn = 148;
+	}
+	return g_sms_bn;
+}
+static int check(const char* what)
+{
+	count_launch();
+	const cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error(what, e);
+		return -1;
+	}
+	return 0;
+}
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+static int grid_for(size_t work_items, int threads, int max_waves = 8)
+{
+	size_t blocks = (work_items + threads - 1) / threads;
+	const size_t cap = (size_t)sms() * max_waves;
+	if (blocks > cap)
+		blocks = cap;
+	return blocks < 1 ? 1 : (int)blocks;
+}
+
+size_t bn_workspace_bytes(int C) { return (size_t)C * (2 * sizeof(double) + 4 * sizeof(float)); }
+static inline double* ws_sums(void* ws) { return (double*)ws; }
+static inline float* ws_coef(void* ws, int C) { return (float*)((double*)ws + 2 * (size_t)C); }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ------------------------------------------------------------------------------------------------ reductions
+// NHWC: thread = (column-vector tx, row-lane ty); each thread walks rows with 4 independent 128-bit loads in flight.
+// MODE 0: s1 = sum(x - k), s2 = sum((x - k)^2), k = x[0, c] (shift keeps the one-pass variance well conditioned).
+// MODE 1: s1 = sum(g'), s2 = sum(g' * (x - mean)); g' = g, or g masked by relu(x * a + b) > 0 when MASK.
+template <int MODE, int MASK>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t rows, const int C, double* __restrict__ ws, const int cpb)
+{
+	__shared__ float4 sh[2][256];
+	const int CV = C >> 2;
+	const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb, rpi = 256 / cpb;
+	const int cv = blockIdx.x * cpb + tx;
+	float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+	if (ty < rpi && cv < CV)
+	{
+		const float4 k = MODE == 0 ? ld4(x + cv * 4) : ld4(mean + cv * 4);
+		float4 a = make_float4(0, 0, 0, 0), b = a;
+		if (MASK)
+			a = ld4(coef + cv * 4), b = ld4(coef + C + cv * 4);
+		const size_t step = (size_t)gridDim.y * rpi;
+		size_t r = (size_t)blockIdx.y * rpi + ty;
+#define BN_ACC(xv, gv) \
+		{ \
+			if (MODE == 0) \
+			{ \
+				const float d0 = xv.x - k.x, d1 = xv.y - k.y, d2 = xv.z - k.z, d3 = xv.w - k.w; \
+				s1.x += d0, s1.y += d1, s1.z += d2, s1.w += d3; \
+				s2.x += d0 * d0, s2.y += d1 * d1, s2.z += d2 * d2, s2.w += d3 * d3; \
+			} else { \
+				float m0_ = gv.x, m1_ = gv.y, m2_ = gv.z, m3_ = gv.w; \
+				if (MASK) \
+				{ \
+					m0_ = fmaf(xv.x, a.x, b.x) > 0.f ? m0_ : 0.f, m1_ = fmaf(xv.y, a.y, b.y) > 0.f ? m1_ : 0.f; \
+					m2_ = fmaf(xv.z, a.z, b.z) > 0.f ? m2_ : 0.f, m3_ = fmaf(xv.w, a.w, b.w) > 0.f ? m3_ : 0.f; \
+				} \
+				s1.x += m0_, s1.y += m1_, s1.z += m2_, s1.w += m3_; \
+				s2.x += m0_ * (xv.x - k.x), s2.y += m1_ * (xv.y - k.y), s2.z += m2_ * (xv.z - k.z), s2.w += m3_ * (xv.w - k.w); \
+			} \
+		}
+		for (; r + 3 * step < rows; r += 4 * step)
+		{
+			const float4 x0 = ld4(x + r * C + cv * 4), x1 = ld4(x + (r + step) * C + cv * 4), x2 = ld4(x + (r + 2 * step) * C + cv * 4), x3 = ld4(x + (r + 3 * step) * C + cv * 4);
+			float4 g0 = x0, g1 = x0, g2 = x0, g3 = x0;
+			if (MODE == 1)
+				g0 = ld4(g + r * C + cv * 4), g1 = ld4(g + (r + step) * C + cv * 4), g2 = ld4(g + (r + 2 * step) * C + cv * 4), g3 = ld4(g + (r + 3 * step) * C + cv * 4);
+			BN_ACC(x0, g0) BN_ACC(x1, g1) BN_ACC(x2, g2) BN_ACC(x3, g3)
+		}
+		for (; r < rows; r += step)
+		{
+			const float4 x0 = ld4(x + r * C + cv * 4);
+			float4 g0 = x0;
+			if (MODE == 1)
+				g0 = ld4(g + r * C + cv * 4);
+			BN_ACC(x0, g0)
+		}
+#undef BN_ACC
+	}
+	sh[0][threadIdx.x] = s1, sh[1][threadIdx.x] = s2;
+	__syncthreads();
+	if (ty == 0 && cv < CV)
+	{
+		for (int t = 1; t < rpi; t++)
+		{
+			const float4 u = sh[0][t * cpb + tx], v = sh[1][t * cpb + tx];
+			s1.x += u.x, s1.y += u.y, s1.z += u.z, s1.w += u.w;
+			s2.x += v.x, s2.y += v.y, s2.z += v.z, s2.w += v.w;
+		}
+		double* w1 = ws + cv * 4;
+		double* w2 = ws + C + cv * 4;
+		atomicAdd(w1, (double)s1.x), atomicAdd(w1 + 1, (double)s1.y), atomicAdd(w1 + 2, (double)s1.z), atomicAdd(w1 + 3, (double)s1.w);
+		atomicAdd(w2, (double)s2.x), atomicAdd(w2 + 1, (double)s2.y), atomicAdd(w2 + 2, (double)s2.z), atomicAdd(w2 + 3, (double)s2.w);
+	}
+}
+
+// any layout [outer, C, inner], scalar: one block per channel (NCHW, or C not a multiple of 4)
+template <int MODE, int MASK>
+__global__ void bn_reduce_generic_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t outer, const int C, const size_t inner, double* __restrict__ ws)
+{
+	__shared__ float sh[2][32];
+	const int c = blockIdx.x;
+	const float k = MODE == 0 ? x[(size_t)c * inner] : mean[c];
+	const float a = MASK ? coef[c] : 0.f, b = MASK ? coef[C + c] : 0.f;
+	float s1 = 0.f, s2 = 0.f;
+	const size_t total = outer * inner;
+	for (size_t i = threadIdx.x; i < total; i += blockDim.x)
+	{
+		const size_t o = i / inner, in = i - o * inner;
+		const size_t idx = (o * C + c) * inner + in;
+		const float xv = x[idx];
+		if (MODE == 0)
+		{
+			const float d = xv - k;
+			s1 += d, s2 += d * d;
+		} else {
+			float gv = g[idx];
+			if (MASK)
+				gv = fmaf(xv, a, b) > 0.f ? gv : 0.f;
+			s1 += gv, s2 += gv * (xv - k);
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1)
+		s1 += __shfl_xor_sync(0xffffffff, s1, o), s2 += __shfl_xor_sync(0xffffffff, s2, o);
+	if ((threadIdx.x & 31) == 0)
+		sh[0][threadIdx.x >> 5] = s1, sh[1][threadIdx.x >> 5] = s2;
+	__syncthreads();
+	if (threadIdx.x < 32)
+	{
+		const int nw = blockDim.x >> 5;
+		s1 = threadIdx.x < nw ? sh[0][threadIdx.x] : 0.f, s2 = threadIdx.x < nw ? sh[1][threadIdx.x] : 0.f;
+		for (int o = 16; o > 0; o >>= 1)
+			s1 += __shfl_xor_sync(0xffffffff, s1, o), s2 += __shfl_xor_sync(0xffffffff, s2, o);
+		if (threadIdx.x == 0)
+			ws[c] = (double)s1, ws[C + c] = (double)s2;
+	}
+}
+
+// per-channel forward affine, shared by forward and (for the ReLU mask) backward so that both see identical bits
+__device__ __forceinline__ void bn_affine(const float scale, const float bias, const float mean, const float inv_std, float& a, float& b)
+{
+	a = scale * inv_std;
+	b = bias - mean * a;
+}
+
+__global__ void bn_fwd_finalize_kernel(const float* __restrict__ x, const size_t shift_stride, const double* __restrict__ ws, const int C, const double count, const float epsilon, const float momentum, const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std, float* __restrict__ coef)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C)
+		return;
+	const double k = (double)x[(size_t)c * shift_stride];
+	const double s1 = ws[c], s2 = ws[C + c];
+	const double mean = k + s1 / count;
+	double var = (s2 - s1 * s1 / count) / count;
+	if (var < 0)
+		var = 0;
+	const float meanf = (float)mean, varf = (float)var;
+	const float inv_std = 1.f / sqrtf(varf + epsilon);
+	saved_mean[c] = meanf;
+	saved_inv_std[c] = inv_std;
+	running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * meanf;
+	running_var[c] = momentum * running_var[c] + (1.f - momentum) * varf;
+	float a, b;
+	bn_affine(scale[c], bias[c], meanf, inv_std, a, b);
+	coef[c] = a, coef[C + c] = b;
+}
+// inference: inv_std = 1 / (sqrt(var) + eps)  (batch_norm_cpu_ref.c:262-279)
+__global__ void bn_test_coef_kernel(const int C, const float epsilon, const float* __restrict__ scale, const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ var, float* __restrict__ coef)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C)
+		return;
+	const float a = scale[c] / (sqrtf(var[c]) + epsilon);
+	coef[c] = a, coef[C + c] = bias[c] - mean[c] * a;
+}
+// backward coefficients: with a = scale * inv_std, dx = a * g' + p * x + q,
+//   p = -a * inv_std * dscale / count,  q = -a * dbias / count - p * mean      (same algebra as batch_norm_cpu_ref.c:430-466)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, const int C, const float count, const float* __restrict__ scale, const float* __restrict__ mean, const float* __restrict__ inv_std, float* __restrict__ dscale, float* __restrict__ dbias, float* __restrict__ coef)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C)
+		return;
+	const float db = (float)ws[c];
+	const float ds = (float)ws[C + c] * inv_std[c];
+	if (dbias)
+		dbias[c] = db;
+	if (dscale)
+		dscale[c] = ds;
+	const float a = scale[c] * inv_std[c];
+	const float p = -a * inv_std[c] * ds / count;
+	coef[2 * C + c] = p;
+	coef[3 * C + c] = -a * db / count - p * mean[c];
+}
+__global__ void bn_mask_coef_kernel(const int C, const float* __restrict__ scale, const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ inv_std, float* __restrict__ coef)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C)
+		return;
+	float a, b;
+	bn_affine(scale[c], bias[c], mean[c], inv_std[c], a, b);
+	coef[c] = a, coef[C + c] = b;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise passes
+// forward: y = x * a + b (optionally relu'd).  backward: dx = a * g' + p * x + q with the optional relu mask on g.
+template <int BWD, int RELU>
+__global__ void __launch_bounds__(256) bn_apply_vec_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, const float* __restrict__ coef, const size_t total4, const int C)
+{
+	const int CV = C >> 2;
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += 2 * stride)
+	{
+		const size_t j = i + stride;
+		const bool two = j < total4;
+		const float4 x0 = ld4(x + i * 4), x1 = two ? ld4(x + j * 4) : x0;
+		float4 g0 = x0, g1 = x0;
+		if (BWD)
+			g0 = ld4(g + i * 4), g1 = two ? ld4(g + j * 4) : g0;
+#pragma unroll
+		for (int u = 0; u < 2; u++)
+		{
+			if (u == 1 && !two)
+				break;
+			const size_t e = u ? j : i;
+			const float4 xv = u ? x1 : x0, gv = u ? g1 : g0;
+			const int c0 = (int)(e % CV) * 4;
+			const float4 a = ld4(coef + c0), b = ld4(coef + C + c0);
+			float4 o;
+			if (!BWD)
+			{
+				o.x = fmaf(xv.x, a.x, b.x), o.y = fmaf(xv.y, a.y, b.y), o.z = fmaf(xv.z, a.z, b.z), o.w = fmaf(xv.w, a.w, b.w);
+				if (RELU)
+					o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+			} else {
+				const float4 p = ld4(coef + 2 * C + c0), q = ld4(coef + 3 * C + c0);
+				float h0 = gv.x, h1 = gv.y, h2 = gv.z, h3 = gv.w;
+				if (RELU)
+				{
+					h0 = fmaf(xv.x, a.x, b.x) > 0.f ? h0 : 0.f, h1 = fmaf(xv.y, a.y, b.y) > 0.f ? h1 : 0.f;
+					h2 = fmaf(xv.z, a.z, b.z) > 0.f ? h2 : 0.f, h3 = fmaf(xv.w, a.w, b.w) > 0.f ? h3 : 0.f;
+				}
+				o.x = fmaf(a.x, h0, fmaf(p.x, xv.x, q.x)), o.y = fmaf(a.y, h1, fmaf(p.y, xv.y, q.y));
+				o.z = fmaf(a.z, h2, fmaf(p.z, xv.z, q.z)), o.w = fmaf(a.w, h3, fmaf(p.w, xv.w, q.w));
+			}
+			st4(out + e * 4, o);
+		}
+	}
+}
+template <int BWD, int RELU>
+__global__ void bn_apply_generic_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, const float* __restrict__ coef, const size_t total, const int C, const size_t inner)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const int c = (int)((i / inner) % C);
+		const float a = coef[c], b = coef[C + c], xv = x[i];
+		if (!BWD)
+		{
+			const float o = fmaf(xv, a, b);
+			out[i] = RELU ? fmaxf(o, 0.f) : o;
+		} else {
+			float h = g[i];
+			if (RELU)
+				h = fmaf(xv, a, b) > 0.f ? h : 0.f;
+			out[i] = fmaf(a, h, fmaf(coef[2 * C + c], xv, coef[3 * C + c]));
+		}
+	}
+}
+
+static void reduce_config(size_t rows, int CV, int& cpb, dim3& grid)
+{
+	cpb = CV >= 256 ? 256 : CV;
+	const int rpi = 256 / cpb;
+	const int gx = (CV + cpb - 1) / cpb;
+	size_t gy = (rows + (size_t)rpi * 32 - 1) / ((size_t)rpi * 32);
+	const size_t cap = (size_t)(sms() * 4 + gx - 1) / gx;
+	if (gy > cap)
+		gy = cap;
+	if (gy < 1)
+		gy = 1;
+	grid = dim3(gx, (unsigned)gy);
+}
+
+template <int MODE, int MASK>
+static int run_reduce(cudaStream_t s, const float* x, const float* g, const float* mean, const float* coef, size_t outer, int C, size_t inner, double* ws)
+{
+	if (inner == 1 && C % 4 == 0 && aligned16(x) && (MODE == 0 || aligned16(g)))
+	{
+		const cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)C * 2 * sizeof(double), s);
+		if (e != cudaSuccess)
+		{
+			set_last_error("memset(bn)", e);
+			return -1;
+		}
+		int cpb;
+		dim3 grid;
+		reduce_config(outer, C / 4, cpb, grid);
+		bn_reduce_kernel<MODE, MASK><<<grid, 256, 0, s>>>(x, g, mean, coef, outer, C, ws, cpb);
+	} else
+		bn_reduce_generic_kernel<MODE, MASK><<<C, 512, 0, s>>>(x, g, mean, coef, outer, C, inner, ws);
+	return check("bn_reduce");
+}
+
+template <int BWD, int RELU>
+static int run_apply(cudaStream_t s, const float* x, const float* g, float* out, const float* coef, size_t outer, int C, size_t inner)
+{
+	const size_t total = outer * C * inner;
+	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(out) && (!BWD || aligned16(g)))
+		bn_apply_vec_kernel<BWD, RELU><<<grid_for(total / 8, 256), 256, 0, s>>>(x, g, out, coef, total / 4, C);
+	else
+		bn_apply_generic_kernel<BWD, RELU><<<grid_for(total, 256), 256, 0, s>>>(x, g, out, coef, total, C, inner);
+	return check("bn_apply");
+}
+
+int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu)
+{
+	if (outer * C * inner == 0)
+		return 0;
+	double* ws = ws_sums(workspace);
+	float* coef = ws_coef(workspace, C);
+	if (run_reduce<0, 0>(s, x, 0, 0, 0, outer, C, inner, ws))
+		return -1;
+	bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, inner, ws, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, coef);
+	if (check("bn_fwd_finalize"))
+		return -1;
+	return fuse_relu ? run_apply<0, 1>(s, x, 0, y, coef, outer, C, inner) : run_apply<0, 0>(s, x, 0, y, coef, outer, C, inner);
+}
+
+int bn_fwd_test_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, const float* mean, const float* var, size_t outer, int C, size_t inner, float epsilon, void* workspace)
+{
+	if (outer * C * inner == 0)
+		return 0;
+	float* coef = ws_coef(workspace, C);
+	bn_test_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, epsilon, scale, bias, mean, var, coef);
+	if (check("bn_test_coef"))
+		return -1;
+	return run_apply<0, 0>(s, x, 0, y, coef, outer, C, inner);
+}
+
+// bias != NULL selects the fused form: g is the gradient w.r.t. relu(bn(x)) and is masked by bn(x) > 0 on the fly
+int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, float* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace)
+{
+	if (outer * C * inner == 0)
+		return 0;
+	double* ws = ws_sums(workspace);
+	float* coef = ws_coef(workspace, C);
+	const int mask = bias != 0;
+	if (mask)
+	{
+		bn_mask_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, scale, bias, saved_mean, saved_inv_std, coef);
+		if (check("bn_mask_coef"))
+			return -1;
+	} else {
+		// a is still needed by the apply pass
+		bn_mask_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, scale, scale, saved_mean, saved_inv_std, coef);
+		if (check("bn_coef"))
+			return -1;
+	}
+	if (mask ? run_reduce<1, 1>(s, x, g, saved_mean, coef, outer, C, inner, ws) : run_reduce<1, 0>(s, x, g, saved_mean, coef, outer, C, inner, ws))
+		return -1;
+	bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(ws, C, (float)((double)outer * (double)inner), scale, saved_mean, saved_inv_std, dscale, dbias, coef);
+	if (check("bn_bwd_finalize"))
+		return -1;
+	if (!dx)
+		return 0;
+	return mask ? run_apply<1, 1>(s, x, g, dx, coef, outer, C, inner) : run_apply<1, 0>(s, x, g, dx, coef, outer, C, inner);
+}
+
+// ------------------------------------------------------------------------------------------------ fused residual adds
+// MODE 0: out = relu(a + b)                      (EWSUM then RELU_FORWARD at the end of a residual block)
+// MODE 1: out = y > 0 ? a + b : 0                (EWSUM of the two branch gradients then RELU_BACKWARD)
+template <int MODE>
+__global__ void __launch_bounds__(256) add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ y, float* __restrict__ out, const size_t n, const int vec)
+{
+	if (vec)
+	{
+		const size_t n4 = n >> 2;
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const float4 u = ld4(a + i * 4), v = ld4(b + i * 4);
+			float4 o = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+			if (MODE == 0)
+				o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+			else {
+				const float4 m = ld4(y + i * 4);
+				o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
+			}
+			st4(out + i * 4, o);
+		}
+		for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const float o = a[i] + b[i];
+			out[i] = MODE == 0 ? fmaxf(o, 0.f) : (y[i] > 0.f ? o : 0.f);
+		}
+	} else
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const float o = a[i] + b[i];
+			out[i] = MODE == 0 ? fmaxf(o, 0.f) : (y[i] > 0.f ? o : 0.f);
+		}
+}
+int ew_add_relu_fwd_f32(cudaStream_t s, const float* a, const float* b, float* out, size_t n)
+{
+	if (n == 0)
+		return 0;
+	const int vec = aligned16(a) && aligned16(b) && aligned16(out);
+	add_relu_kernel<0><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, 0, out, n, vec);
+	return check("add_relu_fwd");
+}
+int ew_add_relu_bwd_f32(cudaStream_t s, const float* a, const float* b, const float* y, float* out, size_t n)
+{
+	if (n == 0)
+		return 0;
+	const int vec = aligned16(a) && aligned16(b) && aligned16(out) && aligned16(y);
+	add_relu_kernel<1><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, y, out, n, vec);
+	return check("add_relu_bwd");
+}
+
+} // namespace sm100

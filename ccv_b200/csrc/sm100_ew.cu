@@ -600,328 +600,6 @@ int pool_avg_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, flo
 	return check("pool_avg_bwd");
 }
 
-// =============================================================================================== batch norm
-// norm/ccv_nnc_batch_norm_cpu_ref.c:16-250 (forward), :312-470 (backward).  Statistics are biased (divide by count);
-// running = momentum * running + (1 - momentum) * batch.  Layout [outer, C, inner].
-//
-// Pass 1 accumulates, per channel, sum(x - k) and sum((x - k)^2) with the per-channel shift k = x[0, c] (keeps the
-// one-pass variance formula well conditioned); block partials go to a double-precision workspace with atomics.
-// workspace (doubles): [0, C) first moment, [C, 2C) second moment.
-size_t bn_workspace_bytes(int C) { return (size_t)C * 2 * sizeof(double); }
-
-// inner == 1 (NHWC): threads (column-vector, row-lane); VEC = 4 uses 128-bit loads along C
-template <int VEC, int MODE> // MODE 0: stats of x. MODE 1: backward sums (g, g * xhat)
-__global__ void bn_reduce_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ inv_std, const size_t rows, const int C, double* __restrict__ ws, const int cpb)
-{
-	extern __shared__ float sh[]; // [2][blockDim.x][VEC]
-	const int CV = C / VEC;
-	const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb, rpi = blockDim.x / cpb;
-	const int cv = blockIdx.x * cpb + tx;
-	float s1[VEC], s2[VEC], k[VEC], k2[VEC];
-#pragma unroll
-	for (int j = 0; j < VEC; j++)
-		s1[j] = s2[j] = 0.f;
-	const bool active = ty < rpi && cv < CV;
-	if (active)
-	{
-#pragma unroll
-		for (int j = 0; j < VEC; j++)
-		{
-			if (MODE == 0)
-				k[j] = x[cv * VEC + j], k2[j] = 0.f;
-			else
-				k[j] = mean[cv * VEC + j], k2[j] = inv_std[cv * VEC + j];
-		}
-		for (size_t r = (size_t)blockIdx.y * rpi + ty; r < rows; r += (size_t)gridDim.y * rpi)
-		{
-			float xv[VEC], gv[VEC];
-			if (VEC == 4)
-			{
-				const float4 t = reinterpret_cast<const float4*>(x + r * C)[cv];
-				xv[0] = t.x, xv[1 % VEC] = t.y, xv[2 % VEC] = t.z, xv[3 % VEC] = t.w;
-				if (MODE == 1)
-				{
-					const float4 u = reinterpret_cast<const float4*>(g + r * C)[cv];
-					gv[0] = u.x, gv[1 % VEC] = u.y, gv[2 % VEC] = u.z, gv[3 % VEC] = u.w;
-				}
-			} else {
-				xv[0] = x[r * C + cv];
-				if (MODE == 1)
-					gv[0] = g[r * C + cv];
-			}
-#pragma unroll
-			for (int j = 0; j < VEC; j++)
-			{
-				if (MODE == 0)
-				{
-					const float d = xv[j] - k[j];
-					s1[j] += d, s2[j] += d * d;
-				} else {
-					s1[j] += gv[j], s2[j] += gv[j] * (xv[j] - k[j]) * k2[j];
-				}
-			}
-		}
-	}
-#pragma unroll
-	for (int j = 0; j < VEC; j++)
-		sh[threadIdx.x * VEC + j] = s1[j], sh[(blockDim.x + threadIdx.x) * VEC + j] = s2[j];
-	__syncthreads();
-	if (ty == 0 && cv < CV)
-	{
-		for (int t = 1; t < rpi; t++)
-#pragma unroll
-			for (int j = 0; j < VEC; j++)
-				s1[j] += sh[(t * cpb + tx) * VEC + j], s2[j] += sh[(blockDim.x + t * cpb + tx) * VEC + j];
-#pragma unroll
-		for (int j = 0; j < VEC; j++)
-		{
-			atomicAdd(ws + cv * VEC + j, (double)s1[j]);
-			atomicAdd(ws + C + cv * VEC + j, (double)s2[j]);
-		}
-	}
-}
-// inner > 1 (NCHW): one block per channel
-template <int MODE>
-__global__ void bn_reduce_generic_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ inv_std, const size_t outer, const int C, const size_t inner, double* __restrict__ ws)
-{
-	__shared__ float sh[32];
-	const int c = blockIdx.x;
-	const float k = MODE == 0 ? x[(size_t)c * inner] : mean[c];
-	const float k2 = MODE == 0 ? 0.f : inv_std[c];
-	float s1 = 0.f, s2 = 0.f;
-	const size_t total = outer * inner;
-	for (size_t i = threadIdx.x; i < total; i += blockDim.x)
-	{
-		const size_t o = i / inner, in = i - o * inner;
-		const size_t idx = (o * C + c) * inner + in;
-		if (MODE == 0)
-		{
-			const float d = x[idx] - k;
-			s1 += d, s2 += d * d;
-		} else {
-			const float gv = g[idx];
-			s1 += gv, s2 += gv * (x[idx] - k) * k2;
-		}
-	}
-	s1 = block_sum(s1, sh);
-	s2 = block_sum(s2, sh);
-	if (threadIdx.x == 0)
-		ws[c] = (double)s1, ws[C + c] = (double)s2;
-}
-__global__ void bn_finalize_kernel(const float* __restrict__ x, const size_t shift_stride, const double* __restrict__ ws, const int C, const double count, const float epsilon, const float momentum, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std)
-{
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= C)
-		return;
-	const double k = (double)x[(size_t)c * shift_stride];
-	const double s1 = ws[c], s2 = ws[C + c];
-	const double mean = k + s1 / count;
-	double var = (s2 - s1 * s1 / count) / count;
-	if (var < 0)
-		var = 0;
-	const float meanf = (float)mean, varf = (float)var;
-	saved_mean[c] = meanf;
-	saved_inv_std[c] = 1.f / sqrtf(varf + epsilon);
-	running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * meanf;
-	running_var[c] = momentum * running_var[c] + (1.f - momentum) * varf;
-}
-// y = (x - mean) * inv_std * scale + bias, evaluated as x * a + b with a = scale * inv_std, b = bias - mean * a
-// (the non-ZERO_MEMORY_ALLOC path of the reference, batch_norm_cpu_ref.c:176-249).  IS_TEST uses 1 / (sqrt(var) + eps).
-template <int VEC, int IS_TEST>
-__global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ var_or_inv_std, const size_t total_vec, const int C, const size_t inner, const float epsilon)
-{
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x)
-	{
-		float xv[VEC];
-		int c[VEC];
-		if (VEC == 4)
-		{
-			const float4 t = reinterpret_cast<const float4*>(x)[i];
-			xv[0] = t.x, xv[1 % VEC] = t.y, xv[2 % VEC] = t.z, xv[3 % VEC] = t.w;
-			const int c0 = (int)((i * 4) % C); // inner == 1 on the vector path
-#pragma unroll
-			for (int j = 0; j < VEC; j++)
-				c[j] = c0 + j;
-		} else {
-			xv[0] = x[i];
-			c[0] = (int)((i / inner) % C);
-		}
-		float o[VEC];
-#pragma unroll
-		for (int j = 0; j < VEC; j++)
-		{
-			const float istd = IS_TEST ? 1.f / (sqrtf(var_or_inv_std[c[j]]) + epsilon) : var_or_inv_std[c[j]];
-			const float a = scale[c[j]] * istd;
-			const float b = bias[c[j]] - mean[c[j]] * a;
-			o[j] = xv[j] * a + b;
-		}
-		if (VEC == 4)
-			reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
-		else
-			y[i] = o[0];
-	}
-}
-static void bn_reduce_config(size_t rows, int CV, int& cpb, dim3& grid)
-{
-	cpb = CV >= 256 ? 256 : CV;
-	// largest divisor-friendly column count: threads beyond rpi * cpb idle
-	const int rpi = 256 / cpb;
-	const int gx = (CV + cpb - 1) / cpb;
-	size_t gy = (rows + (size_t)rpi * 16 - 1) / ((size_t)rpi * 16);
-	const size_t cap = (size_t)(sms() * 4 + gx - 1) / gx;
-	if (gy > cap)
-		gy = cap;
-	if (gy < 1)
-		gy = 1;
-	grid = dim3(gx, (unsigned)gy);
-}
-int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace)
-{
-	double* ws = (double*)workspace;
-	const size_t total = outer * C * inner;
-	if (total == 0)
-		return 0;
-	if (inner == 1)
-	{
-		cudaError_t e = cudaMemsetAsync(ws, 0, bn_workspace_bytes(C), s);
-		if (e != cudaSuccess)
-		{
-			set_last_error("memset(bn)", e);
-			return -1;
-		}
-		const bool vec = C % 4 == 0 && aligned16(x);
-		int cpb;
-		dim3 grid;
-		if (vec)
-		{
-			bn_reduce_config(outer, C / 4, cpb, grid);
-			bn_reduce_nhwc_kernel<4, 0><<<grid, 256, 2 * 256 * 4 * sizeof(float), s>>>(x, 0, 0, 0, outer, C, ws, cpb);
-		} else {
-			bn_reduce_config(outer, C, cpb, grid);
-			bn_reduce_nhwc_kernel<1, 0><<<grid, 256, 2 * 256 * sizeof(float), s>>>(x, 0, 0, 0, outer, C, ws, cpb);
-		}
-		if (check("bn_reduce"))
-			return -1;
-	} else {
-		bn_reduce_generic_kernel<0><<<C, 512, 0, s>>>(x, 0, 0, 0, outer, C, inner, ws);
-		if (check("bn_reduce_generic"))
-			return -1;
-	}
-	bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, inner, ws, C, (double)outer * (double)inner, epsilon, momentum, running_mean, running_var, saved_mean, saved_inv_std);
-	if (check("bn_finalize"))
-		return -1;
-	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(y))
-		bn_apply_kernel<4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(x, y, scale, bias, saved_mean, saved_inv_std, total / 4, C, 1, epsilon);
-	else
-		bn_apply_kernel<1, 0><<<grid_for(total, 256), 256, 0, s>>>(x, y, scale, bias, saved_mean, saved_inv_std, total, C, inner, epsilon);
-	return check("bn_apply");
-}
-int bn_fwd_test_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, const float* mean, const float* var, size_t outer, int C, size_t inner, float epsilon)
-{
-	const size_t total = outer * C * inner;
-	if (total == 0)
-		return 0;
-	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(y))
-		bn_apply_kernel<4, 1><<<grid_for(total / 4, 256), 256, 0, s>>>(x, y, scale, bias, mean, var, total / 4, C, 1, epsilon);
-	else
-		bn_apply_kernel<1, 1><<<grid_for(total, 256), 256, 0, s>>>(x, y, scale, bias, mean, var, total, C, inner, epsilon);
-	return check("bn_apply_test");
-}
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, const int C, float* __restrict__ dscale, float* __restrict__ dbias)
-{
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= C)
-		return;
-	if (dbias)
-		dbias[c] = (float)ws[c];
-	if (dscale)
-		dscale[c] = (float)ws[C + c];
-}
-// h = scale * inv_std / count * (count * g - dbias - xhat * dscale)   (batch_norm_cpu_ref.c:430-466)
-template <int VEC>
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ mean, const float* __restrict__ inv_std, const double* __restrict__ ws, float* __restrict__ dx, const size_t total_vec, const int C, const size_t inner, const float count)
-{
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x)
-	{
-		float xv[VEC], gv[VEC];
-		int c[VEC];
-		if (VEC == 4)
-		{
-			const float4 t = reinterpret_cast<const float4*>(x)[i];
-			const float4 u = reinterpret_cast<const float4*>(g)[i];
-			xv[0] = t.x, xv[1 % VEC] = t.y, xv[2 % VEC] = t.z, xv[3 % VEC] = t.w;
-			gv[0] = u.x, gv[1 % VEC] = u.y, gv[2 % VEC] = u.z, gv[3 % VEC] = u.w;
-			const int c0 = (int)((i * 4) % C);
-#pragma unroll
-			for (int j = 0; j < VEC; j++)
-				c[j] = c0 + j;
-		} else {
-			xv[0] = x[i], gv[0] = g[i];
-			c[0] = (int)((i / inner) % C);
-		}
-		float o[VEC];
-#pragma unroll
-		for (int j = 0; j < VEC; j++)
-		{
-			const float istd = inv_std[c[j]];
-			const float xhat = (xv[j] - mean[c[j]]) * istd;
-			const float sisb = scale[c[j]] * istd / count;
-			o[j] = sisb * (count * gv[j] - (float)ws[c[j]] - xhat * (float)ws[C + c[j]]);
-		}
-		if (VEC == 4)
-			reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
-		else
-			dx[i] = o[0];
-	}
-}
-int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* saved_mean, const float* saved_inv_std, float* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace)
-{
-	double* ws = (double*)workspace;
-	const size_t total = outer * C * inner;
-	if (total == 0)
-		return 0;
-	if (inner == 1)
-	{
-		cudaError_t e = cudaMemsetAsync(ws, 0, bn_workspace_bytes(C), s);
-		if (e != cudaSuccess)
-		{
-			set_last_error("memset(bn_bwd)", e);
-			return -1;
-		}
-		const bool vec = C % 4 == 0 && aligned16(x) && aligned16(g);
-		int cpb;
-		dim3 grid;
-		if (vec)
-		{
-			bn_reduce_config(outer, C / 4, cpb, grid);
-			bn_reduce_nhwc_kernel<4, 1><<<grid, 256, 2 * 256 * 4 * sizeof(float), s>>>(x, g, saved_mean, saved_inv_std, outer, C, ws, cpb);
-		} else {
-			bn_reduce_config(outer, C, cpb, grid);
-			bn_reduce_nhwc_kernel<1, 1><<<grid, 256, 2 * 256 * sizeof(float), s>>>(x, g, saved_mean, saved_inv_std, outer, C, ws, cpb);
-		}
-		if (check("bn_bwd_reduce"))
-			return -1;
-	} else {
-		bn_reduce_generic_kernel<1><<<C, 512, 0, s>>>(x, g, saved_mean, saved_inv_std, outer, C, inner, ws);
-		if (check("bn_bwd_reduce_generic"))
-			return -1;
-	}
-	if (dscale || dbias)
-	{
-		bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(ws, C, dscale, dbias);
-		if (check("bn_bwd_finalize"))
-			return -1;
-	}
-	if (!dx)
-		return 0;
-	const float count = (float)((double)outer * (double)inner);
-	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(g) && aligned16(dx))
-		bn_bwd_apply_kernel<4><<<grid_for(total / 4, 256), 256, 0, s>>>(g, x, scale, saved_mean, saved_inv_std, ws, dx, total / 4, C, 1, count);
-	else
-		bn_bwd_apply_kernel<1><<<grid_for(total, 256), 256, 0, s>>>(g, x, scale, saved_mean, saved_inv_std, ws, dx, total, C, inner, count);
-	return check("bn_bwd_apply");
-}
-
 // =============================================================================================== softmax / losses
 // softmax/ccv_nnc_softmax_cpu_ref.c:13-40: per row, b = exp(a - max) / sum; one block per row
 __global__ void softmax_fwd_kernel(const float* __restrict__ a, float* __restrict__ b, const int count)

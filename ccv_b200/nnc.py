@@ -64,6 +64,14 @@ def lib():
         l.ccv_nnc_sm100_graph_size.argtypes = [vp]
         l.ccv_nnc_sm100_graph_run.restype = i32
         l.ccv_nnc_sm100_graph_run.argtypes = [vp, i32, i32, vp]
+        l.ccv_nnc_sm100_graph_fuse.restype = i32
+        l.ccv_nnc_sm100_graph_fuse.argtypes = [vp]
+        l.ccv_nnc_sm100_graph_node.restype = i32
+        l.ccv_nnc_sm100_graph_node.argtypes = [vp, i32, C.POINTER(u32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        l.ccv_nnc_sm100_graph_node_tensor.restype = vp
+        l.ccv_nnc_sm100_graph_node_tensor.argtypes = [vp, i32, i32, i32]
+        l.ccv_nnc_sm100_graph_profile.restype = i32
+        l.ccv_nnc_sm100_graph_profile.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
         l.ccv_nnc_sm100_graph_capture.restype = i32
         l.ccv_nnc_sm100_graph_capture.argtypes = [vp, i32, i32, vp]
         l.ccv_nnc_sm100_graph_replay.restype = i32
@@ -257,6 +265,27 @@ class Graph(object):
 
     def __len__(self):
         return lib().ccv_nnc_sm100_graph_size(self.ptr)
+
+    def fuse(self):
+        """Peephole fusion of adjacent commands (BN+ReLU, ReLU+BN backward, residual add + ReLU); returns the number of pairs."""
+        return lib().ccv_nnc_sm100_graph_fuse(self.ptr)
+
+    def nodes(self):
+        """[(cmd id, fused kind, [input tensor pointers], [output tensor pointers])] of the current (possibly fused) list"""
+        out = []
+        for i in range(len(self)):
+            cmd, fk, ni, no = C.c_uint32(), C.c_int(), C.c_int(), C.c_int()
+            lib().ccv_nnc_sm100_graph_node(self.ptr, i, C.byref(cmd), C.byref(fk), C.byref(ni), C.byref(no))
+            ins = [lib().ccv_nnc_sm100_graph_node_tensor(self.ptr, i, 0, k) for k in range(ni.value)]
+            outs = [lib().ccv_nnc_sm100_graph_node_tensor(self.ptr, i, 1, k) for k in range(no.value)]
+            out.append((cmd.value, fk.value, ins, outs))
+        return out
+
+    def profile(self, stream, reps=3):
+        """per-node device milliseconds (CUDA events around each node, best of reps)"""
+        ms = (C.c_float * max(len(self), 1))()
+        lib().ccv_nnc_sm100_graph_profile(self.ptr, stream.ptr, reps, ms)
+        return [float(x) for x in ms][:len(self)]
 
     def run(self, stream, begin=0, end=-1):
         return lib().ccv_nnc_sm100_graph_run(self.ptr, begin, end, stream.ptr)

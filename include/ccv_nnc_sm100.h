@@ -495,6 +495,14 @@ int ccv_nnc_sm100_graph_exec_new(ccv_nnc_sm100_graph_t* const graph, const uint3
 int ccv_nnc_sm100_graph_size(const ccv_nnc_sm100_graph_t* const graph);
 /* runs nodes [begin, end) in order on the stream; returns the first non-zero exec status */
 int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin, const int end, ccv_nnc_stream_context_t* const stream_context);
+/* peephole fusion of adjacent nodes (BN+ReLU forward, ReLU+BN backward, residual add + ReLU forward / backward); node
+ * indices change, so call it before choosing capture ranges. Returns the number of pairs fused. */
+int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph);
+/* introspection and per-node device timing (CUDA events, best of reps) of the (possibly fused) node list;
+ * fused_kind: 0 plain command, 1 bn+relu forward, 2 relu+bn backward, 3 add+relu forward, 4 add+relu backward */
+int ccv_nnc_sm100_graph_node(const ccv_nnc_sm100_graph_t* const graph, const int i, uint32_t* const cmd, int* const fused_kind, int* const input_size, int* const output_size);
+void* ccv_nnc_sm100_graph_node_tensor(const ccv_nnc_sm100_graph_t* const graph, const int i, const int is_output, const int k);
+int ccv_nnc_sm100_graph_profile(ccv_nnc_sm100_graph_t* const graph, ccv_nnc_stream_context_t* const stream_context, const int reps, float* const ms);
 /* capture nodes [begin, end) into a CUDA graph (id returned, <0 on failure) / replay it */
 int ccv_nnc_sm100_graph_capture(ccv_nnc_sm100_graph_t* const graph, const int begin, const int end, ccv_nnc_stream_context_t* const stream_context);
 int ccv_nnc_sm100_graph_replay(ccv_nnc_sm100_graph_t* const graph, const int capture_id, ccv_nnc_stream_context_t* const stream_context);
