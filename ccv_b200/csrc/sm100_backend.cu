@@ -342,7 +342,14 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	float* b = outputs[0]->data.f32;
 	if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
 	{
-		const int rc = conv_fprop_tf32(s, g, a, w, bias, b);
+		int rc = conv_fprop_tf32(s, g, a, w, bias, b);
+		if (rc > 0 && g.C % 4 != 0)
+		{
+			// TMA cannot address 12-byte pixels (the 3-channel stem): explicit im2col + tensor-core GEMM
+			void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, conv_im2col_workspace_bytes(g), CCV_TENSOR_GPU_MEMORY);
+			if (ws)
+				rc = conv_fprop_im2col_tf32(s, g, a, w, bias, b, ws);
+		}
 		if (rc == 0)
 			return CCV_NNC_EXEC_SUCCESS;
 		if (rc < 0)
@@ -383,7 +390,15 @@ int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	{
 		int rc = 1;
 		if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
+		{
 			rc = conv_wgrad_tf32(s, g, gb, a, dw_t->data.f32, accumulate);
+			if (rc > 0 && g.C % 4 != 0)
+			{
+				void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, conv_im2col_workspace_bytes(g), CCV_TENSOR_GPU_MEMORY);
+				if (ws)
+					rc = conv_wgrad_im2col_tf32(s, g, gb, a, dw_t->data.f32, accumulate, ws);
+			}
+		}
 		if (rc < 0)
 			return CCV_NNC_EXEC_INVALID;
 		if (rc > 0)
@@ -1214,8 +1229,8 @@ REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_
 REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); }
 REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); }
 REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); }
-REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_forw); }
-REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_back); }
+REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_sdpa_forw); }
+REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_sdpa_back); }
 REGISTER_SM100(CCV_NNC_SOFTMAX_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_forw); }
 REGISTER_SM100(CCV_NNC_SOFTMAX_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_back); }
 REGISTER_SM100(CCV_NNC_BATCH_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_bnorm_forw); }

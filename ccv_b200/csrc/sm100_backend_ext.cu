@@ -72,8 +72,108 @@ bool rows_inner(const ccv_nnc_tensor_t* const x, const int* const axis, const in
 
 extern "C" {
 
-int ccv_nnc_sm100_exec_sdpa_forw(SM100_EXEC_ARGS) { return CCV_NNC_EXEC_NO_KERNEL; }
-int ccv_nnc_sm100_exec_sdpa_back(SM100_EXEC_ARGS) { return CCV_NNC_EXEC_NO_KERNEL; }
+// ---- scaled dot product attention ----------------------------------------------------------------------------------
+// [B, S, H, D] tensors (3-d [B, S, D] = one head), element strides from views; the feature axis must be contiguous
+static bool sdpa_axes(const ccv_nnc_tensor_t* const t, int& B, int& S, int& H, int& D, long long& sb, long long& ss, long long& sh)
+{
+	if (CCV_GET_DATA_TYPE(t->info.datatype) != CCV_32F)
+		return false;
+	const int nd = nd_of(t);
+	if (nd != 3 && nd != 4)
+		return false;
+	long long stride[4];
+	if (CCV_IS_TENSOR_VIEW(t))
+		for (int i = 0; i < nd; i++)
+			stride[i] = ((const ccv_nnc_tensor_view_t*)t)->stride[i];
+	else {
+		long long packed = 1;
+		for (int i = nd - 1; i >= 0; i--)
+			stride[i] = packed, packed *= t->info.dim[i];
+	}
+	if (stride[nd - 1] != 1)
+		return false;
+	B = t->info.dim[0], S = t->info.dim[1];
+	sb = stride[0], ss = stride[1];
+	if (nd == 4)
+		H = t->info.dim[2], D = t->info.dim[3], sh = stride[2];
+	else
+		H = 1, D = t->info.dim[2], sh = 0;
+	return true;
+}
+
+static bool sdpa_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_tensor_t* const q, const ccv_nnc_tensor_t* const k, const ccv_nnc_tensor_t* const v, const ccv_nnc_tensor_t* const o, SdpaGeom& g)
+{
+	memset(&g, 0, sizeof(g));
+	int B2, B3, B4, H3, H4, D2, S3, S4;
+	if (!sdpa_axes(q, g.B, g.Sq, g.H, g.D, g.q_b, g.q_s, g.q_h) || !sdpa_axes(k, B2, g.Sk, g.Hk, D2, g.k_b, g.k_s, g.k_h) ||
+		!sdpa_axes(v, B3, S3, H3, g.Dv, g.v_b, g.v_s, g.v_h) || !sdpa_axes(o, B4, S4, H4, D2, g.o_b, g.o_s, g.o_h))
+		return false;
+	if (B2 != g.B || B3 != g.B || B4 != g.B || S3 != g.Sk || S4 != g.Sq || H3 != g.Hk || H4 != g.H || D2 != g.Dv || g.Hk <= 0 || g.H % g.Hk != 0)
+		return false;
+	if (k->info.dim[nd_of(k) - 1] != g.D)
+		return false;
+	g.scale = cmd.info.scaled_dot_product_attention.scale;
+	g.is_causal = cmd.info.scaled_dot_product_attention.is_causal;
+	return true;
+}
+
+// scaled_dot_product_attention/ccv_nnc_scaled_dot_product_attention_cpu_ref.c:16-183: inputs (q, k, v, [attn_mask]) ->
+// outputs (y, [softmax_lse]).  The fused "unify head" projection (inputs 4, 5) is not offered (CCV_NNC_EXEC_INVALID), the
+// same restriction the reference's flash-attention backend has for its backward (…flash_attn.cu:247-248).
+int ccv_nnc_sm100_exec_sdpa_forw(SM100_EXEC_ARGS)
+{
+	if (input_size < 3 || output_size < 1 || !inputs[0] || !inputs[1] || !inputs[2] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	if (input_size > 4 && inputs[4])
+		return CCV_NNC_EXEC_INVALID;
+	SdpaGeom g;
+	if (!sdpa_geom(cmd, inputs[0], inputs[1], inputs[2], outputs[0], g))
+		return CCV_NNC_EXEC_INVALID;
+	const ccv_nnc_tensor_t* const mask_t = input_size > 3 ? inputs[3] : 0;
+	const float* mask = 0;
+	if (mask_t)
+	{
+		// [.., Sq, Sk] with optional leading (batch, head) axes of extent 1 or full (:82-86,:104)
+		const int nd = nd_of(mask_t);
+		if (!packed_f32(mask_t) || nd < 2 || nd > 4 || mask_t->info.dim[nd - 1] != g.Sk || mask_t->info.dim[nd - 2] != g.Sq)
+			return CCV_NNC_EXEC_INVALID;
+		int md[4] = { 1, 1, g.Sq, g.Sk };
+		for (int i = 0; i < nd - 2; i++)
+			md[2 - (nd - 2) + i] = mask_t->info.dim[i];
+		if ((md[0] != 1 && md[0] != g.B) || (md[1] != 1 && md[1] != g.H))
+			return CCV_NNC_EXEC_INVALID;
+		g.mask_c = 1, g.mask_s = g.Sk;
+		g.mask_h = md[1] > 1 ? (long long)g.Sq * g.Sk : 0;
+		g.mask_b = md[0] > 1 ? (long long)md[1] * g.Sq * g.Sk : 0;
+		mask = mask_t->data.f32;
+	}
+	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, sdpa_workspace_bytes(g.Sq, g.Sk, 0), CCV_TENSOR_GPU_MEMORY);
+	if (!ws)
+		return CCV_NNC_EXEC_OOM;
+	if (sdpa_forward_f32(stream_of(stream_context), g, inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, mask, outputs[0]->data.f32, ws))
+		return CCV_NNC_EXEC_INVALID;
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// :259-479: inputs[0] = g, [3] = q, [4] = k, [5] = v -> outputs (dq, dk, dv); masks are not differentiable here either (:262)
+int ccv_nnc_sm100_exec_sdpa_back(SM100_EXEC_ARGS)
+{
+	if (input_size < 6 || output_size < 3 || !inputs[0] || !inputs[3] || !inputs[4] || !inputs[5] || !outputs[0] || !outputs[1] || !outputs[2])
+		return CCV_NNC_EXEC_INVALID;
+	if ((input_size > 6 && inputs[6]) || (input_size > 7 && inputs[7]))
+		return CCV_NNC_EXEC_INVALID;
+	SdpaGeom g, dg;
+	if (!sdpa_geom(cmd, inputs[3], inputs[4], inputs[5], inputs[0], g) || !sdpa_geom(cmd, outputs[0], outputs[1], outputs[2], inputs[0], dg))
+		return CCV_NNC_EXEC_INVALID;
+	if (dg.B != g.B || dg.H != g.H || dg.Hk != g.Hk || dg.Sq != g.Sq || dg.Sk != g.Sk || dg.D != g.D || dg.Dv != g.Dv)
+		return CCV_NNC_EXEC_INVALID;
+	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, sdpa_workspace_bytes(g.Sq, g.Sk, 1), CCV_TENSOR_GPU_MEMORY);
+	if (!ws)
+		return CCV_NNC_EXEC_OOM;
+	if (sdpa_backward_f32(stream_of(stream_context), g, inputs[0]->data.f32, inputs[3]->data.f32, inputs[4]->data.f32, inputs[5]->data.f32, outputs[0]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, dg, ws))
+		return CCV_NNC_EXEC_INVALID;
+	return CCV_NNC_EXEC_SUCCESS;
+}
 // ---- layer norm / rms norm: statistics over the trailing axes (saved_mean dims [d0, .., 1, .., 1]) -----------------
 // norm/ccv_nnc_layer_norm_cpu_ref.c:16-190: inputs (x, [scale, bias]) -> outputs (y, [saved_mean, saved_inv_std])
 int ccv_nnc_sm100_exec_lnorm_forw(SM100_EXEC_ARGS)

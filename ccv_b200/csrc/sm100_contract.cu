@@ -3,7 +3,7 @@
 // onto its operand modes.  Reference semantics being reproduced: lib/nnc/cmd/blas/ccv_nnc_gemm_cpu_ref.c:110-448,
 // lib/nnc/cmd/convolution/ccv_nnc_conv_cpu_ref.c:13-345 (NHWC).
 #include "sm100_contract.h"
-#include "sm100_umma_gemm.cuh"
+#include "sm100_umma_persistent.cuh"
 #include <atomic>
 #include <mutex>
 #include <stdio.h>
@@ -134,10 +134,83 @@ static int launch_umma(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 	return 0;
 }
 
-// BN = 128 with 3 stages (2 CTAs/SM) is the default shape; BN = 64 keeps small-N problems from wasting MMA columns.
+template <int AMODE, int BMODE, int BN, int STAGES, int EPIW>
+static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p)
+{
+	using S = UmmaPersistentSmem<BN, STAGES, EPIW>;
+	auto kern = umma_gemm_persistent_kernel<AMODE, BMODE, BN, STAGES, EPIW>;
+	static bool configured = false;
+	if (!configured)
+	{
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+		if (e != cudaSuccess)
+		{
+			set_last_error("cudaFuncSetAttribute(umma_gemm_persistent_kernel)", e);
+			return -1;
+		}
+		configured = true;
+	}
+	const long long tiles = (long long)((p.M + UMMA_BLOCK_M - 1) / UMMA_BLOCK_M) * ((p.N + BN - 1) / BN) * p.grid_taps * p.splits;
+	const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+	kern<<<grid, S::THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+	count_launch();
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error("umma_gemm_persistent_kernel launch", e);
+		return -1;
+	}
+	return 0;
+}
+
+static bool use_persistent()
+{
+	static int v = -1;
+	if (v < 0)
+	{
+		const char* e = getenv("CCV_NNC_SM100_PERSISTENT");
+		v = e ? atoi(e) : 1;
+	}
+	return v != 0;
+}
+
+// Kernel choice, from the measurements in profiles/r01_probe3_*.log and r01_probe4_*.log:
+//  * BN = 64 (<= 64 output columns) and weight gradients with <= 128 columns: the one-tile-per-CTA kernel, two CTAs per SM
+//    (these are L2-bound / short tiles; two independent CTAs hide more latency than one persistent CTA);
+//  * otherwise the persistent kernel: long reductions (>= 12 k-iterations per tile) use 4 epilogue warps and the deepest
+//    operand pipeline (MMA-bound), short ones use 8 epilogue warps (the epilogue is then the critical path).
+// CCV_NNC_SM100_PERSISTENT=0 forces the one-tile kernel, =2 forces the persistent one, for A/B runs.
+static int persistent_mode()
+{
+	static int v = -1;
+	if (v < 0)
+	{
+		const char* e = getenv("CCV_NNC_SM100_PERSISTENT");
+		v = e ? atoi(e) : 1;
+	}
+	return v;
+}
+static bool use_persistent() { return persistent_mode() != 0; }
+
 template <int AMODE, int BMODE>
 static int launch_umma_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p, int bn)
 {
+	const int mode = persistent_mode();
+	const int iters_per_tile = (p.k_iters + p.splits - 1) / p.splits;
+	bool persistent = mode != 0;
+	if (mode == 1 && (bn == 64 || (BMODE == OP_IM2COL && bn == 128)))
+		persistent = false;
+	if (persistent)
+	{
+		const bool long_k = iters_per_tile >= 12;
+		if (bn == 64)
+			return launch_umma_persistent<AMODE, BMODE, 64, 7, 8>(stream, tmA, tmB, p);
+		if (bn == 256)
+			return long_k ? launch_umma_persistent<AMODE, BMODE, 256, 4, 4>(stream, tmA, tmB, p) : launch_umma_persistent<AMODE, BMODE, 256, 3, 8>(stream, tmA, tmB, p);
+		return long_k ? launch_umma_persistent<AMODE, BMODE, 128, 6, 4>(stream, tmA, tmB, p) : launch_umma_persistent<AMODE, BMODE, 128, 5, 8>(stream, tmA, tmB, p);
+	}
+	if (bn == 256)
+		bn = 128;
 	const int gx = (p.M + UMMA_BLOCK_M - 1) / UMMA_BLOCK_M;
 	const int gy = (p.N + bn - 1) / bn;
 	if (bn == 64)
@@ -148,9 +221,12 @@ static int launch_umma_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUt
 static int pick_bn(int N)
 {
 	const char* e = getenv("CCV_NNC_SM100_BN");
-	if (e)
-		return atoi(e) == 64 ? 64 : 128;
-	return N <= 64 ? 64 : 128;
+	int bn = e ? atoi(e) : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+	if (bn != 64 && bn != 128 && bn != 256)
+		bn = 128;
+	if (bn == 256 && !use_persistent())
+		bn = 128;
+	return bn;
 }
 
 static void init_params(UmmaGemmParams& p)
@@ -471,6 +547,104 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 			p.tap_off_w[t] = (unsigned short)(s * g.dil_w);
 		}
 	return launch_umma_bn<OP_MN2D, OP_IM2COL>(stream, tmA, tmB, p, bn);
+}
+
+// ------------------------------------------------------------------------------------------------ explicit im2col
+static inline int im2col_kp(const ConvGeom& g) { return (g.R * g.S * g.C + 31) / 32 * 32; }
+static inline bool im2col_applicable(const ConvGeom& g)
+{
+	return g.R * g.S * g.C <= 256 && (long long)g.N * g.P * g.Q <= 0x7fffffffll && g.K % 4 == 0 && g.bw == g.K && g.bh == (long long)g.Q * g.K && g.bn == (long long)g.P * g.Q * g.K;
+}
+size_t conv_im2col_workspace_bytes(const ConvGeom& g)
+{
+	const size_t kp = im2col_kp(g);
+	// patches [NPQ, Kp] + packed filters [K, Kp] + packed filter gradient [K, Kp]
+	return ((size_t)g.N * g.P * g.Q * kp + 2 * (size_t)g.K * kp) * sizeof(float) + 512;
+}
+// patches[m, (r, s, c)] = a[n, p * stride - pad + r * dil, q * stride - pad + s * dil, c] (0 outside / in the padding columns)
+__global__ void im2col_kernel(const ConvGeom g, const float* __restrict__ a, float* __restrict__ out, const int kp, const size_t total)
+{
+	const int rsc = g.R * g.S * g.C;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const int k = (int)(i % kp);
+		const size_t m = i / kp;
+		float v = 0.f;
+		if (k < rsc)
+		{
+			const int c = k % g.C;
+			const int t = k / g.C;
+			const int s = t % g.S, r = t / g.S;
+			const int q = (int)(m % g.Q);
+			const size_t u = m / g.Q;
+			const int p = (int)(u % g.P);
+			const int n = (int)(u / g.P);
+			const int h = p * g.stride_h - g.pad_h0 + r * g.dil_h, w = q * g.stride_w - g.pad_w0 + s * g.dil_w;
+			if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+				v = __ldg(a + n * g.an + h * g.ah + w * g.aw + c);
+		}
+		out[i] = v;
+	}
+}
+// dir 0: packed[k, 0..kp) = w[k, 0..rsc) zero padded.  dir 1: w[k, j] (+)= packed[k, j]
+__global__ void pack_filters_kernel(float* __restrict__ w, float* __restrict__ packed, const int K, const int rsc, const int kp, const int dir, const int accumulate)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= K * kp)
+		return;
+	const int k = i / kp, j = i % kp;
+	if (dir == 0)
+		packed[i] = j < rsc ? w[(size_t)k * rsc + j] : 0.f;
+	else if (j < rsc)
+		w[(size_t)k * rsc + j] = accumulate ? w[(size_t)k * rsc + j] + packed[i] : packed[i];
+}
+static int run_im2col(cudaStream_t stream, const ConvGeom& g, const float* a, float* patches, int kp)
+{
+	const size_t total = (size_t)g.N * g.P * g.Q * kp;
+	size_t blocks = (total + 255) / 256;
+	if (blocks > (size_t)num_sms() * 16)
+		blocks = (size_t)num_sms() * 16;
+	im2col_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, a, patches, kp, total);
+	count_launch();
+	const cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error("im2col_kernel", e);
+		return -1;
+	}
+	return 0;
+}
+int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, void* workspace)
+{
+	if (!tma_api_init() || !im2col_applicable(g) || !workspace)
+		return 1;
+	const int kp = im2col_kp(g), rsc = g.R * g.S * g.C;
+	const size_t m = (size_t)g.N * g.P * g.Q;
+	float* patches = (float*)workspace;
+	float* wp = patches + m * kp;
+	if (run_im2col(stream, g, a, patches, kp))
+		return -1;
+	pack_filters_kernel<<<(g.K * kp + 255) / 256, 256, 0, stream>>>((float*)w, wp, g.K, rsc, kp, 0, 0);
+	count_launch();
+	return gemm_tf32(stream, (int)m, g.K, kp, patches, kp, 0, wp, kp, 1, b, g.K, bias, 0);
+}
+int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, void* workspace)
+{
+	if (!tma_api_init() || !im2col_applicable(g) || !workspace)
+		return 1;
+	const int kp = im2col_kp(g), rsc = g.R * g.S * g.C;
+	const size_t m = (size_t)g.N * g.P * g.Q;
+	float* patches = (float*)workspace;
+	float* dwp = patches + m * kp + (size_t)g.K * kp;
+	if (run_im2col(stream, g, a, patches, kp))
+		return -1;
+	// dWp[K, Kp] = grad_b^T [K, NPQ] * patches [NPQ, Kp]
+	const int rc = gemm_tf32(stream, g.K, kp, (int)m, grad_b, g.K, 1, patches, kp, 0, dwp, kp, 0, 0);
+	if (rc)
+		return rc;
+	pack_filters_kernel<<<(g.K * kp + 255) / 256, 256, 0, stream>>>(grad_w, dwp, g.K, rsc, kp, 1, accumulate);
+	count_launch();
+	return 0;
 }
 
 } // namespace sm100

@@ -26,11 +26,31 @@ int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, cons
 int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a);
 int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate);
 
+// Small-channel convolutions (C not a multiple of 4, e.g. the 3-channel stem): explicit im2col into `workspace`
+// ([N*P*Q, Kp] with Kp = R*S*C rounded up to 32, zero padded) followed by the tensor-core GEMM.  Returns 1 when not applicable.
+size_t conv_im2col_workspace_bytes(const ConvGeom& g);
+int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, void* workspace);
+int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, void* workspace);
+
 // CUDA-core fp32 versions of the same contractions: any stride/alignment, groups, exact fp32 products.
 int gemm_ffma(cudaStream_t stream, int M, int N, int K, const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c, long long ldc, const float* bias, int accumulate);
 int conv_fprop_ffma(cudaStream_t stream, const ConvGeom& g, int groups, const float* a, const float* w, const float* bias, float* b);
 int conv_dgrad_ffma(cudaStream_t stream, const ConvGeom& g, int groups, const float* grad_b, const float* w, float* grad_a);
 int conv_wgrad_ffma(cudaStream_t stream, const ConvGeom& g, int groups, const float* grad_b, const float* a, float* grad_w, int accumulate);
+
+// scaled dot product attention (sm100_sdpa.cu): element strides of q [B, Sq, H, D], k / v [B, Sk, Hk, D | Dv], o [B, Sq, H, Dv]
+struct SdpaGeom {
+	int B, H, Hk, Sq, Sk, D, Dv;
+	float scale;
+	int is_causal;
+	long long q_b, q_s, q_h, k_b, k_s, k_h, v_b, v_s, v_h, o_b, o_s, o_h;
+	long long mask_b, mask_h, mask_s; // additive mask [B | 1, H | 1, Sq, Sk]: 0 strides broadcast
+	int mask_c;
+};
+size_t sdpa_workspace_bytes(int sq, int sk, int backward);
+int sdpa_forward_f32(cudaStream_t s, const SdpaGeom& g, const float* q, const float* k, const float* v, const float* mask, float* o, void* workspace);
+// dg carries the strides of dq / dk / dv in its q_* / k_* / v_* fields
+int sdpa_backward_f32(cudaStream_t s, const SdpaGeom& g, const float* dout, const float* q, const float* k, const float* v, float* dq, float* dk, float* dv, const SdpaGeom& dg, void* workspace);
 
 // bookkeeping shared by every launcher in the backend
 void count_launch(int n = 1);

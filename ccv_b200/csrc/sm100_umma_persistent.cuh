@@ -1,0 +1,302 @@
+// sm100_umma_persistent.cuh -- persistent form of the contraction kernel (same operand modes and parameters as
+// sm100_umma_gemm.cuh): one CTA per SM loops over output tiles, so that
+//   * the TMA producer runs ahead across tile boundaries (no pipeline refill, no per-tile barrier init / TMEM alloc),
+//   * accumulators are double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of tile i + 1,
+//   * the epilogue transposes each 32 x 32 accumulator chunk through shared memory and writes it with 128-bit stores in
+//     which every 128-byte line is written whole (4 rows x 128 B per warp instruction) instead of 32 scattered 16-byte
+//     pieces per instruction.
+// Roles: warp 0 TMA producer, warp 1 TMEM allocator + tcgen05.mma issuer, warps 2..9 epilogue (two warps per TMEM lane
+// quarter, each taking every other 32-column chunk: with a single warp per scheduler the epilogue's dependent
+// LDTM -> STS -> LDS -> STG chain was latency-bound -- profiles/r01_ncu_gemm_n256k64.txt).
+#pragma once
+#include "sm100_umma_gemm.cuh"
+
+namespace sm100 {
+
+template <int BN, int STAGES, int EPIW>
+struct UmmaPersistentSmem {
+	static constexpr int A_BYTES = UMMA_BLOCK_M * UMMA_BLOCK_K * 4;
+	static constexpr int B_BYTES = BN * UMMA_BLOCK_K * 4;
+	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+	static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+	static constexpr int EPI_PITCH = 36;                       // floats per scratch row: 16-byte aligned, bank-shifted
+	static constexpr int EPI_WARPS = EPIW; // 4: one warp per TMEM lane quarter; 8: two, each taking every other 32-column chunk
+	static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4; // one 32 x 32 chunk per epilogue warp
+	static constexpr int THREADS = 64 + EPI_WARPS * 32;
+	static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+	static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+};
+
+template <int AMODE, int BMODE, int BN, int STAGES, int EPIW>
+__global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaGemmParams p)
+{
+	using S = UmmaPersistentSmem<BN, STAGES, EPIW>;
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	uint64_t* full_bar = (uint64_t*)(smem + S::BAR_OFFSET);
+	uint64_t* empty_bar = full_bar + STAGES;
+	uint64_t* tmem_full_bar = empty_bar + STAGES; // [2]
+	uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
+	uint32_t* tmem_slot = (uint32_t*)(tmem_empty_bar + 2);
+
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const int tiles_m = (p.M + UMMA_BLOCK_M - 1) / UMMA_BLOCK_M;
+	const int tiles_n = (p.N + BN - 1) / BN;
+	const int total_tiles = tiles_m * tiles_n * p.grid_taps * p.splits;
+	const int per = (p.k_iters + p.splits - 1) / p.splits;
+
+	if (warp == 0 && lane == 0)
+	{
+		tma_prefetch_desc(&tmA);
+		tma_prefetch_desc(&tmB);
+		for (int s = 0; s < STAGES; s++)
+		{
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], 1);
+		}
+		for (int a = 0; a < 2; a++)
+		{
+			mbar_init(&tmem_full_bar[a], 1);
+			mbar_init(&tmem_empty_bar[a], S::EPI_WARPS); // one arrival per epilogue warp
+		}
+		fence_mbar_init();
+	}
+	if (warp == 1)
+	{
+		tmem_alloc(tmem_slot, 2 * BN);
+		tmem_relinquish();
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp == 0)
+	{
+		// ------------------------------------------------------------------ TMA producer
+		if (lane == 0)
+		{
+			int stage = 0;
+			uint32_t phase = 0;
+			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+			{
+				const int n_blk = tile % tiles_n;
+				const int rest = tile / tiles_n;
+				const int m_blk = rest % tiles_m;
+				const int zz = rest / tiles_m;
+				const int split = zz % p.splits, gtap = zz / p.splits;
+				const int m0 = m_blk * UMMA_BLOCK_M, n0 = n_blk * BN;
+				const int it_begin = split * per;
+				const int it_end = min(p.k_iters, it_begin + per);
+				int a_w = 0, a_h = 0, a_n = 0;
+				if (AMODE == OP_IM2COL)
+				{
+					const int q = m0 % p.Q;
+					const int t = m0 / p.Q;
+					a_w = q * p.stride_w + p.base_w;
+					a_h = (t % p.P) * p.stride_h + p.base_h;
+					a_n = t / p.P;
+				}
+				for (int it = it_begin; it < it_end; it++)
+				{
+					const int tap = it / p.chunks_per_tap;
+					const int chunk = it - tap * p.chunks_per_tap;
+					mbar_wait(&empty_bar[stage], phase ^ 1);
+					uint8_t* sA = smem + stage * S::STAGE_BYTES;
+					uint8_t* sB = sA + S::A_BYTES;
+					mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+					if (AMODE == OP_K2D)
+						tma_load_2d(sA, &tmA, &full_bar[stage], chunk * UMMA_BLOCK_K, m0);
+					else if (AMODE == OP_MN2D) {
+#pragma unroll
+						for (int j = 0; j < UMMA_BLOCK_M / 32; j++)
+							tma_load_2d(sA + j * 4096, &tmA, &full_bar[stage], m0 + 32 * j, it * UMMA_BLOCK_K);
+					} else
+						tma_load_im2col_4d(sA, &tmA, &full_bar[stage], chunk * UMMA_BLOCK_K, a_w, a_h, a_n, p.tap_off_w[tap], p.tap_off_h[tap]);
+					if (BMODE == OP_K2D)
+						tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_b_col[tap] + chunk * UMMA_BLOCK_K, n0);
+					else if (BMODE == OP_MN2D) {
+#pragma unroll
+						for (int j = 0; j < BN / 32; j++)
+							tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], p.tap_b_col[tap] + n0 + 32 * j, chunk * UMMA_BLOCK_K);
+					} else {
+						const int pix = it * UMMA_BLOCK_K;
+						const int q = pix % p.Q;
+						const int t = pix / p.Q;
+						const int b_w = q * p.stride_w + p.base_w;
+						const int b_h = (t % p.P) * p.stride_h + p.base_h;
+						const int b_n = t / p.P;
+#pragma unroll
+						for (int j = 0; j < BN / 32; j++)
+							tma_load_im2col_4d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, b_w, b_h, b_n, p.tap_off_w[gtap], p.tap_off_h[gtap]);
+					}
+					if (++stage == STAGES) { stage = 0; phase ^= 1; }
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ------------------------------------------------------------------ MMA issuer
+		int stage = 0;
+		uint32_t phase = 0;
+		int t = 0;
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++)
+		{
+			const int zz = (tile / tiles_n) / tiles_m;
+			const int split = zz % p.splits;
+			const int it_begin = split * per;
+			const int n_it = min(p.k_iters, it_begin + per) - it_begin;
+			const int acc = t & 1;
+			const uint32_t acc_phase = (t >> 1) & 1;
+			mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1); // the epilogue has drained this accumulator
+			tc_fence_after();
+			const uint32_t tmem_d = tmem_base + acc * BN;
+			for (int it = 0; it < n_it; it++)
+			{
+				mbar_wait(&full_bar[stage], phase);
+				tc_fence_after();
+				if (lane == 0)
+				{
+					const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+					const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+					for (int k = 0; k < UMMA_BLOCK_K / 8; k++)
+					{
+						const uint64_t da = (AMODE == OP_MN2D) ? umma_smem_desc(a_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
+						const uint64_t db = (BMODE == OP_K2D) ? umma_smem_desc(b_addr + k * 32, 16, 1024, 2) : umma_smem_desc(b_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout);
+						umma_tf32(tmem_d, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+					}
+					umma_commit(&empty_bar[stage]);
+				}
+				__syncwarp();
+				if (++stage == STAGES) { stage = 0; phase ^= 1; }
+			}
+			if (lane == 0)
+				umma_commit(&tmem_full_bar[acc]); // fires once every MMA of this tile has completed
+			__syncwarp();
+		}
+	} else {
+		// ------------------------------------------------------------------ epilogue (warps 2..9)
+		const int quarter = warp & 3;        // TMEM lanes [32 * quarter, +32) are the ones this warp may read
+		const int half = (warp - 2) >> 2;    // which of the EPIW / 4 warps of this quarter: chunks half, half + EPIW / 4, ...
+		float* const scratch = reinterpret_cast<float*>(smem + S::EPI_OFFSET) + (warp - 2) * 32 * S::EPI_PITCH;
+		const int sub_row = lane >> 3;       // 0..3: row within a group of 4 rows
+		const int sub_col = (lane & 7) * 4;  // 0..28: first of this lane's 4 columns
+		const bool use_atomic = p.splits > 1;
+		const bool accumulate = p.accumulate != 0;
+		const float* const bias = p.bias;
+		const int N = p.N;
+		int t = 0;
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++)
+		{
+			const int n_blk = tile % tiles_n;
+			const int rest = tile / tiles_n;
+			const int m_blk = rest % tiles_m;
+			const int zz = rest / tiles_m;
+			const int split = zz % p.splits, gtap = zz / p.splits;
+			const int m0 = m_blk * UMMA_BLOCK_M, n0 = n_blk * BN;
+			const int it_begin = split * per;
+			const int n_it = min(p.k_iters, it_begin + per) - it_begin;
+			const int acc = t & 1;
+			const uint32_t acc_phase = (t >> 1) & 1;
+			const bool add_bias = bias != 0 && split == 0;
+			// output row pointers of the 8 rows this lane writes (rows sub_row + 4 * i of the warp's 32-row band)
+			float* orow[8];
+#pragma unroll
+			for (int i = 0; i < 8; i++)
+			{
+				const int row = m0 + quarter * 32 + sub_row + 4 * i;
+				long long off;
+				if (p.rowmap.mode == 0)
+					off = (long long)row * p.rowmap.ld;
+				else {
+					const int pq = p.rowmap.Pc * p.rowmap.Qc;
+					const int n = row / pq;
+					const int rem = row - n * pq;
+					const int ii = rem / p.rowmap.Qc;
+					const int jj = rem - ii * p.rowmap.Qc;
+					off = n * p.rowmap.n_stride + ii * p.rowmap.h_stride + jj * p.rowmap.w_stride;
+				}
+				orow[i] = row < p.M ? p.out + off + (long long)gtap * p.grid_tap_out_stride : 0;
+			}
+			mbar_wait(&tmem_full_bar[acc], acc_phase);
+			tc_fence_after();
+#pragma unroll 1
+			for (int c = half; c < BN / 32; c += EPIW / 4)
+			{
+				uint32_t r[32];
+				if (n_it > 0)
+				{
+					tmem_ld_32x32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + c * 32, r);
+					tmem_ld_wait();
+				} else {
+#pragma unroll
+					for (int i = 0; i < 32; i++)
+						r[i] = 0;
+				}
+				// lane = row: park the row in the scratch tile, then re-read it as (4 rows x 8 lanes x 16 bytes)
+				__syncwarp();
+#pragma unroll
+				for (int i = 0; i < 32; i += 4)
+					*reinterpret_cast<float4*>(scratch + lane * S::EPI_PITCH + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+				__syncwarp();
+				const int col = n0 + c * 32 + sub_col;
+				if (col < N)
+				{
+				float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+				const bool full4 = col + 4 <= N;
+				if (add_bias)
+				{
+					bias4.x = __ldg(bias + col);
+					bias4.y = col + 1 < N ? __ldg(bias + col + 1) : 0.f;
+					bias4.z = col + 2 < N ? __ldg(bias + col + 2) : 0.f;
+					bias4.w = col + 3 < N ? __ldg(bias + col + 3) : 0.f;
+				}
+#pragma unroll
+				for (int i = 0; i < 8; i++)
+				{
+					if (!orow[i])
+						continue;
+					float4 v = *reinterpret_cast<const float4*>(scratch + (sub_row + 4 * i) * S::EPI_PITCH + sub_col);
+					v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
+					float* const o = orow[i] + col;
+					if (full4 && ((((uintptr_t)o) & 15) == 0))
+					{
+						if (use_atomic)
+							red_add_v4(o, v.x, v.y, v.z, v.w);
+						else {
+							if (accumulate)
+							{
+								const float4 e = *reinterpret_cast<const float4*>(o);
+								v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
+							}
+							*reinterpret_cast<float4*>(o) = v;
+						}
+					} else {
+						const float vv[4] = { v.x, v.y, v.z, v.w };
+						for (int j = 0; j < 4; j++)
+							if (col + j < N)
+							{
+								if (use_atomic)
+									atomicAdd(o + j, vv[j]);
+								else
+									o[j] = accumulate ? o[j] + vv[j] : vv[j];
+							}
+					}
+				}
+				}
+			}
+			// all tcgen05.ld of this tile are complete (tmem_ld_wait): hand the accumulator back to the MMA warp
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(&tmem_empty_bar[acc]);
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1)
+		tmem_dealloc(tmem_base, 2 * BN);
+}
+
+} // namespace sm100

@@ -177,6 +177,9 @@ int main(int argc, char** argv)
 	case 14: ok &= test_conv(r50a, 0, 0, 0, 1); ok &= test_conv(r50a, 1, 0, 0, 1); ok &= test_conv(r50a, 2, 0, 0, 1); break; // positive data: bias check
 	case 15: time_gemm(1024, 1024, 1024, 0, 1); time_gemm(1024, 1024, 1024, 0, 0); time_gemm(4096, 4096, 4096, 0, 1); time_gemm(4096, 4096, 4096, 0, 0); time_gemm(8192, 8192, 8192, 0, 1); time_gemm(200704, 256, 64, 0, 1); time_gemm(200704, 64, 256, 0, 1); break;
 	case 16: time_conv(cfg2, 0); time_conv(cfg2, 1); time_conv(cfg2, 2); { ConvCase c = { 256, 56, 56, 64, 64, 3, 3, 1, 1, 1 }; time_conv(c, 0); time_conv(c, 1); time_conv(c, 2); } { ConvCase c = { 256, 14, 14, 256, 256, 3, 3, 1, 1, 1 }; time_conv(c, 0); time_conv(c, 1); time_conv(c, 2); } { ConvCase c = { 256, 56, 56, 128, 128, 3, 3, 2, 1, 1 }; time_conv(c, 0); time_conv(c, 1); time_conv(c, 2); } break;
+	case 17: time_gemm(200704, 256, 64, 0, 1); break; // the 1x1 64->256 convolution of ResNet layer1 at N=64 (write-dominated)
+	case 18: { ConvCase c = { 64, 56, 56, 64, 64, 3, 3, 1, 1, 1 }; time_conv(c, 0); time_conv(c, 2); } break; // BASELINE configs[1]
+	case 19: time_gemm(8192, 8192, 8192, 0, 1); break;
 	default: printf("unknown test id\n"); return 1;
 	}
 	printf("probe %d: %s\n", id, ok ? "ALL PASS" : "SOME FAIL");
