@@ -163,17 +163,6 @@ static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, c
 	return 0;
 }
 
-static bool use_persistent()
-{
-	static int v = -1;
-	if (v < 0)
-	{
-		const char* e = getenv("CCV_NNC_SM100_PERSISTENT");
-		v = e ? atoi(e) : 1;
-	}
-	return v != 0;
-}
-
 // Kernel choice, from the measurements in profiles/r01_probe3_*.log and r01_probe4_*.log:
 //  * BN = 64 (<= 64 output columns) and weight gradients with <= 128 columns: the one-tile-per-CTA kernel, two CTAs per SM
 //    (these are L2-bound / short tiles; two independent CTAs hide more latency than one persistent CTA);
