@@ -176,11 +176,12 @@ def main():
     assert nnc.cmd_exec(xfer, None, 0, [host_in, host_lab], [net.input, net.labels], stream) == 0
     stream.wait()
 
-    # the single gradient exchange: one sum-allreduce over the flat gradient buffer (torch.distributed/NCCL plumbing)
+    # the single gradient exchange: ONE CCV_NNC_COMM_ALLREDUCE_FORWARD command of the backend over the flat gradient buffer
+    # (NCCL inside the library; torch.distributed only carries the communicator id, the barrier and the max-over-ranks time)
     allreduce = None
     if world > 1:
         from ccv_b200 import dp
-        allreduce = dp.FlatAllreduce(net, dist, stream, device)
+        allreduce = dp.CommandAllreduce(net, dist, stream, rank, world)
 
     # eager pass: sizes workspaces, counts launches, checks every command returns success
     l0 = nnc.launch_count()
@@ -248,7 +249,7 @@ def main():
     value = images_per_step / (ms_per_step * 1e-3)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c:17-95) fp32 NHWC, per-GPU batch %d, %dx%d, fwd+bwd + nesterov SGD%s" % (args.batch, args.image, args.image, ", one NCCL sum-allreduce of the flat fp32 gradient buffer" if world > 1 else ""),
+           "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c:17-95) fp32 NHWC, per-GPU batch %d, %dx%d, fwd+bwd + nesterov SGD%s" % (args.batch, args.image, args.image, ", one COMM_ALLREDUCE command (NCCL sum) over the flat fp32 gradient buffer" if world > 1 else ""),
                       "global_batch": images_per_step, "parallelism": "dp%d" % world, "tensor_core_math": "tcgen05 kind::tf32, fp32 accumulate (TMA rounds operands to TF32)",
                       "cuda_graph": use_graph, "fused_pairs": n_fused, "first_step_loss": first_loss, "l2": "activations per step (>20 GB) exceed the 126 MB L2: no flush needed", "mean_loss": loss},
            "e2e": {"value": images_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes + host_lab.nbytes), "d2h_bytes_per_step": int(host_loss.nbytes), "ms_per_step": e2e_ms},

@@ -26,7 +26,7 @@ CCV_NNC_SM100_ALGO_TF32, CCV_NNC_SM100_ALGO_3XTF32, CCV_NNC_SM100_ALGO_FFMA = 0,
 CMD_IDS = dict(
     ADD=0x58fb3664, AVERAGE_POOL=0x51267ab8, BATCH_NORM=0x5419819c, CATEGORICAL_CROSSENTROPY=0x1eb327a2,
     COMM_ALLREDUCE=0x75c8d340, CONVOLUTION=0x254d05f4, DATATYPE_CONVERSION=0xd873e38c, DATA_TRANSFER=0x12d21e1a,
-    EWSUM=0xe21a2c4c, FORMAT_TRANSFORM=0xe4a2b192, GEMM=0x7e87d00c, LAYER_NORM=0xbed3c264, MAX_POOL=0x7bec9360,
+    EWSUM=0xe21a2c4c, FORMAT_TRANSFORM=0xe4a2b192, GEMM=0x7e87d00c, GROUP_NORM=0x17deb074, LAYER_NORM=0xbed3c264, MAX_POOL=0x7bec9360,
     MUL=0x24721a46, RELU=0xc51eaa80, RMSNORM=0x6889e9d0, SCALAR_MUL=0x8b4d86aa,
     SCALED_DOT_PRODUCT_ATTENTION=0x284ed926, SET=0x2b070804, SGD=0xe650ad26, SOFTMAX=0xc969a252,
     SOFTMAX_CROSSENTROPY=0xc26b7b5e, TRANSPOSE=0xb4d506e0, UPSAMPLE=0x73875556,

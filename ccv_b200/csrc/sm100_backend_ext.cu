@@ -217,6 +217,85 @@ int ccv_nnc_sm100_exec_lnorm_back(SM100_EXEC_ARGS)
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
+// ---- group norm -------------------------------------------------------------------------------------------------------
+// norm/ccv_nnc_group_norm_cpu_ref.c:16-222: inputs (x, [scale, bias]) -> outputs (y, saved_mean, saved_inv_std).  The
+// statistics tensor's own dims say which elements share a slot (group axis -> groups, reduced axes -> 1).
+static bool gn_dims(const ccv_nnc_tensor_t* const t, int dim[4], long long stride[4])
+{
+	if (CCV_GET_DATA_TYPE(t->info.datatype) != CCV_32F)
+		return false;
+	const int nd = nd_of(t);
+	if (nd < 1 || nd > 4)
+		return false;
+	long long packed = 1;
+	for (int i = 3; i >= 0; i--)
+	{
+		const int src = i - (4 - nd);
+		dim[i] = src >= 0 ? t->info.dim[src] : 1;
+		if (stride)
+			stride[i] = src >= 0 ? (CCV_IS_TENSOR_VIEW(t) ? ((const ccv_nnc_tensor_view_t*)t)->stride[src] : packed) : 0;
+		packed *= dim[i];
+	}
+	return true;
+}
+
+static bool gn_geom(const ccv_nnc_tensor_t* const x, const ccv_nnc_tensor_t* const y, const ccv_nnc_tensor_t* const h, const ccv_nnc_tensor_t* const stat, const ccv_nnc_tensor_t* const scale, GroupNormGeom& g)
+{
+	int d2[4];
+	if (!gn_dims(x, g.dim, g.xstride) || !gn_dims(y, d2, g.ystride) || memcmp(d2, g.dim, sizeof(d2)) != 0)
+		return false;
+	if (h && (!gn_dims(h, d2, g.hstride) || memcmp(d2, g.dim, sizeof(d2)) != 0))
+		return false;
+	if (!packed_f32(stat) || nd_of(stat) != nd_of(x) || !gn_dims(stat, g.rdim, 0))
+		return false;
+	for (int i = 0; i < 4; i++)
+		g.sdim[i] = 1;
+	if (scale && (!packed_f32(scale) || nd_of(scale) != nd_of(x) || !gn_dims(scale, g.sdim, 0)))
+		return false;
+	for (int i = 0; i < 4; i++)
+		if (g.rdim[i] < 1 || g.rdim[i] > g.dim[i] || g.sdim[i] < 1 || g.sdim[i] > g.dim[i])
+			return false;
+	return true;
+}
+
+int ccv_nnc_sm100_exec_gnorm_forw(SM100_EXEC_ARGS)
+{
+	if (input_size < 1 || output_size < 3 || !inputs[0] || !outputs[0] || !outputs[1] || !outputs[2])
+		return CCV_NNC_EXEC_INVALID;
+	const int affine = cmd.info.gnorm.elementwise_affine;
+	if (affine && (input_size < 3 || !inputs[1] || !inputs[2] || count_of(inputs[1]) != count_of(inputs[2])))
+		return CCV_NNC_EXEC_INVALID;
+	GroupNormGeom g;
+	if (!gn_geom(inputs[0], outputs[0], 0, outputs[1], affine ? inputs[1] : 0, g) || !packed_f32(outputs[2]) || count_of(outputs[2]) != count_of(outputs[1]) || (affine && !packed_f32(inputs[2])))
+		return CCV_NNC_EXEC_INVALID;
+	if (group_norm_fwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, affine ? inputs[1]->data.f32 : 0, affine ? inputs[2]->data.f32 : 0, outputs[0]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, cmd.info.gnorm.epsilon))
+		return CCV_NNC_EXEC_INVALID;
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// norm/ccv_nnc_group_norm_cpu_ref.c:224-505: inputs[0] = g, [3] = x, [4] = scale (affine), [7 | 5] = saved_mean, [8 | 6] = saved_inv_std
+int ccv_nnc_sm100_exec_gnorm_back(SM100_EXEC_ARGS)
+{
+	const int affine = cmd.info.gnorm.elementwise_affine;
+	const int mi = affine ? 7 : 5, si = affine ? 8 : 6;
+	if (input_size <= si || output_size < 1 || !inputs[0] || !inputs[3] || !inputs[mi] || !inputs[si] || (affine && !inputs[4]))
+		return CCV_NNC_EXEC_INVALID;
+	ccv_nnc_tensor_t* const h = outputs[0];
+	ccv_nnc_tensor_t* const ds = output_size > 1 ? outputs[1] : 0;
+	ccv_nnc_tensor_t* const db = output_size > 2 ? outputs[2] : 0;
+	GroupNormGeom g;
+	if (!gn_geom(inputs[3], inputs[0], h, inputs[mi], affine ? inputs[4] : (ds ? ds : db), g) || !packed_f32(inputs[si]) || count_of(inputs[si]) != count_of(inputs[mi]))
+		return CCV_NNC_EXEC_INVALID;
+	if ((ds && (!packed_f32(ds) || (long long)count_of(ds) != (long long)g.sdim[0] * g.sdim[1] * g.sdim[2] * g.sdim[3])) || (db && (!packed_f32(db) || (long long)count_of(db) != (long long)g.sdim[0] * g.sdim[1] * g.sdim[2] * g.sdim[3])))
+		return CCV_NNC_EXEC_INVALID;
+	void* const ws = h ? ccv_nnc_stream_context_get_workspace(stream_context, group_norm_bwd_workspace_bytes(g), CCV_TENSOR_GPU_MEMORY) : 0;
+	if (h && !ws)
+		return CCV_NNC_EXEC_OOM;
+	if (group_norm_bwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, inputs[3]->data.f32, affine ? inputs[4]->data.f32 : 0, inputs[mi]->data.f32, inputs[si]->data.f32, h ? h->data.f32 : 0, ds ? ds->data.f32 : 0, db ? db->data.f32 : 0, ws))
+		return CCV_NNC_EXEC_INVALID;
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
 // norm/ccv_nnc_rmsnorm_cpu_ref.c:16-130: inputs (x, scale) -> outputs (y, saved_inv_std)
 int ccv_nnc_sm100_exec_rmsnorm_forw(SM100_EXEC_ARGS)
 {
@@ -291,6 +370,5 @@ int ccv_nnc_sm100_exec_upsample_back(SM100_EXEC_ARGS)
 		return CCV_NNC_EXEC_INVALID;
 	return CCV_NNC_EXEC_SUCCESS;
 }
-int ccv_nnc_sm100_exec_allreduce(SM100_EXEC_ARGS) { return CCV_NNC_EXEC_NO_KERNEL; }
 
 }

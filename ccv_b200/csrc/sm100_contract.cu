@@ -4,6 +4,7 @@
 // lib/nnc/cmd/convolution/ccv_nnc_conv_cpu_ref.c:13-345 (NHWC).
 #include "sm100_contract.h"
 #include "sm100_umma_persistent.cuh"
+#include "sm100_umma_wgrad.cuh"
 #include <atomic>
 #include <mutex>
 #include <stdio.h>
@@ -481,6 +482,46 @@ int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 	return 0;
 }
 
+// Filter gradient with few filters (K <= 64): taps packed along the UMMA M dimension (sm100_umma_wgrad.cuh).
+template <int BN>
+static int launch_wgrad_taps(cudaStream_t stream, const CUtensorMap& tmX, const CUtensorMap& tmG, const WgradTapsParams& p, int tiles)
+{
+	constexpr int STAGES = 4;
+	using S = WgradTapsSmem<BN, STAGES>;
+	auto kern = umma_wgrad_taps_kernel<BN, STAGES>;
+	static bool configured = false;
+	if (!configured)
+	{
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+		if (e != cudaSuccess)
+		{
+			set_last_error("cudaFuncSetAttribute(umma_wgrad_taps_kernel)", e);
+			return -1;
+		}
+		configured = true;
+	}
+	kern<<<dim3(tiles, p.splits), 192, S::TOTAL, stream>>>(tmX, tmG, p);
+	count_launch();
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error("umma_wgrad_taps_kernel launch", e);
+		return -1;
+	}
+	return 0;
+}
+
+static bool wgrad_taps_enabled()
+{
+	static int v = -1;
+	if (v < 0)
+	{
+		const char* e = getenv("CCV_NNC_SM100_WGRAD_TAPS");
+		v = e ? atoi(e) : 1;
+	}
+	return v != 0;
+}
+
 int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate)
 {
 	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g))
@@ -523,6 +564,35 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 	}
 	if (!make_map_im2col(&tmB, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, 32, UMMA_BLOCK_K, true))
 		return 1;
+	if (g.K <= 64 && g.C % 32 == 0 && g.C <= 128 && wgrad_taps_enabled())
+	{
+		WgradTapsParams w;
+		memset(&w, 0, sizeof(w));
+		w.C = g.C, w.K = g.K, w.taps = g.R * g.S;
+		const int max_tpt = 128 / g.C;
+		const int tiles_m = (w.taps + max_tpt - 1) / max_tpt;
+		w.taps_per_tile = (w.taps + tiles_m - 1) / tiles_m; // balanced: 9 taps of 32 channels -> 3 + 3 + 3
+		w.k_iters = p.k_iters;
+		w.splits = pick_splits(tiles_m, w.k_iters, 16);
+		w.P = g.P, w.Q = g.Q, w.stride_h = g.stride_h, w.stride_w = g.stride_w, w.base_h = -g.pad_h0, w.base_w = -g.pad_w0;
+		for (int r = 0; r < g.R; r++)
+			for (int s = 0; s < g.S; s++)
+				w.tap_off_h[r * g.S + s] = (unsigned short)(r * g.dil_h), w.tap_off_w[r * g.S + s] = (unsigned short)(s * g.dil_w);
+		w.out = grad_w, w.rsc = rsc;
+		w.mn_lbo = p.mn_lbo, w.mn_sbo = p.mn_sbo, w.mn_layout = p.mn_layout;
+		const int wbn = g.K <= 32 ? 32 : 64;
+		w.idesc = umma_instr_desc(2, 1, 1, UMMA_BLOCK_M, wbn);
+		if (!accumulate && !(p.splits > 1)) // the epilogue always adds: dW starts from zero (the generic path above only clears it for split-K)
+		{
+			cudaError_t e = cudaMemsetAsync(grad_w, 0, (size_t)g.K * rsc * 4, stream);
+			if (e != cudaSuccess)
+			{
+				set_last_error("memset(wgrad)", e);
+				return -1;
+			}
+		}
+		return wbn == 32 ? launch_wgrad_taps<32>(stream, tmB, tmA, w, tiles_m) : launch_wgrad_taps<64>(stream, tmB, tmA, w, tiles_m);
+	}
 	p.grid_taps = g.R * g.S;
 	p.grid_tap_out_stride = g.C;
 	p.P = g.P, p.Q = g.Q;

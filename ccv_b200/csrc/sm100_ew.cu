@@ -347,6 +347,47 @@ __global__ void colsum_kernel(const float* __restrict__ g, const size_t rows, co
 		atomicAdd(out + col, acc);
 	}
 }
+// Vector form (cols, ld multiples of 4, 16-byte aligned): a thread owns one float4 column group and keeps four row loads
+// in flight; a block covers `cpb` column groups x (256 / cpb) rows per step.
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const float4* __restrict__ g, const size_t rows, const int cols4, const long long ld4, float* __restrict__ out, const int cpb)
+{
+	__shared__ float4 sh[256];
+	const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb, rpi = 256 / cpb;
+	const int col4 = blockIdx.x * cpb + tx;
+	float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+	if (col4 < cols4)
+	{
+		const size_t step = (size_t)gridDim.y * rpi;
+		size_t r = (size_t)blockIdx.y * rpi + ty;
+		const float4* p = g + col4;
+		for (; r + 3 * step < rows; r += 4 * step)
+		{
+			const float4 v0 = __ldg(p + r * ld4), v1 = __ldg(p + (r + step) * ld4), v2 = __ldg(p + (r + 2 * step) * ld4), v3 = __ldg(p + (r + 3 * step) * ld4);
+			a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+			a1.x += v1.x, a1.y += v1.y, a1.z += v1.z, a1.w += v1.w;
+			a2.x += v2.x, a2.y += v2.y, a2.z += v2.z, a2.w += v2.w;
+			a3.x += v3.x, a3.y += v3.y, a3.z += v3.z, a3.w += v3.w;
+		}
+		for (; r < rows; r += step)
+		{
+			const float4 v0 = __ldg(p + r * ld4);
+			a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+		}
+	}
+	a0.x += a1.x + a2.x + a3.x, a0.y += a1.y + a2.y + a3.y, a0.z += a1.z + a2.z + a3.z, a0.w += a1.w + a2.w + a3.w;
+	sh[threadIdx.x] = a0;
+	__syncthreads();
+	if (ty == 0 && col4 < cols4)
+	{
+		for (int j = 1; j < rpi; j++)
+		{
+			const float4 v = sh[j * cpb + tx];
+			a0.x += v.x, a0.y += v.y, a0.z += v.z, a0.w += v.w;
+		}
+		float* const o = out + 4 * (size_t)col4;
+		atomicAdd(o, a0.x), atomicAdd(o + 1, a0.y), atomicAdd(o + 2, a0.z), atomicAdd(o + 3, a0.w);
+	}
+}
 int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long ld, float* out, int accumulate)
 {
 	if (cols <= 0)
@@ -362,6 +403,23 @@ int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long 
 	}
 	if (rows == 0)
 		return 0;
+	if (cols % 4 == 0 && ld % 4 == 0 && (((uintptr_t)g) & 15) == 0)
+	{
+		const int cols4 = cols / 4;
+		int cpb = 1;
+		while (cpb < cols4 && cpb < 256)
+			cpb <<= 1;
+		const int rpi = 256 / cpb;
+		const int gx = (cols4 + cpb - 1) / cpb;
+		size_t gy = (rows + (size_t)rpi * 16 - 1) / ((size_t)rpi * 16);
+		const size_t cap = (size_t)(sms() * 8 + gx - 1) / gx;
+		if (gy > cap)
+			gy = cap;
+		if (gy < 1)
+			gy = 1;
+		colsum_vec_kernel<<<dim3(gx, (unsigned)gy), 256, 0, s>>>((const float4*)g, rows, cols4, ld / 4, out, cpb);
+		return check("colsum_vec");
+	}
 	const int cpb = cols >= 256 ? 256 : (cols >= 128 ? 128 : (cols >= 64 ? 64 : 32));
 	const int rpi = 256 / cpb;
 	const int gx = (cols + cpb - 1) / cpb;

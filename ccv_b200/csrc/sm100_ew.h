@@ -74,6 +74,17 @@ int layer_norm_bwd_f32(cudaStream_t s, const float* g, const float* x, const flo
 int rmsnorm_fwd_f32(cudaStream_t s, const float* x, const float* scale, float* y, float* saved_inv_std, int rows, int inner, float epsilon);
 int rmsnorm_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* saved_inv_std, float* dx, float* dscale, int rows, int inner, void* workspace);
 
+// ---- group norm: <= 4-d index space, statistics / scale / bias tensors with dims dividing it (slot = i * rdim / dim) ----
+struct GroupNormGeom {
+	int dim[4];            // x / y / g / h dims (leading dims padded with 1)
+	int rdim[4];           // saved_mean / saved_inv_std dims (packed)
+	int sdim[4];           // scale / bias / dscale / dbias dims (packed)
+	long long xstride[4], ystride[4], hstride[4]; // element strides of x, of y (forward) or g (backward), of h
+};
+int group_norm_fwd_f32(cudaStream_t s, const GroupNormGeom& g, const float* x, const float* scale, const float* bias, float* y, float* saved_mean, float* saved_inv_std, float epsilon);
+size_t group_norm_bwd_workspace_bytes(const GroupNormGeom& g);
+int group_norm_bwd_f32(cudaStream_t s, const GroupNormGeom& g, const float* grad, const float* x, const float* scale, const float* saved_mean, const float* saved_inv_std, float* h, float* dscale, float* dbias, void* workspace);
+
 // ---- upsample (NHWC) ------------------------------------------------------------------------------------------
 int upsample_fwd_f32(cudaStream_t s, const float* a, float* b, int N, int H, int W, int C, int OH, int OW, int type, int align_corners, int nchw);
 int upsample_bwd_f32(cudaStream_t s, const float* g, float* h, int N, int H, int W, int C, int OH, int OW, int type, int align_corners, int nchw);

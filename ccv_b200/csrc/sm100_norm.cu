@@ -257,4 +257,212 @@ int upsample_bwd_f32(cudaStream_t s, const float* g, float* h, int N, int H, int
 	return check("upsample_bwd");
 }
 
+
+// ---- group norm (norm/ccv_nnc_group_norm_cpu_ref.c) ------------------------------------------------------------------
+// Everything is a <= 4-d index space `dim`; a statistic / scale / bias tensor has dims rdim with rdim[d] <= dim[d] and the
+// element i of axis d belongs to slot i * rdim[d] / dim[d] (:64-76), i.e. slot g owns the contiguous range
+// [ceil(g * dim / rdim), ceil((g + 1) * dim / rdim)).  One thread block walks the box of one slot.
+struct GnBox {
+	int lo[4], ext[4];
+	long long count;
+};
+
+__device__ __forceinline__ GnBox gn_box(const GroupNormGeom& g, const int* const rdim, long long slot)
+{
+	GnBox b;
+	b.count = 1;
+#pragma unroll
+	for (int d = 3; d >= 0; d--)
+	{
+		const int gd = (int)(slot % rdim[d]);
+		slot /= rdim[d];
+		const int lo = (int)(((long long)gd * g.dim[d] + rdim[d] - 1) / rdim[d]);
+		const int hi = (int)(((long long)(gd + 1) * g.dim[d] + rdim[d] - 1) / rdim[d]);
+		b.lo[d] = lo, b.ext[d] = hi - lo;
+		b.count *= hi - lo;
+	}
+	return b;
+}
+
+__device__ __forceinline__ void gn_coord(const GnBox& b, long long i, int c[4])
+{
+#pragma unroll
+	for (int d = 3; d >= 0; d--)
+	{
+		c[d] = b.lo[d] + (int)(i % b.ext[d]);
+		i /= b.ext[d];
+	}
+}
+
+__device__ __forceinline__ long long gn_offset(const int c[4], const long long stride[4])
+{
+	return c[0] * stride[0] + c[1] * stride[1] + c[2] * stride[2] + c[3] * stride[3];
+}
+
+// slot of coordinate c in a tensor of dims rdim (packed)
+__device__ __forceinline__ long long gn_slot(const GroupNormGeom& g, const int c[4], const int rdim[4])
+{
+	long long s = 0;
+#pragma unroll
+	for (int d = 0; d < 4; d++)
+		s = s * rdim[d] + (long long)c[d] * rdim[d] / g.dim[d];
+	return s;
+}
+
+__device__ __forceinline__ float gn_block_sum(float v, float* const red) { return bsum(v, red); }
+
+__global__ void gn_stats_kernel(const GroupNormGeom g, const float* __restrict__ x, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std, const float epsilon)
+{
+	__shared__ float red[32];
+	const GnBox b = gn_box(g, g.rdim, blockIdx.x);
+	int c[4];
+	float sum = 0;
+	for (long long i = threadIdx.x; i < b.count; i += blockDim.x)
+	{
+		gn_coord(b, i, c);
+		sum += x[gn_offset(c, g.xstride)];
+	}
+	const float inv_n = 1.f / (float)b.count;
+	const float mean = gn_block_sum(sum, red) * inv_n;
+	float sq = 0;
+	for (long long i = threadIdx.x; i < b.count; i += blockDim.x)
+	{
+		gn_coord(b, i, c);
+		const float w = x[gn_offset(c, g.xstride)] - mean;
+		sq += w * w;
+	}
+	const float var = gn_block_sum(sq, red) * inv_n;
+	if (threadIdx.x == 0)
+	{
+		saved_mean[blockIdx.x] = mean;
+		saved_inv_std[blockIdx.x] = 1.f / sqrtf(var + epsilon);
+	}
+}
+
+__global__ void gn_apply_kernel(const GroupNormGeom g, const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ bias, const float* __restrict__ saved_mean, const float* __restrict__ saved_inv_std, float* __restrict__ y, const long long total)
+{
+	GnBox all;
+	for (int d = 0; d < 4; d++)
+		all.lo[d] = 0, all.ext[d] = g.dim[d];
+	int c[4];
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+	{
+		gn_coord(all, i, c);
+		const long long r = gn_slot(g, c, g.rdim);
+		float v = (x[gn_offset(c, g.xstride)] - saved_mean[r]) * saved_inv_std[r];
+		if (scale)
+			v = v * scale[gn_slot(g, c, g.sdim)] + bias[gn_slot(g, c, g.sdim)];
+		y[gn_offset(c, g.ystride)] = v;
+	}
+}
+
+// per statistic slot: gssr = sum g * scale * inv_std, ahgssr = sum xhat * g * scale * inv_std (:412-470)
+__global__ void gn_bwd_stats_kernel(const GroupNormGeom g, const float* __restrict__ grad, const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ saved_mean, const float* __restrict__ saved_inv_std, float* __restrict__ sums)
+{
+	__shared__ float red[32];
+	const GnBox b = gn_box(g, g.rdim, blockIdx.x);
+	const float mean = saved_mean[blockIdx.x], inv_std = saved_inv_std[blockIdx.x];
+	int c[4];
+	float s0 = 0, s1 = 0;
+	for (long long i = threadIdx.x; i < b.count; i += blockDim.x)
+	{
+		gn_coord(b, i, c);
+		const float ah = (x[gn_offset(c, g.xstride)] - mean) * inv_std;
+		float gss = grad[gn_offset(c, g.ystride)] * inv_std;
+		if (scale)
+			gss *= scale[gn_slot(g, c, g.sdim)];
+		s0 += gss, s1 += ah * gss;
+	}
+	s0 = gn_block_sum(s0, red), s1 = gn_block_sum(s1, red);
+	if (threadIdx.x == 0)
+		sums[2 * blockIdx.x] = s0, sums[2 * blockIdx.x + 1] = s1;
+}
+
+// h = gss - (gssr + xhat * ahgssr) / n (:472-500)
+__global__ void gn_bwd_apply_kernel(const GroupNormGeom g, const float* __restrict__ grad, const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ saved_mean, const float* __restrict__ saved_inv_std, const float* __restrict__ sums, float* __restrict__ h, const long long total, const float inv_n)
+{
+	GnBox all;
+	for (int d = 0; d < 4; d++)
+		all.lo[d] = 0, all.ext[d] = g.dim[d];
+	int c[4];
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+	{
+		gn_coord(all, i, c);
+		const long long r = gn_slot(g, c, g.rdim);
+		const float inv_std = saved_inv_std[r];
+		const float ah = (x[gn_offset(c, g.xstride)] - saved_mean[r]) * inv_std;
+		float gss = grad[gn_offset(c, g.ystride)] * inv_std;
+		if (scale)
+			gss *= scale[gn_slot(g, c, g.sdim)];
+		h[gn_offset(c, g.hstride)] = gss - (sums[2 * r] + ah * sums[2 * r + 1]) * inv_n;
+	}
+}
+
+// per scale / bias slot: dscale = sum xhat * g, dbias = sum g (:322-345, :254)
+__global__ void gn_bwd_dparam_kernel(const GroupNormGeom g, const float* __restrict__ grad, const float* __restrict__ x, const float* __restrict__ saved_mean, const float* __restrict__ saved_inv_std, float* __restrict__ dscale, float* __restrict__ dbias)
+{
+	__shared__ float red[32];
+	const GnBox b = gn_box(g, g.sdim, blockIdx.x);
+	int c[4];
+	float s0 = 0, s1 = 0;
+	for (long long i = threadIdx.x; i < b.count; i += blockDim.x)
+	{
+		gn_coord(b, i, c);
+		const long long r = gn_slot(g, c, g.rdim);
+		const float gv = grad[gn_offset(c, g.ystride)];
+		s0 += (x[gn_offset(c, g.xstride)] - saved_mean[r]) * saved_inv_std[r] * gv;
+		s1 += gv;
+	}
+	s0 = gn_block_sum(s0, red), s1 = gn_block_sum(s1, red);
+	if (threadIdx.x == 0)
+	{
+		if (dscale)
+			dscale[blockIdx.x] = s0;
+		if (dbias)
+			dbias[blockIdx.x] = s1;
+	}
+}
+
+static long long gn_count(const int* d) { return (long long)d[0] * d[1] * d[2] * d[3]; }
+
+int group_norm_fwd_f32(cudaStream_t s, const GroupNormGeom& g, const float* x, const float* scale, const float* bias, float* y, float* saved_mean, float* saved_inv_std, float epsilon)
+{
+	const long long total = gn_count(g.dim), slots = gn_count(g.rdim);
+	if (total == 0)
+		return 0;
+	gn_stats_kernel<<<(unsigned)slots, 512, 0, s>>>(g, x, saved_mean, saved_inv_std, epsilon);
+	count_launch();
+	long long blocks = (total + 255) / 256;
+	if (blocks > 148 * 16)
+		blocks = 148 * 16;
+	gn_apply_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, x, scale, bias, saved_mean, saved_inv_std, y, total);
+	return check("group_norm_fwd");
+}
+
+size_t group_norm_bwd_workspace_bytes(const GroupNormGeom& g) { return (size_t)gn_count(g.rdim) * 2 * sizeof(float); }
+
+int group_norm_bwd_f32(cudaStream_t s, const GroupNormGeom& g, const float* grad, const float* x, const float* scale, const float* saved_mean, const float* saved_inv_std, float* h, float* dscale, float* dbias, void* workspace)
+{
+	const long long total = gn_count(g.dim), slots = gn_count(g.rdim);
+	if (total == 0)
+		return 0;
+	if (h)
+	{
+		float* const sums = (float*)workspace;
+		gn_bwd_stats_kernel<<<(unsigned)slots, 512, 0, s>>>(g, grad, x, scale, saved_mean, saved_inv_std, sums);
+		count_launch();
+		long long blocks = (total + 255) / 256;
+		if (blocks > 148 * 16)
+			blocks = 148 * 16;
+		gn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, grad, x, scale, saved_mean, saved_inv_std, sums, h, total, (float)slots / (float)total);
+		count_launch();
+	}
+	if (dscale || dbias)
+	{
+		gn_bwd_dparam_kernel<<<(unsigned)gn_count(g.sdim), 256, 0, s>>>(g, grad, x, saved_mean, saved_inv_std, dscale, dbias);
+		count_launch();
+	}
+	return check("group_norm_bwd") ;
+}
+
 } // namespace sm100

@@ -1,8 +1,10 @@
 """Batch-sharded data parallelism for a command-list model: one process per GPU, a full replica each, and
 ONE sum-allreduce over the flat gradient buffer between the backward commands and the SGD commands.  The reference does the
 same exchange with one CMD_COMM_ALLREDUCE per parameter inside a single process
-(lib/nnc/ccv_nnc_symbolic_graph_parallel.c:546-575, lib/nnc/cmd/comm/gpu/ccv_nnc_comm_gpu_nccl.cu:12-50); here
-torch.distributed is the plumbing (NCCL on GPUs, gloo for the CPU tests)."""
+(lib/nnc/ccv_nnc_symbolic_graph_parallel.c:546-575, lib/nnc/cmd/comm/gpu/ccv_nnc_comm_gpu_nccl.cu:12-50); on GPUs
+the exchange is ONE CCV_NNC_COMM_ALLREDUCE_FORWARD command of this backend (ccv_b200/csrc/sm100_comm.cu, NCCL resolved by
+the library itself) over the flat gradient tensor; torch.distributed only carries the 128-byte communicator id between the
+ranks.  FlatAllreduce (torch.distributed all_reduce) remains for host tensors: the gloo tests of the sharding logic."""
 import numpy as np
 
 
@@ -29,6 +31,23 @@ class FlatAllreduce(object):
         else:
             with self.torch.cuda.stream(self.ext):
                 self.dist.all_reduce(self.tensor)
+
+
+class CommandAllreduce(object):
+    """The gradient exchange as the backend's own command: CMD_COMM_ALLREDUCE_FORWARD(g_flat) -> g_flat on `stream`."""
+
+    def __init__(self, net, dist, stream, rank, world):
+        from ccv_b200 import nnc
+        self.nnc, self.net, self.stream = nnc, net, stream
+        box = [nnc.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nnc.comm_init_rank(box[0], world, rank)
+        self.cmd = nnc.CMD_COMM_ALLREDUCE_FORWARD()
+
+    def __call__(self):
+        st = self.nnc.cmd_exec(self.cmd, None, 0, [self.net.g_flat], [self.net.g_flat], self.stream)
+        if st != 0:
+            raise RuntimeError("COMM_ALLREDUCE returned %d: %s" % (st, self.nnc.lib().ccv_nnc_sm100_last_error()))
 
 
 def shard(array, rank, world):

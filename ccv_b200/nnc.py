@@ -77,6 +77,12 @@ def lib():
         l.ccv_nnc_sm100_graph_replay.restype = i32
         l.ccv_nnc_sm100_graph_replay.argtypes = [vp, i32, vp]
         l.ccv_nnc_sm100_graph_free.argtypes = [vp]
+        l.ccv_nnc_sm100_comm_unique_id.restype = i32
+        l.ccv_nnc_sm100_comm_unique_id.argtypes = [vp, sz]
+        l.ccv_nnc_sm100_comm_init_rank.restype = i32
+        l.ccv_nnc_sm100_comm_init_rank.argtypes = [vp, sz, i32, i32]
+        l.ccv_nnc_sm100_comm_rank.restype = i32
+        l.ccv_nnc_sm100_comm_world.restype = i32
         _lib = l
     return _lib
 
@@ -244,6 +250,21 @@ def cmd_exec(cmd, hint, flags, inputs, outputs, stream=None):
     """ccv_nnc_cmd_exec (lib/nnc/ccv_nnc.h:842). Returns the CCV_NNC_EXEC_* status."""
     return lib().ccv_nnc_sm100_cmd_exec(cmd.cmd, cmd.backend, cmd.algorithm, C.byref(cmd.info), C.byref(hint if hint is not None else abi.NO_HINT), flags,
                                         _ptr_array(inputs), len(inputs), _ptr_array(outputs), len(outputs), stream.ptr if stream else None)
+
+
+def comm_unique_id():
+    """128-byte NCCL id made by rank 0 (ccv_nnc_sm100_comm_unique_id); ship it to the other ranks, then comm_init_rank."""
+    buf = C.create_string_buffer(128)
+    if lib().ccv_nnc_sm100_comm_unique_id(buf, 128) != 0:
+        raise RuntimeError("comm_unique_id failed: %s" % lib().ccv_nnc_sm100_last_error())
+    return buf.raw
+
+
+def comm_init_rank(unique_id, world, rank):
+    """Binds this process's current CUDA device into the communicator CCV_NNC_COMM_ALLREDUCE_* uses."""
+    buf = C.create_string_buffer(bytes(unique_id), 128)
+    if lib().ccv_nnc_sm100_comm_init_rank(buf, 128, world, rank) != 0:
+        raise RuntimeError("comm_init_rank failed: %s" % lib().ccv_nnc_sm100_last_error())
 
 
 def launch_count():
@@ -469,6 +490,10 @@ def CMD_SCALAR_MUL_FORWARD(p, **kw):
 
 def CMD_SCALAR_MUL_BACKWARD(p, **kw):
     return _blas(abi.CCV_NNC_SCALAR_MUL_BACKWARD, p, 0.0, **kw)
+
+
+def CMD_COMM_ALLREDUCE_FORWARD(**kw):
+    return _simple(abi.CCV_NNC_COMM_ALLREDUCE_FORWARD, **kw)
 
 
 def CMD_DATA_TRANSFER_FORWARD(**kw):

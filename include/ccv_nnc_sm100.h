@@ -336,6 +336,8 @@ enum {
 	CCV_NNC_FORMAT_TRANSFORM_BACKWARD = 0xe4a2b193,
 	CCV_NNC_GEMM_FORWARD = 0x7e87d00c,
 	CCV_NNC_GEMM_BACKWARD = 0x7e87d00d,
+	CCV_NNC_GROUP_NORM_FORWARD = 0x17deb074,
+	CCV_NNC_GROUP_NORM_BACKWARD = 0x17deb075,
 	CCV_NNC_LAYER_NORM_FORWARD = 0xbed3c264,
 	CCV_NNC_LAYER_NORM_BACKWARD = 0xbed3c265,
 	CCV_NNC_MAX_POOL_FORWARD = 0x7bec9360,
@@ -397,7 +399,7 @@ enum {
 	X(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) X(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) \
 	X(CCV_NNC_SOFTMAX_FORWARD) X(CCV_NNC_SOFTMAX_BACKWARD) \
 	X(CCV_NNC_BATCH_NORM_FORWARD) X(CCV_NNC_BATCH_NORM_BACKWARD) \
-	X(CCV_NNC_LAYER_NORM_FORWARD) X(CCV_NNC_LAYER_NORM_BACKWARD) \
+	X(CCV_NNC_LAYER_NORM_FORWARD) X(CCV_NNC_LAYER_NORM_BACKWARD) X(CCV_NNC_GROUP_NORM_FORWARD) X(CCV_NNC_GROUP_NORM_BACKWARD) \
 	X(CCV_NNC_RMSNORM_FORWARD) X(CCV_NNC_RMSNORM_BACKWARD) \
 	X(CCV_NNC_EWSUM_FORWARD) X(CCV_NNC_EWSUM_BACKWARD) \
 	X(CCV_NNC_ADD_FORWARD) X(CCV_NNC_ADD_BACKWARD) \
@@ -485,6 +487,17 @@ void ccv_nnc_sm100_event_free(void* const event);
 uint64_t ccv_nnc_sm100_launch_count(void);
 /* last CUDA error string seen by the backend (empty if none) */
 const char* ccv_nnc_sm100_last_error(void);
+
+/* Communicators behind CCV_NNC_COMM_ALLREDUCE_* (replaces ccv_nnc_nccl_get_comm, lib/nnc/gpu/ccv_nnc_compat.cu:1415-1445).
+ * One process per GPU: rank 0 calls _comm_unique_id (128 bytes), ships the id to the other ranks over the host's own side
+ * channel, every rank calls _comm_init_rank after selecting its device; COMM_ALLREDUCE on tensors of this device then
+ * sums across ranks.  One process, P devices (the reference's shape: tensor i on device i) needs no call at all, the
+ * communicators are created on first use.  NCCL is dlopen'ed on first use.  Return 0 on success.                       */
+int ccv_nnc_sm100_comm_unique_id(void* const id, const size_t size);
+int ccv_nnc_sm100_comm_init_rank(const void* const id, const size_t size, const int world, const int rank);
+int ccv_nnc_sm100_comm_rank(void);
+int ccv_nnc_sm100_comm_world(void);
+void ccv_nnc_sm100_comm_destroy(void);
 
 /* A flat, topologically ordered command list: the slice of ccv_nnc_graph_t that ccv_nnc_graph_run's sync path
  * executes (lib/nnc/ccv_nnc_graph_run.c:911-979: for each exec_info -> ccv_nnc_cmd_exec).  Optionally captured into

@@ -34,23 +34,34 @@ class RefFactory(object):
 POOLS = (abi.CCV_NNC_MAX_POOL_FORWARD, abi.CCV_NNC_MAX_POOL_BACKWARD, abi.CCV_NNC_AVERAGE_POOL_FORWARD, abi.CCV_NNC_AVERAGE_POOL_BACKWARD)
 
 
-def run_nodes(nodes):
+def run_node(node):
+    """One ccv_nnc_cmd_exec on CCV_NNC_BACKEND_CPU_REF.  CPU_REF's pooling kernels only walk image 0 of a batch
+    (pool/ccv_nnc_max_pool_cpu_ref.c:37-59), so pooling commands on a batch are issued once per image
+    on [H, W, C] slices."""
+    cmd, hint, flags, ins, outs = node
+    batch = next((t.array.shape[0] for t in list(ins) + list(outs) if t is not None and t.array.ndim == 4), 1)
+    if cmd.cmd in POOLS and batch > 1:
+        for n in range(batch):
+            sub_i = [None if t is None else HostTensor(t.array[n]) for t in ins]
+            sub_o = [None if t is None else HostTensor(t.array[n]) for t in outs]
+            st = ref.cmd_exec(cmd, hint, flags, sub_i, sub_o)
+            for t in sub_i + sub_o:
+                if t is not None:
+                    t.free()
+            if st != 0:
+                raise RuntimeError("CPU_REF returned %d for command 0x%08x" % (st, cmd.cmd))
+        return
+    st = ref.cmd_exec(cmd, hint, flags, ins, outs)
+    if st != 0:
+        raise RuntimeError("CPU_REF returned %d for command 0x%08x" % (st, cmd.cmd))
+
+
+def run_nodes(nodes, before=None, after=None):
     """ccv_nnc_graph_run's sync path on the reference: one ccv_nnc_cmd_exec (backend CPU_REF) per node, in order.
-    CPU_REF's pooling kernels only walk image 0 of a batch (pool/ccv_nnc_max_pool_cpu_ref.c:37-59), so
-    pooling commands on a batch are issued once per image on [H, W, C] slices."""
-    for cmd, hint, flags, ins, outs in nodes:
-        batch = next((t.array.shape[0] for t in list(ins) + list(outs) if t is not None and t.array.ndim == 4), 1)
-        if cmd.cmd in POOLS and batch > 1:
-            for n in range(batch):
-                sub_i = [None if t is None else HostTensor(t.array[n]) for t in ins]
-                sub_o = [None if t is None else HostTensor(t.array[n]) for t in outs]
-                st = ref.cmd_exec(cmd, hint, flags, sub_i, sub_o)
-                for t in sub_i + sub_o:
-                    if t is not None:
-                        t.free()
-                if st != 0:
-                    raise RuntimeError("CPU_REF returned %d for command 0x%08x" % (st, cmd.cmd))
-            continue
-        st = ref.cmd_exec(cmd, hint, flags, ins, outs)
-        if st != 0:
-            raise RuntimeError("CPU_REF returned %d for command 0x%08x" % (st, cmd.cmd))
+    before(i, node) / after(i, node) let a test snapshot the operands of every node (teacher-forced parity)."""
+    for i, node in enumerate(nodes):
+        if before:
+            before(i, node)
+        run_node(node)
+        if after:
+            after(i, node)

@@ -1,0 +1,145 @@
+"""CCV_NNC_COMM_ALLREDUCE_FORWARD on CCV_NNC_BACKEND_GPU_SM100 (ccv_b200/csrc/sm100_comm.cu), the protocol of
+test/int/nnc/nccl.tests.c:13-44: every participant contributes a tensor, every participant ends with the element-wise
+sum.  Integer-valued fp32 inputs make the sum exact, so the check is bit-for-bit.  With one visible GPU the command is
+checked in its single-participant forms; with two or more, two ranks (one process per GPU) run the real exchange and a
+2-way data-parallel step of a small model is compared with the single-device step on the concatenated batch
+(test/int/nnc/parallel.tests.c:192-371)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_allreduce_single_participant_is_a_copy(gpu):
+    nnc = gpu
+    stream = nnc.Stream(0)
+    a, b = nnc.gpu_tensor([1000]), nnc.gpu_tensor([1000])
+    x = np.arange(1000, dtype=np.float32)
+    a.upload(x), b.upload(np.zeros(1000, np.float32))
+    cmd = nnc.CMD_COMM_ALLREDUCE_FORWARD()
+    assert nnc.cmd_exec(cmd, None, 0, [a], [b], stream) == 0
+    stream.wait()
+    assert np.array_equal(b.download(), x)
+    assert nnc.cmd_exec(cmd, None, 0, [a], [a], stream) == 0  # in place
+    stream.wait()
+    assert np.array_equal(a.download(), x)
+    for t in (a, b, stream):
+        t.free()
+
+
+def test_allreduce_world_of_one_through_nccl(gpu):
+    nnc = gpu
+    nnc.comm_init_rank(nnc.comm_unique_id(), 1, 0)
+    stream = nnc.Stream(0)
+    a, b = nnc.gpu_tensor([4, 250]), nnc.gpu_tensor([4, 250])
+    x = np.random.RandomState(0).randint(-100, 100, size=(4, 250)).astype(np.float32)
+    a.upload(x)
+    l0 = nnc.launch_count()
+    assert nnc.cmd_exec(nnc.CMD_COMM_ALLREDUCE_FORWARD(), None, 0, [a, b], [a, b], stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+    stream.wait()
+    assert nnc.launch_count() == l0 + 1  # both tensors in one NCCL group
+    assert np.array_equal(a.download(), x)
+    nnc.lib().ccv_nnc_sm100_comm_destroy()
+    for t in (a, b, stream):
+        t.free()
+
+
+WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch
+import torch.distributed as dist
+from ccv_b200 import dp, nnc, resnet50
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo")  # side channel only: carries the 128-byte communicator id
+nnc.init()
+stream = nnc.Stream(rank)
+
+
+class TinyNet(resnet50.Net):
+    def _build_body(self, x, xs):
+        x, xs = self._conv(x, xs, 3, 8, 3, 2, 1, True, "c0", need_dx=False)
+        x = self._relu(x, xs, "r0")
+        x, xs = self._conv(x, xs, 8, 8, 3, 1, 1, True, "c1")
+        x = self._relu(x, xs, "r1")
+        return x, xs
+
+
+def run(batch, global_batch, x, y, allreduce):
+    net = TinyNet(batch, image=8, classes=5, global_batch=global_batch, device=rank, seed=3, learn_rate=0.1, algorithm=2)
+    net.input.upload(x), net.labels.upload(y)
+    for node in net.fwd + net.bwd:
+        assert nnc.cmd_exec(*node, stream=stream) == 0
+    if allreduce:
+        allreduce(net)
+    for node in net.opt:
+        assert nnc.cmd_exec(*node, stream=stream) == 0
+    stream.wait()
+    return net
+
+
+rs = np.random.RandomState(5)
+x, y = rs.rand(8, 8, 8, 3).astype(np.float32), rs.randint(0, 5, size=(8,)).astype(np.int32)
+exchange = {}
+
+
+def allreduce(net):
+    if "op" not in exchange:
+        exchange["op"] = dp.CommandAllreduce(net, dist, stream, rank, world)
+    exchange["op"].net = net
+    exchange["op"]()
+
+# 1. plain allreduce of integer-valued tensors: exact sum on every rank
+t = nnc.gpu_tensor([3, 1000], device=rank)
+t.upload(np.full((3, 1000), rank + 1, np.float32) * np.arange(1000, dtype=np.float32))
+holder = type("N", (), {"g_flat": t})()
+allreduce(holder)
+stream.wait()
+want = np.arange(1000, dtype=np.float32) * sum(range(1, world + 1))
+assert np.array_equal(t.download(), np.broadcast_to(want, (3, 1000))), "allreduce sum wrong on rank %%d" %% rank
+
+# 2. 2-way data parallel step == single-device step on the concatenated batch
+sharded = run(8 // world, 8, dp.shard(x, rank, world), dp.shard(y, rank, world), allreduce)
+single = run(8, 8, x, y, None)
+w_dp, w_1 = sharded.w_flat.download(), single.w_flat.download()
+err = np.abs(w_dp - w_1).max() / np.abs(w_1).max()
+assert err < 1e-5, "rank %%d: data-parallel weights differ from single-device weights by %%g" %% (rank, err)
+print("rank %%d ok %%g" %% (rank, err))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_allreduce_and_data_parallel_step(gpu, tmp_path):
+    nnc = gpu
+    if nnc.lib().ccv_nnc_device_count(nnc.CCV_STREAM_CONTEXT_GPU) < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        outs.append(out)
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (rank, out[-3000:])
+        assert "rank %d ok" % rank in out

@@ -1,4 +1,4 @@
-"""Parity of layer norm, rms norm and upsample (the ops that feed attention blocks / resampling) vs CPU_REF."""
+"""Parity of layer norm, group norm, rms norm and upsample (the ops that feed attention blocks / resampling) vs CPU_REF."""
 import numpy as np
 import pytest
 
@@ -46,6 +46,53 @@ def test_layer_norm_forward_backward(gpu, ref, shape, axes):
     st_g, (h_g, ds_g, db_g) = gpu_exec(nnc, bwd, None, 0, ins, mk())
     assert st_r == 0 and st_g == 0
     assert_close(h_g, h_r, 1e-3, "dx"), assert_close(ds_g, ds_r, 1e-3, "dscale"), assert_close(db_g, db_r, 1e-3, "dbias")
+
+
+def _gnorm(cmd_id, group_axis, groups, eps, affine, reduce_axes):
+    c = _nnc._simple(cmd_id)
+    c.info.gnorm.group_axis, c.info.gnorm.groups, c.info.gnorm.epsilon, c.info.gnorm.elementwise_affine = group_axis, groups, eps, affine
+    for i, a in enumerate(reduce_axes):
+        c.info.gnorm.reduce_axis[i] = a
+    c.info.gnorm.reduce_count = len(reduce_axes)
+    return c
+
+
+@pytest.mark.parametrize("shape,group_axis,groups,reduce_axes,affine", [
+    ((2, 16, 6, 5), 1, 4, (2, 3), 1),      # NCHW, test/unit/nnc/group.norm.tests.c: groups over channels, reduce over H, W
+    ((2, 6, 5, 16), 3, 4, (1, 2), 1),      # NHWC
+    ((3, 32, 7, 7), 1, 8, (2, 3), 0),      # no affine
+    ((4, 24, 10), 1, 3, (2,), 1),          # 3-d
+])
+def test_group_norm_forward_backward(gpu, ref, shape, group_axis, groups, reduce_axes, affine):
+    """norm/ccv_nnc_group_norm_cpu_ref.c: statistics per (sample, group); per-channel scale / bias.  CPU_REF reads its
+    epsilon through the lnorm arm of the parameter union (:46), i.e. the integer reduce_count reinterpreted as a float
+    (a denormal ~ 0) instead of gnorm.epsilon; this backend uses gnorm.epsilon as documented (lib/nnc/ccv_nnc.h:163) and
+    the inputs here have O(0.3) variance, so the 1e-5 epsilon moves inv_std by ~2e-5 relative, inside the tolerance."""
+    nnc = gpu
+    x = seeded(shape, 1, -1, 1)
+    rshape = tuple(groups if i == group_axis else (1 if i in reduce_axes else d) for i, d in enumerate(shape))
+    pshape = tuple(d if i == group_axis else 1 for i, d in enumerate(shape))
+    scale, bias = seeded(pshape, 2), seeded(pshape, 3)
+    fwd = _gnorm(abi.CCV_NNC_GROUP_NORM_FORWARD, group_axis, groups, 1e-5, affine, reduce_axes)
+    mk = lambda: [np.zeros(shape, np.float32), np.zeros(rshape, np.float32), np.zeros(rshape, np.float32)]
+    fin = [x, scale, bias] if affine else [x]
+    st_r, (y_r, m_r, s_r) = ref_exec(ref, fwd, None, 0, fin, mk())
+    st_g, (y_g, m_g, s_g) = gpu_exec(nnc, fwd, None, 0, fin, mk())
+    assert st_r == 0 and st_g == 0
+    assert_close(y_g, y_r, 1e-4, "y"), assert_close(m_g, m_r, 1e-5, "mean"), assert_close(s_g, s_r, 1e-4, "inv_std")
+    g = seeded(shape, 4, -1, 1)
+    bwd = _gnorm(abi.CCV_NNC_GROUP_NORM_BACKWARD, group_axis, groups, 1e-5, affine, reduce_axes)
+    if affine:
+        ins = [g, None, None, x, scale, None, None, m_r, s_r]
+        mk = lambda: [np.zeros(shape, np.float32), np.zeros(pshape, np.float32), np.zeros(pshape, np.float32)]
+    else:
+        ins = [g, None, None, x, None, m_r, s_r]
+        mk = lambda: [np.zeros(shape, np.float32)]
+    st_r, outs_r = ref_exec(ref, bwd, None, 0, ins, mk())
+    st_g, outs_g = gpu_exec(nnc, bwd, None, 0, ins, mk())
+    assert st_r == 0 and st_g == 0
+    for name, a, b in zip(("dx", "dscale", "dbias"), outs_g, outs_r):
+        assert_close(a, b, 1e-3, name)
 
 
 @pytest.mark.parametrize("shape,axes", [((6, 10, 64), (2,)), ((4, 3, 5, 40), (1, 2, 3))])

@@ -6,14 +6,17 @@ What can honestly be asserted: the FORWARD is well conditioned (a 1e-6 relative 
 logits by 1.4e-5) and is held to 1e-3 (CUDA-core fp32) / 2e-2 (one-pass TF32 through 53 contractions).  The BACKWARD of a
 randomly initialised 50-layer ReLU + small-batch batch-norm network is chaotic: the same 1e-6 perturbation moves the
 oracle's own flat gradient by 1.7e-2 in relative L2 (ReLU masks flip, batch-norm backward subtracts batch means), and
-convolution biases in front of a batch norm have a mathematically zero gradient.  So gradients are only checked for
-gross agreement (relative L2 of the whole gradient, cosine); per-command parity (tests/test_parity_*.py) is the real pin.
+convolution biases in front of a batch norm have a mathematically zero gradient.  So the free-running gradient is only
+checked for gross agreement (relative L2 of the whole gradient, cosine).  The real pin of the backward on ResNet shapes is
+the TEACHER-FORCED test: every one of the ~550 forward + backward nodes is executed on the GPU with exactly the operand
+values the oracle saw in front of that node, and its outputs are compared with the oracle's outputs of the same node
+(fp32 FFMA <= 1e-3, one-pass TF32 <= 1e-2 normalised max error; bit-for-bit ops are not separated out here).
 Also: the fused graph (peephole pass) and its CUDA-graph replay must reproduce the unfused eager result."""
 import numpy as np
 import pytest
 
 from ccv_b200 import abi, resnet50
-from tests.util import assert_close
+from tests.util import assert_close, rel_err
 
 pytestmark = pytest.mark.gpu
 BATCH, IMAGE, CLASSES = 4, 96, 10
@@ -43,12 +46,21 @@ def cpu_net(ref):
     x, lab = _inputs()
     cpu = resnet50.Net(BATCH, image=IMAGE, classes=CLASSES, factory=ref_factory.RefFactory(), seed=7)
     cpu.input.upload(x), cpu.labels.upload(lab)
-    ref_factory.run_nodes(cpu.fwd), ref_factory.run_nodes(cpu.bwd)
+    # operand snapshots around every node, for the teacher-forced test
+    cpu.snap_in, cpu.snap_out = [], []
+
+    def before(i, node):
+        cpu.snap_in.append([None if t is None else t.download() for t in node[3]])
+
+    def after(i, node):
+        cpu.snap_out.append([None if t is None else t.download() for t in node[4]])
+
+    ref_factory.run_nodes(cpu.fwd + cpu.bwd, before, after)
     return cpu
 
 
 @pytest.mark.ref
-@pytest.mark.parametrize("algo,tol_out,tol_grad", [(abi.CCV_NNC_SM100_ALGO_FFMA, 1e-3, 0.15), (abi.CCV_NNC_SM100_ALGO_TF32, 2e-2, 0.5)])
+@pytest.mark.parametrize("algo,tol_out,tol_grad", [(abi.CCV_NNC_SM100_ALGO_FFMA, 1e-3, None), (abi.CCV_NNC_SM100_ALGO_TF32, 2e-2, None)])
 def test_resnet50_forward_backward_vs_cpu_ref(gpu, cpu_net, algo, tol_out, tol_grad):
     nnc = gpu
     stream = nnc.Stream(0)
@@ -61,8 +73,43 @@ def test_resnet50_forward_backward_vs_cpu_ref(gpu, cpu_net, algo, tol_out, tol_g
     rel_l2 = np.linalg.norm(gg - gc) / np.linalg.norm(gc)
     cos = float(gg @ gc / (np.linalg.norm(gg) * np.linalg.norm(gc)))
     print("algo %d: gradient relative L2 error %.3e, cosine %.6f" % (algo, rel_l2, cos))
-    assert rel_l2 < tol_grad and cos > 0.9
+    assert rel_l2 < 1.0 and cos > 0.5, "free-running gradient grossly off (chaotic regime: see module docstring)"
     g.free(), net.free(), stream.free()
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("algo,tol", [(abi.CCV_NNC_SM100_ALGO_FFMA, 1e-3), (abi.CCV_NNC_SM100_ALGO_TF32, 1e-2)])
+def test_resnet50_every_node_teacher_forced_vs_cpu_ref(gpu, cpu_net, algo, tol):
+    nnc = gpu
+    stream = nnc.Stream(0)
+    net = resnet50.Net(BATCH, image=IMAGE, classes=CLASSES, seed=7, algorithm=algo)
+    nodes = net.fwd + net.bwd
+    assert len(nodes) == len(cpu_net.snap_in)
+    worst, failures = {}, []
+    for i, (cmd, hint, flags, ins, outs) in enumerate(nodes):
+        for t, v in zip(ins, cpu_net.snap_in[i]):
+            if t is not None:
+                t.upload(v)
+        assert nnc.cmd_exec(cmd, hint, flags, ins, outs, stream) == 0, "node %d (0x%08x)" % (i, cmd.cmd)
+        stream.wait()
+        for k, (t, want) in enumerate(zip(outs, cpu_net.snap_out[i])):
+            if t is None:
+                continue
+            got = t.download().reshape(want.shape).astype(np.float64)
+            assert np.isfinite(got).all(), "node %d output %d" % (i, k)
+            denom = np.abs(want).max()
+            if cmd.cmd == abi.CCV_NNC_CONVOLUTION_BACKWARD and k == 2:
+                # dbias = sum over pixels of g; in front of a batch norm that sum is mathematically 0, so what is left is
+                # summation rounding: hold it to the forward error bound of the sum (1e-3 * tol * sum |g|)
+                g_in = cpu_net.snap_in[i][0].astype(np.float64)
+                denom = max(denom, 1e-3 * np.abs(g_in).reshape(-1, g_in.shape[-1]).sum(axis=0).max())
+            e = float(np.abs(got - want).max() / max(denom, 1e-30))
+            worst[cmd.cmd] = max(worst.get(cmd.cmd, 0.0), e)
+            if e > tol:
+                failures.append("node %d (command 0x%08x) output %d: normalised max error %.3e > %.1e" % (i, cmd.cmd, k, e, tol))
+    print("algo %d worst per-command errors: %s" % (algo, ", ".join("0x%08x=%.1e" % kv for kv in sorted(worst.items()))))
+    assert not failures, "\n".join(failures[:40])
+    net.free(), stream.free()
 
 
 def test_fused_graph_and_cuda_graph_replay_match_the_unfused_run(gpu):

@@ -180,6 +180,15 @@ int main(int argc, char** argv)
 	case 17: time_gemm(200704, 256, 64, 0, 1); break; // the 1x1 64->256 convolution of ResNet layer1 at N=64 (write-dominated)
 	case 18: { ConvCase c = { 64, 56, 56, 64, 64, 3, 3, 1, 1, 1 }; time_conv(c, 0); time_conv(c, 2); } break; // BASELINE configs[1]
 	case 19: time_gemm(8192, 8192, 8192, 0, 1); break;
+	case 20: { // filter gradients with few filters: the taps-along-M kernel (sm100_umma_wgrad.cuh)
+		const ConvCase a = { 2, 12, 12, 32, 32, 3, 3, 1, 1, 1 }, b = { 3, 13, 9, 128, 48, 3, 3, 1, 1, 1 }, c = { 3, 13, 9, 64, 32, 3, 3, 2, 1, 1 }, d = { 5, 28, 28, 32, 64, 3, 3, 1, 1, 1 };
+		ok &= test_conv(a, 2, 0, -1, 1); ok &= test_conv(b, 2, 0, -1, 1); ok &= test_conv(c, 2, 0, -1, 1); ok &= test_conv(d, 2, 0, -1, 1); ok &= test_conv(k5, 2, 0, -1, 1);
+		ok &= test_conv(small_s1, 2, 0, -1, 1); ok &= test_conv(small_s2, 2, 0, -1, 1); ok &= test_conv(dil2, 2, 0, -1, 1);
+	} break;
+	case 21: { // ResNet-50 stem / layer-1 3x3 filter gradients at N = 256
+		const ConvCase c2 = { 256, 112, 112, 32, 32, 3, 3, 1, 1, 1 }, c3 = { 256, 112, 112, 32, 64, 3, 3, 1, 1, 1 }, l1 = { 256, 56, 56, 64, 64, 3, 3, 1, 1, 1 };
+		time_conv(c2, 2); time_conv(c3, 2); time_conv(l1, 2); time_conv(c2, 1); time_conv(c3, 1); time_conv(c2, 0); time_conv(c3, 0);
+	} break;
 	default: printf("unknown test id\n"); return 1;
 	}
 	printf("probe %d: %s\n", id, ok ? "ALL PASS" : "SOME FAIL");
