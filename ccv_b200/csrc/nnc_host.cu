@@ -596,6 +596,7 @@ int ccv_nnc_sm100_fused_bn_relu_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, 
 int ccv_nnc_sm100_fused_relu_bn_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 int ccv_nnc_sm100_fused_add_relu_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 }
 
 struct ccv_nnc_sm100_graph_s {
@@ -656,6 +657,8 @@ int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin,
 //      unmasked, so the rewrite is only applied when no later node reads g
 //  (c) EWSUM(a, b -> y) ; RELU_FORWARD in place on y                          -> y = relu(a + b)
 //  (d) EWSUM(a, b -> a) ; RELU_BACKWARD in place on a (mask y)                -> a = y > 0 ? a + b : 0
+//  (e) a run of SGD_FORWARD nodes with identical parameters (the per-parameter updates of a model; none of them reads
+//      what another one writes) -> one multi-tensor command; counts as (run length - 1) fused nodes
 int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
 {
 	std::vector<ccv_nnc_sm100_graph_node_t>& nodes = graph->nodes;
@@ -668,6 +671,37 @@ int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
 	for (size_t i = 0; i < n; i++)
 	{
 		ccv_nnc_sm100_graph_node_t& a = nodes[i];
+		// (e)
+		if (is_gpu_sm100(a) && a.cmd.cmd == CCV_NNC_SGD_FORWARD && a.inputs.size() == 3 && a.outputs.size() == 2)
+		{
+			size_t j = i + 1;
+			auto independent = [&](const ccv_nnc_sm100_graph_node_t& x, size_t from, size_t to) {
+				// x must not read anything the nodes [from, to) write (in-place a -> b, m -> n of the SAME node is fine)
+				for (size_t k = from; k < to; k++)
+					for (ccv_nnc_tensor_t* o : nodes[k].outputs)
+						for (ccv_nnc_tensor_t* in : x.inputs)
+							if (o == in || (o && in && o->data.u8 == in->data.u8))
+								return false;
+				return true;
+			};
+			while (j < n && is_gpu_sm100(nodes[j]) && nodes[j].cmd.cmd == CCV_NNC_SGD_FORWARD && nodes[j].inputs.size() == 3 && nodes[j].outputs.size() == 2 &&
+				memcmp(&nodes[j].cmd.info.sgd, &a.cmd.info.sgd, sizeof(a.cmd.info.sgd)) == 0 && nodes[j].flags == a.flags && independent(nodes[j], i, j))
+				j++;
+			if (j - i >= 2)
+			{
+				ccv_nnc_sm100_graph_node_t f = a;
+				for (size_t k = i + 1; k < j; k++)
+				{
+					f.inputs.insert(f.inputs.end(), nodes[k].inputs.begin(), nodes[k].inputs.end());
+					f.outputs.insert(f.outputs.end(), nodes[k].outputs.begin(), nodes[k].outputs.end());
+				}
+				f.fused = ccv_nnc_sm100_fused_sgd_multi;
+				out.push_back(f);
+				fused += (int)(j - i - 1);
+				i = j - 1;
+				continue;
+			}
+		}
 		if (i + 1 < n && is_gpu_sm100(a) && is_gpu_sm100(nodes[i + 1]))
 		{
 			ccv_nnc_sm100_graph_node_t& b = nodes[i + 1];
@@ -743,7 +777,7 @@ int ccv_nnc_sm100_graph_node(const ccv_nnc_sm100_graph_t* const graph, const int
 		return -1;
 	const ccv_nnc_sm100_graph_node_t& n = graph->nodes[i];
 	*cmd = n.cmd.cmd;
-	*fused_kind = n.fused == ccv_nnc_sm100_fused_bn_relu_forw ? 1 : n.fused == ccv_nnc_sm100_fused_relu_bn_back ? 2 : n.fused == ccv_nnc_sm100_fused_add_relu_forw ? 3 : n.fused == ccv_nnc_sm100_fused_add_relu_back ? 4 : 0;
+	*fused_kind = n.fused == ccv_nnc_sm100_fused_bn_relu_forw ? 1 : n.fused == ccv_nnc_sm100_fused_relu_bn_back ? 2 : n.fused == ccv_nnc_sm100_fused_add_relu_forw ? 3 : n.fused == ccv_nnc_sm100_fused_add_relu_back ? 4 : n.fused == ccv_nnc_sm100_fused_sgd_multi ? 5 : 0;
 	*input_size = (int)n.inputs.size();
 	*output_size = (int)n.outputs.size();
 	return 0;

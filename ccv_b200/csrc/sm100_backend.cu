@@ -10,6 +10,7 @@
 #include "sm100_ew.h"
 #include <cuda_runtime.h>
 #include <string.h>
+#include <vector>
 
 using namespace sm100;
 
@@ -983,6 +984,36 @@ int exec_sgd_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int 
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
+// A run of SGD_FORWARD commands with identical parameters, merged by ccv_nnc_sm100_graph_fuse: inputs = (g, a, m) x T,
+// outputs = (b, n) x T.  Every triple is validated exactly as exec_sgd_forw validates one command.
+int exec_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size % 3 != 0 || output_size * 3 != input_size * 2 || input_size == 0)
+		return CCV_NNC_EXEC_INVALID;
+	if (cmd.info.sgd.nesterov && cmd.info.sgd.dampening != 0)
+		return CCV_NNC_EXEC_INVALID;
+	const int T = input_size / 3;
+	std::vector<const float*> g(T), a(T), m(T);
+	std::vector<float*> b(T), n(T);
+	std::vector<size_t> counts(T);
+	for (int t = 0; t < T; t++)
+	{
+		for (int i = 0; i < 3; i++)
+			if (!inputs[3 * t + i] || !is_f32(inputs[3 * t + i]) || !view_of(inputs[3 * t + i]).contiguous)
+				return CCV_NNC_EXEC_INVALID;
+		counts[t] = view_of(inputs[3 * t]).count;
+		if (view_of(inputs[3 * t + 1]).count != counts[t] || view_of(inputs[3 * t + 2]).count != counts[t])
+			return CCV_NNC_EXEC_INVALID;
+		for (int i = 0; i < 2; i++)
+			if (!outputs[2 * t + i] || !is_f32(outputs[2 * t + i]) || !view_of(outputs[2 * t + i]).contiguous || view_of(outputs[2 * t + i]).count != counts[t])
+				return CCV_NNC_EXEC_INVALID;
+		g[t] = inputs[3 * t]->data.f32, a[t] = inputs[3 * t + 1]->data.f32, m[t] = inputs[3 * t + 2]->data.f32;
+		b[t] = outputs[2 * t]->data.f32, n[t] = outputs[2 * t + 1]->data.f32;
+	}
+	RC(sgd_multi_f32(stream_of(stream_context), T, g.data(), a.data(), m.data(), b.data(), n.data(), counts.data(), cmd.info.sgd.nesterov, cmd.info.sgd.rate, cmd.info.sgd.scale, cmd.info.sgd.decay, cmd.info.sgd.momentum, cmd.info.sgd.dampening));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
 int exec_invalid(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	return CCV_NNC_EXEC_INVALID; // e.g. SGD backward (sgd/ccv_nnc_sgd_cpu_ref.c:128-131)
@@ -1222,6 +1253,12 @@ extern "C" int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t cmd, const 
 		return CCV_NNC_EXEC_INVALID;
 	RC(ew_add_relu_bwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, o.count));
 	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// T SGD_FORWARD commands with identical parameters as one command: inputs (g, a, m) x T -> outputs (b, n) x T
+extern "C" int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return exec_sgd_multi(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 
 // ================================================================================================ registration

@@ -165,8 +165,10 @@ static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, c
 }
 
 // Kernel choice, from the measurements in profiles/r01_probe3_*.log and r01_probe4_*.log:
-//  * BN = 64 (<= 64 output columns) and weight gradients with <= 128 columns: the one-tile-per-CTA kernel, two CTAs per SM
-//    (these are L2-bound / short tiles; two independent CTAs hide more latency than one persistent CTA);
+//  * BN = 64 (<= 64 output columns) data gradients / transposed products and weight gradients with <= 128 columns: the
+//    one-tile-per-CTA kernel, two CTAs per SM (these are L2-bound / short tiles; two independent CTAs hide more latency
+//    than one persistent CTA); BN = 64 forward-shaped products (K-major filters) do gain from the persistent kernel
+//    (profiles/r01_probe5_wgrad_taps.log: 32 -> 64 at 112 x 112 fprop 0.635 -> 0.498 ms, dgrad 0.837 -> 1.131 ms);
 //  * otherwise the persistent kernel: long reductions (>= 12 k-iterations per tile) use 4 epilogue warps and the deepest
 //    operand pipeline (MMA-bound), short ones use 8 epilogue warps (the epilogue is then the critical path).
 // CCV_NNC_SM100_PERSISTENT=0 forces the one-tile kernel, =2 forces the persistent one, for A/B runs.
@@ -188,8 +190,8 @@ static int launch_umma_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUt
 	const int mode = persistent_mode();
 	const int iters_per_tile = (p.k_iters + p.splits - 1) / p.splits;
 	bool persistent = mode != 0;
-	if (mode == 1 && (bn == 64 || (BMODE == OP_IM2COL && bn == 128)))
-		persistent = false;
+	if (mode == 1 && ((bn == 64 && !(AMODE != OP_MN2D && BMODE == OP_K2D && p.splits == 1)) || (BMODE == OP_IM2COL && bn == 128)))
+		persistent = false; // bn = 64: only forward-shaped work (K-major B, no split-K) gains from the persistent kernel (r01_probe5)
 	if (persistent)
 	{
 		const bool long_k = iters_per_tile >= 12;
@@ -621,28 +623,37 @@ size_t conv_im2col_workspace_bytes(const ConvGeom& g)
 	return ((size_t)g.N * g.P * g.Q * kp + 2 * (size_t)g.K * kp) * sizeof(float) + 512;
 }
 // patches[m, (r, s, c)] = a[n, p * stride - pad + r * dil, q * stride - pad + s * dil, c] (0 outside / in the padding columns)
-__global__ void im2col_kernel(const ConvGeom g, const float* __restrict__ a, float* __restrict__ out, const int kp, const size_t total)
+// One thread = one 16-byte store (4 consecutive k of one patch row); k -> (tap row offset, tap column offset, channel) comes
+// from a table in shared memory, all index math is 32-bit.
+__global__ void __launch_bounds__(256) im2col_kernel(const ConvGeom g, const float* __restrict__ a, float* __restrict__ out, const int kp, const unsigned rows)
 {
+	__shared__ int tab_h[256], tab_w[256], tab_c[256];
 	const int rsc = g.R * g.S * g.C;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	for (int k = threadIdx.x; k < kp; k += blockDim.x)
 	{
-		const int k = (int)(i % kp);
-		const size_t m = i / kp;
-		float v = 0.f;
-		if (k < rsc)
+		const int c = k % g.C, t = k / g.C;
+		tab_h[k] = k < rsc ? (t / g.S) * g.dil_h - g.pad_h0 : -(1 << 28);
+		tab_w[k] = k < rsc ? (t % g.S) * g.dil_w - g.pad_w0 : -(1 << 28);
+		tab_c[k] = c;
+	}
+	__syncthreads();
+	const unsigned kq = (unsigned)kp >> 2;
+	const unsigned long long total = (unsigned long long)rows * kq;
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x)
+	{
+		const unsigned m = (unsigned)(i / kq), k0 = ((unsigned)(i - (unsigned long long)m * kq)) << 2;
+		const unsigned q = m % (unsigned)g.Q, u = m / (unsigned)g.Q;
+		const unsigned pp = u % (unsigned)g.P, n = u / (unsigned)g.P;
+		const int h0 = (int)pp * g.stride_h, w0 = (int)q * g.stride_w;
+		const float* const an = a + (long long)n * g.an;
+		float v[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++)
 		{
-			const int c = k % g.C;
-			const int t = k / g.C;
-			const int s = t % g.S, r = t / g.S;
-			const int q = (int)(m % g.Q);
-			const size_t u = m / g.Q;
-			const int p = (int)(u % g.P);
-			const int n = (int)(u / g.P);
-			const int h = p * g.stride_h - g.pad_h0 + r * g.dil_h, w = q * g.stride_w - g.pad_w0 + s * g.dil_w;
-			if (h >= 0 && h < g.H && w >= 0 && w < g.W)
-				v = __ldg(a + n * g.an + h * g.ah + w * g.aw + c);
+			const int h = h0 + tab_h[k0 + j], w = w0 + tab_w[k0 + j];
+			v[j] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? __ldg(an + h * g.ah + w * g.aw + tab_c[k0 + j]) : 0.f;
 		}
-		out[i] = v;
+		*reinterpret_cast<float4*>(out + (unsigned long long)m * kp + k0) = make_float4(v[0], v[1], v[2], v[3]);
 	}
 }
 // dir 0: packed[k, 0..kp) = w[k, 0..rsc) zero padded.  dir 1: w[k, j] (+)= packed[k, j]
@@ -659,11 +670,11 @@ __global__ void pack_filters_kernel(float* __restrict__ w, float* __restrict__ p
 }
 static int run_im2col(cudaStream_t stream, const ConvGeom& g, const float* a, float* patches, int kp)
 {
-	const size_t total = (size_t)g.N * g.P * g.Q * kp;
-	size_t blocks = (total + 255) / 256;
-	if (blocks > (size_t)num_sms() * 16)
-		blocks = (size_t)num_sms() * 16;
-	im2col_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, a, patches, kp, total);
+	const size_t rows = (size_t)g.N * g.P * g.Q;
+	size_t blocks = (rows * (kp / 4) + 255) / 256;
+	if (blocks > (size_t)num_sms() * 32)
+		blocks = (size_t)num_sms() * 32;
+	im2col_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, a, patches, kp, (unsigned)rows);
 	count_launch();
 	const cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess)

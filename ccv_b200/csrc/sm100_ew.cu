@@ -488,12 +488,25 @@ __global__ void pool_fwd_kernel(const PoolGeom g, const float* __restrict__ a, f
 	const size_t total = (size_t)g.N * g.P * g.Q * CV;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
 	{
-		const int c = (int)(i % CV) * VEC;
-		size_t r = i / CV;
-		const int q = (int)(r % g.Q);
-		r /= g.Q;
-		const int p = (int)(r % g.P);
-		const int n = (int)(r / g.P);
+		int c, q, p, n;
+		if (total <= 0xffffffffull)
+		{
+			// 32-bit index math (a 64-bit divide costs ~5x a 32-bit one and there are three per element)
+			const unsigned ii = (unsigned)i;
+			unsigned r = ii / (unsigned)CV;
+			c = (int)(ii - r * (unsigned)CV) * VEC;
+			const unsigned r2 = r / (unsigned)g.Q;
+			q = (int)(r - r2 * (unsigned)g.Q);
+			n = (int)(r2 / (unsigned)g.P);
+			p = (int)(r2 - (unsigned)n * (unsigned)g.P);
+		} else {
+			c = (int)(i % CV) * VEC;
+			size_t r = i / CV;
+			q = (int)(r % g.Q);
+			r /= g.Q;
+			p = (int)(r % g.P);
+			n = (int)(r / g.P);
+		}
 		const int h0 = max(p * g.stride_h - g.pad_h, 0), h1 = min(p * g.stride_h - g.pad_h + g.R, g.H);
 		const int w0 = max(q * g.stride_w - g.pad_w, 0), w1 = min(q * g.stride_w - g.pad_w + g.S, g.W);
 		float v[VEC];
@@ -565,12 +578,24 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const float* __restrict__ gb, 
 	const size_t total = (size_t)g.N * g.H * g.W * CV;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
 	{
-		const int c = (int)(i % CV) * VEC;
-		size_t r = i / CV;
-		const int w = (int)(r % g.W);
-		r /= g.W;
-		const int h = (int)(r % g.H);
-		const int n = (int)(r / g.H);
+		int c, w, h, n;
+		if (total <= 0xffffffffull)
+		{
+			const unsigned ii = (unsigned)i;
+			unsigned r = ii / (unsigned)CV;
+			c = (int)(ii - r * (unsigned)CV) * VEC;
+			const unsigned r2 = r / (unsigned)g.W;
+			w = (int)(r - r2 * (unsigned)g.W);
+			n = (int)(r2 / (unsigned)g.H);
+			h = (int)(r2 - (unsigned)n * (unsigned)g.H);
+		} else {
+			c = (int)(i % CV) * VEC;
+			size_t r = i / CV;
+			w = (int)(r % g.W);
+			r /= g.W;
+			h = (int)(r % g.H);
+			n = (int)(r / g.H);
+		}
 		// windows p with p * stride - pad <= h < p * stride - pad + R
 		const int p_lo = max((h + g.pad_h - g.R + g.stride_h) / g.stride_h, 0), p_hi = min((h + g.pad_h) / g.stride_h, g.P - 1);
 		const int q_lo = max((w + g.pad_w - g.S + g.stride_w) / g.stride_w, 0), q_hi = min((w + g.pad_w) / g.stride_w, g.Q - 1);
@@ -900,6 +925,102 @@ int sgd_f32(cudaStream_t s, const float* g, const float* a, const float* m, floa
 	else
 		sgd_kernel<1><<<grid_for(count, 256), 256, 0, s>>>(g, a, m, b, n, count, nesterov, rate, scale, decay, momentum, inv_dampening);
 	return check("sgd");
+}
+
+// Many SGD commands with the same hyper-parameters in one launch (the per-parameter SGD nodes of a model are a run of ~200
+// small tensors): the tensor table travels in the kernel parameters (<= SGD_MULTI_MAX tensors per launch), a block owns
+// one 4096-element chunk of one tensor.  Same arithmetic as sgd_kernel.
+constexpr int SGD_MULTI_MAX = 32;
+constexpr unsigned SGD_MULTI_CHUNK = 4096;
+struct SgdMulti {
+	const float* g[SGD_MULTI_MAX];
+	const float* a[SGD_MULTI_MAX];
+	const float* m[SGD_MULTI_MAX];
+	float* b[SGD_MULTI_MAX];
+	float* n[SGD_MULTI_MAX];
+	unsigned count[SGD_MULTI_MAX];
+	unsigned block_start[SGD_MULTI_MAX + 1];
+	int tensors;
+};
+__global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ SgdMulti t, const int nesterov, const float rate, const float scale, const float decay, const float momentum, const float inv_dampening)
+{
+	int ti = 0;
+	while (ti + 1 < t.tensors && blockIdx.x >= t.block_start[ti + 1])
+		ti++;
+	const unsigned base = (blockIdx.x - t.block_start[ti]) * SGD_MULTI_CHUNK;
+	const unsigned count = t.count[ti];
+	const float* const g = t.g[ti];
+	const float* const a = t.a[ti];
+	const float* const m = t.m[ti];
+	float* const b = t.b[ti];
+	float* const n = t.n[ti];
+#pragma unroll
+	for (int it = 0; it < 4; it++)
+	{
+		const unsigned i = base + (it * 256 + threadIdx.x) * 4;
+		if (i >= count)
+			break;
+		const float4 gv = *reinterpret_cast<const float4*>(g + i), av = *reinterpret_cast<const float4*>(a + i), mv = *reinterpret_cast<const float4*>(m + i);
+		const float gs[4] = { gv.x, gv.y, gv.z, gv.w }, as[4] = { av.x, av.y, av.z, av.w }, ms[4] = { mv.x, mv.y, mv.z, mv.w };
+		float bs[4], ns[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			if (nesterov)
+			{
+				float grad = scale * gs[j];
+				const float mom = ns[j] = momentum * ms[j] + grad + decay * as[j];
+				grad += momentum * mom;
+				bs[j] = as[j] - rate * grad;
+			} else {
+				const float mom = ns[j] = momentum * ms[j] + inv_dampening * (scale * gs[j] + decay * as[j]);
+				bs[j] = as[j] - rate * mom;
+			}
+		}
+		*reinterpret_cast<float4*>(b + i) = make_float4(bs[0], bs[1], bs[2], bs[3]);
+		*reinterpret_cast<float4*>(n + i) = make_float4(ns[0], ns[1], ns[2], ns[3]);
+	}
+}
+int sgd_multi_f32(cudaStream_t s, int tensors, const float* const* g, const float* const* a, const float* const* m, float* const* b, float* const* n, const size_t* counts, int nesterov, float rate, float scale, float decay, float momentum, float dampening)
+{
+	const float inv_dampening = 1.f - dampening;
+	int i = 0;
+	while (i < tensors)
+	{
+		SgdMulti t;
+		t.tensors = 0;
+		unsigned blocks = 0;
+		while (i < tensors && t.tensors < SGD_MULTI_MAX)
+		{
+			const bool vec = counts[i] % 4 == 0 && counts[i] < 0xffffffffull && aligned16(g[i]) && aligned16(a[i]) && aligned16(m[i]) && aligned16(b[i]) && aligned16(n[i]);
+			if (!vec)
+			{
+				if (t.tensors > 0)
+					break; // flush what is batched, then do this one on its own
+				if (sgd_f32(s, g[i], a[i], m[i], b[i], n[i], counts[i], nesterov, rate, scale, decay, momentum, dampening))
+					return -1;
+				i++;
+				continue;
+			}
+			if (counts[i] > 0)
+			{
+				const int k = t.tensors++;
+				t.g[k] = g[i], t.a[k] = a[i], t.m[k] = m[i], t.b[k] = b[i], t.n[k] = n[i];
+				t.count[k] = (unsigned)counts[i];
+				t.block_start[k] = blocks;
+				blocks += (unsigned)((counts[i] + SGD_MULTI_CHUNK - 1) / SGD_MULTI_CHUNK);
+			}
+			i++;
+		}
+		if (t.tensors > 0)
+		{
+			t.block_start[t.tensors] = blocks;
+			sgd_multi_kernel<<<blocks, 256, 0, s>>>(t, nesterov, rate, scale, decay, momentum, inv_dampening);
+			if (check("sgd_multi"))
+				return -1;
+		}
+	}
+	return 0;
 }
 
 // =============================================================================================== dtype conversion

@@ -62,6 +62,9 @@ int softmax_cce_bwd_f32(cudaStream_t s, const float* g, const void* label, int l
 // ---- SGD ------------------------------------------------------------------------------------------------------
 int sgd_f32(cudaStream_t s, const float* g, const float* a, const float* m, float* b, float* n, size_t count, int nesterov, float rate, float scale, float decay, float momentum, float dampening);
 
+// `tensors` independent SGD updates with the same hyper-parameters in ceil(tensors / 32) launches
+int sgd_multi_f32(cudaStream_t s, int tensors, const float* const* g, const float* const* a, const float* const* m, float* const* b, float* const* n, const size_t* counts, int nesterov, float rate, float scale, float decay, float momentum, float dampening);
+
 // ---- datatype / layout ----------------------------------------------------------------------------------------
 // dtype codes: 0 = f32, 1 = f16 (CPU_REF semantics: f32 -> f16 truncates, lib/ccv_util.c:1434-1440), 2 = f64, 3 = bf16 (RNE)
 int convert_dtype(cudaStream_t s, const void* a, int a_dtype, void* b, int b_dtype, size_t n);

@@ -129,6 +129,8 @@ def test_fused_graph_and_cuda_graph_replay_match_the_unfused_run(gpu):
     cid = g1.capture(stream)
     assert g1.replay(cid, stream) == 0
     stream.wait()
-    assert np.array_equal(fused.logits.download(), eager)
+    # same kernels, same data; split-K partial tiles are combined with red.global.add, whose arrival order differs from
+    # launch to launch, so a replay reproduces the eager result to fp32 summation-order rounding, not bit for bit
+    assert_close(fused.logits.download(), eager, 1e-5, "CUDA-graph replay vs eager")
     for x in (g0, g1, plain, fused, stream):
         x.free()
