@@ -161,7 +161,7 @@ def main():
         g_fb.exec_new(cmd, hint, flags, ins, outs)
     for cmd, hint, flags, ins, outs in net.opt:
         g_opt.exec_new(cmd, hint, flags, ins, outs)
-    n_fused = 0 if args.no_fuse else g_fb.fuse()
+    n_fused = 0 if args.no_fuse else g_fb.fuse() + g_opt.fuse()
 
     # synthetic batch in pinned host memory (for the e2e leg) and resident in HBM (for `value`)
     rs = np.random.RandomState(1234 + rank)

@@ -249,7 +249,7 @@ int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		if (db.batch != 1 && db.batch != g.batch)
 			return CCV_NNC_EXEC_INVALID;
 		for (int i = 0; i < g.batch; i++)
-			RC(colsum_f32(s, g.p + i * g.batch_inc, g.rows, g.cols, g.rs, db.p + (db.batch == 1 ? 0 : i * db.batch_inc), accumulate || (db.batch == 1 && i > 0)));
+			RC(colsum_f32(s, g.p + i * g.batch_inc, g.rows, g.cols, g.rs, db.p + (db.batch == 1 ? 0 : i * db.batch_inc), accumulate || (db.batch == 1 && i > 0), ccv_nnc_stream_context_get_workspace(stream_context, colsum_workspace_bytes(g.cols), CCV_TENSOR_GPU_MEMORY)));
 	}
 	if (dw_t)
 	{
@@ -385,7 +385,7 @@ int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	{
 		if (dbias_t->info.dim[0] != g.K || g.bh != (long long)g.Q * g.bw || g.bn != (long long)g.P * g.bh)
 			return CCV_NNC_EXEC_INVALID;
-		RC(colsum_f32(s, gb, (size_t)g.N * g.P * g.Q, g.K, g.bw, dbias_t->data.f32, accumulate));
+		RC(colsum_f32(s, gb, (size_t)g.N * g.P * g.Q, g.K, g.bw, dbias_t->data.f32, accumulate, ccv_nnc_stream_context_get_workspace(stream_context, colsum_workspace_bytes(g.K), CCV_TENSOR_GPU_MEMORY)));
 	}
 	if (dw_t)
 	{
@@ -1268,7 +1268,7 @@ REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_
 REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); }
 REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); }
 REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); }
-REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_sdpa_forw); }
+REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_forw); }
 REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_sdpa_back); }
 REGISTER_SM100(CCV_NNC_SOFTMAX_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_forw); }
 REGISTER_SM100(CCV_NNC_SOFTMAX_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_back); }

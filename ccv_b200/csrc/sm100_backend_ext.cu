@@ -74,9 +74,9 @@ extern "C" {
 
 // ---- scaled dot product attention ----------------------------------------------------------------------------------
 // [B, S, H, D] tensors (3-d [B, S, D] = one head), element strides from views; the feature axis must be contiguous
-static bool sdpa_axes(const ccv_nnc_tensor_t* const t, int& B, int& S, int& H, int& D, long long& sb, long long& ss, long long& sh)
+static bool sdpa_axes(const ccv_nnc_tensor_t* const t, const int datatype, int& B, int& S, int& H, int& D, long long& sb, long long& ss, long long& sh)
 {
-	if (CCV_GET_DATA_TYPE(t->info.datatype) != CCV_32F)
+	if (CCV_GET_DATA_TYPE(t->info.datatype) != datatype)
 		return false;
 	const int nd = nd_of(t);
 	if (nd != 3 && nd != 4)
@@ -105,8 +105,11 @@ static bool sdpa_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_tensor_t* const q,
 {
 	memset(&g, 0, sizeof(g));
 	int B2, B3, B4, H3, H4, D2, S3, S4;
-	if (!sdpa_axes(q, g.B, g.Sq, g.H, g.D, g.q_b, g.q_s, g.q_h) || !sdpa_axes(k, B2, g.Sk, g.Hk, D2, g.k_b, g.k_s, g.k_h) ||
-		!sdpa_axes(v, B3, S3, H3, g.Dv, g.v_b, g.v_s, g.v_h) || !sdpa_axes(o, B4, S4, H4, D2, g.o_b, g.o_s, g.o_h))
+	const int dt = CCV_GET_DATA_TYPE(q->info.datatype);
+	if (dt != CCV_32F && dt != CCV_16F && dt != CCV_16BF)
+		return false;
+	if (!sdpa_axes(q, dt, g.B, g.Sq, g.H, g.D, g.q_b, g.q_s, g.q_h) || !sdpa_axes(k, dt, B2, g.Sk, g.Hk, D2, g.k_b, g.k_s, g.k_h) ||
+		!sdpa_axes(v, dt, B3, S3, H3, g.Dv, g.v_b, g.v_s, g.v_h) || !sdpa_axes(o, dt, B4, S4, H4, D2, g.o_b, g.o_s, g.o_h))
 		return false;
 	if (B2 != g.B || B3 != g.B || B4 != g.B || S3 != g.Sk || S4 != g.Sq || H3 != g.Hk || H4 != g.H || D2 != g.Dv || g.Hk <= 0 || g.H % g.Hk != 0)
 		return false;
@@ -130,6 +133,23 @@ int ccv_nnc_sm100_exec_sdpa_forw(SM100_EXEC_ARGS)
 	if (!sdpa_geom(cmd, inputs[0], inputs[1], inputs[2], outputs[0], g))
 		return CCV_NNC_EXEC_INVALID;
 	const ccv_nnc_tensor_t* const mask_t = input_size > 3 ? inputs[3] : 0;
+	const int dt = CCV_GET_DATA_TYPE(inputs[0]->info.datatype);
+	if (dt != CCV_32F)
+	{
+		// 16-bit tensors: the tcgen05 flash-attention kernel (sm100_fmha.cu); like the reference's flash-attention backend it takes
+		// no additive mask, and it is specialised for a head dimension of 128
+		if (mask_t)
+			return CCV_NNC_EXEC_INVALID;
+		float* lse = 0;
+		if (output_size > 1 && outputs[1])
+		{
+			if (!packed_f32(outputs[1]) || count_of(outputs[1]) != (size_t)g.B * g.H * g.Sq)
+				return CCV_NNC_EXEC_INVALID;
+			lse = outputs[1]->data.f32;
+		}
+		const int rc = sdpa_forward_f16(stream_of(stream_context), g, dt == CCV_16BF, inputs[0]->data.u8, inputs[1]->data.u8, inputs[2]->data.u8, outputs[0]->data.u8, lse);
+		return rc == 0 ? CCV_NNC_EXEC_SUCCESS : (rc > 0 ? CCV_NNC_EXEC_NO_KERNEL : CCV_NNC_EXEC_INVALID);
+	}
 	const float* mask = 0;
 	if (mask_t)
 	{
@@ -162,6 +182,8 @@ int ccv_nnc_sm100_exec_sdpa_back(SM100_EXEC_ARGS)
 		return CCV_NNC_EXEC_INVALID;
 	if ((input_size > 6 && inputs[6]) || (input_size > 7 && inputs[7]))
 		return CCV_NNC_EXEC_INVALID;
+	if (CCV_GET_DATA_TYPE(inputs[3]->info.datatype) != CCV_32F)
+		return CCV_NNC_EXEC_NO_KERNEL; // 16-bit backward: not built yet
 	SdpaGeom g, dg;
 	if (!sdpa_geom(cmd, inputs[3], inputs[4], inputs[5], inputs[0], g) || !sdpa_geom(cmd, outputs[0], outputs[1], outputs[2], inputs[0], dg))
 		return CCV_NNC_EXEC_INVALID;

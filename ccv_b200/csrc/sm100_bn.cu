@@ -46,9 +46,12 @@ static int grid_for(size_t work_items, int threads, int max_waves = 8)
 	return blocks < 1 ? 1 : (int)blocks;
 }
 
-size_t bn_workspace_bytes(int C) { return (size_t)C * (2 * sizeof(double) + 4 * sizeof(float)); }
+// workspace: double s[2C] (reduced sums), float coef[4C] (per-channel a, b, p, q), float part[gy_max][2C] (per-block partial sums)
+static inline size_t bn_part_rows() { return (size_t)sms() * 4 + 8; }
+size_t bn_workspace_bytes(int C) { return (size_t)C * (2 * sizeof(double) + 4 * sizeof(float)) + bn_part_rows() * 2 * (size_t)C * sizeof(float) + 256; }
 static inline double* ws_sums(void* ws) { return (double*)ws; }
 static inline float* ws_coef(void* ws, int C) { return (float*)((double*)ws + 2 * (size_t)C); }
+static inline float* ws_part(void* ws, int C) { return (float*)(((uintptr_t)(ws_coef(ws, C) + 4 * (size_t)C) + 255) & ~(uintptr_t)255); }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -58,7 +61,7 @@ __device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cas
 // MODE 0: s1 = sum(x - k), s2 = sum((x - k)^2), k = x[0, c] (shift keeps the one-pass variance well conditioned).
 // MODE 1: s1 = sum(g'), s2 = sum(g' * (x - mean)); g' = g, or g masked by relu(x * a + b) > 0 when MASK.
 template <int MODE, int MASK>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t rows, const int C, double* __restrict__ ws, const int cpb)
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t rows, const int C, float* __restrict__ part, const int cpb)
 {
 	__shared__ float4 sh[2][256];
 	const int CV = C >> 2;
@@ -119,10 +122,41 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 			s1.x += u.x, s1.y += u.y, s1.z += u.z, s1.w += u.w;
 			s2.x += v.x, s2.y += v.y, s2.z += v.z, s2.w += v.w;
 		}
-		double* w1 = ws + cv * 4;
-		double* w2 = ws + C + cv * 4;
-		atomicAdd(w1, (double)s1.x), atomicAdd(w1 + 1, (double)s1.y), atomicAdd(w1 + 2, (double)s1.z), atomicAdd(w1 + 3, (double)s1.w);
-		atomicAdd(w2, (double)s2.x), atomicAdd(w2 + 1, (double)s2.y), atomicAdd(w2 + 2, (double)s2.z), atomicAdd(w2 + 3, (double)s2.w);
+		// per-block partial sums; partials_reduce_kernel adds the gridDim.y rows in a fixed order (no atomics: 600 same-address
+		// fp64 atomics per channel cost ~15 us per launch, profiles/r01_ncu_bn_reduce_apply.txt, and made the result run-dependent)
+		float* const row = part + (size_t)blockIdx.y * 2 * C;
+		st4(row + cv * 4, s1);
+		st4(row + C + cv * 4, s2);
+	}
+}
+
+// out[col] = sum over y of part[y][col] (double accumulation, fixed order): 32 columns x 32 row-lanes per block
+__global__ void __launch_bounds__(1024) bn_partials_reduce_kernel(const float* __restrict__ part, const int gy, const int ncols, double* __restrict__ out)
+{
+	__shared__ double sh[32][33];
+	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
+	const int col = blockIdx.x * 32 + cx;
+	double acc = 0;
+	if (col < ncols)
+	{
+		int y = yl;
+		for (; y + 96 < gy; y += 128)
+		{
+			const float a0 = part[(size_t)y * ncols + col], a1 = part[(size_t)(y + 32) * ncols + col], a2 = part[(size_t)(y + 64) * ncols + col], a3 = part[(size_t)(y + 96) * ncols + col];
+			acc += (double)a0 + (double)a1 + (double)a2 + (double)a3;
+		}
+		for (; y < gy; y += 32)
+			acc += (double)part[(size_t)y * ncols + col];
+	}
+	sh[yl][cx] = acc;
+	__syncthreads();
+	if (yl == 0 && col < ncols)
+	{
+		double t = 0;
+#pragma unroll
+		for (int j = 0; j < 32; j++)
+			t += sh[j][cx];
+		out[col] = t;
 	}
 }
 
@@ -313,22 +347,20 @@ static void reduce_config(size_t rows, int CV, int& cpb, dim3& grid)
 }
 
 template <int MODE, int MASK>
-static int run_reduce(cudaStream_t s, const float* x, const float* g, const float* mean, const float* coef, size_t outer, int C, size_t inner, double* ws)
+static int run_reduce(cudaStream_t s, const float* x, const float* g, const float* mean, const float* coef, size_t outer, int C, size_t inner, double* ws, float* part)
 {
 	if (inner == 1 && C % 4 == 0 && aligned16(x) && (MODE == 0 || aligned16(g)))
 	{
-		const cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)C * 2 * sizeof(double), s);
-		if (e != cudaSuccess)
-		{
-			set_last_error("memset(bn)", e);
-			return -1;
-		}
 		int cpb;
 		dim3 grid;
 		reduce_config(outer, C / 4, cpb, grid);
-		bn_reduce_kernel<MODE, MASK><<<grid, 256, 0, s>>>(x, g, mean, coef, outer, C, ws, cpb);
-	} else
-		bn_reduce_generic_kernel<MODE, MASK><<<C, 512, 0, s>>>(x, g, mean, coef, outer, C, inner, ws);
+		bn_reduce_kernel<MODE, MASK><<<grid, 256, 0, s>>>(x, g, mean, coef, outer, C, part, cpb);
+		if (check("bn_reduce"))
+			return -1;
+		bn_partials_reduce_kernel<<<(2 * C + 31) / 32, 1024, 0, s>>>(part, (int)grid.y, 2 * C, ws);
+		return check("bn_partials_reduce");
+	}
+	bn_reduce_generic_kernel<MODE, MASK><<<C, 512, 0, s>>>(x, g, mean, coef, outer, C, inner, ws);
 	return check("bn_reduce");
 }
 
@@ -349,7 +381,7 @@ int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scal
 		return 0;
 	double* ws = ws_sums(workspace);
 	float* coef = ws_coef(workspace, C);
-	if (run_reduce<0, 0>(s, x, 0, 0, 0, outer, C, inner, ws))
+	if (run_reduce<0, 0>(s, x, 0, 0, 0, outer, C, inner, ws, ws_part(workspace, C)))
 		return -1;
 	bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, inner, ws, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, coef);
 	if (check("bn_fwd_finalize"))
@@ -387,7 +419,7 @@ int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scal
 		if (check("bn_coef"))
 			return -1;
 	}
-	if (mask ? run_reduce<1, 1>(s, x, g, saved_mean, coef, outer, C, inner, ws) : run_reduce<1, 0>(s, x, g, saved_mean, coef, outer, C, inner, ws))
+	if (mask ? run_reduce<1, 1>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C)) : run_reduce<1, 0>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C)))
 		return -1;
 	bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(ws, C, (float)((double)outer * (double)inner), scale, saved_mean, saved_inv_std, dscale, dbias, coef);
 	if (check("bn_bwd_finalize"))

@@ -52,6 +52,10 @@ int sdpa_forward_f32(cudaStream_t s, const SdpaGeom& g, const float* q, const fl
 // dg carries the strides of dq / dk / dv in its q_* / k_* / v_* fields
 int sdpa_backward_f32(cudaStream_t s, const SdpaGeom& g, const float* dout, const float* q, const float* k, const float* v, float* dq, float* dk, float* dv, const SdpaGeom& dg, void* workspace);
 
+// 16-bit (bf16 / fp16) flash attention forward on tcgen05 (sm100_fmha.cu): D = Dv = 128; lse [B, H, Sq] fp32 or NULL.
+// returns 0 on success, 1 when the shape is not covered, < 0 on CUDA errors
+int sdpa_forward_f16(cudaStream_t s, const SdpaGeom& g, int is_bf16, const void* q, const void* k, const void* v, void* o, float* lse);
+
 // bookkeeping shared by every launcher in the backend
 void count_launch(int n = 1);
 unsigned long long launch_count();

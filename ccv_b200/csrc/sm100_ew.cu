@@ -349,7 +349,7 @@ __global__ void colsum_kernel(const float* __restrict__ g, const size_t rows, co
 }
 // Vector form (cols, ld multiples of 4, 16-byte aligned): a thread owns one float4 column group and keeps four row loads
 // in flight; a block covers `cpb` column groups x (256 / cpb) rows per step.
-__global__ void __launch_bounds__(256) colsum_vec_kernel(const float4* __restrict__ g, const size_t rows, const int cols4, const long long ld4, float* __restrict__ out, const int cpb)
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const float4* __restrict__ g, const size_t rows, const int cols4, const long long ld4, float* __restrict__ out, float* __restrict__ part, const int cpb)
 {
 	__shared__ float4 sh[256];
 	const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb, rpi = 256 / cpb;
@@ -384,15 +384,50 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float4* __restric
 			const float4 v = sh[j * cpb + tx];
 			a0.x += v.x, a0.y += v.y, a0.z += v.z, a0.w += v.w;
 		}
-		float* const o = out + 4 * (size_t)col4;
-		atomicAdd(o, a0.x), atomicAdd(o + 1, a0.y), atomicAdd(o + 2, a0.z), atomicAdd(o + 3, a0.w);
+		if (part) // two-stage: per-block partial rows, summed in a fixed order by colsum_partials_kernel
+			*reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * cols4 + col4) * 4) = a0;
+		else {
+			float* const o = out + 4 * (size_t)col4;
+			atomicAdd(o, a0.x), atomicAdd(o + 1, a0.y), atomicAdd(o + 2, a0.z), atomicAdd(o + 3, a0.w);
+		}
 	}
 }
-int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long ld, float* out, int accumulate)
+// out[col] (+)= sum over y of part[y][col]: 32 columns x 32 row-lanes per block, fixed summation order
+__global__ void __launch_bounds__(1024) colsum_partials_kernel(const float* __restrict__ part, const int gy, const int ncols, float* __restrict__ out, const int accumulate)
+{
+	__shared__ float sh[32][33];
+	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
+	const int col = blockIdx.x * 32 + cx;
+	float acc = 0.f;
+	if (col < ncols)
+	{
+		int y = yl;
+		for (; y + 96 < gy; y += 128)
+		{
+			const float a0 = part[(size_t)y * ncols + col], a1 = part[(size_t)(y + 32) * ncols + col], a2 = part[(size_t)(y + 64) * ncols + col], a3 = part[(size_t)(y + 96) * ncols + col];
+			acc += (a0 + a1) + (a2 + a3);
+		}
+		for (; y < gy; y += 32)
+			acc += part[(size_t)y * ncols + col];
+	}
+	sh[yl][cx] = acc;
+	__syncthreads();
+	if (yl == 0 && col < ncols)
+	{
+		float t = 0.f;
+#pragma unroll
+		for (int j = 0; j < 32; j++)
+			t += sh[j][cx];
+		out[col] = accumulate ? out[col] + t : t;
+	}
+}
+size_t colsum_workspace_bytes(int cols) { return ((size_t)sms() * 8 + 8) * (size_t)((cols + 3) / 4 * 4) * sizeof(float); }
+int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long ld, float* out, int accumulate, void* workspace)
 {
 	if (cols <= 0)
 		return 0;
-	if (!accumulate)
+	const bool vec = cols % 4 == 0 && ld % 4 == 0 && (((uintptr_t)g) & 15) == 0;
+	if (!accumulate && !(vec && workspace && rows > 0))
 	{
 		const cudaError_t e = cudaMemsetAsync(out, 0, (size_t)cols * 4, s);
 		if (e != cudaSuccess)
@@ -403,7 +438,7 @@ int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long 
 	}
 	if (rows == 0)
 		return 0;
-	if (cols % 4 == 0 && ld % 4 == 0 && (((uintptr_t)g) & 15) == 0)
+	if (vec)
 	{
 		const int cols4 = cols / 4;
 		int cpb = 1;
@@ -417,8 +452,15 @@ int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long 
 			gy = cap;
 		if (gy < 1)
 			gy = 1;
-		colsum_vec_kernel<<<dim3(gx, (unsigned)gy), 256, 0, s>>>((const float4*)g, rows, cols4, ld / 4, out, cpb);
-		return check("colsum_vec");
+		colsum_vec_kernel<<<dim3(gx, (unsigned)gy), 256, 0, s>>>((const float4*)g, rows, cols4, ld / 4, out, (float*)workspace, cpb);
+		if (check("colsum_vec"))
+			return -1;
+		if (workspace)
+		{
+			colsum_partials_kernel<<<(cols + 31) / 32, 1024, 0, s>>>((const float*)workspace, (int)gy, cols, out, accumulate);
+			return check("colsum_partials");
+		}
+		return 0;
 	}
 	const int cpb = cols >= 256 ? 256 : (cols >= 128 ? 128 : (cols >= 64 ? 64 : 32));
 	const int rpi = 256 / cpb;

@@ -20,7 +20,9 @@ int ew_mul_bcast_f32(cudaStream_t s, float p, const float* a, const int* astride
 int ew_relu_fwd_f32(cudaStream_t s, const float* a, float* b, size_t n);
 int ew_relu_bwd_f32(cudaStream_t s, const float* g, const float* b, float* h, size_t n); // h = b > 0 ? g : 0
 // out[c] (+)= sum over rows of g[row * ld + c]  (bias gradients of GEMM / convolution)
-int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long ld, float* out, int accumulate);
+// workspace (colsum_workspace_bytes(cols), may be NULL): per-block partial rows, combined in a fixed order instead of by atomics
+size_t colsum_workspace_bytes(int cols);
+int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long ld, float* out, int accumulate, void* workspace);
 // reduce a <= 4-d tensor over the axes where rdim == 1 (sum); out has rdim shape, contiguous
 int reduce_sum_bcast_f32(cudaStream_t s, const float* a, const int* adim, const int* astride, float* out, const int* rdim, float scale, int accumulate);
 

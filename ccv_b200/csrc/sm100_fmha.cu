@@ -1,0 +1,425 @@
+// sm100_fmha.cu -- SCALED_DOT_PRODUCT_ATTENTION forward for 16-bit tensors (bf16 / fp16), head dimension 128:
+// one flash-attention kernel on the tcgen05 tensor cores.  Semantics: scaled_dot_product_attention/
+// ccv_nnc_scaled_dot_product_attention_cpu_ref.c:16-183 (O = softmax(scale * Q K^T [causal, bottom-right aligned :147]) V,
+// GQA through H / Hk :99,113), the same restrictions as the reference's flash-attention backend
+// (gpu/ccv_nnc_scaled_dot_product_attention_flash_attn.cu:13-205: 16-bit only, no additive mask, no unify-head weights).
+//
+// One CTA = 128 query rows of one (batch, head); 192 threads:
+//   warp 0    TMA producer: Q once, then K_j / V_j blocks of 128 keys through two-stage rings (4-D tensor maps over the
+//             caller's [B, S, H, D] strides, 128-byte swizzle)
+//   warp 1    tcgen05.mma issuer (kind::f16, fp32 accumulate in TMEM):
+//               S_j = Q K_j^T  -> TMEM S[j & 1]   (issued one block ahead, so it overlaps the softmax of block j - 1)
+//               O_j = P_j V_j  -> TMEM O          (P_j from shared memory, V_j as an MN-major operand)
+//   warps 2-5 softmax: one query row per thread.  Row max from a first pass over S_j in TMEM, then exp2 / row sum / bf16
+//             P_j written into the 128-byte-swizzled K-major smem tile the second MMA reads; the running output lives in
+//             registers: acc = acc * alpha_j + O_j (O_j read back from TMEM), normalised by the row sum at the end.
+// TMEM: S0, S1, O = 3 x 128 columns.  smem: Q 32 KB + K 2 x 32 KB + V 2 x 32 KB + P 32 KB = 192 KB.
+#include "sm100_contract.h"
+#include "sm100_ptx.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+
+namespace sm100 {
+
+namespace {
+
+constexpr int FM_BLOCK = 128; // query rows per CTA = keys per block
+constexpr int FM_D = 128;     // head dimension (q/k and v)
+constexpr int FM_TILE_BYTES = FM_BLOCK * FM_D * 2; // 32 KB: two 128 x 64 swizzle atoms
+constexpr int FM_ATOM_BYTES = FM_BLOCK * 128;      // 16 KB
+constexpr int FM_KV_STAGES = 2;
+
+struct FmhaParams {
+	int H, Hk, Sq, Sk;
+	int causal;
+	int is_bf16;
+	float scale_log2; // scale * log2(e)
+	void* o;
+	long long o_b, o_s, o_h; // element strides
+	float* lse;              // [B, H, Sq] or NULL
+	uint32_t idesc_qk, idesc_pv;
+	uint32_t v_lbo, v_sbo, v_layout, v_kstep; // smem descriptor of the MN-major V operand
+};
+
+struct FmhaSmem {
+	static constexpr int Q_OFF = 0;
+	static constexpr int K_OFF = Q_OFF + FM_TILE_BYTES;
+	static constexpr int V_OFF = K_OFF + FM_KV_STAGES * FM_TILE_BYTES;
+	static constexpr int P_OFF = V_OFF + FM_KV_STAGES * FM_TILE_BYTES;
+	static constexpr int BAR_OFF = P_OFF + FM_TILE_BYTES;
+	static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t pack2(const float a, const float b, const int is_bf16)
+{
+	if (is_bf16)
+	{
+		const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+		return *reinterpret_cast<const uint32_t*>(&v);
+	}
+	const __half2 v = __floats2half2_rn(a, b);
+	return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(192, 1) fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const FmhaParams p)
+{
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	uint64_t* bars = (uint64_t*)(smem + FmhaSmem::BAR_OFF);
+	uint64_t* q_full = bars;
+	uint64_t* k_full = bars + 1;  // [2]
+	uint64_t* k_empty = bars + 3; // [2]
+	uint64_t* v_full = bars + 5;  // [2]
+	uint64_t* v_empty = bars + 7; // [2]
+	uint64_t* s_full = bars + 9;  // [2] MMA -> softmax
+	uint64_t* s_empty = bars + 11; // [2] softmax -> MMA (4 arrivals)
+	uint64_t* p_full = bars + 13; // softmax -> MMA (4 arrivals)
+	uint64_t* o_full = bars + 14; // MMA -> softmax
+	uint32_t* tmem_slot = (uint32_t*)(bars + 15);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int q0 = blockIdx.x * FM_BLOCK;
+	const int h = blockIdx.y, b = blockIdx.z;
+	const int hk = h / (p.H / p.Hk);
+	// keys this tile attends: causal is aligned to the bottom-right corner (query i sees keys <= i + Sk - Sq)
+	const int shift = p.Sk - p.Sq;
+	int kv_end = p.Sk;
+	if (p.causal)
+		kv_end = min(p.Sk, max(q0 + FM_BLOCK + shift, 0));
+	const int n_blk = (kv_end + FM_BLOCK - 1) / FM_BLOCK;
+
+	if (warp == 0 && lane == 0)
+	{
+		tma_prefetch_desc(&tmQ);
+		tma_prefetch_desc(&tmK);
+		tma_prefetch_desc(&tmV);
+		mbar_init(q_full, 1);
+		for (int s = 0; s < 2; s++)
+		{
+			mbar_init(&k_full[s], 1), mbar_init(&k_empty[s], 1);
+			mbar_init(&v_full[s], 1), mbar_init(&v_empty[s], 1);
+			mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], 4);
+		}
+		mbar_init(p_full, 4);
+		mbar_init(o_full, 1);
+		fence_mbar_init();
+	}
+	if (warp == 1)
+	{
+		tmem_alloc(tmem_slot, 512);
+		tmem_relinquish();
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+	const uint32_t tmem_o = tmem_base + 256;
+
+	if (warp == 0)
+	{
+		if (lane == 0 && n_blk > 0)
+		{
+			mbar_expect_tx(q_full, FM_TILE_BYTES);
+			tma_load_4d(smem + FmhaSmem::Q_OFF, &tmQ, q_full, 0, h, q0, b);
+			tma_load_4d(smem + FmhaSmem::Q_OFF + FM_ATOM_BYTES, &tmQ, q_full, 64, h, q0, b);
+			for (int j = 0; j < n_blk; j++)
+			{
+				const int s = j & 1;
+				const uint32_t ph = (uint32_t)(j >> 1) & 1;
+				mbar_wait(&k_empty[s], ph ^ 1);
+				mbar_expect_tx(&k_full[s], FM_TILE_BYTES);
+				uint8_t* const sk = smem + FmhaSmem::K_OFF + s * FM_TILE_BYTES;
+				tma_load_4d(sk, &tmK, &k_full[s], 0, hk, j * FM_BLOCK, b);
+				tma_load_4d(sk + FM_ATOM_BYTES, &tmK, &k_full[s], 64, hk, j * FM_BLOCK, b);
+				mbar_wait(&v_empty[s], ph ^ 1);
+				mbar_expect_tx(&v_full[s], FM_TILE_BYTES);
+				uint8_t* const sv = smem + FmhaSmem::V_OFF + s * FM_TILE_BYTES;
+				tma_load_4d(sv, &tmV, &v_full[s], 0, hk, j * FM_BLOCK, b);
+				tma_load_4d(sv + FM_ATOM_BYTES, &tmV, &v_full[s], 64, hk, j * FM_BLOCK, b);
+			}
+		}
+	} else if (warp == 1) {
+		if (n_blk > 0)
+		{
+			const uint32_t q_addr = smem_u32(smem + FmhaSmem::Q_OFF);
+			const uint32_t p_addr = smem_u32(smem + FmhaSmem::P_OFF);
+			// S_j = Q K_j^T into S[j & 1]
+			auto issue_qk = [&](const int j) {
+				const int s = j & 1;
+				const uint32_t ph = (uint32_t)(j >> 1) & 1;
+				mbar_wait(&s_empty[s], ph ^ 1); // softmax has finished reading what block j - 2 left in this buffer
+				mbar_wait(&k_full[s], ph);
+				tc_fence_after();
+				if (lane == 0)
+				{
+					const uint32_t k_addr = smem_u32(smem + FmhaSmem::K_OFF + s * FM_TILE_BYTES);
+#pragma unroll
+					for (int k = 0; k < FM_D / 16; k++)
+					{
+						const uint32_t off = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
+						umma_f16(tmem_base + s * 128, umma_smem_desc(q_addr + off, 16, 1024, 2), umma_smem_desc(k_addr + off, 16, 1024, 2), p.idesc_qk, k > 0 ? 1u : 0u);
+					}
+					umma_commit(&k_empty[s]);
+					umma_commit(&s_full[s]);
+				}
+				__syncwarp();
+			};
+			mbar_wait(q_full, 0);
+			issue_qk(0);
+			for (int j = 0; j < n_blk; j++)
+			{
+				if (j + 1 < n_blk)
+					issue_qk(j + 1);
+				const int s = j & 1;
+				const uint32_t ph = (uint32_t)(j >> 1) & 1;
+				mbar_wait(p_full, (uint32_t)j & 1);
+				mbar_wait(&v_full[s], ph);
+				tc_fence_after();
+				if (lane == 0)
+				{
+					const uint32_t v_addr = smem_u32(smem + FmhaSmem::V_OFF + s * FM_TILE_BYTES);
+#pragma unroll
+					for (int k = 0; k < FM_BLOCK / 16; k++)
+					{
+						const uint32_t poff = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
+						umma_f16(tmem_o, umma_smem_desc(p_addr + poff, 16, 1024, 2), umma_smem_desc(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo, p.v_layout), p.idesc_pv, k > 0 ? 1u : 0u);
+					}
+					umma_commit(&v_empty[s]);
+					umma_commit(o_full);
+				}
+				__syncwarp();
+			}
+		}
+	} else {
+		// ------------------------------------------------------------------ softmax / output (warps 2..5)
+		const int quarter = warp & 3;
+		const int row = quarter * 32 + lane;
+		const int qi = q0 + row;
+		const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+		const int kv_limit = p.causal ? min(p.Sk, qi + shift + 1) : p.Sk; // keys [0, kv_limit) are visible to this row
+		float acc[FM_D];
+#pragma unroll
+		for (int i = 0; i < FM_D; i++)
+			acc[i] = 0.f;
+		float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+		uint8_t* const p_row = smem + FmhaSmem::P_OFF + row * 128;
+		for (int j = 0; j < n_blk; j++)
+		{
+			const int s = j & 1;
+			mbar_wait(&s_full[s], (uint32_t)(j >> 1) & 1);
+			tc_fence_after();
+			const uint32_t ts = tmem_base + s * 128 + lane_sel;
+			const int kv0 = j * FM_BLOCK;
+			const bool edge = kv0 + FM_BLOCK > kv_limit; // some keys of this block are masked for this row
+			// pass 1: row max
+			float mx = -INFINITY;
+#pragma unroll 1
+			for (int c = 0; c < 4; c++)
+			{
+				uint32_t r[32];
+				tmem_ld_32x32(ts + c * 32, r);
+				tmem_ld_wait();
+				if (edge)
+				{
+#pragma unroll
+					for (int i = 0; i < 32; i++)
+						if (kv0 + c * 32 + i < kv_limit)
+							mx = fmaxf(mx, __uint_as_float(r[i]));
+				} else {
+#pragma unroll
+					for (int i = 0; i < 32; i++)
+						mx = fmaxf(mx, __uint_as_float(r[i]));
+				}
+			}
+			const float m_new = fmaxf(m, mx * p.scale_log2);
+			const float m_use = m_new == -INFINITY ? 0.f : m_new; // a fully masked row keeps p = 0 without NaN
+			const float alpha = exp2f(m - m_use);                  // m = -inf -> 0
+			// O_{j-1} is complete once o_full flips; it also means P / V of block j - 1 are no longer being read
+			if (j > 0)
+			{
+				mbar_wait(o_full, (uint32_t)(j - 1) & 1);
+				tc_fence_after();
+#pragma unroll
+				for (int c = 0; c < 4; c++)
+				{
+					uint32_t r[32];
+					tmem_ld_32x32(tmem_o + lane_sel + c * 32, r);
+					tmem_ld_wait();
+#pragma unroll
+					for (int i = 0; i < 32; i++)
+						acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+				}
+			}
+			// pass 2: p = exp2(s * scale_log2 - m), row sum, P tile in smem (K-major, 128-byte swizzle)
+			float sum = 0.f;
+#pragma unroll 1
+			for (int c = 0; c < 4; c++)
+			{
+				uint32_t r[32];
+				tmem_ld_32x32(ts + c * 32, r);
+				tmem_ld_wait();
+				uint32_t pk[16];
+#pragma unroll
+				for (int i = 0; i < 32; i += 2)
+				{
+					float e0 = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_use));
+					float e1 = exp2f(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_use));
+					if (edge)
+					{
+						if (kv0 + c * 32 + i >= kv_limit)
+							e0 = 0.f;
+						if (kv0 + c * 32 + i + 1 >= kv_limit)
+							e1 = 0.f;
+					}
+					sum += e0 + e1;
+					pk[i >> 1] = pack2(e0, e1, p.is_bf16);
+				}
+				uint8_t* const atom = p_row + (c >> 1) * FM_ATOM_BYTES;
+#pragma unroll
+				for (int q4 = 0; q4 < 4; q4++)
+				{
+					const int chunk = (c & 1) * 4 + q4;
+					*reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+				}
+			}
+			l = fmaf(l, alpha, sum);
+			m = m_new;
+			alpha_prev = alpha;
+			// hand S[s] back and publish P_j to the tensor core (generic-proxy smem writes -> async proxy)
+			fence_proxy_async();
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0)
+			{
+				mbar_arrive(&s_empty[s]);
+				mbar_arrive(p_full);
+			}
+		}
+		if (n_blk > 0)
+		{
+			mbar_wait(o_full, (uint32_t)(n_blk - 1) & 1);
+			tc_fence_after();
+#pragma unroll
+			for (int c = 0; c < 4; c++)
+			{
+				uint32_t r[32];
+				tmem_ld_32x32(tmem_o + lane_sel + c * 32, r);
+				tmem_ld_wait();
+#pragma unroll
+				for (int i = 0; i < 32; i++)
+					acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+			}
+		}
+		if (qi < p.Sq)
+		{
+			const float inv = l > 0.f ? 1.f / l : 0.f;
+			uint16_t* const orow = (uint16_t*)p.o + b * p.o_b + (long long)qi * p.o_s + h * p.o_h;
+#pragma unroll
+			for (int i = 0; i < FM_D; i += 8)
+			{
+				const uint4 v = make_uint4(pack2(acc[i] * inv, acc[i + 1] * inv, p.is_bf16), pack2(acc[i + 2] * inv, acc[i + 3] * inv, p.is_bf16),
+					pack2(acc[i + 4] * inv, acc[i + 5] * inv, p.is_bf16), pack2(acc[i + 6] * inv, acc[i + 7] * inv, p.is_bf16));
+				*reinterpret_cast<uint4*>(orow + i) = v;
+			}
+			if (p.lse)
+				p.lse[((long long)b * p.H + h) * p.Sq + qi] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1)
+		tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*encode_tiled_f)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_f g_encode = 0;
+
+bool encode_init()
+{
+	static std::once_flag once;
+	std::call_once(once, []() {
+		void* fn = 0;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+			g_encode = (encode_tiled_f)fn;
+	});
+	return g_encode != 0;
+}
+
+// 16-bit [B, S, H, D] tensor with element strides (sb, ss, sh), D contiguous: box = {64 d, 1 head, 128 rows, 1 batch}
+bool make_map_bshd(CUtensorMap* map, const void* ptr, int B, int S, int H, int D, long long sb, long long ss, long long sh, int is_bf16)
+{
+	if ((((uintptr_t)ptr) & 15) || ((sb * 2) & 15) || ((ss * 2) & 15) || ((sh * 2) & 15))
+		return false;
+	// a stride of 0 is not encodable; extents of 1 never advance, any positive multiple of 16 bytes will do
+	if (H == 1 && sh <= 0)
+		sh = D;
+	if (B == 1 && sb <= 0)
+		sb = (long long)S * ss;
+	cuuint64_t dims[4] = { (cuuint64_t)D, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B };
+	cuuint64_t strides[3] = { (cuuint64_t)sh * 2, (cuuint64_t)ss * 2, (cuuint64_t)sb * 2 };
+	cuuint32_t box[4] = { 64, 1, FM_BLOCK, 1 };
+	cuuint32_t estr[4] = { 1, 1, 1, 1 };
+	return g_encode(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int env_int(const char* name, int dflt)
+{
+	const char* e = getenv(name);
+	return e ? atoi(e) : dflt;
+}
+
+} // namespace
+
+// returns 0 on success, 1 when the shape is outside this kernel (D = Dv = 128, 16-byte aligned strides), < 0 on CUDA errors
+int sdpa_forward_f16(cudaStream_t stream, const SdpaGeom& g, int is_bf16, const void* q, const void* k, const void* v, void* o, float* lse)
+{
+	if (g.D != FM_D || g.Dv != FM_D || g.B <= 0 || g.H <= 0 || g.Hk <= 0 || g.H % g.Hk != 0 || g.Sq <= 0 || g.Sk <= 0 || !encode_init())
+		return 1;
+	if ((((uintptr_t)o) & 15) || (g.o_b & 7) || (g.o_s & 7) || (g.o_h & 7))
+		return 1;
+	CUtensorMap tmQ, tmK, tmV;
+	if (!make_map_bshd(&tmQ, q, g.B, g.Sq, g.H, g.D, g.q_b, g.q_s, g.q_h, is_bf16) || !make_map_bshd(&tmK, k, g.B, g.Sk, g.Hk, g.D, g.k_b, g.k_s, g.k_h, is_bf16) ||
+		!make_map_bshd(&tmV, v, g.B, g.Sk, g.Hk, g.Dv, g.v_b, g.v_s, g.v_h, is_bf16))
+		return 1;
+	FmhaParams p;
+	memset(&p, 0, sizeof(p));
+	p.H = g.H, p.Hk = g.Hk, p.Sq = g.Sq, p.Sk = g.Sk;
+	p.causal = g.is_causal, p.is_bf16 = is_bf16;
+	p.scale_log2 = g.scale * 1.4426950408889634f;
+	p.o = o, p.o_b = g.o_b, p.o_s = g.o_s, p.o_h = g.o_h;
+	p.lse = lse;
+	p.idesc_qk = umma_instr_desc(is_bf16 ? 1 : 0, 0, 0, FM_BLOCK, FM_BLOCK);
+	p.idesc_pv = umma_instr_desc(is_bf16 ? 1 : 0, 0, 1, FM_BLOCK, FM_D);
+	// V [128 keys x 128 d] as an MN-major B operand: two 64-wide d atoms 16 KB apart (LBO), 8-key groups 1 KB apart (SBO),
+	// one MMA consumes 16 keys = 2 KB
+	p.v_lbo = (uint32_t)env_int("CCV_NNC_SM100_FMHA_V_LBO", FM_ATOM_BYTES);
+	p.v_sbo = (uint32_t)env_int("CCV_NNC_SM100_FMHA_V_SBO", 1024);
+	p.v_layout = (uint32_t)env_int("CCV_NNC_SM100_FMHA_V_LAYOUT", 2);
+	p.v_kstep = (uint32_t)env_int("CCV_NNC_SM100_FMHA_V_KSTEP", 2048);
+	static bool configured = false;
+	if (!configured)
+	{
+		const cudaError_t e = cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem::TOTAL);
+		if (e != cudaSuccess)
+		{
+			set_last_error("cudaFuncSetAttribute(fmha_fwd_kernel)", e);
+			return -1;
+		}
+		configured = true;
+	}
+	fmha_fwd_kernel<<<dim3((g.Sq + FM_BLOCK - 1) / FM_BLOCK, g.H, g.B), 192, FmhaSmem::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+	count_launch();
+	const cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error("fmha_fwd_kernel launch", e);
+		return -1;
+	}
+	return 0;
+}
+
+} // namespace sm100

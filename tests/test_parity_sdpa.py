@@ -55,3 +55,81 @@ def test_sdpa_with_additive_mask(gpu, ref):
     st_g, (o_g, _) = gpu_exec(nnc, fwd, None, 0, [q, k, v, mask], [np.zeros_like(q), None])
     assert st_r == 0 and st_g == 0
     assert_close(o_g, o_r, 2e-3, "masked attention")
+
+
+# ---- 16-bit flash attention (ccv_b200/csrc/sm100_fmha.cu) --------------------------------------------------------------
+def _to_bf16(a):
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)  # round to nearest even
+
+
+def _from_bf16(u):
+    return (u.astype(np.uint32) << 16).view(np.float32)
+
+
+def _attention_f64(q, k, v, scale, causal):
+    """Plain float64 restatement of ..._cpu_ref.c:88-183 on [B, S, H, D] arrays (GQA by head ratio, causal aligned to the
+    bottom-right corner :147); returns (O, LSE [B, H, Sq])."""
+    B, Sq, H, D = q.shape
+    Sk, Hk = k.shape[1], k.shape[2]
+    o = np.zeros((B, Sq, H, v.shape[3]))
+    lse = np.zeros((B, H, Sq))
+    for b in range(B):
+        for h in range(H):
+            hk = h // (H // Hk)
+            s = scale * (q[b, :, h].astype(np.float64) @ k[b, :, hk].astype(np.float64).T)
+            if causal:
+                i, j = np.arange(Sq)[:, None], np.arange(Sk)[None, :]
+                s = np.where(j <= i + Sk - Sq, s, -np.inf)
+            m = s.max(axis=1, keepdims=True)
+            e = np.exp(s - m)
+            den = e.sum(axis=1, keepdims=True)
+            o[b, :, h] = (e / den) @ v[b, :, hk].astype(np.float64)
+            lse[b, h] = (m + np.log(den))[:, 0]
+    return o, lse
+
+
+FMHA_TRIALS = [
+    # B, Sq, Sk, Hq, Hk, causal
+    (2, 256, 256, 4, 4, 0), (2, 256, 256, 4, 4, 1), (1, 128, 384, 8, 2, 1), (1, 200, 333, 2, 2, 0), (1, 333, 333, 2, 1, 1), (1, 1024, 1024, 2, 2, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,causal", FMHA_TRIALS)
+def test_flash_attention_16bit_forward(gpu, ref, B, Sq, Sk, Hq, Hk, causal, dtype):
+    """bf16 / fp16 SDPA forward, D = 128 (BASELINE configs[4] shape family).  There is no 16-bit CPU_REF kernel (SURVEY 8c:
+    "parity defined as fp32-oracle-on-rounded-inputs"): the inputs are rounded to the 16-bit type, CPU_REF runs on those
+    values in fp32, and the GPU result is held to 1e-2 of max|ref| (BASELINE tolerance for bf16); LSE to 1e-3."""
+    nnc = gpu
+    D = 128
+    scale = 1.0 / np.sqrt(D)
+    q, k, v = seeded((B, Sq, Hq, D), 1, -1, 1), seeded((B, Sk, Hk, D), 2, -1, 1), seeded((B, Sk, Hk, D), 3, -1, 1)
+    if dtype == "bf16":
+        bits = [_to_bf16(x) for x in (q, k, v)]
+        q, k, v = (_from_bf16(x) for x in bits)
+        ccv_dt = abi.CCV_16BF
+    else:
+        bits = [x.astype(np.float16).view(np.uint16) for x in (q, k, v)]
+        q, k, v = (x.view(np.float16).astype(np.float32) for x in bits)
+        ccv_dt = abi.CCV_16F
+    fwd = _cmd(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD, scale, causal)
+    o64, lse64 = _attention_f64(q, k, v, scale, causal)
+    if Sq * Sk <= 256 * 256:  # CPU_REF itself on the rounded values (small cases; it agrees with the float64 restatement)
+        st_r, (o_r, _) = ref_exec(ref, fwd, None, 0, [q, k, v], [np.zeros((B, Sq, Hq, D), np.float32), None])
+        assert st_r == 0
+        assert_close(o_r, o64, 1e-4, "CPU_REF vs float64 restatement")
+    stream = nnc.Stream(0)
+    tq, tk, tv = (nnc.gpu_tensor(list(x.shape), datatype=ccv_dt) for x in (q, k, v))
+    to = nnc.gpu_tensor([B, Sq, Hq, D], datatype=ccv_dt)
+    tl = nnc.gpu_tensor([B, Hq, Sq])
+    for t, x in zip((tq, tk, tv), bits):
+        t.upload(x.view(np.float16) if ccv_dt == abi.CCV_16F else x)
+    assert nnc.cmd_exec(fwd, None, 0, [tq, tk, tv], [to, tl], stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+    stream.wait()
+    got = to.download()
+    got = _from_bf16(got) if ccv_dt == abi.CCV_16BF else got.astype(np.float32)
+    assert_close(got, o64, 1e-2, "flash attention output")
+    assert_close(tl.download(), lse64, 1e-3, "log-sum-exp")
+    for t in (tq, tk, tv, to, tl, stream):
+        t.free()
