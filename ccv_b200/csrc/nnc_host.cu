@@ -684,23 +684,34 @@ int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
 								return false;
 				return true;
 			};
-			while (j < n && is_gpu_sm100(nodes[j]) && nodes[j].cmd.cmd == CCV_NNC_SGD_FORWARD && nodes[j].inputs.size() == 3 && nodes[j].outputs.size() == 2 &&
-				memcmp(&nodes[j].cmd.info.sgd, &a.cmd.info.sgd, sizeof(a.cmd.info.sgd)) == 0 && nodes[j].flags == a.flags && independent(nodes[j], i, j))
+			// the maximal run of mutually independent SGD nodes: inside it the order is free, so nodes are grouped by their
+			// hyper-parameters (weights with decay, biases / norm parameters without) even when the groups interleave
+			while (j < n && is_gpu_sm100(nodes[j]) && nodes[j].cmd.cmd == CCV_NNC_SGD_FORWARD && nodes[j].inputs.size() == 3 && nodes[j].outputs.size() == 2 && independent(nodes[j], i, j))
 				j++;
-			if (j - i >= 2)
+			std::vector<char> done(j - i, 0);
+			for (size_t k = i; k < j; k++)
 			{
-				ccv_nnc_sm100_graph_node_t f = a;
-				for (size_t k = i + 1; k < j; k++)
+				if (done[k - i])
+					continue;
+				ccv_nnc_sm100_graph_node_t f = nodes[k];
+				int members = 1;
+				for (size_t q = k + 1; q < j; q++)
+					if (!done[q - i] && memcmp(&nodes[q].cmd.info.sgd, &f.cmd.info.sgd, sizeof(f.cmd.info.sgd)) == 0 && nodes[q].flags == f.flags && nodes[q].cmd.algorithm == f.cmd.algorithm)
+					{
+						f.inputs.insert(f.inputs.end(), nodes[q].inputs.begin(), nodes[q].inputs.end());
+						f.outputs.insert(f.outputs.end(), nodes[q].outputs.begin(), nodes[q].outputs.end());
+						done[q - i] = 1;
+						members++;
+					}
+				if (members > 1)
 				{
-					f.inputs.insert(f.inputs.end(), nodes[k].inputs.begin(), nodes[k].inputs.end());
-					f.outputs.insert(f.outputs.end(), nodes[k].outputs.begin(), nodes[k].outputs.end());
+					f.fused = ccv_nnc_sm100_fused_sgd_multi;
+					fused += members - 1;
 				}
-				f.fused = ccv_nnc_sm100_fused_sgd_multi;
 				out.push_back(f);
-				fused += (int)(j - i - 1);
-				i = j - 1;
-				continue;
 			}
+			i = j - 1;
+			continue;
 		}
 		if (i + 1 < n && is_gpu_sm100(a) && is_gpu_sm100(nodes[i + 1]))
 		{

@@ -267,6 +267,66 @@ __global__ void bn_mask_coef_kernel(const int C, const float* __restrict__ scale
 	coef[c] = a, coef[C + c] = b;
 }
 
+// The same finalisation fed directly from the per-block partial rows of bn_reduce_kernel (one launch instead of partials-reduce +
+// finalize): 32 channels x 32 row-lanes per block; row-lane 0 of each channel finishes the statistics.
+// MODE 0 forward, MODE 1 backward; WITH_A (backward without a fused ReLU): also writes a = scale * inv_std for the apply pass.
+template <int MODE, int WITH_A>
+__global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float* __restrict__ part, const int gy, const float* __restrict__ x, const int C, const double count, const float epsilon, const float momentum,
+	const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std,
+	float* __restrict__ dscale, float* __restrict__ dbias, float* __restrict__ coef)
+{
+	__shared__ double sh[2][32][33];
+	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
+	const int c = blockIdx.x * 32 + cx;
+	double a1 = 0, a2 = 0;
+	if (c < C)
+		for (int y = yl; y < gy; y += 32)
+		{
+			const float* const row = part + (size_t)y * 2 * C;
+			a1 += (double)row[c], a2 += (double)row[C + c];
+		}
+	sh[0][yl][cx] = a1, sh[1][yl][cx] = a2;
+	__syncthreads();
+	if (yl != 0 || c >= C)
+		return;
+	double s1 = 0, s2 = 0;
+#pragma unroll
+	for (int j = 0; j < 32; j++)
+		s1 += sh[0][j][cx], s2 += sh[1][j][cx];
+	if (MODE == 0)
+	{
+		const double k = (double)x[c];
+		const double mean = k + s1 / count;
+		double var = (s2 - s1 * s1 / count) / count;
+		if (var < 0)
+			var = 0;
+		const float meanf = (float)mean, varf = (float)var;
+		const float inv_std = 1.f / sqrtf(varf + epsilon);
+		saved_mean[c] = meanf;
+		saved_inv_std[c] = inv_std;
+		running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * meanf;
+		running_var[c] = momentum * running_var[c] + (1.f - momentum) * varf;
+		float a, b;
+		bn_affine(scale[c], bias[c], meanf, inv_std, a, b);
+		coef[c] = a, coef[C + c] = b;
+	} else {
+		const float cnt = (float)count;
+		const float inv_std = saved_inv_std[c];
+		const float db = (float)s1;
+		const float ds = (float)s2 * inv_std;
+		if (dbias)
+			dbias[c] = db;
+		if (dscale)
+			dscale[c] = ds;
+		const float a = scale[c] * inv_std;
+		const float pp = -a * inv_std * ds / cnt;
+		if (WITH_A)
+			coef[c] = a;
+		coef[2 * C + c] = pp;
+		coef[3 * C + c] = -a * db / cnt - pp * saved_mean[c];
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ elementwise passes
 // forward: y = x * a + b (optionally relu'd).  backward: dx = a * g' + p * x + q with the optional relu mask on g.
 template <int BWD, int RELU>
@@ -347,19 +407,20 @@ static void reduce_config(size_t rows, int CV, int& cpb, dim3& grid)
 }
 
 template <int MODE, int MASK>
-static int run_reduce(cudaStream_t s, const float* x, const float* g, const float* mean, const float* coef, size_t outer, int C, size_t inner, double* ws, float* part)
+static int run_reduce(cudaStream_t s, const float* x, const float* g, const float* mean, const float* coef, size_t outer, int C, size_t inner, double* ws, float* part, int* part_rows)
 {
+	// NHWC vector path: leaves *part_rows > 0 rows of per-block partial sums in `part` (finished by bn_finalize_partials_kernel);
+	// generic path: one block per channel writes the sums to ws directly (*part_rows = 0)
 	if (inner == 1 && C % 4 == 0 && aligned16(x) && (MODE == 0 || aligned16(g)))
 	{
 		int cpb;
 		dim3 grid;
 		reduce_config(outer, C / 4, cpb, grid);
 		bn_reduce_kernel<MODE, MASK><<<grid, 256, 0, s>>>(x, g, mean, coef, outer, C, part, cpb);
-		if (check("bn_reduce"))
-			return -1;
-		bn_partials_reduce_kernel<<<(2 * C + 31) / 32, 1024, 0, s>>>(part, (int)grid.y, 2 * C, ws);
-		return check("bn_partials_reduce");
+		*part_rows = (int)grid.y;
+		return check("bn_reduce");
 	}
+	*part_rows = 0;
 	bn_reduce_generic_kernel<MODE, MASK><<<C, 512, 0, s>>>(x, g, mean, coef, outer, C, inner, ws);
 	return check("bn_reduce");
 }
@@ -381,9 +442,13 @@ int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scal
 		return 0;
 	double* ws = ws_sums(workspace);
 	float* coef = ws_coef(workspace, C);
-	if (run_reduce<0, 0>(s, x, 0, 0, 0, outer, C, inner, ws, ws_part(workspace, C)))
+	int part_rows = 0;
+	if (run_reduce<0, 0>(s, x, 0, 0, 0, outer, C, inner, ws, ws_part(workspace, C), &part_rows))
 		return -1;
-	bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, inner, ws, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, coef);
+	if (part_rows > 0)
+		bn_finalize_partials_kernel<0, 0><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, x, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, 0, 0, coef);
+	else
+		bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, inner, ws, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, coef);
 	if (check("bn_fwd_finalize"))
 		return -1;
 	return fuse_relu ? run_apply<0, 1>(s, x, 0, y, coef, outer, C, inner) : run_apply<0, 0>(s, x, 0, y, coef, outer, C, inner);
@@ -408,20 +473,28 @@ int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scal
 	double* ws = ws_sums(workspace);
 	float* coef = ws_coef(workspace, C);
 	const int mask = bias != 0;
+	const bool vec = inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(g);
 	if (mask)
 	{
 		bn_mask_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, scale, bias, saved_mean, saved_inv_std, coef);
 		if (check("bn_mask_coef"))
 			return -1;
-	} else {
-		// a is still needed by the apply pass
+	} else if (!vec) {
+		// a is still needed by the apply pass (the vector path gets it from bn_finalize_partials_kernel<1, 1>)
 		bn_mask_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, scale, scale, saved_mean, saved_inv_std, coef);
 		if (check("bn_coef"))
 			return -1;
 	}
-	if (mask ? run_reduce<1, 1>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C)) : run_reduce<1, 0>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C)))
+	int part_rows = 0;
+	if (mask ? run_reduce<1, 1>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C), &part_rows) : run_reduce<1, 0>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C), &part_rows))
 		return -1;
-	bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(ws, C, (float)((double)outer * (double)inner), scale, saved_mean, saved_inv_std, dscale, dbias, coef);
+	const double count = (double)outer * (double)inner;
+	if (part_rows > 0 && mask)
+		bn_finalize_partials_kernel<1, 0><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, 0, C, count, 0.f, 0.f, scale, 0, 0, 0, const_cast<float*>(saved_mean), const_cast<float*>(saved_inv_std), dscale, dbias, coef);
+	else if (part_rows > 0)
+		bn_finalize_partials_kernel<1, 1><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, 0, C, count, 0.f, 0.f, scale, 0, 0, 0, const_cast<float*>(saved_mean), const_cast<float*>(saved_inv_std), dscale, dbias, coef);
+	else
+		bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(ws, C, (float)count, scale, saved_mean, saved_inv_std, dscale, dbias, coef);
 	if (check("bn_bwd_finalize"))
 		return -1;
 	if (!dx)

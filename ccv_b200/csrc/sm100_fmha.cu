@@ -4,15 +4,18 @@
 // GQA through H / Hk :99,113), the same restrictions as the reference's flash-attention backend
 // (gpu/ccv_nnc_scaled_dot_product_attention_flash_attn.cu:13-205: 16-bit only, no additive mask, no unify-head weights).
 //
-// One CTA = 128 query rows of one (batch, head); 192 threads:
+// One CTA = 128 query rows of one (batch, head); 320 threads:
 //   warp 0    TMA producer: Q once, then K_j / V_j blocks of 128 keys through two-stage rings (4-D tensor maps over the
 //             caller's [B, S, H, D] strides, 128-byte swizzle)
 //   warp 1    tcgen05.mma issuer (kind::f16, fp32 accumulate in TMEM):
 //               S_j = Q K_j^T  -> TMEM S[j & 1]   (issued one block ahead, so it overlaps the softmax of block j - 1)
 //               O_j = P_j V_j  -> TMEM O          (P_j from shared memory, V_j as an MN-major operand)
-//   warps 2-5 softmax: one query row per thread.  Row max from a first pass over S_j in TMEM, then exp2 / row sum / bf16
-//             P_j written into the 128-byte-swizzled K-major smem tile the second MMA reads; the running output lives in
-//             registers: acc = acc * alpha_j + O_j (O_j read back from TMEM), normalised by the row sum at the end.
+//   warps 2-9 softmax: two threads per query row (warps w and w + 4 share a TMEM lane quarter; each owns 64 of the 128
+//             key columns of S_j and 64 of the 128 output columns).  The two halves exchange their row max through shared
+//             memory (one named barrier per lane quarter), then exp2 / partial row sum / bf16 P_j written into the
+//             128-byte-swizzled K-major smem tile the second MMA reads; the running output lives in registers:
+//             acc = acc * alpha_j + O_j (O_j read back from TMEM), normalised by the row sum at the end.
+//             Two warps per scheduler instead of one hide the tcgen05.ld / MUFU latency of the other.
 // TMEM: S0, S1, O = 3 x 128 columns.  smem: Q 32 KB + K 2 x 32 KB + V 2 x 32 KB + P 32 KB = 192 KB.
 #include "sm100_contract.h"
 #include "sm100_ptx.cuh"
@@ -50,7 +53,8 @@ struct FmhaSmem {
 	static constexpr int V_OFF = K_OFF + FM_KV_STAGES * FM_TILE_BYTES;
 	static constexpr int P_OFF = V_OFF + FM_KV_STAGES * FM_TILE_BYTES;
 	static constexpr int BAR_OFF = P_OFF + FM_TILE_BYTES;
-	static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+	static constexpr int XCHG_OFF = BAR_OFF + 256; // float [6][128]: row maxima per (S buffer, half), final partial row sums per half
+	static constexpr int TOTAL = XCHG_OFF + 6 * FM_BLOCK * 4 + 1024;
 };
 
 __device__ __forceinline__ uint32_t pack2(const float a, const float b, const int is_bf16)
@@ -64,7 +68,8 @@ __device__ __forceinline__ uint32_t pack2(const float a, const float b, const in
 	return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(192, 1) fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const FmhaParams p)
+template <int CL>
+__global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const FmhaParams p)
 {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -75,8 +80,8 @@ __global__ void __launch_bounds__(192, 1) fmha_fwd_kernel(const __grid_constant_
 	uint64_t* v_full = bars + 5;  // [2]
 	uint64_t* v_empty = bars + 7; // [2]
 	uint64_t* s_full = bars + 9;  // [2] MMA -> softmax
-	uint64_t* s_empty = bars + 11; // [2] softmax -> MMA (4 arrivals)
-	uint64_t* p_full = bars + 13; // softmax -> MMA (4 arrivals)
+	uint64_t* s_empty = bars + 11; // [2] softmax -> MMA (8 arrivals)
+	uint64_t* p_full = bars + 13; // softmax -> MMA (8 arrivals)
 	uint64_t* o_full = bars + 14; // MMA -> softmax
 	uint32_t* tmem_slot = (uint32_t*)(bars + 15);
 
@@ -90,6 +95,20 @@ __global__ void __launch_bounds__(192, 1) fmha_fwd_kernel(const __grid_constant_
 	if (p.causal)
 		kv_end = min(p.Sk, max(q0 + FM_BLOCK + shift, 0));
 	const int n_blk = (kv_end + FM_BLOCK - 1) / FM_BLOCK;
+	// a cluster of CL consecutive query tiles shares every K / V block: each CTA fetches 1 / CL of it and multicasts.  All
+	// CTAs must walk the same number of blocks (the cluster's last tile sees the most keys under a causal mask).
+	int n_max = n_blk;
+	uint32_t cta_rank = 0;
+	if (CL > 1)
+	{
+		cta_rank = cluster_ctarank();
+		if (p.causal)
+		{
+			const int q_last = ((int)blockIdx.x / CL * CL + CL - 1) * FM_BLOCK;
+			n_max = (min(p.Sk, max(q_last + FM_BLOCK + shift, 0)) + FM_BLOCK - 1) / FM_BLOCK;
+		}
+	}
+	const uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
 
 	if (warp == 0 && lane == 0)
 	{
@@ -99,11 +118,11 @@ __global__ void __launch_bounds__(192, 1) fmha_fwd_kernel(const __grid_constant_
 		mbar_init(q_full, 1);
 		for (int s = 0; s < 2; s++)
 		{
-			mbar_init(&k_full[s], 1), mbar_init(&k_empty[s], 1);
-			mbar_init(&v_full[s], 1), mbar_init(&v_empty[s], 1);
-			mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], 4);
+			mbar_init(&k_full[s], 1), mbar_init(&k_empty[s], CL);
+			mbar_init(&v_full[s], 1), mbar_init(&v_empty[s], CL);
+			mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], 8);
 		}
-		mbar_init(p_full, 4);
+		mbar_init(p_full, 8);
 		mbar_init(o_full, 1);
 		fence_mbar_init();
 	}
@@ -114,177 +133,197 @@ __global__ void __launch_bounds__(192, 1) fmha_fwd_kernel(const __grid_constant_
 	}
 	tc_fence_before();
 	__syncthreads();
+	if (CL > 1)
+		cluster_sync_all(); // every CTA's barriers exist before any peer multicasts into them
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot;
 	const uint32_t tmem_o = tmem_base + 256;
 
 	if (warp == 0)
 	{
-		if (lane == 0 && n_blk > 0)
+		if (lane == 0 && n_max > 0)
 		{
-			mbar_expect_tx(q_full, FM_TILE_BYTES);
-			tma_load_4d(smem + FmhaSmem::Q_OFF, &tmQ, q_full, 0, h, q0, b);
-			tma_load_4d(smem + FmhaSmem::Q_OFF + FM_ATOM_BYTES, &tmQ, q_full, 64, h, q0, b);
-			for (int j = 0; j < n_blk; j++)
+			if (n_blk > 0)
+			{
+				mbar_expect_tx(q_full, FM_TILE_BYTES);
+				tma_load_4d(smem + FmhaSmem::Q_OFF, &tmQ, q_full, 0, h, q0, b);
+				tma_load_4d(smem + FmhaSmem::Q_OFF + FM_ATOM_BYTES, &tmQ, q_full, 64, h, q0, b);
+			}
+			for (int j = 0; j < n_max; j++)
 			{
 				const int s = j & 1;
 				const uint32_t ph = (uint32_t)(j >> 1) & 1;
-				mbar_wait(&k_empty[s], ph ^ 1);
-				mbar_expect_tx(&k_full[s], FM_TILE_BYTES);
 				uint8_t* const sk = smem + FmhaSmem::K_OFF + s * FM_TILE_BYTES;
-				tma_load_4d(sk, &tmK, &k_full[s], 0, hk, j * FM_BLOCK, b);
-				tma_load_4d(sk + FM_ATOM_BYTES, &tmK, &k_full[s], 64, hk, j * FM_BLOCK, b);
+				uint8_t* const sv = smem + FmhaSmem::V_OFF + s * FM_TILE_BYTES;
+				mbar_wait(&k_empty[s], ph ^ 1); // all CL consumers of this stage are done with it
+				mbar_expect_tx(&k_full[s], FM_TILE_BYTES);
+				if (CL == 1)
+				{
+					tma_load_4d(sk, &tmK, &k_full[s], 0, hk, j * FM_BLOCK, b);
+					tma_load_4d(sk + FM_ATOM_BYTES, &tmK, &k_full[s], 64, hk, j * FM_BLOCK, b);
+				} else // CL == 2: this CTA fetches the 64-wide d atom `rank` for both CTAs
+					tma_load_4d_multicast(sk + cta_rank * FM_ATOM_BYTES, &tmK, &k_full[s], 64 * (int)cta_rank, hk, j * FM_BLOCK, b, cl_mask);
 				mbar_wait(&v_empty[s], ph ^ 1);
 				mbar_expect_tx(&v_full[s], FM_TILE_BYTES);
-				uint8_t* const sv = smem + FmhaSmem::V_OFF + s * FM_TILE_BYTES;
-				tma_load_4d(sv, &tmV, &v_full[s], 0, hk, j * FM_BLOCK, b);
-				tma_load_4d(sv + FM_ATOM_BYTES, &tmV, &v_full[s], 64, hk, j * FM_BLOCK, b);
+				if (CL == 1)
+				{
+					tma_load_4d(sv, &tmV, &v_full[s], 0, hk, j * FM_BLOCK, b);
+					tma_load_4d(sv + FM_ATOM_BYTES, &tmV, &v_full[s], 64, hk, j * FM_BLOCK, b);
+				} else
+					tma_load_4d_multicast(sv + cta_rank * FM_ATOM_BYTES, &tmV, &v_full[s], 64 * (int)cta_rank, hk, j * FM_BLOCK, b, cl_mask);
 			}
 		}
 	} else if (warp == 1) {
-		if (n_blk > 0)
+		if (n_max > 0)
 		{
 			const uint32_t q_addr = smem_u32(smem + FmhaSmem::Q_OFF);
 			const uint32_t p_addr = smem_u32(smem + FmhaSmem::P_OFF);
-			// S_j = Q K_j^T into S[j & 1]
+			auto release = [&](uint64_t* bar) {
+				if (CL == 1)
+					umma_commit(bar);
+				else
+					umma_commit_multicast(bar, cl_mask); // the stage is free once every CTA of the cluster has read it
+			};
+			// S_j = Q K_j^T into S[j & 1]; blocks past this tile's causal horizon are only drained (the cluster shares the ring)
 			auto issue_qk = [&](const int j) {
 				const int s = j & 1;
 				const uint32_t ph = (uint32_t)(j >> 1) & 1;
-				mbar_wait(&s_empty[s], ph ^ 1); // softmax has finished reading what block j - 2 left in this buffer
+				if (j < n_blk)
+					mbar_wait(&s_empty[s], ph ^ 1); // softmax has finished reading what block j - 2 left in this buffer
 				mbar_wait(&k_full[s], ph);
 				tc_fence_after();
 				if (lane == 0)
 				{
-					const uint32_t k_addr = smem_u32(smem + FmhaSmem::K_OFF + s * FM_TILE_BYTES);
-#pragma unroll
-					for (int k = 0; k < FM_D / 16; k++)
+					if (j < n_blk)
 					{
-						const uint32_t off = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
-						umma_f16(tmem_base + s * 128, umma_smem_desc(q_addr + off, 16, 1024, 2), umma_smem_desc(k_addr + off, 16, 1024, 2), p.idesc_qk, k > 0 ? 1u : 0u);
+						const uint32_t k_addr = smem_u32(smem + FmhaSmem::K_OFF + s * FM_TILE_BYTES);
+#pragma unroll
+						for (int k = 0; k < FM_D / 16; k++)
+						{
+							const uint32_t off = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
+							umma_f16(tmem_base + s * 128, umma_smem_desc(q_addr + off, 16, 1024, 2), umma_smem_desc(k_addr + off, 16, 1024, 2), p.idesc_qk, k > 0 ? 1u : 0u);
+						}
 					}
-					umma_commit(&k_empty[s]);
-					umma_commit(&s_full[s]);
+					release(&k_empty[s]);
+					if (j < n_blk)
+						umma_commit(&s_full[s]);
 				}
 				__syncwarp();
 			};
-			mbar_wait(q_full, 0);
+			if (n_blk > 0)
+				mbar_wait(q_full, 0);
 			issue_qk(0);
-			for (int j = 0; j < n_blk; j++)
+			for (int j = 0; j < n_max; j++)
 			{
-				if (j + 1 < n_blk)
+				if (j + 1 < n_max)
 					issue_qk(j + 1);
 				const int s = j & 1;
 				const uint32_t ph = (uint32_t)(j >> 1) & 1;
-				mbar_wait(p_full, (uint32_t)j & 1);
+				if (j < n_blk)
+					mbar_wait(p_full, (uint32_t)j & 1);
 				mbar_wait(&v_full[s], ph);
 				tc_fence_after();
 				if (lane == 0)
 				{
-					const uint32_t v_addr = smem_u32(smem + FmhaSmem::V_OFF + s * FM_TILE_BYTES);
-#pragma unroll
-					for (int k = 0; k < FM_BLOCK / 16; k++)
+					if (j < n_blk)
 					{
-						const uint32_t poff = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
-						umma_f16(tmem_o, umma_smem_desc(p_addr + poff, 16, 1024, 2), umma_smem_desc(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo, p.v_layout), p.idesc_pv, k > 0 ? 1u : 0u);
+						const uint32_t v_addr = smem_u32(smem + FmhaSmem::V_OFF + s * FM_TILE_BYTES);
+#pragma unroll
+						for (int k = 0; k < FM_BLOCK / 16; k++)
+						{
+							const uint32_t poff = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
+							umma_f16(tmem_o, umma_smem_desc(p_addr + poff, 16, 1024, 2), umma_smem_desc(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo, p.v_layout), p.idesc_pv, k > 0 ? 1u : 0u);
+						}
 					}
-					umma_commit(&v_empty[s]);
-					umma_commit(o_full);
+					release(&v_empty[s]);
+					if (j < n_blk)
+						umma_commit(o_full);
 				}
 				__syncwarp();
 			}
 		}
 	} else {
-		// ------------------------------------------------------------------ softmax / output (warps 2..5)
-		const int quarter = warp & 3;
+		// ------------------------------------------------------------------ softmax / output (warps 2..9)
+		const int quarter = warp & 3;       // TMEM lanes [32 * quarter, +32) are the ones this warp may touch
+		const int half = (warp - 2) >> 2;   // key columns / output columns [64 * half, +64)
 		const int row = quarter * 32 + lane;
 		const int qi = q0 + row;
 		const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
 		const int kv_limit = p.causal ? min(p.Sk, qi + shift + 1) : p.Sk; // keys [0, kv_limit) are visible to this row
-		float acc[FM_D];
+		float* const mx_x = (float*)(smem + FmhaSmem::XCHG_OFF); // [6][128 rows]
+		float acc[64];
 #pragma unroll
-		for (int i = 0; i < FM_D; i++)
+		for (int i = 0; i < 64; i++)
 			acc[i] = 0.f;
 		float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-		uint8_t* const p_row = smem + FmhaSmem::P_OFF + row * 128;
+		uint8_t* const p_row = smem + FmhaSmem::P_OFF + half * FM_ATOM_BYTES + row * 128;
 		for (int j = 0; j < n_blk; j++)
 		{
 			const int s = j & 1;
 			mbar_wait(&s_full[s], (uint32_t)(j >> 1) & 1);
 			tc_fence_after();
-			const uint32_t ts = tmem_base + s * 128 + lane_sel;
-			const int kv0 = j * FM_BLOCK;
-			const bool edge = kv0 + FM_BLOCK > kv_limit; // some keys of this block are masked for this row
-			// pass 1: row max
+			const uint32_t ts = tmem_base + s * 128 + half * 64 + lane_sel;
+			const int kv0 = j * FM_BLOCK + half * 64;
+			const bool edge = kv0 + 64 > kv_limit; // some keys of this half block are masked for this row
+			uint32_t sr[64];
+			tmem_ld_32x32(ts, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+			tmem_ld_32x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+			tmem_ld_wait();
 			float mx = -INFINITY;
-#pragma unroll 1
-			for (int c = 0; c < 4; c++)
+			if (edge)
 			{
-				uint32_t r[32];
-				tmem_ld_32x32(ts + c * 32, r);
-				tmem_ld_wait();
-				if (edge)
-				{
 #pragma unroll
-					for (int i = 0; i < 32; i++)
-						if (kv0 + c * 32 + i < kv_limit)
-							mx = fmaxf(mx, __uint_as_float(r[i]));
-				} else {
+				for (int i = 0; i < 64; i++)
+					if (kv0 + i < kv_limit)
+						mx = fmaxf(mx, __uint_as_float(sr[i]));
+			} else {
 #pragma unroll
-					for (int i = 0; i < 32; i++)
-						mx = fmaxf(mx, __uint_as_float(r[i]));
-				}
+				for (int i = 0; i < 64; i++)
+					mx = fmaxf(mx, __uint_as_float(sr[i]));
 			}
+			// the other half of this row lives in warp (warp +- 4): exchange the maxima
+			mx_x[(s * 2 + half) * FM_BLOCK + row] = mx;
+			asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+			mx = fmaxf(mx, mx_x[(s * 2 + (half ^ 1)) * FM_BLOCK + row]);
 			const float m_new = fmaxf(m, mx * p.scale_log2);
 			const float m_use = m_new == -INFINITY ? 0.f : m_new; // a fully masked row keeps p = 0 without NaN
 			const float alpha = exp2f(m - m_use);                  // m = -inf -> 0
+			// p = exp2(s * scale_log2 - m) and the partial row sum first: the MUFU phase (16 ex2 / clk / SM = the MMA time of a
+			// whole block) runs while the tensor core is still busy with O_{j-1} = P_{j-1} V_{j-1}
+			float sum = 0.f;
+			uint32_t pk[32];
+#pragma unroll
+			for (int i = 0; i < 64; i += 2)
+			{
+				float e0 = ex2_approx(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_use));
+				float e1 = ex2_approx(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_use));
+				if (edge)
+				{
+					if (kv0 + i >= kv_limit)
+						e0 = 0.f;
+					if (kv0 + i + 1 >= kv_limit)
+						e1 = 0.f;
+				}
+				sum += e0 + e1;
+				pk[i >> 1] = pack2(e0, e1, p.is_bf16);
+			}
 			// O_{j-1} is complete once o_full flips; it also means P / V of block j - 1 are no longer being read
 			if (j > 0)
 			{
 				mbar_wait(o_full, (uint32_t)(j - 1) & 1);
 				tc_fence_after();
-#pragma unroll
-				for (int c = 0; c < 4; c++)
-				{
-					uint32_t r[32];
-					tmem_ld_32x32(tmem_o + lane_sel + c * 32, r);
-					tmem_ld_wait();
-#pragma unroll
-					for (int i = 0; i < 32; i++)
-						acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
-				}
-			}
-			// pass 2: p = exp2(s * scale_log2 - m), row sum, P tile in smem (K-major, 128-byte swizzle)
-			float sum = 0.f;
-#pragma unroll 1
-			for (int c = 0; c < 4; c++)
-			{
-				uint32_t r[32];
-				tmem_ld_32x32(ts + c * 32, r);
+				uint32_t r[64];
+				tmem_ld_32x32(tmem_o + lane_sel + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+				tmem_ld_32x32(tmem_o + lane_sel + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
 				tmem_ld_wait();
-				uint32_t pk[16];
 #pragma unroll
-				for (int i = 0; i < 32; i += 2)
-				{
-					float e0 = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_use));
-					float e1 = exp2f(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_use));
-					if (edge)
-					{
-						if (kv0 + c * 32 + i >= kv_limit)
-							e0 = 0.f;
-						if (kv0 + c * 32 + i + 1 >= kv_limit)
-							e1 = 0.f;
-					}
-					sum += e0 + e1;
-					pk[i >> 1] = pack2(e0, e1, p.is_bf16);
-				}
-				uint8_t* const atom = p_row + (c >> 1) * FM_ATOM_BYTES;
-#pragma unroll
-				for (int q4 = 0; q4 < 4; q4++)
-				{
-					const int chunk = (c & 1) * 4 + q4;
-					*reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-				}
+				for (int i = 0; i < 64; i++)
+					acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(r[i]));
 			}
+			// P tile in smem (K-major, 128-byte swizzle; this half = one 64-key atom)
+#pragma unroll
+			for (int c = 0; c < 8; c++)
+				*reinterpret_cast<uint4*>(p_row + ((c ^ (row & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
 			l = fmaf(l, alpha, sum);
 			m = m_new;
 			alpha_prev = alpha;
@@ -302,34 +341,37 @@ __global__ void __launch_bounds__(192, 1) fmha_fwd_kernel(const __grid_constant_
 		{
 			mbar_wait(o_full, (uint32_t)(n_blk - 1) & 1);
 			tc_fence_after();
+			uint32_t r[64];
+			tmem_ld_32x32(tmem_o + lane_sel + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+			tmem_ld_32x32(tmem_o + lane_sel + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+			tmem_ld_wait();
 #pragma unroll
-			for (int c = 0; c < 4; c++)
-			{
-				uint32_t r[32];
-				tmem_ld_32x32(tmem_o + lane_sel + c * 32, r);
-				tmem_ld_wait();
-#pragma unroll
-				for (int i = 0; i < 32; i++)
-					acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
-			}
+			for (int i = 0; i < 64; i++)
+				acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(r[i]));
 		}
+		// the row sum is the sum of the two halves' partial sums (same running max on both sides)
+		mx_x[(4 + half) * FM_BLOCK + row] = l;
+		asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+		l += mx_x[(4 + (half ^ 1)) * FM_BLOCK + row];
 		if (qi < p.Sq)
 		{
 			const float inv = l > 0.f ? 1.f / l : 0.f;
-			uint16_t* const orow = (uint16_t*)p.o + b * p.o_b + (long long)qi * p.o_s + h * p.o_h;
+			uint16_t* const orow = (uint16_t*)p.o + b * p.o_b + (long long)qi * p.o_s + h * p.o_h + half * 64;
 #pragma unroll
-			for (int i = 0; i < FM_D; i += 8)
+			for (int i = 0; i < 64; i += 8)
 			{
 				const uint4 v = make_uint4(pack2(acc[i] * inv, acc[i + 1] * inv, p.is_bf16), pack2(acc[i + 2] * inv, acc[i + 3] * inv, p.is_bf16),
 					pack2(acc[i + 4] * inv, acc[i + 5] * inv, p.is_bf16), pack2(acc[i + 6] * inv, acc[i + 7] * inv, p.is_bf16));
 				*reinterpret_cast<uint4*>(orow + i) = v;
 			}
-			if (p.lse)
+			if (p.lse && half == 0)
 				p.lse[((long long)b * p.H + h) * p.Sq + qi] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
 		}
 	}
 	tc_fence_before();
 	__syncthreads();
+	if (CL > 1)
+		cluster_sync_all(); // no CTA leaves while a peer may still arrive on its barriers
 	if (warp == 1)
 		tmem_dealloc(tmem_base, 512);
 }
@@ -403,7 +445,9 @@ int sdpa_forward_f16(cudaStream_t stream, const SdpaGeom& g, int is_bf16, const 
 	static bool configured = false;
 	if (!configured)
 	{
-		const cudaError_t e = cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem::TOTAL);
+		cudaError_t e = cudaFuncSetAttribute(fmha_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem::TOTAL);
+		if (e == cudaSuccess)
+			e = cudaFuncSetAttribute(fmha_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem::TOTAL);
 		if (e != cudaSuccess)
 		{
 			set_last_error("cudaFuncSetAttribute(fmha_fwd_kernel)", e);
@@ -411,7 +455,27 @@ int sdpa_forward_f16(cudaStream_t stream, const SdpaGeom& g, int is_bf16, const 
 		}
 		configured = true;
 	}
-	fmha_fwd_kernel<<<dim3((g.Sq + FM_BLOCK - 1) / FM_BLOCK, g.H, g.B), 192, FmhaSmem::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+	const int q_tiles = (g.Sq + FM_BLOCK - 1) / FM_BLOCK;
+	// CCV_NNC_SM100_FMHA_CLUSTER=2: pairs of query tiles of one (b, h) share their K / V blocks through TMA multicast (halves the
+	// L2 -> smem traffic).  Measured slightly slower than independent CTAs at configs[4] (564 vs 591 TFLOP/s): the kernel is
+	// bound by the softmax warps, not by L2, so it stays off by default
+	const int cl = (q_tiles % 2 == 0 && env_int("CCV_NNC_SM100_FMHA_CLUSTER", 1) == 2) ? 2 : 1;
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.gridDim = dim3(q_tiles, g.H, g.B);
+	cfg.blockDim = dim3(320, 1, 1);
+	cfg.dynamicSmemBytes = FmhaSmem::TOTAL;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = cl, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr, cfg.numAttrs = 1;
+	const cudaError_t le = cl == 2 ? cudaLaunchKernelEx(&cfg, fmha_fwd_kernel<2>, tmQ, tmK, tmV, p) : cudaLaunchKernelEx(&cfg, fmha_fwd_kernel<1>, tmQ, tmK, tmV, p);
+	if (le != cudaSuccess)
+	{
+		set_last_error("fmha_fwd_kernel launch", le);
+		return -1;
+	}
 	count_launch();
 	const cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess)

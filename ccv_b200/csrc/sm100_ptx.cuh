@@ -81,6 +81,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* desc, 
 		"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
 		: "memory");
 }
+// the same 4-D tile load delivered to every CTA of the cluster named in cta_mask (same smem offset, same mbarrier offset in each)
+__device__ __forceinline__ void tma_load_4d_multicast(void* dst, const CUtensorMap* desc, uint64_t* bar, int c0, int c1, int c2, int c3, uint16_t cta_mask)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+		"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+		: "memory");
+}
 // im2col mode over an NHWC tensor {C, W, H, N}: loads `pixelsPerColumn` pixels x `channelsPerPixel` channels,
 // walking base pixels from (w, h, n) through the descriptor's bounding box; (off_w, off_h) is the filter-tap offset.
 __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* desc, uint64_t* bar, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h)
@@ -135,6 +143,27 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same, arriving on the barrier at this offset in every CTA of the cluster named in cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2_approx(const float x)
+{
+	float y;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
