@@ -271,7 +271,7 @@ def main():
         dist.destroy_process_group()
 
 
-FUSED_NAMES = {1: "bn_relu_fwd", 2: "relu_bn_bwd", 3: "add_relu_fwd", 4: "add_relu_bwd", 5: "sgd"}
+FUSED_NAMES = {1: "bn_relu_fwd", 2: "relu_bn_bwd", 3: "add_relu_fwd", 4: "add_relu_bwd", 5: "sgd", 7: "bn_fwd"}
 
 
 def node_cost(cmd, fused_kind, ins, outs):
@@ -279,6 +279,10 @@ def node_cost(cmd, fused_kind, ins, outs):
     contractions = 2 * M * N * K flops; everything else = the bytes it must read + write once)."""
     from ccv_b200 import abi
     nb = lambda t: 0 if t is None else t.nbytes
+    if fused_kind == 6:  # convolution that also emits the batch-norm statistics: cost it as the convolution it is
+        fused_kind, outs = 0, outs[:1]
+    if fused_kind in (1, 7) and len(ins) == 6:  # batch norm reading those statistics: the small statistics tensor is not activation traffic
+        ins = ins[:5]
     io = sum(nb(t) for t in ins) + sum(nb(t) for t in outs)
     if fused_kind:
         return FUSED_NAMES[fused_kind], 0.0, io

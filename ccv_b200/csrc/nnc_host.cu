@@ -489,6 +489,35 @@ ccv_nnc_stream_context_t* ccv_nnc_stream_context_find_neighbor(ccv_nnc_stream_co
 }
 
 // ---------------------------------------------------------------------------------------------------- FFI helpers
+// lib/nnc/ccv_nnc_cmd.c:399-600 reduced to the one backend this host carries: ask the backend's autotune function (if the command has
+// one and more than one algorithm) which algorithm to use for these operands; inputs / outputs are used as scratch exactly as
+// the reference uses its copies.  Returns the command with .backend and .algorithm filled in.
+ccv_nnc_cmd_t ccv_nnc_cmd_autotune(const ccv_nnc_cmd_t cmd, const size_t max_workspace_size, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	ccv_nnc_init();
+	ccv_nnc_cmd_t tuned = cmd;
+	auto it = g_registry.find(cmd.cmd);
+	if (it == g_registry.end() || !it->second.exec)
+		return tuned;
+	tuned.backend = CCV_NNC_BACKEND_GPU_SM100;
+	if (it->second.algorithms <= 1)
+	{
+		tuned.algorithm = 0;
+		return tuned;
+	}
+	if (it->second.autotune)
+		tuned.algorithm = it->second.autotune(tuned, max_workspace_size, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	return tuned;
+}
+
+void ccv_nnc_sm100_cmd_autotune(const uint32_t cmd, const ccv_nnc_cmd_param_t* const info, const ccv_nnc_hint_t* const hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context, int* const algorithm)
+{
+	ccv_nnc_cmd_t c = ccv_nnc_cmd(cmd, 0, *info, 0);
+	c.backend = CCV_NNC_BACKEND_GPU_SM100;
+	c.algorithm = -1;
+	*algorithm = ccv_nnc_cmd_autotune(c, 0, *hint, flags, inputs, input_size, outputs, output_size, stream_context).algorithm;
+}
+
 int ccv_nnc_sm100_cmd_exec(const uint32_t cmd, const uint32_t backend, const int algorithm, const ccv_nnc_cmd_param_t* const info, const ccv_nnc_hint_t* const hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	ccv_nnc_cmd_t c = ccv_nnc_cmd(cmd, 0, *info, 0);
@@ -597,11 +626,14 @@ int ccv_nnc_sm100_fused_relu_bn_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, 
 int ccv_nnc_sm100_fused_add_relu_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_fused_conv_stats_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_fused_bn_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 }
 
 struct ccv_nnc_sm100_graph_s {
 	std::vector<ccv_nnc_sm100_graph_node_t> nodes;
 	std::vector<cudaGraphExec_t> captures;
+	std::vector<ccv_nnc_tensor_t*> owned; // statistics tensors of fused convolution -> batch-norm pairs
 };
 
 extern "C" {
@@ -777,6 +809,38 @@ int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
 		}
 		out.push_back(a);
 	}
+	// (f) CONVOLUTION_FORWARD ; BATCH_NORM_FORWARD(train) (plain or already fused with its ReLU) reading the convolution's output:
+	//     the convolution's tensor-core epilogue also produces the per-channel sums the batch norm needs, through a small
+	//     statistics tensor owned by the graph (one fewer pass over the activation).  CCV_NNC_SM100_FUSE_CONV_BN=0 turns it off.
+	const char* const env = getenv("CCV_NNC_SM100_FUSE_CONV_BN");
+	if (!env || atoi(env) != 0)
+		for (size_t i = 0; i + 1 < out.size(); i++)
+		{
+			ccv_nnc_sm100_graph_node_t& c = out[i];
+			ccv_nnc_sm100_graph_node_t& b = out[i + 1];
+			if (c.fused || c.cmd.cmd != CCV_NNC_CONVOLUTION_FORWARD || c.outputs.size() != 1 || !c.outputs[0] || c.cmd.algorithm == CCV_NNC_SM100_ALGO_FFMA || c.cmd.info.convolution.groups != 1)
+				continue;
+			if (b.cmd.cmd != CCV_NNC_BATCH_NORM_FORWARD || b.cmd.info.bnorm.is_test || b.inputs.size() != 5 || b.inputs[0] != c.outputs[0] || (b.fused && b.fused != ccv_nnc_sm100_fused_bn_relu_forw))
+				continue;
+			if (CCV_IS_TENSOR_VIEW(c.outputs[0]) || CCV_TENSOR_GET_MEMORY(c.outputs[0]->info.type) != CCV_TENSOR_GPU_MEMORY)
+				continue;
+			const int K = c.cmd.info.convolution.count;
+			ccv_nnc_tensor_param_t params = c.outputs[0]->info;
+			memset(params.dim, 0, sizeof(params.dim));
+			params.dim[0] = 160, params.dim[1] = 2 * K; // >= one partial row per SM
+			params.datatype = CCV_32F;
+			ccv_nnc_tensor_t* const stats = ccv_nnc_tensor_new(0, params, 0);
+			if (!stats || !stats->data.u8)
+				continue;
+			stats->sig = 0;
+			graph->owned.push_back(stats);
+			c.outputs.push_back(stats);
+			c.fused = ccv_nnc_sm100_fused_conv_stats_forw;
+			b.inputs.push_back(stats);
+			if (!b.fused)
+				b.fused = ccv_nnc_sm100_fused_bn_forw;
+			// no node is removed by this rewrite: the return value keeps counting removed nodes only
+		}
 	nodes.swap(out);
 	return fused;
 }
@@ -788,7 +852,7 @@ int ccv_nnc_sm100_graph_node(const ccv_nnc_sm100_graph_t* const graph, const int
 		return -1;
 	const ccv_nnc_sm100_graph_node_t& n = graph->nodes[i];
 	*cmd = n.cmd.cmd;
-	*fused_kind = n.fused == ccv_nnc_sm100_fused_bn_relu_forw ? 1 : n.fused == ccv_nnc_sm100_fused_relu_bn_back ? 2 : n.fused == ccv_nnc_sm100_fused_add_relu_forw ? 3 : n.fused == ccv_nnc_sm100_fused_add_relu_back ? 4 : n.fused == ccv_nnc_sm100_fused_sgd_multi ? 5 : 0;
+	*fused_kind = n.fused == ccv_nnc_sm100_fused_bn_relu_forw ? 1 : n.fused == ccv_nnc_sm100_fused_relu_bn_back ? 2 : n.fused == ccv_nnc_sm100_fused_add_relu_forw ? 3 : n.fused == ccv_nnc_sm100_fused_add_relu_back ? 4 : n.fused == ccv_nnc_sm100_fused_sgd_multi ? 5 : n.fused == ccv_nnc_sm100_fused_conv_stats_forw ? 6 : n.fused == ccv_nnc_sm100_fused_bn_forw ? 7 : 0;
 	*input_size = (int)n.inputs.size();
 	*output_size = (int)n.outputs.size();
 	return 0;
@@ -892,6 +956,8 @@ void ccv_nnc_sm100_graph_free(ccv_nnc_sm100_graph_t* const graph)
 		return;
 	for (cudaGraphExec_t ge : graph->captures)
 		cudaGraphExecDestroy(ge);
+	for (ccv_nnc_tensor_t* t : graph->owned)
+		ccv_nnc_tensor_free(t);
 	delete graph;
 }
 

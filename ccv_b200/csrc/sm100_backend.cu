@@ -460,7 +460,10 @@ bool bn_layout(const TV& a, const TV& scale, size_t& outer, int& C, size_t& inne
 
 int bnorm_forw(const int fuse_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
-	if (input_size != 5 || output_size < 1)
+	// a 6th input is the statistics tensor of a fused convolution -> batch norm pair (ccv_nnc_sm100_graph_fuse): its `sig`
+	// field carries the number of valid partial rows the convolution produced for this issue (0 = none: reduce here)
+	const ccv_nnc_tensor_t* const stats_t = input_size == 6 ? inputs[5] : 0;
+	if ((input_size != 5 && input_size != 6) || output_size < 1)
 		return CCV_NNC_EXEC_INVALID;
 	for (int i = 0; i < 5; i++)
 		if (!inputs[i] || !is_f32(inputs[i]))
@@ -496,7 +499,8 @@ int bnorm_forw(const int fuse_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_
 	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
 	if (!ws)
 		return CCV_NNC_EXEC_OOM;
-	RC(bn_fwd_train_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, outputs[3]->data.f32, outputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, cmd.info.bnorm.momentum, ws, fuse_relu));
+	RC(bn_fwd_train_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, outputs[3]->data.f32, outputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, cmd.info.bnorm.momentum, ws, fuse_relu,
+		stats_t && inner == 1 ? stats_t->data.f32 : 0, stats_t ? (int)stats_t->sig : 0));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -1201,6 +1205,47 @@ void fill(ccv_nnc_cmd_backend_registry_t* const registry, const int formats, con
 
 const int ALL_FORMATS = CCV_TENSOR_FORMAT_NCHW | CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_CHWN;
 
+// registry->autotune of the contraction commands (lib/nnc/ccv_nnc.h:323; called by ccv_nnc_cmd_autotune, ccv_nnc_cmd.c:519-531, on
+// scratch copies of the operands): every algorithm of this backend that accepts the shapes is timed on the device (CUDA
+// events on the caller's stream, best of 3 after a warm-up) and the index of the fastest one is returned.  The generic
+// fallback of the reference times the asynchronous *enqueue* with a host clock (ccv_nnc_cmd.c:549-555), which says nothing
+// about a GPU kernel -- hence a real autotune function.
+template <ccv_nnc_cmd_exec_f EXEC>
+int autotune_contraction(const ccv_nnc_cmd_t cmd, const size_t max_workspace_size, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	cudaStream_t s = stream_of(stream_context);
+	cudaEvent_t e0, e1;
+	if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+		return 0;
+	int best = 0;
+	float best_ms = -1.f;
+	const int candidates[2] = { CCV_NNC_SM100_ALGO_TF32, CCV_NNC_SM100_ALGO_FFMA }; // 3xTF32 is reserved
+	for (int k = 0; k < 2; k++)
+	{
+		ccv_nnc_cmd_t c = cmd;
+		c.algorithm = candidates[k];
+		if (EXEC(c, hint, flags, inputs, input_size, outputs, output_size, stream_context) != CCV_NNC_EXEC_SUCCESS) // warm-up + applicability
+			continue;
+		float ms = -1.f;
+		for (int rep = 0; rep < 3; rep++)
+		{
+			cudaEventRecord(e0, s);
+			EXEC(c, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+			cudaEventRecord(e1, s);
+			float t = 0.f;
+			if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&t, e0, e1) != cudaSuccess)
+				continue;
+			if (ms < 0.f || t < ms)
+				ms = t;
+		}
+		if (ms >= 0.f && (best_ms < 0.f || ms < best_ms))
+			best_ms = ms, best = candidates[k];
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return best;
+}
+
 } // namespace
 
 // implemented in sm100_backend_ext.cu (attention, layer / rms norm, upsample, allreduce)
@@ -1224,6 +1269,12 @@ int ccv_nnc_sm100_exec_allreduce(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, cons
 extern "C" int ccv_nnc_sm100_fused_bn_relu_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	return bnorm_forw(1, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
+// BATCH_NORM_FORWARD with the statistics tensor of its producing convolution as a 6th input (no ReLU)
+extern "C" int ccv_nnc_sm100_fused_bn_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return bnorm_forw(0, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 
 extern "C" int ccv_nnc_sm100_fused_relu_bn_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
@@ -1255,6 +1306,24 @@ extern "C" int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t cmd, const 
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
+// CONVOLUTION_FORWARD whose output feeds a training BATCH_NORM_FORWARD: outputs[1] is the statistics tensor
+// ([rows, 2K] fp32) shared with the batch-norm node; the tensor-core epilogue adds sum(y), sum(y * y) per channel into it and
+// the number of partial rows lands in its `sig` field (0 when the launch took a path without that epilogue).
+extern "C" int ccv_nnc_sm100_fused_conv_stats_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (output_size != 2 || !outputs[1])
+		return CCV_NNC_EXEC_INVALID;
+	ccv_nnc_tensor_t* const stats_t = outputs[1];
+	int rows = 0;
+	const int max_rows = stats_t->info.dim[0];
+	if (outputs[0] && stats_t->info.dim[1] == 2 * cmd.info.convolution.count)
+		conv_stats_request(stats_t->data.f32, max_rows, &rows);
+	const int rc = exec_conv_forw(cmd, hint, flags, inputs, input_size, outputs, 1, stream_context);
+	conv_stats_request(0, 0, 0); // never leave a request pending for an unrelated launch
+	stats_t->sig = rc == CCV_NNC_EXEC_SUCCESS ? (uint64_t)rows : 0;
+	return rc;
+}
+
 // T SGD_FORWARD commands with identical parameters as one command: inputs (g, a, m) x T -> outputs (b, n) x T
 extern "C" int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
@@ -1264,12 +1333,12 @@ extern "C" int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_
 // ================================================================================================ registration
 #define REGISTER_SM100(cmd) extern "C" void _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(ccv_nnc_cmd_backend_registry_t* const registry)
 
-REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_forw); }
-REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); }
-REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); }
-REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); }
+REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_forw); registry->autotune = autotune_contraction<exec_gemm_forw>; }
+REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); registry->autotune = autotune_contraction<exec_gemm_back>; }
+REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); registry->autotune = autotune_contraction<exec_conv_forw>; }
+REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); registry->autotune = autotune_contraction<exec_conv_back>; }
 REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_forw); }
-REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_sdpa_back); }
+REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_back); }
 REGISTER_SM100(CCV_NNC_SOFTMAX_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_forw); }
 REGISTER_SM100(CCV_NNC_SOFTMAX_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_back); }
 REGISTER_SM100(CCV_NNC_BATCH_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_bnorm_forw); }

@@ -182,9 +182,49 @@ int ccv_nnc_sm100_exec_sdpa_back(SM100_EXEC_ARGS)
 		return CCV_NNC_EXEC_INVALID;
 	if ((input_size > 6 && inputs[6]) || (input_size > 7 && inputs[7]))
 		return CCV_NNC_EXEC_INVALID;
-	if (CCV_GET_DATA_TYPE(inputs[3]->info.datatype) != CCV_32F)
-		return CCV_NNC_EXEC_NO_KERNEL; // 16-bit backward: not built yet
 	SdpaGeom g, dg;
+	const int dt = CCV_GET_DATA_TYPE(inputs[3]->info.datatype);
+	if (dt != CCV_32F)
+	{
+		// 16-bit backward, functional form: widen g, q, k, v to fp32 in the stream workspace, run the fp32 composed backward
+		// (TF32 tensor-core GEMMs per (b, h)), narrow dq, dk, dv back (round to nearest even).  A fused 16-bit flash
+		// backward kernel is the next step; this keeps the command usable for bf16 / fp16 training meanwhile.
+		for (int i : { 0, 3, 4, 5 })
+			if (CCV_IS_TENSOR_VIEW(inputs[i]))
+				return CCV_NNC_EXEC_INVALID;
+		for (int i = 0; i < 3; i++)
+			if (CCV_IS_TENSOR_VIEW(outputs[i]))
+				return CCV_NNC_EXEC_INVALID;
+		if (!sdpa_geom(cmd, inputs[3], inputs[4], inputs[5], inputs[0], g) || !sdpa_geom(cmd, outputs[0], outputs[1], outputs[2], inputs[0], dg))
+			return CCV_NNC_EXEC_INVALID;
+		if (dg.B != g.B || dg.H != g.H || dg.Hk != g.Hk || dg.Sq != g.Sq || dg.Sk != g.Sk || dg.D != g.D || dg.Dv != g.Dv)
+			return CCV_NNC_EXEC_INVALID;
+		const size_t nq = count_of(inputs[3]), nk = count_of(inputs[4]), nv = count_of(inputs[5]), no = count_of(inputs[0]);
+		const size_t floats = no + 2 * nq + 2 * nk + 2 * nv;
+		const size_t ws_bytes = floats * sizeof(float) + 256 + sdpa_workspace_bytes(g.Sq, g.Sk, 1);
+		float* const base = (float*)ccv_nnc_stream_context_get_workspace(stream_context, ws_bytes, CCV_TENSOR_GPU_MEMORY);
+		if (!base)
+			return CCV_NNC_EXEC_OOM;
+		float* const g32 = base;
+		float* const q32 = g32 + no;
+		float* const k32 = q32 + nq;
+		float* const v32 = k32 + nk;
+		float* const dq32 = v32 + nv;
+		float* const dk32 = dq32 + nq;
+		float* const dv32 = dk32 + nk;
+		void* const inner_ws = (void*)(((uintptr_t)(dv32 + nv) + 255) & ~(uintptr_t)255);
+		const int code = dt == CCV_16BF ? 3 : 1;
+		cudaStream_t st = stream_of(stream_context);
+		if (convert_dtype(st, inputs[0]->data.u8, code, g32, 0, no) || convert_dtype(st, inputs[3]->data.u8, code, q32, 0, nq) ||
+			convert_dtype(st, inputs[4]->data.u8, code, k32, 0, nk) || convert_dtype(st, inputs[5]->data.u8, code, v32, 0, nv))
+			return CCV_NNC_EXEC_INVALID;
+		if (sdpa_backward_f32(st, g, g32, q32, k32, v32, dq32, dk32, dv32, dg, inner_ws))
+			return CCV_NNC_EXEC_INVALID;
+		// fp16 narrowing follows the reference's truncating f32 -> f16 (lib/ccv_util.c:1434-1440), bf16 rounds to nearest even
+		if (convert_dtype(st, dq32, 0, outputs[0]->data.u8, code, nq) || convert_dtype(st, dk32, 0, outputs[1]->data.u8, code, nk) || convert_dtype(st, dv32, 0, outputs[2]->data.u8, code, nv))
+			return CCV_NNC_EXEC_INVALID;
+		return CCV_NNC_EXEC_SUCCESS;
+	}
 	if (!sdpa_geom(cmd, inputs[3], inputs[4], inputs[5], inputs[0], g) || !sdpa_geom(cmd, outputs[0], outputs[1], outputs[2], inputs[0], dg))
 		return CCV_NNC_EXEC_INVALID;
 	if (dg.B != g.B || dg.H != g.H || dg.Hk != g.Hk || dg.Sq != g.Sq || dg.Sk != g.Sk || dg.D != g.D || dg.Dv != g.Dv)

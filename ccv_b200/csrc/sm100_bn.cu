@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
 		s1 += sh[0][j][cx], s2 += sh[1][j][cx];
 	if (MODE == 0)
 	{
-		const double k = (double)x[c];
+		const double k = x ? (double)x[c] : 0.0; // externally produced sums (convolution epilogue) are not shifted
 		const double mean = k + s1 / count;
 		double var = (s2 - s1 * s1 / count) / count;
 		if (var < 0)
@@ -436,13 +436,21 @@ static int run_apply(cudaStream_t s, const float* x, const float* g, float* out,
 	return check("bn_apply");
 }
 
-int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu)
+int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu, const float* ext_part, int ext_rows)
 {
 	if (outer * C * inner == 0)
 		return 0;
 	double* ws = ws_sums(workspace);
 	float* coef = ws_coef(workspace, C);
 	int part_rows = 0;
+	if (ext_part && ext_rows > 0)
+	{
+		// the producing convolution already summed v and v * v per output channel in its epilogue (ext_rows partial rows of 2C)
+		bn_finalize_partials_kernel<0, 0><<<(C + 31) / 32, 1024, 0, s>>>(ext_part, ext_rows, 0, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, 0, 0, coef);
+		if (check("bn_fwd_finalize(ext)"))
+			return -1;
+		return fuse_relu ? run_apply<0, 1>(s, x, 0, y, coef, outer, C, inner) : run_apply<0, 0>(s, x, 0, y, coef, outer, C, inner);
+	}
 	if (run_reduce<0, 0>(s, x, 0, 0, 0, outer, C, inner, ws, ws_part(workspace, C), &part_rows))
 		return -1;
 	if (part_rows > 0)

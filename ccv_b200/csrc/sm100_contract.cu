@@ -107,6 +107,21 @@ static int num_sms()
 	return g_num_sms;
 }
 
+// One-shot request (per host thread) for per-column output statistics from the next forward-shaped launch: set by the fused
+// convolution + batch-norm command, consumed (and cleared) by launch_umma_persistent when the launch qualifies.
+struct StatsRequest {
+	float* part;
+	int max_rows;
+	int* rows_out;
+};
+static thread_local StatsRequest t_stats_request = { 0, 0, 0 };
+void conv_stats_request(float* part, int max_rows, int* rows_out)
+{
+	t_stats_request.part = part, t_stats_request.max_rows = max_rows, t_stats_request.rows_out = rows_out;
+	if (rows_out)
+		*rows_out = 0;
+}
+
 template <int AMODE, int BMODE, int BN, int STAGES>
 static int launch_umma(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p, int grid_x, int grid_y)
 {
@@ -124,6 +139,7 @@ static int launch_umma(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 		configured = true;
 	}
 	dim3 grid(grid_x, grid_y, p.grid_taps * p.splits);
+	t_stats_request.part = 0; // this kernel does not produce statistics: the requester sees rows_out == 0
 	kern<<<grid, 192, S::TOTAL, stream>>>(tmA, tmB, p);
 	count_launch();
 	cudaError_t e = cudaGetLastError();
@@ -153,7 +169,25 @@ static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, c
 	}
 	const long long tiles = (long long)((p.M + UMMA_BLOCK_M - 1) / UMMA_BLOCK_M) * ((p.N + BN - 1) / BN) * p.grid_taps * p.splits;
 	const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-	kern<<<grid, S::THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+	UmmaGemmParams q = p;
+	q.stats = 0;
+	if (t_stats_request.part)
+	{
+		const StatsRequest r = t_stats_request;
+		t_stats_request.part = 0;
+		if (AMODE != OP_MN2D && BMODE == OP_K2D && p.splits == 1 && p.grid_taps == 1 && !p.accumulate && p.rowmap.mode == 0 && p.N % 32 == 0 && grid <= r.max_rows)
+		{
+			const cudaError_t e = cudaMemsetAsync(r.part, 0, (size_t)grid * 2 * p.N * sizeof(float), stream);
+			if (e != cudaSuccess)
+			{
+				set_last_error("memset(conv stats)", e);
+				return -1;
+			}
+			q.stats = r.part;
+			*r.rows_out = grid;
+		}
+	}
+	kern<<<grid, S::THREADS, S::TOTAL, stream>>>(tmA, tmB, q);
 	count_launch();
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess)

@@ -26,6 +26,11 @@ int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, cons
 int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a);
 int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate);
 
+// Ask the NEXT conv_fprop_tf32 / gemm_tf32 launch of this host thread to also produce per-column sums of its output:
+// part[row][0..N) = sum(v), part[row][N..2N) = sum(v * v) over the output rows one CTA wrote; *rows_out = number of rows
+// written (0 when the launch took a path without this epilogue; the request is consumed either way).
+void conv_stats_request(float* part, int max_rows, int* rows_out);
+
 // Small-channel convolutions (C not a multiple of 4, e.g. the 3-channel stem): explicit im2col into `workspace`
 // ([N*P*Q, Kp] with Kp = R*S*C rounded up to 32, zero padded) followed by the tensor-core GEMM.  Returns 1 when not applicable.
 size_t conv_im2col_workspace_bytes(const ConvGeom& g);

@@ -16,7 +16,7 @@
 //             128-byte-swizzled K-major smem tile the second MMA reads; the running output lives in registers:
 //             acc = acc * alpha_j + O_j (O_j read back from TMEM), normalised by the row sum at the end.
 //             Two warps per scheduler instead of one hide the tcgen05.ld / MUFU latency of the other.
-// TMEM: S0, S1, O = 3 x 128 columns.  smem: Q 32 KB + K 2 x 32 KB + V 2 x 32 KB + P 32 KB = 192 KB.
+// TMEM: S0, S1, O0, O1 = 4 x 128 columns (O_j alternates so that folding O_{j-1} into the registers overlaps P_j V_j).  smem: Q 32 KB + K 2 x 32 KB + V 2 x 32 KB + P 32 KB = 192 KB.
 #include "sm100_contract.h"
 #include "sm100_ptx.cuh"
 #include <cuda_bf16.h>
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 						for (int k = 0; k < FM_BLOCK / 16; k++)
 						{
 							const uint32_t poff = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
-							umma_f16(tmem_o, umma_smem_desc(p_addr + poff, 16, 1024, 2), umma_smem_desc(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo, p.v_layout), p.idesc_pv, k > 0 ? 1u : 0u);
+							umma_f16(tmem_o + (uint32_t)(j & 1) * 128, umma_smem_desc(p_addr + poff, 16, 1024, 2), umma_smem_desc(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo, p.v_layout), p.idesc_pv, k > 0 ? 1u : 0u);
 						}
 					}
 					release(&v_empty[s]);
@@ -307,26 +307,16 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 				sum += e0 + e1;
 				pk[i >> 1] = pack2(e0, e1, p.is_bf16);
 			}
-			// O_{j-1} is complete once o_full flips; it also means P / V of block j - 1 are no longer being read
+			// o_full flips when O_{j-1} = P_{j-1} V_{j-1} is complete: the P tile may be overwritten
 			if (j > 0)
 			{
 				mbar_wait(o_full, (uint32_t)(j - 1) & 1);
 				tc_fence_after();
-				uint32_t r[64];
-				tmem_ld_32x32(tmem_o + lane_sel + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-				tmem_ld_32x32(tmem_o + lane_sel + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-				tmem_ld_wait();
-#pragma unroll
-				for (int i = 0; i < 64; i++)
-					acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(r[i]));
 			}
 			// P tile in smem (K-major, 128-byte swizzle; this half = one 64-key atom)
 #pragma unroll
 			for (int c = 0; c < 8; c++)
 				*reinterpret_cast<uint4*>(p_row + ((c ^ (row & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-			l = fmaf(l, alpha, sum);
-			m = m_new;
-			alpha_prev = alpha;
 			// hand S[s] back and publish P_j to the tensor core (generic-proxy smem writes -> async proxy)
 			fence_proxy_async();
 			tc_fence_before();
@@ -336,14 +326,32 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 				mbar_arrive(&s_empty[s]);
 				mbar_arrive(p_full);
 			}
+			// O_{j-1} sits in the other output buffer (O_j goes to O[j & 1]): fold it into the running output off the critical
+			// path, while the tensor core already works on P_j V_j
+			if (j > 0)
+			{
+				uint32_t r[64];
+				const uint32_t to = tmem_o + (uint32_t)((j - 1) & 1) * 128 + lane_sel + half * 64;
+				tmem_ld_32x32(to, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+				tmem_ld_32x32(to + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+				tmem_ld_wait();
+#pragma unroll
+				for (int i = 0; i < 64; i++)
+					acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(r[i]));
+				tc_fence_before();
+			}
+			l = fmaf(l, alpha, sum);
+			m = m_new;
+			alpha_prev = alpha;
 		}
 		if (n_blk > 0)
 		{
 			mbar_wait(o_full, (uint32_t)(n_blk - 1) & 1);
 			tc_fence_after();
 			uint32_t r[64];
-			tmem_ld_32x32(tmem_o + lane_sel + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-			tmem_ld_32x32(tmem_o + lane_sel + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+			const uint32_t to = tmem_o + (uint32_t)((n_blk - 1) & 1) * 128 + lane_sel + half * 64;
+			tmem_ld_32x32(to, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+			tmem_ld_32x32(to + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
 			tmem_ld_wait();
 #pragma unroll
 			for (int i = 0; i < 64; i++)

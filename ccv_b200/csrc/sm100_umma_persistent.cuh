@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 		const bool accumulate = p.accumulate != 0;
 		const float* const bias = p.bias;
 		const int N = p.N;
+		float* const stats = p.stats ? p.stats + (size_t)blockIdx.x * 2 * p.N : 0;
 		int t = 0;
 		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++)
 		{
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 					bias4.z = col + 2 < N ? __ldg(bias + col + 2) : 0.f;
 					bias4.w = col + 3 < N ? __ldg(bias + col + 3) : 0.f;
 				}
+				float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = st1;
 #pragma unroll
 				for (int i = 0; i < 8; i++)
 				{
@@ -259,6 +261,11 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 						continue;
 					float4 v = *reinterpret_cast<const float4*>(scratch + (sub_row + 4 * i) * S::EPI_PITCH + sub_col);
 					v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
+					if (stats)
+					{
+						st1.x += v.x, st1.y += v.y, st1.z += v.z, st1.w += v.w;
+						st2.x = fmaf(v.x, v.x, st2.x), st2.y = fmaf(v.y, v.y, st2.y), st2.z = fmaf(v.z, v.z, st2.z), st2.w = fmaf(v.w, v.w, st2.w);
+					}
 					float* const o = orow[i] + col;
 					if (full4 && ((((uintptr_t)o) & 15) == 0))
 					{
@@ -282,6 +289,21 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 								else
 									o[j] = accumulate ? o[j] + vv[j] : vv[j];
 							}
+					}
+				}
+				if (stats)
+				{
+					// the 4 lanes that share these columns (sub_row 0..3) combine their 8-row partials: 32 rows x 4 columns per lane group
+#pragma unroll
+					for (int o = 8; o <= 16; o <<= 1)
+					{
+						st1.x += __shfl_xor_sync(0xffffffffu, st1.x, o), st1.y += __shfl_xor_sync(0xffffffffu, st1.y, o), st1.z += __shfl_xor_sync(0xffffffffu, st1.z, o), st1.w += __shfl_xor_sync(0xffffffffu, st1.w, o);
+						st2.x += __shfl_xor_sync(0xffffffffu, st2.x, o), st2.y += __shfl_xor_sync(0xffffffffu, st2.y, o), st2.z += __shfl_xor_sync(0xffffffffu, st2.z, o), st2.w += __shfl_xor_sync(0xffffffffu, st2.w, o);
+					}
+					if (sub_row == 0 && full4)
+					{
+						red_add_v4(stats + col, st1.x, st1.y, st1.z, st1.w);
+						red_add_v4(stats + N + col, st2.x, st2.y, st2.z, st2.w);
 					}
 				}
 				}

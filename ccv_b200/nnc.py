@@ -77,6 +77,8 @@ def lib():
         l.ccv_nnc_sm100_graph_replay.restype = i32
         l.ccv_nnc_sm100_graph_replay.argtypes = [vp, i32, vp]
         l.ccv_nnc_sm100_graph_free.argtypes = [vp]
+        l.ccv_nnc_sm100_cmd_autotune.restype = None
+        l.ccv_nnc_sm100_cmd_autotune.argtypes = [u32, C.POINTER(abi.CmdParam), C.POINTER(abi.Hint), i32, C.POINTER(vp), i32, C.POINTER(vp), i32, vp, C.POINTER(i32)]
         l.ccv_nnc_sm100_comm_unique_id.restype = i32
         l.ccv_nnc_sm100_comm_unique_id.argtypes = [vp, sz]
         l.ccv_nnc_sm100_comm_init_rank.restype = i32
@@ -265,6 +267,15 @@ def comm_init_rank(unique_id, world, rank):
     buf = C.create_string_buffer(bytes(unique_id), 128)
     if lib().ccv_nnc_sm100_comm_init_rank(buf, 128, world, rank) != 0:
         raise RuntimeError("comm_init_rank failed: %s" % lib().ccv_nnc_sm100_last_error())
+
+
+def cmd_autotune(cmd, hint, flags, inputs, outputs, stream=None):
+    """ccv_nnc_cmd_autotune (lib/nnc/ccv_nnc.h:829): the backend times its algorithms on these (scratch) operands; returns
+    a copy of `cmd` with .algorithm set to the fastest."""
+    algo = C.c_int(-1)
+    lib().ccv_nnc_sm100_cmd_autotune(cmd.cmd, C.byref(cmd.info), C.byref(hint if hint is not None else abi.NO_HINT), flags, _ptr_array(inputs), len(inputs),
+                                     _ptr_array(outputs), len(outputs), stream.ptr if stream else None, C.byref(algo))
+    return Command(cmd.cmd, info=cmd.info, backend=cmd.backend, algorithm=algo.value)
 
 
 def launch_count():

@@ -471,6 +471,10 @@ ccv_nnc_stream_context_t* ccv_nnc_stream_context_find_neighbor(ccv_nnc_stream_co
 /* FFI conveniences (not in the reference): the same calls with every struct passed by pointer, for bindings      */
 /* that cannot pass 152-byte structs by value (ctypes, cgo, JNI).                                                 */
 /* ------------------------------------------------------------------------------------------------------------ */
+/* lib/nnc/ccv_nnc.h:829 / ccv_nnc_cmd.c:399-600: pick the fastest algorithm of the backend for these operands (device-timed);
+ * inputs / outputs are scratch.  The _sm100_ form takes the structs by pointer and returns the algorithm index.                */
+ccv_nnc_cmd_t ccv_nnc_cmd_autotune(const ccv_nnc_cmd_t cmd, const size_t max_workspace_size, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context);
+void ccv_nnc_sm100_cmd_autotune(const uint32_t cmd, const ccv_nnc_cmd_param_t* const info, const ccv_nnc_hint_t* const hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context, int* const algorithm);
 int ccv_nnc_sm100_cmd_exec(const uint32_t cmd, const uint32_t backend, const int algorithm, const ccv_nnc_cmd_param_t* const info, const ccv_nnc_hint_t* const hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context);
 ccv_nnc_tensor_t* ccv_nnc_sm100_tensor_new(const void* const ptr, const ccv_nnc_tensor_param_t* const params);
 ccv_nnc_tensor_view_t* ccv_nnc_sm100_tensor_view_new(const ccv_nnc_tensor_t* const tensor, const ccv_nnc_tensor_param_t* const params, const int* const ofs, const int* const stride);
@@ -513,7 +517,8 @@ int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin,
 int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph);
 /* introspection and per-node device timing (CUDA events, best of reps) of the (possibly fused) node list;
  * fused_kind: 0 plain command, 1 bn+relu forward, 2 relu+bn backward, 3 add+relu forward, 4 add+relu backward,
- * 5 a run of SGD commands as one multi-tensor launch */
+ * 5 a run of SGD commands as one multi-tensor launch, 6 convolution forward that also produces the batch-norm statistics of
+ * its output (extra output: the statistics tensor), 7 batch-norm forward consuming them (extra input) */
 int ccv_nnc_sm100_graph_node(const ccv_nnc_sm100_graph_t* const graph, const int i, uint32_t* const cmd, int* const fused_kind, int* const input_size, int* const output_size);
 void* ccv_nnc_sm100_graph_node_tensor(const ccv_nnc_sm100_graph_t* const graph, const int i, const int is_output, const int k);
 int ccv_nnc_sm100_graph_profile(ccv_nnc_sm100_graph_t* const graph, ccv_nnc_stream_context_t* const stream_context, const int reps, float* const ms);

@@ -218,3 +218,27 @@ def test_full_size_properties_config2(gpu):
     assert_close(lhs, rhs, 1e-3, "conv(a1 + a2) == conv(a1) + conv(a2)")
     for x in t + [o1, o2, o3, s]:
         x.free()
+
+
+def test_autotune_picks_a_working_algorithm(gpu):
+    """registry->autotune (lib/nnc/ccv_nnc.h:323) of the contraction commands: device-timed choice between the tcgen05 TF32 and the
+    CUDA-core FFMA algorithm.  A large GEMM must come out as TF32 (algorithm 0); a grouped convolution, which the tensor-core
+    path does not take, must come out as FFMA (algorithm 2); the tuned command must then execute."""
+    nnc = gpu
+    stream = nnc.Stream(0)
+    a, w, b = nnc.gpu_tensor([1024, 1024]), nnc.gpu_tensor([1024, 1024]), nnc.gpu_tensor([1024, 1024])
+    a.upload(seeded((1024, 1024), 1)), w.upload(seeded((1024, 1024), 2))
+    cmd = nnc.CMD_GEMM_FORWARD(transpose_b=(0, 1))
+    tuned = nnc.cmd_autotune(cmd, None, 0, [a, w], [b], stream)
+    assert tuned.algorithm == abi.CCV_NNC_SM100_ALGO_TF32
+    assert nnc.cmd_exec(tuned, None, 0, [a, w], [b], stream) == 0
+    x, f, y = nnc.gpu_tensor([2, 16, 16, 32]), nnc.gpu_tensor([64, 3, 3, 16]), nnc.gpu_tensor([2, 16, 16, 64])
+    x.upload(seeded((2, 16, 16, 32), 3)), f.upload(seeded((64, 3, 3, 16), 4))
+    conv = nnc.CMD_CONVOLUTION_FORWARD(2, 64, 3, 3, 32)
+    hint = nnc.hint((1, 1), (1, 1))
+    tuned = nnc.cmd_autotune(conv, hint, 0, [x, f], [y], stream)
+    assert tuned.algorithm == abi.CCV_NNC_SM100_ALGO_FFMA
+    assert nnc.cmd_exec(tuned, hint, 0, [x, f], [y], stream) == 0
+    stream.wait()
+    for t in (a, w, b, x, f, y, stream):
+        t.free()

@@ -133,3 +133,27 @@ def test_flash_attention_16bit_forward(gpu, ref, B, Sq, Sk, Hq, Hk, causal, dtyp
     assert_close(tl.download(), lse64, 1e-3, "log-sum-exp")
     for t in (tq, tk, tv, to, tl, stream):
         t.free()
+
+
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,causal", [(1, 128, 128, 2, 2, 0), (2, 64, 96, 4, 2, 1)])
+def test_attention_bf16_backward(gpu, ref, B, Sq, Sk, Hq, Hk, causal):
+    """bf16 SDPA backward (functional form: widened to fp32, composed from the TF32 GEMMs, narrowed with RNE) against CPU_REF's
+    fp32 backward on the bf16-rounded operands; 1e-2 of max|ref| (bf16 output rounding alone is 4e-3)."""
+    nnc = gpu
+    D = 128
+    scale = 1.0 / np.sqrt(D)
+    arrs = [seeded((B, Sq, Hq, D), 4, -1, 1), None, None, seeded((B, Sq, Hq, D), 1, -1, 1), seeded((B, Sk, Hk, D), 2, -1, 1), seeded((B, Sk, Hk, D), 3, -1, 1)]
+    bits = [None if a is None else _to_bf16(a) for a in arrs]
+    vals = [None if b is None else _from_bf16(b) for b in bits]
+    bwd = _cmd(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD, scale, causal)
+    st_r, (dq_r, dk_r, dv_r) = ref_exec(ref, bwd, None, 0, vals, [np.zeros_like(vals[3]), np.zeros_like(vals[4]), np.zeros_like(vals[5])])
+    assert st_r == 0
+    stream = nnc.Stream(0)
+    ins = [None if b is None else nnc.gpu_tensor(list(b.shape), datatype=abi.CCV_16BF).upload(b) for b in bits]
+    outs = [nnc.gpu_tensor(list(vals[i].shape), datatype=abi.CCV_16BF) for i in (3, 4, 5)]
+    assert nnc.cmd_exec(bwd, None, 0, ins, outs, stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+    stream.wait()
+    for t, want, name in zip(outs, (dq_r, dk_r, dv_r), ("dq", "dk", "dv")):
+        assert_close(_from_bf16(t.download()), want, 1e-2, "bf16 " + name)
+    for t in [x for x in ins if x is not None] + outs + [stream]:
+        t.free()

@@ -119,6 +119,9 @@ def test_fused_graph_and_cuda_graph_replay_match_the_unfused_run(gpu):
     fused, g1, n = _gpu_net(nnc, -1, True, stream)
     assert n >= 60, "expected the BN+ReLU / residual pairs of ResNet-50 to fuse, got %d" % n
     assert len(g1) == len(g0) - n
+    # every convolution that feeds a training batch norm also produces that batch norm's statistics in its epilogue
+    kinds = [k for _, k, _, _ in g1.nodes()]
+    assert kinds.count(6) >= 50 and kinds.count(6) == sum(1 for _, k, ins, _ in g1.nodes() if k in (1, 7) and len(ins) == 6)
     # forward is bit-identical (same arithmetic, one pass instead of two); the backward recomputes the ReLU mask from
     # x * a + b with the same fmaf, so gradients agree to rounding of the re-associated batch-norm backward algebra
     # not bit-identical: split-K red.add and the batch-norm cross-block atomics make summation order run-dependent
