@@ -330,8 +330,17 @@ def profile_nodes(nnc, net, graphs, stream, pk):
     tc = [r for r in rows if r["flops"] > 0]
     tc_flops, tc_ms = sum(r["flops"] for r in tc), sum(r["ms"] for r in tc)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "umma_gemm_kernel (tcgen05 kind::tf32; all convolution + GEMM commands of one step)", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak, "traffic": None, "peak_source": "%s bf16 cuBLAS burst peak / 2 (TF32 tensor rate is half the bf16 rate)" % pk["source"],
+    # DRAM bytes of the same launches from one `ncu --set full` capture (tools/run_ncu_traffic.sh -> profiles/): all
+    # contraction launches of one step, to be read against the algorithmic operand + result bytes of those commands
+    traffic, traffic_note = None, None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_contraction_traffic.json")))
+        traffic, traffic_note = float(t["dram_bytes_per_step"]), "dram__bytes_read.sum + dram__bytes_write.sum over the %d contraction launches of one step (ncu --set full, profiles/r01_contraction_traffic.json)" % t["launches"]
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "umma_* (tcgen05 kind::tf32 GEMM / implicit-GEMM convolution kernels; all convolution + GEMM commands of one step)", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf32_peak, "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes_per_step": sum(r["bytes"] for r in tc),
+                "peak_source": "%s bf16 cuBLAS burst peak / 2 (TF32 tensor rate is half the bf16 rate)" % pk["source"],
                 "launch_ms_total": tc_ms, "algorithmic_flops_per_step": tc_flops, "total_ms_all_commands": sum(r["ms"] for r in rows)}
     return dict(roofline=roofline, summary=summary, rows=rows)
 

@@ -122,41 +122,11 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 			s1.x += u.x, s1.y += u.y, s1.z += u.z, s1.w += u.w;
 			s2.x += v.x, s2.y += v.y, s2.z += v.z, s2.w += v.w;
 		}
-		// per-block partial sums; partials_reduce_kernel adds the gridDim.y rows in a fixed order (no atomics: 600 same-address
+		// per-block partial sums; bn_finalize_partials_kernel adds the gridDim.y rows in a fixed order (no atomics: 600 same-address
 		// fp64 atomics per channel cost ~15 us per launch, profiles/r01_ncu_bn_reduce_apply.txt, and made the result run-dependent)
 		float* const row = part + (size_t)blockIdx.y * 2 * C;
 		st4(row + cv * 4, s1);
 		st4(row + C + cv * 4, s2);
-	}
-}
-
-// out[col] = sum over y of part[y][col] (double accumulation, fixed order): 32 columns x 32 row-lanes per block
-__global__ void __launch_bounds__(1024) bn_partials_reduce_kernel(const float* __restrict__ part, const int gy, const int ncols, double* __restrict__ out)
-{
-	__shared__ double sh[32][33];
-	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
-	const int col = blockIdx.x * 32 + cx;
-	double acc = 0;
-	if (col < ncols)
-	{
-		int y = yl;
-		for (; y + 96 < gy; y += 128)
-		{
-			const float a0 = part[(size_t)y * ncols + col], a1 = part[(size_t)(y + 32) * ncols + col], a2 = part[(size_t)(y + 64) * ncols + col], a3 = part[(size_t)(y + 96) * ncols + col];
-			acc += (double)a0 + (double)a1 + (double)a2 + (double)a3;
-		}
-		for (; y < gy; y += 32)
-			acc += (double)part[(size_t)y * ncols + col];
-	}
-	sh[yl][cx] = acc;
-	__syncthreads();
-	if (yl == 0 && col < ncols)
-	{
-		double t = 0;
-#pragma unroll
-		for (int j = 0; j < 32; j++)
-			t += sh[j][cx];
-		out[col] = t;
 	}
 }
 

@@ -638,6 +638,21 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const float* __restrict__ gb, 
 			h = (int)(r % g.H);
 			n = (int)(r / g.H);
 		}
+		if (!IS_MAX && VEC == 4 && g.R == g.stride_h && g.S == g.stride_w && g.pad_h == 0 && g.pad_w == 0)
+		{
+			// non-overlapping windows (the 2 x 2 / 2 shortcut pools, the global pool): every input position belongs to at most one
+			// window, whose size is never clipped -> one load, one divide per lane, one store
+			const int p = h / g.stride_h, q = w / g.stride_w;
+			float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (p < g.P && q < g.Q)
+			{
+				const float4 t = *reinterpret_cast<const float4*>(gb + n * g.bn + p * g.bh + q * g.bw + c);
+				const float inv = (float)(g.R * g.S);
+				o = make_float4(t.x / inv, t.y / inv, t.z / inv, t.w / inv);
+			}
+			*reinterpret_cast<float4*>(ga + n * g.an + h * g.ah + w * g.aw + c) = o;
+			continue;
+		}
 		// windows p with p * stride - pad <= h < p * stride - pad + R
 		const int p_lo = max((h + g.pad_h - g.R + g.stride_h) / g.stride_h, 0), p_hi = min((h + g.pad_h) / g.stride_h, g.P - 1);
 		const int q_lo = max((w + g.pad_w - g.S + g.stride_w) / g.stride_w, 0), q_hi = min((w + g.pad_w) / g.stride_w, g.Q - 1);

@@ -232,3 +232,49 @@ def test_set_transfer_format_transform_transpose_are_bit_exact(gpu, ref):
     ref_exec(ref, nnc.CMD_TRANSPOSE_FORWARD(1, 2), None, 0, [a], [t_r])
     st, (t_g,) = gpu_exec(nnc, nnc.CMD_TRANSPOSE_FORWARD(1, 2), None, 0, [a], [t_g])
     assert st == 0 and np.array_equal(t_g, t_r)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("N,H,C,K,R,relu", [(8, 28, 64, 128, 3, 1), (16, 14, 256, 64, 1, 0), (4, 32, 3, 32, 3, 1)])
+def test_convolution_epilogue_statistics_feed_the_batch_norm(gpu, ref, N, H, C, K, R, relu):
+    """Graph rewrite (f) of ccv_nnc_sm100_graph_fuse: CONVOLUTION_FORWARD -> BATCH_NORM_FORWARD(train) [-> RELU in place].  The
+    convolution's tensor-core epilogue sums y and y * y per channel and the batch norm skips its statistics pass.  Checked against
+    CPU_REF running the same three commands one by one: y within the TF32 bound, saved mean / inv_std / running statistics
+    within 1e-3 (they are sums over N * H * W = thousands of TF32-accurate values)."""
+    nnc = gpu
+    pad = R // 2
+    x, w, b = seeded((N, H, H, C), 1, -1, 1), seeded((K, R, R, C), 2, -1, 1) / (R * R * C) ** 0.5, seeded((K,), 3, -1, 1)
+    scale, bias = seeded((1, 1, 1, K), 4, 0.5, 1.5), seeded((1, 1, 1, K), 5, -1, 1)
+    hint = nnc.hint((1, 1), (pad, pad))
+    conv = nnc.CMD_CONVOLUTION_FORWARD(1, K, R, R, C)
+    bn = nnc.CMD_BATCH_NORM_FORWARD(1e-4, 0, 0.9)
+    # oracle: conv, bn, relu one by one
+    y = np.zeros((N, H, H, K), np.float32)
+    assert ref_exec(ref, conv, hint, 0, [x, w, b], [y])[0] == 0
+    mean, var = np.zeros((1, 1, 1, K), np.float32), np.ones((1, 1, 1, K), np.float32)
+    z, sm, sis = np.zeros_like(y), np.zeros((1, 1, 1, K), np.float32), np.zeros((1, 1, 1, K), np.float32)
+    assert ref_exec(ref, bn, None, 0, [y, scale, bias, mean, var], [z, mean, var, sm, sis])[0] == 0
+    if relu:
+        z = np.maximum(z, 0)
+    # GPU: the same commands as a graph, fused
+    stream = nnc.Stream(0)
+    T = lambda a: nnc.gpu_tensor(list(a.shape)).upload(a)
+    tx, tw, tb, tscale, tbias = T(x), T(w), T(b), T(scale), T(bias)
+    tmean, tvar = T(np.zeros((1, 1, 1, K), np.float32)), T(np.ones((1, 1, 1, K), np.float32))
+    ty, tz, tsm, tsis = (nnc.gpu_tensor(s) for s in ([N, H, H, K], [N, H, H, K], [1, 1, 1, K], [1, 1, 1, K]))
+    g = nnc.Graph()
+    g.exec_new(conv, hint, 0, [tx, tw, tb], [ty])
+    g.exec_new(bn, None, 0, [ty, tscale, tbias, tmean, tvar], [tz, tmean, tvar, tsm, tsis])
+    if relu:
+        g.exec_new(nnc.CMD_RELU_FORWARD(), None, 0, [tz], [tz])
+    g.fuse()
+    kinds = [k for _, k, _, _ in g.nodes()]
+    assert kinds == ([6, 1] if relu else [6, 7]), kinds
+    assert g.run(stream) == 0
+    stream.wait()
+    assert_close(ty.download(), y, 1e-3, "convolution output")
+    assert_close(tsm.download(), sm, 1e-3, "saved mean"), assert_close(tsis.download(), sis, 1e-3, "saved inv_std")
+    assert_close(tmean.download(), mean, 1e-3, "running mean"), assert_close(tvar.download(), var, 1e-3, "running var")
+    assert_close(tz.download(), z, 2e-3, "normalised output")
+    for t in (tx, tw, tb, tscale, tbias, tmean, tvar, ty, tz, tsm, tsis, g, stream):
+        t.free()
