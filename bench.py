@@ -271,7 +271,7 @@ def main():
         dist.destroy_process_group()
 
 
-FUSED_NAMES = {1: "bn_relu_fwd", 2: "relu_bn_bwd", 3: "add_relu_fwd", 4: "add_relu_bwd", 5: "sgd", 7: "bn_fwd"}
+FUSED_NAMES = {1: "bn_relu_fwd", 2: "relu_bn_bwd", 3: "add_relu_fwd", 4: "add_relu_bwd", 5: "sgd", 7: "bn_fwd", 8: "bn_bwd"}
 
 
 def node_cost(cmd, fused_kind, ins, outs):

@@ -628,6 +628,7 @@ int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t,
 int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 int ccv_nnc_sm100_fused_conv_stats_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 int ccv_nnc_sm100_fused_bn_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
+int ccv_nnc_sm100_fused_bn_back(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);
 }
 
 struct ccv_nnc_sm100_graph_s {
@@ -841,6 +842,25 @@ int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
 				b.fused = ccv_nnc_sm100_fused_bn_forw;
 			// no node is removed by this rewrite: the return value keeps counting removed nodes only
 		}
+	// (g) BATCH_NORM_BACKWARD (plain or fused with the ReLU backward in front) ; CONVOLUTION_BACKWARD whose incoming gradient is the
+	//     dx of that batch norm and which wants a bias gradient: the batch norm's apply pass sums the dx it writes per channel and
+	//     stores the convolution's dbias directly; the convolution skips its column-sum pass over dx.
+	if (!env || atoi(env) != 0)
+		for (size_t i = 0; i + 1 < out.size(); i++)
+		{
+			ccv_nnc_sm100_graph_node_t& b = out[i];
+			ccv_nnc_sm100_graph_node_t& c = out[i + 1];
+			if (b.cmd.cmd != CCV_NNC_BATCH_NORM_BACKWARD || (b.fused && b.fused != ccv_nnc_sm100_fused_relu_bn_back) || b.outputs.size() != 3 || !b.outputs[0])
+				continue;
+			if (c.fused || c.cmd.cmd != CCV_NNC_CONVOLUTION_BACKWARD || (c.flags & CCV_NNC_ACCUMULATE_OUTPUT) || c.inputs.empty() || c.inputs[0] != b.outputs[0] || c.outputs.size() < 3 || !c.outputs[2])
+				continue;
+			if (CCV_IS_TENSOR_VIEW(c.outputs[2]) || CCV_IS_TENSOR_VIEW(b.outputs[0]))
+				continue;
+			b.outputs.push_back(c.outputs[2]);
+			c.outputs[2] = 0;
+			if (!b.fused)
+				b.fused = ccv_nnc_sm100_fused_bn_back;
+		}
 	nodes.swap(out);
 	return fused;
 }
@@ -852,7 +872,7 @@ int ccv_nnc_sm100_graph_node(const ccv_nnc_sm100_graph_t* const graph, const int
 		return -1;
 	const ccv_nnc_sm100_graph_node_t& n = graph->nodes[i];
 	*cmd = n.cmd.cmd;
-	*fused_kind = n.fused == ccv_nnc_sm100_fused_bn_relu_forw ? 1 : n.fused == ccv_nnc_sm100_fused_relu_bn_back ? 2 : n.fused == ccv_nnc_sm100_fused_add_relu_forw ? 3 : n.fused == ccv_nnc_sm100_fused_add_relu_back ? 4 : n.fused == ccv_nnc_sm100_fused_sgd_multi ? 5 : n.fused == ccv_nnc_sm100_fused_conv_stats_forw ? 6 : n.fused == ccv_nnc_sm100_fused_bn_forw ? 7 : 0;
+	*fused_kind = n.fused == ccv_nnc_sm100_fused_bn_relu_forw ? 1 : n.fused == ccv_nnc_sm100_fused_relu_bn_back ? 2 : n.fused == ccv_nnc_sm100_fused_add_relu_forw ? 3 : n.fused == ccv_nnc_sm100_fused_add_relu_back ? 4 : n.fused == ccv_nnc_sm100_fused_sgd_multi ? 5 : n.fused == ccv_nnc_sm100_fused_conv_stats_forw ? 6 : n.fused == ccv_nnc_sm100_fused_bn_forw ? 7 : n.fused == ccv_nnc_sm100_fused_bn_back ? 8 : 0;
 	*input_size = (int)n.inputs.size();
 	*output_size = (int)n.outputs.size();
 	return 0;

@@ -509,6 +509,8 @@ int exec_bnorm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const in
 	return bnorm_forw(0, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 
+static inline bool h_t_ok(const ccv_nnc_tensor_t* const h) { return h != 0; }
+
 // norm/ccv_nnc_batch_norm_cpu_ref.c:312-470: inputs[0] = g, [5] = a, [6] = scale, [13] = saved_mean, [14] = saved_inv_std;
 // outputs (h, dscale, dbias)
 int bnorm_back(const int fused_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
@@ -529,10 +531,15 @@ int bnorm_back(const int fused_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint
 	ccv_nnc_tensor_t* const h_t = outputs[0];
 	ccv_nnc_tensor_t* const dscale_t = output_size > 1 ? outputs[1] : 0;
 	ccv_nnc_tensor_t* const dbias_t = output_size > 2 ? outputs[2] : 0;
+	// a 4th output is the bias gradient of the convolution that produced this batch norm's input (graph rewrite (g) of
+	// ccv_nnc_sm100_graph_fuse): sum over pixels of the dx written here
+	ccv_nnc_tensor_t* const conv_dbias_t = output_size > 3 ? outputs[3] : 0;
 	const TV a = view_of(a_t), g = view_of(g_t), scale = view_of(scale_t);
 	size_t outer, inner;
 	int C;
 	if (!same_shape(a, g) || !g.contiguous || !bn_layout(a, scale, outer, C, inner))
+		return CCV_NNC_EXEC_INVALID;
+	if (conv_dbias_t && (!h_t_ok(outputs[0]) || !is_f32(conv_dbias_t) || view_of(conv_dbias_t).count != (size_t)C || !view_of(conv_dbias_t).contiguous))
 		return CCV_NNC_EXEC_INVALID;
 	if (h_t && (!same_shape(view_of(h_t), a) || !view_of(h_t).contiguous))
 		return CCV_NNC_EXEC_INVALID;
@@ -540,7 +547,7 @@ int bnorm_back(const int fused_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint
 	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
 	if (!ws)
 		return CCV_NNC_EXEC_OOM;
-	RC(bn_bwd_f32(s, g_t->data.f32, a_t->data.f32, scale_t->data.f32, bias_t ? bias_t->data.f32 : 0, mean_t->data.f32, istd_t->data.f32, h_t ? h_t->data.f32 : 0, dscale_t ? dscale_t->data.f32 : 0, dbias_t ? dbias_t->data.f32 : 0, outer, C, inner, ws));
+	RC(bn_bwd_f32(s, g_t->data.f32, a_t->data.f32, scale_t->data.f32, bias_t ? bias_t->data.f32 : 0, mean_t->data.f32, istd_t->data.f32, h_t ? h_t->data.f32 : 0, dscale_t ? dscale_t->data.f32 : 0, dbias_t ? dbias_t->data.f32 : 0, outer, C, inner, ws, conv_dbias_t ? conv_dbias_t->data.f32 : 0));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -1275,6 +1282,12 @@ extern "C" int ccv_nnc_sm100_fused_bn_relu_forw(const ccv_nnc_cmd_t cmd, const c
 extern "C" int ccv_nnc_sm100_fused_bn_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	return bnorm_forw(0, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
+// BATCH_NORM_BACKWARD with the bias gradient of the producing convolution as a 4th output (no ReLU in front)
+extern "C" int ccv_nnc_sm100_fused_bn_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return bnorm_back(0, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 
 extern "C" int ccv_nnc_sm100_fused_relu_bn_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)

@@ -299,11 +299,15 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
 
 // ------------------------------------------------------------------------------------------------ elementwise passes
 // forward: y = x * a + b (optionally relu'd).  backward: dx = a * g' + p * x + q with the optional relu mask on g.
-template <int BWD, int RELU>
-__global__ void __launch_bounds__(256) bn_apply_vec_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, const float* __restrict__ coef, const size_t total4, const int C)
+// COLSUM (backward only): also leaves per-channel sums of the values written in `part` (rows of C floats; the caller guarantees
+// stride % CV == 0, so a thread stays on one channel group, and 256 % CV == 0 or CV % 256 == 0) -- the bias gradient of the
+// convolution that consumes dx, without another pass over dx.
+template <int BWD, int RELU, int COLSUM>
+__global__ void __launch_bounds__(256) bn_apply_vec_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, const float* __restrict__ coef, const size_t total4, const int C, float* __restrict__ part)
 {
 	const int CV = C >> 2;
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += 2 * stride)
 	{
 		const size_t j = i + stride;
@@ -339,7 +343,55 @@ __global__ void __launch_bounds__(256) bn_apply_vec_kernel(const float* __restri
 				o.z = fmaf(a.z, h2, fmaf(p.z, xv.z, q.z)), o.w = fmaf(a.w, h3, fmaf(p.w, xv.w, q.w));
 			}
 			st4(out + e * 4, o);
+			if (COLSUM)
+				cs.x += o.x, cs.y += o.y, cs.z += o.z, cs.w += o.w;
 		}
+	}
+	if (COLSUM)
+	{
+		if (CV < 256)
+		{
+			// 256 / CV threads of this block share a channel group (256 % CV == 0): one partial row per block
+			__shared__ float4 sh[256];
+			sh[threadIdx.x] = cs;
+			__syncthreads();
+			if ((int)threadIdx.x < CV)
+			{
+				for (int k = threadIdx.x + CV; k < 256; k += CV)
+				{
+					const float4 v = sh[k];
+					cs.x += v.x, cs.y += v.y, cs.z += v.z, cs.w += v.w;
+				}
+				st4(part + ((size_t)blockIdx.x * CV + threadIdx.x) * 4, cs);
+			}
+		} else // CV % 256 == 0: every thread of the grid owns (row, channel group) = divmod(global thread id, CV)
+			st4(part + (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, cs);
+	}
+}
+// out[c] = sum over rows of part[row][c] in a fixed order: 32 columns x 32 row-lanes per block
+__global__ void __launch_bounds__(1024) bn_colsum_rows_kernel(const float* __restrict__ part, const int rows, const int C, float* __restrict__ out)
+{
+	__shared__ float sh[32][33];
+	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
+	const int c = blockIdx.x * 32 + cx;
+	float acc = 0.f;
+	if (c < C)
+	{
+		int y = yl;
+		for (; y + 96 < rows; y += 128)
+			acc += (part[(size_t)y * C + c] + part[(size_t)(y + 32) * C + c]) + (part[(size_t)(y + 64) * C + c] + part[(size_t)(y + 96) * C + c]);
+		for (; y < rows; y += 32)
+			acc += part[(size_t)y * C + c];
+	}
+	sh[yl][cx] = acc;
+	__syncthreads();
+	if (yl == 0 && c < C)
+	{
+		float t = 0.f;
+#pragma unroll
+		for (int j = 0; j < 32; j++)
+			t += sh[j][cx];
+		out[c] = t;
 	}
 }
 template <int BWD, int RELU>
@@ -396,12 +448,27 @@ static int run_reduce(cudaStream_t s, const float* x, const float* g, const floa
 }
 
 template <int BWD, int RELU>
-static int run_apply(cudaStream_t s, const float* x, const float* g, float* out, const float* coef, size_t outer, int C, size_t inner)
+static int run_apply(cudaStream_t s, const float* x, const float* g, float* out, const float* coef, size_t outer, int C, size_t inner, float* part = 0, float* colsum_out = 0, int* colsum_done = 0)
 {
 	const size_t total = outer * C * inner;
 	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(out) && (!BWD || aligned16(g)))
-		bn_apply_vec_kernel<BWD, RELU><<<grid_for(total / 8, 256), 256, 0, s>>>(x, g, out, coef, total / 4, C);
-	else
+	{
+		int grid = grid_for(total / 8, 256);
+		const int CV = C / 4;
+		if (BWD && part && colsum_out && (256 % CV == 0 || CV % 256 == 0))
+		{
+			if (CV > 256) // the grid stride must be a multiple of CV
+				grid = (grid + CV / 256 - 1) / (CV / 256) * (CV / 256);
+			bn_apply_vec_kernel<BWD, RELU, 1><<<grid, 256, 0, s>>>(x, g, out, coef, total / 4, C, part);
+			if (check("bn_apply"))
+				return -1;
+			const int rows = CV < 256 ? grid : (int)((size_t)grid * 256 / CV);
+			bn_colsum_rows_kernel<<<(C + 31) / 32, 1024, 0, s>>>(part, rows, C, colsum_out);
+			*colsum_done = 1;
+			return check("bn_colsum_rows");
+		}
+		bn_apply_vec_kernel<BWD, RELU, 0><<<grid, 256, 0, s>>>(x, g, out, coef, total / 4, C, 0);
+	} else
 		bn_apply_generic_kernel<BWD, RELU><<<grid_for(total, 256), 256, 0, s>>>(x, g, out, coef, total, C, inner);
 	return check("bn_apply");
 }
@@ -444,7 +511,7 @@ int bn_fwd_test_f32(cudaStream_t s, const float* x, float* y, const float* scale
 }
 
 // bias != NULL selects the fused form: g is the gradient w.r.t. relu(bn(x)) and is masked by bn(x) > 0 on the fly
-int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, float* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace)
+int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, float* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace, float* dx_colsum)
 {
 	if (outer * C * inner == 0)
 		return 0;
@@ -477,7 +544,15 @@ int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scal
 		return -1;
 	if (!dx)
 		return 0;
-	return mask ? run_apply<1, 1>(s, x, g, dx, coef, outer, C, inner) : run_apply<1, 0>(s, x, g, dx, coef, outer, C, inner);
+	// dx_colsum: per-channel sum of dx (the bias gradient of the convolution that produced x), gathered by the apply pass itself;
+	// the partial rows reuse the reduce pass's partial area (its contents were consumed by the finalize kernel above)
+	int done = 0;
+	float* const part = dx_colsum ? ws_part(workspace, C) : 0;
+	if (mask ? run_apply<1, 1>(s, x, g, dx, coef, outer, C, inner, part, dx_colsum, &done) : run_apply<1, 0>(s, x, g, dx, coef, outer, C, inner, part, dx_colsum, &done))
+		return -1;
+	if (dx_colsum && !done) // layouts the vector path does not take: a separate column sum over dx
+		return colsum_f32(s, dx, outer * inner, C, C, dx_colsum, 0, 0);
+	return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ fused residual adds

@@ -280,7 +280,9 @@ static int pick_splits(long long tiles, int k_iters, int min_iters_per_split)
 	const long long target = 2ll * num_sms();
 	if (tiles >= target)
 		return 1;
-	long long s = (target + tiles - 1) / tiles;
+	// floor, not ceil: tiles * splits must fit in ONE wave of 2 CTAs per SM -- 5 tiles x 60 splits = 300 CTAs on 296 slots ran a
+	// second wave of 4 CTAs and doubled the kernel time (profiles/r01_ncu_wgrad_taps64.txt)
+	long long s = target / tiles;
 	const long long max_s = k_iters / min_iters_per_split;
 	if (s > max_s)
 		s = max_s;

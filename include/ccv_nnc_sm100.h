@@ -518,7 +518,8 @@ int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph);
 /* introspection and per-node device timing (CUDA events, best of reps) of the (possibly fused) node list;
  * fused_kind: 0 plain command, 1 bn+relu forward, 2 relu+bn backward, 3 add+relu forward, 4 add+relu backward,
  * 5 a run of SGD commands as one multi-tensor launch, 6 convolution forward that also produces the batch-norm statistics of
- * its output (extra output: the statistics tensor), 7 batch-norm forward consuming them (extra input) */
+ * its output (extra output: the statistics tensor), 7 batch-norm forward consuming them (extra input), 8 batch-norm backward
+ * that also writes the bias gradient of the convolution in front of it (extra output; kind 2 may carry it too) */
 int ccv_nnc_sm100_graph_node(const ccv_nnc_sm100_graph_t* const graph, const int i, uint32_t* const cmd, int* const fused_kind, int* const input_size, int* const output_size);
 void* ccv_nnc_sm100_graph_node_tensor(const ccv_nnc_sm100_graph_t* const graph, const int i, const int is_output, const int k);
 int ccv_nnc_sm100_graph_profile(ccv_nnc_sm100_graph_t* const graph, ccv_nnc_stream_context_t* const stream_context, const int reps, float* const ms);

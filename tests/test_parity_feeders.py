@@ -278,3 +278,53 @@ def test_convolution_epilogue_statistics_feed_the_batch_norm(gpu, ref, N, H, C, 
     assert_close(tz.download(), z, 2e-3, "normalised output")
     for t in (tx, tw, tb, tscale, tbias, tmean, tvar, ty, tz, tsm, tsis, g, stream):
         t.free()
+
+
+@pytest.mark.parametrize("C,relu", [(64, 0), (256, 1), (2048, 0)])
+def test_batch_norm_backward_also_writes_the_convolution_bias_gradient(gpu, C, relu):
+    """Graph rewrite (g): [RELU_BACKWARD ;] BATCH_NORM_BACKWARD ; CONVOLUTION_BACKWARD(g = the batch norm's dx).  The fused list must
+    give the convolution the same dbias = sum over pixels of dx (mathematically 0 behind a batch norm, so the comparison is
+    against the magnitude of the summands), the same dx and the same filter gradient as the unfused list."""
+    nnc = gpu
+    N, H, Cin, R = 8, 7, 32, 1
+    stream = nnc.Stream(0)
+    rs = np.random.RandomState(3)
+    x_in, w = seeded((N, H, H, Cin), 1, -1, 1), seeded((C, R, R, Cin), 2, -1, 1) / Cin ** 0.5
+    y = rs.randn(N, H, H, C).astype(np.float32)            # the convolution's output = the batch norm's input
+    gy = rs.randn(N, H, H, C).astype(np.float32)
+    scale, bias = seeded((1, 1, 1, C), 4, 0.5, 1.5), seeded((1, 1, 1, C), 5, -1, 1)
+    mean = y.mean(axis=(0, 1, 2)).reshape(1, 1, 1, C).astype(np.float32)
+    inv_std = (1.0 / np.sqrt(y.var(axis=(0, 1, 2)) + 1e-4)).reshape(1, 1, 1, C).astype(np.float32)
+    z = np.maximum((y - mean) * inv_std * scale + bias, 0).astype(np.float32)  # relu(bn(y)), the mask source
+
+    def run(fuse):
+        T = lambda a: nnc.gpu_tensor(list(a.shape)).upload(a)
+        t = dict(x=T(x_in), w=T(w), y=T(y), g=T(gy), scale=T(scale), bias=T(bias), mean=T(mean), istd=T(inv_std), z=T(z))
+        t.update(dx=nnc.gpu_tensor([N, H, H, C]), dscale=nnc.gpu_tensor([1, 1, 1, C]), dbias=nnc.gpu_tensor([1, 1, 1, C]),
+                 h=nnc.gpu_tensor([N, H, H, Cin]), dw=nnc.gpu_tensor([C, R, R, Cin]), cdb=nnc.gpu_tensor([C]), mv=T(np.zeros((1, 1, 1, C), np.float32)))
+        gr = nnc.Graph()
+        # a forward batch norm node so that the ReLU-backward fusion can find the bias of the masked activation
+        gr.exec_new(nnc.CMD_BATCH_NORM_FORWARD(1e-4, 0, 0.9), None, 0, [t["y"], t["scale"], t["bias"], t["mv"], t["mv"]], [t["z"], t["mv"], t["mv"], t["mean"], t["istd"]])
+        if relu:
+            gr.exec_new(nnc.CMD_RELU_BACKWARD(), None, 0, [t["g"], None, t["z"]], [t["g"]])
+        bn_in = [t["g"]] + [None] * 4 + [t["y"], t["scale"]] + [None] * 6 + [t["mean"], t["istd"]]
+        gr.exec_new(nnc.CMD_BATCH_NORM_BACKWARD(1e-4, 0, 0.9), None, 0, bn_in, [t["dx"], t["dscale"], t["dbias"]])
+        gr.exec_new(nnc.CMD_CONVOLUTION_BACKWARD(1, C, R, R, Cin), nnc.hint((1, 1), (0, 0)), 0, [t["dx"], t["x"], t["w"]], [t["h"], t["dw"], t["cdb"]])
+        if fuse:
+            gr.fuse()
+            kinds = [k for _, k, _, _ in gr.nodes()]
+            assert (2 in kinds) if relu else (8 in kinds), kinds
+        assert gr.run(stream) == 0
+        stream.wait()
+        res = {k: t[k].download() for k in ("dx", "dw", "cdb", "h", "dscale", "dbias")}
+        for v in t.values():
+            v.free()
+        gr.free()
+        return res
+
+    a, b = run(False), run(True)
+    for k in ("dx", "dw", "h", "dscale", "dbias"):
+        assert_close(b[k], a[k], 1e-5, k)
+    bound = 1e-5 * np.abs(a["dx"]).reshape(-1, C).sum(axis=0).max()
+    assert np.abs(b["cdb"] - a["cdb"]).max() <= bound, (np.abs(b["cdb"] - a["cdb"]).max(), bound)
+    stream.free()
