@@ -331,16 +331,63 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	if (!is_f32(inputs[0]) || !is_f32(inputs[1]) || !is_f32(outputs[0]) || (bias_t && (!is_f32(bias_t) || CCV_IS_TENSOR_VIEW(bias_t))))
 		return CCV_NNC_EXEC_INVALID;
 	ConvGeom g;
-	if (!conv_geom(cmd, hint, view_of(inputs[0]), view_of(inputs[1]), view_of(outputs[0]), g))
-		return CCV_NNC_EXEC_INVALID;
-	if (bias_t && bias_t->info.dim[0] != g.K)
-		return CCV_NNC_EXEC_INVALID;
 	const int groups = cmd.info.convolution.groups > 0 ? cmd.info.convolution.groups : 1;
 	cudaStream_t s = stream_of(stream_context);
 	const float* a = inputs[0]->data.f32;
 	const float* w = inputs[1]->data.f32;
 	const float* bias = bias_t ? bias_t->data.f32 : 0;
 	float* b = outputs[0]->data.f32;
+	float* nchw_out = 0; // NCHW call: the NHWC result is staged here and transposed back at the end
+	TV ta = view_of(inputs[0]), tw = view_of(inputs[1]), tb = view_of(outputs[0]);
+	if (ta.format == CCV_TENSOR_FORMAT_NCHW && tb.format == CCV_TENSOR_FORMAT_NCHW)
+	{
+		// NCHW activations [N, C, H, W] and filters [K, C / g, kh, kw] (convolution/ccv_nnc_conv_cpu_ref.c:66-120): the kernels are
+		// NHWC, so x and w are re-laid out into the stream workspace (two strided copies), the convolution runs there and the
+		// result is transposed back.  Forward only, like CPU_REF (its backward is NHWC-only, :358).
+		if (ta.nd != 4 || tb.nd != 4 || tw.nd != 4 || !ta.contiguous || !tb.contiguous || !tw.contiguous)
+			return CCV_NNC_EXEC_INVALID;
+		const int N = ta.dim[0], C = ta.dim[1], H = ta.dim[2], W = ta.dim[3], K = tb.dim[1], P = tb.dim[2], Q = tb.dim[3], Cg = tw.dim[1], R = tw.dim[2], S = tw.dim[3];
+		if (tb.dim[0] != N || tw.dim[0] != K)
+			return CCV_NNC_EXEC_INVALID;
+		const size_t nx = ta.count, nw = tw.count, ny = tb.count;
+		float* const ws = (float*)ccv_nnc_stream_context_get_workspace(stream_context, (nx + nw + ny) * sizeof(float) + 1024, CCV_TENSOR_GPU_MEMORY);
+		if (!ws)
+			return CCV_NNC_EXEC_OOM;
+		float* const xh = ws;
+		float* const wh = (float*)(((uintptr_t)(xh + nx) + 255) & ~(uintptr_t)255);
+		float* const yh = (float*)(((uintptr_t)(wh + nw) + 255) & ~(uintptr_t)255);
+		const int xd[4] = { N, H, W, C }, xs[4] = { C * H * W, W, 1, H * W }, xt[4] = { H * W * C, W * C, C, 1 };
+		const int wd[4] = { K, R, S, Cg }, wsrc[4] = { Cg * R * S, S, 1, R * S }, wdst[4] = { R * S * Cg, S * Cg, Cg, 1 };
+		RC(copy_strided(s, a, xs, xh, xt, xd, 4));
+		RC(copy_strided(s, w, wsrc, wh, wdst, wd, 4));
+		memset(&ta, 0, sizeof(ta)), memset(&tw, 0, sizeof(tw)), memset(&tb, 0, sizeof(tb));
+		ta.nd = tw.nd = tb.nd = 4, ta.format = tw.format = tb.format = CCV_TENSOR_FORMAT_NHWC, ta.contiguous = tw.contiguous = tb.contiguous = 1;
+		const int yd[4] = { N, P, Q, K };
+		for (int i = 3, px = 1, pw = 1, py = 1; i >= 0; i--)
+		{
+			ta.dim[i] = xd[i], ta.stride[i] = px, px *= xd[i];
+			tw.dim[i] = wd[i], tw.stride[i] = pw, pw *= wd[i];
+			tb.dim[i] = yd[i], tb.stride[i] = py, py *= yd[i];
+		}
+		ta.count = nx, tw.count = nw, tb.count = ny;
+		a = xh, w = wh, b = yh, nchw_out = outputs[0]->data.f32;
+	}
+	if (!conv_geom(cmd, hint, ta, tw, tb, g))
+		return CCV_NNC_EXEC_INVALID;
+	if (bias_t && bias_t->info.dim[0] != g.K)
+		return CCV_NNC_EXEC_INVALID;
+	if (nchw_out)
+	{
+		// the staged convolution, then [N, P, Q, K] -> [N, K, P, Q]
+		int rc = groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA ? conv_fprop_tf32(s, g, a, w, bias, b) : 1;
+		if (rc < 0)
+			return CCV_NNC_EXEC_INVALID;
+		if (rc > 0)
+			RC(conv_fprop_ffma(s, g, groups, a, w, bias, b));
+		const int yd[4] = { g.N, g.K, g.P, g.Q }, ysrc[4] = { g.P * g.Q * g.K, 1, g.Q * g.K, g.K }, ydst[4] = { g.K * g.P * g.Q, g.P * g.Q, g.Q, 1 };
+		RC(copy_strided(s, b, ysrc, nchw_out, ydst, yd, 4));
+		return CCV_NNC_EXEC_SUCCESS;
+	}
 	if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
 	{
 		int rc = conv_fprop_tf32(s, g, a, w, bias, b);
@@ -1348,7 +1395,7 @@ extern "C" int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_
 
 REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_forw); registry->autotune = autotune_contraction<exec_gemm_forw>; }
 REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); registry->autotune = autotune_contraction<exec_gemm_back>; }
-REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); registry->autotune = autotune_contraction<exec_conv_forw>; }
+REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); registry->autotune = autotune_contraction<exec_conv_forw>; }
 REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); registry->autotune = autotune_contraction<exec_conv_back>; }
 REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_forw); }
 REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_back); }

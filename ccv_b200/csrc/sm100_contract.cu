@@ -276,22 +276,55 @@ static void init_params(UmmaGemmParams& p)
 
 static int pick_splits(long long tiles, int k_iters, int min_iters_per_split)
 {
-	// aim for ~2 CTAs per SM in flight; never split finer than `min_iters_per_split` k-iterations
-	const long long target = 2ll * num_sms();
-	if (tiles >= target)
+	// Split-K factor against wave quantisation.  Model: `tiles * s` work items of size 1 / s run in rounds of one per SM, so the
+	// launch costs ceil(tiles * s / SMs) / s tile-times.  5 tiles -> s = 59 (295 CTAs, one wave of 2 CTAs per SM; s = 60 would
+	// spill 4 CTAs into a second wave and double the time, profiles/r01_ncu_wgrad_taps64.txt); 196 tiles (7 x 7 layers, N = 512)
+	// -> s = 3 (588 items, 3.97 rounds of thirds instead of 2 rounds of which the second is 1/3 full).  When the tiles already fill
+	// the machine a split is only taken if it buys more than 20 % (partial tiles cost a zero-fill, red.add traffic and the fused
+	// batch-norm statistics of the epilogue), never finer than `min_iters_per_split`.
+	const long long sms = num_sms();
+	long long max_s = k_iters / min_iters_per_split;
+	if (max_s < 1)
+		max_s = 1;
+	if (tiles >= 4 * sms || max_s == 1)
 		return 1;
-	// floor, not ceil: tiles * splits must fit in ONE wave of 2 CTAs per SM -- 5 tiles x 60 splits = 300 CTAs on 296 slots ran a
-	// second wave of 4 CTAs and doubled the kernel time (profiles/r01_ncu_wgrad_taps64.txt)
-	long long s = target / tiles;
-	const long long max_s = k_iters / min_iters_per_split;
-	if (s > max_s)
-		s = max_s;
-	if (s < 1)
-		s = 1;
-	// no empty splits: per = ceil(k/s) must leave the last split non-empty
-	while (s > 1 && (long long)((k_iters + s - 1) / s) * (s - 1) >= k_iters)
-		s--;
-	return (int)s;
+	if (tiles < sms)
+	{
+		// fewer tiles than SMs: one wave of two co-resident CTAs per SM (the one-tile kernels overlap each other's epilogue)
+		long long k = 2 * sms / (tiles > 0 ? tiles : 1);
+		if (k > max_s)
+			k = max_s;
+		while (k > 1 && (long long)((k_iters + k - 1) / k) * (k - 1) >= k_iters)
+			k--;
+		return (int)(k < 1 ? 1 : k);
+	}
+	long long limit = 2 * sms / (tiles > 0 ? tiles : 1);
+	if (limit < 4)
+		limit = 4;
+	if (limit > max_s)
+		limit = max_s;
+	double best_cost = 1e30;
+	for (long long k = 1; k <= limit; k++)
+	{
+		const double cost = (double)((tiles * k + sms - 1) / sms) / (double)k;
+		if (cost < best_cost)
+			best_cost = cost;
+	}
+	const double unsplit = (double)((tiles + sms - 1) / sms);
+	if (tiles >= sms && best_cost > unsplit * 0.8)
+		return 1;
+	for (long long k = 1; k <= limit; k++)
+	{
+		const double cost = (double)((tiles * k + sms - 1) / sms) / (double)k;
+		if (cost <= best_cost * 1.05)
+		{
+			// no empty splits: per = ceil(k_iters / k) must leave the last split non-empty
+			while (k > 1 && (long long)((k_iters + k - 1) / k) * (k - 1) >= k_iters)
+				k--;
+			return (int)k;
+		}
+	}
+	return 1;
 }
 
 int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long long lda, int trans_a, const float* b, long long ldb, int trans_b, float* c, long long ldc, const float* bias, int accumulate)

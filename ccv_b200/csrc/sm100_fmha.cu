@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 	uint32_t* tmem_slot = (uint32_t*)(bars + 15);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int q0 = blockIdx.x * FM_BLOCK;
+	// causal: the last query tiles see the most keys; issue them first so the tail of the launch is made of short tiles
+	const int q_tile = (CL == 1 && p.causal) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+	const int q0 = q_tile * FM_BLOCK;
 	const int h = blockIdx.y, b = blockIdx.z;
 	const int hk = h / (p.H / p.Hk);
 	// keys this tile attends: causal is aligned to the bottom-right corner (query i sees keys <= i + Sk - Sq)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from ccv_b200 import abi
-from tests.util import NHWC, assert_close, gpu_exec, ref_exec, seeded
+from tests.util import NCHW, NHWC, assert_close, gpu_exec, ref_exec, seeded
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = {abi.CCV_NNC_SM100_ALGO_TF32: 1e-3, abi.CCV_NNC_SM100_ALGO_FFMA: 1e-5}
@@ -242,3 +242,21 @@ def test_autotune_picks_a_working_algorithm(gpu):
     stream.wait()
     for t in (a, w, b, x, f, y, stream):
         t.free()
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("N,C,H,K,R,st,groups", [(2, 32, 12, 64, 3, 1, 1), (3, 16, 9, 24, 3, 2, 1), (2, 16, 10, 24, 3, 1, 4)])
+def test_convolution_forward_nchw(gpu, ref, N, C, H, K, R, st, groups):
+    """NCHW activations [N, C, H, W] and filters [K, C / g, kh, kw] (convolution/ccv_nnc_conv_cpu_ref.c:66-120; protocol of the NCHW
+    cases of test/int/nnc/cudnn.tests.c): staged through NHWC on the device, compared with CPU_REF's own NCHW path."""
+    nnc = gpu
+    pad = R // 2
+    P = (H + 2 * pad - R) // st + 1
+    x, w, bias = seeded((N, C, H, H), 1, -1, 1), seeded((K, C // groups, R, R), 2, -1, 1) / (R * R * C) ** 0.5, seeded((K,), 3, -1, 1)
+    cmd = nnc.CMD_CONVOLUTION_FORWARD(groups, K, R, R, C)
+    hint = nnc.hint((st, st), (pad, pad))
+    fmts = dict(in_fmts=[NCHW, NCHW, NHWC], out_fmts=[NCHW])
+    st_r, (y_r,) = ref_exec(ref, cmd, hint, 0, [x, w, bias], [np.zeros((N, K, P, P), np.float32)], **fmts)
+    st_g, (y_g,) = gpu_exec(nnc, cmd, hint, 0, [x, w, bias], [np.zeros((N, K, P, P), np.float32)], **fmts)
+    assert st_r == 0 and st_g == 0
+    assert_close(y_g, y_r, 1e-3, "NCHW convolution")
