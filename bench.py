@@ -235,12 +235,33 @@ def main():
     ms = timed(step, args.steps)
     ms_per_step = ms / args.steps
 
+    # end to end: every step copies its batch from pinned host memory and reads the loss back, through the same public calls
+    # (CMD_DATA_TRANSFER on stream contexts).  The copy of batch k+1 runs on a second stream context while step k computes
+    # (stream signals order the two: lib/nnc/ccv_nnc.h:1041-1053); the compute stream then only does a device-to-device move of
+    # the staged batch into the network's input tensor.  Steady state: one host-to-device copy and one loss read per step, all
+    # inside the timed region; the first batch is staged before the clock starts, the prefetch of one extra batch is inside it.
+    copy_stream = nnc.Stream(device)
+    stage_in = nnc.gpu_tensor([args.batch, args.image, args.image, 3], device=device)
+    stage_lab = nnc.gpu_tensor([args.batch], datatype=nnc.CCV_32S, device=device)
+    staged, consumed = nnc.Signal(device), nnc.Signal(device)
+
+    def prefetch():
+        consumed.wait(copy_stream)  # the previous staged batch has been moved into the network input
+        nnc.cmd_exec(xfer, None, 0, [host_in, host_lab], [stage_in, stage_lab], copy_stream)
+        staged.emit(copy_stream)
+
     def e2e_step():
-        nnc.cmd_exec(xfer, None, 0, [host_in, host_lab], [net.input, net.labels], stream)
+        staged.wait(stream)
+        nnc.cmd_exec(xfer, None, 0, [stage_in, stage_lab], [net.input, net.labels], stream)
+        consumed.emit(stream)
+        prefetch()  # next batch: overlaps this step's compute
         step()
         nnc.cmd_exec(xfer, None, 0, [net.loss], [host_loss], stream)
+    consumed.emit(stream)
+    prefetch()
     e2e_step()
     e2e_ms = timed(e2e_step, args.steps) / args.steps
+    copy_stream.wait()
     sampler.stop_flag = True
     sampler.join()
     loss = float(np.mean(host_loss.download()))
@@ -252,7 +273,8 @@ def main():
            "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c:17-95) fp32 NHWC, per-GPU batch %d, %dx%d, fwd+bwd + nesterov SGD%s" % (args.batch, args.image, args.image, ", one COMM_ALLREDUCE command (NCCL sum) over the flat fp32 gradient buffer" if world > 1 else ""),
                       "global_batch": images_per_step, "parallelism": "dp%d" % world, "tensor_core_math": "tcgen05 kind::tf32, fp32 accumulate (TMA rounds operands to TF32)",
                       "cuda_graph": use_graph, "fused_pairs": n_fused, "first_step_loss": first_loss, "l2": "activations per step (>20 GB) exceed the 126 MB L2: no flush needed", "mean_loss": loss},
-           "e2e": {"value": images_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes + host_lab.nbytes), "d2h_bytes_per_step": int(host_loss.nbytes), "ms_per_step": e2e_ms},
+           "e2e": {"value": images_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes + host_lab.nbytes), "d2h_bytes_per_step": int(host_loss.nbytes), "ms_per_step": e2e_ms,
+                   "pipeline": "batch k+1 is copied host->device on a second stream context while step k computes (stream signals); one pinned-host copy + one loss read per step inside the timed region"},
            "gpu_launches": int(launches_per_step * (args.steps * 2 + args.warmup + 2)), "gpu_launches_per_step": int(launches_per_step), "clocks": sampler.summary()}
 
     if rank == 0:

@@ -473,6 +473,56 @@ int ccv_nnc_device_count(const int type)
 	return count;
 }
 
+// lib/nnc/ccv_nnc.h:1022-1064 / lib/nnc/ccv_nnc_stream.c: stream signals = CUDA events (no timing) that one stream emits and
+// another waits for, without blocking the host -- how the reference's graph runner orders work across streams.
+struct ccv_nnc_stream_signal_s {
+	int type;
+	cudaEvent_t event;
+	ccv_nnc_stream_context_t* emitter;
+};
+
+ccv_nnc_stream_signal_t* ccv_nnc_stream_signal_new(const int type)
+{
+	ccv_nnc_stream_signal_t* const signal = (ccv_nnc_stream_signal_t*)calloc(1, sizeof(ccv_nnc_stream_signal_t));
+	signal->type = type;
+	if (CCV_STREAM_GET_CONTEXT(type) == CCV_STREAM_CONTEXT_GPU)
+	{
+		cudaSetDevice(CCV_STREAM_GET_DEVICE_ID(type));
+		if (cudaEventCreateWithFlags(&signal->event, cudaEventDisableTiming) != cudaSuccess)
+		{
+			free(signal);
+			return 0;
+		}
+	}
+	return signal;
+}
+
+int ccv_nnc_stream_signal_type(const ccv_nnc_stream_signal_t* const signal) { return signal->type; }
+
+void ccv_nnc_stream_context_emit_signal(ccv_nnc_stream_context_t* const stream, ccv_nnc_stream_signal_t* const signal)
+{
+	signal->emitter = stream;
+	if (signal->event)
+		cudaEventRecord(signal->event, (cudaStream_t)ccv_nnc_stream_context_get_stream(stream));
+}
+
+void ccv_nnc_stream_context_wait_signal(const ccv_nnc_stream_context_t* const stream, const ccv_nnc_stream_signal_t* const signal)
+{
+	if (signal->event)
+		cudaStreamWaitEvent((cudaStream_t)ccv_nnc_stream_context_get_stream(stream), signal->event, 0);
+}
+
+ccv_nnc_stream_context_t* ccv_nnc_stream_signal_get_emitter(const ccv_nnc_stream_signal_t* const signal) { return signal->emitter; }
+
+void ccv_nnc_stream_signal_free(ccv_nnc_stream_signal_t* const signal)
+{
+	if (!signal)
+		return;
+	if (signal->event)
+		cudaEventDestroy(signal->event);
+	free(signal);
+}
+
 void ccv_nnc_stream_context_set_neighbor_discovery(ccv_nnc_stream_context_t* const stream_context, ccv_nnc_stream_context_neighbor_discovery_f discovery, void* const context)
 {
 	stream_context->neighbor_discovery = discovery;

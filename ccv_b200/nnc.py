@@ -77,6 +77,11 @@ def lib():
         l.ccv_nnc_sm100_graph_replay.restype = i32
         l.ccv_nnc_sm100_graph_replay.argtypes = [vp, i32, vp]
         l.ccv_nnc_sm100_graph_free.argtypes = [vp]
+        l.ccv_nnc_stream_signal_new.restype = vp
+        l.ccv_nnc_stream_signal_new.argtypes = [i32]
+        l.ccv_nnc_stream_context_emit_signal.argtypes = [vp, vp]
+        l.ccv_nnc_stream_context_wait_signal.argtypes = [vp, vp]
+        l.ccv_nnc_stream_signal_free.argtypes = [vp]
         l.ccv_nnc_sm100_cmd_autotune.restype = None
         l.ccv_nnc_sm100_cmd_autotune.argtypes = [u32, C.POINTER(abi.CmdParam), C.POINTER(abi.Hint), i32, C.POINTER(vp), i32, C.POINTER(vp), i32, vp, C.POINTER(i32)]
         l.ccv_nnc_sm100_comm_unique_id.restype = i32
@@ -207,6 +212,26 @@ class Stream(object):
     def free(self):
         if self.ptr:
             lib().ccv_nnc_stream_context_free(self.ptr)
+            self.ptr = None
+
+
+class Signal(object):
+    """ccv_nnc_stream_signal_t (lib/nnc/ccv_nnc.h:1022-1064): emitted on one stream, waited for on another."""
+
+    def __init__(self, device=0):
+        self.ptr = lib().ccv_nnc_stream_signal_new(abi.CCV_STREAM_CONTEXT_GPU | (device << 8))
+        if not self.ptr:
+            raise RuntimeError("ccv_nnc_stream_signal_new failed")
+
+    def emit(self, stream):
+        lib().ccv_nnc_stream_context_emit_signal(stream.ptr, self.ptr)
+
+    def wait(self, stream):
+        lib().ccv_nnc_stream_context_wait_signal(stream.ptr, self.ptr)
+
+    def free(self):
+        if self.ptr:
+            lib().ccv_nnc_stream_signal_free(self.ptr)
             self.ptr = None
 
 

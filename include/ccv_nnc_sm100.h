@@ -463,6 +463,14 @@ void ccv_nnc_stream_context_drain(ccv_nnc_stream_context_t* const stream_context
 void ccv_nnc_stream_context_wait(const ccv_nnc_stream_context_t* const stream_context);
 void ccv_nnc_stream_context_free(ccv_nnc_stream_context_t* const stream_context);
 int ccv_nnc_device_count(const int type);
+/* lib/nnc/ccv_nnc.h:1022-1064: a signal is emitted on one stream and waited for on another (device-side ordering, no host block) */
+typedef struct ccv_nnc_stream_signal_s ccv_nnc_stream_signal_t;
+ccv_nnc_stream_signal_t* ccv_nnc_stream_signal_new(const int type);
+int ccv_nnc_stream_signal_type(const ccv_nnc_stream_signal_t* const signal);
+void ccv_nnc_stream_context_emit_signal(ccv_nnc_stream_context_t* const stream, ccv_nnc_stream_signal_t* const signal);
+void ccv_nnc_stream_context_wait_signal(const ccv_nnc_stream_context_t* const stream, const ccv_nnc_stream_signal_t* const signal);
+ccv_nnc_stream_context_t* ccv_nnc_stream_signal_get_emitter(const ccv_nnc_stream_signal_t* const signal);
+void ccv_nnc_stream_signal_free(ccv_nnc_stream_signal_t* const signal);
 typedef ccv_nnc_stream_context_t*(*ccv_nnc_stream_context_neighbor_discovery_f)(const int device_id, void* const context);
 void ccv_nnc_stream_context_set_neighbor_discovery(ccv_nnc_stream_context_t* const stream_context, ccv_nnc_stream_context_neighbor_discovery_f discovery, void* const context);
 ccv_nnc_stream_context_t* ccv_nnc_stream_context_find_neighbor(ccv_nnc_stream_context_t* const stream_context, const int device_id);

@@ -143,3 +143,25 @@ def test_two_rank_allreduce_and_data_parallel_step(gpu, tmp_path):
     for rank, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, "rank %d failed:\n%s" % (rank, out[-3000:])
         assert "rank %d ok" % rank in out
+
+
+def test_stream_signals_order_two_stream_contexts(gpu):
+    """ccv_nnc_stream_context_emit_signal / wait_signal (lib/nnc/ccv_nnc.h:1041-1053): work on stream B that waits for a signal emitted
+    on stream A sees everything A enqueued before the emit (the mechanism bench.py's end-to-end leg uses to prefetch the next
+    batch on a copy stream)."""
+    nnc = gpu
+    a_stream, b_stream = nnc.Stream(0), nnc.Stream(0)
+    sig = nnc.Signal(0)
+    n = 1 << 24
+    src, dst = nnc.gpu_tensor([n]), nnc.gpu_tensor([n])
+    dst.upload(np.zeros(n, np.float32))
+    for value in (3.0, 7.0):
+        assert nnc.cmd_exec(nnc.CMD_SET_FORWARD(value), None, 0, [], [src], a_stream) == 0   # a long enough fill on A
+        sig.emit(a_stream)
+        sig.wait(b_stream)
+        assert nnc.cmd_exec(nnc.CMD_DATA_TRANSFER_FORWARD(), None, 0, [src], [dst], b_stream) == 0
+        b_stream.wait()
+        assert np.all(dst.download() == value)
+        a_stream.wait()
+    for t in (src, dst, sig, a_stream, b_stream):
+        t.free()
