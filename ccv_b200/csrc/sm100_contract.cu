@@ -55,15 +55,17 @@ static bool tma_api_init()
 }
 
 // fp32 2-D row-major [rows, cols] with row pitch `ld` elements; box = {box_cols (<= 32), box_rows}
-static bool make_map_2d(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool mn_major = false)
+static bool make_map_2d(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool mn_major = false, int dtype = -1)
 {
+	if (dtype < 0)
+		dtype = g_tma_dtype;
 	if ((((uintptr_t)ptr) & 15) || ((ld * 4) & 15) || ld * 4 >= (1ll << 40))
 		return false;
 	cuuint64_t dims[2] = { (cuuint64_t)cols, (cuuint64_t)rows };
 	cuuint64_t strides[1] = { (cuuint64_t)ld * 4 };
 	cuuint32_t box[2] = { (cuuint32_t)box_cols, (cuuint32_t)box_rows };
 	cuuint32_t estr[2] = { 1, 1 };
-	CUresult r = g_encode_tiled(map, (CUtensorMapDataType)g_tma_dtype, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	CUresult r = g_encode_tiled(map, (CUtensorMapDataType)dtype, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	return r == CUDA_SUCCESS;
 }
 
@@ -187,7 +189,19 @@ static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, c
 			*r.rows_out = grid;
 		}
 	}
-	kern<<<grid, S::THREADS, S::TOTAL, stream>>>(tmA, tmB, q);
+	// TMA tile stores for the plain "write the tile" epilogue (dense row-major output, no split-K, no accumulate)
+	CUtensorMap tmC = tmA;
+	static int tma_store_enabled = -1;
+	if (tma_store_enabled < 0)
+	{
+		const char* e = getenv("CCV_NNC_SM100_TMA_STORE");
+		tma_store_enabled = e ? atoi(e) : 1;
+	}
+	q.tma_store = 0;
+	if (tma_store_enabled && p.splits == 1 && p.grid_taps == 1 && !p.accumulate && p.rowmap.mode == 0 && p.N % 4 == 0 && (!p.bias || (((uintptr_t)p.bias) & 15) == 0) &&
+		make_map_2d(&tmC, p.out, p.M, p.N, p.rowmap.ld, 32, 32, false, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
+		q.tma_store = 1;
+	kern<<<grid, S::THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, q);
 	count_launch();
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess)
@@ -230,7 +244,7 @@ static int launch_umma_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUt
 	{
 		const bool long_k = iters_per_tile >= 12;
 		if (bn == 64)
-			return launch_umma_persistent<AMODE, BMODE, 64, 7, 8>(stream, tmA, tmB, p);
+			return launch_umma_persistent<AMODE, BMODE, 64, 6, 8>(stream, tmA, tmB, p);
 		if (bn == 256)
 			return long_k ? launch_umma_persistent<AMODE, BMODE, 256, 4, 4>(stream, tmA, tmB, p) : launch_umma_persistent<AMODE, BMODE, 256, 3, 8>(stream, tmA, tmB, p);
 		return long_k ? launch_umma_persistent<AMODE, BMODE, 128, 6, 4>(stream, tmA, tmB, p) : launch_umma_persistent<AMODE, BMODE, 128, 5, 8>(stream, tmA, tmB, p);

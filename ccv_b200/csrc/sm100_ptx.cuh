@@ -89,6 +89,26 @@ __device__ __forceinline__ void tma_load_4d_multicast(void* dst, const CUtensorM
 		"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
 		: "memory");
 }
+// shared -> global tile store (bulk async group): the box at smem `src` is written at tensor coordinates (c0, c1); rows / columns
+// outside the tensor are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* desc, const void* src, int c0, int c1)
+{
+	asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group()
+{
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read()
+{
+	asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group()
+{
+	asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 // im2col mode over an NHWC tensor {C, W, H, N}: loads `pixelsPerColumn` pixels x `channelsPerPixel` channels,
 // walking base pixels from (w, h, n) through the descriptor's bounding box; (off_w, off_h) is the filter-tap offset.
 __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* desc, uint64_t* bar, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h)

@@ -57,6 +57,7 @@ struct UmmaGemmParams {
 	// optional per-column statistics of the output (batch-norm forward fused into the producing convolution; persistent kernel
 	// only): stats + blockIdx.x * 2 * N receives sum(v) in [0, N) and sum(v * v) in [N, 2N) over the rows this CTA wrote
 	float* stats;
+	int tma_store; // persistent kernel: the epilogue writes 32 x 32 chunks with TMA tile stores through the output tensor map
 	uint32_t idesc;
 	// smem descriptor fields for MN-major operands (layout SWIZZLE_128B_BASE32B: 128 B of MN x 4 k-rows per atom)
 	uint32_t mn_lbo, mn_sbo, mn_layout;

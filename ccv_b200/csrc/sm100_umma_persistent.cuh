@@ -21,14 +21,15 @@ struct UmmaPersistentSmem {
 	static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
 	static constexpr int EPI_PITCH = 36;                       // floats per scratch row: 16-byte aligned, bank-shifted
 	static constexpr int EPI_WARPS = EPIW; // 4: one warp per TMEM lane quarter; 8: two, each taking every other 32-column chunk
-	static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4; // one 32 x 32 chunk per epilogue warp
+	static constexpr int EPI_WARP_BYTES = 8192;                // per epilogue warp: two 4 KB chunk buffers (TMA-store path) / one pitch-36 chunk
+	static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
 	static constexpr int THREADS = 64 + EPI_WARPS * 32;
 	static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
 	static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
 template <int AMODE, int BMODE, int BN, int STAGES, int EPIW>
-__global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaGemmParams p)
+__global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const UmmaGemmParams p)
 {
 	using S = UmmaPersistentSmem<BN, STAGES, EPIW>;
 	extern __shared__ uint8_t smem_raw[];
@@ -179,7 +180,9 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 		// ------------------------------------------------------------------ epilogue (warps 2..9)
 		const int quarter = warp & 3;        // TMEM lanes [32 * quarter, +32) are the ones this warp may read
 		const int half = (warp - 2) >> 2;    // which of the EPIW / 4 warps of this quarter: chunks half, half + EPIW / 4, ...
-		float* const scratch = reinterpret_cast<float*>(smem + S::EPI_OFFSET) + (warp - 2) * 32 * S::EPI_PITCH;
+		float* const scratch = reinterpret_cast<float*>(smem + S::EPI_OFFSET + (warp - 2) * S::EPI_WARP_BYTES);
+		const bool tma_store = p.tma_store != 0;
+		int chunk_no = 0;
 		const int sub_row = lane >> 3;       // 0..3: row within a group of 4 rows
 		const int sub_col = (lane & 7) * 4;  // 0..28: first of this lane's 4 columns
 		const bool use_atomic = p.splits > 1;
@@ -234,6 +237,67 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 #pragma unroll
 					for (int i = 0; i < 32; i++)
 						r[i] = 0;
+				}
+				if (tma_store)
+				{
+					// lane = row.  The 32 x 32 chunk goes (+bias) into one of this warp's two 4 KB buffers in the 128-byte-swizzled
+					// layout the output tensor map expects and leaves as ONE TMA tile store: ~60 instructions per chunk instead of
+					// ~400 (LDS / address checks / STG per row: the epilogue was issue-bound, profiles/r01_ncu_expand_1x1_*.txt)
+					float* const buf = scratch + (chunk_no & 1) * 1024;
+					chunk_no++;
+					if (lane == 0)
+						bulk_wait_group_read<1>(); // the store issued two chunks ago has finished reading this buffer
+					__syncwarp();
+					const int col0 = n0 + c * 32;
+					const bool row_ok = m0 + quarter * 32 + lane < p.M;
+					float v[32];
+#pragma unroll
+					for (int i = 0; i < 32; i++)
+						v[i] = __uint_as_float(r[i]);
+					if (add_bias)
+					{
+#pragma unroll
+						for (int i = 0; i < 32; i += 4)
+							if (col0 + i < N)
+							{
+								const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+								v[i] += b4.x, v[i + 1] += b4.y, v[i + 2] += b4.z, v[i + 3] += b4.w;
+							}
+					}
+					if (stats && !row_ok)
+					{
+#pragma unroll
+						for (int i = 0; i < 32; i++)
+							v[i] = 0.f; // rows past M are clipped by the store but must not count in the statistics
+					}
+#pragma unroll
+					for (int j = 0; j < 8; j++)
+						*reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					fence_proxy_async();
+					__syncwarp();
+					if (stats)
+					{
+						// lane = column: sum the 32 staged rows of this column (all lanes read the same 128-byte row: no bank conflict)
+						float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+						for (int rr = 0; rr < 32; rr++)
+						{
+							const float x = buf[rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3)];
+							s1 += x;
+							s2 = fmaf(x, x, s2);
+						}
+						if (col0 + lane < N)
+						{
+							atomicAdd(stats + col0 + lane, s1);
+							atomicAdd(stats + N + col0 + lane, s2);
+						}
+					}
+					if (lane == 0 && col0 < N)
+					{
+						tma_store_2d(&tmC, buf, col0, m0 + quarter * 32);
+						bulk_commit_group();
+					}
+					continue;
 				}
 				// lane = row: park the row in the scratch tile, then re-read it as (4 rows x 8 lanes x 16 bytes)
 				__syncwarp();
@@ -314,6 +378,8 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 			if (lane == 0)
 				mbar_arrive(&tmem_empty_bar[acc]);
 		}
+		if (tma_store && lane == 0)
+			bulk_wait_group<0>(); // every tile store of this warp has been written out before the CTA exits
 	}
 	tc_fence_before();
 	__syncthreads();
