@@ -242,7 +242,15 @@ static int launch_umma_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUt
 		persistent = false; // bn = 64: only forward-shaped work (K-major B, no split-K) gains from the persistent kernel (r01_probe5)
 	if (persistent)
 	{
-		const bool long_k = iters_per_tile >= 12;
+		bool long_k = iters_per_tile >= 12;
+		static int force_long_k = -2;
+		if (force_long_k == -2)
+		{
+			const char* e = getenv("CCV_NNC_SM100_LONGK"); // A/B switch: 1 = always 4 epilogue warps + deepest ring, 0 = always 8 + shorter ring
+			force_long_k = e ? atoi(e) : -1;
+		}
+		if (force_long_k >= 0)
+			long_k = force_long_k != 0;
 		if (bn == 64)
 			return launch_umma_persistent<AMODE, BMODE, 64, 6, 8>(stream, tmA, tmB, p);
 		if (bn == 256)
