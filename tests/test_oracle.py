@@ -102,3 +102,43 @@ def test_committed_fixtures_are_what_the_reference_produces(ref):
     b = np.zeros_like(g["b"])
     assert ref_exec(ref, nnc.CMD_GEMM_FORWARD((0, 0), (0, 1)), None, 0, [g["a"], g["w"], g["bias"]], [b])[0] == 0
     assert np.array_equal(b, g["b"])
+
+
+@pytest.mark.ref
+def test_compiled_reference_reproduces_its_closed_form_convolution_cases(ref, port):
+    """test/unit/nnc/forward.tests.c:14-44 ("convolutional network of 11x11 on 225x185 with uniform weights"): all-ones image and
+    filters, stride 4 / border 1 from ccv_nnc_hint_auto -> 363 inside, 330 on the edges, 300 in the corners.  Checked on the
+    compiled reference and on the plain-C restatement."""
+    a, w, bias = np.ones((225, 185, 3), np.float32), np.ones((4, 11, 11, 3), np.float32), np.zeros((4,), np.float32)
+    b = np.zeros((55, 45, 4), np.float32)
+    cmd = nnc.CMD_CONVOLUTION_FORWARD(1, 4, 11, 11, 3)
+    hint = nnc.hint((4, 4), (1, 1))  # what ccv_nnc_hint_auto derives for 225x185 -> 55x45 with an 11x11 window
+    assert ref_exec(ref, cmd, hint, 0, [a, w, bias], [b])[0] == 0
+    want = np.full((55, 45, 4), 363, np.float32)
+    want[0, :], want[-1, :], want[:, 0], want[:, -1] = 330, 330, 330, 330
+    want[0, 0], want[0, -1], want[-1, 0], want[-1, -1] = 300, 300, 300, 300
+    assert np.array_equal(b, want)
+    d = port.conv_desc(1, 225, 185, 3, 4, 11, 11, 4, 1)
+    assert np.array_equal(port.conv_forw(d, a[None], w, bias)[0], want)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("causal", [0, 1])
+def test_compiled_reference_attention_equals_the_composed_graph(ref, causal):
+    """test/unit/nnc/attention.tests.c:14-97: SCALED_DOT_PRODUCT_ATTENTION_FORWARD on CPU_REF equals transpose -> scale -> q k^T ->
+    softmax -> . v (here the composed side is float64 numpy; shapes scaled down from 32 x 128 x 8 x 64 / 96)."""
+    B, S, H, D, Dv = 2, 32, 4, 16, 24
+    q, k, v = seeded((B, S, H, D), 1), seeded((B, S, H, D), 2), seeded((B, S, H, Dv), 3)
+    cmd = nnc._simple(nnc.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD)
+    cmd.info.scaled_dot_product_attention.scale, cmd.info.scaled_dot_product_attention.is_causal = 1.0 / 8, causal
+    o = np.zeros((B, S, H, Dv), np.float32)
+    assert ref_exec(ref, cmd, None, 0, [q, k, v], [o, None])[0] == 0
+    want = np.zeros_like(o, dtype=np.float64)
+    for b in range(B):
+        for h in range(H):
+            s = (q[b, :, h].astype(np.float64) / 8) @ k[b, :, h].astype(np.float64).T
+            if causal:
+                s = np.where(np.arange(S)[None, :] <= np.arange(S)[:, None], s, -np.inf)
+            e = np.exp(s - s.max(axis=1, keepdims=True))
+            want[b, :, h] = (e / e.sum(axis=1, keepdims=True)) @ v[b, :, h].astype(np.float64)
+    assert_close(o, want, 1e-5, "CPU_REF attention vs composed graph")
