@@ -2,12 +2,17 @@
 // sm100_umma_gemm.cuh): one CTA per SM loops over output tiles, so that
 //   * the TMA producer runs ahead across tile boundaries (no pipeline refill, no per-tile barrier init / TMEM alloc),
 //   * accumulators are double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of tile i + 1,
-//   * the epilogue transposes each 32 x 32 accumulator chunk through shared memory and writes it with 128-bit stores in
-//     which every 128-byte line is written whole (4 rows x 128 B per warp instruction) instead of 32 scattered 16-byte
-//     pieces per instruction.
-// Roles: warp 0 TMA producer, warp 1 TMEM allocator + tcgen05.mma issuer, warps 2..9 epilogue (two warps per TMEM lane
-// quarter, each taking every other 32-column chunk: with a single warp per scheduler the epilogue's dependent
-// LDTM -> STS -> LDS -> STG chain was latency-bound -- profiles/r01_ncu_gemm_n256k64.txt).
+//   * the epilogue handles each 32 x 32 accumulator chunk (tcgen05.ld, lane = row) in one of two ways:
+//       - plain "write the tile" (dense row-major output, no split-K / accumulate): the chunk is staged (+bias) in shared memory
+//         in the 128-byte-swizzled layout of the output tensor map and written by ONE TMA tile store; two buffers per warp,
+//         cp.async.bulk.wait_group.read keeps one store in flight (profiles/r01_ncu_expand_1x1_persistent_8epiwarps.txt: the
+//         row-store variant below was instruction-issue-bound);
+//       - otherwise: transposed through a pitch-36 scratch tile and written with 128-bit stores / red.global.add.v4 in which
+//         every 128-byte line is touched whole (4 rows x 128 B per warp instruction);
+//     either way it can also accumulate per-column sum(v), sum(v * v) of what it writes (batch-norm statistics, p.stats).
+// Roles: warp 0 TMA producer, warp 1 TMEM allocator + tcgen05.mma issuer, warps 2.. epilogue (EPIW = 4: one warp per TMEM
+// lane quarter; 8: two, each taking every other 32-column chunk -- with a single warp per scheduler the dependent
+// LDTM -> STS -> LDS -> STG chain was latency-bound, profiles/r01_ncu_gemm_n256k64_persistent_4epiwarps.txt).
 #pragma once
 #include "sm100_umma_gemm.cuh"
 
