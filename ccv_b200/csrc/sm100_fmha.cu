@@ -68,6 +68,21 @@ __device__ __forceinline__ uint32_t pack2(const float a, const float b, const in
 	return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// sm_100 packed / 3-input fp32 instructions: FMNMX3 halves the row-max pass, FFMA2 halves the scale-and-shift in front of the exp2
+// and the running-output update (the softmax warps are issue-limited: profiles/r01_ncu_fmha_bf16_config5.txt)
+__device__ __forceinline__ float max3(const float a, const float b, const float c)
+{
+	float d;
+	asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+	return d;
+}
+__device__ __forceinline__ void fma2(float& d0, float& d1, const float a0, const float a1, const float b0, const float b1, const float c0, const float c1)
+{
+	asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\tfma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+		: "=f"(d0), "=f"(d1)
+		: "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
 template <int CL>
 __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const FmhaParams p)
 {
@@ -280,8 +295,8 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 						mx = fmaxf(mx, __uint_as_float(sr[i]));
 			} else {
 #pragma unroll
-				for (int i = 0; i < 64; i++)
-					mx = fmaxf(mx, __uint_as_float(sr[i]));
+				for (int i = 0; i < 64; i += 2)
+					mx = max3(mx, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
 			}
 			// the other half of this row lives in warp (warp +- 4): exchange the maxima
 			mx_x[(s * 2 + half) * FM_BLOCK + row] = mx;
@@ -297,8 +312,10 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 #pragma unroll
 			for (int i = 0; i < 64; i += 2)
 			{
-				float e0 = ex2_approx(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_use));
-				float e1 = ex2_approx(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_use));
+				float t0, t1;
+				fma2(t0, t1, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]), p.scale_log2, p.scale_log2, -m_use, -m_use);
+				float e0 = ex2_approx(t0);
+				float e1 = ex2_approx(t1);
 				if (edge)
 				{
 					if (kv0 + i >= kv_limit)
@@ -338,8 +355,8 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 				tmem_ld_32x32(to + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
 				tmem_ld_wait();
 #pragma unroll
-				for (int i = 0; i < 64; i++)
-					acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(r[i]));
+				for (int i = 0; i < 64; i += 2)
+					fma2(acc[i], acc[i + 1], acc[i], acc[i + 1], alpha_prev, alpha_prev, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
 				tc_fence_before();
 			}
 			l = fmaf(l, alpha, sum);
@@ -356,8 +373,8 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 			tmem_ld_32x32(to + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
 			tmem_ld_wait();
 #pragma unroll
-			for (int i = 0; i < 64; i++)
-				acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(r[i]));
+			for (int i = 0; i < 64; i += 2)
+				fma2(acc[i], acc[i + 1], acc[i], acc[i + 1], alpha_prev, alpha_prev, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
 		}
 		// the row sum is the sum of the two halves' partial sums (same running max on both sides)
 		mx_x[(4 + half) * FM_BLOCK + row] = l;
