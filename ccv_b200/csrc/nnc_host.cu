@@ -173,14 +173,28 @@ int ccv_nnc_cmd_exec(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const i
 	auto it = g_registry.find(cmd.cmd);
 	if (it == g_registry.end() || !it->second.exec)
 		return CCV_NNC_EXEC_NO_KERNEL;
+	// a backend named explicitly is still held to its registered tensor memory (ccv_nnc_cmd_find_backend does the same test,
+	// ccv_nnc_cmd.c:307-328): host tensors never reach a device kernel, except through the transfer commands that register both
+	int memory = 0;
+	for (int i = 0; i < input_size; i++)
+		if (inputs[i])
+			memory |= CCV_TENSOR_GET_MEMORY(inputs[i]->info.type);
+	for (int i = 0; i < output_size; i++)
+		if (outputs[i])
+			memory |= CCV_TENSOR_GET_MEMORY(outputs[i]->info.type);
+	if ((it->second.tensor_memory & memory) != memory)
+		return CCV_NNC_EXEC_NO_KERNEL;
 	const int ret = it->second.exec(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 	if (!stream_context)
 	{
 		// the synchronous form: results are visible (and the per-thread workspace released) on return
 		const int device = device_of(inputs, input_size, outputs, output_size);
-		ccv_nnc_stream_context_t* const s = default_stream(device);
-		ccv_nnc_stream_context_wait(s);
-		ccv_nnc_stream_context_drain(s);
+		if (device >= 0)
+		{
+			ccv_nnc_stream_context_t* const s = default_stream(device);
+			ccv_nnc_stream_context_wait(s);
+			ccv_nnc_stream_context_drain(s);
+		}
 	}
 	return ret;
 }

@@ -76,3 +76,17 @@ def test_fuse_leaves_unrelated_and_dependent_nodes_alone():
     assert g.fuse() == 0
     assert [k for _, k, _, _ in g.nodes()] == [0, 0, 0, 0]
     g.free()
+
+
+def test_comm_plumbing_without_a_device():
+    """The communicator side channel is host-only: rank 0's 128-byte id can be produced without a GPU (NCCL is dlopen'ed), and the
+    allreduce command refuses host tensors instead of touching them (no CPU fallback)."""
+    nnc.init()
+    try:
+        a, b = nnc.comm_unique_id(), nnc.comm_unique_id()
+    except RuntimeError:
+        import pytest
+        pytest.skip("libnccl.so.2 not loadable here")
+    assert len(a) == 128 and len(b) == 128 and a != b
+    x = _t(16)
+    assert nnc.cmd_exec(nnc.CMD_COMM_ALLREDUCE_FORWARD(), None, 0, [x], [x]) != 0
