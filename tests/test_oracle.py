@@ -142,3 +142,29 @@ def test_compiled_reference_attention_equals_the_composed_graph(ref, causal):
             e = np.exp(s - s.max(axis=1, keepdims=True))
             want[b, :, h] = (e / e.sum(axis=1, keepdims=True)) @ v[b, :, h].astype(np.float64)
     assert_close(o, want, 1e-5, "CPU_REF attention vs composed graph")
+
+
+@pytest.mark.ref
+def test_hint_auto_of_the_standalone_host_equals_the_reference():
+    """ccv_nnc_hint_auto (lib/nnc/ccv_nnc_cmd.c:214-262) restated in ccv_b200/csrc/nnc_host.cu: stride and border (begin / end) for
+    the window / input / output combinations the tests and the ResNet-50 driver use, byte for byte against the compiled reference."""
+    import ctypes as C
+    from ccv_b200 import abi
+    from oracle import ref as r
+    if not r.available():
+        pytest.skip("oracle/_ref/libccv_ref.so not built")
+    nnc.init()
+    cases = [((11, 11, 3), (225, 185, 3), (55, 45, 4)), ((5, 3, 1), (17, 27, 1), (17, 27, 4)), ((3, 3, 3), (224, 224, 3), (112, 112, 32)),
+             ((3, 3, 64), (56, 56, 64), (56, 56, 64)), ((3, 3, 128), (56, 56, 128), (28, 28, 128)), ((1, 1, 64), (56, 56, 64), (56, 56, 256)),
+             ((2, 2, 256), (56, 56, 256), (28, 28, 256)), ((3, 3, 64), (112, 112, 64), (56, 56, 64)), ((7, 7, 2048), (7, 7, 2048), (1, 1, 2048)),
+             ((3, 3, 8), (4, 13, 9, 8), (4, 7, 5, 16))]
+    for size, a_dims, b_dims in cases:
+        info = abi.CmdParam()
+        for i, d in enumerate(size):
+            info.size.dim[i] = d
+        pa = abi.tensor_param(abi.CCV_TENSOR_CPU_MEMORY, abi.CCV_TENSOR_FORMAT_NHWC, abi.CCV_32F, list(a_dims), 0)
+        pb = abi.tensor_param(abi.CCV_TENSOR_CPU_MEMORY, abi.CCV_TENSOR_FORMAT_NHWC, abi.CCV_32F, list(b_dims), 0)
+        mine, theirs = abi.Hint(), abi.Hint()
+        nnc.lib().ccv_nnc_sm100_hint_auto(C.byref(info), C.byref(pa), C.byref(pb), C.byref(mine))
+        r.ref().ref_hint_auto(C.byref(info), C.byref(pa), C.byref(pb), C.byref(theirs))
+        assert bytes(mine) == bytes(theirs), (size, a_dims, b_dims, list(mine.stride.dim[:3]), list(theirs.stride.dim[:3]), list(mine.border.begin[:3]), list(theirs.border.begin[:3]))
