@@ -11,6 +11,7 @@
  * GEMM (blas/ccv_nnc_gemm_cpu_ref.c:28-33), double max/sum for softmax (softmax/ccv_nnc_softmax_cpu_ref.c:27-36). */
 #include "nnc_port.h"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -487,5 +488,109 @@ void port_float_to_half(const float* f, uint16_t* h, size_t n)
 			h[i] = (uint16_t)(sign | 0x7c00u);
 		else
 			h[i] = (uint16_t)(sign | (0x7c00u + (m >> 13)));
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------ attention / row norms
+ * Restated from /root/reference/lib/nnc/cmd/scaled_dot_product_attention/ccv_nnc_scaled_dot_product_attention_cpu_ref.c:88-183.
+ * Packed tensors q [B, Sq, H, D], k [B, Sk, Hk, D], v [B, Sk, Hk, Dv], o [B, Sq, H, Dv]; query head h reads key / value head
+ * h / (H / Hk) (:99,113-114); logits = scale * q.k (+ mask[Sq, Sk] when given, :127); causal keeps keys [0, x - Sq + Sk + 1) of
+ * query x (:147) -- the masked tail contributes exactly 0; softmax with max and sum kept in double, exponent in float (:150-171);
+ * output = sum_y p[y] * v[y] accumulated in key order (:172-180).  `scratch` holds Sk floats per call. */
+static void port_sdpa_row(const float* q, const float* k, const float* v, const float* mask, float* o, float* p, int Sk, int D, int Dv, long long k_stride, long long v_stride, float scale, int visible)
+{
+	int y, d;
+	for (y = 0; y < Sk; y++)
+	{
+		float dot = 0;
+		for (d = 0; d < D; d++)
+			dot += q[d] * k[(long long)y * k_stride + d];
+		p[y] = scale * dot + (mask ? mask[y] : 0);
+	}
+	if (visible >= 0 && visible < Sk)
+		memset(p + visible, 0, sizeof(float) * (size_t)(Sk - visible));
+	if (visible > 0)
+	{
+		double mx = p[0], sum = 0;
+		for (y = 1; y < visible; y++)
+			if (p[y] > mx)
+				mx = p[y];
+		for (y = 0; y < visible; y++)
+			sum += (p[y] = expf(p[y] - mx));
+		sum = 1.0 / sum;
+		for (y = 0; y < visible; y++)
+			p[y] *= sum;
+	}
+	for (d = 0; d < Dv; d++)
+		o[d] = 0;
+	for (y = 0; y < Sk; y++)
+		for (d = 0; d < Dv; d++)
+			o[d] += p[y] * v[(long long)y * v_stride + d];
+}
+
+void port_sdpa_forw(const float* q, const float* k, const float* v, const float* mask, float* o, int B, int Sq, int Sk, int H, int Hk, int D, int Dv, float scale, int is_causal)
+{
+	const int ratio = H / Hk;
+	const long long total = (long long)B * H * Sq;
+	long long r;
+#pragma omp parallel for schedule(static)
+	for (r = 0; r < total; r++)
+	{
+		const int x = (int)(r % Sq), h = (int)((r / Sq) % H), b = (int)(r / ((long long)Sq * H));
+		float* const p = (float*)malloc(sizeof(float) * (size_t)Sk);
+		int visible = Sk;
+		if (is_causal)
+		{
+			visible = x - Sq + Sk + 1;
+			if (visible < 0)
+				visible = 0;
+			if (visible > Sk)
+				visible = Sk;
+		}
+		port_sdpa_row(q + (((long long)b * Sq + x) * H + h) * D, k + ((long long)b * Sk * Hk + h / ratio) * D, v + ((long long)b * Sk * Hk + h / ratio) * Dv,
+			mask ? mask + (long long)x * Sk : 0, o + (((long long)b * Sq + x) * H + h) * Dv, p, Sk, D, Dv, (long long)Hk * D, (long long)Hk * Dv, scale, visible);
+		free(p);
+	}
+}
+
+/* /root/reference/lib/nnc/cmd/norm/ccv_nnc_layer_norm_cpu_ref.c:16-190 for statistics over the trailing `inner` elements of each of
+ * `rows` rows: mean = sum / n, inv_std = 1 / sqrtf(sum((x - mean)^2) / n + epsilon) (the epsilon sits inside the square root, :105),
+ * y = (x - mean) * inv_std [* scale + bias].  rms = 1: /root/reference/lib/nnc/cmd/norm/ccv_nnc_rmsnorm_cpu_ref.c:16-130, no mean,
+ * inv_std = 1 / sqrtf(sum(x^2) / n + epsilon), y = x * inv_std * scale. */
+void port_row_norm_forw(const float* x, const float* scale, const float* bias, float* y, float* saved_mean, float* saved_inv_std, int rows, int inner, float epsilon, int rms)
+{
+	int r;
+	const float inv_n = 1. / inner;
+	for (r = 0; r < rows; r++)
+	{
+		const float* const xr = x + (size_t)r * inner;
+		float* const yr = y + (size_t)r * inner;
+		float mean = 0, var = 0;
+		int i;
+		if (!rms)
+		{
+			for (i = 0; i < inner; i++)
+				mean += xr[i];
+			mean = mean * inv_n;
+		}
+		for (i = 0; i < inner; i++)
+		{
+			const float w = xr[i] - mean;
+			var += w * w;
+		}
+		const float inv_std = 1. / sqrtf(var * inv_n + epsilon);
+		if (saved_mean)
+			saved_mean[r] = mean;
+		if (saved_inv_std)
+			saved_inv_std[r] = inv_std;
+		for (i = 0; i < inner; i++)
+		{
+			float t = (xr[i] - mean) * inv_std;
+			if (scale)
+				t = t * scale[i];
+			if (bias)
+				t += bias[i];
+			yr[i] = t;
+		}
 	}
 }

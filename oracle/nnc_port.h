@@ -34,6 +34,10 @@ void port_cce_forw(const float* a, const int* label, float* c, int batch, int co
 void port_cce_back(const float* g, const float* a, const int* label, float* h, int batch, int count, float trim0, float trim1);
 void port_sgd(const float* g, const float* a, const float* m, float* b, float* n, size_t count, int nesterov, float rate, float scale, float decay, float momentum, float dampening);
 void port_float_to_half(const float* f, uint16_t* h, size_t n);
+/* scaled dot product attention forward, packed [B, S, H, D] tensors, optional additive mask [Sq, Sk] (cpu_ref.c:88-183) */
+void port_sdpa_forw(const float* q, const float* k, const float* v, const float* mask, float* o, int B, int Sq, int Sk, int H, int Hk, int D, int Dv, float scale, int is_causal);
+/* layer norm (rms = 0) / rms norm (rms = 1) forward over the trailing `inner` elements of `rows` rows */
+void port_row_norm_forw(const float* x, const float* scale, const float* bias, float* y, float* saved_mean, float* saved_inv_std, int rows, int inner, float epsilon, int rms);
 #ifdef __cplusplus
 }
 #endif

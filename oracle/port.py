@@ -119,3 +119,25 @@ def avg_pool_forw(p, a):
     b = np.zeros((p.N, p.P, p.Q, p.C), np.float32)
     lib().port_avg_pool_forw(C.byref(p), _p(a), _p(b))
     return b
+
+
+def sdpa_forw(q, k, v, scale, is_causal, mask=None):
+    """q [B, Sq, H, D], k [B, Sk, Hk, D], v [B, Sk, Hk, Dv] -> o [B, Sq, H, Dv]; mask [Sq, Sk] additive or None"""
+    q, k, v = f32(q), f32(k), f32(v)
+    B, Sq, H, D = q.shape
+    Sk, Hk, Dv = k.shape[1], k.shape[2], v.shape[3]
+    o = np.zeros((B, Sq, H, Dv), np.float32)
+    m = None if mask is None else f32(mask)
+    lib().port_sdpa_forw(_p(q), _p(k), _p(v), _p(m) if m is not None else None, _p(o), B, Sq, Sk, H, Hk, D, Dv, C.c_float(scale), int(is_causal))
+    return o
+
+
+def row_norm_forw(x, scale, bias, inner, eps, rms=0):
+    """layer norm / rms norm over the trailing `inner` elements; returns (y, saved_mean, saved_inv_std)"""
+    x = f32(x)
+    rows = x.size // inner
+    y, sm, sis = np.zeros_like(x), np.zeros((rows,), np.float32), np.zeros((rows,), np.float32)
+    s = None if scale is None else f32(scale)
+    b = None if bias is None else f32(bias)
+    lib().port_row_norm_forw(_p(x), _p(s) if s is not None else None, _p(b) if b is not None else None, _p(y), _p(sm), _p(sis), rows, inner, C.c_float(eps), int(rms))
+    return y, sm, sis

@@ -168,3 +168,42 @@ def test_hint_auto_of_the_standalone_host_equals_the_reference():
         nnc.lib().ccv_nnc_sm100_hint_auto(C.byref(info), C.byref(pa), C.byref(pb), C.byref(mine))
         r.ref().ref_hint_auto(C.byref(info), C.byref(pa), C.byref(pb), C.byref(theirs))
         assert bytes(mine) == bytes(theirs), (size, a_dims, b_dims, list(mine.stride.dim[:3]), list(theirs.stride.dim[:3]), list(mine.border.begin[:3]), list(theirs.border.begin[:3]))
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("B,Sq,Sk,H,Hk,D,Dv,causal,masked", [(2, 24, 24, 4, 4, 16, 16, 0, 0), (1, 20, 28, 8, 2, 32, 24, 1, 0), (2, 16, 16, 2, 2, 8, 8, 0, 1)])
+def test_port_attention_matches_compiled_reference(port, ref, B, Sq, Sk, H, Hk, D, Dv, causal, masked):
+    """oracle/nnc_port.c:port_sdpa_forw (restated from ..._attention_cpu_ref.c:88-183) against CPU_REF itself: GQA, bottom-right
+    causal alignment with Sq != Sk, additive mask."""
+    q, k, v = seeded((B, Sq, H, D), 1, -1, 1), seeded((B, Sk, Hk, D), 2, -1, 1), seeded((B, Sk, Hk, Dv), 3, -1, 1)
+    mask = np.where(np.random.RandomState(5).rand(Sq, Sk) < 0.3, -1e9, 0.0).astype(np.float32) if masked else None
+    if masked:
+        mask[np.arange(Sq), np.arange(Sq) % Sk] = 0
+    cmd = nnc._simple(nnc.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD)
+    cmd.info.scaled_dot_product_attention.scale, cmd.info.scaled_dot_product_attention.is_causal = 1.0 / np.sqrt(D), causal
+    o = np.zeros((B, Sq, H, Dv), np.float32)
+    ins = [q, k, v] + ([mask.reshape(1, 1, Sq, Sk)] if masked else [])
+    assert ref_exec(ref, cmd, None, 0, ins, [o, None])[0] == 0
+    assert_close(port.sdpa_forw(q, k, v, 1.0 / np.sqrt(D), causal, mask), o, 1e-6, "port attention")
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("rms", [0, 1])
+def test_port_row_norms_match_compiled_reference(port, ref, rms):
+    """oracle/nnc_port.c:port_row_norm_forw against CPU_REF's LAYER_NORM_FORWARD / RMSNORM_FORWARD over the last axis."""
+    from ccv_b200 import abi
+    shape, inner = (6, 10, 64), 64
+    x, scale, bias = seeded(shape, 1, -1, 1), seeded((1, 1, inner), 2, 0.5, 1.5), seeded((1, 1, inner), 3, -1, 1)
+    y, sm, sis = np.zeros(shape, np.float32), np.zeros((6, 10, 1), np.float32), np.zeros((6, 10, 1), np.float32)
+    if rms:
+        cmd = nnc._simple(abi.CCV_NNC_RMSNORM_FORWARD)
+        cmd.info.rmsnorm.axis[0], cmd.info.rmsnorm.count, cmd.info.rmsnorm.epsilon = 2, 1, 1e-5
+        assert ref_exec(ref, cmd, None, 0, [x, scale], [y, sis])[0] == 0
+        yp, _, sp = port.row_norm_forw(x, scale, None, inner, 1e-5, rms=1)
+    else:
+        cmd = nnc._simple(abi.CCV_NNC_LAYER_NORM_FORWARD)
+        cmd.info.lnorm.axis[0], cmd.info.lnorm.count, cmd.info.lnorm.epsilon, cmd.info.lnorm.elementwise_affine = 2, 1, 1e-5, 1
+        assert ref_exec(ref, cmd, None, 0, [x, scale, bias], [y, sm, sis])[0] == 0
+        yp, mp, sp = port.row_norm_forw(x, scale, bias, inner, 1e-5, rms=0)
+        assert_close(mp.reshape(sm.shape), sm, 1e-6, "port mean")
+    assert_close(yp, y, 1e-6, "port norm output"), assert_close(sp.reshape(sis.shape), sis, 1e-6, "port inv_std")
