@@ -22,6 +22,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# CPU_REF timing hygiene (must be in the environment before libgomp loads): threads pinned to cores and spinning between the
+# thousands of small parallel regions of a step; the thread COUNT is set explicitly in reference_measure()
+os.environ.setdefault("OMP_PROC_BIND", "true")
+os.environ.setdefault("OMP_PLACES", "cores")
+os.environ.setdefault("OMP_WAIT_POLICY", "active")
 
 METRIC = "resnet50_fp32_n256_fwd_bwd_images_per_sec"
 UNIT = "images/s"
@@ -64,24 +69,24 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
 
 
-def reference_arm(args):
-    """The reference's own implementation of the path: the identical ResNet-50 command list executed by the compiled,
-    unmodified reference (oracle/_ref/libccv_ref.so, CCV_NNC_BACKEND_CPU_REF) on the host cores.  A step is a bounded
-    sample of the workload: batch 1 (CPU_REF's pooling only walks one image per call) at 224x224, the
-    same forward + backward + SGD commands.  Rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+REF_SAMPLE_BATCH = 8   # images per CPU_REF step: pooling is issued per image, every other command sees the batch
+REF_SAMPLE_STEPS = 5   # timed steps; the reported value is their median
+
+
+def reference_measure(image, batch=REF_SAMPLE_BATCH, steps=REF_SAMPLE_STEPS, warmup=1):
+    """ONE definition of the CPU number, used both by `--impl reference` and by the cpu_baseline object of the GPU arm:
+    the identical ResNet-50 command list executed by the compiled, unmodified reference (oracle/_ref/libccv_ref.so,
+    CCV_NNC_BACKEND_CPU_REF) on a bounded sample of the workload -- `batch` images of image x image per step, forward +
+    backward + SGD -- with an explicit OpenMP thread count (one per physical core; an inherited OMP_NUM_THREADS, e.g. the 1
+    torchrun exports, is overridden), one untimed step first (page faults, OpenMP pool start-up), median of `steps`."""
     from oracle import ref, ref_factory
     from ccv_b200 import resnet50
     if not ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libccv_ref.so not built (make -C oracle)"}))
-        return
-    sample_batch = 1
-    net = resnet50.Net(sample_batch, image=args.image, classes=1000, global_batch=sample_batch, factory=ref_factory.RefFactory())
-    net.input.upload(np.random.RandomState(0).rand(sample_batch, args.image, args.image, 3).astype(np.float32))
-    net.labels.upload(np.zeros((sample_batch,), np.int32))
-    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+        return None
+    cores = ref.set_num_threads(ref.physical_cores())
+    net = resnet50.Net(batch, image=image, classes=1000, global_batch=batch, factory=ref_factory.RefFactory())
+    net.input.upload(np.random.RandomState(0).rand(batch, image, image, 3).astype(np.float32))
+    net.labels.upload((np.arange(batch) % 1000).astype(np.int32))
 
     def step():
         ref_factory.run_nodes(net.fwd)
@@ -89,38 +94,41 @@ def reference_arm(args):
         ref_factory.run_nodes(net.opt)
     for _ in range(warmup):
         step()
-    t0 = time.time()
+    times = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         step()
-    dt = (time.time() - t0) / steps
-    v = sample_batch / dt
-    cores = ref.num_threads()
-    sample = "ResNet-50 v1d fwd+bwd+SGD, batch %d of %dx%d, CCV_NNC_BACKEND_CPU_REF, %d OpenMP threads, %d step(s)" % (sample_batch, args.image, args.image, cores, steps)
-    print(json.dumps({"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        times.append(time.perf_counter() - t0)
+    dt = float(np.median(times))
+    sample = ("ResNet-50 v1d fwd+bwd+SGD on CCV_NNC_BACKEND_CPU_REF (unmodified reference compiled into oracle/_ref), batch %d of %dx%d per step, "
+              "%d OpenMP threads (one per physical core, set explicitly), %d warm-up + %d timed steps, median; per-step seconds: %s"
+              % (batch, image, image, cores, warmup, steps, ", ".join("%.2f" % t for t in times)))
+    return {"value": batch / dt, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample, "ms_per_step": dt * 1e3, "batch": batch, "steps": steps, "warmup": warmup,
+            "spread": float((max(times) - min(times)) / dt)}
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores.  Rank 0 only (the other
+    ranks of a torchrun launch exit without work)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m = reference_measure(args.image)
+    if m is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libccv_ref.so not built (make -C oracle)"}))
+        return
+    print(json.dumps({"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": m["steps"], "warmup": m["warmup"], "ms_per_step": m["ms_per_step"], "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-                      "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c) fp32 NHWC fwd+bwd+SGD; bounded sample: batch 1 per step on the host CPU", "image": args.image},
-                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
-                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+                      "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c) fp32 NHWC fwd+bwd+SGD; bounded sample: batch %d per step on the host CPU" % m["batch"], "image": args.image},
+                      "cpu_baseline": {k: m[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                      "e2e": {"value": m["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
-def cpu_baseline(image, budget_s=30.0):
-    """Reported next to the GPU number (rank 0, N=1): the same command list on the reference's CPU_REF, batch 1."""
+def cpu_baseline(image):
+    """Reported next to the GPU number (rank 0, N=1): exactly the measurement `--impl reference` prints."""
     try:
-        from oracle import ref, ref_factory
-        from ccv_b200 import resnet50
-        if not ref.available():
-            return None
-        net = resnet50.Net(1, image=image, classes=1000, global_batch=1, factory=ref_factory.RefFactory())
-        net.input.upload(np.random.RandomState(0).rand(1, image, image, 3).astype(np.float32))
-        net.labels.upload(np.zeros((1,), np.int32))
-        t0 = time.time()
-        n = 0
-        while n < 1 or (time.time() - t0 < budget_s / 3 and n < 3):
-            ref_factory.run_nodes(net.fwd), ref_factory.run_nodes(net.bwd), ref_factory.run_nodes(net.opt)
-            n += 1
-        dt = (time.time() - t0) / n
-        return {"value": 1.0 / dt, "unit": UNIT, "cores": ref.num_threads(), "kind": "reference",
-                "sample": "ResNet-50 v1d fwd+bwd+SGD, batch 1 of %dx%d per step, %d step(s), CCV_NNC_BACKEND_CPU_REF compiled from /root/reference (oracle/_ref), OpenMP" % (image, image, n)}
+        m = reference_measure(image)
+        return None if m is None else {k: m[k] for k in ("value", "unit", "cores", "kind", "sample")}
     except Exception as e:  # the baseline must never take the benchmark down
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
 

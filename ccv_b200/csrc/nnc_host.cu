@@ -59,7 +59,10 @@ int tensor_nd(const int* const dim)
 	return CCV_NNC_MAX_DIM_ALLOC;
 }
 
-// per-thread default stream contexts, one per device (lib/nnc/gpu/ccv_nnc_compat.cu:342-350)
+// per-thread default stream contexts, one per device (lib/nnc/gpu/ccv_nnc_compat.cu:342-350).  As in the reference, whose
+// per-thread context is zero-initialised, their CUDA stream is the legacy default stream (0): work issued with
+// stream_context == NULL is ordered with every later synchronous CUDA call of the caller, so ccv_nnc_cmd_exec only has to
+// drain (not wait) on that path (lib/nnc/ccv_nnc_cmd.c:690-691).
 thread_local ccv_nnc_stream_context_t* t_default_streams[64] = { 0 };
 
 ccv_nnc_stream_context_t* default_stream(const int device)
@@ -67,9 +70,12 @@ ccv_nnc_stream_context_t* default_stream(const int device)
 	const int d = device < 0 ? 0 : device & 63;
 	if (!t_default_streams[d])
 	{
-		int type = CCV_STREAM_CONTEXT_GPU;
-		CCV_STREAM_SET_DEVICE_ID(type, d);
-		t_default_streams[d] = ccv_nnc_stream_context_new(type);
+		ccv_nnc_stream_context_t* const s = (ccv_nnc_stream_context_t*)calloc(1, sizeof(ccv_nnc_stream_context_t));
+		s->type = CCV_STREAM_CONTEXT_GPU;
+		CCV_STREAM_SET_DEVICE_ID(s->type, d);
+		s->device = d;
+		s->stream = 0;
+		t_default_streams[d] = s;
 	}
 	return t_default_streams[d];
 }
@@ -153,7 +159,8 @@ int ccv_nnc_cmd_exec(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const i
 		const int device = device_of(inputs, input_size, outputs, output_size);
 		if (device >= 0)
 			cudaSetDevice(device);
-	}
+	} else if (CCV_STREAM_GET_CONTEXT(stream_context->type) == CCV_STREAM_CONTEXT_GPU)
+		cudaSetDevice(stream_context->device); // the reference's stream getter does this (gpu/ccv_nnc_compat.cu:319-340); kernels, workspace and function attributes follow the stream's device
 	if (cmd.cmd == CCV_NNC_CUSTOM_FORWARD || cmd.cmd == CCV_NNC_CUSTOM_BACKWARD)
 		return CCV_NNC_EXEC_NO_KERNEL; // custom vtabs live above this slice of the API
 	uint32_t backend = cmd.backend;
@@ -187,38 +194,49 @@ int ccv_nnc_cmd_exec(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const i
 	const int ret = it->second.exec(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 	if (!stream_context)
 	{
-		// the synchronous form: results are visible (and the per-thread workspace released) on return
+		// lib/nnc/ccv_nnc_cmd.c:690-691: without a stream the per-thread context is drained (its workspace released); the work
+		// itself sits on the legacy default stream, ordered before whatever the caller does next
 		const int device = device_of(inputs, input_size, outputs, output_size);
 		if (device >= 0)
-		{
-			ccv_nnc_stream_context_t* const s = default_stream(device);
-			ccv_nnc_stream_context_wait(s);
-			ccv_nnc_stream_context_drain(s);
-		}
+			ccv_nnc_stream_context_drain(default_stream(device));
 	}
 	return ret;
 }
 
 ccv_nnc_hint_t ccv_nnc_hint_auto(const ccv_nnc_cmd_param_t cmd, const ccv_nnc_tensor_param_t a, const ccv_nnc_tensor_param_t b)
 {
-	// lib/nnc/ccv_nnc_cmd.c:204-250: for each spatial axis, stride = ceil(a / b)-ish guess and symmetric-as-possible border
+	// lib/nnc/ccv_nnc_cmd.c:181-217.  Per spatial axis: the stride that roughly maps a's extent onto b's, then whatever total
+	// border makes (b - 1) * stride + size cover a, the larger half in front.  Nothing is clamped: a window smaller than the
+	// stride yields a negative border, exactly as the reference reports it (ccv_nnc_hint_verify is what rejects bad hints).
 	ccv_nnc_hint_t hint;
 	memset(&hint, 0, sizeof(hint));
+	if (a.format != b.format)
+		return hint;
 	const int a_nd = tensor_nd(a.dim), b_nd = tensor_nd(b.dim);
 	if (a_nd != b_nd || (a_nd != CCV_NNC_MAX_DIM + 1 && a_nd != CCV_NNC_MAX_DIM + 2))
 		return hint;
-	const int hw_a = (a.format == CCV_TENSOR_FORMAT_NHWC) ? (a_nd == CCV_NNC_MAX_DIM + 1 ? 0 : 1) : (a.format == CCV_TENSOR_FORMAT_NCHW ? (a_nd == CCV_NNC_MAX_DIM + 1 ? 1 : 2) : 0);
-	int i;
-	for (i = 0; i < CCV_NNC_MAX_DIM; i++)
+	int hw;
+	if (a.format == CCV_TENSOR_FORMAT_CHWN || (a.format == CCV_TENSOR_FORMAT_NHWC && a_nd == CCV_NNC_MAX_DIM + 1))
+		hw = 0;
+	else if ((a.format == CCV_TENSOR_FORMAT_NHWC && a_nd == CCV_NNC_MAX_DIM + 2) || (a.format == CCV_TENSOR_FORMAT_NCHW && a_nd == CCV_NNC_MAX_DIM + 1))
+		hw = 1;
+	else if (a.format == CCV_TENSOR_FORMAT_NCHW && a_nd == CCV_NNC_MAX_DIM + 2)
+		hw = 2;
+	else
+		return hint;
+	for (int i = 0; i < CCV_NNC_MAX_DIM; i++)
 	{
-		const int ad = a.dim[i + hw_a], bd = b.dim[i + hw_a];
-		if (bd <= 0)
-			continue;
-		const int stride = (ad + bd / 2) / bd > 0 ? (ad + bd / 2) / bd : 1;
+		const int ad = a.dim[i + hw], bd = b.dim[i + hw];
+		if (ad <= 0 || bd <= 0)
+		{
+			memset(&hint, 0, sizeof(hint));
+			return hint;
+		}
+		const int stride = (ad + bd / 2) / bd;
+		const int border = (bd - 1) * stride - ad + cmd.size.dim[i];
 		hint.stride.dim[i] = stride;
-		const int border = cmd.size.dim[i] - (ad - stride * (bd - 1));
-		hint.border.begin[i] = (border + 1) / 2 > 0 ? (border + 1) / 2 : 0;
-		hint.border.end[i] = border - hint.border.begin[i] > 0 ? border - hint.border.begin[i] : 0;
+		hint.border.begin[i] = (border + 1) / 2;
+		hint.border.end[i] = border - hint.border.begin[i];
 	}
 	return hint;
 }
@@ -411,6 +429,7 @@ void* ccv_nnc_stream_context_get_workspace(ccv_nnc_stream_context_t* const strea
 	}
 	if (s->gpu_workspace_size < workspace_size)
 	{
+		cudaSetDevice(s->device); // the buffer belongs to the stream's device, whichever device happens to be current
 		if (s->gpu_workspace)
 		{
 			// kernels already enqueued may still be using the old buffer
@@ -892,7 +911,7 @@ int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
 			const int K = c.cmd.info.convolution.count;
 			ccv_nnc_tensor_param_t params = c.outputs[0]->info;
 			memset(params.dim, 0, sizeof(params.dim));
-			params.dim[0] = 160, params.dim[1] = 2 * K; // >= one partial row per SM
+			params.dim[0] = 4 * 4 * 160, params.dim[1] = K; // four planes (count, shift, sum, sum of squares) of >= 4 rows per SM
 			params.datatype = CCV_32F;
 			ccv_nnc_tensor_t* const stats = ccv_nnc_tensor_new(0, params, 0);
 			if (!stats || !stats->data.u8)

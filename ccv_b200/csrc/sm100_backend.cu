@@ -89,6 +89,20 @@ inline cudaStream_t stream_of(ccv_nnc_stream_context_t* const stream_context)
 	return (cudaStream_t)ccv_nnc_stream_context_get_stream(stream_context);
 }
 
+// split-K scratch of one command: the stream workspace (grow-only, one buffer per stream: lib/nnc/gpu/ccv_nnc_compat.cu:438-471).
+// A command that also stages tensors in the workspace asks for both at once and passes the tail (scratch_at).
+inline Scratch scratch_of(ccv_nnc_stream_context_t* const stream_context)
+{
+	void* const p = ccv_nnc_stream_context_get_workspace(stream_context, CONTRACT_SCRATCH_BYTES, CCV_TENSOR_GPU_MEMORY);
+	const Scratch s = { p, p ? CONTRACT_SCRATCH_BYTES : 0 };
+	return s;
+}
+inline Scratch scratch_at(void* const p, const size_t bytes)
+{
+	const Scratch s = { p, p ? bytes : 0 };
+	return s;
+}
+
 inline bool is_f32(const ccv_nnc_tensor_t* const t) { return CCV_GET_DATA_TYPE(t->info.datatype) == CCV_32F; }
 
 bool same_shape(const TV& a, const TV& b)
@@ -156,8 +170,28 @@ bool mat_of(const TV& v, const int transpose[2], Mat& m)
 	return true;
 }
 
+// Algorithm of a GEMM command.  An explicit cmd.algorithm (what ccv_nnc_cmd_autotune stores) wins; otherwise fp32 data means
+// fp32-grade products -- the reference's cuBLAS path computes fp32 GEMMs in CUBLAS_COMPUTE_32F
+// (lib/nnc/gpu/ccv_nnc_compat.cu:786-803) -- i.e. the error-compensated 3xTF32 kernel, unless the caller opted into TF32 with
+// CCV_NNC_GEMM_32TF (lib/nnc/ccv_nnc.h:103-105).
+int gemm_algorithm(const ccv_nnc_cmd_t& cmd)
+{
+	if (cmd.algorithm >= 0 && cmd.algorithm < CCV_NNC_SM100_ALGO_COUNT)
+		return cmd.algorithm;
+	return (cmd.info.blas.flags & CCV_NNC_GEMM_32TF) ? CCV_NNC_SM100_ALGO_TF32 : CCV_NNC_SM100_ALGO_3XTF32;
+}
+// Algorithm of a CONVOLUTION command: explicit, else one-pass TF32 -- the reference's own GPU convolution sets
+// CUDNN_TENSOR_OP_MATH on every convolution descriptor (lib/nnc/gpu/ccv_nnc_compat.cu:1393), which is TF32 tensor-core math
+// for fp32 data; CCV_NNC_SM100_ALGO_3XTF32 / _FFMA are there for callers that need fp32-grade convolutions.
+int conv_algorithm(const ccv_nnc_cmd_t& cmd)
+{
+	if (cmd.algorithm >= 0 && cmd.algorithm < CCV_NNC_SM100_ALGO_COUNT)
+		return cmd.algorithm;
+	return CCV_NNC_SM100_ALGO_TF32;
+}
+
 // C[M, N] (+)= A[M, K] * B[K, N] + bias over arbitrary (row, col) element strides
-int gemm_dispatch(cudaStream_t s, const int algorithm, const int M, const int N, const int K, const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c, long long c_rs, long long c_cs, const float* bias, const int accumulate)
+int gemm_dispatch(cudaStream_t s, const Scratch& scratch, const int algorithm, const int M, const int N, const int K, const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c, long long c_rs, long long c_cs, const float* bias, const int accumulate)
 {
 	if (M <= 0 || N <= 0)
 		return 0;
@@ -170,7 +204,7 @@ int gemm_dispatch(cudaStream_t s, const int algorithm, const int M, const int N,
 		if (bias)
 			return 1;
 		// C^T = B^T A^T
-		return gemm_dispatch(s, algorithm, N, M, K, b, b_cs, b_rs, a, a_cs, a_rs, c, c_cs, 1, 0, accumulate);
+		return gemm_dispatch(s, scratch, algorithm, N, M, K, b, b_cs, b_rs, a, a_cs, a_rs, c, c_cs, 1, 0, accumulate);
 	}
 	if (algorithm != CCV_NNC_SM100_ALGO_FFMA)
 	{
@@ -186,7 +220,7 @@ int gemm_dispatch(cudaStream_t s, const int algorithm, const int M, const int N,
 			tb = 1, ldb = b_cs;
 		if (ta >= 0 && tb >= 0)
 		{
-			const int rc = gemm_tf32(s, M, N, K, a, lda, ta, b, ldb, tb, c, c_rs, bias, accumulate);
+			const int rc = gemm_tf32(s, M, N, K, a, lda, ta, b, ldb, tb, c, c_rs, bias, accumulate, scratch, algorithm == CCV_NNC_SM100_ALGO_3XTF32);
 			if (rc <= 0)
 				return rc;
 		}
@@ -222,8 +256,9 @@ int exec_gemm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 			bias.batch_inc = 0;
 	}
 	cudaStream_t s = stream_of(stream_context);
+	const Scratch scratch = scratch_of(stream_context);
 	for (int i = 0; i < b.batch; i++)
-		RC(gemm_dispatch(s, cmd.algorithm, b.rows, b.cols, a.cols, a.p + i * a.batch_inc, a.rs, a.cs, w.p + i * w.batch_inc, w.rs, w.cs, b.p + i * b.batch_inc, b.rs, b.cs, bias_t ? bias.p + i * bias.batch_inc : 0, 0));
+		RC(gemm_dispatch(s, scratch, gemm_algorithm(cmd), b.rows, b.cols, a.cols, a.p + i * a.batch_inc, a.rs, a.cs, w.p + i * w.batch_inc, w.rs, w.cs, b.p + i * b.batch_inc, b.rs, b.cs, bias_t ? bias.p + i * bias.batch_inc : 0, 0));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -264,7 +299,7 @@ int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 			a.batch_inc = 0;
 		// dw[K, N] = a^T[K, M] * g[M, N]; a shared dw sums over the batch
 		for (int i = 0; i < g.batch; i++)
-			RC(gemm_dispatch(s, cmd.algorithm, dw.rows, dw.cols, g.rows, a.p + i * a.batch_inc, a.cs, a.rs, g.p + i * g.batch_inc, g.rs, g.cs, dw.p + (dw.batch == 1 ? 0 : i * dw.batch_inc), dw.rs, dw.cs, 0, accumulate || (dw.batch == 1 && i > 0)));
+			RC(gemm_dispatch(s, scratch_of(stream_context), gemm_algorithm(cmd), dw.rows, dw.cols, g.rows, a.p + i * a.batch_inc, a.cs, a.rs, g.p + i * g.batch_inc, g.rs, g.cs, dw.p + (dw.batch == 1 ? 0 : i * dw.batch_inc), dw.rs, dw.cs, 0, accumulate || (dw.batch == 1 && i > 0)));
 	}
 	if (h_t)
 	{
@@ -279,7 +314,7 @@ int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 			w.batch_inc = 0;
 		// h[M, K] = g[M, N] * w^T[N, K]
 		for (int i = 0; i < g.batch; i++)
-			RC(gemm_dispatch(s, cmd.algorithm, h.rows, h.cols, g.cols, g.p + i * g.batch_inc, g.rs, g.cs, w.p + i * w.batch_inc, w.cs, w.rs, h.p + (h.batch == 1 ? 0 : i * h.batch_inc), h.rs, h.cs, 0, accumulate || (h.batch == 1 && i > 0)));
+			RC(gemm_dispatch(s, scratch_of(stream_context), gemm_algorithm(cmd), h.rows, h.cols, g.cols, g.p + i * g.batch_inc, g.rs, g.cs, w.p + i * w.batch_inc, w.cs, w.rs, h.p + (h.batch == 1 ? 0 : i * h.batch_inc), h.rs, h.cs, 0, accumulate || (h.batch == 1 && i > 0)));
 	}
 	return CCV_NNC_EXEC_SUCCESS;
 }
@@ -332,12 +367,14 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		return CCV_NNC_EXEC_INVALID;
 	ConvGeom g;
 	const int groups = cmd.info.convolution.groups > 0 ? cmd.info.convolution.groups : 1;
+	const int algo = conv_algorithm(cmd), x3 = algo == CCV_NNC_SM100_ALGO_3XTF32;
 	cudaStream_t s = stream_of(stream_context);
 	const float* a = inputs[0]->data.f32;
 	const float* w = inputs[1]->data.f32;
 	const float* bias = bias_t ? bias_t->data.f32 : 0;
 	float* b = outputs[0]->data.f32;
 	float* nchw_out = 0; // NCHW call: the NHWC result is staged here and transposed back at the end
+	Scratch nchw_scratch = { 0, 0 };
 	TV ta = view_of(inputs[0]), tw = view_of(inputs[1]), tb = view_of(outputs[0]);
 	if (ta.format == CCV_TENSOR_FORMAT_NCHW && tb.format == CCV_TENSOR_FORMAT_NCHW)
 	{
@@ -350,12 +387,13 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		if (tb.dim[0] != N || tw.dim[0] != K)
 			return CCV_NNC_EXEC_INVALID;
 		const size_t nx = ta.count, nw = tw.count, ny = tb.count;
-		float* const ws = (float*)ccv_nnc_stream_context_get_workspace(stream_context, (nx + nw + ny) * sizeof(float) + 1024, CCV_TENSOR_GPU_MEMORY);
+		float* const ws = (float*)ccv_nnc_stream_context_get_workspace(stream_context, (nx + nw + ny) * sizeof(float) + 1024 + CONTRACT_SCRATCH_BYTES, CCV_TENSOR_GPU_MEMORY);
 		if (!ws)
 			return CCV_NNC_EXEC_OOM;
 		float* const xh = ws;
 		float* const wh = (float*)(((uintptr_t)(xh + nx) + 255) & ~(uintptr_t)255);
 		float* const yh = (float*)(((uintptr_t)(wh + nw) + 255) & ~(uintptr_t)255);
+		nchw_scratch = scratch_at((void*)(((uintptr_t)(yh + ny) + 255) & ~(uintptr_t)255), CONTRACT_SCRATCH_BYTES);
 		const int xd[4] = { N, H, W, C }, xs[4] = { C * H * W, W, 1, H * W }, xt[4] = { H * W * C, W * C, C, 1 };
 		const int wd[4] = { K, R, S, Cg }, wsrc[4] = { Cg * R * S, S, 1, R * S }, wdst[4] = { R * S * Cg, S * Cg, Cg, 1 };
 		RC(copy_strided(s, a, xs, xh, xt, xd, 4));
@@ -379,7 +417,7 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	if (nchw_out)
 	{
 		// the staged convolution, then [N, P, Q, K] -> [N, K, P, Q]
-		int rc = groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA ? conv_fprop_tf32(s, g, a, w, bias, b) : 1;
+		int rc = groups == 1 && algo != CCV_NNC_SM100_ALGO_FFMA ? conv_fprop_tf32(s, g, a, w, bias, b, nchw_scratch, x3) : 1;
 		if (rc < 0)
 			return CCV_NNC_EXEC_INVALID;
 		if (rc > 0)
@@ -388,15 +426,15 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		RC(copy_strided(s, b, ysrc, nchw_out, ydst, yd, 4));
 		return CCV_NNC_EXEC_SUCCESS;
 	}
-	if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
+	if (groups == 1 && algo != CCV_NNC_SM100_ALGO_FFMA)
 	{
-		int rc = conv_fprop_tf32(s, g, a, w, bias, b);
+		int rc = conv_fprop_tf32(s, g, a, w, bias, b, scratch_of(stream_context), x3);
 		if (rc > 0 && g.C % 4 != 0)
 		{
 			// TMA cannot address 12-byte pixels (the 3-channel stem): explicit im2col + tensor-core GEMM
 			void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, conv_im2col_workspace_bytes(g), CCV_TENSOR_GPU_MEMORY);
 			if (ws)
-				rc = conv_fprop_im2col_tf32(s, g, a, w, bias, b, ws);
+				rc = conv_fprop_im2col_tf32(s, g, a, w, bias, b, ws, x3);
 		}
 		if (rc == 0)
 			return CCV_NNC_EXEC_SUCCESS;
@@ -425,6 +463,7 @@ int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		return CCV_NNC_EXEC_INVALID;
 	const int groups = cmd.info.convolution.groups > 0 ? cmd.info.convolution.groups : 1;
 	const int accumulate = (flags & CCV_NNC_ACCUMULATE_OUTPUT) ? 1 : 0;
+	const int algo = conv_algorithm(cmd), x3 = algo == CCV_NNC_SM100_ALGO_3XTF32;
 	cudaStream_t s = stream_of(stream_context);
 	const float* gb = inputs[0]->data.f32;
 	const float* a = inputs[1]->data.f32;
@@ -437,14 +476,14 @@ int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	if (dw_t)
 	{
 		int rc = 1;
-		if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
+		if (groups == 1 && algo != CCV_NNC_SM100_ALGO_FFMA)
 		{
-			rc = conv_wgrad_tf32(s, g, gb, a, dw_t->data.f32, accumulate);
+			rc = conv_wgrad_tf32(s, g, gb, a, dw_t->data.f32, accumulate, scratch_of(stream_context), x3);
 			if (rc > 0 && g.C % 4 != 0)
 			{
 				void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, conv_im2col_workspace_bytes(g), CCV_TENSOR_GPU_MEMORY);
 				if (ws)
-					rc = conv_wgrad_im2col_tf32(s, g, gb, a, dw_t->data.f32, accumulate, ws);
+					rc = conv_wgrad_im2col_tf32(s, g, gb, a, dw_t->data.f32, accumulate, ws, x3);
 			}
 		}
 		if (rc < 0)
@@ -460,8 +499,8 @@ int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		if (!conv_geom(cmd, hint, view_of(h_t), view_of(w_t), view_of(inputs[0]), gh))
 			return CCV_NNC_EXEC_INVALID;
 		int rc = 1;
-		if (groups == 1 && cmd.algorithm != CCV_NNC_SM100_ALGO_FFMA)
-			rc = conv_dgrad_tf32(s, gh, gb, w_t->data.f32, h_t->data.f32);
+		if (groups == 1 && algo != CCV_NNC_SM100_ALGO_FFMA)
+			rc = conv_dgrad_tf32(s, gh, gb, w_t->data.f32, h_t->data.f32, scratch_of(stream_context), x3);
 		if (rc < 0)
 			return CCV_NNC_EXEC_INVALID;
 		if (rc > 0)
@@ -1273,8 +1312,8 @@ int autotune_contraction(const ccv_nnc_cmd_t cmd, const size_t max_workspace_siz
 		return 0;
 	int best = 0;
 	float best_ms = -1.f;
-	const int candidates[2] = { CCV_NNC_SM100_ALGO_TF32, CCV_NNC_SM100_ALGO_FFMA }; // 3xTF32 is reserved
-	for (int k = 0; k < 2; k++)
+	const int candidates[3] = { CCV_NNC_SM100_ALGO_TF32, CCV_NNC_SM100_ALGO_3XTF32, CCV_NNC_SM100_ALGO_FFMA };
+	for (int k = 0; k < 3; k++)
 	{
 		ccv_nnc_cmd_t c = cmd;
 		c.algorithm = candidates[k];
@@ -1367,16 +1406,17 @@ extern "C" int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t cmd, const 
 }
 
 // CONVOLUTION_FORWARD whose output feeds a training BATCH_NORM_FORWARD: outputs[1] is the statistics tensor
-// ([rows, 2K] fp32) shared with the batch-norm node; the tensor-core epilogue adds sum(y), sum(y * y) per channel into it and
-// the number of partial rows lands in its `sig` field (0 when the launch took a path without that epilogue).
+// ([4 planes x rows, K] fp32: count, shift, shifted sum, shifted sum of squares per (CTA, warp quarter) row) shared with the
+// batch-norm node; the tensor-core epilogue folds its output into it and the number of rows in use lands in the `sig` field
+// (0 when the launch took a path without that epilogue).
 extern "C" int ccv_nnc_sm100_fused_conv_stats_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (output_size != 2 || !outputs[1])
 		return CCV_NNC_EXEC_INVALID;
 	ccv_nnc_tensor_t* const stats_t = outputs[1];
 	int rows = 0;
-	const int max_rows = stats_t->info.dim[0];
-	if (outputs[0] && stats_t->info.dim[1] == 2 * cmd.info.convolution.count)
+	const int max_rows = stats_t->info.dim[0] / 4;
+	if (outputs[0] && stats_t->info.dim[1] == cmd.info.convolution.count)
 		conv_stats_request(stats_t->data.f32, max_rows, &rows);
 	const int rc = exec_conv_forw(cmd, hint, flags, inputs, input_size, outputs, 1, stream_context);
 	conv_stats_request(0, 0, 0); // never leave a request pending for an unrelated launch

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
 		s1 += sh[0][j][cx], s2 += sh[1][j][cx];
 	if (MODE == 0)
 	{
-		const double k = x ? (double)x[c] : 0.0; // externally produced sums (convolution epilogue) are not shifted
+		const double k = (double)x[c];
 		const double mean = k + s1 / count;
 		double var = (s2 - s1 * s1 / count) / count;
 		if (var < 0)
@@ -295,6 +295,64 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
 		coef[2 * C + c] = pp;
 		coef[3 * C + c] = -a * db / cnt - pp * saved_mean[c];
 	}
+}
+
+// Forward finalisation from the statistics a convolution epilogue produced (sm100_umma_persistent.cuh): four planes [rows][C] --
+// count, shift k, sum(v - k), sum((v - k)^2) -- one row per (CTA, epilogue warp quarter); rows with count 0 were never touched.
+// Each slot is its own shifted one-pass estimate; they are merged with Chan's parallel update in double precision, in a fixed
+// order (32 row-lanes per channel, then lane by lane): deterministic, and free of the E[v^2] - E[v]^2 cancellation however far
+// the channel mean is from zero (norm/ccv_nnc_batch_norm_cpu_ref.c:66-110 is the two-pass form this has to agree with).
+__global__ void __launch_bounds__(1024) bn_finalize_ext_kernel(const float* __restrict__ part, const int rows, const int C, const float epsilon, const float momentum,
+	const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std, float* __restrict__ coef)
+{
+	__shared__ double sh[3][32][33];
+	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
+	const int c = blockIdx.x * 32 + cx;
+	const size_t plane = (size_t)rows * C;
+	double n = 0, mean = 0, m2 = 0;
+	if (c < C)
+		for (int y = yl; y < rows; y += 32)
+		{
+			const size_t at = (size_t)y * C + c;
+			const double nb = (double)part[at];
+			if (nb > 0)
+			{
+				const double s1 = (double)part[2 * plane + at], s2 = (double)part[3 * plane + at];
+				const double mb = (double)part[plane + at] + s1 / nb;
+				double m2b = s2 - s1 * s1 / nb;
+				if (m2b < 0)
+					m2b = 0;
+				const double tot = n + nb, delta = mb - mean;
+				mean += delta * (nb / tot);
+				m2 += m2b + delta * delta * (n * nb / tot);
+				n = tot;
+			}
+		}
+	sh[0][yl][cx] = n, sh[1][yl][cx] = mean, sh[2][yl][cx] = m2;
+	__syncthreads();
+	if (yl != 0 || c >= C)
+		return;
+	n = 0, mean = 0, m2 = 0;
+	for (int j = 0; j < 32; j++)
+	{
+		const double nb = sh[0][j][cx];
+		if (nb > 0)
+		{
+			const double tot = n + nb, delta = sh[1][j][cx] - mean;
+			mean += delta * (nb / tot);
+			m2 += sh[2][j][cx] + delta * delta * (n * nb / tot);
+			n = tot;
+		}
+	}
+	const float meanf = (float)mean, varf = n > 0 ? (float)(m2 / n) : 0.f;
+	const float inv_std = 1.f / sqrtf(varf + epsilon);
+	saved_mean[c] = meanf;
+	saved_inv_std[c] = inv_std;
+	running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * meanf;
+	running_var[c] = momentum * running_var[c] + (1.f - momentum) * varf;
+	float a, b;
+	bn_affine(scale[c], bias[c], meanf, inv_std, a, b);
+	coef[c] = a, coef[C + c] = b;
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise passes
@@ -482,8 +540,8 @@ int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scal
 	int part_rows = 0;
 	if (ext_part && ext_rows > 0)
 	{
-		// the producing convolution already summed v and v * v per output channel in its epilogue (ext_rows partial rows of 2C)
-		bn_finalize_partials_kernel<0, 0><<<(C + 31) / 32, 1024, 0, s>>>(ext_part, ext_rows, 0, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, 0, 0, coef);
+		// the producing convolution already folded its output into per-(CTA, warp quarter) shifted sums (four planes of ext_rows x C)
+		bn_finalize_ext_kernel<<<(C + 31) / 32, 1024, 0, s>>>(ext_part, ext_rows, C, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, coef);
 		if (check("bn_fwd_finalize(ext)"))
 			return -1;
 		return fuse_relu ? run_apply<0, 1>(s, x, 0, y, coef, outer, C, inner) : run_apply<0, 0>(s, x, 0, y, coef, outer, C, inner);

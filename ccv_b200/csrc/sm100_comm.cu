@@ -215,7 +215,10 @@ int ccv_nnc_sm100_exec_allreduce(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t h
 			return nccl_fail("ncclGroupStart", rc);
 		for (int i = 0; i < count; i++)
 			if ((rc = g_nccl.AllReduce(inputs[i]->data.u8, outputs[i]->data.u8, tensor_count(inputs[i]), nccl_datatype(inputs[i]->info.datatype), NCCL_SUM, g_rank_comm, stream)) != NCCL_SUCCESS)
+			{
+				g_nccl.GroupEnd(); // never leave the group open
 				return nccl_fail("ncclAllReduce", rc);
+			}
 		if ((rc = g_nccl.GroupEnd()) != NCCL_SUCCESS)
 			return nccl_fail("ncclGroupEnd", rc);
 		sm100::count_launch(1);
@@ -233,6 +236,19 @@ int ccv_nnc_sm100_exec_allreduce(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t h
 			return nccl_fail("ncclCommInitAll", rc);
 		}
 	}
+	// Per-device streams: with a stream context, the neighbour the graph runner registered for that device
+	// (comm/gpu/ccv_nnc_comm_gpu_nccl.cu:43-44) -- a missing neighbour is an error, not a silent fall to another stream, because
+	// nothing would order the reduction with the kernels that produced the gradients there.  Without a stream context
+	// (synchronous form), each device's legacy default stream, which is what this host's per-thread default contexts wrap.
+	std::vector<cudaStream_t> streams(count, (cudaStream_t)0);
+	if (stream_context)
+		for (int i = 0; i < count; i++)
+		{
+			ccv_nnc_stream_context_t* const neighbor = ccv_nnc_stream_context_find_neighbor(stream_context, CCV_TENSOR_GET_DEVICE_ID(inputs[i]->info.type));
+			if (!neighbor)
+				return CCV_NNC_EXEC_INVALID;
+			streams[i] = (cudaStream_t)ccv_nnc_stream_context_get_stream(neighbor);
+		}
 	int restore = 0;
 	cudaGetDevice(&restore);
 	if ((rc = g_nccl.GroupStart()) != NCCL_SUCCESS)
@@ -240,13 +256,13 @@ int ccv_nnc_sm100_exec_allreduce(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t h
 	for (int i = 0; i < count; i++)
 	{
 		const int device = CCV_TENSOR_GET_DEVICE_ID(inputs[i]->info.type);
-		ccv_nnc_stream_context_t* const neighbor = stream_context ? ccv_nnc_stream_context_find_neighbor(stream_context, device) : 0;
-		cudaStream_t stream = 0;
-		if (neighbor)
-			stream = (cudaStream_t)ccv_nnc_stream_context_get_stream(neighbor);
 		cudaSetDevice(device);
-		if ((rc = g_nccl.AllReduce(inputs[i]->data.u8, outputs[i]->data.u8, tensor_count(inputs[i]), nccl_datatype(inputs[i]->info.datatype), NCCL_SUM, g_all_comms[device], stream)) != NCCL_SUCCESS)
+		if ((rc = g_nccl.AllReduce(inputs[i]->data.u8, outputs[i]->data.u8, tensor_count(inputs[i]), nccl_datatype(inputs[i]->info.datatype), NCCL_SUM, g_all_comms[device], streams[i])) != NCCL_SUCCESS)
+		{
+			g_nccl.GroupEnd();
+			cudaSetDevice(restore);
 			return nccl_fail("ncclAllReduce", rc);
+		}
 	}
 	rc = g_nccl.GroupEnd();
 	cudaSetDevice(restore);

@@ -54,11 +54,22 @@ static bool tma_api_init()
 	return g_encode_tiled != 0 && g_encode_im2col != 0;
 }
 
+// Math mode of the launches a contraction entry point issues: 0 = one-pass TF32 (operands rounded to TF32 by the TMA unit),
+// 1 = 3xTF32 (raw fp32 operands, hi / lo split in shared memory, three MMAs per k-step; persistent kernel only).  Set by the
+// entry points for the duration of the call (host thread local, like the statistics request).
+static thread_local int t_x3 = 0;
+struct X3Scope {
+	int saved;
+	explicit X3Scope(int x3) : saved(t_x3) { t_x3 = x3; }
+	~X3Scope() { t_x3 = saved; }
+};
+static inline int operand_dtype() { return t_x3 ? (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : g_tma_dtype; }
+
 // fp32 2-D row-major [rows, cols] with row pitch `ld` elements; box = {box_cols (<= 32), box_rows}
 static bool make_map_2d(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool mn_major = false, int dtype = -1)
 {
 	if (dtype < 0)
-		dtype = g_tma_dtype;
+		dtype = operand_dtype();
 	if ((((uintptr_t)ptr) & 15) || ((ld * 4) & 15) || ld * 4 >= (1ll << 40))
 		return false;
 	cuuint64_t dims[2] = { (cuuint64_t)cols, (cuuint64_t)rows };
@@ -71,8 +82,10 @@ static bool make_map_2d(CUtensorMap* map, const float* ptr, long long rows, long
 
 // fp32 NHWC tensor {C, W, H, N} in im2col mode. Base pixels run over [lower, dim + upper) per spatial axis with the
 // given traversal stride; each load fetches `pixels` base pixels x `channels` channels at base + tap offset.
-static bool make_map_im2col(CUtensorMap* map, const float* ptr, int N, int H, int W, int C, long long sn, long long sh, long long sw, int lower_h, int lower_w, int upper_h, int upper_w, int trav_h, int trav_w, int channels, int pixels, bool mn_major = false)
+static bool make_map_im2col(CUtensorMap* map, const float* ptr, int N, int H, int W, int C, long long sn, long long sh, long long sw, int lower_h, int lower_w, int upper_h, int upper_w, int trav_h, int trav_w, int channels, int pixels, bool mn_major = false, int dtype = -1)
 {
+	if (dtype < 0)
+		dtype = operand_dtype();
 	if ((((uintptr_t)ptr) & 15) || ((sw * 4) & 15) || ((sh * 4) & 15) || ((sn * 4) & 15))
 		return false;
 	if (lower_h < -128 || lower_h > 127 || lower_w < -128 || lower_w > 127 || upper_h < -128 || upper_h > 127 || upper_w < -128 || upper_w > 127)
@@ -84,7 +97,7 @@ static bool make_map_im2col(CUtensorMap* map, const float* ptr, int N, int H, in
 	int lower[2] = { lower_w, lower_h };
 	int upper[2] = { upper_w, upper_h };
 	cuuint32_t estr[4] = { 1, (cuuint32_t)trav_w, (cuuint32_t)trav_h, 1 };
-	CUresult r = g_encode_im2col(map, (CUtensorMapDataType)g_tma_dtype, 4, (void*)ptr, dims, strides, lower, upper, (cuuint32_t)channels, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	CUresult r = g_encode_im2col(map, (CUtensorMapDataType)dtype, 4, (void*)ptr, dims, strides, lower, upper, (cuuint32_t)channels, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS)
 		return false;
 	// Same driver workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): for tensors under 128 KiB, drivers
@@ -109,6 +122,104 @@ static int num_sms()
 	return g_num_sms;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: each launcher keeps one flag per device (a single
+// process may drive several GPUs, comm/gpu/ccv_nnc_comm_gpu_nccl.cu:12-58)
+constexpr int MAX_DEVICES = 64;
+template <typename Kern>
+static int ensure_dynamic_smem(Kern kern, int bytes, bool (&done)[MAX_DEVICES], const char* what)
+{
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= MAX_DEVICES)
+		dev = 0;
+	if (done[dev])
+		return 0;
+	const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (e != cudaSuccess)
+	{
+		set_last_error(what, e);
+		return -1;
+	}
+	done[dev] = true;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ ordered split-K combine
+// out[r, c] = (accumulate ? out[r, c] : 0) + part[0][r, c] + part[1][r, c] + ... in that order: the deterministic second half of
+// every split-K launch (the contraction kernels write one scratch slice per split with plain stores).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, const int splits, const long long split_stride, const int rows, const int cols, const long long ldp, float* __restrict__ out, const long long ldo, const int accumulate, const int vec)
+{
+	if (vec)
+	{
+		const int cv = cols >> 2;
+		const long long total = (long long)rows * cv;
+		for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+		{
+			const int r = (int)(i / cv), c = (int)(i - (long long)r * cv) << 2;
+			const float* src = part + (long long)r * ldp + c;
+			float* const dst = out + (long long)r * ldo + c;
+			float4 acc = accumulate ? *reinterpret_cast<const float4*>(dst) : make_float4(0.f, 0.f, 0.f, 0.f);
+			int k = 0;
+			for (; k + 1 < splits; k += 2, src += 2 * split_stride)
+			{
+				const float4 u = *reinterpret_cast<const float4*>(src), v = *reinterpret_cast<const float4*>(src + split_stride);
+				acc.x += u.x, acc.y += u.y, acc.z += u.z, acc.w += u.w;
+				acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+			}
+			if (k < splits)
+			{
+				const float4 u = *reinterpret_cast<const float4*>(src);
+				acc.x += u.x, acc.y += u.y, acc.z += u.z, acc.w += u.w;
+			}
+			*reinterpret_cast<float4*>(dst) = acc;
+		}
+	} else {
+		const long long total = (long long)rows * cols;
+		for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+		{
+			const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+			const float* src = part + (long long)r * ldp + c;
+			float* const dst = out + (long long)r * ldo + c;
+			float acc = accumulate ? *dst : 0.f;
+			for (int k = 0; k < splits; k++, src += split_stride)
+				acc += *src;
+			*dst = acc;
+		}
+	}
+}
+static int splitk_reduce(cudaStream_t stream, const float* part, int splits, long long split_stride, int rows, int cols, long long ldp, float* out, long long ldo, int accumulate)
+{
+	const int vec = cols % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0 && split_stride % 4 == 0 && ((((uintptr_t)part) | ((uintptr_t)out)) & 15) == 0;
+	const long long work = (long long)rows * (vec ? cols / 4 : cols);
+	long long blocks = (work + 255) / 256;
+	if (blocks > (long long)num_sms() * 8)
+		blocks = (long long)num_sms() * 8;
+	if (blocks < 1)
+		blocks = 1;
+	splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(part, splits, split_stride, rows, cols, ldp, out, ldo, accumulate, vec);
+	count_launch();
+	const cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error("splitk_reduce_kernel", e);
+		return -1;
+	}
+	return 0;
+}
+// the largest split factor <= splits whose slices fit the scratch and none of which is empty
+static int fit_splits(int splits, int k_iters, size_t slice_bytes, const Scratch& scratch)
+{
+	if (splits <= 1 || !scratch.ptr || slice_bytes == 0)
+		return 1;
+	const size_t room = scratch.bytes / slice_bytes;
+	long long k = splits;
+	if ((size_t)k > room)
+		k = (long long)room;
+	while (k > 1 && (long long)((k_iters + k - 1) / k) * (k - 1) >= k_iters)
+		k--;
+	return (int)(k < 1 ? 1 : k);
+}
+
 // One-shot request (per host thread) for per-column output statistics from the next forward-shaped launch: set by the fused
 // convolution + batch-norm command, consumed (and cleared) by launch_umma_persistent when the launch qualifies.
 struct StatsRequest {
@@ -129,17 +240,9 @@ static int launch_umma(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 {
 	using S = UmmaSmem<BN, STAGES>;
 	auto kern = umma_gemm_kernel<AMODE, BMODE, BN, STAGES>;
-	static bool configured = false;
-	if (!configured)
-	{
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-		if (e != cudaSuccess)
-		{
-			set_last_error("cudaFuncSetAttribute(umma_gemm_kernel)", e);
-			return -1;
-		}
-		configured = true;
-	}
+	static bool configured[MAX_DEVICES];
+	if (ensure_dynamic_smem(kern, S::TOTAL, configured, "cudaFuncSetAttribute(umma_gemm_kernel)"))
+		return -1;
 	dim3 grid(grid_x, grid_y, p.grid_taps * p.splits);
 	t_stats_request.part = 0; // this kernel does not produce statistics: the requester sees rows_out == 0
 	kern<<<grid, 192, S::TOTAL, stream>>>(tmA, tmB, p);
@@ -153,42 +256,18 @@ static int launch_umma(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 	return 0;
 }
 
-template <int AMODE, int BMODE, int BN, int STAGES, int EPIW>
+template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0>
 static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p)
 {
-	using S = UmmaPersistentSmem<BN, STAGES, EPIW>;
-	auto kern = umma_gemm_persistent_kernel<AMODE, BMODE, BN, STAGES, EPIW>;
-	static bool configured = false;
-	if (!configured)
-	{
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-		if (e != cudaSuccess)
-		{
-			set_last_error("cudaFuncSetAttribute(umma_gemm_persistent_kernel)", e);
-			return -1;
-		}
-		configured = true;
-	}
+	using S = UmmaPersistentSmem<BN, STAGES, EPIW, X3>;
+	auto kern = umma_gemm_persistent_kernel<AMODE, BMODE, BN, STAGES, EPIW, X3>;
+	static bool configured[MAX_DEVICES];
+	if (ensure_dynamic_smem(kern, S::TOTAL, configured, "cudaFuncSetAttribute(umma_gemm_persistent_kernel)"))
+		return -1;
 	const long long tiles = (long long)((p.M + UMMA_BLOCK_M - 1) / UMMA_BLOCK_M) * ((p.N + BN - 1) / BN) * p.grid_taps * p.splits;
 	const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
 	UmmaGemmParams q = p;
-	q.stats = 0;
-	if (t_stats_request.part)
-	{
-		const StatsRequest r = t_stats_request;
-		t_stats_request.part = 0;
-		if (AMODE != OP_MN2D && BMODE == OP_K2D && p.splits == 1 && p.grid_taps == 1 && !p.accumulate && p.rowmap.mode == 0 && p.N % 32 == 0 && grid <= r.max_rows)
-		{
-			const cudaError_t e = cudaMemsetAsync(r.part, 0, (size_t)grid * 2 * p.N * sizeof(float), stream);
-			if (e != cudaSuccess)
-			{
-				set_last_error("memset(conv stats)", e);
-				return -1;
-			}
-			q.stats = r.part;
-			*r.rows_out = grid;
-		}
-	}
+	q.stats = 0, q.stats_rows = 0;
 	// TMA tile stores for the plain "write the tile" epilogue (dense row-major output, no split-K, no accumulate)
 	CUtensorMap tmC = tmA;
 	static int tma_store_enabled = -1;
@@ -201,6 +280,23 @@ static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, c
 	if (tma_store_enabled && p.splits == 1 && p.grid_taps == 1 && !p.accumulate && p.rowmap.mode == 0 && p.N % 4 == 0 && (!p.bias || (((uintptr_t)p.bias) & 15) == 0) &&
 		make_map_2d(&tmC, p.out, p.M, p.N, p.rowmap.ld, 32, 32, false, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
 		q.tma_store = 1;
+	if (t_stats_request.part)
+	{
+		const StatsRequest r = t_stats_request;
+		t_stats_request.part = 0;
+		// forward-shaped launches only; the statistics ride on the TMA-store epilogue (one slot row per CTA and warp quarter)
+		if (q.tma_store && AMODE != OP_MN2D && BMODE == OP_K2D && p.N % 32 == 0 && grid * 4 <= r.max_rows)
+		{
+			const cudaError_t e = cudaMemsetAsync(r.part, 0, (size_t)grid * 4 * p.N * sizeof(float), stream); // the count plane
+			if (e != cudaSuccess)
+			{
+				set_last_error("memset(conv stats)", e);
+				return -1;
+			}
+			q.stats = r.part, q.stats_rows = grid * 4;
+			*r.rows_out = grid * 4;
+		}
+	}
 	kern<<<grid, S::THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, q);
 	count_launch();
 	cudaError_t e = cudaGetLastError();
@@ -235,6 +331,13 @@ static bool use_persistent() { return persistent_mode() != 0; }
 template <int AMODE, int BMODE>
 static int launch_umma_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p, int bn)
 {
+	if (t_x3)
+	{
+		// 2 x (A + B) per stage: BN <= 128; four epilogue warps + four split warps
+		if (bn == 64)
+			return launch_umma_persistent<AMODE, BMODE, 64, 4, 4, 1>(stream, tmA, tmB, p);
+		return launch_umma_persistent<AMODE, BMODE, 128, 3, 4, 1>(stream, tmA, tmB, p);
+	}
 	const int mode = persistent_mode();
 	const int iters_per_tile = (p.k_iters + p.splits - 1) / p.splits;
 	bool persistent = mode != 0;
@@ -272,7 +375,7 @@ static int pick_bn(int N)
 	int bn = e ? atoi(e) : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
 	if (bn != 64 && bn != 128 && bn != 256)
 		bn = 128;
-	if (bn == 256 && !use_persistent())
+	if (bn == 256 && (!use_persistent() || t_x3))
 		bn = 128;
 	return bn;
 }
@@ -349,8 +452,30 @@ static int pick_splits(long long tiles, int k_iters, int min_iters_per_split)
 	return 1;
 }
 
-int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long long lda, int trans_a, const float* b, long long ldb, int trans_b, float* c, long long ldc, const float* bias, int accumulate)
+// launches the kernel family for (AMODE, BMODE); when p.splits > 1 the partial tiles land in scratch slices [rows, cols] (pitch
+// ldp) that are then added into `out` in split order
+template <int AMODE, int BMODE>
+static int launch_umma_split(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaGemmParams& p, int bn, const Scratch& scratch, int rows, int cols, long long ldo, int accumulate)
 {
+	if (p.splits <= 1)
+	{
+		p.splits = 1, p.split_out_stride = 0, p.accumulate = accumulate;
+		return launch_umma_bn<AMODE, BMODE>(stream, tmA, tmB, p, bn);
+	}
+	float* const out = p.out;
+	p.out = (float*)scratch.ptr;
+	p.rowmap.mode = 0, p.rowmap.ld = ldo; // slices have the layout of the output itself (same pitch), packed one after the other
+	p.split_out_stride = (long long)rows * ldo;
+	p.accumulate = 0;
+	const int rc = launch_umma_bn<AMODE, BMODE>(stream, tmA, tmB, p, bn);
+	if (rc)
+		return rc;
+	return splitk_reduce(stream, (const float*)scratch.ptr, p.splits, p.split_out_stride, rows, cols, ldo, out, ldo, accumulate);
+}
+
+int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long long lda, int trans_a, const float* b, long long ldb, int trans_b, float* c, long long ldc, const float* bias, int accumulate, const Scratch& scratch, int x3)
+{
+	const X3Scope math(x3);
 	if (!tma_api_init() || M <= 0 || N <= 0 || K <= 0)
 		return 1;
 	const int bn = pick_bn(N);
@@ -373,21 +498,31 @@ int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long lon
 	p.M = M, p.N = N;
 	p.k_iters = (K + UMMA_BLOCK_K - 1) / UMMA_BLOCK_K;
 	p.chunks_per_tap = p.k_iters;
-	p.out = c, p.bias = bias, p.accumulate = accumulate;
+	p.out = c, p.bias = bias;
 	p.rowmap.mode = 0, p.rowmap.ld = ldc;
 	p.idesc = umma_instr_desc(2, trans_a, !trans_b, UMMA_BLOCK_M, bn);
 	const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn);
-	p.splits = pick_splits(tiles, p.k_iters, 8);
-	if (p.splits > 1 && !accumulate)
+	// split-K slices are dense [M, Np] tiles in the scratch (pitch Np = N rounded up to 4 floats)
+	const long long ldp = ((long long)N + 3) & ~3ll;
+	p.splits = fit_splits(pick_splits(tiles, p.k_iters, 8), p.k_iters, (size_t)M * ldp * sizeof(float), scratch);
+	if (p.splits > 1)
 	{
-		// split-K partial sums are combined with red.add: start from zero
-		cudaError_t e = cudaMemset2DAsync(c, ldc * 4, 0, (size_t)N * 4, M, stream);
-		if (e != cudaSuccess)
-		{
-			set_last_error("memset(split-K)", e);
-			return -1;
-		}
+		float* const part = (float*)scratch.ptr;
+		p.out = part, p.rowmap.ld = ldp, p.split_out_stride = (long long)M * ldp, p.accumulate = 0;
+		int rc;
+		if (!trans_a && trans_b)
+			rc = launch_umma_bn<OP_K2D, OP_K2D>(stream, tmA, tmB, p, bn);
+		else if (!trans_a && !trans_b)
+			rc = launch_umma_bn<OP_K2D, OP_MN2D>(stream, tmA, tmB, p, bn);
+		else if (trans_a && trans_b)
+			rc = launch_umma_bn<OP_MN2D, OP_K2D>(stream, tmA, tmB, p, bn);
+		else
+			rc = launch_umma_bn<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn);
+		if (rc)
+			return rc;
+		return splitk_reduce(stream, part, p.splits, p.split_out_stride, M, N, ldp, c, ldc, accumulate);
 	}
+	p.accumulate = accumulate;
 	if (!trans_a && trans_b)
 		return launch_umma_bn<OP_K2D, OP_K2D>(stream, tmA, tmB, p, bn);
 	if (!trans_a && !trans_b)
@@ -420,15 +555,16 @@ static bool conv_shape_consistent(const ConvGeom& g)
 		g.R * g.S <= UMMA_MAX_TAPS && g.C % 4 == 0 && g.K % 4 == 0;
 }
 
-int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b)
+int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, const Scratch& scratch, int x3)
 {
+	const X3Scope math(x3);
 	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g))
 		return 1;
 	const long long M = (long long)g.N * g.P * g.Q;
 	if (M > 0x7fffffffll)
 		return 1;
 	if (conv_is_pointwise(g)) // a plain [NHW, C] x [K, C]^T GEMM
-		return gemm_tf32(stream, (int)M, g.K, g.C, a, g.C, 0, w, g.C, 1, b, g.K, bias, 0);
+		return gemm_tf32(stream, (int)M, g.K, g.C, a, g.C, 0, w, g.C, 1, b, g.K, bias, 0, scratch, x3);
 	const int bn = pick_bn(g.K);
 	CUtensorMap tmA, tmB;
 	if (!make_map_im2col(&tmA, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, 32, UMMA_BLOCK_M))
@@ -458,12 +594,13 @@ int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, cons
 	return launch_umma_bn<OP_IM2COL, OP_K2D>(stream, tmA, tmB, p, bn);
 }
 
-int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a)
+int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a, const Scratch& scratch, int x3)
 {
+	const X3Scope math(x3);
 	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g) || !conv_in_contiguous(g))
 		return 1;
 	if (conv_is_pointwise(g)) // dA[NHW, C] = dB[NHW, K] x W[K, C]
-		return gemm_tf32(stream, g.N * g.H * g.W, g.C, g.K, grad_b, g.K, 0, w, g.C, 0, grad_a, g.C, 0, 0);
+		return gemm_tf32(stream, g.N * g.H * g.W, g.C, g.K, grad_b, g.K, 0, w, g.C, 0, grad_a, g.C, 0, 0, scratch, x3);
 	const int bn = pick_bn(g.C);
 	const long long rsc = (long long)g.R * g.S * g.C;
 	CUtensorMap tmB;
@@ -582,17 +719,9 @@ static int launch_wgrad_taps(cudaStream_t stream, const CUtensorMap& tmX, const 
 	constexpr int STAGES = 4;
 	using S = WgradTapsSmem<BN, STAGES>;
 	auto kern = umma_wgrad_taps_kernel<BN, STAGES>;
-	static bool configured = false;
-	if (!configured)
-	{
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-		if (e != cudaSuccess)
-		{
-			set_last_error("cudaFuncSetAttribute(umma_wgrad_taps_kernel)", e);
-			return -1;
-		}
-		configured = true;
-	}
+	static bool configured[MAX_DEVICES];
+	if (ensure_dynamic_smem(kern, S::TOTAL, configured, "cudaFuncSetAttribute(umma_wgrad_taps_kernel)"))
+		return -1;
 	kern<<<dim3(tiles, p.splits), 192, S::TOTAL, stream>>>(tmX, tmG, p);
 	count_launch();
 	cudaError_t e = cudaGetLastError();
@@ -615,8 +744,9 @@ static bool wgrad_taps_enabled()
 	return v != 0;
 }
 
-int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate)
+int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, const Scratch& scratch, int x3)
 {
+	const X3Scope math(x3);
 	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g))
 		return 1;
 	const long long npq = (long long)g.N * g.P * g.Q;
@@ -637,27 +767,19 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 	p.rowmap.mode = 0, p.rowmap.ld = rsc;
 	p.idesc = umma_instr_desc(2, 1, 1, UMMA_BLOCK_M, bn);
 	const long long tiles = (long long)((g.K + 127) / 128) * ((g.C + bn - 1) / bn) * g.R * g.S;
-	p.splits = pick_splits(tiles, p.k_iters, 16);
-	if (p.splits > 1 && !accumulate)
-	{
-		cudaError_t e = cudaMemsetAsync(grad_w, 0, (size_t)g.K * rsc * 4, stream);
-		if (e != cudaSuccess)
-		{
-			set_last_error("memset(wgrad)", e);
-			return -1;
-		}
-	}
-	p.accumulate = accumulate;
+	// split-K slices have the layout of dW itself ([K, RSC]); splitk_reduce adds them (and the old dW when accumulating)
+	const size_t dw_bytes = (size_t)g.K * rsc * sizeof(float);
+	p.splits = fit_splits(pick_splits(tiles, p.k_iters, 16), p.k_iters, dw_bytes, scratch);
 	if (conv_is_pointwise(g))
 	{
 		// B = a: [NHW, C], also MN-major
 		if (!make_map_2d(&tmB, a, npq, g.C, g.C, 32, UMMA_BLOCK_K, true))
 			return 1;
-		return launch_umma_bn<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn);
+		return launch_umma_split<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn, scratch, g.K, (int)rsc, rsc, accumulate);
 	}
 	if (!make_map_im2col(&tmB, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, 32, UMMA_BLOCK_K, true))
 		return 1;
-	if (g.K <= 64 && g.C % 32 == 0 && g.C <= 128 && wgrad_taps_enabled())
+	if (g.K <= 64 && g.C % 32 == 0 && g.C <= 128 && wgrad_taps_enabled() && !t_x3)
 	{
 		WgradTapsParams w;
 		memset(&w, 0, sizeof(w));
@@ -666,7 +788,7 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 		const int tiles_m = (w.taps + max_tpt - 1) / max_tpt;
 		w.taps_per_tile = (w.taps + tiles_m - 1) / tiles_m; // balanced: 9 taps of 32 channels -> 3 + 3 + 3
 		w.k_iters = p.k_iters;
-		w.splits = pick_splits(tiles_m, w.k_iters, 16);
+		w.splits = fit_splits(pick_splits(tiles_m, w.k_iters, 16), w.k_iters, dw_bytes, scratch);
 		w.P = g.P, w.Q = g.Q, w.stride_h = g.stride_h, w.stride_w = g.stride_w, w.base_h = -g.pad_h0, w.base_w = -g.pad_w0;
 		for (int r = 0; r < g.R; r++)
 			for (int s = 0; s < g.S; s++)
@@ -675,16 +797,16 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 		w.mn_lbo = p.mn_lbo, w.mn_sbo = p.mn_sbo, w.mn_layout = p.mn_layout;
 		const int wbn = g.K <= 32 ? 32 : 64;
 		w.idesc = umma_instr_desc(2, 1, 1, UMMA_BLOCK_M, wbn);
-		if (!accumulate && !(p.splits > 1)) // the epilogue always adds: dW starts from zero (the generic path above only clears it for split-K)
-		{
-			cudaError_t e = cudaMemsetAsync(grad_w, 0, (size_t)g.K * rsc * 4, stream);
-			if (e != cudaSuccess)
-			{
-				set_last_error("memset(wgrad)", e);
-				return -1;
-			}
-		}
-		return wbn == 32 ? launch_wgrad_taps<32>(stream, tmB, tmA, w, tiles_m) : launch_wgrad_taps<64>(stream, tmB, tmA, w, tiles_m);
+		// one split and nothing to add to: the tile stores go straight to dW; otherwise slices + ordered combine
+		const bool direct = w.splits == 1 && !accumulate;
+		if (!direct && (!scratch.ptr || scratch.bytes < dw_bytes * (size_t)w.splits))
+			return 1;
+		w.out = direct ? grad_w : (float*)scratch.ptr;
+		w.split_out_stride = (long long)g.K * rsc;
+		const int rc = wbn == 32 ? launch_wgrad_taps<32>(stream, tmB, tmA, w, tiles_m) : launch_wgrad_taps<64>(stream, tmB, tmA, w, tiles_m);
+		if (rc || direct)
+			return rc;
+		return splitk_reduce(stream, (const float*)scratch.ptr, w.splits, w.split_out_stride, g.K, (int)rsc, rsc, grad_w, rsc, accumulate);
 	}
 	p.grid_taps = g.R * g.S;
 	p.grid_tap_out_stride = g.C;
@@ -698,7 +820,7 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 			p.tap_off_h[t] = (unsigned short)(r * g.dil_h);
 			p.tap_off_w[t] = (unsigned short)(s * g.dil_w);
 		}
-	return launch_umma_bn<OP_MN2D, OP_IM2COL>(stream, tmA, tmB, p, bn);
+	return launch_umma_split<OP_MN2D, OP_IM2COL>(stream, tmA, tmB, p, bn, scratch, g.K, (int)rsc, rsc, accumulate);
 }
 
 // ------------------------------------------------------------------------------------------------ explicit im2col
@@ -711,7 +833,13 @@ size_t conv_im2col_workspace_bytes(const ConvGeom& g)
 {
 	const size_t kp = im2col_kp(g);
 	// patches [NPQ, Kp] + packed filters [K, Kp] + packed filter gradient [K, Kp]
-	return ((size_t)g.N * g.P * g.Q * kp + 2 * (size_t)g.K * kp) * sizeof(float) + 512;
+	return ((size_t)g.N * g.P * g.Q * kp + 2 * (size_t)g.K * kp) * sizeof(float) + 1024 + CONTRACT_SCRATCH_BYTES;
+}
+static Scratch im2col_scratch(const ConvGeom& g, void* workspace)
+{
+	const size_t used = (((size_t)g.N * g.P * g.Q * im2col_kp(g) + 2 * (size_t)g.K * im2col_kp(g)) * sizeof(float) + 511) & ~(size_t)511;
+	Scratch s = { (char*)workspace + used, CONTRACT_SCRATCH_BYTES };
+	return s;
 }
 // patches[m, (r, s, c)] = a[n, p * stride - pad + r * dil, q * stride - pad + s * dil, c] (0 outside / in the padding columns)
 // One thread = one 16-byte store (4 consecutive k of one patch row); k -> (tap row offset, tap column offset, channel) comes
@@ -775,7 +903,7 @@ static int run_im2col(cudaStream_t stream, const ConvGeom& g, const float* a, fl
 	}
 	return 0;
 }
-int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, void* workspace)
+int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, void* workspace, int x3)
 {
 	if (!tma_api_init() || !im2col_applicable(g) || !workspace)
 		return 1;
@@ -787,9 +915,9 @@ int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* 
 		return -1;
 	pack_filters_kernel<<<(g.K * kp + 255) / 256, 256, 0, stream>>>((float*)w, wp, g.K, rsc, kp, 0, 0);
 	count_launch();
-	return gemm_tf32(stream, (int)m, g.K, kp, patches, kp, 0, wp, kp, 1, b, g.K, bias, 0);
+	return gemm_tf32(stream, (int)m, g.K, kp, patches, kp, 0, wp, kp, 1, b, g.K, bias, 0, im2col_scratch(g, workspace), x3);
 }
-int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, void* workspace)
+int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, void* workspace, int x3)
 {
 	if (!tma_api_init() || !im2col_applicable(g) || !workspace)
 		return 1;
@@ -800,7 +928,7 @@ int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* 
 	if (run_im2col(stream, g, a, patches, kp))
 		return -1;
 	// dWp[K, Kp] = grad_b^T [K, NPQ] * patches [NPQ, Kp]
-	const int rc = gemm_tf32(stream, g.K, kp, (int)m, grad_b, g.K, 1, patches, kp, 0, dwp, kp, 0, 0);
+	const int rc = gemm_tf32(stream, g.K, kp, (int)m, grad_b, g.K, 1, patches, kp, 0, dwp, kp, 0, 0, im2col_scratch(g, workspace), x3);
 	if (rc)
 		return rc;
 	pack_filters_kernel<<<(g.K * kp + 255) / 256, 256, 0, stream>>>(grad_w, dwp, g.K, rsc, kp, 1, accumulate);

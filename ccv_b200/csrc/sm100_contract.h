@@ -19,23 +19,39 @@ struct ConvGeom {
 	long long bn, bh, bw;
 };
 
+// Device scratch of the calling command (a slice of the stream workspace, valid for the work this call enqueues).  Split-K
+// launches write one partial tile set per split into it and a second kernel adds the slices in a fixed order (deterministic,
+// replay-stable results instead of red.global.add); with too little scratch the split factor is reduced, down to no split.
+struct Scratch {
+	void* ptr;
+	size_t bytes;
+};
+// what a caller should ask the stream workspace for so that no split factor has to be reduced (tiles x splits never exceeds
+// ~2 CTAs per SM plus one wave of 128 x 256 fp32 tiles)
+constexpr size_t CONTRACT_SCRATCH_BYTES = (size_t)96 << 20;
+
+// x3 (last argument of every entry point): 0 = one-pass TF32, 1 = error-compensated 3xTF32 (fp32-grade products, a third of
+// the tensor rate; sm100_umma_persistent.cuh).
 // returns 0 on success, 1 if the shape/alignment cannot use the TMA+tcgen05 path (caller falls back to FFMA), <0 on CUDA error.
 // C[M, N] (+)= op(A) * op(B) + bias; A is [M, K] (lda) or, if trans_a, [K, M]; B is [K, N] (ldb) or, if trans_b, [N, K].
-int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long long lda, int trans_a, const float* b, long long ldb, int trans_b, float* c, long long ldc, const float* bias, int accumulate);
-int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b);
-int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a);
-int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate);
+int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long long lda, int trans_a, const float* b, long long ldb, int trans_b, float* c, long long ldc, const float* bias, int accumulate, const Scratch& scratch, int x3 = 0);
+int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, const Scratch& scratch, int x3 = 0);
+int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a, const Scratch& scratch, int x3 = 0);
+int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, const Scratch& scratch, int x3 = 0);
 
-// Ask the NEXT conv_fprop_tf32 / gemm_tf32 launch of this host thread to also produce per-column sums of its output:
-// part[row][0..N) = sum(v), part[row][N..2N) = sum(v * v) over the output rows one CTA wrote; *rows_out = number of rows
-// written (0 when the launch took a path without this epilogue; the request is consumed either way).
+// Ask the NEXT conv_fprop_tf32 / gemm_tf32 launch of this host thread to also produce per-column statistics of its output
+// (batch-norm forward fused into the producing convolution).  `part` holds four planes of max_rows x N floats -- count,
+// shift k, sum(v - k), sum((v - k)^2) -- one row per (CTA, epilogue warp quarter); *rows_out = rows in use (the plane
+// pitch is *rows_out x N; 0 when the launch took a path without this epilogue; the request is consumed either way).
+// Combined by bn_fwd_train_f32 (ext_part / ext_rows) with a Chan merge in double precision.
 void conv_stats_request(float* part, int max_rows, int* rows_out);
 
 // Small-channel convolutions (C not a multiple of 4, e.g. the 3-channel stem): explicit im2col into `workspace`
 // ([N*P*Q, Kp] with Kp = R*S*C rounded up to 32, zero padded) followed by the tensor-core GEMM.  Returns 1 when not applicable.
 size_t conv_im2col_workspace_bytes(const ConvGeom& g);
-int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, void* workspace);
-int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, void* workspace);
+// (the workspace must hold conv_im2col_workspace_bytes(g), which includes CONTRACT_SCRATCH_BYTES for the GEMM's split-K slices)
+int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, void* workspace, int x3 = 0);
+int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, void* workspace, int x3 = 0);
 
 // CUDA-core fp32 versions of the same contractions: any stride/alignment, groups, exact fp32 products.
 int gemm_ffma(cudaStream_t stream, int M, int N, int K, const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c, long long ldc, const float* bias, int accumulate);

@@ -41,7 +41,7 @@ int pool_avg_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, flo
 // ---- batch norm over [outer, C, inner] (NHWC: inner = 1; NCHW: outer = N, inner = H * W) ----------------------
 // training forward: writes y, saved_mean, saved_inv_std and updates the running mean / var in place
 // fuse_relu: y = relu(bn(x)) in the same pass (BATCH_NORM_FORWARD followed by an in-place RELU_FORWARD)
-// ext_part / ext_rows: per-channel sum(x), sum(x * x) partial rows [ext_rows][2C] produced by the convolution that wrote x
+// ext_part / ext_rows: per-channel statistics slots (four planes [ext_rows][C]: count, shift, shifted sum, shifted sum of squares) produced by the convolution that wrote x
 // (conv_stats_request); the statistics pass over x is then skipped
 int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu, const float* ext_part = 0, int ext_rows = 0);
 size_t bn_workspace_bytes(int C);

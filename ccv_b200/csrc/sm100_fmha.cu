@@ -469,7 +469,11 @@ int sdpa_forward_f16(cudaStream_t stream, const SdpaGeom& g, int is_bf16, const 
 	p.v_sbo = (uint32_t)env_int("CCV_NNC_SM100_FMHA_V_SBO", 1024);
 	p.v_layout = (uint32_t)env_int("CCV_NNC_SM100_FMHA_V_LAYOUT", 2);
 	p.v_kstep = (uint32_t)env_int("CCV_NNC_SM100_FMHA_V_KSTEP", 2048);
-	static bool configured = false;
+	// the attribute is per device: one flag per device (a process may drive several GPUs)
+	static bool configured_on[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	bool& configured = configured_on[dev & 63];
 	if (!configured)
 	{
 		cudaError_t e = cudaFuncSetAttribute(fmha_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem::TOTAL);

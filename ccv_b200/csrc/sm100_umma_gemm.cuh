@@ -8,7 +8,7 @@
 //
 //   warp 0   TMA producer: cp.async.bulk.tensor (tile mode or im2col mode) -> 128B-swizzled smem stages, mbarrier tx
 //   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 8, kind::tf32), tcgen05.commit
-//   warp 2-5 epilogue: tcgen05.ld 32x32b -> registers -> (+bias, +C) -> 128-bit global stores / red.add (split-K)
+//   warp 2-5 epilogue: tcgen05.ld 32x32b -> registers -> (+bias, +C) -> 128-bit global stores (split-K: into this split's scratch slice)
 //
 // Two CTAs are resident per SM (3 stages x 32 KB at BN = 128), so one CTA's epilogue overlaps the other's main loop.
 #pragma once
@@ -39,7 +39,10 @@ struct UmmaGemmParams {
 	int M, N;
 	int k_iters;        // BLOCK_K iterations over the whole reduction (all taps x chunks)
 	int chunks_per_tap; // k-iteration it -> tap = it / chunks_per_tap, chunk = it % chunks_per_tap
-	int splits;         // split-K factor; gridDim.z = grid_taps * splits
+	int splits;         // split-K factor; gridDim.z = grid_taps * splits.  Split s writes its partial tile to out + s * split_out_stride
+	                    // (a scratch slice per split, plain stores); splitk_reduce_kernel then adds the slices in a fixed order, so the
+	                    // result does not depend on CTA arrival order (no red.global.add anywhere in the contraction kernels)
+	long long split_out_stride;
 	int grid_taps;      // > 1 only for wgrad: the filter tap is a grid dimension
 	long long grid_tap_out_stride; // output column offset per grid tap
 	// im2col geometry of the operand that uses OP_IM2COL: base pixel p -> (w, h, n) TMA coordinates
@@ -54,19 +57,18 @@ struct UmmaGemmParams {
 	int accumulate; // 1: D += existing output (CCV_NNC_ACCUMULATE_OUTPUT)
 	float alpha;    // scales the product (1 for the reference's commands)
 	UmmaRowMap rowmap;
-	// optional per-column statistics of the output (batch-norm forward fused into the producing convolution; persistent kernel
-	// only): stats + blockIdx.x * 2 * N receives sum(v) in [0, N) and sum(v * v) in [N, 2N) over the rows this CTA wrote
+	// optional per-column statistics of the output (batch-norm forward fused into the producing convolution; persistent kernel,
+	// TMA-store epilogue only).  Four planes of stats_rows x N floats: count, shift k, sum(v - k), sum((v - k)^2).  Row
+	// blockIdx.x * 4 + quarter belongs to one epilogue warp quarter of one CTA and every (row, column) slot to exactly one thread,
+	// which updates it with plain loads / stores tile after tile: no atomics, a fixed summation order, and a per-slot shift (the
+	// first value seen) that keeps the one-pass variance well conditioned.  The count plane must be zero on entry.
 	float* stats;
+	int stats_rows;
 	int tma_store; // persistent kernel: the epilogue writes 32 x 32 chunks with TMA tile stores through the output tensor map
 	uint32_t idesc;
 	// smem descriptor fields for MN-major operands (layout SWIZZLE_128B_BASE32B: 128 B of MN x 4 k-rows per atom)
 	uint32_t mn_lbo, mn_sbo, mn_layout;
 };
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
-{
-	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 template <int BN, int STAGES>
 struct UmmaSmem {
@@ -228,10 +230,9 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
 			const int j = rem - i * p.rowmap.Qc;
 			row_off = n * p.rowmap.n_stride + i * p.rowmap.h_stride + j * p.rowmap.w_stride;
 		}
-		float* const orow = p.out + row_off + (long long)gtap * p.grid_tap_out_stride;
+		float* const orow = p.out + row_off + (long long)gtap * p.grid_tap_out_stride + (long long)split * p.split_out_stride;
 		const bool row_ok = row < p.M;
 		const bool vec_ok = ((((uintptr_t)orow) & 15) == 0);
-		const bool use_atomic = p.splits > 1;
 		const bool add_bias = p.bias != 0 && split == 0;
 #pragma unroll 1
 		for (int c = 0; c < BN / 32; c++)
@@ -263,34 +264,22 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
 			float* const o = orow + col0;
 			if (col0 + 32 <= p.N && vec_ok)
 			{
-				if (use_atomic)
+				if (p.accumulate)
 				{
 #pragma unroll
 					for (int i = 0; i < 32; i += 4)
-						red_add_v4(o + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-				} else {
-					if (p.accumulate)
 					{
-#pragma unroll
-						for (int i = 0; i < 32; i += 4)
-						{
-							const float4 e = *reinterpret_cast<const float4*>(o + i);
-							v[i] += e.x, v[i + 1] += e.y, v[i + 2] += e.z, v[i + 3] += e.w;
-						}
+						const float4 e = *reinterpret_cast<const float4*>(o + i);
+						v[i] += e.x, v[i + 1] += e.y, v[i + 2] += e.z, v[i + 3] += e.w;
 					}
-#pragma unroll
-					for (int i = 0; i < 32; i += 4)
-						*reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
 				}
+#pragma unroll
+				for (int i = 0; i < 32; i += 4)
+					*reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
 			} else {
 				for (int i = 0; i < 32; i++)
 					if (col0 + i < p.N)
-					{
-						if (use_atomic)
-							atomicAdd(o + i, v[i]);
-						else
-							o[i] = p.accumulate ? o[i] + v[i] : v[i];
-					}
+						o[i] = p.accumulate ? o[i] + v[i] : v[i];
 			}
 		}
 	}

@@ -7,9 +7,10 @@
 //         in the 128-byte-swizzled layout of the output tensor map and written by ONE TMA tile store; two buffers per warp,
 //         cp.async.bulk.wait_group.read keeps one store in flight (profiles/r01_ncu_expand_1x1_persistent_8epiwarps.txt: the
 //         row-store variant below was instruction-issue-bound);
-//       - otherwise: transposed through a pitch-36 scratch tile and written with 128-bit stores / red.global.add.v4 in which
-//         every 128-byte line is touched whole (4 rows x 128 B per warp instruction);
-//     either way it can also accumulate per-column sum(v), sum(v * v) of what it writes (batch-norm statistics, p.stats).
+//       - otherwise (strided rows, accumulate, split-K scratch slices): transposed through a pitch-36 scratch tile and written
+//         with 128-bit stores in which every 128-byte line is touched whole (4 rows x 128 B per warp instruction);
+//     the TMA-store form can also fold per-column shifted sums of what it writes into per-(CTA, warp quarter) slots
+//     (batch-norm statistics, p.stats): plain loads / stores by the one thread that owns the slot -- deterministic.
 // Roles: warp 0 TMA producer, warp 1 TMEM allocator + tcgen05.mma issuer, warps 2.. epilogue (EPIW = 4: one warp per TMEM
 // lane quarter; 8: two, each taking every other 32-column chunk -- with a single warp per scheduler the dependent
 // LDTM -> STS -> LDS -> STG chain was latency-bound, profiles/r01_ncu_gemm_n256k64_persistent_4epiwarps.txt).
@@ -18,32 +19,42 @@
 
 namespace sm100 {
 
-template <int BN, int STAGES, int EPIW>
+// X3 = 1 selects the error-compensated "3xTF32" form (CCV_NNC_SM100_ALGO_3XTF32): the operands arrive as raw fp32
+// (tensor map data type FLOAT32, no rounding), four extra warps split every staged element into hi = x with the low 13
+// mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32), hi rewritten in place and lo into a
+// second buffer of the stage, and the issuer runs three MMAs per k-step -- lo*hi + hi*lo + hi*hi (lo*lo ~ 2^-22 is dropped)
+// -- into the same fp32 TMEM accumulator.  The product then carries ~2^-21 relative error per term instead of TF32's 2^-11:
+// fp32-grade results (the reference's fp32 GEMM is CUBLAS_COMPUTE_32F, lib/nnc/gpu/ccv_nnc_compat.cu:786-803) at a third of
+// the tensor rate.
+template <int BN, int STAGES, int EPIW, int X3 = 0>
 struct UmmaPersistentSmem {
 	static constexpr int A_BYTES = UMMA_BLOCK_M * UMMA_BLOCK_K * 4;
 	static constexpr int B_BYTES = BN * UMMA_BLOCK_K * 4;
-	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+	static constexpr int RAW_BYTES = A_BYTES + B_BYTES;        // what the TMA fills per stage
+	static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1); // X3: [A hi][B hi][A lo][B lo]
+	static constexpr int XFORM_WARPS = X3 ? 4 : 0;
 	static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
 	static constexpr int EPI_PITCH = 36;                       // floats per scratch row: 16-byte aligned, bank-shifted
 	static constexpr int EPI_WARPS = EPIW; // 4: one warp per TMEM lane quarter; 8: two, each taking every other 32-column chunk
 	static constexpr int EPI_WARP_BYTES = 8192;                // per epilogue warp: two 4 KB chunk buffers (TMA-store path) / one pitch-36 chunk
 	static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
-	static constexpr int THREADS = 64 + EPI_WARPS * 32;
+	static constexpr int THREADS = 64 + EPI_WARPS * 32 + XFORM_WARPS * 32;
 	static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
 	static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
-template <int AMODE, int BMODE, int BN, int STAGES, int EPIW>
-__global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const UmmaGemmParams p)
+template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0>
+__global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const UmmaGemmParams p)
 {
-	using S = UmmaPersistentSmem<BN, STAGES, EPIW>;
+	using S = UmmaPersistentSmem<BN, STAGES, EPIW, X3>;
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint64_t* full_bar = (uint64_t*)(smem + S::BAR_OFFSET);
 	uint64_t* empty_bar = full_bar + STAGES;
 	uint64_t* tmem_full_bar = empty_bar + STAGES; // [2]
 	uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
-	uint32_t* tmem_slot = (uint32_t*)(tmem_empty_bar + 2);
+	uint64_t* xform_bar = tmem_empty_bar + 2;     // [STAGES] (X3): the hi / lo split of the stage is in place
+	uint32_t* tmem_slot = (uint32_t*)(xform_bar + STAGES);
 
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
@@ -60,6 +71,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 		{
 			mbar_init(&full_bar[s], 1);
 			mbar_init(&empty_bar[s], 1);
+			mbar_init(&xform_bar[s], X3 ? S::XFORM_WARPS : 1);
 		}
 		for (int a = 0; a < 2; a++)
 		{
@@ -111,7 +123,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 					mbar_wait(&empty_bar[stage], phase ^ 1);
 					uint8_t* sA = smem + stage * S::STAGE_BYTES;
 					uint8_t* sB = sA + S::A_BYTES;
-					mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+					mbar_expect_tx(&full_bar[stage], S::RAW_BYTES);
 					if (AMODE == OP_K2D)
 						tma_load_2d(sA, &tmA, &full_bar[stage], chunk * UMMA_BLOCK_K, m0);
 					else if (AMODE == OP_MN2D) {
@@ -159,7 +171,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 			const uint32_t tmem_d = tmem_base + acc * BN;
 			for (int it = 0; it < n_it; it++)
 			{
-				mbar_wait(&full_bar[stage], phase);
+				mbar_wait(X3 ? &xform_bar[stage] : &full_bar[stage], phase);
 				tc_fence_after();
 				if (lane == 0)
 				{
@@ -170,7 +182,15 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 					{
 						const uint64_t da = (AMODE == OP_MN2D) ? umma_smem_desc(a_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
 						const uint64_t db = (BMODE == OP_K2D) ? umma_smem_desc(b_addr + k * 32, 16, 1024, 2) : umma_smem_desc(b_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout);
-						umma_tf32(tmem_d, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+						if (X3)
+						{
+							// the lo tiles sit RAW_BYTES behind their hi tiles (same layout): small terms first, then hi * hi
+							constexpr uint64_t LO = (uint64_t)(S::RAW_BYTES >> 4); // start-address field is in 16-byte units
+							umma_tf32(tmem_d, da + LO, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+							umma_tf32(tmem_d, da, db + LO, p.idesc, 1u);
+							umma_tf32(tmem_d, da, db, p.idesc, 1u);
+						} else
+							umma_tf32(tmem_d, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
 					}
 					umma_commit(&empty_bar[stage]);
 				}
@@ -181,6 +201,42 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 				umma_commit(&tmem_full_bar[acc]); // fires once every MMA of this tile has completed
 			__syncwarp();
 		}
+	} else if (X3 && warp >= 2 + EPIW) {
+		// ------------------------------------------------------------------ hi / lo split of every staged operand element (X3)
+		const int tid = threadIdx.x - (2 + EPIW) * 32; // 0..127
+		int stage = 0;
+		uint32_t phase = 0;
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+		{
+			const int zz = (tile / tiles_n) / tiles_m;
+			const int split = zz % p.splits;
+			const int it_begin = split * per;
+			const int n_it = min(p.k_iters, it_begin + per) - it_begin;
+			for (int it = 0; it < n_it; it++)
+			{
+				mbar_wait(&full_bar[stage], phase); // the TMA has filled the raw tiles
+				float4* const raw = reinterpret_cast<float4*>(smem + stage * S::STAGE_BYTES);
+				float4* const lo = reinterpret_cast<float4*>(smem + stage * S::STAGE_BYTES + S::RAW_BYTES);
+#pragma unroll 4
+				for (int i = tid; i < S::RAW_BYTES / 16; i += S::XFORM_WARPS * 32)
+				{
+					const float4 x = raw[i];
+					float4 h, l;
+					h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u), h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+					h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u), h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+					// x - hi is exact; an infinity keeps lo = 0 so that inf stays inf instead of turning into inf - inf
+					l.x = fabsf(x.x) < __int_as_float(0x7f800000) ? x.x - h.x : 0.f, l.y = fabsf(x.y) < __int_as_float(0x7f800000) ? x.y - h.y : 0.f;
+					l.z = fabsf(x.z) < __int_as_float(0x7f800000) ? x.z - h.z : 0.f, l.w = fabsf(x.w) < __int_as_float(0x7f800000) ? x.w - h.w : 0.f;
+					raw[i] = h;
+					lo[i] = l;
+				}
+				fence_proxy_async(); // the tensor core reads shared memory through the async proxy
+				__syncwarp();
+				if (lane == 0)
+					mbar_arrive(&xform_bar[stage]);
+				if (++stage == STAGES) { stage = 0; phase ^= 1; }
+			}
+		}
 	} else {
 		// ------------------------------------------------------------------ epilogue (warps 2..9)
 		const int quarter = warp & 3;        // TMEM lanes [32 * quarter, +32) are the ones this warp may read
@@ -190,11 +246,12 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 		int chunk_no = 0;
 		const int sub_row = lane >> 3;       // 0..3: row within a group of 4 rows
 		const int sub_col = (lane & 7) * 4;  // 0..28: first of this lane's 4 columns
-		const bool use_atomic = p.splits > 1;
 		const bool accumulate = p.accumulate != 0;
 		const float* const bias = p.bias;
 		const int N = p.N;
-		float* const stats = p.stats ? p.stats + (size_t)blockIdx.x * 2 * p.N : 0;
+		// statistics slots of this warp quarter: plane 0 of row blockIdx.x * 4 + quarter (count); planes k, s1, s2 follow at stats_plane
+		float* const stats = p.stats && p.tma_store ? p.stats + ((size_t)blockIdx.x * 4 + quarter) * p.N : 0;
+		const size_t stats_plane = (size_t)p.stats_rows * p.N;
 		int t = 0;
 		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++)
 		{
@@ -226,7 +283,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 					const int jj = rem - ii * p.rowmap.Qc;
 					off = n * p.rowmap.n_stride + ii * p.rowmap.h_stride + jj * p.rowmap.w_stride;
 				}
-				orow[i] = row < p.M ? p.out + off + (long long)gtap * p.grid_tap_out_stride : 0;
+				orow[i] = row < p.M ? p.out + off + (long long)gtap * p.grid_tap_out_stride + (long long)split * p.split_out_stride : 0;
 			}
 			mbar_wait(&tmem_full_bar[acc], acc_phase);
 			tc_fence_after();
@@ -254,7 +311,6 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 						bulk_wait_group_read<1>(); // the store issued two chunks ago has finished reading this buffer
 					__syncwarp();
 					const int col0 = n0 + c * 32;
-					const bool row_ok = m0 + quarter * 32 + lane < p.M;
 					float v[32];
 #pragma unroll
 					for (int i = 0; i < 32; i++)
@@ -269,33 +325,35 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 								v[i] += b4.x, v[i + 1] += b4.y, v[i + 2] += b4.z, v[i + 3] += b4.w;
 							}
 					}
-					if (stats && !row_ok)
-					{
-#pragma unroll
-						for (int i = 0; i < 32; i++)
-							v[i] = 0.f; // rows past M are clipped by the store but must not count in the statistics
-					}
 #pragma unroll
 					for (int j = 0; j < 8; j++)
 						*reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 					fence_proxy_async();
 					__syncwarp();
-					if (stats)
+					const int valid = min(32, p.M - (m0 + quarter * 32)); // rows of this chunk inside the tensor (the store clips the rest)
+					if (stats && valid > 0 && col0 + lane < N)
 					{
-						// lane = column: sum the 32 staged rows of this column (all lanes read the same 128-byte row: no bank conflict)
+						// lane = column: fold the staged rows of this column into the slot this thread owns (all lanes read the same
+						// 128-byte row: no bank conflict).  Shifted sums: k is the first value this slot ever saw.
+						float* const slot = stats + col0 + lane;
+						const float cnt = slot[0];
+						const float k = cnt > 0.f ? slot[stats_plane] : buf[((lane >> 2) << 2) + (lane & 3)];
 						float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
 						for (int rr = 0; rr < 32; rr++)
-						{
-							const float x = buf[rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3)];
-							s1 += x;
-							s2 = fmaf(x, x, s2);
-						}
-						if (col0 + lane < N)
-						{
-							atomicAdd(stats + col0 + lane, s1);
-							atomicAdd(stats + N + col0 + lane, s2);
-						}
+							if (rr < valid)
+							{
+								const float d = buf[rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3)] - k;
+								s1 += d;
+								s2 = fmaf(d, d, s2);
+							}
+						if (cnt > 0.f)
+							s1 += slot[2 * stats_plane], s2 += slot[3 * stats_plane];
+						else
+							slot[stats_plane] = k;
+						slot[0] = cnt + (float)valid;
+						slot[2 * stats_plane] = s1;
+						slot[3 * stats_plane] = s2;
 					}
 					if (lane == 0 && col0 < N)
 					{
@@ -322,7 +380,6 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 					bias4.z = col + 2 < N ? __ldg(bias + col + 2) : 0.f;
 					bias4.w = col + 3 < N ? __ldg(bias + col + 3) : 0.f;
 				}
-				float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = st1;
 #pragma unroll
 				for (int i = 0; i < 8; i++)
 				{
@@ -330,49 +387,20 @@ __global__ void __launch_bounds__(64 + EPIW * 32, 1) umma_gemm_persistent_kernel
 						continue;
 					float4 v = *reinterpret_cast<const float4*>(scratch + (sub_row + 4 * i) * S::EPI_PITCH + sub_col);
 					v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
-					if (stats)
-					{
-						st1.x += v.x, st1.y += v.y, st1.z += v.z, st1.w += v.w;
-						st2.x = fmaf(v.x, v.x, st2.x), st2.y = fmaf(v.y, v.y, st2.y), st2.z = fmaf(v.z, v.z, st2.z), st2.w = fmaf(v.w, v.w, st2.w);
-					}
 					float* const o = orow[i] + col;
 					if (full4 && ((((uintptr_t)o) & 15) == 0))
 					{
-						if (use_atomic)
-							red_add_v4(o, v.x, v.y, v.z, v.w);
-						else {
-							if (accumulate)
-							{
-								const float4 e = *reinterpret_cast<const float4*>(o);
-								v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
-							}
-							*reinterpret_cast<float4*>(o) = v;
+						if (accumulate)
+						{
+							const float4 e = *reinterpret_cast<const float4*>(o);
+							v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
 						}
+						*reinterpret_cast<float4*>(o) = v;
 					} else {
 						const float vv[4] = { v.x, v.y, v.z, v.w };
 						for (int j = 0; j < 4; j++)
 							if (col + j < N)
-							{
-								if (use_atomic)
-									atomicAdd(o + j, vv[j]);
-								else
-									o[j] = accumulate ? o[j] + vv[j] : vv[j];
-							}
-					}
-				}
-				if (stats)
-				{
-					// the 4 lanes that share these columns (sub_row 0..3) combine their 8-row partials: 32 rows x 4 columns per lane group
-#pragma unroll
-					for (int o = 8; o <= 16; o <<= 1)
-					{
-						st1.x += __shfl_xor_sync(0xffffffffu, st1.x, o), st1.y += __shfl_xor_sync(0xffffffffu, st1.y, o), st1.z += __shfl_xor_sync(0xffffffffu, st1.z, o), st1.w += __shfl_xor_sync(0xffffffffu, st1.w, o);
-						st2.x += __shfl_xor_sync(0xffffffffu, st2.x, o), st2.y += __shfl_xor_sync(0xffffffffu, st2.y, o), st2.z += __shfl_xor_sync(0xffffffffu, st2.z, o), st2.w += __shfl_xor_sync(0xffffffffu, st2.w, o);
-					}
-					if (sub_row == 0 && full4)
-					{
-						red_add_v4(stats + col, st1.x, st1.y, st1.z, st1.w);
-						red_add_v4(stats + N + col, st2.x, st2.y, st2.z, st2.w);
+								o[j] = accumulate ? o[j] + vv[j] : vv[j];
 					}
 				}
 				}

@@ -11,9 +11,10 @@
 //               filter-tap offset, laid side by side as the 32-wide MN atoms of one MN-major 128 x 32 tile
 //   B (N side)  dY[pixels, K] as an MN-major operand: K / 32 plain 2-D boxes {32 filters, 32 pixels}
 //
-// grid = (M tiles over the R*S*C filter positions, split-K over the pixels); the epilogue adds its partial tile into
-// dW[k, tap, c] with red.global.add (for a fixed k the 32 lanes of a warp hit 32 consecutive floats).  dW must be zeroed
-// by the launcher unless the command accumulates.
+// grid = (M tiles over the R*S*C filter positions, split-K over the pixels); the epilogue stores its tile into
+// out[k, tap, c] + split * split_out_stride (for a fixed k the 32 lanes of a warp hit 32 consecutive floats): dW itself when
+// there is one split and nothing to accumulate, otherwise one scratch slice per split that splitk_reduce_kernel adds up in a
+// fixed order (deterministic: no red.global.add).
 #pragma once
 #include "sm100_umma_gemm.cuh"
 
@@ -27,7 +28,8 @@ struct WgradTapsParams {
 	int splits;         // gridDim.y
 	int P, Q, stride_h, stride_w, base_h, base_w;
 	unsigned short tap_off_h[UMMA_MAX_TAPS], tap_off_w[UMMA_MAX_TAPS];
-	float* out;         // dW [K, R, S, C]
+	float* out;         // dW [K, R, S, C], or the first scratch slice of the same layout
+	long long split_out_stride;
 	long long rsc;
 	uint32_t idesc, mn_lbo, mn_sbo, mn_layout;
 };
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(192, 2) umma_wgrad_taps_kernel(const __grid_co
 		mbar_wait(tmem_full_bar, 0);
 		tc_fence_after();
 		const bool row_ok = m < nt * p.C;
-		float* const o = p.out + (long long)tap0 * p.C + m;
+		float* const o = p.out + (long long)blockIdx.y * p.split_out_stride + (long long)tap0 * p.C + m;
 #pragma unroll 1
 		for (int c = 0; c < BN / 32; c++)
 		{
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(192, 2) umma_wgrad_taps_kernel(const __grid_co
 #pragma unroll
 				for (int i = 0; i < 32; i++)
 					if (c * 32 + i < p.K)
-						atomicAdd(o + (long long)(c * 32 + i) * p.rsc, __uint_as_float(r[i]));
+						o[(long long)(c * 32 + i) * p.rsc] = __uint_as_float(r[i]);
 			}
 		}
 	}

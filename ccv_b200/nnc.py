@@ -209,6 +209,16 @@ class Stream(object):
     def cuda_stream(self):
         return lib().ccv_nnc_stream_context_get_stream(self.ptr)
 
+    def set_neighbors(self, streams):
+        """ccv_nnc_stream_context_set_neighbor_discovery (lib/nnc/ccv_nnc.h:1009-1020): `streams` maps device id -> Stream; the
+        multi-device COMM_ALLREDUCE looks its per-device streams up through this, as the graph runner wires it
+        (lib/nnc/ccv_nnc_graph_run.c:507-512)."""
+        table = dict((int(d), st.ptr) for d, st in streams.items())
+        cb_t = C.CFUNCTYPE(C.c_void_p, C.c_int, C.c_void_p)
+        self._neighbor_cb = cb_t(lambda device, ctx: table.get(int(device)))
+        lib().ccv_nnc_stream_context_set_neighbor_discovery.argtypes = [C.c_void_p, cb_t, C.c_void_p]
+        lib().ccv_nnc_stream_context_set_neighbor_discovery(self.ptr, self._neighbor_cb, None)
+
     def free(self):
         if self.ptr:
             lib().ccv_nnc_stream_context_free(self.ptr)

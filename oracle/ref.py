@@ -47,6 +47,7 @@ def ref():
         l.ref_float_to_half.argtypes = [vp, vp, C.c_size_t]
         l.ref_half_to_float.argtypes = [vp, vp, C.c_size_t]
         l.ref_num_threads.restype = i32
+        l.ref_set_num_threads.argtypes = [i32]
         l.ref_nnc_init()
         _ref = l
     return _ref
@@ -110,6 +111,28 @@ def run(cmd, hint, flags, in_arrays, out_arrays, fmt=abi.CCV_TENSOR_FORMAT_NHWC,
 
 def num_threads():
     return int(ref().ref_num_threads())
+
+
+def physical_cores():
+    """Distinct (package, core) pairs among the CPUs this process may run on; falls back to the affinity count."""
+    try:
+        allowed = os.sched_getaffinity(0)
+    except AttributeError:
+        allowed = set(range(os.cpu_count() or 1))
+    cores = set()
+    for cpu in allowed:
+        try:
+            base = "/sys/devices/system/cpu/cpu%d/topology/" % cpu
+            cores.add((open(base + "physical_package_id").read().strip(), open(base + "core_id").read().strip()))
+        except OSError:
+            return max(1, len(allowed))
+    return max(1, len(cores))
+
+
+def set_num_threads(n):
+    """OpenMP threads of the compiled reference for the timed CPU_REF runs (overrides an inherited OMP_NUM_THREADS)."""
+    ref().ref_set_num_threads(int(n))
+    return num_threads()
 
 
 def float_to_half(a):

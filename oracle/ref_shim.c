@@ -27,6 +27,18 @@ int ref_num_threads(void)
 #endif
 }
 
+/* explicit thread count for the timed CPU_REF runs: torchrun exports OMP_NUM_THREADS=1 to its workers, which silently turned
+ * the reference arm into a one-thread measurement */
+void ref_set_num_threads(const int n)
+{
+#ifdef _OPENMP
+	if (n > 0)
+		omp_set_num_threads(n);
+#else
+	(void)n;
+#endif
+}
+
 /* sizes the boundary header must reproduce */
 void ref_abi_sizes(int* const out)
 {

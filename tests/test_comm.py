@@ -145,6 +145,47 @@ def test_two_rank_allreduce_and_data_parallel_step(gpu, tmp_path):
         assert "rank %d ok" % rank in out
 
 
+def test_one_process_two_devices_convolution_and_allreduce(gpu, ref):
+    """The reference's own shape (comm/gpu/ccv_nnc_comm_gpu_nccl.cu:12-58, test/int/nnc/nccl.tests.c:13-44): ONE process drives
+    several devices.  A tcgen05 convolution (dynamic shared memory attribute, stream workspace, tensor maps) runs on device 1
+    through a stream context of device 1 while device 0 is current, and is checked against CPU_REF; then one
+    COMM_ALLREDUCE command sums a tensor per device, its per-device streams found through neighbour discovery."""
+    from tests.util import assert_close, ref_exec, seeded
+    nnc = gpu
+    if nnc.lib().ccv_nnc_device_count(nnc.CCV_STREAM_CONTEXT_GPU) < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    s0, s1 = nnc.Stream(0), nnc.Stream(1)
+    s0.set_neighbors({0: s0, 1: s1})
+    N, H, Cc, K = 4, 28, 64, 128
+    a, w, bias = seeded((N, H, H, Cc), 1, -1, 1), seeded((K, 3, 3, Cc), 2, -1, 1) / 24, seeded((K,), 3)
+    hint = nnc.hint((1, 1), (1, 1))
+    cmd = nnc.CMD_CONVOLUTION_FORWARD(1, K, 3, 3, Cc)
+    want = np.zeros((N, H, H, K), np.float32)
+    assert ref_exec(ref, cmd, hint, 0, [a, w, bias], [want])[0] == 0
+    outs = []
+    for dev, st in ((0, s0), (1, s1)):
+        ta, tw, tb = (nnc.gpu_tensor(list(v.shape), device=dev).upload(v) for v in (a, w, bias))
+        ty = nnc.gpu_tensor([N, H, H, K], device=dev)
+        assert nnc.cmd_exec(cmd, hint, 0, [ta, tw, tb], [ty], st) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+        st.wait()
+        assert_close(ty.download(), want, 1e-3, "convolution on device %d" % dev)
+        outs.append(ty)
+        for t in (ta, tw, tb):
+            t.free()
+    # integer-valued payloads: the sum is exact
+    x0, x1 = np.arange(4096, dtype=np.float32), np.arange(4096, dtype=np.float32)[::-1] * 3
+    t0, t1 = nnc.gpu_tensor([4096], device=0).upload(x0), nnc.gpu_tensor([4096], device=1).upload(x1)
+    assert nnc.cmd_exec(nnc.CMD_COMM_ALLREDUCE_FORWARD(), None, 0, [t0, t1], [t0, t1], s0) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+    s0.wait(), s1.wait()
+    assert np.array_equal(t0.download(), x0 + x1) and np.array_equal(t1.download(), x0 + x1)
+    # a stream context that cannot name the other device's stream is refused (nothing would order the reduction there)
+    lonely = nnc.Stream(0)
+    assert nnc.cmd_exec(nnc.CMD_COMM_ALLREDUCE_FORWARD(), None, 0, [t0, t1], [t0, t1], lonely) != 0
+    nnc.lib().ccv_nnc_sm100_comm_destroy()
+    for t in outs + [t0, t1, lonely, s0, s1]:
+        t.free()
+
+
 def test_stream_signals_order_two_stream_contexts(gpu):
     """ccv_nnc_stream_context_emit_signal / wait_signal (lib/nnc/ccv_nnc.h:1041-1053): work on stream B that waits for a signal emitted
     on stream A sees everything A enqueued before the emit (the mechanism bench.py's end-to-end leg uses to prefetch the next

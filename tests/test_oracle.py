@@ -146,7 +146,7 @@ def test_compiled_reference_attention_equals_the_composed_graph(ref, causal):
 
 @pytest.mark.ref
 def test_hint_auto_of_the_standalone_host_equals_the_reference():
-    """ccv_nnc_hint_auto (lib/nnc/ccv_nnc_cmd.c:214-262) restated in ccv_b200/csrc/nnc_host.cu: stride and border (begin / end) for
+    """ccv_nnc_hint_auto (lib/nnc/ccv_nnc_cmd.c:181-217) restated in ccv_b200/csrc/nnc_host.cu: stride and border (begin / end) for
     the window / input / output combinations the tests and the ResNet-50 driver use, byte for byte against the compiled reference."""
     import ctypes as C
     from ccv_b200 import abi
@@ -157,13 +157,21 @@ def test_hint_auto_of_the_standalone_host_equals_the_reference():
     cases = [((11, 11, 3), (225, 185, 3), (55, 45, 4)), ((5, 3, 1), (17, 27, 1), (17, 27, 4)), ((3, 3, 3), (224, 224, 3), (112, 112, 32)),
              ((3, 3, 64), (56, 56, 64), (56, 56, 64)), ((3, 3, 128), (56, 56, 128), (28, 28, 128)), ((1, 1, 64), (56, 56, 64), (56, 56, 256)),
              ((2, 2, 256), (56, 56, 256), (28, 28, 256)), ((3, 3, 64), (112, 112, 64), (56, 56, 64)), ((7, 7, 2048), (7, 7, 2048), (1, 1, 2048)),
-             ((3, 3, 8), (4, 13, 9, 8), (4, 7, 5, 16))]
-    for size, a_dims, b_dims in cases:
+             ((3, 3, 8), (4, 13, 9, 8), (4, 7, 5, 16)),
+             # windows smaller than the stride: the reference reports NEGATIVE borders (no clamping, ccv_nnc_cmd.c:212-214)
+             ((1, 1, 16), (56, 56, 16), (28, 28, 16)), ((2, 2, 8), (60, 60, 8), (15, 15, 8)), ((1, 2, 4), (4, 33, 17, 4), (4, 11, 4, 4)),
+             # NCHW, 3 and 4 dimensions; differing formats -> no hint
+             ((3, 3, 8), (8, 32, 32), (8, 16, 16), "nchw"), ((5, 5, 8), (2, 8, 31, 29), (2, 8, 16, 15), "nchw"), ((3, 3, 8), (32, 32, 8), (8, 16, 16), "mixed")]
+    for case in cases:
+        size, a_dims, b_dims = case[:3]
+        kind = case[3] if len(case) > 3 else "nhwc"
+        fa = abi.CCV_TENSOR_FORMAT_NHWC if kind in ("nhwc", "mixed") else abi.CCV_TENSOR_FORMAT_NCHW
+        fb = abi.CCV_TENSOR_FORMAT_NHWC if kind == "nhwc" else abi.CCV_TENSOR_FORMAT_NCHW
         info = abi.CmdParam()
         for i, d in enumerate(size):
             info.size.dim[i] = d
-        pa = abi.tensor_param(abi.CCV_TENSOR_CPU_MEMORY, abi.CCV_TENSOR_FORMAT_NHWC, abi.CCV_32F, list(a_dims), 0)
-        pb = abi.tensor_param(abi.CCV_TENSOR_CPU_MEMORY, abi.CCV_TENSOR_FORMAT_NHWC, abi.CCV_32F, list(b_dims), 0)
+        pa = abi.tensor_param(abi.CCV_TENSOR_CPU_MEMORY, fa, abi.CCV_32F, list(a_dims), 0)
+        pb = abi.tensor_param(abi.CCV_TENSOR_CPU_MEMORY, fb, abi.CCV_32F, list(b_dims), 0)
         mine, theirs = abi.Hint(), abi.Hint()
         nnc.lib().ccv_nnc_sm100_hint_auto(C.byref(info), C.byref(pa), C.byref(pb), C.byref(mine))
         r.ref().ref_hint_auto(C.byref(info), C.byref(pa), C.byref(pb), C.byref(theirs))

@@ -2,8 +2,12 @@
 CCV_NNC_BACKEND_CPU_REF on the same seeded inputs, through the C ABI.
 
 Tolerance: BASELINE.json north_star -- <= 1e-3 relative for fp32, applied to max|diff| / max|ref| (tests/util.rel_err).
-The default algorithm is one tcgen05 kind::tf32 pass with TMA's round-to-nearest TF32 conversion; CCV_NNC_SM100_ALGO_FFMA
-(CUDA-core fp32) is held to 1e-5."""
+Algorithms: CCV_NNC_SM100_ALGO_TF32 (one tcgen05 kind::tf32 pass, TMA rounds the operands to TF32: the convolution default,
+as the reference's cuDNN path runs CUDNN_TENSOR_OP_MATH) is held to 1e-3; CCV_NNC_SM100_ALGO_3XTF32 (error-compensated, three
+MMAs on hi / lo splits: the GEMM default, as the reference's cuBLAS path computes in CUBLAS_COMPUTE_32F) to 2e-5;
+CCV_NNC_SM100_ALGO_FFMA (CUDA-core fp32) to 1e-5.  The full-size BASELINE configs (GEMM 1024^3, convolution N=64 C=64 56x56
+K=64 3x3 forward + backward) are compared with CPU_REF itself at the end of this file, with the element-wise relative error
+(absolute floor 1e-2 of max|ref|) reported next to the max-normalised one."""
 import os
 
 import numpy as np
@@ -13,8 +17,8 @@ from ccv_b200 import abi
 from tests.util import NCHW, NHWC, assert_close, gpu_exec, ref_exec, seeded
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL = {abi.CCV_NNC_SM100_ALGO_TF32: 1e-3, abi.CCV_NNC_SM100_ALGO_FFMA: 1e-5}
-ALGOS = [abi.CCV_NNC_SM100_ALGO_TF32, abi.CCV_NNC_SM100_ALGO_FFMA]
+TOL = {abi.CCV_NNC_SM100_ALGO_TF32: 1e-3, abi.CCV_NNC_SM100_ALGO_3XTF32: 2e-5, abi.CCV_NNC_SM100_ALGO_FFMA: 1e-5}
+ALGOS = [abi.CCV_NNC_SM100_ALGO_TF32, abi.CCV_NNC_SM100_ALGO_3XTF32, abi.CCV_NNC_SM100_ALGO_FFMA]
 
 pytestmark = pytest.mark.gpu
 
@@ -260,3 +264,58 @@ def test_convolution_forward_nchw(gpu, ref, N, C, H, K, R, st, groups):
     st_g, (y_g,) = gpu_exec(nnc, cmd, hint, 0, [x, w, bias], [np.zeros((N, K, P, P), np.float32)], **fmts)
     assert st_r == 0 and st_g == 0
     assert_close(y_g, y_r, 1e-3, "NCHW convolution")
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs at full size
+def _report(name, got, want, tol):
+    from tests.util import elem_rel_err, rel_err
+    n, e = rel_err(got, want), elem_rel_err(got, want)
+    print("%s: max-normalised error %.3e, element-wise relative error (floor 1e-2 max|ref|) %.3e" % (name, n, e))
+    assert np.isfinite(got).all(), name
+    assert n <= tol, "%s: normalised max error %.3e > %.1e" % (name, n, tol)
+    assert e <= 100 * tol, "%s: element-wise relative error %.3e > %.1e" % (name, e, 100 * tol)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("tb", [0, 1])
+def test_baseline_config1_gemm_1024_cubed_vs_cpu_ref(gpu, ref, tb):
+    """BASELINE.json configs[0]: CCV_NNC_GEMM_FORWARD fp32 1024 x 1024 x 1024 (NN and NT), the whole result against
+    CCV_NNC_BACKEND_CPU_REF (sequential-k float accumulation, blas/ccv_nnc_gemm_cpu_ref.c:28-33).  The DEFAULT algorithm of
+    an fp32 GEMM is the error-compensated 3xTF32 kernel (the reference computes fp32 GEMMs in CUBLAS_COMPUTE_32F), held to the
+    fp32 bound of the north star with two orders of magnitude to spare; with CCV_NNC_GEMM_32TF the one-pass TF32 kernel runs."""
+    nnc = gpu
+    a, w = seeded((1024, 1024), 31, -1, 1), seeded((1024, 1024), 32, -1, 1)
+    cmd = lambda **kw: nnc.CMD_GEMM_FORWARD((0, 0), (0, 1) if tb else (0, 0), **kw)
+    _, (want,) = ref_exec(ref, cmd(), None, 0, [a, w], [np.zeros((1024, 1024), np.float32)])
+    st, (got,) = gpu_exec(nnc, cmd(), None, 0, [a, w], [np.zeros((1024, 1024), np.float32)])
+    assert st == 0
+    _report("GEMM 1024^3 %s default (3xTF32)" % ("NT" if tb else "NN"), got, want, 1e-5)
+    tf = cmd()
+    tf.info.blas.flags = abi.CCV_NNC_GEMM_32TF
+    st, (got,) = gpu_exec(nnc, tf, None, 0, [a, w], [np.zeros((1024, 1024), np.float32)])
+    assert st == 0
+    _report("GEMM 1024^3 %s CCV_NNC_GEMM_32TF" % ("NT" if tb else "NN"), got, want, 1e-3)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("algo", [abi.CCV_NNC_SM100_ALGO_TF32, abi.CCV_NNC_SM100_ALGO_3XTF32])
+def test_baseline_config2_convolution_full_size_vs_cpu_ref(gpu, ref, algo):
+    """BASELINE.json configs[1]: CCV_NNC_CONVOLUTION_FORWARD + BACKWARD fp32 N=64 C=64 H=W=56 K=64 3x3, every element of
+    y, dx, dw against CPU_REF (zero-mean data: nothing hides behind a large common offset)."""
+    nnc = gpu
+    N, H, C, K = 64, 56, 64, 64
+    a, w, g = seeded((N, H, H, C), 41, -1, 1), seeded((K, 3, 3, C), 42, -1, 1) / 24, seeded((N, H, H, K), 43, -1, 1)
+    hint = nnc.hint((1, 1), (1, 1))
+    fwd, bwd = (lambda **kw: nnc.CMD_CONVOLUTION_FORWARD(1, K, 3, 3, C, **kw)), (lambda **kw: nnc.CMD_CONVOLUTION_BACKWARD(1, K, 3, 3, C, **kw))
+    _, (y_r,) = ref_exec(ref, fwd(), hint, 0, [a, w], [np.zeros((N, H, H, K), np.float32)])
+    _, (h_r, dw_r) = ref_exec(ref, bwd(), hint, 0, [g, a, w], [np.zeros_like(a), np.zeros_like(w)])
+    st, (y_g,) = gpu_exec(nnc, fwd(algorithm=algo), hint, 0, [a, w], [np.zeros((N, H, H, K), np.float32)])
+    assert st == 0
+    st, (h_g, dw_g) = gpu_exec(nnc, bwd(algorithm=algo), hint, 0, [g, a, w], [np.zeros_like(a), np.zeros_like(w)])
+    assert st == 0
+    tol = TOL[algo]
+    _report("conv cfg2 algo %d forward" % algo, y_g, y_r, tol)
+    _report("conv cfg2 algo %d dgrad" % algo, h_g, h_r, tol)
+    # the filter gradient sums 200 704 products per element: CPU_REF's own sequential fp32 accumulation is only good to
+    # ~1e-5 of the largest element there, so the compensated kernel is held to 1e-4 on this output
+    _report("conv cfg2 algo %d wgrad" % algo, dw_g, dw_r, max(tol, 1e-4))

@@ -235,15 +235,20 @@ def test_set_transfer_format_transform_transpose_are_bit_exact(gpu, ref):
 
 
 @pytest.mark.ref
-@pytest.mark.parametrize("N,H,C,K,R,relu", [(8, 28, 64, 128, 3, 1), (16, 14, 256, 64, 1, 0), (4, 32, 3, 32, 3, 1)])
-def test_convolution_epilogue_statistics_feed_the_batch_norm(gpu, ref, N, H, C, K, R, relu):
+@pytest.mark.parametrize("N,H,C,K,R,relu,offset", [(8, 28, 64, 128, 3, 1, 0.0), (16, 14, 256, 64, 1, 0, 0.0), (4, 32, 3, 32, 3, 1, 0.0),
+                                                     (32, 28, 64, 128, 3, 0, 60.0),   # 196 output tiles (some CTAs own two), channel mean / std ~ 100
+                                                     (8, 14, 128, 512, 1, 1, -80.0),  # two column blocks of 256
+                                                     (4, 7, 64, 2048, 1, 0, 25.0)])   # eight column blocks: a CTA's tiles alternate between two of them
+def test_convolution_epilogue_statistics_feed_the_batch_norm(gpu, ref, N, H, C, K, R, relu, offset):
     """Graph rewrite (f) of ccv_nnc_sm100_graph_fuse: CONVOLUTION_FORWARD -> BATCH_NORM_FORWARD(train) [-> RELU in place].  The
-    convolution's tensor-core epilogue sums y and y * y per channel and the batch norm skips its statistics pass.  Checked against
-    CPU_REF running the same three commands one by one: y within the TF32 bound, saved mean / inv_std / running statistics
-    within 1e-3 (they are sums over N * H * W = thousands of TF32-accurate values)."""
+    convolution's tensor-core epilogue folds its output into per-(CTA, warp quarter) shifted sums and the batch norm skips its
+    statistics pass.  Checked against CPU_REF running the same three commands one by one (two-pass variance,
+    norm/ccv_nnc_batch_norm_cpu_ref.c:66-110): y within the TF32 bound, saved mean / inv_std / running statistics within 1e-3,
+    also when a convolution bias puts the channel means ~100 standard deviations from zero (the case in which an unshifted
+    E[y^2] - E[y]^2 loses the variance), and the result is bit-identical from run to run (no atomics)."""
     nnc = gpu
     pad = R // 2
-    x, w, b = seeded((N, H, H, C), 1, -1, 1), seeded((K, R, R, C), 2, -1, 1) / (R * R * C) ** 0.5, seeded((K,), 3, -1, 1)
+    x, w, b = seeded((N, H, H, C), 1, -1, 1), seeded((K, R, R, C), 2, -1, 1) / (R * R * C) ** 0.5, seeded((K,), 3, -1, 1) + np.float32(offset)
     scale, bias = seeded((1, 1, 1, K), 4, 0.5, 1.5), seeded((1, 1, 1, K), 5, -1, 1)
     hint = nnc.hint((1, 1), (pad, pad))
     conv = nnc.CMD_CONVOLUTION_FORWARD(1, K, R, R, C)
@@ -276,6 +281,13 @@ def test_convolution_epilogue_statistics_feed_the_batch_norm(gpu, ref, N, H, C, 
     assert_close(tsm.download(), sm, 1e-3, "saved mean"), assert_close(tsis.download(), sis, 1e-3, "saved inv_std")
     assert_close(tmean.download(), mean, 1e-3, "running mean"), assert_close(tvar.download(), var, 1e-3, "running var")
     assert_close(tz.download(), z, 2e-3, "normalised output")
+    # deterministic: a second run of the same graph reproduces every bit of the statistics and of the output
+    first = [t.download() for t in (tsm, tsis, tz)]
+    tmean.upload(np.zeros((1, 1, 1, K), np.float32)), tvar.upload(np.ones((1, 1, 1, K), np.float32))
+    assert g.run(stream) == 0
+    stream.wait()
+    for t, f in zip((tsm, tsis, tz), first):
+        assert np.array_equal(t.download(), f)
     for t in (tx, tw, tb, tscale, tbias, tmean, tvar, ty, tz, tsm, tsis, g, stream):
         t.free()
 

@@ -67,6 +67,16 @@ def rel_err(got, want):
     return float(np.abs(got - want).max() / denom)
 
 
+def elem_rel_err(got, want, floor=1e-2):
+    """Element-wise relative error max |got - want| / max(|want|, floor * max|want|): small outputs count with their own
+    magnitude down to an absolute floor of `floor` x the largest reference value (below that, fp32 summation-order noise of
+    the reference itself dominates)."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    scale = max(np.abs(want).max(), 1e-30)
+    return float((np.abs(got - want) / np.maximum(np.abs(want), floor * scale)).max())
+
+
 def assert_close(got, want, tol, what=""):
     assert got.shape == want.shape, (what, got.shape, want.shape)
     assert np.isfinite(got).all(), what + ": non-finite output"
