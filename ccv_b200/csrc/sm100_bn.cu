@@ -298,53 +298,99 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
 }
 
 // Forward finalisation from the statistics a convolution epilogue produced (sm100_umma_persistent.cuh): four planes [rows][C] --
-// count, shift k, sum(v - k), sum((v - k)^2) -- one row per (CTA, epilogue warp quarter); rows with count 0 were never touched.
-// Each slot is its own shifted one-pass estimate; they are merged with Chan's parallel update in double precision, in a fixed
-// order (32 row-lanes per channel, then lane by lane): deterministic, and free of the E[v^2] - E[v]^2 cancellation however far
-// the channel mean is from zero (norm/ccv_nnc_batch_norm_cpu_ref.c:66-110 is the two-pass form this has to agree with).
+// count n_i, shift k_i, s1_i = sum(v - k_i), s2_i = sum((v - k_i)^2) -- one row per (CTA, epilogue warp quarter); rows with
+// count 0 were never touched.  Each slot is its own shifted one-pass estimate.  They are combined in double precision, in a
+// fixed order (32 row-lanes per channel, then lane by lane), in two sweeps over the (L2-resident) slots:
+//   mean = sum_i (n_i k_i + s1_i) / N
+//   M2   = sum_i [ s2_i - 2 d_i s1_i + n_i d_i^2 ],  d_i = mean - k_i        (= sum over the slot of (v - mean)^2, exactly)
+// Both are plain sums (no serial dependency, several loads in flight), deterministic, and free of the E[v^2] - E[v]^2
+// cancellation however far the channel mean is from zero, because every d_i is of the order of one standard deviation
+// (norm/ccv_nnc_batch_norm_cpu_ref.c:66-110 is the two-pass form this has to agree with).
 __global__ void __launch_bounds__(1024) bn_finalize_ext_kernel(const float* __restrict__ part, const int rows, const int C, const float epsilon, const float momentum,
 	const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std, float* __restrict__ coef)
 {
-	__shared__ double sh[3][32][33];
+	__shared__ double sh[2][32][33];
+	__shared__ double sh_mean[32];
 	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
 	const int c = blockIdx.x * 32 + cx;
 	const size_t plane = (size_t)rows * C;
-	double n = 0, mean = 0, m2 = 0;
+	const float* const p0 = part + c;
+	double a0 = 0, a1 = 0, n0 = 0, n1 = 0;
 	if (c < C)
-		for (int y = yl; y < rows; y += 32)
+	{
+		int y = yl;
+		for (; y + 32 < rows; y += 64)
 		{
-			const size_t at = (size_t)y * C + c;
-			const double nb = (double)part[at];
-			if (nb > 0)
+			const size_t u = (size_t)y * C, v = (size_t)(y + 32) * C;
+			const float nu = p0[u], nv = p0[v], ku = p0[plane + u], kv = p0[plane + v], su = p0[2 * plane + u], sv = p0[2 * plane + v];
+			n0 += (double)nu, n1 += (double)nv;
+			// untouched slots (count 0) hold whatever the buffer held: never let them into the sums
+			a0 += nu > 0.f ? (double)nu * (double)ku + (double)su : 0.0, a1 += nv > 0.f ? (double)nv * (double)kv + (double)sv : 0.0;
+		}
+		for (; y < rows; y += 32)
+		{
+			const size_t u = (size_t)y * C;
+			const float nu = p0[u];
+			n0 += (double)nu;
+			a0 += nu > 0.f ? (double)nu * (double)p0[plane + u] + (double)p0[2 * plane + u] : 0.0;
+		}
+	}
+	sh[0][yl][cx] = n0 + n1, sh[1][yl][cx] = a0 + a1;
+	__syncthreads();
+	if (yl == 0)
+	{
+		double n = 0, a = 0;
+#pragma unroll
+		for (int j = 0; j < 32; j++)
+			n += sh[0][j][cx], a += sh[1][j][cx];
+		sh_mean[cx] = n > 0 ? a / n : 0.0;
+		sh[0][0][cx] = n; // total count, read back after the second sweep
+	}
+	__syncthreads();
+	const double mean = sh_mean[cx];
+	const double total = sh[0][0][cx];
+	__syncthreads();
+	double m0 = 0, m1 = 0;
+	if (c < C)
+	{
+		int y = yl;
+		for (; y + 32 < rows; y += 64)
+		{
+			const size_t u = (size_t)y * C, v = (size_t)(y + 32) * C;
+			const float nu = p0[u], nv = p0[v];
+			if (nu > 0.f)
 			{
-				const double s1 = (double)part[2 * plane + at], s2 = (double)part[3 * plane + at];
-				const double mb = (double)part[plane + at] + s1 / nb;
-				double m2b = s2 - s1 * s1 / nb;
-				if (m2b < 0)
-					m2b = 0;
-				const double tot = n + nb, delta = mb - mean;
-				mean += delta * (nb / tot);
-				m2 += m2b + delta * delta * (n * nb / tot);
-				n = tot;
+				const double d = mean - (double)p0[plane + u];
+				m0 += (double)p0[3 * plane + u] - 2.0 * d * (double)p0[2 * plane + u] + (double)nu * d * d;
+			}
+			if (nv > 0.f)
+			{
+				const double d = mean - (double)p0[plane + v];
+				m1 += (double)p0[3 * plane + v] - 2.0 * d * (double)p0[2 * plane + v] + (double)nv * d * d;
 			}
 		}
-	sh[0][yl][cx] = n, sh[1][yl][cx] = mean, sh[2][yl][cx] = m2;
+		for (; y < rows; y += 32)
+		{
+			const size_t u = (size_t)y * C;
+			const float nu = p0[u];
+			if (nu > 0.f)
+			{
+				const double d = mean - (double)p0[plane + u];
+				m0 += (double)p0[3 * plane + u] - 2.0 * d * (double)p0[2 * plane + u] + (double)nu * d * d;
+			}
+		}
+	}
+	sh[1][yl][cx] = m0 + m1;
 	__syncthreads();
 	if (yl != 0 || c >= C)
 		return;
-	n = 0, mean = 0, m2 = 0;
+	double m2 = 0;
+#pragma unroll
 	for (int j = 0; j < 32; j++)
-	{
-		const double nb = sh[0][j][cx];
-		if (nb > 0)
-		{
-			const double tot = n + nb, delta = sh[1][j][cx] - mean;
-			mean += delta * (nb / tot);
-			m2 += sh[2][j][cx] + delta * delta * (n * nb / tot);
-			n = tot;
-		}
-	}
-	const float meanf = (float)mean, varf = n > 0 ? (float)(m2 / n) : 0.f;
+		m2 += sh[1][j][cx];
+	if (m2 < 0)
+		m2 = 0;
+	const float meanf = (float)mean, varf = total > 0 ? (float)(m2 / total) : 0.f;
 	const float inv_std = 1.f / sqrtf(varf + epsilon);
 	saved_mean[c] = meanf;
 	saved_inv_std[c] = inv_std;

@@ -265,7 +265,12 @@ static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, c
 	if (ensure_dynamic_smem(kern, S::TOTAL, configured, "cudaFuncSetAttribute(umma_gemm_persistent_kernel)"))
 		return -1;
 	const long long tiles = (long long)((p.M + UMMA_BLOCK_M - 1) / UMMA_BLOCK_M) * ((p.N + BN - 1) / BN) * p.grid_taps * p.splits;
-	const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+	int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+	// with statistics requested every tile of a CTA must cover the same output columns (the epilogue keeps its per-column sums in
+	// registers for the whole kernel): tile = blockIdx.x + i * grid and n_blk = tile % tiles_n, so grid becomes a multiple of tiles_n
+	const int tiles_n_ = (p.N + BN - 1) / BN;
+	if (t_stats_request.part && tiles_n_ > 1 && grid >= tiles_n_)
+		grid = grid / tiles_n_ * tiles_n_;
 	UmmaGemmParams q = p;
 	q.stats = 0, q.stats_rows = 0;
 	// TMA tile stores for the plain "write the tile" epilogue (dense row-major output, no split-K, no accumulate)
@@ -285,7 +290,7 @@ static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, c
 		const StatsRequest r = t_stats_request;
 		t_stats_request.part = 0;
 		// forward-shaped launches only; the statistics ride on the TMA-store epilogue (one slot row per CTA and warp quarter)
-		if (q.tma_store && AMODE != OP_MN2D && BMODE == OP_K2D && p.N % 32 == 0 && grid * 4 <= r.max_rows)
+		if (q.tma_store && AMODE != OP_MN2D && BMODE == OP_K2D && p.N % 32 == 0 && grid * 4 <= r.max_rows && (tiles_n_ == 1 || grid % tiles_n_ == 0))
 		{
 			const cudaError_t e = cudaMemsetAsync(r.part, 0, (size_t)grid * 4 * p.N * sizeof(float), stream); // the count plane
 			if (e != cudaSuccess)

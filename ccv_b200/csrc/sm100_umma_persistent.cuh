@@ -249,9 +249,18 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 		const bool accumulate = p.accumulate != 0;
 		const float* const bias = p.bias;
 		const int N = p.N;
-		// statistics slots of this warp quarter: plane 0 of row blockIdx.x * 4 + quarter (count); planes k, s1, s2 follow at stats_plane
+		// statistics slots of this warp quarter: plane 0 of row blockIdx.x * 4 + quarter (count); planes k, s1, s2 follow at stats_plane.
+		// The launcher makes gridDim.x a multiple of tiles_n, so every tile of this CTA covers the same columns: the shifted sums of
+		// the warp's chunks live in (thread-local) arrays for the whole kernel and are stored once at the end.
 		float* const stats = p.stats && p.tma_store ? p.stats + ((size_t)blockIdx.x * 4 + quarter) * p.N : 0;
 		const size_t stats_plane = (size_t)p.stats_rows * p.N;
+		constexpr int CHUNKS_PER_WARP = (BN / 32 + EPIW / 4 - 1) / (EPIW / 4);
+		float st_k[CHUNKS_PER_WARP], st_s1[CHUNKS_PER_WARP], st_s2[CHUNKS_PER_WARP];
+		float st_n = 0.f;
+		int st_n0 = 0;
+#pragma unroll
+		for (int i = 0; i < CHUNKS_PER_WARP; i++)
+			st_k[i] = st_s1[i] = st_s2[i] = 0.f;
 		int t = 0;
 		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++)
 		{
@@ -331,13 +340,12 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 					fence_proxy_async();
 					__syncwarp();
 					const int valid = min(32, p.M - (m0 + quarter * 32)); // rows of this chunk inside the tensor (the store clips the rest)
-					if (stats && valid > 0 && col0 + lane < N)
+					if (stats && valid > 0)
 					{
-						// lane = column: fold the staged rows of this column into the slot this thread owns (all lanes read the same
-						// 128-byte row: no bank conflict).  Shifted sums: k is the first value this slot ever saw.
-						float* const slot = stats + col0 + lane;
-						const float cnt = slot[0];
-						const float k = cnt > 0.f ? slot[stats_plane] : buf[((lane >> 2) << 2) + (lane & 3)];
+						// lane = column: fold the staged rows of this column into this thread's running shifted sums (all lanes read the
+						// same 128-byte row: no bank conflict).  k is the first value the thread ever saw for the column.
+						const int ci = (c - half) / (EPIW / 4);
+						const float k = st_n > 0.f ? st_k[ci] : buf[lane];
 						float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
 						for (int rr = 0; rr < 32; rr++)
@@ -347,13 +355,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 								s1 += d;
 								s2 = fmaf(d, d, s2);
 							}
-						if (cnt > 0.f)
-							s1 += slot[2 * stats_plane], s2 += slot[3 * stats_plane];
-						else
-							slot[stats_plane] = k;
-						slot[0] = cnt + (float)valid;
-						slot[2 * stats_plane] = s1;
-						slot[3 * stats_plane] = s2;
+						st_k[ci] = k, st_s1[ci] += s1, st_s2[ci] += s2;
 					}
 					if (lane == 0 && col0 < N)
 					{
@@ -405,11 +407,30 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 				}
 				}
 			}
+			if (stats)
+			{
+				const int valid = min(32, p.M - (m0 + quarter * 32));
+				if (valid > 0)
+					st_n += (float)valid, st_n0 = n0;
+			}
 			// all tcgen05.ld of this tile are complete (tmem_ld_wait): hand the accumulator back to the MMA warp
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0)
 				mbar_arrive(&tmem_empty_bar[acc]);
+		}
+		if (stats && st_n > 0.f)
+		{
+#pragma unroll
+			for (int ci = 0; ci < CHUNKS_PER_WARP; ci++)
+			{
+				const int col = st_n0 + (half + ci * (EPIW / 4)) * 32 + lane;
+				if (half + ci * (EPIW / 4) < BN / 32 && col < N)
+				{
+					float* const slot = stats + col;
+					slot[0] = st_n, slot[stats_plane] = st_k[ci], slot[2 * stats_plane] = st_s1[ci], slot[3 * stats_plane] = st_s2[ci];
+				}
+			}
 		}
 		if (tma_store && lane == 0)
 			bulk_wait_group<0>(); // every tile store of this warp has been written out before the CTA exits

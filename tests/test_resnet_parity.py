@@ -112,22 +112,27 @@ def test_resnet50_every_node_teacher_forced_vs_cpu_ref(gpu, cpu_net, algo, tol):
     net.free(), stream.free()
 
 
-def test_fused_graph_and_cuda_graph_replay_match_the_unfused_run(gpu):
+@pytest.mark.parametrize("algo,tol", [(abi.CCV_NNC_SM100_ALGO_3XTF32, 1e-5), (abi.CCV_NNC_SM100_ALGO_TF32, 1e-2)])
+def test_fused_graph_and_cuda_graph_replay_match_the_unfused_run(gpu, algo, tol):
     nnc = gpu
     stream = nnc.Stream(0)
-    plain, g0, _ = _gpu_net(nnc, -1, False, stream)
-    fused, g1, n = _gpu_net(nnc, -1, True, stream)
+    plain, g0, _ = _gpu_net(nnc, algo, False, stream)
+    fused, g1, n = _gpu_net(nnc, algo, True, stream)
     assert n >= 60, "expected the BN+ReLU / residual pairs of ResNet-50 to fuse, got %d" % n
     assert len(g1) == len(g0) - n
     # every convolution that feeds a training batch norm also produces that batch norm's statistics in its epilogue
     kinds = [k for _, k, _, _ in g1.nodes()]
     assert kinds.count(6) >= 50 and kinds.count(6) == sum(1 for _, k, ins, _ in g1.nodes() if k in (1, 7) and len(ins) == 6)
-    # Forward: the same convolution / GEMM kernels produce the same activations; the only arithmetic that differs is where the
-    # batch-norm statistics are summed (convolution epilogue, Chan merge in double, instead of the shifted two-level reduction):
-    # both are accurate to a few fp32 ulp of the mean / variance, and every reduction in either path has a fixed order, so the
-    # logits agree to accumulated rounding of 50 batch-norm layers
-    assert_close(fused.logits.download(), plain.logits.download(), 1e-5, "fused vs unfused logits")
-    assert_close(fused.loss.download(), plain.loss.download(), 1e-5, "fused vs unfused loss")
+    # Forward: the same convolution / GEMM kernels run in both graphs; the only arithmetic that differs is where the batch-norm
+    # statistics are summed (convolution epilogue + merge in double, instead of the shifted two-level reduction).  Both are
+    # accurate to a few fp32 ulp (measured layer by layer with tools/debug_fused_diff.py: the first batch-norm outputs differ by
+    # 4.6e-7), so with fp32-grade products (3xTF32) the logits agree to 1e-5.  One-pass TF32 ROUNDS every operand to 10 mantissa
+    # bits on the way into the tensor core: an input that moved by one fp32 ulp can land on the other side of a rounding boundary
+    # and move by 2^-11, so the same 4.6e-7 perturbation reads 6.2e-5 after the next convolution and ~3e-3 after all 53 (the
+    # quantisation noise of the algorithm itself, sqrt(53) x 2^-11) -- that configuration is held to 1e-2 here and pinned against
+    # CPU_REF in test_fused_cuda_graph_vs_cpu_ref.
+    assert_close(fused.logits.download(), plain.logits.download(), tol, "fused vs unfused logits")
+    assert_close(fused.loss.download(), plain.loss.download(), tol, "fused vs unfused loss")
     # chaotic backward (module docstring): the rewrites change rounding, which this randomly initialised batch-4 network
     # amplifies; each rewrite is pinned on its own in tests/test_parity_feeders.py, here only gross agreement is asked for
     a, b = fused.g_flat.download().astype(np.float64), plain.g_flat.download().astype(np.float64)
