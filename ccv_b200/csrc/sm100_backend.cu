@@ -104,6 +104,18 @@ inline Scratch scratch_at(void* const p, const size_t bytes)
 }
 
 inline bool is_f32(const ccv_nnc_tensor_t* const t) { return CCV_GET_DATA_TYPE(t->info.datatype) == CCV_32F; }
+// element kind of the kernels that exist for three floating-point types: 0 = fp32, 1 = bf16, 2 = fp16; -1 otherwise
+inline int kind_of(const ccv_nnc_tensor_t* const t)
+{
+	switch (CCV_GET_DATA_TYPE(t->info.datatype))
+	{
+		case CCV_32F: return 0;
+		case CCV_16BF: return 1;
+		case CCV_16F: return 2;
+	}
+	return -1;
+}
+inline size_t kind_size(const int kind) { return kind == 0 ? 4 : 2; }
 
 bool same_shape(const TV& a, const TV& b)
 {
@@ -228,13 +240,42 @@ int gemm_dispatch(cudaStream_t s, const Scratch& scratch, const int algorithm, c
 	return gemm_ffma(s, M, N, K, a, a_rs, a_cs, b, b_rs, b_cs, c, c_rs, bias, accumulate);
 }
 
+// the same for 16-bit tensors (kind 1 = bf16, 2 = fp16): tensor-core path only (unit stride along one axis of every operand)
+int gemm_dispatch16(cudaStream_t s, const Scratch& scratch, const int kind, const int M, const int N, const int K, const void* a, long long a_rs, long long a_cs, const void* b, long long b_rs, long long b_cs, void* c, long long c_rs, long long c_cs, const float* bias32, const void* bias16, const int accumulate)
+{
+	if (M <= 0 || N <= 0)
+		return 0;
+	if (K <= 0)
+		return 1;
+	if (c_cs != 1 && N > 1)
+	{
+		if ((c_rs != 1 && M > 1) || bias32 || bias16)
+			return 1;
+		return gemm_dispatch16(s, scratch, kind, N, M, K, b, b_cs, b_rs, a, a_cs, a_rs, c, c_cs, 1, 0, 0, accumulate); // C^T = B^T A^T
+	}
+	int ta = -1, tb = -1;
+	long long lda = 0, ldb = 0;
+	if (a_cs == 1 || K == 1)
+		ta = 0, lda = a_rs;
+	else if (a_rs == 1 || M == 1)
+		ta = 1, lda = a_cs;
+	if (b_cs == 1 || N == 1)
+		tb = 0, ldb = b_rs;
+	else if (b_rs == 1 || K == 1)
+		tb = 1, ldb = b_cs;
+	if (ta < 0 || tb < 0)
+		return 1;
+	return gemm_16(s, kind, M, N, K, a, lda, ta, b, ldb, tb, c, c_rs, bias32, bias16, accumulate, scratch);
+}
+
 // blas/ccv_nnc_gemm_cpu_ref.c:110-184
 int exec_gemm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1] || !outputs[0])
 		return CCV_NNC_EXEC_INVALID;
 	const ccv_nnc_tensor_t* const bias_t = input_size > 2 ? inputs[2] : 0;
-	if (!is_f32(inputs[0]) || !is_f32(inputs[1]) || !is_f32(outputs[0]) || (bias_t && !is_f32(bias_t)))
+	const int kind = kind_of(inputs[0]);
+	if (kind < 0 || kind_of(inputs[1]) != kind || kind_of(outputs[0]) != kind || (bias_t && kind_of(bias_t) != kind && !is_f32(bias_t)))
 		return CCV_NNC_EXEC_INVALID;
 	const int no_transpose[2] = { 0, 0 };
 	Mat a, w, b, bias;
@@ -257,6 +298,16 @@ int exec_gemm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	}
 	cudaStream_t s = stream_of(stream_context);
 	const Scratch scratch = scratch_of(stream_context);
+	if (kind != 0)
+	{
+		// 16-bit operands: tcgen05 kind::f16, fp32 accumulate; the bias may be fp32 or in the operands' type
+		const char* const bias_p = bias_t ? (const char*)bias.p : 0;
+		const bool bias32 = bias_t && is_f32(bias_t);
+		for (int i = 0; i < b.batch; i++)
+			RC(gemm_dispatch16(s, scratch, kind, b.rows, b.cols, a.cols, (const char*)a.p + (size_t)i * a.batch_inc * 2, a.rs, a.cs, (const char*)w.p + (size_t)i * w.batch_inc * 2, w.rs, w.cs, (char*)b.p + (size_t)i * b.batch_inc * 2, b.rs, b.cs,
+				bias32 ? (const float*)(bias_p + (size_t)i * bias.batch_inc * 4) : 0, bias_t && !bias32 ? bias_p + (size_t)i * bias.batch_inc * 2 : 0, 0));
+		return CCV_NNC_EXEC_SUCCESS;
+	}
 	for (int i = 0; i < b.batch; i++)
 		RC(gemm_dispatch(s, scratch, gemm_algorithm(cmd), b.rows, b.cols, a.cols, a.p + i * a.batch_inc, a.rs, a.cs, w.p + i * w.batch_inc, w.rs, w.cs, b.p + i * b.batch_inc, b.rs, b.cs, bias_t ? bias.p + i * bias.batch_inc : 0, 0));
 	return CCV_NNC_EXEC_SUCCESS;
@@ -270,8 +321,10 @@ int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	const int no_transpose[2] = { 0, 0 };
 	const int accumulate = (flags & CCV_NNC_ACCUMULATE_OUTPUT) ? 1 : 0;
 	Mat g;
-	if (!is_f32(inputs[0]) || !mat_of(view_of(inputs[0]), no_transpose, g))
+	const int kind = kind_of(inputs[0]);
+	if (kind < 0 || !mat_of(view_of(inputs[0]), no_transpose, g))
 		return CCV_NNC_EXEC_INVALID;
+	const size_t esz = kind_size(kind);
 	cudaStream_t s = stream_of(stream_context);
 	ccv_nnc_tensor_t* const dbias_t = output_size > 2 ? outputs[2] : 0;
 	ccv_nnc_tensor_t* const dw_t = output_size > 1 ? outputs[1] : 0;
@@ -283,12 +336,15 @@ int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 			return CCV_NNC_EXEC_INVALID;
 		if (db.batch != 1 && db.batch != g.batch)
 			return CCV_NNC_EXEC_INVALID;
+		const int db_kind = kind_of(dbias_t);
+		if (db_kind < 0)
+			return CCV_NNC_EXEC_INVALID;
 		for (int i = 0; i < g.batch; i++)
-			RC(colsum_f32(s, g.p + i * g.batch_inc, g.rows, g.cols, g.rs, db.p + (db.batch == 1 ? 0 : i * db.batch_inc), accumulate || (db.batch == 1 && i > 0), ccv_nnc_stream_context_get_workspace(stream_context, colsum_workspace_bytes(g.cols), CCV_TENSOR_GPU_MEMORY)));
+			RC(colsum_any(s, kind, (const char*)g.p + (size_t)i * g.batch_inc * esz, g.rows, g.cols, g.rs, (char*)db.p + (db.batch == 1 ? 0 : (size_t)i * db.batch_inc * kind_size(db_kind)), db_kind, accumulate || (db.batch == 1 && i > 0), ccv_nnc_stream_context_get_workspace(stream_context, colsum_workspace_bytes(g.cols), CCV_TENSOR_GPU_MEMORY)));
 	}
 	if (dw_t)
 	{
-		if (!inputs[1])
+		if (!inputs[1] || kind_of(inputs[1]) != kind || kind_of(dw_t) != kind)
 			return CCV_NNC_EXEC_INVALID;
 		Mat a, dw;
 		if (!mat_of(view_of(inputs[1]), cmd.info.blas.transpose_a, a) || !mat_of(view_of(dw_t), cmd.info.blas.transpose_b, dw))
@@ -298,12 +354,17 @@ int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		if (a.batch == 1)
 			a.batch_inc = 0;
 		// dw[K, N] = a^T[K, M] * g[M, N]; a shared dw sums over the batch
+		if (kind != 0)
+		{
+			for (int i = 0; i < g.batch; i++)
+				RC(gemm_dispatch16(s, scratch_of(stream_context), kind, dw.rows, dw.cols, g.rows, (const char*)a.p + (size_t)i * a.batch_inc * 2, a.cs, a.rs, (const char*)g.p + (size_t)i * g.batch_inc * 2, g.rs, g.cs, (char*)dw.p + (dw.batch == 1 ? 0 : (size_t)i * dw.batch_inc * 2), dw.rs, dw.cs, 0, 0, accumulate || (dw.batch == 1 && i > 0)));
+		} else
 		for (int i = 0; i < g.batch; i++)
 			RC(gemm_dispatch(s, scratch_of(stream_context), gemm_algorithm(cmd), dw.rows, dw.cols, g.rows, a.p + i * a.batch_inc, a.cs, a.rs, g.p + i * g.batch_inc, g.rs, g.cs, dw.p + (dw.batch == 1 ? 0 : i * dw.batch_inc), dw.rs, dw.cs, 0, accumulate || (dw.batch == 1 && i > 0)));
 	}
 	if (h_t)
 	{
-		if (input_size < 3 || !inputs[2])
+		if (input_size < 3 || !inputs[2] || kind_of(inputs[2]) != kind || kind_of(h_t) != kind)
 			return CCV_NNC_EXEC_INVALID;
 		Mat h, w;
 		if (!mat_of(view_of(h_t), cmd.info.blas.transpose_a, h) || !mat_of(view_of(inputs[2]), cmd.info.blas.transpose_b, w))
@@ -313,6 +374,11 @@ int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		if (w.batch == 1)
 			w.batch_inc = 0;
 		// h[M, K] = g[M, N] * w^T[N, K]
+		if (kind != 0)
+		{
+			for (int i = 0; i < g.batch; i++)
+				RC(gemm_dispatch16(s, scratch_of(stream_context), kind, h.rows, h.cols, g.cols, (const char*)g.p + (size_t)i * g.batch_inc * 2, g.rs, g.cs, (const char*)w.p + (size_t)i * w.batch_inc * 2, w.cs, w.rs, (char*)h.p + (h.batch == 1 ? 0 : (size_t)i * h.batch_inc * 2), h.rs, h.cs, 0, 0, accumulate || (h.batch == 1 && i > 0)));
+		} else
 		for (int i = 0; i < g.batch; i++)
 			RC(gemm_dispatch(s, scratch_of(stream_context), gemm_algorithm(cmd), h.rows, h.cols, g.cols, g.p + i * g.batch_inc, g.rs, g.cs, w.p + i * w.batch_inc, w.cs, w.rs, h.p + (h.batch == 1 ? 0 : i * h.batch_inc), h.rs, h.cs, 0, accumulate || (h.batch == 1 && i > 0)));
 	}
@@ -363,6 +429,28 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1] || !outputs[0])
 		return CCV_NNC_EXEC_INVALID;
 	const ccv_nnc_tensor_t* const bias_t = input_size > 2 ? inputs[2] : 0;
+	const int kind = kind_of(inputs[0]);
+	if (kind > 0)
+	{
+		// bf16 / fp16 tensors: NHWC, one group, tcgen05 kind::f16 with fp32 accumulation; the bias is fp32 or of the tensors' type
+		if (kind_of(inputs[1]) != kind || kind_of(outputs[0]) != kind || (bias_t && ((kind_of(bias_t) != kind && !is_f32(bias_t)) || CCV_IS_TENSOR_VIEW(bias_t))))
+			return CCV_NNC_EXEC_INVALID;
+		ConvGeom g16;
+		if ((cmd.info.convolution.groups > 1) || !conv_geom(cmd, hint, view_of(inputs[0]), view_of(inputs[1]), view_of(outputs[0]), g16) || (bias_t && bias_t->info.dim[0] != g16.K))
+			return CCV_NNC_EXEC_INVALID;
+		cudaStream_t s16 = stream_of(stream_context);
+		const float* const bias32 = bias_t && is_f32(bias_t) ? bias_t->data.f32 : 0;
+		const void* const bias16 = bias_t && !is_f32(bias_t) ? (const void*)bias_t->data.u8 : 0;
+		int rc = conv_fprop_16(s16, kind, g16, inputs[0]->data.u8, inputs[1]->data.u8, bias32, bias16, outputs[0]->data.u8, scratch_of(stream_context));
+		if (rc > 0 && g16.C % 8 != 0)
+		{
+			// pixels that TMA cannot address (the 3-channel stem): explicit im2col + tensor-core GEMM
+			void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, conv_im2col_workspace_bytes(g16, kind), CCV_TENSOR_GPU_MEMORY);
+			if (ws)
+				rc = conv_fprop_im2col_16(s16, kind, g16, inputs[0]->data.u8, inputs[1]->data.u8, bias32, bias16, outputs[0]->data.u8, ws);
+		}
+		return rc == 0 ? CCV_NNC_EXEC_SUCCESS : CCV_NNC_EXEC_INVALID;
+	}
 	if (!is_f32(inputs[0]) || !is_f32(inputs[1]) || !is_f32(outputs[0]) || (bias_t && (!is_f32(bias_t) || CCV_IS_TENSOR_VIEW(bias_t))))
 		return CCV_NNC_EXEC_INVALID;
 	ConvGeom g;
@@ -456,6 +544,46 @@ int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	ccv_nnc_tensor_t* const dbias_t = output_size > 2 ? outputs[2] : 0;
 	const ccv_nnc_tensor_t* const w_t = input_size > 2 ? inputs[2] : 0;
 	const ccv_nnc_tensor_t* const filt = dw_t ? dw_t : w_t;
+	const int kind = kind_of(inputs[0]);
+	if (kind > 0 && filt)
+	{
+		// bf16 / fp16: the same three products on the kind::f16 kernels; dbias in fp32 or the tensors' type
+		if (kind_of(inputs[1]) != kind || kind_of(filt) != kind || (h_t && kind_of(h_t) != kind) || (w_t && kind_of(w_t) != kind) || cmd.info.convolution.groups > 1)
+			return CCV_NNC_EXEC_INVALID;
+		ConvGeom g16;
+		if (!conv_geom(cmd, hint, view_of(inputs[1]), view_of(filt), view_of(inputs[0]), g16))
+			return CCV_NNC_EXEC_INVALID;
+		const int acc16 = (flags & CCV_NNC_ACCUMULATE_OUTPUT) ? 1 : 0;
+		cudaStream_t s16 = stream_of(stream_context);
+		if (dbias_t)
+		{
+			const int db_kind = kind_of(dbias_t);
+			if (db_kind < 0 || dbias_t->info.dim[0] != g16.K || g16.bh != (long long)g16.Q * g16.bw || g16.bn != (long long)g16.P * g16.bh)
+				return CCV_NNC_EXEC_INVALID;
+			RC(colsum_any(s16, kind, inputs[0]->data.u8, (size_t)g16.N * g16.P * g16.Q, g16.K, g16.bw, dbias_t->data.u8, db_kind, acc16, ccv_nnc_stream_context_get_workspace(stream_context, colsum_workspace_bytes(g16.K), CCV_TENSOR_GPU_MEMORY)));
+		}
+		if (dw_t)
+		{
+			int rc = conv_wgrad_16(s16, kind, g16, inputs[0]->data.u8, inputs[1]->data.u8, dw_t->data.u8, acc16, scratch_of(stream_context));
+			if (rc > 0 && g16.C % 8 != 0)
+			{
+				void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, conv_im2col_workspace_bytes(g16, kind), CCV_TENSOR_GPU_MEMORY);
+				if (ws)
+					rc = conv_wgrad_im2col_16(s16, kind, g16, inputs[0]->data.u8, inputs[1]->data.u8, dw_t->data.u8, acc16, ws);
+			}
+			if (rc)
+				return CCV_NNC_EXEC_INVALID;
+		}
+		if (h_t)
+		{
+			ConvGeom gh16;
+			if (!w_t || !conv_geom(cmd, hint, view_of(h_t), view_of(w_t), view_of(inputs[0]), gh16))
+				return CCV_NNC_EXEC_INVALID;
+			if (conv_dgrad_16(s16, kind, gh16, inputs[0]->data.u8, w_t->data.u8, h_t->data.u8, scratch_of(stream_context)))
+				return CCV_NNC_EXEC_INVALID;
+		}
+		return CCV_NNC_EXEC_SUCCESS;
+	}
 	if (!filt || !is_f32(inputs[0]) || !is_f32(inputs[1]))
 		return CCV_NNC_EXEC_INVALID;
 	ConvGeom g;
@@ -551,10 +679,12 @@ int bnorm_forw(const int fuse_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_
 	const ccv_nnc_tensor_t* const stats_t = input_size == 6 ? inputs[5] : 0;
 	if ((input_size != 5 && input_size != 6) || output_size < 1)
 		return CCV_NNC_EXEC_INVALID;
-	for (int i = 0; i < 5; i++)
+	// x / y may be fp32, bf16 or fp16; scale, bias and the statistics are fp32 (lib/nnc/ccv_cnnp_model_addons.c:954-956)
+	for (int i = 1; i < 5; i++)
 		if (!inputs[i] || !is_f32(inputs[i]))
 			return CCV_NNC_EXEC_INVALID;
-	if (!outputs[0] || !is_f32(outputs[0]))
+	const int kind = inputs[0] ? kind_of(inputs[0]) : -1;
+	if (kind < 0 || !outputs[0] || kind_of(outputs[0]) != kind)
 		return CCV_NNC_EXEC_INVALID;
 	const TV a = view_of(inputs[0]), scale = view_of(inputs[1]), b = view_of(outputs[0]);
 	size_t outer, inner;
@@ -572,7 +702,10 @@ int bnorm_forw(const int fuse_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_
 		void* const tws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
 		if (!tws)
 			return CCV_NNC_EXEC_OOM;
-		RC(bn_fwd_test_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, inputs[3]->data.f32, inputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, tws));
+		if (kind == 0)
+			RC(bn_fwd_test_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, inputs[3]->data.f32, inputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, tws));
+		else
+			RC(bn_fwd_test_16(s, kind, inputs[0]->data.u8, outputs[0]->data.u8, inputs[1]->data.f32, inputs[2]->data.f32, inputs[3]->data.f32, inputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, tws));
 		return CCV_NNC_EXEC_SUCCESS;
 	}
 	if (output_size != 5 || !outputs[1] || !outputs[2] || !outputs[3] || !outputs[4])
@@ -585,8 +718,15 @@ int bnorm_forw(const int fuse_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_
 	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
 	if (!ws)
 		return CCV_NNC_EXEC_OOM;
-	RC(bn_fwd_train_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, outputs[3]->data.f32, outputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, cmd.info.bnorm.momentum, ws, fuse_relu,
-		stats_t && inner == 1 ? stats_t->data.f32 : 0, stats_t ? (int)stats_t->sig : 0));
+	for (int i = 1; i < 5; i++)
+		if (!is_f32(outputs[i]))
+			return CCV_NNC_EXEC_INVALID;
+	if (kind == 0)
+		RC(bn_fwd_train_f32(s, inputs[0]->data.f32, outputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, outputs[3]->data.f32, outputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, cmd.info.bnorm.momentum, ws, fuse_relu,
+			stats_t && inner == 1 ? stats_t->data.f32 : 0, stats_t ? (int)stats_t->sig : 0));
+	else
+		RC(bn_fwd_train_16(s, kind, inputs[0]->data.u8, outputs[0]->data.u8, inputs[1]->data.f32, inputs[2]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, outputs[3]->data.f32, outputs[4]->data.f32, outer, C, inner, cmd.info.bnorm.epsilon, cmd.info.bnorm.momentum, ws, fuse_relu,
+			stats_t && inner == 1 ? stats_t->data.f32 : 0, stats_t ? (int)stats_t->sig : 0));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -625,7 +765,10 @@ int bnorm_back(const int fused_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint
 	int C;
 	if (!same_shape(a, g) || !g.contiguous || !bn_layout(a, scale, outer, C, inner))
 		return CCV_NNC_EXEC_INVALID;
-	if (conv_dbias_t && (!h_t_ok(outputs[0]) || !is_f32(conv_dbias_t) || view_of(conv_dbias_t).count != (size_t)C || !view_of(conv_dbias_t).contiguous))
+	const int kind = kind_of(g_t);
+	if (kind < 0 || kind_of(a_t) != kind || (h_t && kind_of(h_t) != kind) || !is_f32(scale_t) || !is_f32(mean_t) || !is_f32(istd_t) || (bias_t && !is_f32(bias_t)) || (dscale_t && !is_f32(dscale_t)) || (dbias_t && !is_f32(dbias_t)))
+		return CCV_NNC_EXEC_INVALID;
+	if (conv_dbias_t && (!h_t_ok(outputs[0]) || kind_of(conv_dbias_t) < 0 || view_of(conv_dbias_t).count != (size_t)C || !view_of(conv_dbias_t).contiguous))
 		return CCV_NNC_EXEC_INVALID;
 	if (h_t && (!same_shape(view_of(h_t), a) || !view_of(h_t).contiguous))
 		return CCV_NNC_EXEC_INVALID;
@@ -633,7 +776,13 @@ int bnorm_back(const int fused_relu, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint
 	void* const ws = ccv_nnc_stream_context_get_workspace(stream_context, bn_workspace_bytes(C), CCV_TENSOR_GPU_MEMORY);
 	if (!ws)
 		return CCV_NNC_EXEC_OOM;
-	RC(bn_bwd_f32(s, g_t->data.f32, a_t->data.f32, scale_t->data.f32, bias_t ? bias_t->data.f32 : 0, mean_t->data.f32, istd_t->data.f32, h_t ? h_t->data.f32 : 0, dscale_t ? dscale_t->data.f32 : 0, dbias_t ? dbias_t->data.f32 : 0, outer, C, inner, ws, conv_dbias_t ? conv_dbias_t->data.f32 : 0));
+	if (kind == 0 && (!conv_dbias_t || is_f32(conv_dbias_t)))
+		RC(bn_bwd_f32(s, g_t->data.f32, a_t->data.f32, scale_t->data.f32, bias_t ? bias_t->data.f32 : 0, mean_t->data.f32, istd_t->data.f32, h_t ? h_t->data.f32 : 0, dscale_t ? dscale_t->data.f32 : 0, dbias_t ? dbias_t->data.f32 : 0, outer, C, inner, ws, conv_dbias_t ? conv_dbias_t->data.f32 : 0));
+	else if (kind != 0)
+		RC(bn_bwd_16(s, kind, g_t->data.u8, a_t->data.u8, scale_t->data.f32, bias_t ? bias_t->data.f32 : 0, mean_t->data.f32, istd_t->data.f32, h_t ? (void*)h_t->data.u8 : 0, dscale_t ? dscale_t->data.f32 : 0, dbias_t ? dbias_t->data.f32 : 0, outer, C, inner, ws,
+			conv_dbias_t ? (void*)conv_dbias_t->data.u8 : 0, conv_dbias_t ? kind_of(conv_dbias_t) : 0));
+	else
+		return CCV_NNC_EXEC_INVALID;
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -645,12 +794,15 @@ int exec_bnorm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const in
 // ================================================================================================ RELU / EW
 int exec_relu_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
-	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || kind_of(inputs[0]) < 0 || kind_of(outputs[0]) != kind_of(inputs[0]))
 		return CCV_NNC_EXEC_INVALID;
 	const TV a = view_of(inputs[0]), b = view_of(outputs[0]);
 	if (!a.contiguous || !b.contiguous || a.count != b.count)
 		return CCV_NNC_EXEC_INVALID;
-	RC(ew_relu_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, outputs[0]->data.f32, a.count));
+	if (kind_of(inputs[0]) == 0)
+		RC(ew_relu_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, outputs[0]->data.f32, a.count));
+	else
+		RC(ew_relu_fwd_16(stream_of(stream_context), kind_of(inputs[0]), inputs[0]->data.u8, outputs[0]->data.u8, a.count));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -661,18 +813,46 @@ int exec_relu_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	const TV g = view_of(inputs[0]), b = view_of(inputs[2]), h = view_of(outputs[0]);
 	if (!g.contiguous || !b.contiguous || !h.contiguous || g.count != b.count || g.count != h.count)
 		return CCV_NNC_EXEC_INVALID;
-	RC(ew_relu_bwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, g.count));
+	const int kind = kind_of(inputs[0]);
+	if (kind < 0 || kind_of(inputs[2]) != kind || kind_of(outputs[0]) != kind)
+		return CCV_NNC_EXEC_INVALID;
+	if (kind == 0)
+		RC(ew_relu_bwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, g.count));
+	else
+		RC(ew_relu_bwd_16(stream_of(stream_context), kind, inputs[0]->data.u8, inputs[2]->data.u8, outputs[0]->data.u8, g.count));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
 // ew/ccv_nnc_ew_cpu_ref.c:15-110,207-214
 int exec_ewsum_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
-	if (input_size < 1 || output_size < 1 || !outputs[0] || !is_f32(outputs[0]))
+	if (input_size < 1 || output_size < 1 || !outputs[0] || kind_of(outputs[0]) < 0)
 		return CCV_NNC_EXEC_INVALID;
 	const TV c = view_of(outputs[0]);
 	if (!c.contiguous || input_size > 64)
 		return CCV_NNC_EXEC_INVALID;
+	if (kind_of(outputs[0]) > 0)
+	{
+		// bf16 / fp16: up to 8 operands, summed in fp32 and rounded once
+		const int kind = kind_of(outputs[0]);
+		const void* p16[8];
+		if (input_size > 8)
+			return CCV_NNC_EXEC_INVALID;
+		for (int i = 0; i < input_size; i++)
+		{
+			if (!inputs[i] || kind_of(inputs[i]) != kind || !view_of(inputs[i]).contiguous || view_of(inputs[i]).count != c.count)
+				return CCV_NNC_EXEC_INVALID;
+			p16[i] = inputs[i]->data.u8;
+		}
+		if (input_size == 1)
+		{
+			if (p16[0] != outputs[0]->data.u8 && cudaMemcpyAsync(outputs[0]->data.u8, p16[0], c.count * 2, cudaMemcpyDeviceToDevice, stream_of(stream_context)) != cudaSuccess)
+				return CCV_NNC_EXEC_INVALID;
+			return CCV_NNC_EXEC_SUCCESS;
+		}
+		RC(ew_sum_16(stream_of(stream_context), kind, p16, input_size, outputs[0]->data.u8, c.count));
+		return CCV_NNC_EXEC_SUCCESS;
+	}
 	const float* ptrs[64];
 	for (int i = 0; i < input_size; i++)
 	{
@@ -703,16 +883,20 @@ int exec_ewsum_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const in
 		if (!outputs[i])
 			continue;
 		const TV h = view_of(outputs[i]);
-		if (!h.contiguous || !is_f32(outputs[i]))
+		const int kind = kind_of(outputs[i]);
+		if (!h.contiguous || kind < 0)
 			return CCV_NNC_EXEC_INVALID;
 		if (input_size < 1 || !inputs[0])
-			RC(ew_set_f32(s, outputs[i]->data.f32, h.count, 1.f));
-		else if (inputs[0]->data.f32 != outputs[i]->data.f32)
 		{
+			if (kind == 0)
+				RC(ew_set_f32(s, outputs[i]->data.f32, h.count, 1.f));
+			else
+				RC(ew_set_u16(s, (uint16_t*)outputs[i]->data.u8, h.count, kind == 1 ? (uint16_t)0x3f80 : (uint16_t)0x3c00));
+		} else if (inputs[0]->data.u8 != outputs[i]->data.u8) {
 			const TV g = view_of(inputs[0]);
-			if (!g.contiguous || g.count != h.count)
+			if (!g.contiguous || g.count != h.count || kind_of(inputs[0]) != kind)
 				return CCV_NNC_EXEC_INVALID;
-			if (cudaMemcpyAsync(outputs[i]->data.f32, inputs[0]->data.f32, h.count * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+			if (cudaMemcpyAsync(outputs[i]->data.u8, inputs[0]->data.u8, h.count * kind_size(kind), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
 				return CCV_NNC_EXEC_INVALID;
 		}
 	}
@@ -911,12 +1095,15 @@ bool pool_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, const TV& a
 template <int IS_MAX>
 int exec_pool_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
-	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || kind_of(inputs[0]) < 0 || kind_of(outputs[0]) != kind_of(inputs[0]))
 		return CCV_NNC_EXEC_INVALID;
+	const int kind = kind_of(inputs[0]);
 	PoolGeom g;
 	if (!pool_geom(cmd, hint, view_of(inputs[0]), view_of(outputs[0]), g))
 		return CCV_NNC_EXEC_INVALID;
-	if (IS_MAX)
+	if (kind != 0)
+		RC(IS_MAX ? pool_max_fwd_16(stream_of(stream_context), kind, g, inputs[0]->data.u8, outputs[0]->data.u8) : pool_avg_fwd_16(stream_of(stream_context), kind, g, inputs[0]->data.u8, outputs[0]->data.u8));
+	else if (IS_MAX)
 		RC(pool_max_fwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, outputs[0]->data.f32));
 	else
 		RC(pool_avg_fwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, outputs[0]->data.f32));
@@ -927,8 +1114,9 @@ int exec_pool_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 template <int IS_MAX>
 int exec_pool_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
-	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || !is_f32(inputs[0]) || !is_f32(outputs[0]))
+	if (input_size < 1 || output_size < 1 || !inputs[0] || !outputs[0] || kind_of(inputs[0]) < 0 || kind_of(outputs[0]) != kind_of(inputs[0]))
 		return CCV_NNC_EXEC_INVALID;
+	const int kind = kind_of(inputs[0]);
 	PoolGeom g;
 	if (!pool_geom(cmd, hint, view_of(outputs[0]), view_of(inputs[0]), g))
 		return CCV_NNC_EXEC_INVALID;
@@ -946,8 +1134,15 @@ int exec_pool_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		for (int i = 0; i < b.nd; i++)
 			if (b.stride[i] != gv.stride[i])
 				return CCV_NNC_EXEC_INVALID;
-		RC(pool_max_bwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32));
-	} else
+		if (kind_of(inputs[1]) != kind || kind_of(inputs[2]) != kind)
+			return CCV_NNC_EXEC_INVALID;
+		if (kind != 0)
+			RC(pool_max_bwd_16(stream_of(stream_context), kind, g, inputs[0]->data.u8, inputs[1]->data.u8, inputs[2]->data.u8, outputs[0]->data.u8));
+		else
+			RC(pool_max_bwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32));
+	} else if (kind != 0)
+		RC(pool_avg_bwd_16(stream_of(stream_context), kind, g, inputs[0]->data.u8, outputs[0]->data.u8));
+	else
 		RC(pool_avg_bwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, outputs[0]->data.f32));
 	return CCV_NNC_EXEC_SUCCESS;
 }
@@ -1063,9 +1258,11 @@ int exec_sgd_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int 
 	if (input_size != 3 || output_size != 2)
 		return CCV_NNC_EXEC_INVALID;
 	size_t count = 0;
+	// the gradient may be fp32, bf16 or fp16; parameters and momenta are fp32 (the reference's GPU kernel takes the mixed form
+	// g 16-bit / a, m fp32 too: sgd/gpu/ccv_nnc_sgd_gpu_ref.cu:71-74)
 	for (int i = 0; i < 3; i++)
 	{
-		if (!inputs[i] || !is_f32(inputs[i]) || !view_of(inputs[i]).contiguous)
+		if (!inputs[i] || (i == 0 ? kind_of(inputs[i]) < 0 : !is_f32(inputs[i])) || !view_of(inputs[i]).contiguous)
 			return CCV_NNC_EXEC_INVALID;
 		if (i == 0)
 			count = view_of(inputs[0]).count;
@@ -1077,7 +1274,7 @@ int exec_sgd_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int 
 			return CCV_NNC_EXEC_INVALID;
 	if (cmd.info.sgd.nesterov && cmd.info.sgd.dampening != 0)
 		return CCV_NNC_EXEC_INVALID;
-	RC(sgd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, outputs[1]->data.f32, count, cmd.info.sgd.nesterov, cmd.info.sgd.rate, cmd.info.sgd.scale, cmd.info.sgd.decay, cmd.info.sgd.momentum, cmd.info.sgd.dampening));
+	RC(sgd_any(stream_of(stream_context), kind_of(inputs[0]), inputs[0]->data.u8, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, outputs[1]->data.f32, count, cmd.info.sgd.nesterov, cmd.info.sgd.rate, cmd.info.sgd.scale, cmd.info.sgd.decay, cmd.info.sgd.momentum, cmd.info.sgd.dampening));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -1090,13 +1287,17 @@ int exec_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	if (cmd.info.sgd.nesterov && cmd.info.sgd.dampening != 0)
 		return CCV_NNC_EXEC_INVALID;
 	const int T = input_size / 3;
-	std::vector<const float*> g(T), a(T), m(T);
+	std::vector<const void*> g(T);
+	std::vector<const float*> a(T), m(T);
 	std::vector<float*> b(T), n(T);
+	const int g_kind = inputs[0] ? kind_of(inputs[0]) : -1;
+	if (g_kind < 0)
+		return CCV_NNC_EXEC_INVALID;
 	std::vector<size_t> counts(T);
 	for (int t = 0; t < T; t++)
 	{
 		for (int i = 0; i < 3; i++)
-			if (!inputs[3 * t + i] || !is_f32(inputs[3 * t + i]) || !view_of(inputs[3 * t + i]).contiguous)
+			if (!inputs[3 * t + i] || (i == 0 ? kind_of(inputs[3 * t]) != g_kind : !is_f32(inputs[3 * t + i])) || !view_of(inputs[3 * t + i]).contiguous)
 				return CCV_NNC_EXEC_INVALID;
 		counts[t] = view_of(inputs[3 * t]).count;
 		if (view_of(inputs[3 * t + 1]).count != counts[t] || view_of(inputs[3 * t + 2]).count != counts[t])
@@ -1104,10 +1305,10 @@ int exec_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		for (int i = 0; i < 2; i++)
 			if (!outputs[2 * t + i] || !is_f32(outputs[2 * t + i]) || !view_of(outputs[2 * t + i]).contiguous || view_of(outputs[2 * t + i]).count != counts[t])
 				return CCV_NNC_EXEC_INVALID;
-		g[t] = inputs[3 * t]->data.f32, a[t] = inputs[3 * t + 1]->data.f32, m[t] = inputs[3 * t + 2]->data.f32;
+		g[t] = inputs[3 * t]->data.u8, a[t] = inputs[3 * t + 1]->data.f32, m[t] = inputs[3 * t + 2]->data.f32;
 		b[t] = outputs[2 * t]->data.f32, n[t] = outputs[2 * t + 1]->data.f32;
 	}
-	RC(sgd_multi_f32(stream_of(stream_context), T, g.data(), a.data(), m.data(), b.data(), n.data(), counts.data(), cmd.info.sgd.nesterov, cmd.info.sgd.rate, cmd.info.sgd.scale, cmd.info.sgd.decay, cmd.info.sgd.momentum, cmd.info.sgd.dampening));
+	RC(sgd_multi_any(stream_of(stream_context), T, g_kind, g.data(), a.data(), m.data(), b.data(), n.data(), counts.data(), cmd.info.sgd.nesterov, cmd.info.sgd.rate, cmd.info.sgd.scale, cmd.info.sgd.decay, cmd.info.sgd.momentum, cmd.info.sgd.dampening));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -1387,9 +1588,13 @@ extern "C" int ccv_nnc_sm100_fused_add_relu_forw(const ccv_nnc_cmd_t cmd, const 
 	if (input_size != 2 || output_size != 1 || !inputs[0] || !inputs[1] || !outputs[0])
 		return CCV_NNC_EXEC_INVALID;
 	const TV a = view_of(inputs[0]), b = view_of(inputs[1]), y = view_of(outputs[0]);
-	if (!a.contiguous || !b.contiguous || !y.contiguous || a.count != y.count || b.count != y.count || !is_f32(inputs[0]) || !is_f32(inputs[1]) || !is_f32(outputs[0]))
+	const int kind = kind_of(outputs[0]);
+	if (!a.contiguous || !b.contiguous || !y.contiguous || a.count != y.count || b.count != y.count || kind < 0 || kind_of(inputs[0]) != kind || kind_of(inputs[1]) != kind)
 		return CCV_NNC_EXEC_INVALID;
-	RC(ew_add_relu_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, outputs[0]->data.f32, y.count));
+	if (kind != 0)
+		RC(ew_add_relu_fwd_16(stream_of(stream_context), kind, inputs[0]->data.u8, inputs[1]->data.u8, outputs[0]->data.u8, y.count));
+	else
+		RC(ew_add_relu_fwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, outputs[0]->data.f32, y.count));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -1399,9 +1604,13 @@ extern "C" int ccv_nnc_sm100_fused_add_relu_back(const ccv_nnc_cmd_t cmd, const 
 	if (input_size != 3 || output_size != 1 || !inputs[0] || !inputs[1] || !inputs[2] || !outputs[0])
 		return CCV_NNC_EXEC_INVALID;
 	const TV a = view_of(inputs[0]), b = view_of(inputs[1]), y = view_of(inputs[2]), o = view_of(outputs[0]);
-	if (!a.contiguous || !b.contiguous || !y.contiguous || !o.contiguous || a.count != o.count || b.count != o.count || y.count != o.count)
+	const int kind = kind_of(outputs[0]);
+	if (!a.contiguous || !b.contiguous || !y.contiguous || !o.contiguous || a.count != o.count || b.count != o.count || y.count != o.count || kind < 0 || kind_of(inputs[0]) != kind || kind_of(inputs[1]) != kind || kind_of(inputs[2]) != kind)
 		return CCV_NNC_EXEC_INVALID;
-	RC(ew_add_relu_bwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, o.count));
+	if (kind != 0)
+		RC(ew_add_relu_bwd_16(stream_of(stream_context), kind, inputs[0]->data.u8, inputs[1]->data.u8, inputs[2]->data.u8, outputs[0]->data.u8, o.count));
+	else
+		RC(ew_add_relu_bwd_f32(stream_of(stream_context), inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, outputs[0]->data.f32, o.count));
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -1433,36 +1642,36 @@ extern "C" int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_
 // ================================================================================================ registration
 #define REGISTER_SM100(cmd) extern "C" void _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(ccv_nnc_cmd_backend_registry_t* const registry)
 
-REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_forw); registry->autotune = autotune_contraction<exec_gemm_forw>; }
-REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); registry->autotune = autotune_contraction<exec_gemm_back>; }
-REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); registry->autotune = autotune_contraction<exec_conv_forw>; }
-REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); registry->autotune = autotune_contraction<exec_conv_back>; }
+REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_forw); registry->autotune = autotune_contraction<exec_gemm_forw>; }
+REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); registry->autotune = autotune_contraction<exec_gemm_back>; }
+REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); registry->autotune = autotune_contraction<exec_conv_forw>; }
+REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); registry->autotune = autotune_contraction<exec_conv_back>; }
 REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_forw); }
 REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_back); }
 REGISTER_SM100(CCV_NNC_SOFTMAX_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_forw); }
 REGISTER_SM100(CCV_NNC_SOFTMAX_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_back); }
-REGISTER_SM100(CCV_NNC_BATCH_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_bnorm_forw); }
-REGISTER_SM100(CCV_NNC_BATCH_NORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_bnorm_back); }
+REGISTER_SM100(CCV_NNC_BATCH_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_bnorm_forw); }
+REGISTER_SM100(CCV_NNC_BATCH_NORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_bnorm_back); }
 REGISTER_SM100(CCV_NNC_LAYER_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_lnorm_forw); }
 REGISTER_SM100(CCV_NNC_LAYER_NORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_lnorm_back); }
 REGISTER_SM100(CCV_NNC_GROUP_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_gnorm_forw); }
 REGISTER_SM100(CCV_NNC_GROUP_NORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_gnorm_back); }
 REGISTER_SM100(CCV_NNC_RMSNORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_rmsnorm_forw); }
 REGISTER_SM100(CCV_NNC_RMSNORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_rmsnorm_back); }
-REGISTER_SM100(CCV_NNC_EWSUM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_ewsum_forw); }
-REGISTER_SM100(CCV_NNC_EWSUM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_ewsum_back); }
+REGISTER_SM100(CCV_NNC_EWSUM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_ewsum_forw); }
+REGISTER_SM100(CCV_NNC_EWSUM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_ewsum_back); }
 REGISTER_SM100(CCV_NNC_ADD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_add_forw); }
 REGISTER_SM100(CCV_NNC_ADD_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_add_back); }
 REGISTER_SM100(CCV_NNC_MUL_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_mul_forw); }
 REGISTER_SM100(CCV_NNC_MUL_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_mul_back); }
 REGISTER_SM100(CCV_NNC_SCALAR_MUL_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_scalar_mul_forw); }
 REGISTER_SM100(CCV_NNC_SCALAR_MUL_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_scalar_mul_back); }
-REGISTER_SM100(CCV_NNC_RELU_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_relu_forw); }
-REGISTER_SM100(CCV_NNC_RELU_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_relu_back); }
-REGISTER_SM100(CCV_NNC_MAX_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, 1, exec_pool_forw<1>); }
-REGISTER_SM100(CCV_NNC_MAX_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, 1, exec_pool_back<1>); }
-REGISTER_SM100(CCV_NNC_AVERAGE_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, 1, exec_pool_forw<0>); }
-REGISTER_SM100(CCV_NNC_AVERAGE_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F, 1, exec_pool_back<0>); }
+REGISTER_SM100(CCV_NNC_RELU_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_relu_forw); }
+REGISTER_SM100(CCV_NNC_RELU_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_relu_back); }
+REGISTER_SM100(CCV_NNC_MAX_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_forw<1>); }
+REGISTER_SM100(CCV_NNC_MAX_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_back<1>); }
+REGISTER_SM100(CCV_NNC_AVERAGE_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_forw<0>); }
+REGISTER_SM100(CCV_NNC_AVERAGE_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_back<0>); }
 REGISTER_SM100(CCV_NNC_UPSAMPLE_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, 1, ccv_nnc_sm100_exec_upsample_forw); }
 REGISTER_SM100(CCV_NNC_UPSAMPLE_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, 1, ccv_nnc_sm100_exec_upsample_back); }
 REGISTER_SM100(CCV_NNC_SET_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_set_forw); }
@@ -1475,7 +1684,7 @@ REGISTER_SM100(CCV_NNC_TRANSPOSE_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F 
 REGISTER_SM100(CCV_NNC_TRANSPOSE_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_transpose); }
 REGISTER_SM100(CCV_NNC_DATATYPE_CONVERSION_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF, 1, exec_datatype_conversion); }
 REGISTER_SM100(CCV_NNC_DATATYPE_CONVERSION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF, 1, exec_datatype_conversion); }
-REGISTER_SM100(CCV_NNC_SGD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_sgd_forw); }
+REGISTER_SM100(CCV_NNC_SGD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_sgd_forw); }
 REGISTER_SM100(CCV_NNC_SGD_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_invalid); }
 REGISTER_SM100(CCV_NNC_CATEGORICAL_CROSSENTROPY_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_cce_forw); }
 REGISTER_SM100(CCV_NNC_CATEGORICAL_CROSSENTROPY_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_cce_back); }

@@ -9,6 +9,7 @@
 // Workspace (bn_workspace_bytes): double s[2C] (cross-block sums) followed by float coef[4C] (per-channel a, b, p, q).
 #include "sm100_ew.h"
 #include "sm100_contract.h"
+#include "sm100_elem.cuh"
 
 namespace sm100 {
 
@@ -36,7 +37,6 @@ static int check(const char* what)
 	}
 	return 0;
 }
-static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 static int grid_for(size_t work_items, int threads, int max_waves = 8)
 {
 	size_t blocks = (work_items + threads - 1) / threads;
@@ -53,15 +53,13 @@ static inline double* ws_sums(void* ws) { return (double*)ws; }
 static inline float* ws_coef(void* ws, int C) { return (float*)((double*)ws + 2 * (size_t)C); }
 static inline float* ws_part(void* ws, int C) { return (float*)(((uintptr_t)(ws_coef(ws, C) + 4 * (size_t)C) + 255) & ~(uintptr_t)255); }
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ------------------------------------------------------------------------------------------------ reductions
 // NHWC: thread = (column-vector tx, row-lane ty); each thread walks rows with 4 independent 128-bit loads in flight.
 // MODE 0: s1 = sum(x - k), s2 = sum((x - k)^2), k = x[0, c] (shift keeps the one-pass variance well conditioned).
 // MODE 1: s1 = sum(g'), s2 = sum(g' * (x - mean)); g' = g, or g masked by relu(x * a + b) > 0 when MASK.
-template <int MODE, int MASK>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t rows, const int C, float* __restrict__ part, const int cpb)
+template <typename T, int MODE, int MASK>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t rows, const int C, float* __restrict__ part, const int cpb)
 {
 	__shared__ float4 sh[2][256];
 	const int CV = C >> 2;
@@ -131,12 +129,12 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 }
 
 // any layout [outer, C, inner], scalar: one block per channel (NCHW, or C not a multiple of 4)
-template <int MODE, int MASK>
-__global__ void bn_reduce_generic_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t outer, const int C, const size_t inner, double* __restrict__ ws)
+template <typename T, int MODE, int MASK>
+__global__ void bn_reduce_generic_kernel(const T* __restrict__ x, const T* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t outer, const int C, const size_t inner, double* __restrict__ ws)
 {
 	__shared__ float sh[2][32];
 	const int c = blockIdx.x;
-	const float k = MODE == 0 ? x[(size_t)c * inner] : mean[c];
+	const float k = MODE == 0 ? ldf(x + (size_t)c * inner) : mean[c];
 	const float a = MASK ? coef[c] : 0.f, b = MASK ? coef[C + c] : 0.f;
 	float s1 = 0.f, s2 = 0.f;
 	const size_t total = outer * inner;
@@ -144,13 +142,13 @@ __global__ void bn_reduce_generic_kernel(const float* __restrict__ x, const floa
 	{
 		const size_t o = i / inner, in = i - o * inner;
 		const size_t idx = (o * C + c) * inner + in;
-		const float xv = x[idx];
+		const float xv = ldf(x + idx);
 		if (MODE == 0)
 		{
 			const float d = xv - k;
 			s1 += d, s2 += d * d;
 		} else {
-			float gv = g[idx];
+			float gv = ldf(g + idx);
 			if (MASK)
 				gv = fmaf(xv, a, b) > 0.f ? gv : 0.f;
 			s1 += gv, s2 += gv * (xv - k);
@@ -179,12 +177,13 @@ __device__ __forceinline__ void bn_affine(const float scale, const float bias, c
 	b = bias - mean * a;
 }
 
-__global__ void bn_fwd_finalize_kernel(const float* __restrict__ x, const size_t shift_stride, const double* __restrict__ ws, const int C, const double count, const float epsilon, const float momentum, const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std, float* __restrict__ coef)
+template <typename T>
+__global__ void bn_fwd_finalize_kernel(const T* __restrict__ x, const size_t shift_stride, const double* __restrict__ ws, const int C, const double count, const float epsilon, const float momentum, const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std, float* __restrict__ coef)
 {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= C)
 		return;
-	const double k = (double)x[(size_t)c * shift_stride];
+	const double k = (double)ldf(x + (size_t)c * shift_stride);
 	const double s1 = ws[c], s2 = ws[C + c];
 	const double mean = k + s1 / count;
 	double var = (s2 - s1 * s1 / count) / count;
@@ -240,8 +239,8 @@ __global__ void bn_mask_coef_kernel(const int C, const float* __restrict__ scale
 // The same finalisation fed directly from the per-block partial rows of bn_reduce_kernel (one launch instead of partials-reduce +
 // finalize): 32 channels x 32 row-lanes per block; row-lane 0 of each channel finishes the statistics.
 // MODE 0 forward, MODE 1 backward; WITH_A (backward without a fused ReLU): also writes a = scale * inv_std for the apply pass.
-template <int MODE, int WITH_A>
-__global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float* __restrict__ part, const int gy, const float* __restrict__ x, const int C, const double count, const float epsilon, const float momentum,
+template <typename T, int MODE, int WITH_A>
+__global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float* __restrict__ part, const int gy, const T* __restrict__ x, const int C, const double count, const float epsilon, const float momentum,
 	const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ saved_mean, float* __restrict__ saved_inv_std,
 	float* __restrict__ dscale, float* __restrict__ dbias, float* __restrict__ coef)
 {
@@ -265,7 +264,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
 		s1 += sh[0][j][cx], s2 += sh[1][j][cx];
 	if (MODE == 0)
 	{
-		const double k = (double)x[c];
+		const double k = (double)ldf(x + c);
 		const double mean = k + s1 / count;
 		double var = (s2 - s1 * s1 / count) / count;
 		if (var < 0)
@@ -406,8 +405,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_ext_kernel(const float* __re
 // COLSUM (backward only): also leaves per-channel sums of the values written in `part` (rows of C floats; the caller guarantees
 // stride % CV == 0, so a thread stays on one channel group, and 256 % CV == 0 or CV % 256 == 0) -- the bias gradient of the
 // convolution that consumes dx, without another pass over dx.
-template <int BWD, int RELU, int COLSUM>
-__global__ void __launch_bounds__(256) bn_apply_vec_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, const float* __restrict__ coef, const size_t total4, const int C, float* __restrict__ part)
+template <typename T, int BWD, int RELU, int COLSUM>
+__global__ void __launch_bounds__(256) bn_apply_vec_kernel(const T* __restrict__ x, const T* __restrict__ g, T* __restrict__ out, const float* __restrict__ coef, const size_t total4, const int C, float* __restrict__ part)
 {
 	const int CV = C >> 2;
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -473,7 +472,7 @@ __global__ void __launch_bounds__(256) bn_apply_vec_kernel(const float* __restri
 	}
 }
 // out[c] = sum over rows of part[row][c] in a fixed order: 32 columns x 32 row-lanes per block
-__global__ void __launch_bounds__(1024) bn_colsum_rows_kernel(const float* __restrict__ part, const int rows, const int C, float* __restrict__ out)
+__global__ void __launch_bounds__(1024) bn_colsum_rows_kernel(const float* __restrict__ part, const int rows, const int C, void* __restrict__ out, const int out_kind)
 {
 	__shared__ float sh[32][33];
 	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
@@ -495,25 +494,25 @@ __global__ void __launch_bounds__(1024) bn_colsum_rows_kernel(const float* __res
 #pragma unroll
 		for (int j = 0; j < 32; j++)
 			t += sh[j][cx];
-		out[c] = t;
+		st_kind(out, c, t, out_kind);
 	}
 }
-template <int BWD, int RELU>
-__global__ void bn_apply_generic_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, const float* __restrict__ coef, const size_t total, const int C, const size_t inner)
+template <typename T, int BWD, int RELU>
+__global__ void bn_apply_generic_kernel(const T* __restrict__ x, const T* __restrict__ g, T* __restrict__ out, const float* __restrict__ coef, const size_t total, const int C, const size_t inner)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
 	{
 		const int c = (int)((i / inner) % C);
-		const float a = coef[c], b = coef[C + c], xv = x[i];
+		const float a = coef[c], b = coef[C + c], xv = ldf(x + i);
 		if (!BWD)
 		{
 			const float o = fmaf(xv, a, b);
-			out[i] = RELU ? fmaxf(o, 0.f) : o;
+			stf(out + i, RELU ? fmaxf(o, 0.f) : o);
 		} else {
-			float h = g[i];
+			float h = ldf(g + i);
 			if (RELU)
 				h = fmaf(xv, a, b) > 0.f ? h : 0.f;
-			out[i] = fmaf(a, h, fmaf(coef[2 * C + c], xv, coef[3 * C + c]));
+			stf(out + i, fmaf(a, h, fmaf(coef[2 * C + c], xv, coef[3 * C + c])));
 		}
 	}
 }
@@ -532,30 +531,31 @@ static void reduce_config(size_t rows, int CV, int& cpb, dim3& grid)
 	grid = dim3(gx, (unsigned)gy);
 }
 
-template <int MODE, int MASK>
-static int run_reduce(cudaStream_t s, const float* x, const float* g, const float* mean, const float* coef, size_t outer, int C, size_t inner, double* ws, float* part, int* part_rows)
+template <typename T, int MODE, int MASK>
+static int run_reduce(cudaStream_t s, const T* x, const T* g, const float* mean, const float* coef, size_t outer, int C, size_t inner, double* ws, float* part, int* part_rows)
 {
 	// NHWC vector path: leaves *part_rows > 0 rows of per-block partial sums in `part` (finished by bn_finalize_partials_kernel);
 	// generic path: one block per channel writes the sums to ws directly (*part_rows = 0)
-	if (inner == 1 && C % 4 == 0 && aligned16(x) && (MODE == 0 || aligned16(g)))
+	if (inner == 1 && C % 4 == 0 && aligned_v4(x) && (MODE == 0 || aligned_v4(g)))
 	{
 		int cpb;
 		dim3 grid;
 		reduce_config(outer, C / 4, cpb, grid);
-		bn_reduce_kernel<MODE, MASK><<<grid, 256, 0, s>>>(x, g, mean, coef, outer, C, part, cpb);
+		bn_reduce_kernel<T, MODE, MASK><<<grid, 256, 0, s>>>(x, g, mean, coef, outer, C, part, cpb);
 		*part_rows = (int)grid.y;
 		return check("bn_reduce");
 	}
 	*part_rows = 0;
-	bn_reduce_generic_kernel<MODE, MASK><<<C, 512, 0, s>>>(x, g, mean, coef, outer, C, inner, ws);
+	bn_reduce_generic_kernel<T, MODE, MASK><<<C, 512, 0, s>>>(x, g, mean, coef, outer, C, inner, ws);
 	return check("bn_reduce");
 }
 
-template <int BWD, int RELU>
-static int run_apply(cudaStream_t s, const float* x, const float* g, float* out, const float* coef, size_t outer, int C, size_t inner, float* part = 0, float* colsum_out = 0, int* colsum_done = 0)
+// colsum_out / colsum_kind: per-channel sums of the values written (backward only), stored in element kind colsum_kind
+template <typename T, int BWD, int RELU>
+static int run_apply(cudaStream_t s, const T* x, const T* g, T* out, const float* coef, size_t outer, int C, size_t inner, float* part = 0, void* colsum_out = 0, int colsum_kind = 0, int* colsum_done = 0)
 {
 	const size_t total = outer * C * inner;
-	if (inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(out) && (!BWD || aligned16(g)))
+	if (inner == 1 && C % 4 == 0 && aligned_v4(x) && aligned_v4(out) && (!BWD || aligned_v4(g)))
 	{
 		int grid = grid_for(total / 8, 256);
 		const int CV = C / 4;
@@ -563,21 +563,22 @@ static int run_apply(cudaStream_t s, const float* x, const float* g, float* out,
 		{
 			if (CV > 256) // the grid stride must be a multiple of CV
 				grid = (grid + CV / 256 - 1) / (CV / 256) * (CV / 256);
-			bn_apply_vec_kernel<BWD, RELU, 1><<<grid, 256, 0, s>>>(x, g, out, coef, total / 4, C, part);
+			bn_apply_vec_kernel<T, BWD, RELU, 1><<<grid, 256, 0, s>>>(x, g, out, coef, total / 4, C, part);
 			if (check("bn_apply"))
 				return -1;
 			const int rows = CV < 256 ? grid : (int)((size_t)grid * 256 / CV);
-			bn_colsum_rows_kernel<<<(C + 31) / 32, 1024, 0, s>>>(part, rows, C, colsum_out);
+			bn_colsum_rows_kernel<<<(C + 31) / 32, 1024, 0, s>>>(part, rows, C, colsum_out, colsum_kind);
 			*colsum_done = 1;
 			return check("bn_colsum_rows");
 		}
-		bn_apply_vec_kernel<BWD, RELU, 0><<<grid, 256, 0, s>>>(x, g, out, coef, total / 4, C, 0);
+		bn_apply_vec_kernel<T, BWD, RELU, 0><<<grid, 256, 0, s>>>(x, g, out, coef, total / 4, C, 0);
 	} else
-		bn_apply_generic_kernel<BWD, RELU><<<grid_for(total, 256), 256, 0, s>>>(x, g, out, coef, total, C, inner);
+		bn_apply_generic_kernel<T, BWD, RELU><<<grid_for(total, 256), 256, 0, s>>>(x, g, out, coef, total, C, inner);
 	return check("bn_apply");
 }
 
-int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu, const float* ext_part, int ext_rows)
+template <typename T>
+static int bn_fwd_train_t(cudaStream_t s, const T* x, T* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu, const float* ext_part, int ext_rows)
 {
 	if (outer * C * inner == 0)
 		return 0;
@@ -590,20 +591,21 @@ int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scal
 		bn_finalize_ext_kernel<<<(C + 31) / 32, 1024, 0, s>>>(ext_part, ext_rows, C, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, coef);
 		if (check("bn_fwd_finalize(ext)"))
 			return -1;
-		return fuse_relu ? run_apply<0, 1>(s, x, 0, y, coef, outer, C, inner) : run_apply<0, 0>(s, x, 0, y, coef, outer, C, inner);
+		return fuse_relu ? run_apply<T, 0, 1>(s, x, (const T*)0, y, coef, outer, C, inner) : run_apply<T, 0, 0>(s, x, (const T*)0, y, coef, outer, C, inner);
 	}
-	if (run_reduce<0, 0>(s, x, 0, 0, 0, outer, C, inner, ws, ws_part(workspace, C), &part_rows))
+	if (run_reduce<T, 0, 0>(s, x, (const T*)0, 0, 0, outer, C, inner, ws, ws_part(workspace, C), &part_rows))
 		return -1;
 	if (part_rows > 0)
-		bn_finalize_partials_kernel<0, 0><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, x, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, 0, 0, coef);
+		bn_finalize_partials_kernel<T, 0, 0><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, x, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, 0, 0, coef);
 	else
-		bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, inner, ws, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, coef);
+		bn_fwd_finalize_kernel<T><<<(C + 127) / 128, 128, 0, s>>>(x, inner, ws, C, (double)outer * (double)inner, epsilon, momentum, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, coef);
 	if (check("bn_fwd_finalize"))
 		return -1;
-	return fuse_relu ? run_apply<0, 1>(s, x, 0, y, coef, outer, C, inner) : run_apply<0, 0>(s, x, 0, y, coef, outer, C, inner);
+	return fuse_relu ? run_apply<T, 0, 1>(s, x, (const T*)0, y, coef, outer, C, inner) : run_apply<T, 0, 0>(s, x, (const T*)0, y, coef, outer, C, inner);
 }
 
-int bn_fwd_test_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, const float* mean, const float* var, size_t outer, int C, size_t inner, float epsilon, void* workspace)
+template <typename T>
+static int bn_fwd_test_t(cudaStream_t s, const T* x, T* y, const float* scale, const float* bias, const float* mean, const float* var, size_t outer, int C, size_t inner, float epsilon, void* workspace)
 {
 	if (outer * C * inner == 0)
 		return 0;
@@ -611,18 +613,19 @@ int bn_fwd_test_f32(cudaStream_t s, const float* x, float* y, const float* scale
 	bn_test_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, epsilon, scale, bias, mean, var, coef);
 	if (check("bn_test_coef"))
 		return -1;
-	return run_apply<0, 0>(s, x, 0, y, coef, outer, C, inner);
+	return run_apply<T, 0, 0>(s, x, (const T*)0, y, coef, outer, C, inner);
 }
 
 // bias != NULL selects the fused form: g is the gradient w.r.t. relu(bn(x)) and is masked by bn(x) > 0 on the fly
-int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, float* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace, float* dx_colsum)
+template <typename T>
+static int bn_bwd_t(cudaStream_t s, const T* g, const T* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, T* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace, void* dx_colsum, int colsum_kind)
 {
 	if (outer * C * inner == 0)
 		return 0;
 	double* ws = ws_sums(workspace);
 	float* coef = ws_coef(workspace, C);
 	const int mask = bias != 0;
-	const bool vec = inner == 1 && C % 4 == 0 && aligned16(x) && aligned16(g);
+	const bool vec = inner == 1 && C % 4 == 0 && aligned_v4(x) && aligned_v4(g);
 	if (mask)
 	{
 		bn_mask_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, scale, bias, saved_mean, saved_inv_std, coef);
@@ -635,13 +638,13 @@ int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scal
 			return -1;
 	}
 	int part_rows = 0;
-	if (mask ? run_reduce<1, 1>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C), &part_rows) : run_reduce<1, 0>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C), &part_rows))
+	if (mask ? run_reduce<T, 1, 1>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C), &part_rows) : run_reduce<T, 1, 0>(s, x, g, saved_mean, coef, outer, C, inner, ws, ws_part(workspace, C), &part_rows))
 		return -1;
 	const double count = (double)outer * (double)inner;
 	if (part_rows > 0 && mask)
-		bn_finalize_partials_kernel<1, 0><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, 0, C, count, 0.f, 0.f, scale, 0, 0, 0, const_cast<float*>(saved_mean), const_cast<float*>(saved_inv_std), dscale, dbias, coef);
+		bn_finalize_partials_kernel<T, 1, 0><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, (const T*)0, C, count, 0.f, 0.f, scale, 0, 0, 0, const_cast<float*>(saved_mean), const_cast<float*>(saved_inv_std), dscale, dbias, coef);
 	else if (part_rows > 0)
-		bn_finalize_partials_kernel<1, 1><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, 0, C, count, 0.f, 0.f, scale, 0, 0, 0, const_cast<float*>(saved_mean), const_cast<float*>(saved_inv_std), dscale, dbias, coef);
+		bn_finalize_partials_kernel<T, 1, 1><<<(C + 31) / 32, 1024, 0, s>>>(ws_part(workspace, C), part_rows, (const T*)0, C, count, 0.f, 0.f, scale, 0, 0, 0, const_cast<float*>(saved_mean), const_cast<float*>(saved_inv_std), dscale, dbias, coef);
 	else
 		bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(ws, C, (float)count, scale, saved_mean, saved_inv_std, dscale, dbias, coef);
 	if (check("bn_bwd_finalize"))
@@ -652,61 +655,98 @@ int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scal
 	// the partial rows reuse the reduce pass's partial area (its contents were consumed by the finalize kernel above)
 	int done = 0;
 	float* const part = dx_colsum ? ws_part(workspace, C) : 0;
-	if (mask ? run_apply<1, 1>(s, x, g, dx, coef, outer, C, inner, part, dx_colsum, &done) : run_apply<1, 0>(s, x, g, dx, coef, outer, C, inner, part, dx_colsum, &done))
+	if (mask ? run_apply<T, 1, 1>(s, x, g, dx, coef, outer, C, inner, part, dx_colsum, colsum_kind, &done) : run_apply<T, 1, 0>(s, x, g, dx, coef, outer, C, inner, part, dx_colsum, colsum_kind, &done))
 		return -1;
 	if (dx_colsum && !done) // layouts the vector path does not take: a separate column sum over dx
-		return colsum_f32(s, dx, outer * inner, C, C, dx_colsum, 0, 0);
+		return colsum_any(s, ElemKind<T>::value, dx, outer * inner, C, C, dx_colsum, colsum_kind, 0, 0);
 	return 0;
+}
+
+int bn_fwd_train_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu, const float* ext_part, int ext_rows)
+{
+	return bn_fwd_train_t<float>(s, x, y, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, outer, C, inner, epsilon, momentum, workspace, fuse_relu, ext_part, ext_rows);
+}
+int bn_fwd_test_f32(cudaStream_t s, const float* x, float* y, const float* scale, const float* bias, const float* mean, const float* var, size_t outer, int C, size_t inner, float epsilon, void* workspace)
+{
+	return bn_fwd_test_t<float>(s, x, y, scale, bias, mean, var, outer, C, inner, epsilon, workspace);
+}
+int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, float* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace, float* dx_colsum)
+{
+	return bn_bwd_t<float>(s, g, x, scale, bias, saved_mean, saved_inv_std, dx, dscale, dbias, outer, C, inner, workspace, dx_colsum, 0);
+}
+// 16-bit activations (kind 1 = bf16, 2 = fp16); scale / bias / statistics / parameter gradients stay fp32
+// (lib/nnc/ccv_cnnp_model_addons.c:954-956)
+int bn_fwd_train_16(cudaStream_t s, int kind, const void* x, void* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu, const float* ext_part, int ext_rows)
+{
+	if (kind == 1)
+		return bn_fwd_train_t<__nv_bfloat16>(s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, outer, C, inner, epsilon, momentum, workspace, fuse_relu, ext_part, ext_rows);
+	return bn_fwd_train_t<__half>(s, (const __half*)x, (__half*)y, scale, bias, running_mean, running_var, saved_mean, saved_inv_std, outer, C, inner, epsilon, momentum, workspace, fuse_relu, ext_part, ext_rows);
+}
+int bn_fwd_test_16(cudaStream_t s, int kind, const void* x, void* y, const float* scale, const float* bias, const float* mean, const float* var, size_t outer, int C, size_t inner, float epsilon, void* workspace)
+{
+	if (kind == 1)
+		return bn_fwd_test_t<__nv_bfloat16>(s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, scale, bias, mean, var, outer, C, inner, epsilon, workspace);
+	return bn_fwd_test_t<__half>(s, (const __half*)x, (__half*)y, scale, bias, mean, var, outer, C, inner, epsilon, workspace);
+}
+int bn_bwd_16(cudaStream_t s, int kind, const void* g, const void* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, void* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace, void* dx_colsum, int colsum_kind)
+{
+	if (kind == 1)
+		return bn_bwd_t<__nv_bfloat16>(s, (const __nv_bfloat16*)g, (const __nv_bfloat16*)x, scale, bias, saved_mean, saved_inv_std, (__nv_bfloat16*)dx, dscale, dbias, outer, C, inner, workspace, dx_colsum, colsum_kind);
+	return bn_bwd_t<__half>(s, (const __half*)g, (const __half*)x, scale, bias, saved_mean, saved_inv_std, (__half*)dx, dscale, dbias, outer, C, inner, workspace, dx_colsum, colsum_kind);
 }
 
 // ------------------------------------------------------------------------------------------------ fused residual adds
 // MODE 0: out = relu(a + b)                      (EWSUM then RELU_FORWARD at the end of a residual block)
 // MODE 1: out = y > 0 ? a + b : 0                (EWSUM of the two branch gradients then RELU_BACKWARD)
-template <int MODE>
-__global__ void __launch_bounds__(256) add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ y, float* __restrict__ out, const size_t n, const int vec)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) add_relu_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ y, T* __restrict__ out, const size_t n, const int vec)
 {
-	if (vec)
+	const size_t n4 = vec ? n >> 2 : 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
 	{
-		const size_t n4 = n >> 2;
-		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
-		{
-			const float4 u = ld4(a + i * 4), v = ld4(b + i * 4);
-			float4 o = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
-			if (MODE == 0)
-				o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-			else {
-				const float4 m = ld4(y + i * 4);
-				o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
-			}
-			st4(out + i * 4, o);
+		const float4 u = ld4(a + i * 4), v = ld4(b + i * 4);
+		float4 o = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+		if (MODE == 0)
+			o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+		else {
+			const float4 m = ld4(y + i * 4);
+			o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
 		}
-		for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-		{
-			const float o = a[i] + b[i];
-			out[i] = MODE == 0 ? fmaxf(o, 0.f) : (y[i] > 0.f ? o : 0.f);
-		}
-	} else
-		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-		{
-			const float o = a[i] + b[i];
-			out[i] = MODE == 0 ? fmaxf(o, 0.f) : (y[i] > 0.f ? o : 0.f);
-		}
+		st4(out + i * 4, o);
+	}
+	for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const float o = ldf(a + i) + ldf(b + i);
+		stf(out + i, MODE == 0 ? fmaxf(o, 0.f) : (ldf(y + i) > 0.f ? o : 0.f));
+	}
 }
-int ew_add_relu_fwd_f32(cudaStream_t s, const float* a, const float* b, float* out, size_t n)
+template <typename T>
+static int add_relu_fwd_t(cudaStream_t s, const T* a, const T* b, T* out, size_t n)
 {
 	if (n == 0)
 		return 0;
-	const int vec = aligned16(a) && aligned16(b) && aligned16(out);
-	add_relu_kernel<0><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, 0, out, n, vec);
+	const int vec = aligned_v4(a) && aligned_v4(b) && aligned_v4(out);
+	add_relu_kernel<T, 0><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, (const T*)0, out, n, vec);
 	return check("add_relu_fwd");
 }
-int ew_add_relu_bwd_f32(cudaStream_t s, const float* a, const float* b, const float* y, float* out, size_t n)
+template <typename T>
+static int add_relu_bwd_t(cudaStream_t s, const T* a, const T* b, const T* y, T* out, size_t n)
 {
 	if (n == 0)
 		return 0;
-	const int vec = aligned16(a) && aligned16(b) && aligned16(out) && aligned16(y);
-	add_relu_kernel<1><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, y, out, n, vec);
+	const int vec = aligned_v4(a) && aligned_v4(b) && aligned_v4(out) && aligned_v4(y);
+	add_relu_kernel<T, 1><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, y, out, n, vec);
 	return check("add_relu_bwd");
+}
+int ew_add_relu_fwd_f32(cudaStream_t s, const float* a, const float* b, float* out, size_t n) { return add_relu_fwd_t<float>(s, a, b, out, n); }
+int ew_add_relu_bwd_f32(cudaStream_t s, const float* a, const float* b, const float* y, float* out, size_t n) { return add_relu_bwd_t<float>(s, a, b, y, out, n); }
+int ew_add_relu_fwd_16(cudaStream_t s, int kind, const void* a, const void* b, void* out, size_t n)
+{
+	return kind == 1 ? add_relu_fwd_t<__nv_bfloat16>(s, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n) : add_relu_fwd_t<__half>(s, (const __half*)a, (const __half*)b, (__half*)out, n);
+}
+int ew_add_relu_bwd_16(cudaStream_t s, int kind, const void* a, const void* b, const void* y, void* out, size_t n)
+{
+	return kind == 1 ? add_relu_bwd_t<__nv_bfloat16>(s, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)y, (__nv_bfloat16*)out, n) : add_relu_bwd_t<__half>(s, (const __half*)a, (const __half*)b, (const __half*)y, (__half*)out, n);
 }
 
 } // namespace sm100

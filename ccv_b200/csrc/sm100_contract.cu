@@ -5,6 +5,7 @@
 #include "sm100_contract.h"
 #include "sm100_umma_persistent.cuh"
 #include "sm100_umma_wgrad.cuh"
+#include "sm100_elem.cuh"
 #include <atomic>
 #include <mutex>
 #include <stdio.h>
@@ -80,6 +81,44 @@ static bool make_map_2d(CUtensorMap* map, const float* ptr, long long rows, long
 	return r == CUDA_SUCCESS;
 }
 
+// 16-bit (bf16 / fp16) 2-D row-major [rows, cols], row pitch `ld` elements; box = {box_cols (<= 64 = one 128-byte span), box_rows}.
+// kind: 1 = bf16, 2 = fp16.  MN-major 16-bit operands use the ordinary 128-byte swizzle (64-element atoms).  swizzle64: the
+// 32 x 32 output chunks of the TMA-store epilogue (64-byte rows).
+static bool make_map_2d16(CUtensorMap* map, const void* ptr, int kind, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool swizzle64 = false)
+{
+	if ((((uintptr_t)ptr) & 15) || ((ld * 2) & 15) || ld * 2 >= (1ll << 40))
+		return false;
+	cuuint64_t dims[2] = { (cuuint64_t)cols, (cuuint64_t)rows };
+	cuuint64_t strides[1] = { (cuuint64_t)ld * 2 };
+	cuuint32_t box[2] = { (cuuint32_t)box_cols, (cuuint32_t)box_rows };
+	cuuint32_t estr[2] = { 1, 1 };
+	const CUresult r = g_encode_tiled(map, kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS;
+}
+// 16-bit NHWC tensor {C, W, H, N} in im2col mode (element strides sn, sh, sw; channel stride 1)
+static bool make_map_im2col16(CUtensorMap* map, const void* ptr, int kind, int N, int H, int W, int C, long long sn, long long sh, long long sw, int lower_h, int lower_w, int upper_h, int upper_w, int trav_h, int trav_w, int channels, int pixels)
+{
+	if ((((uintptr_t)ptr) & 15) || ((sw * 2) & 15) || ((sh * 2) & 15) || ((sn * 2) & 15))
+		return false;
+	if (lower_h < -128 || lower_h > 127 || lower_w < -128 || lower_w > 127 || upper_h < -128 || upper_h > 127 || upper_w < -128 || upper_w > 127)
+		return false;
+	if (trav_h < 1 || trav_h > 8 || trav_w < 1 || trav_w > 8)
+		return false;
+	cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N };
+	cuuint64_t strides[3] = { (cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2 };
+	int lower[2] = { lower_w, lower_h };
+	int upper[2] = { upper_w, upper_h };
+	cuuint32_t estr[4] = { 1, (cuuint32_t)trav_w, (cuuint32_t)trav_h, 1 };
+	const CUresult r = g_encode_im2col(map, kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)ptr, dims, strides, lower, upper, (cuuint32_t)channels, (cuuint32_t)pixels, estr,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS)
+		return false;
+	if (g_driver_version <= 13010 && (long long)N * sn * 2 < 131072) // same driver workaround as make_map_im2col
+		reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+	return true;
+}
+
 // fp32 NHWC tensor {C, W, H, N} in im2col mode. Base pixels run over [lower, dim + upper) per spatial axis with the
 // given traversal stride; each load fetches `pixels` base pixels x `channels` channels at base + tap offset.
 static bool make_map_im2col(CUtensorMap* map, const float* ptr, int N, int H, int W, int C, long long sn, long long sh, long long sw, int lower_h, int lower_w, int upper_h, int upper_w, int trav_h, int trav_w, int channels, int pixels, bool mn_major = false, int dtype = -1)
@@ -147,6 +186,21 @@ static int ensure_dynamic_smem(Kern kern, int bytes, bool (&done)[MAX_DEVICES], 
 // ------------------------------------------------------------------------------------------------ ordered split-K combine
 // out[r, c] = (accumulate ? out[r, c] : 0) + part[0][r, c] + part[1][r, c] + ... in that order: the deterministic second half of
 // every split-K launch (the contraction kernels write one scratch slice per split with plain stores).
+// 16-bit outputs (out_kind 1 = bf16, 2 = fp16): out16 replaces out, the sum is rounded once at the end
+__global__ void __launch_bounds__(256) splitk_reduce16_kernel(const float* __restrict__ part, const int splits, const long long split_stride, const int rows, const int cols, const long long ldp, uint16_t* __restrict__ out, const long long ldo, const int accumulate, const int out_kind)
+{
+	const long long total = (long long)rows * cols;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+	{
+		const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+		const float* src = part + (long long)r * ldp + c;
+		uint16_t* const dst = out + (long long)r * ldo + c;
+		float acc = accumulate ? cvt16(*dst, out_kind) : 0.f;
+		for (int k = 0; k < splits; k++, src += split_stride)
+			acc += *src;
+		*dst = (uint16_t)(pack16x2(acc, 0.f, out_kind) & 0xffffu);
+	}
+}
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, const int splits, const long long split_stride, const int rows, const int cols, const long long ldp, float* __restrict__ out, const long long ldo, const int accumulate, const int vec)
 {
 	if (vec)
@@ -187,8 +241,23 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 		}
 	}
 }
-static int splitk_reduce(cudaStream_t stream, const float* part, int splits, long long split_stride, int rows, int cols, long long ldp, float* out, long long ldo, int accumulate)
+static int splitk_reduce(cudaStream_t stream, const float* part, int splits, long long split_stride, int rows, int cols, long long ldp, float* out, long long ldo, int accumulate, int out_kind = 0)
 {
+	if (out_kind)
+	{
+		long long blocks = ((long long)rows * cols + 255) / 256;
+		if (blocks > (long long)num_sms() * 8)
+			blocks = (long long)num_sms() * 8;
+		splitk_reduce16_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(part, splits, split_stride, rows, cols, ldp, (uint16_t*)out, ldo, accumulate, out_kind);
+		count_launch();
+		const cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+		{
+			set_last_error("splitk_reduce16_kernel", e);
+			return -1;
+		}
+		return 0;
+	}
 	const int vec = cols % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0 && split_stride % 4 == 0 && ((((uintptr_t)part) | ((uintptr_t)out)) & 15) == 0;
 	const long long work = (long long)rows * (vec ? cols / 4 : cols);
 	long long blocks = (work + 255) / 256;
@@ -256,11 +325,11 @@ static int launch_umma(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 	return 0;
 }
 
-template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0>
+template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0, int OUT16 = 0>
 static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p)
 {
 	using S = UmmaPersistentSmem<BN, STAGES, EPIW, X3>;
-	auto kern = umma_gemm_persistent_kernel<AMODE, BMODE, BN, STAGES, EPIW, X3>;
+	auto kern = umma_gemm_persistent_kernel<AMODE, BMODE, BN, STAGES, EPIW, X3, OUT16>;
 	static bool configured[MAX_DEVICES];
 	if (ensure_dynamic_smem(kern, S::TOTAL, configured, "cudaFuncSetAttribute(umma_gemm_persistent_kernel)"))
 		return -1;
@@ -282,9 +351,13 @@ static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, c
 		tma_store_enabled = e ? atoi(e) : 1;
 	}
 	q.tma_store = 0;
-	if (tma_store_enabled && p.splits == 1 && p.grid_taps == 1 && !p.accumulate && p.rowmap.mode == 0 && p.N % 4 == 0 && (!p.bias || (((uintptr_t)p.bias) & 15) == 0) &&
-		make_map_2d(&tmC, p.out, p.M, p.N, p.rowmap.ld, 32, 32, false, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
-		q.tma_store = 1;
+	if (tma_store_enabled && p.splits == 1 && p.grid_taps == 1 && !p.accumulate && p.rowmap.mode == 0 && (!p.bias || (((uintptr_t)p.bias) & 15) == 0))
+	{
+		if (!OUT16 && p.N % 4 == 0 && make_map_2d(&tmC, p.out, p.M, p.N, p.rowmap.ld, 32, 32, false, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
+			q.tma_store = 1;
+		if (OUT16 && p.N % 8 == 0 && (!p.bias16 || (((uintptr_t)p.bias16) & 15) == 0) && make_map_2d16(&tmC, p.out, p.out_kind, p.M, p.N, p.rowmap.ld, 32, 32, true))
+			q.tma_store = 1;
+	}
 	if (t_stats_request.part)
 	{
 		const StatsRequest r = t_stats_request;
@@ -402,6 +475,7 @@ static void init_params(UmmaGemmParams& p)
 		layout = (e = getenv("CCV_NNC_SM100_MN_LAYOUT")) ? atoi(e) : 1;
 	}
 	p.mn_lbo = lbo, p.mn_sbo = sbo, p.mn_layout = layout;
+	p.kind16 = 0, p.bk = UMMA_BLOCK_K, p.mn_box_bytes = 4096, p.mn_step = 1024, p.out_kind = 0, p.bias16 = 0;
 }
 
 static int pick_splits(long long tiles, int k_iters, int min_iters_per_split)
@@ -459,82 +533,144 @@ static int pick_splits(long long tiles, int k_iters, int min_iters_per_split)
 
 // launches the kernel family for (AMODE, BMODE); when p.splits > 1 the partial tiles land in scratch slices [rows, cols] (pitch
 // ldp) that are then added into `out` in split order
+// ------------------------------------------------------------------------------------------------ element kinds
+// Every contraction below exists for three element kinds: 0 = fp32 (kind::tf32 or 3xTF32), 1 = bf16, 2 = fp16 (kind::f16, fp32
+// accumulate).  The kind only changes how many elements a 128-byte operand row holds, the tensor-map data type, the
+// instruction / MN-major descriptors and the epilogue's output conversion; tiling, split-K and the launch logic are shared.
+static inline int kind_bk(int kind) { return kind ? 64 : UMMA_BLOCK_K; }
+static inline size_t kind_esz(int kind) { return kind ? 2 : 4; }
+static inline int kind_align(int kind) { return kind ? 8 : 4; } // elements per 16 bytes: what TMA asks of every stride
+// 2-D row-major [rows, cols] (pitch ld): box = one 128-byte span of columns x box_rows
+static bool map_2d(CUtensorMap* map, int kind, const void* ptr, long long rows, long long cols, long long ld, int box_rows, bool mn_major)
+{
+	if (kind == 0)
+		return make_map_2d(map, (const float*)ptr, rows, cols, ld, 32, box_rows, mn_major);
+	return make_map_2d16(map, ptr, kind, rows, cols, ld, 64, box_rows);
+}
+static bool map_im2col(CUtensorMap* map, int kind, const void* ptr, int N, int H, int W, int C, long long sn, long long sh, long long sw, int lower_h, int lower_w, int upper_h, int upper_w, int trav_h, int trav_w, int pixels, bool mn_major)
+{
+	if (kind == 0)
+		return make_map_im2col(map, (const float*)ptr, N, H, W, C, sn, sh, sw, lower_h, lower_w, upper_h, upper_w, trav_h, trav_w, 32, pixels, mn_major);
+	return make_map_im2col16(map, ptr, kind, N, H, W, C, sn, sh, sw, lower_h, lower_w, upper_h, upper_w, trav_h, trav_w, 64, pixels);
+}
+static void init_params_kind(UmmaGemmParams& p, int kind)
+{
+	init_params(p);
+	if (kind)
+	{
+		// 16-bit MN-major operands: ordinary 128-byte swizzle, 64-element atoms; boxes of 64 k-rows x 128 B; K = 16 per MMA
+		p.kind16 = 1, p.bk = 64, p.mn_box_bytes = 64 * 128, p.mn_step = 16 * 128;
+		p.mn_lbo = 64 * 128, p.mn_sbo = 1024, p.mn_layout = 2;
+		p.out_kind = kind;
+	}
+}
+static inline uint32_t idesc_kind(int kind, int a_mn_major, int b_mn_major, int bn)
+{
+	return umma_instr_desc(kind == 0 ? 2 : (kind == 1 ? 1 : 0), a_mn_major, b_mn_major, UMMA_BLOCK_M, bn);
+}
+// kernel choice per kind: fp32 goes through the measured table of launch_umma_bn; 16-bit always takes the persistent kernel with
+// eight epilogue warps (the MMAs are twice as fast, the epilogue is the critical path); out16 = the output tensor is 16-bit
+// (false for split-K slices, which stay fp32)
 template <int AMODE, int BMODE>
-static int launch_umma_split(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaGemmParams& p, int bn, const Scratch& scratch, int rows, int cols, long long ldo, int accumulate)
+static int launch_kind(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p, int bn, int kind, bool out16)
+{
+	if (kind == 0)
+		return launch_umma_bn<AMODE, BMODE>(stream, tmA, tmB, p, bn);
+	if (out16)
+	{
+		if (bn == 64)
+			return launch_umma_persistent<AMODE, BMODE, 64, 6, 8, 0, 1>(stream, tmA, tmB, p);
+		if (bn == 256)
+			return launch_umma_persistent<AMODE, BMODE, 256, 3, 8, 0, 1>(stream, tmA, tmB, p);
+		return launch_umma_persistent<AMODE, BMODE, 128, 5, 8, 0, 1>(stream, tmA, tmB, p);
+	}
+	if (bn == 64)
+		return launch_umma_persistent<AMODE, BMODE, 64, 6, 8>(stream, tmA, tmB, p);
+	if (bn == 256)
+		return launch_umma_persistent<AMODE, BMODE, 256, 3, 8>(stream, tmA, tmB, p);
+	return launch_umma_persistent<AMODE, BMODE, 128, 5, 8>(stream, tmA, tmB, p);
+}
+
+// Launch with the split factor already chosen in p.splits.  One split: straight into `out` (pitch ldo, element kind `kind`).
+// Several: fp32 slices [rows, ldp] in the scratch, one per split, then the ordered combine into `out` (which also applies
+// CCV_NNC_ACCUMULATE_OUTPUT and rounds once for 16-bit outputs).
+template <int AMODE, int BMODE>
+static int launch_umma_split(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaGemmParams& p, int bn, int kind, const Scratch& scratch, int rows, int cols, void* out, long long ldo, int accumulate)
 {
 	if (p.splits <= 1)
 	{
 		p.splits = 1, p.split_out_stride = 0, p.accumulate = accumulate;
-		return launch_umma_bn<AMODE, BMODE>(stream, tmA, tmB, p, bn);
+		p.out = (float*)out;
+		return launch_kind<AMODE, BMODE>(stream, tmA, tmB, p, bn, kind, kind != 0);
 	}
-	float* const out = p.out;
+	// slices are dense [rows, cols] tiles of pitch cols rounded up to 4 floats (for a filter gradient cols = R * S * C is already
+	// a multiple of 4, so a slice has dW's own layout and tap-as-grid-dimension launches address it unchanged)
+	const long long slice_ld = ((long long)cols + 3) & ~3ll;
 	p.out = (float*)scratch.ptr;
-	p.rowmap.mode = 0, p.rowmap.ld = ldo; // slices have the layout of the output itself (same pitch), packed one after the other
-	p.split_out_stride = (long long)rows * ldo;
+	p.rowmap.mode = 0, p.rowmap.ld = slice_ld;
+	p.split_out_stride = (long long)rows * slice_ld;
 	p.accumulate = 0;
-	const int rc = launch_umma_bn<AMODE, BMODE>(stream, tmA, tmB, p, bn);
+	p.bias16 = 0; // a 16-bit bias is only read by the 16-bit epilogue: callers do not split when they pass one
+	const int rc = launch_kind<AMODE, BMODE>(stream, tmA, tmB, p, bn, kind, false);
 	if (rc)
 		return rc;
-	return splitk_reduce(stream, (const float*)scratch.ptr, p.splits, p.split_out_stride, rows, cols, ldo, out, ldo, accumulate);
+	return splitk_reduce(stream, (const float*)scratch.ptr, p.splits, p.split_out_stride, rows, cols, slice_ld, (float*)out, ldo, accumulate, kind);
+}
+static inline size_t slice_bytes(long long rows, long long cols)
+{
+	return (size_t)rows * (size_t)((cols + 3) & ~3ll) * sizeof(float);
 }
 
-int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long long lda, int trans_a, const float* b, long long ldb, int trans_b, float* c, long long ldc, const float* bias, int accumulate, const Scratch& scratch, int x3)
+// C[M, N] (+)= op(A) * op(B) + bias for element kind `kind` (bias: fp32 `bias`, or for 16-bit kinds `bias16` in the element type)
+static int gemm_any(cudaStream_t stream, int kind, int M, int N, int K, const void* a, long long lda, int trans_a, const void* b, long long ldb, int trans_b, void* c, long long ldc, const float* bias, const void* bias16, int accumulate, const Scratch& scratch, int x3)
 {
-	const X3Scope math(x3);
+	const X3Scope math(kind == 0 ? x3 : 0);
 	if (!tma_api_init() || M <= 0 || N <= 0 || K <= 0)
 		return 1;
-	const int bn = pick_bn(N);
+	const int bn = pick_bn(N), bk = kind_bk(kind);
 	CUtensorMap tmA, tmB;
 	bool ok;
 	if (!trans_a)
-		ok = make_map_2d(&tmA, a, M, K, lda, 32, UMMA_BLOCK_M);
+		ok = map_2d(&tmA, kind, a, M, K, lda, UMMA_BLOCK_M, false);
 	else
-		ok = make_map_2d(&tmA, a, K, M, lda, 32, UMMA_BLOCK_K, true);
+		ok = map_2d(&tmA, kind, a, K, M, lda, bk, true);
 	if (!ok)
 		return 1;
 	if (trans_b) // stored [N, K]: K-major
-		ok = make_map_2d(&tmB, b, N, K, ldb, 32, bn);
+		ok = map_2d(&tmB, kind, b, N, K, ldb, bn, false);
 	else // stored [K, N]: N contiguous
-		ok = make_map_2d(&tmB, b, K, N, ldb, 32, UMMA_BLOCK_K, true);
+		ok = map_2d(&tmB, kind, b, K, N, ldb, bk, true);
 	if (!ok)
 		return 1;
+	if (kind && ((ldc * 2) & 7)) // 16-bit rows are written 8 bytes at a time at least
+		return 1;
 	UmmaGemmParams p;
-	init_params(p);
+	init_params_kind(p, kind);
 	p.M = M, p.N = N;
-	p.k_iters = (K + UMMA_BLOCK_K - 1) / UMMA_BLOCK_K;
+	p.k_iters = (K + bk - 1) / bk;
 	p.chunks_per_tap = p.k_iters;
-	p.out = c, p.bias = bias;
+	p.bias = bias, p.bias16 = bias ? 0 : bias16;
 	p.rowmap.mode = 0, p.rowmap.ld = ldc;
-	p.idesc = umma_instr_desc(2, trans_a, !trans_b, UMMA_BLOCK_M, bn);
+	p.idesc = idesc_kind(kind, trans_a, !trans_b, bn);
 	const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn);
-	// split-K slices are dense [M, Np] tiles in the scratch (pitch Np = N rounded up to 4 floats)
-	const long long ldp = ((long long)N + 3) & ~3ll;
-	p.splits = fit_splits(pick_splits(tiles, p.k_iters, 8), p.k_iters, (size_t)M * ldp * sizeof(float), scratch);
-	if (p.splits > 1)
-	{
-		float* const part = (float*)scratch.ptr;
-		p.out = part, p.rowmap.ld = ldp, p.split_out_stride = (long long)M * ldp, p.accumulate = 0;
-		int rc;
-		if (!trans_a && trans_b)
-			rc = launch_umma_bn<OP_K2D, OP_K2D>(stream, tmA, tmB, p, bn);
-		else if (!trans_a && !trans_b)
-			rc = launch_umma_bn<OP_K2D, OP_MN2D>(stream, tmA, tmB, p, bn);
-		else if (trans_a && trans_b)
-			rc = launch_umma_bn<OP_MN2D, OP_K2D>(stream, tmA, tmB, p, bn);
-		else
-			rc = launch_umma_bn<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn);
-		if (rc)
-			return rc;
-		return splitk_reduce(stream, part, p.splits, p.split_out_stride, M, N, ldp, c, ldc, accumulate);
-	}
-	p.accumulate = accumulate;
+	p.splits = p.bias16 ? 1 : fit_splits(pick_splits(tiles, p.k_iters, 8), p.k_iters, slice_bytes(M, N), scratch);
 	if (!trans_a && trans_b)
-		return launch_umma_bn<OP_K2D, OP_K2D>(stream, tmA, tmB, p, bn);
+		return launch_umma_split<OP_K2D, OP_K2D>(stream, tmA, tmB, p, bn, kind, scratch, M, N, c, ldc, accumulate);
 	if (!trans_a && !trans_b)
-		return launch_umma_bn<OP_K2D, OP_MN2D>(stream, tmA, tmB, p, bn);
+		return launch_umma_split<OP_K2D, OP_MN2D>(stream, tmA, tmB, p, bn, kind, scratch, M, N, c, ldc, accumulate);
 	if (trans_a && trans_b)
-		return launch_umma_bn<OP_MN2D, OP_K2D>(stream, tmA, tmB, p, bn);
-	return launch_umma_bn<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn);
+		return launch_umma_split<OP_MN2D, OP_K2D>(stream, tmA, tmB, p, bn, kind, scratch, M, N, c, ldc, accumulate);
+	return launch_umma_split<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn, kind, scratch, M, N, c, ldc, accumulate);
+}
+int gemm_tf32(cudaStream_t stream, int M, int N, int K, const float* a, long long lda, int trans_a, const float* b, long long ldb, int trans_b, float* c, long long ldc, const float* bias, int accumulate, const Scratch& scratch, int x3)
+{
+	return gemm_any(stream, 0, M, N, K, a, lda, trans_a, b, ldb, trans_b, c, ldc, bias, 0, accumulate, scratch, x3);
+}
+int gemm_16(cudaStream_t stream, int kind, int M, int N, int K, const void* a, long long lda, int trans_a, const void* b, long long ldb, int trans_b, void* c, long long ldc, const float* bias32, const void* bias16, int accumulate, const Scratch& scratch)
+{
+	if (kind != 1 && kind != 2)
+		return 1;
+	return gemm_any(stream, kind, M, N, K, a, lda, trans_a, b, ldb, trans_b, c, ldc, bias32, bias16, accumulate, scratch, 0);
 }
 
 static bool conv_is_pointwise(const ConvGeom& g)
@@ -560,27 +696,29 @@ static bool conv_shape_consistent(const ConvGeom& g)
 		g.R * g.S <= UMMA_MAX_TAPS && g.C % 4 == 0 && g.K % 4 == 0;
 }
 
-int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, const Scratch& scratch, int x3)
+static int conv_fprop_any(cudaStream_t stream, int kind, const ConvGeom& g, const void* a, const void* w, const float* bias, const void* bias16, void* b, const Scratch& scratch, int x3)
 {
-	const X3Scope math(x3);
-	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g))
+	const X3Scope math(kind == 0 ? x3 : 0);
+	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g) || g.C % kind_align(kind) || g.K % kind_align(kind))
 		return 1;
 	const long long M = (long long)g.N * g.P * g.Q;
 	if (M > 0x7fffffffll)
 		return 1;
 	if (conv_is_pointwise(g)) // a plain [NHW, C] x [K, C]^T GEMM
-		return gemm_tf32(stream, (int)M, g.K, g.C, a, g.C, 0, w, g.C, 1, b, g.K, bias, 0, scratch, x3);
-	const int bn = pick_bn(g.K);
+		return gemm_any(stream, kind, (int)M, g.K, g.C, a, g.C, 0, w, g.C, 1, b, g.K, bias, bias16, 0, scratch, x3);
+	const int bn = pick_bn(g.K), bk = kind_bk(kind);
 	CUtensorMap tmA, tmB;
-	if (!make_map_im2col(&tmA, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, 32, UMMA_BLOCK_M))
+	if (!map_im2col(&tmA, kind, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, UMMA_BLOCK_M, false))
 		return 1;
 	const long long rsc = (long long)g.R * g.S * g.C;
-	if (!make_map_2d(&tmB, w, g.K, rsc, rsc, 32, bn))
+	if (!map_2d(&tmB, kind, w, g.K, rsc, rsc, bn, false))
 		return 1;
 	UmmaGemmParams p;
-	init_params(p);
+	init_params_kind(p, kind);
 	p.M = (int)M, p.N = g.K;
-	p.chunks_per_tap = (g.C + 31) / 32;
+	// a tap's channels are walked in spans of bk; a last span that runs past C reads zeros from the input (TMA bounds) and the
+	// next tap's filter columns from w, whose products with those zeros vanish
+	p.chunks_per_tap = (g.C + bk - 1) / bk;
 	p.k_iters = g.R * g.S * p.chunks_per_tap;
 	p.P = g.P, p.Q = g.Q;
 	p.stride_h = g.stride_h, p.stride_w = g.stride_w;
@@ -593,23 +731,32 @@ int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, cons
 			p.tap_off_w[t] = (unsigned short)(s * g.dil_w);
 			p.tap_b_col[t] = t * g.C;
 		}
-	p.out = b, p.bias = bias;
+	p.out = (float*)b, p.bias = bias, p.bias16 = bias ? 0 : bias16;
 	p.rowmap.mode = 0, p.rowmap.ld = g.K;
-	p.idesc = umma_instr_desc(2, 0, 0, UMMA_BLOCK_M, bn);
-	return launch_umma_bn<OP_IM2COL, OP_K2D>(stream, tmA, tmB, p, bn);
+	p.idesc = idesc_kind(kind, 0, 0, bn);
+	return launch_kind<OP_IM2COL, OP_K2D>(stream, tmA, tmB, p, bn, kind, kind != 0);
+}
+int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, const Scratch& scratch, int x3)
+{
+	return conv_fprop_any(stream, 0, g, a, w, bias, 0, b, scratch, x3);
+}
+int conv_fprop_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* a, const void* w, const float* bias32, const void* bias16, void* b, const Scratch& scratch)
+{
+	return kind == 1 || kind == 2 ? conv_fprop_any(stream, kind, g, a, w, bias32, bias16, b, scratch, 0) : 1;
 }
 
-int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a, const Scratch& scratch, int x3)
+static int conv_dgrad_any(cudaStream_t stream, int kind, const ConvGeom& g, const void* grad_b, const void* w, void* grad_a, const Scratch& scratch, int x3)
 {
-	const X3Scope math(x3);
-	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g) || !conv_in_contiguous(g))
+	const X3Scope math(kind == 0 ? x3 : 0);
+	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g) || !conv_in_contiguous(g) || g.C % kind_align(kind) || g.K % kind_align(kind))
 		return 1;
 	if (conv_is_pointwise(g)) // dA[NHW, C] = dB[NHW, K] x W[K, C]
-		return gemm_tf32(stream, g.N * g.H * g.W, g.C, g.K, grad_b, g.K, 0, w, g.C, 0, grad_a, g.C, 0, 0, scratch, x3);
-	const int bn = pick_bn(g.C);
+		return gemm_any(stream, kind, g.N * g.H * g.W, g.C, g.K, grad_b, g.K, 0, w, g.C, 0, grad_a, g.C, 0, 0, 0, scratch, x3);
+	const int bn = pick_bn(g.C), bk = kind_bk(kind);
+	const size_t esz = kind_esz(kind);
 	const long long rsc = (long long)g.R * g.S * g.C;
 	CUtensorMap tmB;
-	if (!make_map_2d(&tmB, w, g.K, rsc, rsc, 32, UMMA_BLOCK_K, true))
+	if (!map_2d(&tmB, kind, w, g.K, rsc, rsc, bk, true))
 		return 1;
 	// Decompose by output-pixel residue class (ah, aw) modulo the stride: within a class, pixel h = i * stride + ah
 	// receives from filter row r iff (ah + pad - r * dil) % stride == 0, reading grad_b row i + (ah + pad - r * dil) / stride.
@@ -646,7 +793,7 @@ int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 		}
 	if (need_zero)
 	{
-		cudaError_t e = cudaMemsetAsync(grad_a, 0, (size_t)g.N * g.H * g.W * g.C * 4, stream);
+		cudaError_t e = cudaMemsetAsync(grad_a, 0, (size_t)g.N * g.H * g.W * g.C * esz, stream);
 		if (e != cudaSuccess)
 		{
 			set_last_error("memset(dgrad)", e);
@@ -686,12 +833,12 @@ int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 				continue;
 			CUtensorMap tmA;
 			// base pixels i in [0, Hc) map to grad_b rows i + lo_h + offset: bounding box [lo_h, P + (Hc - P + lo_h))
-			if (!make_map_im2col(&tmA, grad_b, g.N, g.P, g.Q, g.K, g.bn, g.bh, g.bw, lo_h, lo_w, Hc - g.P + lo_h, Wc - g.Q + lo_w, 1, 1, 32, UMMA_BLOCK_M))
+			if (!map_im2col(&tmA, kind, grad_b, g.N, g.P, g.Q, g.K, g.bn, g.bh, g.bw, lo_h, lo_w, Hc - g.P + lo_h, Wc - g.Q + lo_w, 1, 1, UMMA_BLOCK_M, false))
 				return 1;
 			UmmaGemmParams p;
-			init_params(p);
+			init_params_kind(p, kind);
 			p.M = g.N * Hc * Wc, p.N = g.C;
-			p.chunks_per_tap = (g.K + 31) / 32;
+			p.chunks_per_tap = (g.K + bk - 1) / bk;
 			p.k_iters = cp.ntaps_h * cp.ntaps_w * p.chunks_per_tap;
 			p.P = Hc, p.Q = Wc;
 			p.base_h = lo_h, p.base_w = lo_w;
@@ -703,18 +850,26 @@ int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 					p.tap_off_w[t] = (unsigned short)(cp.e_w[j] - lo_w);
 					p.tap_b_col[t] = (cp.r_h[i] * g.S + cp.s_w[j]) * g.C;
 				}
-			p.out = grad_a + ((long long)ah * g.W + aw) * g.C;
+			p.out = (float*)((char*)grad_a + ((long long)ah * g.W + aw) * g.C * esz);
 			p.rowmap.mode = 1;
 			p.rowmap.Pc = Hc, p.rowmap.Qc = Wc;
 			p.rowmap.n_stride = (long long)g.H * g.W * g.C;
 			p.rowmap.h_stride = (long long)g.stride_h * g.W * g.C;
 			p.rowmap.w_stride = (long long)g.stride_w * g.C;
-			p.idesc = umma_instr_desc(2, 0, 1, UMMA_BLOCK_M, bn);
-			const int rc = launch_umma_bn<OP_IM2COL, OP_MN2D>(stream, tmA, tmB, p, bn);
+			p.idesc = idesc_kind(kind, 0, 1, bn);
+			const int rc = launch_kind<OP_IM2COL, OP_MN2D>(stream, tmA, tmB, p, bn, kind, kind != 0);
 			if (rc)
 				return rc;
 		}
 	return 0;
+}
+int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a, const Scratch& scratch, int x3)
+{
+	return conv_dgrad_any(stream, 0, g, grad_b, w, grad_a, scratch, x3);
+}
+int conv_dgrad_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* grad_b, const void* w, void* grad_a, const Scratch& scratch)
+{
+	return kind == 1 || kind == 2 ? conv_dgrad_any(stream, kind, g, grad_b, w, grad_a, scratch, 0) : 1;
 }
 
 // Filter gradient with few filters (K <= 64): taps packed along the UMMA M dimension (sm100_umma_wgrad.cuh).
@@ -749,11 +904,12 @@ static bool wgrad_taps_enabled()
 	return v != 0;
 }
 
-int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, const Scratch& scratch, int x3)
+static int conv_wgrad_any(cudaStream_t stream, int kind, const ConvGeom& g, const void* grad_b, const void* a, void* grad_w, int accumulate, const Scratch& scratch, int x3)
 {
-	const X3Scope math(x3);
-	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g))
+	const X3Scope math(kind == 0 ? x3 : 0);
+	if (!tma_api_init() || !conv_shape_consistent(g) || !conv_out_contiguous(g) || g.C % kind_align(kind) || g.K % kind_align(kind))
 		return 1;
+	const int bk = kind_bk(kind);
 	const long long npq = (long long)g.N * g.P * g.Q;
 	if (npq > 0x7fffffffll)
 		return 1;
@@ -761,16 +917,15 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 	const long long rsc = (long long)g.R * g.S * g.C;
 	CUtensorMap tmA, tmB;
 	// A = grad_b^T: [K, NPQ] read from the [NPQ, K] tensor as an MN-major operand
-	if (!make_map_2d(&tmA, grad_b, npq, g.K, g.K, 32, UMMA_BLOCK_K, true))
+	if (!map_2d(&tmA, kind, grad_b, npq, g.K, g.K, bk, true))
 		return 1;
 	UmmaGemmParams p;
-	init_params(p);
+	init_params_kind(p, kind);
 	p.M = g.K, p.N = g.C;
-	p.k_iters = (int)((npq + UMMA_BLOCK_K - 1) / UMMA_BLOCK_K);
+	p.k_iters = (int)((npq + bk - 1) / bk);
 	p.chunks_per_tap = p.k_iters;
-	p.out = grad_w;
 	p.rowmap.mode = 0, p.rowmap.ld = rsc;
-	p.idesc = umma_instr_desc(2, 1, 1, UMMA_BLOCK_M, bn);
+	p.idesc = idesc_kind(kind, 1, 1, bn);
 	const long long tiles = (long long)((g.K + 127) / 128) * ((g.C + bn - 1) / bn) * g.R * g.S;
 	// split-K slices have the layout of dW itself ([K, RSC]); splitk_reduce adds them (and the old dW when accumulating)
 	const size_t dw_bytes = (size_t)g.K * rsc * sizeof(float);
@@ -778,13 +933,13 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 	if (conv_is_pointwise(g))
 	{
 		// B = a: [NHW, C], also MN-major
-		if (!make_map_2d(&tmB, a, npq, g.C, g.C, 32, UMMA_BLOCK_K, true))
+		if (!map_2d(&tmB, kind, a, npq, g.C, g.C, bk, true))
 			return 1;
-		return launch_umma_split<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn, scratch, g.K, (int)rsc, rsc, accumulate);
+		return launch_umma_split<OP_MN2D, OP_MN2D>(stream, tmA, tmB, p, bn, kind, scratch, g.K, (int)rsc, grad_w, rsc, accumulate);
 	}
-	if (!make_map_im2col(&tmB, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, 32, UMMA_BLOCK_K, true))
+	if (!map_im2col(&tmB, kind, a, g.N, g.H, g.W, g.C, g.an, g.ah, g.aw, -g.pad_h0, -g.pad_w0, g.pad_h1 - (g.R - 1) * g.dil_h, g.pad_w1 - (g.S - 1) * g.dil_w, g.stride_h, g.stride_w, bk, true))
 		return 1;
-	if (g.K <= 64 && g.C % 32 == 0 && g.C <= 128 && wgrad_taps_enabled() && !t_x3)
+	if (kind == 0 && g.K <= 64 && g.C % 32 == 0 && g.C <= 128 && wgrad_taps_enabled() && !t_x3)
 	{
 		WgradTapsParams w;
 		memset(&w, 0, sizeof(w));
@@ -798,7 +953,7 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 		for (int r = 0; r < g.R; r++)
 			for (int s = 0; s < g.S; s++)
 				w.tap_off_h[r * g.S + s] = (unsigned short)(r * g.dil_h), w.tap_off_w[r * g.S + s] = (unsigned short)(s * g.dil_w);
-		w.out = grad_w, w.rsc = rsc;
+		w.out = (float*)grad_w, w.rsc = rsc;
 		w.mn_lbo = p.mn_lbo, w.mn_sbo = p.mn_sbo, w.mn_layout = p.mn_layout;
 		const int wbn = g.K <= 32 ? 32 : 64;
 		w.idesc = umma_instr_desc(2, 1, 1, UMMA_BLOCK_M, wbn);
@@ -806,12 +961,12 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 		const bool direct = w.splits == 1 && !accumulate;
 		if (!direct && (!scratch.ptr || scratch.bytes < dw_bytes * (size_t)w.splits))
 			return 1;
-		w.out = direct ? grad_w : (float*)scratch.ptr;
+		w.out = direct ? (float*)grad_w : (float*)scratch.ptr;
 		w.split_out_stride = (long long)g.K * rsc;
 		const int rc = wbn == 32 ? launch_wgrad_taps<32>(stream, tmB, tmA, w, tiles_m) : launch_wgrad_taps<64>(stream, tmB, tmA, w, tiles_m);
 		if (rc || direct)
 			return rc;
-		return splitk_reduce(stream, (const float*)scratch.ptr, w.splits, w.split_out_stride, g.K, (int)rsc, rsc, grad_w, rsc, accumulate);
+		return splitk_reduce(stream, (const float*)scratch.ptr, w.splits, w.split_out_stride, g.K, (int)rsc, rsc, (float*)grad_w, rsc, accumulate);
 	}
 	p.grid_taps = g.R * g.S;
 	p.grid_tap_out_stride = g.C;
@@ -825,31 +980,45 @@ int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b,
 			p.tap_off_h[t] = (unsigned short)(r * g.dil_h);
 			p.tap_off_w[t] = (unsigned short)(s * g.dil_w);
 		}
-	return launch_umma_split<OP_MN2D, OP_IM2COL>(stream, tmA, tmB, p, bn, scratch, g.K, (int)rsc, rsc, accumulate);
+	return launch_umma_split<OP_MN2D, OP_IM2COL>(stream, tmA, tmB, p, bn, kind, scratch, g.K, (int)rsc, grad_w, rsc, accumulate);
+}
+int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, const Scratch& scratch, int x3)
+{
+	return conv_wgrad_any(stream, 0, g, grad_b, a, grad_w, accumulate, scratch, x3);
+}
+int conv_wgrad_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* grad_b, const void* a, void* grad_w, int accumulate, const Scratch& scratch)
+{
+	return kind == 1 || kind == 2 ? conv_wgrad_any(stream, kind, g, grad_b, a, grad_w, accumulate, scratch, 0) : 1;
 }
 
 // ------------------------------------------------------------------------------------------------ explicit im2col
-static inline int im2col_kp(const ConvGeom& g) { return (g.R * g.S * g.C + 31) / 32 * 32; }
-static inline bool im2col_applicable(const ConvGeom& g)
+// Small-channel convolutions whose pixels TMA cannot address (C * element size not a multiple of 16 bytes: the 3-channel stem):
+// patches [N*P*Q, Kp] with Kp = R*S*C rounded up to one operand span (32 fp32 / 64 16-bit elements, zero padded), then the GEMM.
+static inline int im2col_kp(const ConvGeom& g, int kind) { const int span = kind_bk(kind); return (g.R * g.S * g.C + span - 1) / span * span; }
+static inline bool im2col_applicable(const ConvGeom& g, int kind)
 {
-	return g.R * g.S * g.C <= 256 && (long long)g.N * g.P * g.Q <= 0x7fffffffll && g.K % 4 == 0 && g.bw == g.K && g.bh == (long long)g.Q * g.K && g.bn == (long long)g.P * g.Q * g.K;
+	return g.R * g.S * g.C <= 256 && (long long)g.N * g.P * g.Q <= 0x7fffffffll && g.K % kind_align(kind) == 0 && g.bw == g.K && g.bh == (long long)g.Q * g.K && g.bn == (long long)g.P * g.Q * g.K;
 }
-size_t conv_im2col_workspace_bytes(const ConvGeom& g)
+static size_t im2col_used_bytes(const ConvGeom& g, int kind)
 {
-	const size_t kp = im2col_kp(g);
+	const size_t kp = im2col_kp(g, kind);
 	// patches [NPQ, Kp] + packed filters [K, Kp] + packed filter gradient [K, Kp]
-	return ((size_t)g.N * g.P * g.Q * kp + 2 * (size_t)g.K * kp) * sizeof(float) + 1024 + CONTRACT_SCRATCH_BYTES;
+	return ((((size_t)g.N * g.P * g.Q * kp + 2 * (size_t)g.K * kp) * kind_esz(kind)) + 511) & ~(size_t)511;
 }
-static Scratch im2col_scratch(const ConvGeom& g, void* workspace)
+size_t conv_im2col_workspace_bytes(const ConvGeom& g, int kind)
 {
-	const size_t used = (((size_t)g.N * g.P * g.Q * im2col_kp(g) + 2 * (size_t)g.K * im2col_kp(g)) * sizeof(float) + 511) & ~(size_t)511;
-	Scratch s = { (char*)workspace + used, CONTRACT_SCRATCH_BYTES };
+	return im2col_used_bytes(g, kind) + 512 + CONTRACT_SCRATCH_BYTES;
+}
+static Scratch im2col_scratch(const ConvGeom& g, int kind, void* workspace)
+{
+	Scratch s = { (char*)workspace + im2col_used_bytes(g, kind), CONTRACT_SCRATCH_BYTES };
 	return s;
 }
 // patches[m, (r, s, c)] = a[n, p * stride - pad + r * dil, q * stride - pad + s * dil, c] (0 outside / in the padding columns)
-// One thread = one 16-byte store (4 consecutive k of one patch row); k -> (tap row offset, tap column offset, channel) comes
-// from a table in shared memory, all index math is 32-bit.
-__global__ void __launch_bounds__(256) im2col_kernel(const ConvGeom g, const float* __restrict__ a, float* __restrict__ out, const int kp, const unsigned rows)
+// One thread = 4 consecutive k of one patch row (one 16- or 8-byte store); k -> (tap row offset, tap column offset, channel)
+// comes from a table in shared memory, all index math is 32-bit.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const ConvGeom g, const T* __restrict__ a, T* __restrict__ out, const int kp, const unsigned rows)
 {
 	__shared__ int tab_h[256], tab_w[256], tab_c[256];
 	const int rsc = g.R * g.S * g.C;
@@ -869,36 +1038,38 @@ __global__ void __launch_bounds__(256) im2col_kernel(const ConvGeom g, const flo
 		const unsigned q = m % (unsigned)g.Q, u = m / (unsigned)g.Q;
 		const unsigned pp = u % (unsigned)g.P, n = u / (unsigned)g.P;
 		const int h0 = (int)pp * g.stride_h, w0 = (int)q * g.stride_w;
-		const float* const an = a + (long long)n * g.an;
+		const T* const an = a + (long long)n * g.an;
 		float v[4];
 #pragma unroll
 		for (int j = 0; j < 4; j++)
 		{
 			const int h = h0 + tab_h[k0 + j], w = w0 + tab_w[k0 + j];
-			v[j] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? __ldg(an + h * g.ah + w * g.aw + tab_c[k0 + j]) : 0.f;
+			v[j] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? ldf(an + h * g.ah + w * g.aw + tab_c[k0 + j]) : 0.f;
 		}
-		*reinterpret_cast<float4*>(out + (unsigned long long)m * kp + k0) = make_float4(v[0], v[1], v[2], v[3]);
+		st4(out + (unsigned long long)m * kp + k0, make_float4(v[0], v[1], v[2], v[3]));
 	}
 }
 // dir 0: packed[k, 0..kp) = w[k, 0..rsc) zero padded.  dir 1: w[k, j] (+)= packed[k, j]
-__global__ void pack_filters_kernel(float* __restrict__ w, float* __restrict__ packed, const int K, const int rsc, const int kp, const int dir, const int accumulate)
+template <typename T>
+__global__ void pack_filters_kernel(T* __restrict__ w, T* __restrict__ packed, const int K, const int rsc, const int kp, const int dir, const int accumulate)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= K * kp)
 		return;
 	const int k = i / kp, j = i % kp;
 	if (dir == 0)
-		packed[i] = j < rsc ? w[(size_t)k * rsc + j] : 0.f;
+		stf(packed + i, j < rsc ? ldf(w + (size_t)k * rsc + j) : 0.f);
 	else if (j < rsc)
-		w[(size_t)k * rsc + j] = accumulate ? w[(size_t)k * rsc + j] + packed[i] : packed[i];
+		stf(w + (size_t)k * rsc + j, accumulate ? ldf(w + (size_t)k * rsc + j) + ldf(packed + i) : ldf(packed + i));
 }
-static int run_im2col(cudaStream_t stream, const ConvGeom& g, const float* a, float* patches, int kp)
+template <typename T>
+static int run_im2col(cudaStream_t stream, const ConvGeom& g, const T* a, T* patches, int kp)
 {
 	const size_t rows = (size_t)g.N * g.P * g.Q;
 	size_t blocks = (rows * (kp / 4) + 255) / 256;
 	if (blocks > (size_t)num_sms() * 32)
 		blocks = (size_t)num_sms() * 32;
-	im2col_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, a, patches, kp, (unsigned)rows);
+	im2col_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(g, a, patches, kp, (unsigned)rows);
 	count_launch();
 	const cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess)
@@ -908,37 +1079,61 @@ static int run_im2col(cudaStream_t stream, const ConvGeom& g, const float* a, fl
 	}
 	return 0;
 }
+template <typename T>
+static int conv_fprop_im2col_t(cudaStream_t stream, const ConvGeom& g, const T* a, const T* w, const float* bias, const void* bias16, T* b, void* workspace, int x3)
+{
+	constexpr int kind = ElemKind<T>::value;
+	if (!tma_api_init() || !im2col_applicable(g, kind) || !workspace)
+		return 1;
+	const int kp = im2col_kp(g, kind), rsc = g.R * g.S * g.C;
+	const size_t m = (size_t)g.N * g.P * g.Q;
+	T* patches = (T*)workspace;
+	T* wp = patches + m * kp;
+	if (run_im2col<T>(stream, g, a, patches, kp))
+		return -1;
+	pack_filters_kernel<T><<<(g.K * kp + 255) / 256, 256, 0, stream>>>((T*)w, wp, g.K, rsc, kp, 0, 0);
+	count_launch();
+	return gemm_any(stream, kind, (int)m, g.K, kp, patches, kp, 0, wp, kp, 1, b, g.K, bias, bias16, 0, im2col_scratch(g, kind, workspace), x3);
+}
+template <typename T>
+static int conv_wgrad_im2col_t(cudaStream_t stream, const ConvGeom& g, const T* grad_b, const T* a, T* grad_w, int accumulate, void* workspace, int x3)
+{
+	constexpr int kind = ElemKind<T>::value;
+	if (!tma_api_init() || !im2col_applicable(g, kind) || !workspace)
+		return 1;
+	const int kp = im2col_kp(g, kind), rsc = g.R * g.S * g.C;
+	const size_t m = (size_t)g.N * g.P * g.Q;
+	T* patches = (T*)workspace;
+	T* dwp = patches + m * kp + (size_t)g.K * kp;
+	if (run_im2col<T>(stream, g, a, patches, kp))
+		return -1;
+	// dWp[K, Kp] = grad_b^T [K, NPQ] * patches [NPQ, Kp]
+	const int rc = gemm_any(stream, kind, g.K, kp, (int)m, grad_b, g.K, 1, patches, kp, 0, dwp, kp, 0, 0, 0, im2col_scratch(g, kind, workspace), x3);
+	if (rc)
+		return rc;
+	pack_filters_kernel<T><<<(g.K * kp + 255) / 256, 256, 0, stream>>>(grad_w, dwp, g.K, rsc, kp, 1, accumulate);
+	count_launch();
+	return 0;
+}
 int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, void* workspace, int x3)
 {
-	if (!tma_api_init() || !im2col_applicable(g) || !workspace)
-		return 1;
-	const int kp = im2col_kp(g), rsc = g.R * g.S * g.C;
-	const size_t m = (size_t)g.N * g.P * g.Q;
-	float* patches = (float*)workspace;
-	float* wp = patches + m * kp;
-	if (run_im2col(stream, g, a, patches, kp))
-		return -1;
-	pack_filters_kernel<<<(g.K * kp + 255) / 256, 256, 0, stream>>>((float*)w, wp, g.K, rsc, kp, 0, 0);
-	count_launch();
-	return gemm_tf32(stream, (int)m, g.K, kp, patches, kp, 0, wp, kp, 1, b, g.K, bias, 0, im2col_scratch(g, workspace), x3);
+	return conv_fprop_im2col_t<float>(stream, g, a, w, bias, 0, b, workspace, x3);
 }
 int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, void* workspace, int x3)
 {
-	if (!tma_api_init() || !im2col_applicable(g) || !workspace)
-		return 1;
-	const int kp = im2col_kp(g), rsc = g.R * g.S * g.C;
-	const size_t m = (size_t)g.N * g.P * g.Q;
-	float* patches = (float*)workspace;
-	float* dwp = patches + m * kp + (size_t)g.K * kp;
-	if (run_im2col(stream, g, a, patches, kp))
-		return -1;
-	// dWp[K, Kp] = grad_b^T [K, NPQ] * patches [NPQ, Kp]
-	const int rc = gemm_tf32(stream, g.K, kp, (int)m, grad_b, g.K, 1, patches, kp, 0, dwp, kp, 0, 0, im2col_scratch(g, workspace), x3);
-	if (rc)
-		return rc;
-	pack_filters_kernel<<<(g.K * kp + 255) / 256, 256, 0, stream>>>(grad_w, dwp, g.K, rsc, kp, 1, accumulate);
-	count_launch();
-	return 0;
+	return conv_wgrad_im2col_t<float>(stream, g, grad_b, a, grad_w, accumulate, workspace, x3);
+}
+int conv_fprop_im2col_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* a, const void* w, const float* bias32, const void* bias16, void* b, void* workspace)
+{
+	if (kind == 1)
+		return conv_fprop_im2col_t<__nv_bfloat16>(stream, g, (const __nv_bfloat16*)a, (const __nv_bfloat16*)w, bias32, bias16, (__nv_bfloat16*)b, workspace, 0);
+	return conv_fprop_im2col_t<__half>(stream, g, (const __half*)a, (const __half*)w, bias32, bias16, (__half*)b, workspace, 0);
+}
+int conv_wgrad_im2col_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* grad_b, const void* a, void* grad_w, int accumulate, void* workspace)
+{
+	if (kind == 1)
+		return conv_wgrad_im2col_t<__nv_bfloat16>(stream, g, (const __nv_bfloat16*)grad_b, (const __nv_bfloat16*)a, (__nv_bfloat16*)grad_w, accumulate, workspace, 0);
+	return conv_wgrad_im2col_t<__half>(stream, g, (const __half*)grad_b, (const __half*)a, (__half*)grad_w, accumulate, workspace, 0);
 }
 
 } // namespace sm100

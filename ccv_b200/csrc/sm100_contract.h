@@ -39,6 +39,14 @@ int conv_fprop_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, cons
 int conv_dgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* w, float* grad_a, const Scratch& scratch, int x3 = 0);
 int conv_wgrad_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, const Scratch& scratch, int x3 = 0);
 
+// The same contractions on 16-bit tensors (kind 1 = bf16, 2 = fp16): tcgen05 kind::f16 with fp32 accumulation in TMEM, 16-bit
+// result (rounded once, to nearest even).  Every leading dimension / channel count must be a multiple of 8 elements (16 bytes).
+// bias: fp32 (bias32) or in the tensors' 16-bit type (bias16); at most one of them.  Returns as above (1 = shape not covered).
+int gemm_16(cudaStream_t stream, int kind, int M, int N, int K, const void* a, long long lda, int trans_a, const void* b, long long ldb, int trans_b, void* c, long long ldc, const float* bias32, const void* bias16, int accumulate, const Scratch& scratch);
+int conv_fprop_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* a, const void* w, const float* bias32, const void* bias16, void* b, const Scratch& scratch);
+int conv_dgrad_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* grad_b, const void* w, void* grad_a, const Scratch& scratch);
+int conv_wgrad_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* grad_b, const void* a, void* grad_w, int accumulate, const Scratch& scratch);
+
 // Ask the NEXT conv_fprop_tf32 / gemm_tf32 launch of this host thread to also produce per-column statistics of its output
 // (batch-norm forward fused into the producing convolution).  `part` holds four planes of max_rows x N floats -- count,
 // shift k, sum(v - k), sum((v - k)^2) -- one row per (CTA, epilogue warp quarter); *rows_out = rows in use (the plane
@@ -48,10 +56,12 @@ void conv_stats_request(float* part, int max_rows, int* rows_out);
 
 // Small-channel convolutions (C not a multiple of 4, e.g. the 3-channel stem): explicit im2col into `workspace`
 // ([N*P*Q, Kp] with Kp = R*S*C rounded up to 32, zero padded) followed by the tensor-core GEMM.  Returns 1 when not applicable.
-size_t conv_im2col_workspace_bytes(const ConvGeom& g);
+size_t conv_im2col_workspace_bytes(const ConvGeom& g, int kind = 0); // kind: 0 = fp32, 1 = bf16, 2 = fp16
 // (the workspace must hold conv_im2col_workspace_bytes(g), which includes CONTRACT_SCRATCH_BYTES for the GEMM's split-K slices)
 int conv_fprop_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* a, const float* w, const float* bias, float* b, void* workspace, int x3 = 0);
 int conv_wgrad_im2col_tf32(cudaStream_t stream, const ConvGeom& g, const float* grad_b, const float* a, float* grad_w, int accumulate, void* workspace, int x3 = 0);
+int conv_fprop_im2col_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* a, const void* w, const float* bias32, const void* bias16, void* b, void* workspace);
+int conv_wgrad_im2col_16(cudaStream_t stream, int kind, const ConvGeom& g, const void* grad_b, const void* a, void* grad_w, int accumulate, void* workspace);
 
 // CUDA-core fp32 versions of the same contractions: any stride/alignment, groups, exact fp32 products.
 int gemm_ffma(cudaStream_t stream, int M, int N, int K, const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c, long long ldc, const float* bias, int accumulate);

@@ -3,6 +3,7 @@
 // SM count; reductions use warp shuffles and one atomic per block.  Semantics follow CCV_NNC_BACKEND_CPU_REF
 // (file:line cited per kernel, relative to /root/reference/lib/nnc/cmd).
 #include "sm100_ew.h"
+#include "sm100_elem.cuh"
 #include "sm100_contract.h"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -523,8 +524,8 @@ int reduce_sum_bcast_f32(cudaStream_t s, const float* a, const int* adim, const 
 // =============================================================================================== pooling (NHWC)
 // pool/ccv_nnc_max_pool_cpu_ref.c:13-59, pool/ccv_nnc_avg_pool_cpu_ref.c:13-58: the window is clipped to the input
 // (SET_BORDER_OFFSET_SIZE_FOR, ccv_nnc_internal.h:209-213); the average divides by the clipped window size.
-template <int VEC, int IS_MAX>
-__global__ void pool_fwd_kernel(const PoolGeom g, const float* __restrict__ a, float* __restrict__ b)
+template <typename T, int VEC, int IS_MAX>
+__global__ void pool_fwd_kernel(const PoolGeom g, const T* __restrict__ a, T* __restrict__ b)
 {
 	const int CV = g.C / VEC;
 	const size_t total = (size_t)g.N * g.P * g.Q * CV;
@@ -558,14 +559,14 @@ __global__ void pool_fwd_kernel(const PoolGeom g, const float* __restrict__ a, f
 		for (int h = h0; h < h1; h++)
 			for (int w = w0; w < w1; w++)
 			{
-				const float* ap = a + n * g.an + h * g.ah + w * g.aw + c;
+				const T* ap = a + n * g.an + h * g.ah + w * g.aw + c;
 				float x[VEC];
 				if (VEC == 4)
 				{
-					const float4 t = *reinterpret_cast<const float4*>(ap);
+					const float4 t = ld4(ap);
 					x[0] = t.x, x[1 % VEC] = t.y, x[2 % VEC] = t.z, x[3 % VEC] = t.w;
 				} else
-					x[0] = *ap;
+					x[0] = ldf(ap);
 #pragma unroll
 				for (int k = 0; k < VEC; k++)
 					v[k] = IS_MAX ? fmaxf(v[k], x[k]) : v[k] + x[k];
@@ -577,44 +578,45 @@ __global__ void pool_fwd_kernel(const PoolGeom g, const float* __restrict__ a, f
 			for (int k = 0; k < VEC; k++)
 				v[k] = v[k] / inv;
 		}
-		float* bp = b + n * g.bn + p * g.bh + q * g.bw + c;
+		T* bp = b + n * g.bn + p * g.bh + q * g.bw + c;
 		if (VEC == 4)
-			*reinterpret_cast<float4*>(bp) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+			st4(bp, make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
 		else
-			bp[0] = v[0];
+			stf(bp, v[0]);
 	}
 }
-static bool pool_vec_ok(const PoolGeom& g, const void* a, const void* b)
+template <typename T>
+static bool pool_vec_ok(const PoolGeom& g, const T* a, const T* b)
 {
-	return g.C % 4 == 0 && aligned16(a) && aligned16(b) && g.aw % 4 == 0 && g.ah % 4 == 0 && g.an % 4 == 0 && g.bw % 4 == 0 && g.bh % 4 == 0 && g.bn % 4 == 0;
+	return g.C % 4 == 0 && aligned_v4(a) && aligned_v4(b) && g.aw % 4 == 0 && g.ah % 4 == 0 && g.an % 4 == 0 && g.bw % 4 == 0 && g.bh % 4 == 0 && g.bn % 4 == 0;
 }
-int pool_max_fwd_f32(cudaStream_t s, const PoolGeom& g, const float* a, float* b)
+template <typename T, int IS_MAX>
+static int pool_fwd_t(cudaStream_t s, const PoolGeom& g, const T* a, T* b)
 {
 	const size_t total = (size_t)g.N * g.P * g.Q * g.C;
 	if (total == 0)
 		return 0;
-	if (pool_vec_ok(g, a, b))
-		pool_fwd_kernel<4, 1><<<grid_for(total / 4, 256), 256, 0, s>>>(g, a, b);
+	if (pool_vec_ok(g, a, (const T*)b))
+		pool_fwd_kernel<T, 4, IS_MAX><<<grid_for(total / 4, 256), 256, 0, s>>>(g, a, b);
 	else
-		pool_fwd_kernel<1, 1><<<grid_for(total, 256), 256, 0, s>>>(g, a, b);
-	return check("pool_max_fwd");
+		pool_fwd_kernel<T, 1, IS_MAX><<<grid_for(total, 256), 256, 0, s>>>(g, a, b);
+	return check(IS_MAX ? "pool_max_fwd" : "pool_avg_fwd");
 }
-int pool_avg_fwd_f32(cudaStream_t s, const PoolGeom& g, const float* a, float* b)
+int pool_max_fwd_f32(cudaStream_t s, const PoolGeom& g, const float* a, float* b) { return pool_fwd_t<float, 1>(s, g, a, b); }
+int pool_avg_fwd_f32(cudaStream_t s, const PoolGeom& g, const float* a, float* b) { return pool_fwd_t<float, 0>(s, g, a, b); }
+int pool_max_fwd_16(cudaStream_t s, int kind, const PoolGeom& g, const void* a, void* b)
 {
-	const size_t total = (size_t)g.N * g.P * g.Q * g.C;
-	if (total == 0)
-		return 0;
-	if (pool_vec_ok(g, a, b))
-		pool_fwd_kernel<4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(g, a, b);
-	else
-		pool_fwd_kernel<1, 0><<<grid_for(total, 256), 256, 0, s>>>(g, a, b);
-	return check("pool_avg_fwd");
+	return kind == 1 ? pool_fwd_t<__nv_bfloat16, 1>(s, g, (const __nv_bfloat16*)a, (__nv_bfloat16*)b) : pool_fwd_t<__half, 1>(s, g, (const __half*)a, (__half*)b);
+}
+int pool_avg_fwd_16(cudaStream_t s, int kind, const PoolGeom& g, const void* a, void* b)
+{
+	return kind == 1 ? pool_fwd_t<__nv_bfloat16, 0>(s, g, (const __nv_bfloat16*)a, (__nv_bfloat16*)b) : pool_fwd_t<__half, 0>(s, g, (const __half*)a, (__half*)b);
 }
 // Backward as a gather over input positions (no atomics): input (h, w) collects from every window that covers it.
 // max: pool/ccv_nnc_max_pool_cpu_ref.c:61-139 -- every position equal to the window max receives the gradient.
 // avg: pool/ccv_nnc_avg_pool_cpu_ref.c:60-110 -- gradient / clipped window size.
-template <int VEC, int IS_MAX>
-__global__ void pool_bwd_kernel(const PoolGeom g, const float* __restrict__ gb, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ ga)
+template <typename T, int VEC, int IS_MAX>
+__global__ void pool_bwd_kernel(const PoolGeom g, const T* __restrict__ gb, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ ga)
 {
 	const int CV = g.C / VEC;
 	const size_t total = (size_t)g.N * g.H * g.W * CV;
@@ -646,11 +648,11 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const float* __restrict__ gb, 
 			float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 			if (p < g.P && q < g.Q)
 			{
-				const float4 t = *reinterpret_cast<const float4*>(gb + n * g.bn + p * g.bh + q * g.bw + c);
+				const float4 t = ld4(gb + n * g.bn + p * g.bh + q * g.bw + c);
 				const float inv = (float)(g.R * g.S);
 				o = make_float4(t.x / inv, t.y / inv, t.z / inv, t.w / inv);
 			}
-			*reinterpret_cast<float4*>(ga + n * g.an + h * g.ah + w * g.aw + c) = o;
+			st4(ga + n * g.an + h * g.ah + w * g.aw + c, o);
 			continue;
 		}
 		// windows p with p * stride - pad <= h < p * stride - pad + R
@@ -662,13 +664,13 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const float* __restrict__ gb, 
 			acc[k] = 0.f, x[k] = 0.f;
 		if (IS_MAX)
 		{
-			const float* ap = a + n * g.an + h * g.ah + w * g.aw + c;
+			const T* ap = a + n * g.an + h * g.ah + w * g.aw + c;
 			if (VEC == 4)
 			{
-				const float4 t = *reinterpret_cast<const float4*>(ap);
+				const float4 t = ld4(ap);
 				x[0] = t.x, x[1 % VEC] = t.y, x[2 % VEC] = t.z, x[3 % VEC] = t.w;
 			} else
-				x[0] = *ap;
+				x[0] = ldf(ap);
 		}
 		for (int p = p_lo; p <= p_hi; p++)
 		{
@@ -683,17 +685,17 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const float* __restrict__ gb, 
 				float gv[VEC], bv[VEC];
 				if (VEC == 4)
 				{
-					const float4 t = *reinterpret_cast<const float4*>(gb + o);
+					const float4 t = ld4(gb + o);
 					gv[0] = t.x, gv[1 % VEC] = t.y, gv[2 % VEC] = t.z, gv[3 % VEC] = t.w;
 					if (IS_MAX)
 					{
-						const float4 u = *reinterpret_cast<const float4*>(b + o);
+						const float4 u = ld4(b + o);
 						bv[0] = u.x, bv[1 % VEC] = u.y, bv[2 % VEC] = u.z, bv[3 % VEC] = u.w;
 					}
 				} else {
-					gv[0] = gb[o];
+					gv[0] = ldf(gb + o);
 					if (IS_MAX)
-						bv[0] = b[o];
+						bv[0] = ldf(b + o);
 				}
 				if (IS_MAX)
 				{
@@ -710,34 +712,47 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const float* __restrict__ gb, 
 				}
 			}
 		}
-		float* hp = ga + n * g.an + h * g.ah + w * g.aw + c;
+		T* hp = ga + n * g.an + h * g.ah + w * g.aw + c;
 		if (VEC == 4)
-			*reinterpret_cast<float4*>(hp) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+			st4(hp, make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]));
 		else
-			hp[0] = acc[0];
+			stf(hp, acc[0]);
 	}
 }
-int pool_max_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, const float* a, const float* b, float* grad_a)
+template <typename T>
+static int pool_max_bwd_t(cudaStream_t s, const PoolGeom& g, const T* grad_b, const T* a, const T* b, T* grad_a)
 {
 	const size_t total = (size_t)g.N * g.H * g.W * g.C;
 	if (total == 0)
 		return 0;
-	if (pool_vec_ok(g, a, b) && aligned16(grad_b) && aligned16(grad_a))
-		pool_bwd_kernel<4, 1><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
+	if (pool_vec_ok(g, a, b) && aligned_v4(grad_b) && aligned_v4(grad_a))
+		pool_bwd_kernel<T, 4, 1><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
 	else
-		pool_bwd_kernel<1, 1><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
+		pool_bwd_kernel<T, 1, 1><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
 	return check("pool_max_bwd");
 }
-int pool_avg_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, float* grad_a)
+template <typename T>
+static int pool_avg_bwd_t(cudaStream_t s, const PoolGeom& g, const T* grad_b, T* grad_a)
 {
 	const size_t total = (size_t)g.N * g.H * g.W * g.C;
 	if (total == 0)
 		return 0;
-	if (pool_vec_ok(g, grad_a, grad_b))
-		pool_bwd_kernel<4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, 0, 0, grad_a);
+	if (pool_vec_ok(g, (const T*)grad_a, grad_b))
+		pool_bwd_kernel<T, 4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, (const T*)0, (const T*)0, grad_a);
 	else
-		pool_bwd_kernel<1, 0><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, 0, 0, grad_a);
+		pool_bwd_kernel<T, 1, 0><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, (const T*)0, (const T*)0, grad_a);
 	return check("pool_avg_bwd");
+}
+int pool_max_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, const float* a, const float* b, float* grad_a) { return pool_max_bwd_t<float>(s, g, grad_b, a, b, grad_a); }
+int pool_avg_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, float* grad_a) { return pool_avg_bwd_t<float>(s, g, grad_b, grad_a); }
+int pool_max_bwd_16(cudaStream_t s, int kind, const PoolGeom& g, const void* grad_b, const void* a, const void* b, void* grad_a)
+{
+	return kind == 1 ? pool_max_bwd_t<__nv_bfloat16>(s, g, (const __nv_bfloat16*)grad_b, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)grad_a)
+		: pool_max_bwd_t<__half>(s, g, (const __half*)grad_b, (const __half*)a, (const __half*)b, (__half*)grad_a);
+}
+int pool_avg_bwd_16(cudaStream_t s, int kind, const PoolGeom& g, const void* grad_b, void* grad_a)
+{
+	return kind == 1 ? pool_avg_bwd_t<__nv_bfloat16>(s, g, (const __nv_bfloat16*)grad_b, (__nv_bfloat16*)grad_a) : pool_avg_bwd_t<__half>(s, g, (const __half*)grad_b, (__half*)grad_a);
 }
 
 // =============================================================================================== softmax / losses
@@ -936,7 +951,7 @@ int softmax_cce_bwd_f32(cudaStream_t s, const float* g, const void* label, int l
 // =============================================================================================== SGD
 // sgd/ccv_nnc_sgd_cpu_ref.c:16-126
 template <int VEC>
-__global__ void sgd_kernel(const float* __restrict__ g, const float* __restrict__ a, const float* __restrict__ m, float* __restrict__ b, float* __restrict__ n, const size_t count, const int nesterov, const float rate, const float scale, const float decay, const float momentum, const float inv_dampening)
+__global__ void sgd_kernel(const void* __restrict__ g, const int g_kind, const float* __restrict__ a, const float* __restrict__ m, float* __restrict__ b, float* __restrict__ n, const size_t count, const int nesterov, const float rate, const float scale, const float decay, const float momentum, const float inv_dampening)
 {
 	const size_t cv = VEC == 4 ? count >> 2 : count;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cv; i += (size_t)gridDim.x * blockDim.x)
@@ -944,12 +959,14 @@ __global__ void sgd_kernel(const float* __restrict__ g, const float* __restrict_
 		float gv[VEC], av[VEC], mv[VEC], bv[VEC], nv[VEC];
 		if (VEC == 4)
 		{
-			const float4 t = reinterpret_cast<const float4*>(g)[i], u = reinterpret_cast<const float4*>(a)[i], w = reinterpret_cast<const float4*>(m)[i];
+			// the gradient may be 16-bit while parameters and momenta are fp32 (the reference's mixed form, sgd/gpu/ccv_nnc_sgd_gpu_ref.cu:71-74)
+			const float4 t = g_kind == 0 ? ld4(reinterpret_cast<const float*>(g) + i * 4) : g_kind == 1 ? ld4(reinterpret_cast<const __nv_bfloat16*>(g) + i * 4) : ld4(reinterpret_cast<const __half*>(g) + i * 4);
+			const float4 u = reinterpret_cast<const float4*>(a)[i], w = reinterpret_cast<const float4*>(m)[i];
 			gv[0] = t.x, gv[1 % VEC] = t.y, gv[2 % VEC] = t.z, gv[3 % VEC] = t.w;
 			av[0] = u.x, av[1 % VEC] = u.y, av[2 % VEC] = u.z, av[3 % VEC] = u.w;
 			mv[0] = w.x, mv[1 % VEC] = w.y, mv[2 % VEC] = w.z, mv[3 % VEC] = w.w;
 		} else
-			gv[0] = g[i], av[0] = a[i], mv[0] = m[i];
+			gv[0] = ld_kind(g, i, g_kind), av[0] = a[i], mv[0] = m[i];
 #pragma unroll
 		for (int j = 0; j < VEC; j++)
 		{
@@ -972,16 +989,21 @@ __global__ void sgd_kernel(const float* __restrict__ g, const float* __restrict_
 			b[i] = bv[0], n[i] = nv[0];
 	}
 }
-int sgd_f32(cudaStream_t s, const float* g, const float* a, const float* m, float* b, float* n, size_t count, int nesterov, float rate, float scale, float decay, float momentum, float dampening)
+static inline bool g_aligned(const void* g, int g_kind) { return (((uintptr_t)g) & (g_kind ? 7 : 15)) == 0; }
+int sgd_any(cudaStream_t s, int g_kind, const void* g, const float* a, const float* m, float* b, float* n, size_t count, int nesterov, float rate, float scale, float decay, float momentum, float dampening)
 {
 	if (count == 0)
 		return 0;
 	const float inv_dampening = 1.f - dampening;
-	if (count % 4 == 0 && aligned16(g) && aligned16(a) && aligned16(m) && aligned16(b) && aligned16(n))
-		sgd_kernel<4><<<grid_for(count / 4, 256), 256, 0, s>>>(g, a, m, b, n, count, nesterov, rate, scale, decay, momentum, inv_dampening);
+	if (count % 4 == 0 && g_aligned(g, g_kind) && aligned16(a) && aligned16(m) && aligned16(b) && aligned16(n))
+		sgd_kernel<4><<<grid_for(count / 4, 256), 256, 0, s>>>(g, g_kind, a, m, b, n, count, nesterov, rate, scale, decay, momentum, inv_dampening);
 	else
-		sgd_kernel<1><<<grid_for(count, 256), 256, 0, s>>>(g, a, m, b, n, count, nesterov, rate, scale, decay, momentum, inv_dampening);
+		sgd_kernel<1><<<grid_for(count, 256), 256, 0, s>>>(g, g_kind, a, m, b, n, count, nesterov, rate, scale, decay, momentum, inv_dampening);
 	return check("sgd");
+}
+int sgd_f32(cudaStream_t s, const float* g, const float* a, const float* m, float* b, float* n, size_t count, int nesterov, float rate, float scale, float decay, float momentum, float dampening)
+{
+	return sgd_any(s, 0, g, a, m, b, n, count, nesterov, rate, scale, decay, momentum, dampening);
 }
 
 // Many SGD commands with the same hyper-parameters in one launch (the per-parameter SGD nodes of a model are a run of ~200
@@ -990,7 +1012,8 @@ int sgd_f32(cudaStream_t s, const float* g, const float* a, const float* m, floa
 constexpr int SGD_MULTI_MAX = 32;
 constexpr unsigned SGD_MULTI_CHUNK = 4096;
 struct SgdMulti {
-	const float* g[SGD_MULTI_MAX];
+	const void* g[SGD_MULTI_MAX];
+	int g_kind;
 	const float* a[SGD_MULTI_MAX];
 	const float* m[SGD_MULTI_MAX];
 	float* b[SGD_MULTI_MAX];
@@ -1006,7 +1029,7 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ 
 		ti++;
 	const unsigned base = (blockIdx.x - t.block_start[ti]) * SGD_MULTI_CHUNK;
 	const unsigned count = t.count[ti];
-	const float* const g = t.g[ti];
+	const void* const g = t.g[ti];
 	const float* const a = t.a[ti];
 	const float* const m = t.m[ti];
 	float* const b = t.b[ti];
@@ -1017,7 +1040,8 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ 
 		const unsigned i = base + (it * 256 + threadIdx.x) * 4;
 		if (i >= count)
 			break;
-		const float4 gv = *reinterpret_cast<const float4*>(g + i), av = *reinterpret_cast<const float4*>(a + i), mv = *reinterpret_cast<const float4*>(m + i);
+		const float4 gv = t.g_kind == 0 ? ld4(reinterpret_cast<const float*>(g) + i) : t.g_kind == 1 ? ld4(reinterpret_cast<const __nv_bfloat16*>(g) + i) : ld4(reinterpret_cast<const __half*>(g) + i);
+		const float4 av = *reinterpret_cast<const float4*>(a + i), mv = *reinterpret_cast<const float4*>(m + i);
 		const float gs[4] = { gv.x, gv.y, gv.z, gv.w }, as[4] = { av.x, av.y, av.z, av.w }, ms[4] = { mv.x, mv.y, mv.z, mv.w };
 		float bs[4], ns[4];
 #pragma unroll
@@ -1040,21 +1064,25 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ 
 }
 int sgd_multi_f32(cudaStream_t s, int tensors, const float* const* g, const float* const* a, const float* const* m, float* const* b, float* const* n, const size_t* counts, int nesterov, float rate, float scale, float decay, float momentum, float dampening)
 {
+	return sgd_multi_any(s, tensors, 0, reinterpret_cast<const void* const*>(g), a, m, b, n, counts, nesterov, rate, scale, decay, momentum, dampening);
+}
+int sgd_multi_any(cudaStream_t s, int tensors, int g_kind, const void* const* g, const float* const* a, const float* const* m, float* const* b, float* const* n, const size_t* counts, int nesterov, float rate, float scale, float decay, float momentum, float dampening)
+{
 	const float inv_dampening = 1.f - dampening;
 	int i = 0;
 	while (i < tensors)
 	{
 		SgdMulti t;
-		t.tensors = 0;
+		t.tensors = 0, t.g_kind = g_kind;
 		unsigned blocks = 0;
 		while (i < tensors && t.tensors < SGD_MULTI_MAX)
 		{
-			const bool vec = counts[i] % 4 == 0 && counts[i] < 0xffffffffull && aligned16(g[i]) && aligned16(a[i]) && aligned16(m[i]) && aligned16(b[i]) && aligned16(n[i]);
+			const bool vec = counts[i] % 4 == 0 && counts[i] < 0xffffffffull && g_aligned(g[i], g_kind) && aligned16(a[i]) && aligned16(m[i]) && aligned16(b[i]) && aligned16(n[i]);
 			if (!vec)
 			{
 				if (t.tensors > 0)
 					break; // flush what is batched, then do this one on its own
-				if (sgd_f32(s, g[i], a[i], m[i], b[i], n[i], counts[i], nesterov, rate, scale, decay, momentum, dampening))
+				if (sgd_any(s, g_kind, g[i], a[i], m[i], b[i], n[i], counts[i], nesterov, rate, scale, decay, momentum, dampening))
 					return -1;
 				i++;
 				continue;
@@ -1078,6 +1106,168 @@ int sgd_multi_f32(cudaStream_t s, int tensors, const float* const* g, const floa
 		}
 	}
 	return 0;
+}
+
+// =============================================================================================== 16-bit elementwise
+// relu / n-ary sum / column sums on bf16 / fp16 tensors (fp32 arithmetic, one rounding on the way out)
+template <typename T, int BWD>
+__global__ void relu16_kernel(const T* __restrict__ g, const T* __restrict__ a, T* __restrict__ out, const size_t n, const int vec)
+{
+	const size_t n4 = vec ? n >> 2 : 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const float4 x = ld4(a + i * 4);
+		if (!BWD)
+			st4(out + i * 4, make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)));
+		else {
+			const float4 y = ld4(g + i * 4);
+			st4(out + i * 4, make_float4(x.x > 0 ? y.x : 0.f, x.y > 0 ? y.y : 0.f, x.z > 0 ? y.z : 0.f, x.w > 0 ? y.w : 0.f));
+		}
+	}
+	for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		stf(out + i, BWD ? (ldf(a + i) > 0 ? ldf(g + i) : 0.f) : fmaxf(ldf(a + i), 0.f));
+}
+template <typename T>
+static int relu16_t(cudaStream_t s, const T* g, const T* a, T* out, size_t n, int bwd)
+{
+	if (n == 0)
+		return 0;
+	const int vec = aligned_v4(a) && aligned_v4(out) && (!bwd || aligned_v4(g));
+	if (bwd)
+		relu16_kernel<T, 1><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(g, a, out, n, vec);
+	else
+		relu16_kernel<T, 0><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(g, a, out, n, vec);
+	return check("relu16");
+}
+int ew_relu_fwd_16(cudaStream_t s, int kind, const void* a, void* b, size_t n)
+{
+	return kind == 1 ? relu16_t<__nv_bfloat16>(s, 0, (const __nv_bfloat16*)a, (__nv_bfloat16*)b, n, 0) : relu16_t<__half>(s, 0, (const __half*)a, (__half*)b, n, 0);
+}
+int ew_relu_bwd_16(cudaStream_t s, int kind, const void* g, const void* b, void* h, size_t n)
+{
+	return kind == 1 ? relu16_t<__nv_bfloat16>(s, (const __nv_bfloat16*)g, (const __nv_bfloat16*)b, (__nv_bfloat16*)h, n, 1) : relu16_t<__half>(s, (const __half*)g, (const __half*)b, (__half*)h, n, 1);
+}
+struct SumArgs16 {
+	const void* in[8];
+	int k;
+};
+template <typename T>
+__global__ void sum16_kernel(const SumArgs16 a, T* __restrict__ out, const size_t n, const int vec)
+{
+	const size_t n4 = vec ? n >> 2 : 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+	{
+		float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 8
+		for (int j = 0; j < a.k; j++)
+		{
+			const float4 v = ld4(reinterpret_cast<const T*>(a.in[j]) + i * 4);
+			acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+		}
+		st4(out + i * 4, acc);
+	}
+	for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	{
+		float acc = 0.f;
+		for (int j = 0; j < a.k; j++)
+			acc += ldf(reinterpret_cast<const T*>(a.in[j]) + i);
+		stf(out + i, acc);
+	}
+}
+// c = a0 + a1 + ... (<= 8 operands per call; the sum is formed in fp32 and rounded once)
+int ew_sum_16(cudaStream_t s, int kind, const void* const* inputs, int k, void* out, size_t n)
+{
+	if (n == 0 || k <= 0)
+		return 0;
+	if (k > 8)
+		return 1;
+	SumArgs16 a;
+	a.k = k;
+	bool vec = (((uintptr_t)out) & 7) == 0;
+	for (int j = 0; j < k; j++)
+		a.in[j] = inputs[j], vec = vec && (((uintptr_t)inputs[j]) & 7) == 0;
+	if (kind == 1)
+		sum16_kernel<__nv_bfloat16><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, (__nv_bfloat16*)out, n, vec);
+	else
+		sum16_kernel<__half><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, (__half*)out, n, vec);
+	return check("ew_sum16");
+}
+// column sums with any input / output element kind: per-block partial rows (fp32) in the workspace, combined in a fixed order
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_any_kernel(const T* __restrict__ g, const size_t rows, const int cols, const long long ld, float* __restrict__ part)
+{
+	// thread = (column group of 4, row lane); blockIdx.y = row slab
+	__shared__ float4 sh[256];
+	const int cols4 = cols >> 2;
+	const int cpb = cols4 >= 256 ? 256 : cols4, rpi = 256 / cpb;
+	const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb;
+	const int col4 = blockIdx.x * cpb + tx;
+	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (ty < rpi && col4 < cols4)
+		for (size_t r = (size_t)blockIdx.y * rpi + ty; r < rows; r += (size_t)gridDim.y * rpi)
+		{
+			const float4 v = ld4(g + r * ld + col4 * 4);
+			acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+		}
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	if (ty == 0 && col4 < cols4)
+	{
+		for (int j = 1; j < rpi; j++)
+		{
+			const float4 v = sh[j * cpb + tx];
+			acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+		}
+		*reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * cols4 + col4) * 4) = acc;
+	}
+}
+__global__ void __launch_bounds__(1024) colsum_partials_any_kernel(const float* __restrict__ part, const int gy, const int ncols, void* __restrict__ out, const int out_kind, const int accumulate)
+{
+	__shared__ float sh[32][33];
+	const int cx = threadIdx.x & 31, yl = threadIdx.x >> 5;
+	const int col = blockIdx.x * 32 + cx;
+	float acc = 0.f;
+	if (col < ncols)
+		for (int y = yl; y < gy; y += 32)
+			acc += part[(size_t)y * ncols + col];
+	sh[yl][cx] = acc;
+	__syncthreads();
+	if (yl == 0 && col < ncols)
+	{
+		float t = 0.f;
+#pragma unroll
+		for (int j = 0; j < 32; j++)
+			t += sh[j][cx];
+		st_kind(out, col, accumulate ? ld_kind(out, col, out_kind) + t : t, out_kind);
+	}
+}
+int colsum_any(cudaStream_t s, int g_kind, const void* g, size_t rows, int cols, long long ld, void* out, int out_kind, int accumulate, void* workspace)
+{
+	if (g_kind == 0 && out_kind == 0)
+		return colsum_f32(s, (const float*)g, rows, cols, ld, (float*)out, accumulate, workspace);
+	if (cols <= 0)
+		return 0;
+	if (cols % 4 || ld % 4 || !workspace || (((uintptr_t)g) & 7))
+		return 1;
+	const int cols4 = cols / 4, cpb = cols4 >= 256 ? 256 : cols4, rpi = 256 / cpb;
+	const int gx = (cols4 + cpb - 1) / cpb;
+	size_t gy = (rows + (size_t)rpi * 32 - 1) / ((size_t)rpi * 32);
+	const size_t cap = (size_t)(sms() * 8 + gx - 1) / gx;
+	if (gy > cap)
+		gy = cap;
+	if (gy < 1)
+		gy = 1;
+	float* const part = (float*)workspace;
+	if (g_kind == 0)
+		colsum_any_kernel<float><<<dim3(gx, (unsigned)gy), 256, 0, s>>>((const float*)g, rows, cols, ld, part);
+	else if (g_kind == 1)
+		colsum_any_kernel<__nv_bfloat16><<<dim3(gx, (unsigned)gy), 256, 0, s>>>((const __nv_bfloat16*)g, rows, cols, ld, part);
+	else
+		colsum_any_kernel<__half><<<dim3(gx, (unsigned)gy), 256, 0, s>>>((const __half*)g, rows, cols, ld, part);
+	if (check("colsum_any"))
+		return -1;
+	colsum_partials_any_kernel<<<(cols + 31) / 32, 1024, 0, s>>>(part, (int)gy, cols, out, out_kind, accumulate);
+	return check("colsum_partials_any");
 }
 
 // =============================================================================================== dtype conversion

@@ -19,10 +19,16 @@ int ew_axpby_bcast_f32(cudaStream_t s, float p, const float* a, const int* astri
 int ew_mul_bcast_f32(cudaStream_t s, float p, const float* a, const int* astride, const float* b, const int* bstride, float* c, const int* cstride, const int* dim);
 int ew_relu_fwd_f32(cudaStream_t s, const float* a, float* b, size_t n);
 int ew_relu_bwd_f32(cudaStream_t s, const float* g, const float* b, float* h, size_t n); // h = b > 0 ? g : 0
+// the same on bf16 (kind 1) / fp16 (kind 2) tensors
+int ew_relu_fwd_16(cudaStream_t s, int kind, const void* a, void* b, size_t n);
+int ew_relu_bwd_16(cudaStream_t s, int kind, const void* g, const void* b, void* h, size_t n);
+int ew_sum_16(cudaStream_t s, int kind, const void* const* inputs, int k, void* out, size_t n); // k <= 8
 // out[c] (+)= sum over rows of g[row * ld + c]  (bias gradients of GEMM / convolution)
 // workspace (colsum_workspace_bytes(cols), may be NULL): per-block partial rows, combined in a fixed order instead of by atomics
 size_t colsum_workspace_bytes(int cols);
 int colsum_f32(cudaStream_t s, const float* g, size_t rows, int cols, long long ld, float* out, int accumulate, void* workspace);
+// g of element kind g_kind (0 = fp32, 1 = bf16, 2 = fp16), out of kind out_kind; fp32 accumulation
+int colsum_any(cudaStream_t s, int g_kind, const void* g, size_t rows, int cols, long long ld, void* out, int out_kind, int accumulate, void* workspace);
 // reduce a <= 4-d tensor over the axes where rdim == 1 (sum); out has rdim shape, contiguous
 int reduce_sum_bcast_f32(cudaStream_t s, const float* a, const int* adim, const int* astride, float* out, const int* rdim, float scale, int accumulate);
 
@@ -37,6 +43,10 @@ int pool_max_fwd_f32(cudaStream_t s, const PoolGeom& g, const float* a, float* b
 int pool_max_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, const float* a, const float* b, float* grad_a);
 int pool_avg_fwd_f32(cudaStream_t s, const PoolGeom& g, const float* a, float* b);
 int pool_avg_bwd_f32(cudaStream_t s, const PoolGeom& g, const float* grad_b, float* grad_a);
+int pool_max_fwd_16(cudaStream_t s, int kind, const PoolGeom& g, const void* a, void* b);
+int pool_max_bwd_16(cudaStream_t s, int kind, const PoolGeom& g, const void* grad_b, const void* a, const void* b, void* grad_a);
+int pool_avg_fwd_16(cudaStream_t s, int kind, const PoolGeom& g, const void* a, void* b);
+int pool_avg_bwd_16(cudaStream_t s, int kind, const PoolGeom& g, const void* grad_b, void* grad_a);
 
 // ---- batch norm over [outer, C, inner] (NHWC: inner = 1; NCHW: outer = N, inner = H * W) ----------------------
 // training forward: writes y, saved_mean, saved_inv_std and updates the running mean / var in place
@@ -50,6 +60,13 @@ int bn_fwd_test_f32(cudaStream_t s, const float* x, float* y, const float* scale
 // in front of it: g is masked by bn(x) > 0 on the fly (the mask is recomputed from x, bit-identical to the forward)
 // dx_colsum != NULL: also writes sum over rows of dx per channel (NHWC only; = the bias gradient of the convolution in front)
 int bn_bwd_f32(cudaStream_t s, const float* g, const float* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, float* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace, float* dx_colsum = 0);
+// the same on 16-bit activations (kind 1 = bf16, 2 = fp16): scale / bias / running and saved statistics / dscale / dbias stay fp32
+// (lib/nnc/ccv_cnnp_model_addons.c:954-956); dx_colsum is written in element kind colsum_kind (0 = fp32)
+int bn_fwd_train_16(cudaStream_t s, int kind, const void* x, void* y, const float* scale, const float* bias, float* running_mean, float* running_var, float* saved_mean, float* saved_inv_std, size_t outer, int C, size_t inner, float epsilon, float momentum, void* workspace, int fuse_relu, const float* ext_part = 0, int ext_rows = 0);
+int bn_fwd_test_16(cudaStream_t s, int kind, const void* x, void* y, const float* scale, const float* bias, const float* mean, const float* var, size_t outer, int C, size_t inner, float epsilon, void* workspace);
+int bn_bwd_16(cudaStream_t s, int kind, const void* g, const void* x, const float* scale, const float* bias, const float* saved_mean, const float* saved_inv_std, void* dx, float* dscale, float* dbias, size_t outer, int C, size_t inner, void* workspace, void* dx_colsum = 0, int colsum_kind = 0);
+int ew_add_relu_fwd_16(cudaStream_t s, int kind, const void* a, const void* b, void* out, size_t n);
+int ew_add_relu_bwd_16(cudaStream_t s, int kind, const void* a, const void* b, const void* y, void* out, size_t n);
 // out = relu(a + b); out = y > 0 ? a + b : 0  (residual block end, forward / backward)
 int ew_add_relu_fwd_f32(cudaStream_t s, const float* a, const float* b, float* out, size_t n);
 int ew_add_relu_bwd_f32(cudaStream_t s, const float* a, const float* b, const float* y, float* out, size_t n);
@@ -67,6 +84,10 @@ int softmax_cce_bwd_f32(cudaStream_t s, const float* g, const void* label, int l
 // ---- SGD ------------------------------------------------------------------------------------------------------
 int sgd_f32(cudaStream_t s, const float* g, const float* a, const float* m, float* b, float* n, size_t count, int nesterov, float rate, float scale, float decay, float momentum, float dampening);
 
+// g of element kind g_kind (0 = fp32, 1 = bf16, 2 = fp16) with fp32 parameters / momenta: the reference's mixed-precision form
+// (sgd/gpu/ccv_nnc_sgd_gpu_ref.cu:71-74)
+int sgd_any(cudaStream_t s, int g_kind, const void* g, const float* a, const float* m, float* b, float* n, size_t count, int nesterov, float rate, float scale, float decay, float momentum, float dampening);
+int sgd_multi_any(cudaStream_t s, int tensors, int g_kind, const void* const* g, const float* const* a, const float* const* m, float* const* b, float* const* n, const size_t* counts, int nesterov, float rate, float scale, float decay, float momentum, float dampening);
 // `tensors` independent SGD updates with the same hyper-parameters in ceil(tensors / 32) launches
 int sgd_multi_f32(cudaStream_t s, int tensors, const float* const* g, const float* const* a, const float* const* m, float* const* b, float* const* n, const size_t* counts, int nesterov, float rate, float scale, float decay, float momentum, float dampening);
 

@@ -16,8 +16,26 @@
 // LDTM -> STS -> LDS -> STG chain was latency-bound, profiles/r01_ncu_gemm_n256k64_persistent_4epiwarps.txt).
 #pragma once
 #include "sm100_umma_gemm.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace sm100 {
+
+// 16-bit output helpers (OUT16 kernels): kind 1 = bf16, 2 = fp16, round to nearest even
+__device__ __forceinline__ uint32_t pack16x2(const float a, const float b, const int kind)
+{
+	if (kind == 1)
+	{
+		const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+		return *reinterpret_cast<const uint32_t*>(&v);
+	}
+	const __half2 v = __floats2half2_rn(a, b);
+	return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float cvt16(const uint16_t x, const int kind)
+{
+	return kind == 1 ? __uint_as_float((uint32_t)x << 16) : __half2float(__ushort_as_half(x));
+}
 
 // X3 = 1 selects the error-compensated "3xTF32" form (CCV_NNC_SM100_ALGO_3XTF32): the operands arrive as raw fp32
 // (tensor map data type FLOAT32, no rounding), four extra warps split every staged element into hi = x with the low 13
@@ -43,7 +61,8 @@ struct UmmaPersistentSmem {
 	static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
-template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0>
+// OUT16 = 1: the output tensor (and an optional 16-bit bias) is bf16 / fp16 (p.out_kind); accumulation stays fp32 in TMEM.
+template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0, int OUT16 = 0>
 __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const UmmaGemmParams p)
 {
 	using S = UmmaPersistentSmem<BN, STAGES, EPIW, X3>;
@@ -124,30 +143,29 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 					uint8_t* sA = smem + stage * S::STAGE_BYTES;
 					uint8_t* sB = sA + S::A_BYTES;
 					mbar_expect_tx(&full_bar[stage], S::RAW_BYTES);
+					// bk = K elements per stage = MN elements per MN-major box (32 fp32 / 64 16-bit); every box row is 128 bytes
+					const int bk = p.bk;
 					if (AMODE == OP_K2D)
-						tma_load_2d(sA, &tmA, &full_bar[stage], chunk * UMMA_BLOCK_K, m0);
+						tma_load_2d(sA, &tmA, &full_bar[stage], chunk * bk, m0);
 					else if (AMODE == OP_MN2D) {
-#pragma unroll
-						for (int j = 0; j < UMMA_BLOCK_M / 32; j++)
-							tma_load_2d(sA + j * 4096, &tmA, &full_bar[stage], m0 + 32 * j, it * UMMA_BLOCK_K);
+						for (int j = 0; j * bk < UMMA_BLOCK_M; j++)
+							tma_load_2d(sA + j * p.mn_box_bytes, &tmA, &full_bar[stage], m0 + bk * j, it * bk);
 					} else
-						tma_load_im2col_4d(sA, &tmA, &full_bar[stage], chunk * UMMA_BLOCK_K, a_w, a_h, a_n, p.tap_off_w[tap], p.tap_off_h[tap]);
+						tma_load_im2col_4d(sA, &tmA, &full_bar[stage], chunk * bk, a_w, a_h, a_n, p.tap_off_w[tap], p.tap_off_h[tap]);
 					if (BMODE == OP_K2D)
-						tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_b_col[tap] + chunk * UMMA_BLOCK_K, n0);
+						tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_b_col[tap] + chunk * bk, n0);
 					else if (BMODE == OP_MN2D) {
-#pragma unroll
-						for (int j = 0; j < BN / 32; j++)
-							tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], p.tap_b_col[tap] + n0 + 32 * j, chunk * UMMA_BLOCK_K);
+						for (int j = 0; j * bk < BN; j++)
+							tma_load_2d(sB + j * p.mn_box_bytes, &tmB, &full_bar[stage], p.tap_b_col[tap] + n0 + bk * j, chunk * bk);
 					} else {
-						const int pix = it * UMMA_BLOCK_K;
+						const int pix = it * bk;
 						const int q = pix % p.Q;
 						const int t = pix / p.Q;
 						const int b_w = q * p.stride_w + p.base_w;
 						const int b_h = (t % p.P) * p.stride_h + p.base_h;
 						const int b_n = t / p.P;
-#pragma unroll
-						for (int j = 0; j < BN / 32; j++)
-							tma_load_im2col_4d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, b_w, b_h, b_n, p.tap_off_w[gtap], p.tap_off_h[gtap]);
+						for (int j = 0; j * bk < BN; j++)
+							tma_load_im2col_4d(sB + j * p.mn_box_bytes, &tmB, &full_bar[stage], n0 + bk * j, b_w, b_h, b_n, p.tap_off_w[gtap], p.tap_off_h[gtap]);
 					}
 					if (++stage == STAGES) { stage = 0; phase ^= 1; }
 				}
@@ -180,9 +198,13 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 #pragma unroll
 					for (int k = 0; k < UMMA_BLOCK_K / 8; k++)
 					{
-						const uint64_t da = (AMODE == OP_MN2D) ? umma_smem_desc(a_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
-						const uint64_t db = (BMODE == OP_K2D) ? umma_smem_desc(b_addr + k * 32, 16, 1024, 2) : umma_smem_desc(b_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout);
-						if (X3)
+						// one MMA covers 32 bytes of K (8 fp32 / 16 16-bit): K-major operands advance 32 B inside the swizzled row,
+						// MN-major ones by UMMA_K k-rows of 128 B (p.mn_step)
+						const uint64_t da = (AMODE == OP_MN2D) ? umma_smem_desc(a_addr + k * p.mn_step, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
+						const uint64_t db = (BMODE == OP_K2D) ? umma_smem_desc(b_addr + k * 32, 16, 1024, 2) : umma_smem_desc(b_addr + k * p.mn_step, p.mn_lbo, p.mn_sbo, p.mn_layout);
+						if (!X3 && p.kind16)
+							umma_f16(tmem_d, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+						else if (X3)
 						{
 							// the lo tiles sit RAW_BYTES behind their hi tiles (same layout): small terms first, then hi * hi
 							constexpr uint64_t LO = (uint64_t)(S::RAW_BYTES >> 4); // start-address field is in 16-byte units
@@ -248,6 +270,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 		const int sub_col = (lane & 7) * 4;  // 0..28: first of this lane's 4 columns
 		const bool accumulate = p.accumulate != 0;
 		const float* const bias = p.bias;
+		const uint16_t* const bias16 = OUT16 && !p.bias ? reinterpret_cast<const uint16_t*>(p.bias16) : 0;
 		const int N = p.N;
 		// statistics slots of this warp quarter: plane 0 of row blockIdx.x * 4 + quarter (count); planes k, s1, s2 follow at stats_plane.
 		// The launcher makes gridDim.x a multiple of tiles_n, so every tile of this CTA covers the same columns: the shifted sums of
@@ -276,7 +299,8 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 			const uint32_t acc_phase = (t >> 1) & 1;
 			const bool add_bias = bias != 0 && split == 0;
 			// output row pointers of the 8 rows this lane writes (rows sub_row + 4 * i of the warp's 32-row band)
-			float* orow[8];
+			constexpr int OSZ = OUT16 ? 2 : 4; // bytes per output element
+			char* orow[8];
 #pragma unroll
 			for (int i = 0; i < 8; i++)
 			{
@@ -292,7 +316,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 					const int jj = rem - ii * p.rowmap.Qc;
 					off = n * p.rowmap.n_stride + ii * p.rowmap.h_stride + jj * p.rowmap.w_stride;
 				}
-				orow[i] = row < p.M ? p.out + off + (long long)gtap * p.grid_tap_out_stride + (long long)split * p.split_out_stride : 0;
+				orow[i] = row < p.M ? reinterpret_cast<char*>(p.out) + (off + (long long)gtap * p.grid_tap_out_stride + (long long)split * p.split_out_stride) * OSZ : 0;
 			}
 			mbar_wait(&tmem_full_bar[acc], acc_phase);
 			tc_fence_after();
@@ -333,25 +357,54 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 								const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
 								v[i] += b4.x, v[i + 1] += b4.y, v[i + 2] += b4.z, v[i + 3] += b4.w;
 							}
-					}
+					} else if (OUT16 && bias16 && split == 0) {
 #pragma unroll
-					for (int j = 0; j < 8; j++)
-						*reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+						for (int i = 0; i < 32; i += 8)
+							if (col0 + i < N)
+							{
+								const uint4 b8 = __ldg(reinterpret_cast<const uint4*>(bias16 + col0 + i));
+								const uint32_t w[4] = { b8.x, b8.y, b8.z, b8.w };
+#pragma unroll
+								for (int j = 0; j < 4; j++)
+									v[i + 2 * j] += cvt16((uint16_t)(w[j] & 0xffffu), p.out_kind), v[i + 2 * j + 1] += cvt16((uint16_t)(w[j] >> 16), p.out_kind);
+							}
+					}
+					if (!OUT16)
+					{
+#pragma unroll
+						for (int j = 0; j < 8; j++)
+							*reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					} else {
+						// 32 rows x 64 bytes in the 64-byte-swizzled layout of the 16-bit output map: 16-byte unit u of row r sits at
+						// unit u ^ ((r >> 1) & 3) (8 consecutive lanes then cover all 32 banks: conflict-free 128-bit stores)
+						char* const b8 = reinterpret_cast<char*>(buf) + lane * 64;
+#pragma unroll
+						for (int j = 0; j < 4; j++)
+							*reinterpret_cast<uint4*>(b8 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pack16x2(v[8 * j], v[8 * j + 1], p.out_kind), pack16x2(v[8 * j + 2], v[8 * j + 3], p.out_kind),
+								pack16x2(v[8 * j + 4], v[8 * j + 5], p.out_kind), pack16x2(v[8 * j + 6], v[8 * j + 7], p.out_kind));
+					}
 					fence_proxy_async();
 					__syncwarp();
 					const int valid = min(32, p.M - (m0 + quarter * 32)); // rows of this chunk inside the tensor (the store clips the rest)
 					if (stats && valid > 0)
 					{
 						// lane = column: fold the staged rows of this column into this thread's running shifted sums (all lanes read the
-						// same 128-byte row: no bank conflict).  k is the first value the thread ever saw for the column.
+						// same row: no bank conflict).  k is the first value the thread ever saw for the column.  16-bit outputs are
+						// read back as stored (rounded): the statistics describe the tensor the batch norm will normalise.
 						const int ci = (c - half) / (EPIW / 4);
-						const float k = st_n > 0.f ? st_k[ci] : buf[lane];
+						const uint16_t* const buf16 = reinterpret_cast<const uint16_t*>(buf);
+						auto staged = [&](const int rr) -> float {
+							if (!OUT16)
+								return buf[rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3)];
+							return cvt16(buf16[rr * 32 + ((((lane >> 3) ^ ((rr >> 1) & 3))) << 3) + (lane & 7)], p.out_kind);
+						};
+						const float k = st_n > 0.f ? st_k[ci] : staged(0);
 						float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
 						for (int rr = 0; rr < 32; rr++)
 							if (rr < valid)
 							{
-								const float d = buf[rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3)] - k;
+								const float d = staged(rr) - k;
 								s1 += d;
 								s2 = fmaf(d, d, s2);
 							}
@@ -381,6 +434,11 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 					bias4.y = col + 1 < N ? __ldg(bias + col + 1) : 0.f;
 					bias4.z = col + 2 < N ? __ldg(bias + col + 2) : 0.f;
 					bias4.w = col + 3 < N ? __ldg(bias + col + 3) : 0.f;
+				} else if (OUT16 && bias16 && split == 0) {
+					bias4.x = cvt16(__ldg(bias16 + col), p.out_kind);
+					bias4.y = col + 1 < N ? cvt16(__ldg(bias16 + col + 1), p.out_kind) : 0.f;
+					bias4.z = col + 2 < N ? cvt16(__ldg(bias16 + col + 2), p.out_kind) : 0.f;
+					bias4.w = col + 3 < N ? cvt16(__ldg(bias16 + col + 3), p.out_kind) : 0.f;
 				}
 #pragma unroll
 				for (int i = 0; i < 8; i++)
@@ -389,20 +447,41 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 						continue;
 					float4 v = *reinterpret_cast<const float4*>(scratch + (sub_row + 4 * i) * S::EPI_PITCH + sub_col);
 					v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
-					float* const o = orow[i] + col;
-					if (full4 && ((((uintptr_t)o) & 15) == 0))
+					char* const ob = orow[i] + (long long)col * OSZ;
+					if (!OUT16)
 					{
-						if (accumulate)
+						float* const o = reinterpret_cast<float*>(ob);
+						if (full4 && ((((uintptr_t)o) & 15) == 0))
 						{
-							const float4 e = *reinterpret_cast<const float4*>(o);
-							v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
+							if (accumulate)
+							{
+								const float4 e = *reinterpret_cast<const float4*>(o);
+								v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
+							}
+							*reinterpret_cast<float4*>(o) = v;
+						} else {
+							const float vv[4] = { v.x, v.y, v.z, v.w };
+							for (int j = 0; j < 4; j++)
+								if (col + j < N)
+									o[j] = accumulate ? o[j] + vv[j] : vv[j];
 						}
-						*reinterpret_cast<float4*>(o) = v;
 					} else {
-						const float vv[4] = { v.x, v.y, v.z, v.w };
-						for (int j = 0; j < 4; j++)
-							if (col + j < N)
-								o[j] = accumulate ? o[j] + vv[j] : vv[j];
+						uint16_t* const o = reinterpret_cast<uint16_t*>(ob);
+						if (full4 && ((((uintptr_t)o) & 7) == 0))
+						{
+							if (accumulate)
+							{
+								const uint2 e = *reinterpret_cast<const uint2*>(o);
+								v.x += cvt16((uint16_t)(e.x & 0xffffu), p.out_kind), v.y += cvt16((uint16_t)(e.x >> 16), p.out_kind);
+								v.z += cvt16((uint16_t)(e.y & 0xffffu), p.out_kind), v.w += cvt16((uint16_t)(e.y >> 16), p.out_kind);
+							}
+							*reinterpret_cast<uint2*>(o) = make_uint2(pack16x2(v.x, v.y, p.out_kind), pack16x2(v.z, v.w, p.out_kind));
+						} else {
+							const float vv[4] = { v.x, v.y, v.z, v.w };
+							for (int j = 0; j < 4; j++)
+								if (col + j < N)
+									o[j] = (uint16_t)(pack16x2(accumulate ? cvt16(o[j], p.out_kind) + vv[j] : vv[j], 0.f, p.out_kind) & 0xffffu);
+						}
 					}
 				}
 				}

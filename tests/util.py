@@ -82,3 +82,65 @@ def assert_close(got, want, tol, what=""):
     assert np.isfinite(got).all(), what + ": non-finite output"
     e = rel_err(got, want)
     assert e <= tol, "%s: normalised max error %.3e > %.1e" % (what, e, tol)
+
+
+# ---- 16-bit tensors: bf16 travels as uint16 (numpy has no bfloat16), fp16 as numpy float16 ------------------------------
+def to_bf16(a):
+    """fp32 -> bf16 bits (uint16), round to nearest even."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    return r.reshape(np.shape(a))
+
+
+def from_bf16(u):
+    return (np.ascontiguousarray(u, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32).reshape(np.shape(u))
+
+
+def round16(a, kind):
+    """The fp32 values a 16-bit tensor of this kind (abi.CCV_16BF / abi.CCV_16F) actually holds."""
+    return from_bf16(to_bf16(a)) if kind == abi.CCV_16BF else np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+def pack16(a, kind):
+    return to_bf16(a) if kind == abi.CCV_16BF else np.asarray(a, np.float32).astype(np.float16)
+
+
+def unpack16(u, kind):
+    return from_bf16(u) if kind == abi.CCV_16BF else np.asarray(u, np.float16).astype(np.float32)
+
+
+def gpu_exec16(nnc, cmd, hint, flags, in_arrays, out_arrays, kind, keep32=(), stream=None):
+    """gpu_exec with fp32 numpy arrays travelling as 16-bit tensors of `kind`.  `keep32`: ids (id(array)) of operands that stay
+    fp32 (batch-norm parameters / statistics, fp32 master weights of SGD).  Integer arrays travel unchanged.  The same array
+    object in both lists is the same GPU tensor.  Returns (status, [fp32 output arrays])."""
+    cache = {}
+
+    def tensor_for(a):
+        if a is None:
+            return None
+        if id(a) not in cache:
+            if a.dtype != np.float32 or id(a) in keep32:
+                t = nnc.gpu_tensor(list(a.shape), NHWC, NP_TO_CCV[a.dtype])
+                t.upload(a)
+            else:
+                t = nnc.gpu_tensor(list(a.shape), NHWC, kind)
+                t.upload(pack16(a, kind))
+            cache[id(a)] = t
+        return cache[id(a)]
+
+    ins = [tensor_for(a) for a in in_arrays]
+    outs = [tensor_for(a) for a in out_arrays]
+    status = nnc.cmd_exec(cmd, hint, flags, ins, outs, stream)
+    if stream is not None:
+        stream.wait()
+    results = []
+    for t in outs:
+        if t is None:
+            results.append(None)
+        elif (t.params.datatype & 0xFF000) in (abi.CCV_16BF, abi.CCV_16F):
+            results.append(unpack16(t.download(), t.params.datatype & 0xFF000))
+        else:
+            results.append(t.download())
+    for t in cache.values():
+        t.free()
+    return status, results
