@@ -133,37 +133,24 @@ def cpu_baseline(image):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="sm100")
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE: 256)")
-    ap.add_argument("--image", type=int, default=224)
-    ap.add_argument("--no-cuda-graph", action="store_true")
-    ap.add_argument("--no-fuse", action="store_true", help="run every reference command as its own kernel sequence (no peephole fusion)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--per-op", default="", help="write the per-command profile to this JSON file")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return reference_arm(args)
-    args.warmup = max(args.warmup, 3)
+DTYPES = {"f32": 0x04000, "bf16": 0x80000, "f16": 0x20000}
+MATH = {"f32": {-1: "tcgen05 kind::tf32, fp32 accumulate (TMA rounds operands to TF32); the dense layer 3xTF32", 0: "tcgen05 kind::tf32, fp32 accumulate (TMA rounds operands to TF32)",
+                1: "3xTF32: three tcgen05 kind::tf32 MMAs on (hi, lo) operand splits, fp32 accumulate", 2: "CUDA-core fp32 FFMA"},
+        "bf16": "tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM", "f16": "tcgen05 kind::f16 (fp16 operands), fp32 accumulate in TMEM"}
 
-    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+def to_bf16(a):
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
+
+
+def run_model(args, dist, rank, world, local_rank, dtype="f32", algorithm=-1, per_op_path=""):
+    """One measured configuration of the ResNet-50 step: returns the JSON object (rank 0 fills roofline / per_op)."""
     from ccv_b200 import nnc, resnet50
-    nnc.init()
-    if nnc.lib().ccv_nnc_device_count(nnc.CCV_STREAM_CONTEXT_GPU) <= 0:
-        raise SystemExit("bench.py: no CUDA device and there is no CPU fallback (use --impl reference for the CPU_REF arm)")
     device = local_rank
+    dt = DTYPES[dtype]
     stream = nnc.Stream(device)
-    net = resnet50.Net(args.batch, image=args.image, classes=1000, device=device, global_batch=args.batch * world, learn_rate=4e-5)  # 0.4 * 0.0001: the first warm-up rate of bin/nnc/imagenet.c:296-312
+    net = resnet50.Net(args.batch, image=args.image, classes=1000, device=device, global_batch=args.batch * world, learn_rate=4e-5, algorithm=algorithm, dtype=dt)  # 0.4 * 0.0001: the first warm-up rate of bin/nnc/imagenet.c:296-312
     g_fb, g_opt = nnc.Graph(), nnc.Graph()
     for cmd, hint, flags, ins, outs in net.fwd + net.bwd:
         g_fb.exec_new(cmd, hint, flags, ins, outs)
@@ -171,20 +158,21 @@ def main():
         g_opt.exec_new(cmd, hint, flags, ins, outs)
     n_fused = 0 if args.no_fuse else g_fb.fuse() + g_opt.fuse()
 
-    # synthetic batch in pinned host memory (for the e2e leg) and resident in HBM (for `value`)
+    # synthetic batch in pinned host memory (for the e2e leg) and resident in HBM (for `value`); a 16-bit model takes a 16-bit batch
     rs = np.random.RandomState(1234 + rank)
-    host_in = nnc.cpu_tensor([args.batch, args.image, args.image, 3])
+    host_in = nnc.cpu_tensor([args.batch, args.image, args.image, 3], datatype=dt)
     host_lab = nnc.cpu_tensor([args.batch], datatype=nnc.CCV_32S)
     host_loss = nnc.cpu_tensor([args.batch])
     for t in (host_in, host_lab, host_loss):
         nnc.lib().ccv_nnc_tensor_pin_memory(t.ptr)
-    host_in.upload(rs.rand(args.batch, args.image, args.image, 3).astype(np.float32))
+    img = rs.rand(args.batch, args.image, args.image, 3).astype(np.float32)
+    host_in.upload(img if dtype == "f32" else to_bf16(img) if dtype == "bf16" else img.astype(np.float16))
     host_lab.upload(rs.randint(0, 1000, size=(args.batch,)).astype(np.int32))
     xfer = nnc.CMD_DATA_TRANSFER_FORWARD()
     assert nnc.cmd_exec(xfer, None, 0, [host_in, host_lab], [net.input, net.labels], stream) == 0
     stream.wait()
 
-    # the single gradient exchange: ONE CCV_NNC_COMM_ALLREDUCE_FORWARD command of the backend over the flat gradient buffer
+    # the single gradient exchange: ONE CCV_NNC_COMM_ALLREDUCE_FORWARD command of the backend over the flat gradient buffer(s)
     # (NCCL inside the library; torch.distributed only carries the communicator id, the barrier and the max-over-ranks time)
     allreduce = None
     if world > 1:
@@ -249,7 +237,7 @@ def main():
     # the staged batch into the network's input tensor.  Steady state: one host-to-device copy and one loss read per step, all
     # inside the timed region; the first batch is staged before the clock starts, the prefetch of one extra batch is inside it.
     copy_stream = nnc.Stream(device)
-    stage_in = nnc.gpu_tensor([args.batch, args.image, args.image, 3], device=device)
+    stage_in = nnc.gpu_tensor([args.batch, args.image, args.image, 3], datatype=dt, device=device)
     stage_lab = nnc.gpu_tensor([args.batch], datatype=nnc.CCV_32S, device=device)
     staged, consumed = nnc.Signal(device), nnc.Signal(device)
 
@@ -276,23 +264,159 @@ def main():
 
     images_per_step = args.batch * world
     value = images_per_step / (ms_per_step * 1e-3)
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c:17-95) fp32 NHWC, per-GPU batch %d, %dx%d, fwd+bwd + nesterov SGD%s" % (args.batch, args.image, args.image, ", one COMM_ALLREDUCE command (NCCL sum) over the flat fp32 gradient buffer" if world > 1 else ""),
-                      "global_batch": images_per_step, "parallelism": "dp%d" % world, "tensor_core_math": "tcgen05 kind::tf32, fp32 accumulate (TMA rounds operands to TF32)",
-                      "cuda_graph": use_graph, "fused_pairs": n_fused, "first_step_loss": first_loss, "l2": "activations per step (>20 GB) exceed the 126 MB L2: no flush needed", "mean_loss": loss},
+    math = MATH[dtype][algorithm] if dtype == "f32" else MATH[dtype]
+    exchange = ""
+    if world > 1:
+        exchange = ", one COMM_ALLREDUCE command (NCCL sum) over the flat %s gradient buffer%s" % ("fp32" if dtype == "f32" else dtype, "" if dtype == "f32" else " (+ the small fp32 batch-norm gradient buffer, same NCCL group)")
+    out = {"metric": METRIC if dtype == "f32" else METRIC.replace("fp32", dtype), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+           "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c:17-95) %s NHWC, per-GPU batch %d, %dx%d, fwd+bwd + nesterov SGD%s%s" % (
+                          "fp32" if dtype == "f32" else dtype + " activations / filters / gradients, fp32 master weights + batch-norm parameters", args.batch, args.image, args.image,
+                          "" if dtype == "f32" else " (mixed precision)", exchange),
+                      "global_batch": images_per_step, "parallelism": "dp%d" % world, "tensor_core_math": math,
+                      "cuda_graph": use_graph, "fused_pairs": n_fused, "first_step_loss": first_loss, "l2": "activations per step (>10 GB) exceed the 126 MB L2: no flush needed", "mean_loss": loss},
            "e2e": {"value": images_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes + host_lab.nbytes), "d2h_bytes_per_step": int(host_loss.nbytes), "ms_per_step": e2e_ms,
                    "pipeline": "batch k+1 is copied host->device on a second stream context while step k computes (stream signals); one pinned-host copy + one loss read per step inside the timed region"},
            "gpu_launches": int(launches_per_step * (args.steps * 2 + args.warmup + 2)), "gpu_launches_per_step": int(launches_per_step), "clocks": sampler.summary()}
-
     if rank == 0:
         # per-command profile (eager, CUDA events around every command) -> roofline of the dominant kernel
         pk = peaks()
-        prof = profile_nodes(nnc, net, (g_fb, g_opt), stream, pk)
+        prof = profile_nodes(nnc, net, (g_fb, g_opt), stream, pk, dtype, algorithm)
         out["roofline"] = prof["roofline"]
         out["per_op"] = prof["summary"]
-        if args.per_op:
-            json.dump(prof, open(args.per_op, "w"), indent=1)
+        if per_op_path:
+            json.dump(prof, open(per_op_path, "w"), indent=1)
+    for x in (g_fb, g_opt, net, stage_in, stage_lab, host_in, host_lab, host_loss, copy_stream, stream):
+        x.free()
+    return out
+
+
+def run_sdpa_cfg5(args):
+    """BASELINE.json configs[4]: CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD bf16 B=32 H=16 S=2048 D=128, non-causal and causal,
+    scale 1/sqrt(128), through ccv_nnc_cmd_exec; q / k / v are the reference's i / count ramps (test/int/nnc/cublas.tests.c:2786-2794)
+    rounded to bf16.  Per variant: device-timed (CUDA events) with the operands resident in HBM, and end to end from pinned host
+    buffers (the three 268 MB operands in, the 268 MB result out, every step, inside the timed region)."""
+    from ccv_b200 import abi, nnc
+    B, H, S, D = 32, 16, 2048, 128
+    stream = nnc.Stream(0)
+    pk = peaks()
+    n = B * S * H * D
+    ramp = to_bf16((np.arange(n, dtype=np.float64) / n).astype(np.float32)).reshape(B, S, H, D)
+    dev = [nnc.gpu_tensor([B, S, H, D], datatype=abi.CCV_16BF) for _ in range(4)]
+    host = [nnc.cpu_tensor([B, S, H, D], datatype=abi.CCV_16BF) for _ in range(4)]
+    for t in host:
+        nnc.lib().ccv_nnc_tensor_pin_memory(t.ptr)
+    for t in host[:3]:
+        t.upload(ramp)
+    lse = nnc.gpu_tensor([B, H, S])
+    xfer = nnc.CMD_DATA_TRANSFER_FORWARD()
+    assert nnc.cmd_exec(xfer, None, 0, host[:3], dev[:3], stream) == 0
+    sampler = ClockSampler(0)
+    sampler.start()
+    out = {}
+    for causal in (0, 1):
+        cmd = nnc._simple(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD)
+        cmd.info.scaled_dot_product_attention.scale = 1.0 / np.sqrt(D)
+        cmd.info.scaled_dot_product_attention.is_causal = causal
+
+        def fwd():
+            assert nnc.cmd_exec(cmd, None, 0, dev[:3], [dev[3], lse], stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+
+        def e2e():
+            nnc.cmd_exec(xfer, None, 0, host[:3], dev[:3], stream)
+            fwd()
+            nnc.cmd_exec(xfer, None, 0, [dev[3]], [host[3]], stream)
+        res = {}
+        for name, fn, reps in (("device", fwd, 20), ("e2e", e2e, 5)):
+            for _ in range(3):
+                fn()
+            e0, e1 = nnc.Event(), nnc.Event()
+            stream.wait()
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            res[name] = e0.elapsed_ms(e1) / reps
+        flops = 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
+        byts = 4.0 * n * 2 + B * H * S * 4
+        ms = res["device"]
+        out["causal" if causal else "full"] = {
+            "ms": ms, "tflops": flops / ms * 1e-9, "frac_of_bf16_peak": flops / ms * 1e-9 / pk["bf16_tflops"], "gbs": byts / ms * 1e-6, "frac_of_hbm_peak": byts / ms * 1e-6 / pk["hbm_gbs"],
+            "algorithmic_flops": flops, "algorithmic_bytes": byts, "l2": "Q + K + V + O = 1.07 GB per launch: larger than the 126 MB L2",
+            "e2e": {"ms": res["e2e"], "tflops": flops / res["e2e"] * 1e-9, "h2d_bytes_per_step": int(3 * n * 2), "d2h_bytes_per_step": int(n * 2)}}
+    sampler.stop_flag = True
+    sampler.join()
+    out["clocks"] = sampler.summary()
+    out["workload"] = "CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD bf16 B=32 H=16 S=2048 D=128 (BASELINE.json configs[4]), tcgen05 flash-attention kernel, LSE written"
+    for t in dev + host + [lse, stream]:
+        t.free()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sm100")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE: 256)")
+    ap.add_argument("--image", type=int, default=224)
+    ap.add_argument("--dtype", default="f32", choices=sorted(DTYPES), help="headline model dtype (the JSON line's own numbers); the other configurations ride along under `variants`")
+    ap.add_argument("--algorithm", type=int, default=-1, help="fp32 contraction algorithm: -1 default (convolutions TF32, GEMM 3xTF32), 0 TF32, 1 3xTF32, 2 FFMA")
+    ap.add_argument("--workload", default="resnet50", choices=["resnet50", "sdpa_cfg5"])
+    ap.add_argument("--no-variants", action="store_true", help="only the headline configuration")
+    ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="run every reference command as its own kernel sequence (no peephole fusion)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-op", default="", help="write the per-command profile to this JSON file")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ccv_b200 import nnc
+    nnc.init()
+    if nnc.lib().ccv_nnc_device_count(nnc.CCV_STREAM_CONTEXT_GPU) <= 0:
+        raise SystemExit("bench.py: no CUDA device and there is no CPU fallback (use --impl reference for the CPU_REF arm)")
+    if args.workload == "sdpa_cfg5":
+        if rank == 0:
+            r = run_sdpa_cfg5(args)
+            full = r["full"]
+            print(json.dumps({"metric": "sdpa_fwd_bf16_b32_h16_s2048_d128_tflops", "value": full["tflops"], "unit": "TFLOP/s", "n_gpus": 1, "steps": 20, "warmup": 3, "ms_per_step": full["ms"], "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": {"workload": r["workload"]},
+                              "roofline": {"bound": "tensor", "achieved": full["tflops"], "peak": peaks()["bf16_tflops"], "unit": "TFLOP/s", "frac": full["frac_of_bf16_peak"], "traffic": None},
+                              "e2e": {"value": full["e2e"]["tflops"], "unit": "TFLOP/s", "h2d_bytes_per_step": full["e2e"]["h2d_bytes_per_step"], "d2h_bytes_per_step": full["e2e"]["d2h_bytes_per_step"]},
+                              "gpu_launches": 2 * (23 + 8), "sdpa": r, "clocks": r["clocks"]}))
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    out = run_model(args, dist, rank, world, local_rank, args.dtype, args.algorithm, args.per_op)
+    if not args.no_variants:
+        # the other BASELINE configurations, measured by the same code in the same process (same box, same clocks):
+        #   bf16     configs[3] (ResNet-50 16-bit, batch-sharded): at N GPUs this IS configs[3]'s per-GPU shard of N x 256 images
+        #   3xtf32   the fp32 model with fp32-grade (error-compensated) convolutions: what the <= 1e-3 whole-model parity is held on
+        #   sdpa     configs[4] (N = 1 only: a single-op config, replicas add nothing)
+        variants = {}
+        for name, (dtype, algorithm) in (("bf16", ("bf16", -1)), ("fp32_3xtf32", ("f32", 1))):
+            if dtype == args.dtype and algorithm == args.algorithm:
+                continue
+            v = run_model(args, dist, rank, world, local_rank, dtype, algorithm)
+            variants[name] = {k: v[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "config", "e2e", "gpu_launches_per_step", "clocks") if k in v}
+            if "roofline" in v:
+                variants[name]["roofline"], variants[name]["per_op"] = v["roofline"], v["per_op"]
+        if world == 1 and rank == 0:
+            variants["sdpa_cfg5"] = run_sdpa_cfg5(args)
+        out["variants"] = variants
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.image)
         print(json.dumps(out))
@@ -334,7 +458,7 @@ def node_cost(cmd, fused_kind, ins, outs):
     return names.get(c, "other"), 0.0, io
 
 
-def profile_nodes(nnc, net, graphs, stream, pk):
+def profile_nodes(nnc, net, graphs, stream, pk, dtype="f32", algorithm=-1):
     """Every node of one step run on its own with CUDA events around it (best of 3), through the same runner."""
     by_ptr = dict((t.ptr, t) for t in net.tensors)
     rows = []
@@ -350,11 +474,14 @@ def profile_nodes(nnc, net, graphs, stream, pk):
         s["ms"] += r["ms"]
         s["flops"] += r["flops"]
         s["bytes"] += r["bytes"]
-    tf32_peak = pk["bf16_tflops"] / 2.0
+    # tensor peak of the math the contractions run in: bf16 / fp16 = the measured cuBLAS bf16 number; TF32 = half of it;
+    # 3xTF32 = a third of the TF32 rate (three MMAs per product)
+    tf32_peak = pk["bf16_tflops"] if dtype != "f32" else pk["bf16_tflops"] / 2.0 / (3.0 if algorithm == 1 else 1.0)
+    peak_note = "bf16 cuBLAS burst peak" if dtype != "f32" else ("bf16 cuBLAS burst peak / 2 (TF32 tensor rate is half the bf16 rate)" + (" / 3 (3xTF32 issues three MMAs per product)" if algorithm == 1 else ""))
     for k, s in summary.items():
         if s["flops"] > 0:
             s["tflops"] = s["flops"] / (s["ms"] * 1e-3) / 1e12
-            s["frac_of_tf32_peak"] = s["tflops"] / tf32_peak
+            s["frac_of_tensor_peak"] = s["tflops"] / tf32_peak
         s["gbs"] = s["bytes"] / (s["ms"] * 1e-3) / 1e9
         s["frac_of_hbm_peak"] = s["gbs"] / pk["hbm_gbs"]
     tc = [r for r in rows if r["flops"] > 0]
@@ -368,9 +495,11 @@ def profile_nodes(nnc, net, graphs, stream, pk):
         traffic, traffic_note = float(t["dram_bytes_per_step"]), "dram__bytes_read.sum + dram__bytes_write.sum over the %d contraction launches of one step (ncu --set full, profiles/r01_contraction_traffic.json)" % t["launches"]
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "umma_* (tcgen05 kind::tf32 GEMM / implicit-GEMM convolution kernels; all convolution + GEMM commands of one step)", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+    if dtype != "f32" or algorithm == 1:
+        traffic, traffic_note = None, None  # the committed ncu capture is of the fp32 / TF32 configuration
+    roofline = {"bound": "tensor", "kernel": "umma_* (tcgen05 GEMM / implicit-GEMM convolution kernels; all convolution + GEMM commands of one step)", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": achieved / tf32_peak, "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes_per_step": sum(r["bytes"] for r in tc),
-                "peak_source": "%s bf16 cuBLAS burst peak / 2 (TF32 tensor rate is half the bf16 rate)" % pk["source"],
+                "peak_source": "%s %s" % (pk["source"], peak_note),
                 "launch_ms_total": tc_ms, "algorithmic_flops_per_step": tc_flops, "total_ms_all_commands": sum(r["ms"] for r in rows)}
     return dict(roofline=roofline, summary=summary, rows=rows)
 

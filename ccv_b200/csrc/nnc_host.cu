@@ -31,9 +31,30 @@ struct ccv_nnc_stream_context_s {
 
 namespace {
 
-// dispatch table: cmd id -> registry record of the (single) GPU_SM100 backend
-std::unordered_map<uint32_t, ccv_nnc_cmd_backend_registry_t> g_registry;
+// The registry of lib/nnc/ccv_nnc_cmd.c:27-66: init_map[command slot].backends[backend slot], both slots found by the generated
+// perfect hashes (lib/nnc/cmd/ccv_nnc_cmd.inc:152-190; here nnc_registry_generated.inc, written by tools/gen_backend_ph.py:
+// the reference's own command hash and the 8-slot backend hash that includes CCV_NNC_BACKEND_GPU_SM100).  Only the SM100 column
+// is ever filled in this stand-alone host -- the other seven backends are the reference's -- but lookup, capability matching and
+// the backend preference order are the reference's code paths, slot for slot.
+#include "nnc_registry_generated.inc"
+struct sm100_cmd_init_t {
+	const char* name;
+	uint32_t cmd;
+	ccv_nnc_cmd_backend_registry_t backends[CCV_NNC_SM100_BACKEND_SLOTS];
+};
+sm100_cmd_init_t init_map[CCV_NNC_SM100_CMD_SLOTS];
 std::once_flag g_init_once;
+
+// registry record of (cmd, backend), or NULL when either id is not one the tables know
+const ccv_nnc_cmd_backend_registry_t* registry_of(const uint32_t cmd, const uint32_t backend)
+{
+	const int cmd_idx = _ccv_nnc_cmd_ph(cmd), backend_idx = _ccv_nnc_cmd_backend_ph(backend);
+	if (cmd_idx < 0 || cmd_idx >= CCV_NNC_SM100_CMD_SLOTS || init_map[cmd_idx].cmd != cmd)
+		return 0;
+	if (backend_idx < 0 || backend_idx >= CCV_NNC_SM100_BACKEND_SLOTS || sm100_backend_init_map[backend_idx].backend != backend)
+		return 0;
+	return &init_map[cmd_idx].backends[backend_idx];
+}
 
 enum { MATRIX_DENSE = 0x00100000, UNMANAGED = 0x20000000, NO_DATA_ALLOC = 0x10000000 };
 
@@ -99,7 +120,11 @@ extern "C" {
 void ccv_nnc_init(void)
 {
 	std::call_once(g_init_once, []() {
-#define CCV_SM100_CALL_REGISTER(cmd) { ccv_nnc_cmd_backend_registry_t r; memset(&r, 0, sizeof(r)); _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(&r); g_registry[(uint32_t)cmd] = r; }
+		memset(init_map, 0, sizeof(init_map));
+		for (int i = 0; i < CCV_NNC_SM100_CMD_SLOTS; i++)
+			init_map[i].name = sm100_cmd_init_map[i].name, init_map[i].cmd = sm100_cmd_init_map[i].cmd;
+		// what the generated _ccv_nnc_cmd_init() does for every (command, backend) pair (integration/ccv_nnc_cmd_sm100_init.inc)
+#define CCV_SM100_CALL_REGISTER(cmd) _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(&init_map[_ccv_nnc_cmd_ph((uint32_t)cmd)].backends[_ccv_nnc_cmd_backend_ph(CCV_NNC_BACKEND_GPU_SM100)]);
 		CCV_NNC_SM100_COMMANDS(CCV_SM100_CALL_REGISTER)
 #undef CCV_SM100_CALL_REGISTER
 	});
@@ -121,11 +146,10 @@ int ccv_nnc_cmd_ok(const uint32_t cmd, const uint32_t backend)
 {
 	if (cmd == CCV_NNC_NOOP)
 		return 1;
-	if (backend != CCV_NNC_BACKEND_GPU_SM100 && backend != CCV_NNC_NO_BACKEND)
-		return 0;
 	ccv_nnc_init();
-	auto it = g_registry.find(cmd);
-	return it != g_registry.end() && it->second.exec != 0;
+	// lib/nnc/ccv_nnc_cmd.c:117-131
+	const ccv_nnc_cmd_backend_registry_t* const r = registry_of(cmd, backend == CCV_NNC_NO_BACKEND ? (uint32_t)CCV_NNC_BACKEND_GPU_SM100 : backend);
+	return r && r->exec != 0;
 }
 
 uint32_t ccv_nnc_cmd_find_backend(const ccv_nnc_cmd_t cmd, const int tensor_memory, const int tensor_formats, const int tensor_datatypes)
@@ -133,12 +157,17 @@ uint32_t ccv_nnc_cmd_find_backend(const ccv_nnc_cmd_t cmd, const int tensor_memo
 	if (cmd.cmd == CCV_NNC_NOOP || cmd.cmd == CCV_NNC_CUSTOM_FORWARD || cmd.cmd == CCV_NNC_CUSTOM_BACKWARD)
 		return cmd.backend;
 	ccv_nnc_init();
-	auto it = g_registry.find(cmd.cmd);
-	if (it == g_registry.end())
+	// lib/nnc/ccv_nnc_cmd.c:307-328: the first backend slot, in table order, whose record has a kernel and covers every memory
+	// kind, format and datatype of the operands
+	const int cmd_idx = _ccv_nnc_cmd_ph(cmd.cmd);
+	if (cmd_idx < 0 || cmd_idx >= CCV_NNC_SM100_CMD_SLOTS || init_map[cmd_idx].cmd != cmd.cmd)
 		return cmd.backend;
-	const ccv_nnc_cmd_backend_registry_t& r = it->second;
-	if (r.exec && (r.tensor_memory & tensor_memory) == tensor_memory && (r.tensor_formats & tensor_formats) == tensor_formats && (r.tensor_datatypes & tensor_datatypes) == tensor_datatypes)
-		return CCV_NNC_BACKEND_GPU_SM100;
+	for (int i = 0; i < CCV_NNC_SM100_BACKEND_SLOTS; i++)
+	{
+		const ccv_nnc_cmd_backend_registry_t& r = init_map[cmd_idx].backends[i];
+		if (r.exec && (r.tensor_memory & tensor_memory) == tensor_memory && (r.tensor_formats & tensor_formats) == tensor_formats && (r.tensor_datatypes & tensor_datatypes) == tensor_datatypes)
+			return sm100_backend_init_map[i].backend;
+	}
 	return cmd.backend;
 }
 
@@ -175,10 +204,10 @@ int ccv_nnc_cmd_exec(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const i
 				tensor_memory |= CCV_TENSOR_GET_MEMORY(outputs[i]->info.type), tensor_formats |= outputs[i]->info.format, tensor_datatypes |= CCV_GET_DATA_TYPE(outputs[i]->info.datatype);
 		backend = ccv_nnc_cmd_find_backend(cmd, tensor_memory, tensor_formats, tensor_datatypes);
 	}
-	if (backend != CCV_NNC_BACKEND_GPU_SM100)
-		return CCV_NNC_EXEC_NO_KERNEL; // there is deliberately no CPU fallback in this library
-	auto it = g_registry.find(cmd.cmd);
-	if (it == g_registry.end() || !it->second.exec)
+	// init_map[cmd].backends[backend].exec (lib/nnc/ccv_nnc_cmd.c:682-686); every column but GPU_SM100 is empty here: there is
+	// deliberately no CPU fallback in this library
+	const ccv_nnc_cmd_backend_registry_t* const reg = registry_of(cmd.cmd, backend);
+	if (!reg || !reg->exec)
 		return CCV_NNC_EXEC_NO_KERNEL;
 	// a backend named explicitly is still held to its registered tensor memory (ccv_nnc_cmd_find_backend does the same test,
 	// ccv_nnc_cmd.c:307-328): host tensors never reach a device kernel, except through the transfer commands that register both
@@ -189,9 +218,9 @@ int ccv_nnc_cmd_exec(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const i
 	for (int i = 0; i < output_size; i++)
 		if (outputs[i])
 			memory |= CCV_TENSOR_GET_MEMORY(outputs[i]->info.type);
-	if ((it->second.tensor_memory & memory) != memory)
+	if ((reg->tensor_memory & memory) != memory)
 		return CCV_NNC_EXEC_NO_KERNEL;
-	const int ret = it->second.exec(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	const int ret = reg->exec(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 	if (!stream_context)
 	{
 		// lib/nnc/ccv_nnc_cmd.c:690-691: without a stream the per-thread context is drained (its workspace released); the work
@@ -579,17 +608,17 @@ ccv_nnc_cmd_t ccv_nnc_cmd_autotune(const ccv_nnc_cmd_t cmd, const size_t max_wor
 {
 	ccv_nnc_init();
 	ccv_nnc_cmd_t tuned = cmd;
-	auto it = g_registry.find(cmd.cmd);
-	if (it == g_registry.end() || !it->second.exec)
+	const ccv_nnc_cmd_backend_registry_t* const reg = registry_of(cmd.cmd, CCV_NNC_BACKEND_GPU_SM100);
+	if (!reg || !reg->exec)
 		return tuned;
 	tuned.backend = CCV_NNC_BACKEND_GPU_SM100;
-	if (it->second.algorithms <= 1)
+	if (reg->algorithms <= 1)
 	{
 		tuned.algorithm = 0;
 		return tuned;
 	}
-	if (it->second.autotune)
-		tuned.algorithm = it->second.autotune(tuned, max_workspace_size, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	if (reg->autotune)
+		tuned.algorithm = reg->autotune(tuned, max_workspace_size, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 	return tuned;
 }
 

@@ -35,17 +35,21 @@ class FlatAllreduce(object):
 
 class CommandAllreduce(object):
     """The gradient exchange as the backend's own command: CMD_COMM_ALLREDUCE_FORWARD(g_flat) -> g_flat on `stream`."""
+    _bound = None
 
     def __init__(self, net, dist, stream, rank, world):
         from ccv_b200 import nnc
         self.nnc, self.net, self.stream = nnc, net, stream
-        box = [nnc.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        nnc.comm_init_rank(box[0], world, rank)
+        if CommandAllreduce._bound != (world, rank):  # one communicator per process: later models of the same job reuse it
+            box = [nnc.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            nnc.comm_init_rank(box[0], world, rank)
+            CommandAllreduce._bound = (world, rank)
         self.cmd = nnc.CMD_COMM_ALLREDUCE_FORWARD()
 
     def __call__(self):
-        st = self.nnc.cmd_exec(self.cmd, None, 0, [self.net.g_flat], [self.net.g_flat], self.stream)
+        flats = getattr(self.net, "grad_flats", None) or [self.net.g_flat]  # a 16-bit model has a 16-bit and a small fp32 buffer: one NCCL group
+        st = self.nnc.cmd_exec(self.cmd, None, 0, flats, flats, self.stream)
         if st != 0:
             raise RuntimeError("COMM_ALLREDUCE returned %d: %s" % (st, self.nnc.lib().ccv_nnc_sm100_last_error()))
 
