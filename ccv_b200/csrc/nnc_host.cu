@@ -730,6 +730,7 @@ struct ccv_nnc_sm100_graph_node_t {
 	int flags;
 	std::vector<ccv_nnc_tensor_t*> inputs, outputs;
 	ccv_nnc_cmd_exec_f fused; // non-NULL: a fused pair installed by ccv_nnc_sm100_graph_fuse, called instead of ccv_nnc_cmd_exec
+	int side;                 // 1: issued on the graph's side stream context (ccv_nnc_sm100_graph_exec_set_side_stream)
 };
 
 extern "C" {
@@ -747,6 +748,13 @@ struct ccv_nnc_sm100_graph_s {
 	std::vector<ccv_nnc_sm100_graph_node_t> nodes;
 	std::vector<cudaGraphExec_t> captures;
 	std::vector<ccv_nnc_tensor_t*> owned; // statistics tensors of fused convolution -> batch-norm pairs
+	// second stream context for nodes marked `side` (gradient-exchange commands that overlap the rest of the backward pass), on the
+	// device of the stream the graph runs on; two reusable signals order it with the main stream (what the reference's graph
+	// runner does with per-node wait / emit signals across its streams, lib/nnc/ccv_nnc_graph_run.c:451-543)
+	ccv_nnc_stream_context_t* side_stream;
+	ccv_nnc_stream_signal_t* fork_signal;
+	ccv_nnc_stream_signal_t* join_signal;
+	ccv_nnc_sm100_graph_s() : side_stream(0), fork_signal(0), join_signal(0) {}
 };
 
 extern "C" {
@@ -767,8 +775,22 @@ int ccv_nnc_sm100_graph_exec_new(ccv_nnc_sm100_graph_t* const graph, const uint3
 	node.inputs.assign(inputs, inputs + input_size);
 	node.outputs.assign(outputs, outputs + output_size);
 	node.fused = 0;
+	node.side = 0;
 	graph->nodes.push_back(node);
 	return (int)graph->nodes.size() - 1;
+}
+
+// Marks node `i` as asynchronous to the main stream: when the runner reaches it, the side stream waits for everything issued
+// on the main stream so far, the node is issued on the side stream, and the main stream carries on; the end of the run (or of
+// the captured CUDA graph) waits for the side stream.  For commands whose results are only needed after the run -- the
+// COMM_ALLREDUCE of a gradient bucket that is complete while the rest of the backward pass still computes
+// (lib/nnc/ccv_nnc_symbolic_graph_parallel.c:546-575 places its allreduce nodes the same way, one stream per device).
+int ccv_nnc_sm100_graph_exec_set_side_stream(ccv_nnc_sm100_graph_t* const graph, const int i, const int side)
+{
+	if (i < 0 || i >= (int)graph->nodes.size() || !graph->captures.empty())
+		return -1;
+	graph->nodes[i].side = side ? 1 : 0;
+	return 0;
 }
 
 int ccv_nnc_sm100_graph_size(const ccv_nnc_sm100_graph_t* const graph)
@@ -781,16 +803,45 @@ int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin,
 	// lib/nnc/ccv_nnc_graph_run.c:911-979: for each exec in topological order: ccv_nnc_cmd_exec(...); non-zero is reported, not fatal
 	int status = 0, i;
 	const int last = end < 0 || end > (int)graph->nodes.size() ? (int)graph->nodes.size() : end;
+	bool side_pending = false;
 	for (i = begin < 0 ? 0 : begin; i < last; i++)
 	{
 		ccv_nnc_sm100_graph_node_t& n = graph->nodes[i];
-		const int ret = n.fused ? n.fused(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), stream_context) :
-			ccv_nnc_cmd_exec(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), stream_context);
+		ccv_nnc_stream_context_t* sc = stream_context;
+		if (n.side && stream_context && CCV_STREAM_GET_CONTEXT(stream_context->type) == CCV_STREAM_CONTEXT_GPU)
+		{
+			if (!graph->side_stream || graph->side_stream->device != stream_context->device)
+			{
+				if (graph->side_stream)
+					ccv_nnc_stream_context_free(graph->side_stream);
+				if (graph->fork_signal)
+					ccv_nnc_stream_signal_free(graph->fork_signal), ccv_nnc_stream_signal_free(graph->join_signal);
+				graph->side_stream = ccv_nnc_stream_context_new(stream_context->type);
+				graph->fork_signal = ccv_nnc_stream_signal_new(stream_context->type);
+				graph->join_signal = ccv_nnc_stream_signal_new(stream_context->type);
+			}
+			if (graph->side_stream && graph->fork_signal && graph->join_signal)
+			{
+				// fork: the side stream sees everything the main stream has been given so far
+				ccv_nnc_stream_context_emit_signal(stream_context, graph->fork_signal);
+				ccv_nnc_stream_context_wait_signal(graph->side_stream, graph->fork_signal);
+				sc = graph->side_stream;
+				side_pending = true;
+			}
+		}
+		const int ret = n.fused ? n.fused(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), sc) :
+			ccv_nnc_cmd_exec(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), sc);
 		if (ret != 0 && status == 0)
 		{
 			fprintf(stderr, "[ccv_nnc_sm100] graph node %d (cmd 0x%08x) returned %d\n", i, n.cmd.cmd, ret);
 			status = ret;
 		}
+	}
+	if (side_pending)
+	{
+		// join: whatever runs after this graph on the main stream is ordered behind the side stream's commands
+		ccv_nnc_stream_context_emit_signal(graph->side_stream, graph->join_signal);
+		ccv_nnc_stream_context_wait_signal(stream_context, graph->join_signal);
 	}
 	return status;
 }
@@ -812,7 +863,7 @@ int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
 	std::vector<ccv_nnc_sm100_graph_node_t> out;
 	int fused = 0;
 	const size_t n = nodes.size();
-	auto is_gpu_sm100 = [](const ccv_nnc_sm100_graph_node_t& x) { return x.fused == 0 && (x.cmd.backend == CCV_NNC_BACKEND_GPU_SM100 || x.cmd.backend == CCV_NNC_NO_BACKEND); };
+	auto is_gpu_sm100 = [](const ccv_nnc_sm100_graph_node_t& x) { return x.fused == 0 && !x.side && (x.cmd.backend == CCV_NNC_BACKEND_GPU_SM100 || x.cmd.backend == CCV_NNC_NO_BACKEND); };
 	for (size_t i = 0; i < n; i++)
 	{
 		ccv_nnc_sm100_graph_node_t& a = nodes[i];
@@ -1090,6 +1141,12 @@ void ccv_nnc_sm100_graph_free(ccv_nnc_sm100_graph_t* const graph)
 		cudaGraphExecDestroy(ge);
 	for (ccv_nnc_tensor_t* t : graph->owned)
 		ccv_nnc_tensor_free(t);
+	if (graph->side_stream)
+		ccv_nnc_stream_context_free(graph->side_stream);
+	if (graph->fork_signal)
+		ccv_nnc_stream_signal_free(graph->fork_signal);
+	if (graph->join_signal)
+		ccv_nnc_stream_signal_free(graph->join_signal);
 	delete graph;
 }
 

@@ -325,11 +325,11 @@ static int launch_umma(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 	return 0;
 }
 
-template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0, int OUT16 = 0>
+template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0, int K16 = 0, int OUT16 = 0>
 static int launch_umma_persistent(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaGemmParams& p)
 {
 	using S = UmmaPersistentSmem<BN, STAGES, EPIW, X3>;
-	auto kern = umma_gemm_persistent_kernel<AMODE, BMODE, BN, STAGES, EPIW, X3, OUT16>;
+	auto kern = umma_gemm_persistent_kernel<AMODE, BMODE, BN, STAGES, EPIW, X3, K16, OUT16>;
 	static bool configured[MAX_DEVICES];
 	if (ensure_dynamic_smem(kern, S::TOTAL, configured, "cudaFuncSetAttribute(umma_gemm_persistent_kernel)"))
 		return -1;
@@ -475,7 +475,7 @@ static void init_params(UmmaGemmParams& p)
 		layout = (e = getenv("CCV_NNC_SM100_MN_LAYOUT")) ? atoi(e) : 1;
 	}
 	p.mn_lbo = lbo, p.mn_sbo = sbo, p.mn_layout = layout;
-	p.kind16 = 0, p.bk = UMMA_BLOCK_K, p.mn_box_bytes = 4096, p.mn_step = 1024, p.out_kind = 0, p.bias16 = 0;
+	p.kind16 = 0, p.out_kind = 0, p.bias16 = 0;
 }
 
 static int pick_splits(long long tiles, int k_iters, int min_iters_per_split)
@@ -559,7 +559,7 @@ static void init_params_kind(UmmaGemmParams& p, int kind)
 	if (kind)
 	{
 		// 16-bit MN-major operands: ordinary 128-byte swizzle, 64-element atoms; boxes of 64 k-rows x 128 B; K = 16 per MMA
-		p.kind16 = 1, p.bk = 64, p.mn_box_bytes = 64 * 128, p.mn_step = 16 * 128;
+		p.kind16 = 1;
 		p.mn_lbo = 64 * 128, p.mn_sbo = 1024, p.mn_layout = 2;
 		p.out_kind = kind;
 	}
@@ -579,16 +579,16 @@ static int launch_kind(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 	if (out16)
 	{
 		if (bn == 64)
-			return launch_umma_persistent<AMODE, BMODE, 64, 6, 8, 0, 1>(stream, tmA, tmB, p);
+			return launch_umma_persistent<AMODE, BMODE, 64, 6, 8, 0, 1, 1>(stream, tmA, tmB, p);
 		if (bn == 256)
-			return launch_umma_persistent<AMODE, BMODE, 256, 3, 8, 0, 1>(stream, tmA, tmB, p);
-		return launch_umma_persistent<AMODE, BMODE, 128, 5, 8, 0, 1>(stream, tmA, tmB, p);
+			return launch_umma_persistent<AMODE, BMODE, 256, 3, 8, 0, 1, 1>(stream, tmA, tmB, p);
+		return launch_umma_persistent<AMODE, BMODE, 128, 5, 8, 0, 1, 1>(stream, tmA, tmB, p);
 	}
 	if (bn == 64)
-		return launch_umma_persistent<AMODE, BMODE, 64, 6, 8>(stream, tmA, tmB, p);
+		return launch_umma_persistent<AMODE, BMODE, 64, 6, 8, 0, 1, 0>(stream, tmA, tmB, p);
 	if (bn == 256)
-		return launch_umma_persistent<AMODE, BMODE, 256, 3, 8>(stream, tmA, tmB, p);
-	return launch_umma_persistent<AMODE, BMODE, 128, 5, 8>(stream, tmA, tmB, p);
+		return launch_umma_persistent<AMODE, BMODE, 256, 3, 8, 0, 1, 0>(stream, tmA, tmB, p);
+	return launch_umma_persistent<AMODE, BMODE, 128, 5, 8, 0, 1, 0>(stream, tmA, tmB, p);
 }
 
 // Launch with the split factor already chosen in p.splits.  One split: straight into `out` (pitch ldo, element kind `kind`).

@@ -68,10 +68,8 @@ struct UmmaGemmParams {
 	// Operand / output format of the PERSISTENT kernel (the one-tile and taps kernels are fp32-only and ignore these).  Operand
 	// tiles are always 128-byte-span swizzled rows, so a stage holds bk = 128 / sizeof(element) elements along K: 32 fp32
 	// (kind::tf32, 4 MMAs of K = 8) or 64 bf16 / fp16 (kind::f16, 4 MMAs of K = 16); all byte sizes are the same.
-	int kind16;            // 0: fp32 operands through kind::tf32; 1: 16-bit operands through kind::f16 (idesc names bf16 / fp16)
-	int bk;                // K elements per stage; also the MN elements per TMA box of an MN-major operand
-	uint32_t mn_box_bytes; // bytes per MN-major box: bk k-rows x 128 B (4096 / 8192)
-	uint32_t mn_step;      // start-address advance per MMA of an MN-major operand: UMMA_K k-rows x 128 B (1024 / 2048)
+	int kind16;            // 0: fp32 operands through kind::tf32; 1: 16-bit operands through kind::f16 (idesc names bf16 / fp16); the
+	                       // kernel itself is compiled per operand size (template K16), this records which one the host chose
 	int out_kind;          // OUT16 kernels: 1 = bf16, 2 = fp16 output elements (0: fp32 output)
 	const void* bias16;    // OUT16 kernels: bias in the output's 16-bit type (p.bias, fp32, wins when both are given)
 	uint32_t idesc;

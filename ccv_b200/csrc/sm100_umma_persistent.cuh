@@ -61,8 +61,11 @@ struct UmmaPersistentSmem {
 	static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
+// K16 = 1: 16-bit (bf16 / fp16) operands through kind::f16 -- 64 elements per 128-byte operand row, K = 16 per MMA, ordinary
+// 128-byte swizzle for MN-major tiles; K16 = 0: fp32 operands through kind::tf32 (32 elements per row, K = 8 per MMA).  A
+// compile-time switch so that the producer's box loops and the issuer's descriptor arithmetic stay fully unrolled constants.
 // OUT16 = 1: the output tensor (and an optional 16-bit bias) is bf16 / fp16 (p.out_kind); accumulation stays fp32 in TMEM.
-template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0, int OUT16 = 0>
+template <int AMODE, int BMODE, int BN, int STAGES, int EPIW, int X3 = 0, int K16 = 0, int OUT16 = 0>
 __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const UmmaGemmParams p)
 {
 	using S = UmmaPersistentSmem<BN, STAGES, EPIW, X3>;
@@ -75,6 +78,9 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 	uint64_t* xform_bar = tmem_empty_bar + 2;     // [STAGES] (X3): the hi / lo split of the stage is in place
 	uint32_t* tmem_slot = (uint32_t*)(xform_bar + STAGES);
 
+	constexpr int BK = K16 ? 64 : 32;                  // K elements per stage = MN elements per MN-major box: one 128-byte span
+	constexpr int MN_BOX_BYTES = BK * 128;             // an MN-major box: BK k-rows of 128 bytes
+	constexpr int MN_STEP = (K16 ? 16 : 8) * 128;      // start-address advance per MMA of an MN-major operand (UMMA_K k-rows)
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
 	const int tiles_m = (p.M + UMMA_BLOCK_M - 1) / UMMA_BLOCK_M;
@@ -143,29 +149,30 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 					uint8_t* sA = smem + stage * S::STAGE_BYTES;
 					uint8_t* sB = sA + S::A_BYTES;
 					mbar_expect_tx(&full_bar[stage], S::RAW_BYTES);
-					// bk = K elements per stage = MN elements per MN-major box (32 fp32 / 64 16-bit); every box row is 128 bytes
-					const int bk = p.bk;
 					if (AMODE == OP_K2D)
-						tma_load_2d(sA, &tmA, &full_bar[stage], chunk * bk, m0);
+						tma_load_2d(sA, &tmA, &full_bar[stage], chunk * BK, m0);
 					else if (AMODE == OP_MN2D) {
-						for (int j = 0; j * bk < UMMA_BLOCK_M; j++)
-							tma_load_2d(sA + j * p.mn_box_bytes, &tmA, &full_bar[stage], m0 + bk * j, it * bk);
+#pragma unroll
+						for (int j = 0; j < UMMA_BLOCK_M / BK; j++)
+							tma_load_2d(sA + j * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + BK * j, it * BK);
 					} else
-						tma_load_im2col_4d(sA, &tmA, &full_bar[stage], chunk * bk, a_w, a_h, a_n, p.tap_off_w[tap], p.tap_off_h[tap]);
+						tma_load_im2col_4d(sA, &tmA, &full_bar[stage], chunk * BK, a_w, a_h, a_n, p.tap_off_w[tap], p.tap_off_h[tap]);
 					if (BMODE == OP_K2D)
-						tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_b_col[tap] + chunk * bk, n0);
+						tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_b_col[tap] + chunk * BK, n0);
 					else if (BMODE == OP_MN2D) {
-						for (int j = 0; j * bk < BN; j++)
-							tma_load_2d(sB + j * p.mn_box_bytes, &tmB, &full_bar[stage], p.tap_b_col[tap] + n0 + bk * j, chunk * bk);
+#pragma unroll
+						for (int j = 0; j < BN / BK; j++)
+							tma_load_2d(sB + j * MN_BOX_BYTES, &tmB, &full_bar[stage], p.tap_b_col[tap] + n0 + BK * j, chunk * BK);
 					} else {
-						const int pix = it * bk;
+						const int pix = it * BK;
 						const int q = pix % p.Q;
 						const int t = pix / p.Q;
 						const int b_w = q * p.stride_w + p.base_w;
 						const int b_h = (t % p.P) * p.stride_h + p.base_h;
 						const int b_n = t / p.P;
-						for (int j = 0; j * bk < BN; j++)
-							tma_load_im2col_4d(sB + j * p.mn_box_bytes, &tmB, &full_bar[stage], n0 + bk * j, b_w, b_h, b_n, p.tap_off_w[gtap], p.tap_off_h[gtap]);
+#pragma unroll
+						for (int j = 0; j < BN / BK; j++)
+							tma_load_im2col_4d(sB + j * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + BK * j, b_w, b_h, b_n, p.tap_off_w[gtap], p.tap_off_h[gtap]);
 					}
 					if (++stage == STAGES) { stage = 0; phase ^= 1; }
 				}
@@ -200,9 +207,9 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 					{
 						// one MMA covers 32 bytes of K (8 fp32 / 16 16-bit): K-major operands advance 32 B inside the swizzled row,
 						// MN-major ones by UMMA_K k-rows of 128 B (p.mn_step)
-						const uint64_t da = (AMODE == OP_MN2D) ? umma_smem_desc(a_addr + k * p.mn_step, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
-						const uint64_t db = (BMODE == OP_K2D) ? umma_smem_desc(b_addr + k * 32, 16, 1024, 2) : umma_smem_desc(b_addr + k * p.mn_step, p.mn_lbo, p.mn_sbo, p.mn_layout);
-						if (!X3 && p.kind16)
+						const uint64_t da = (AMODE == OP_MN2D) ? umma_smem_desc(a_addr + k * MN_STEP, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
+						const uint64_t db = (BMODE == OP_K2D) ? umma_smem_desc(b_addr + k * 32, 16, 1024, 2) : umma_smem_desc(b_addr + k * MN_STEP, p.mn_lbo, p.mn_sbo, p.mn_layout);
+						if (K16)
 							umma_f16(tmem_d, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
 						else if (X3)
 						{
@@ -400,14 +407,26 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 						};
 						const float k = st_n > 0.f ? st_k[ci] : staged(0);
 						float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-						for (int rr = 0; rr < 32; rr++)
-							if (rr < valid)
+						if (valid == 32)
+						{
+							// the common case, branch-free: two independent accumulator pairs halve the dependent-add chain
+							float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+							for (int rr = 0; rr < 32; rr += 2)
+							{
+								const float d0 = staged(rr) - k, d1 = staged(rr + 1) - k;
+								s1 += d0, t1 += d1;
+								s2 = fmaf(d0, d0, s2), t2 = fmaf(d1, d1, t2);
+							}
+							s1 += t1, s2 += t2;
+						} else {
+							for (int rr = 0; rr < valid; rr++)
 							{
 								const float d = staged(rr) - k;
 								s1 += d;
 								s2 = fmaf(d, d, s2);
 							}
+						}
 						st_k[ci] = k, st_s1[ci] += s1, st_s2[ci] += s2;
 					}
 					if (lane == 0 && col0 < N)

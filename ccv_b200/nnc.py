@@ -333,6 +333,12 @@ class Graph(object):
     def __len__(self):
         return lib().ccv_nnc_sm100_graph_size(self.ptr)
 
+    def set_side_stream(self, node, side=True):
+        """node runs on the graph's side stream (forked after what precedes it, joined at the end of the run)"""
+        lib().ccv_nnc_sm100_graph_exec_set_side_stream.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        if lib().ccv_nnc_sm100_graph_exec_set_side_stream(self.ptr, node, 1 if side else 0) != 0:
+            raise RuntimeError("set_side_stream: bad node index or graph already captured")
+
     def fuse(self):
         """Peephole fusion of adjacent commands (BN+ReLU, ReLU+BN backward, residual add + ReLU); returns the number of pairs."""
         return lib().ccv_nnc_sm100_graph_fuse(self.ptr)

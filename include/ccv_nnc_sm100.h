@@ -518,6 +518,8 @@ typedef struct ccv_nnc_sm100_graph_s ccv_nnc_sm100_graph_t;
 ccv_nnc_sm100_graph_t* ccv_nnc_sm100_graph_new(void);
 int ccv_nnc_sm100_graph_exec_new(ccv_nnc_sm100_graph_t* const graph, const uint32_t cmd, const uint32_t backend, const int algorithm, const ccv_nnc_cmd_param_t* const info, const ccv_nnc_hint_t* const hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size);
 int ccv_nnc_sm100_graph_size(const ccv_nnc_sm100_graph_t* const graph);
+/* node i runs on the graph's side stream: forked after everything issued before it, joined at the end of the run (gradient-bucket allreduce) */
+int ccv_nnc_sm100_graph_exec_set_side_stream(ccv_nnc_sm100_graph_t* const graph, const int i, const int side);
 /* runs nodes [begin, end) in order on the stream; returns the first non-zero exec status */
 int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin, const int end, ccv_nnc_stream_context_t* const stream_context);
 /* peephole fusion of adjacent nodes (BN+ReLU forward, ReLU+BN backward, residual add + ReLU forward / backward); node

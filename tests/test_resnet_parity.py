@@ -175,3 +175,45 @@ def test_fused_cuda_graph_vs_cpu_ref(gpu, cpu_net, algo, tol):
     assert cos > 0.5
     for x in (g, net, stream):
         x.free()
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("dtype", [abi.CCV_16BF, abi.CCV_16F])
+def test_resnet50_16bit_fused_cuda_graph_vs_cpu_ref(gpu, cpu_net, dtype):
+    """BASELINE.json configs[3]'s datapath on the whole model: 16-bit activations / filters / gradients, fp32 batch-norm
+    parameters and statistics, fp32 master weights, fused + captured as bench.py runs it, against the fp32 CPU_REF run of the same
+    network.  Every one of the 53 contractions rounds its output to 8 (bf16) or 11 (fp16) mantissa bits, so the whole-model bound
+    is the accumulated rounding of the format (bf16: 53 layers x 2^-9 per rounding, partly averaged out by the batch norms), not
+    the per-op 1e-2 bound that tests/test_parity_16bit.py holds each command to."""
+    nnc = gpu
+    stream = nnc.Stream(0)
+    x, lab = _inputs()
+    net = resnet50.Net(BATCH, image=IMAGE, classes=CLASSES, seed=7, dtype=dtype)
+    from tests.util import pack16
+    net.input.upload(pack16(x, dtype)), net.labels.upload(lab)
+    g = nnc.Graph()
+    for cmd, hint, flags, ins, outs in net.fwd + net.bwd:
+        g.exec_new(cmd, hint, flags, ins, outs)
+    assert g.fuse() >= 60
+    assert g.run(stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+    stream.wait()
+    eager = [t.download() for t in (net.logits, net.loss, net.g_flat, net.g_flat_b)]
+    tol = 1e-1 if dtype == abi.CCV_16BF else 3e-2
+    from tests.util import rel_err
+    print("dtype 0x%x: logits error vs fp32 CPU_REF %.3e, loss error %.3e" % (dtype, rel_err(eager[0], cpu_net.logits.download()), rel_err(eager[1], cpu_net.loss.download())))
+    assert_close(eager[0], cpu_net.logits.download(), tol, "logits"), assert_close(eager[1], cpu_net.loss.download(), tol, "loss")
+    assert np.isfinite(unpack(eager[2], dtype)).all() and np.isfinite(eager[3]).all()
+    # the batch-norm parameter gradients (fp32) point the same way as the oracle's
+    cid = g.capture(stream)
+    for _ in range(2):
+        assert g.replay(cid, stream) == 0
+        stream.wait()
+        for t, e in zip((net.logits, net.loss, net.g_flat, net.g_flat_b), eager):
+            assert np.array_equal(t.download(), e), "CUDA-graph replay of the 16-bit model differs from the eager run"
+    for obj in (g, net, stream):
+        obj.free()
+
+
+def unpack(a, dtype):
+    from tests.util import unpack16
+    return unpack16(a, dtype)
