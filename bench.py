@@ -152,8 +152,21 @@ def run_model(args, dist, rank, world, local_rank, dtype="f32", algorithm=-1, pe
     stream = nnc.Stream(device)
     net = resnet50.Net(args.batch, image=args.image, classes=1000, device=device, global_batch=args.batch * world, learn_rate=4e-5, algorithm=algorithm, dtype=dt)  # 0.4 * 0.0001: the first warm-up rate of bin/nnc/imagenet.c:296-312
     g_fb, g_opt = nnc.Graph(), nnc.Graph()
-    for cmd, hint, flags, ins, outs in net.fwd + net.bwd:
+    # Gradient exchange (N > 1).  "overlap": COMM_ALLREDUCE nodes, one per gradient bucket, sit inside the backward graph on its
+    # side stream, each right behind the node that completes its bucket, and are captured into the same CUDA graph -- the NCCL
+    # kernels run under the remaining backward kernels.  "between": one allreduce command over the whole flat buffer between the
+    # two CUDA graphs (round 1's scheme).
+    in_graph = world > 1 and args.exchange == "overlap"
+    if world > 1:
+        from ccv_b200 import dp
+        allreduce_between = dp.CommandAllreduce(net, dist, stream, rank, world)  # binds the NCCL communicator of this rank
+    bwd_nodes, side = net.backward_with_exchange(args.buckets) if in_graph else (net.bwd, [])
+    for cmd, hint, flags, ins, outs in net.fwd:
         g_fb.exec_new(cmd, hint, flags, ins, outs)
+    for j, (cmd, hint, flags, ins, outs) in enumerate(bwd_nodes):
+        idx = g_fb.exec_new(cmd, hint, flags, ins, outs)
+        if j in side:
+            g_fb.set_side_stream(idx)
     for cmd, hint, flags, ins, outs in net.opt:
         g_opt.exec_new(cmd, hint, flags, ins, outs)
     n_fused = 0 if args.no_fuse else g_fb.fuse() + g_opt.fuse()
@@ -174,10 +187,7 @@ def run_model(args, dist, rank, world, local_rank, dtype="f32", algorithm=-1, pe
 
     # the single gradient exchange: ONE CCV_NNC_COMM_ALLREDUCE_FORWARD command of the backend over the flat gradient buffer(s)
     # (NCCL inside the library; torch.distributed only carries the communicator id, the barrier and the max-over-ranks time)
-    allreduce = None
-    if world > 1:
-        from ccv_b200 import dp
-        allreduce = dp.CommandAllreduce(net, dist, stream, rank, world)
+    allreduce = allreduce_between if world > 1 and not in_graph else None
 
     # eager pass: sizes workspaces, counts launches, checks every command returns success
     l0 = nnc.launch_count()
@@ -267,7 +277,9 @@ def run_model(args, dist, rank, world, local_rank, dtype="f32", algorithm=-1, pe
     math = MATH[dtype][algorithm] if dtype == "f32" else MATH[dtype]
     exchange = ""
     if world > 1:
-        exchange = ", one COMM_ALLREDUCE command (NCCL sum) over the flat %s gradient buffer%s" % ("fp32" if dtype == "f32" else dtype, "" if dtype == "f32" else " (+ the small fp32 batch-norm gradient buffer, same NCCL group)")
+        exchange = ", %s over the flat %s gradient buffer%s" % (
+            "%d COMM_ALLREDUCE commands (NCCL sum; one per gradient bucket, on the backward graph's side stream, overlapped with the rest of the backward pass)" % len(side) if in_graph else "one COMM_ALLREDUCE command (NCCL sum) between backward and SGD",
+            "fp32" if dtype == "f32" else dtype, "" if dtype == "f32" else " (+ the small fp32 batch-norm gradient buffer, same NCCL group)")
     out = {"metric": METRIC if dtype == "f32" else METRIC.replace("fp32", dtype), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
            "config": {"workload": "ResNet-50 v1d (bin/nnc/imagenet.c:17-95) %s NHWC, per-GPU batch %d, %dx%d, fwd+bwd + nesterov SGD%s%s" % (
@@ -365,6 +377,8 @@ def main():
     ap.add_argument("--algorithm", type=int, default=-1, help="fp32 contraction algorithm: -1 default (convolutions TF32, GEMM 3xTF32), 0 TF32, 1 3xTF32, 2 FFMA")
     ap.add_argument("--workload", default="resnet50", choices=["resnet50", "sdpa_cfg5"])
     ap.add_argument("--no-variants", action="store_true", help="only the headline configuration")
+    ap.add_argument("--exchange", default="overlap", choices=["overlap", "between"], help="N > 1: bucketed allreduce inside the backward graph on a side stream, or one allreduce between the graphs")
+    ap.add_argument("--buckets", type=int, default=4, help="gradient buckets of the overlapped exchange")
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="run every reference command as its own kernel sequence (no peephole fusion)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

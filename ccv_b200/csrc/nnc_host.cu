@@ -1060,6 +1060,11 @@ int ccv_nnc_sm100_graph_profile(ccv_nnc_sm100_graph_t* const graph, ccv_nnc_stre
 	int status = 0;
 	for (int i = 0; i < (int)graph->nodes.size(); i++)
 	{
+		if (graph->nodes[i].side || graph->nodes[i].cmd.cmd == CCV_NNC_COMM_ALLREDUCE_FORWARD || graph->nodes[i].cmd.cmd == CCV_NNC_COMM_ALLREDUCE_BACKWARD)
+		{
+			ms[i] = 0.f; // a collective cannot be timed by one rank on its own: every rank would have to issue it
+			continue;
+		}
 		float best = 1e30f;
 		for (int r = 0; r < (reps < 1 ? 1 : reps); r++)
 		{

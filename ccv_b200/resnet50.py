@@ -87,6 +87,7 @@ class Net(object):
             offs.append(total[low])
             total[low] += (int(np.prod(shape)) + 63) // 64 * 64  # 256-byte aligned fp32 slices (128-byte for 16-bit): TMA friendly
         self.w, self.g, self.m, self.w_master = [], [], [], []
+        self.grad_slices = []   # per parameter: (flat gradient buffer, element offset, padded element count)
         if not mixed:
             self.flat_count = total[False]
             self.w_flat, self.g_flat, self.m_flat = (self.alloc([total[False]]) for _ in range(3))
@@ -97,6 +98,7 @@ class Net(object):
                 for flat, lst in ((self.w_flat, self.w), (self.g_flat, self.g), (self.m_flat, self.m)):
                     lst.append(self.alias(flat, o, shape))
                 self.params.append((name, shape, decay))
+                self.grad_slices.append((self.g_flat, o, (n + 63) // 64 * 64))
             self.w_master = self.w
             self.w_flat.upload(host)
             self.m_flat.upload(np.zeros((total[False],), np.float32))
@@ -118,12 +120,14 @@ class Net(object):
                 self.g.append(self.alias(self.g_flat, o, shape, self.dtype))
                 self.w_master.append(self.alias(self.w_flat, o, shape))
                 self.m.append(self.alias(self.m_flat, o, shape))
+                self.grad_slices.append((self.g_flat, o, (n + 63) // 64 * 64))
             else:
                 host_b[o:o + n] = init.reshape(-1)
                 self.w.append(self.alias(self.w_flat_b, o, shape))
                 self.g.append(self.alias(self.g_flat_b, o, shape))
                 self.w_master.append(self.w[-1])
                 self.m.append(self.alias(self.m_flat_b, o, shape))
+                self.grad_slices.append((self.g_flat_b, o, (n + 63) // 64 * 64))
             self.params.append((name, shape, decay))
         self.w_flat.upload(host_a), self.w_flat_b.upload(host_b)
         for t in (self.m_flat, self.m_flat_b, self.g_flat_b):
@@ -343,6 +347,57 @@ class Net(object):
         for idx, (name, shape, decay) in enumerate(self.params):
             cmd = nnc.CMD_SGD_FORWARD(1, self.learn_rate, 1.0 / self.global_batch, decay, 0.9, 0.0)
             self._node(self.opt, cmd, None, 0, [G[idx], self.w_master[idx], self.m[idx]], [self.w_master[idx], self.m[idx]])
+
+    # ------------------------------------------------------------------------------------------------ data-parallel exchange
+    def backward_with_exchange(self, buckets=4):
+        """The backward node list with the gradient exchange woven in (the reference places one allreduce per
+        parameter right behind the node that produces its gradient, lib/nnc/ccv_nnc_symbolic_graph_parallel.c:546-575).  The flat
+        gradient buffer is cut into `buckets` contiguous slices of similar size, walking the parameters from the last layer
+        backwards -- the order in which the backward pass completes them; one COMM_ALLREDUCE_FORWARD node per slice is placed
+        behind the first convolution / GEMM backward node after which the whole slice has been written.  Returns
+        (nodes, side) where side lists the indices of the allreduce nodes: issued on the graph's side stream
+        (Graph.set_side_stream) they run under the remaining backward kernels; the graph's end joins them, so the SGD commands that
+        follow see the summed gradients.  A 16-bit model's small fp32 batch-norm gradient buffer travels with the last slice."""
+        ready = {}
+        for j, (_, _, _, _, outs) in enumerate(self.bwd):
+            for t in outs:
+                if t is not None:
+                    ready[id(t)] = j
+        main = [i for i, (flat, _, _) in enumerate(self.grad_slices) if flat is self.g_flat]
+        total = sum(self.grad_slices[i][2] for i in main)
+        cuts, acc, cur = [], 0, []
+        for i in reversed(main):  # parameters are created in forward order: the backward pass finishes them last to first
+            cur.append(i)
+            acc += self.grad_slices[i][2]
+            if acc >= total * (len(cuts) + 1) / float(buckets) and len(cuts) < buckets - 1:
+                cuts.append(cur)
+                cur = []
+        if cur:
+            cuts.append(cur)
+        inserts = []  # (after node index, [tensors])
+        for k, members in enumerate(cuts):
+            lo = min(self.grad_slices[i][1] for i in members)
+            hi = max(self.grad_slices[i][1] + self.grad_slices[i][2] for i in members)
+            done = max(ready[id(self.g[i])] for i in members)
+            tensors = [self.alias(self.g_flat, lo, (hi - lo,), self.dtype if self.g_flat.params.datatype != abi.CCV_32F else abi.CCV_32F)]
+            if k == len(cuts) - 1:
+                if getattr(self, "g_flat_b", None) is not None:
+                    tensors.append(self.g_flat_b)
+                done = len(self.bwd) - 1
+            j = done
+            while j < len(self.bwd) - 1 and self.bwd[j][0].cmd not in (abi.CCV_NNC_CONVOLUTION_BACKWARD, abi.CCV_NNC_GEMM_BACKWARD):
+                j += 1  # never split a pair the peephole pass fuses (ReLU backward + batch-norm backward, batch norm + convolution)
+            inserts.append((j, tensors))
+        nodes, side = [], []
+        by_pos = {}
+        for j, tensors in inserts:
+            by_pos.setdefault(j, []).extend(tensors)
+        for j, node in enumerate(self.bwd):
+            nodes.append(node)
+            if j in by_pos:
+                side.append(len(nodes))
+                nodes.append((nnc.CMD_COMM_ALLREDUCE_FORWARD(), None, 0, by_pos[j], by_pos[j]))
+        return nodes, side
 
     # ------------------------------------------------------------------------------------------------ execution
     def graphs(self):

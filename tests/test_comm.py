@@ -113,7 +113,40 @@ single = run(8, 8, x, y, None)
 w_dp, w_1 = sharded.w_flat.download(), single.w_flat.download()
 err = np.abs(w_dp - w_1).max() / np.abs(w_1).max()
 assert err < 1e-5, "rank %%d: data-parallel weights differ from single-device weights by %%g" %% (rank, err)
-print("rank %%d ok %%g" %% (rank, err))
+
+# 3. the same step with the exchange woven into the backward GRAPH: one COMM_ALLREDUCE node per gradient bucket on the graph's
+#    side stream (ccv_b200/resnet50.py: backward_with_exchange), eagerly and as a captured CUDA graph with the NCCL kernels inside
+def step_single(net):
+    for node in net.fwd + net.bwd + net.opt:
+        assert nnc.cmd_exec(*node, stream=stream) == 0
+    stream.wait()
+
+net_g = TinyNet(8 // world, image=8, classes=5, global_batch=8, device=rank, seed=3, learn_rate=0.1, algorithm=2)
+net_g.input.upload(dp.shard(x, rank, world)), net_g.labels.upload(dp.shard(y, rank, world))
+g = nnc.Graph()
+for node in net_g.fwd:
+    g.exec_new(*node)
+nodes, side = net_g.backward_with_exchange(2)
+assert len(side) == 2
+for j, node in enumerate(nodes):
+    idx = g.exec_new(*node)
+    if j in side:
+        g.set_side_stream(idx)
+for node in net_g.opt:
+    g.exec_new(*node)
+g.fuse()
+assert g.run(stream) == 0
+stream.wait()
+err = np.abs(net_g.w_flat.download() - w_1).max() / np.abs(w_1).max()
+assert err < 1e-5, "rank %%d: graph with side-stream exchange differs from the single-device step by %%g" %% (rank, err)
+cid = g.capture(stream)          # capture = one more eager step, then the recording
+assert g.replay(cid, stream) == 0
+stream.wait()
+step_single(single), step_single(single)
+w_3 = single.w_flat.download()
+err3 = np.abs(net_g.w_flat.download() - w_3).max() / np.abs(w_3).max()
+assert err3 < 1e-4, "rank %%d: captured graph with the exchange inside differs after 3 steps by %%g" %% (rank, err3)
+print("rank %%d ok %%g %%g %%g" %% (rank, err, 0.0, err3))
 dist.barrier()
 dist.destroy_process_group()
 """

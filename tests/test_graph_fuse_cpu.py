@@ -90,3 +90,32 @@ def test_comm_plumbing_without_a_device():
     assert len(a) == 128 and len(b) == 128 and a != b
     x = _t(16)
     assert nnc.cmd_exec(nnc.CMD_COMM_ALLREDUCE_FORWARD(), None, 0, [x], [x]) != 0
+
+
+def test_gradient_buckets_cover_the_flat_buffer_and_follow_their_producers():
+    """ccv_b200/resnet50.py backward_with_exchange (host logic, oracle-side tensors): the allreduce nodes partition the flat
+    gradient buffer, and each sits behind the last backward node that writes into its bucket."""
+    from oracle import ref, ref_factory
+    if not ref.available():
+        pytest.skip("oracle/_ref/libccv_ref.so not built")
+    from ccv_b200 import abi, resnet50
+    net = resnet50.Net(2, image=32, classes=10, factory=ref_factory.RefFactory())
+    nodes, side = net.backward_with_exchange(4)
+    assert len(side) == 4 and len(nodes) == len(net.bwd) + 4
+    base = net.g_flat.array.ctypes.data
+    spans = []
+    for i in side:
+        cmd, _, _, ins, outs = nodes[i]
+        assert cmd.cmd == abi.CCV_NNC_COMM_ALLREDUCE_FORWARD and ins == outs
+        assert nodes[i - 1][0].cmd in (abi.CCV_NNC_CONVOLUTION_BACKWARD, abi.CCV_NNC_GEMM_BACKWARD) or i == len(nodes) - 1
+        lo = (ins[0].array.ctypes.data - base) // 4
+        spans.append((lo, lo + ins[0].array.size, i))
+    spans.sort()
+    assert spans[0][0] == 0 and spans[-1][1] == net.flat_count and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    # every gradient tensor of a bucket is written by a node in front of the bucket's allreduce
+    for lo, hi, at in spans:
+        for j in range(at + 1, len(nodes)):
+            for t in nodes[j][4]:
+                if t is not None and hasattr(t, "array") and nodes[j][0].cmd != abi.CCV_NNC_COMM_ALLREDUCE_FORWARD:
+                    off = (t.array.ctypes.data - base) // 4
+                    assert not (0 <= off < net.flat_count and lo <= off < hi), "a gradient of bucket [%d, %d) is written after its allreduce" % (lo, hi)
