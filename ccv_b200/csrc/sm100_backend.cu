@@ -263,9 +263,35 @@ int gemm_dispatch16(cudaStream_t s, const Scratch& scratch, const int kind, cons
 		tb = 0, ldb = b_rs;
 	else if (b_rs == 1 || K == 1)
 		tb = 1, ldb = b_cs;
-	if (ta < 0 || tb < 0)
+	if (ta >= 0 && tb >= 0)
+	{
+		const int rc = gemm_16(s, kind, M, N, K, a, lda, ta, b, ldb, tb, c, c_rs, bias32, bias16, accumulate, scratch);
+		if (rc <= 0)
+			return rc;
+	}
+	// Shapes the tensor-core path cannot take (a leading dimension that is not a multiple of 16 bytes, e.g. a 10-class head):
+	// widen the operands into the command's scratch, multiply in fp32 on the CUDA cores, narrow the result (one rounding).  Small
+	// by construction: anything large has TMA-friendly strides.
+	const size_t need = ((size_t)M * K + (size_t)K * N + (size_t)M * N + (size_t)N) * sizeof(float) + 1024;
+	if (!scratch.ptr || scratch.bytes < need)
 		return 1;
-	return gemm_16(s, kind, M, N, K, a, lda, ta, b, ldb, tb, c, c_rs, bias32, bias16, accumulate, scratch);
+	float* const a32 = (float*)scratch.ptr;
+	float* const b32 = a32 + (((size_t)M * K + 63) & ~(size_t)63);
+	float* const c32 = b32 + (((size_t)K * N + 63) & ~(size_t)63);
+	float* const bias_w = c32 + (((size_t)M * N + 63) & ~(size_t)63);
+	if (widen_matrix(s, a, kind, a_rs, a_cs, a32, M, K) || widen_matrix(s, b, kind, b_rs, b_cs, b32, K, N))
+		return -1;
+	const float* bias_f = bias32;
+	if (!bias_f && bias16)
+	{
+		if (widen_matrix(s, bias16, kind, 0, 1, bias_w, 1, N))
+			return -1;
+		bias_f = bias_w;
+	}
+	const int rc = gemm_ffma(s, M, N, K, a32, K, 1, b32, N, 1, c32, N, bias_f, 0);
+	if (rc)
+		return rc;
+	return narrow_matrix(s, c32, c, kind, c_rs, c_cs, M, N, accumulate) ? -1 : 0;
 }
 
 // blas/ccv_nnc_gemm_cpu_ref.c:110-184

@@ -642,8 +642,6 @@ static int gemm_any(cudaStream_t stream, int kind, int M, int N, int K, const vo
 		ok = map_2d(&tmB, kind, b, K, N, ldb, bk, true);
 	if (!ok)
 		return 1;
-	if (kind && ((ldc * 2) & 7)) // 16-bit rows are written 8 bytes at a time at least
-		return 1;
 	UmmaGemmParams p;
 	init_params_kind(p, kind);
 	p.M = M, p.N = N;

@@ -1241,6 +1241,25 @@ __global__ void __launch_bounds__(1024) colsum_partials_any_kernel(const float* 
 		st_kind(out, col, accumulate ? ld_kind(out, col, out_kind) + t : t, out_kind);
 	}
 }
+// one block per column, any stride / alignment / element kind (odd shapes: a 10-class head); fixed summation order
+__global__ void colsum_scalar_kernel(const void* __restrict__ g, const int g_kind, const size_t rows, const long long ld, void* __restrict__ out, const int out_kind, const int accumulate)
+{
+	__shared__ float sh[256];
+	const int col = blockIdx.x;
+	float acc = 0.f;
+	for (size_t r = threadIdx.x; r < rows; r += blockDim.x)
+		acc += ld_kind(g, r * ld + col, g_kind);
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1)
+	{
+		if ((int)threadIdx.x < o)
+			sh[threadIdx.x] += sh[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+		st_kind(out, col, accumulate ? ld_kind(out, col, out_kind) + sh[0] : sh[0], out_kind);
+}
 int colsum_any(cudaStream_t s, int g_kind, const void* g, size_t rows, int cols, long long ld, void* out, int out_kind, int accumulate, void* workspace)
 {
 	if (g_kind == 0 && out_kind == 0)
@@ -1248,7 +1267,10 @@ int colsum_any(cudaStream_t s, int g_kind, const void* g, size_t rows, int cols,
 	if (cols <= 0)
 		return 0;
 	if (cols % 4 || ld % 4 || !workspace || (((uintptr_t)g) & 7))
-		return 1;
+	{
+		colsum_scalar_kernel<<<cols, 256, 0, s>>>(g, g_kind, rows, ld, out, out_kind, accumulate);
+		return check("colsum_scalar");
+	}
 	const int cols4 = cols / 4, cpb = cols4 >= 256 ? 256 : cols4, rpi = 256 / cpb;
 	const int gx = (cols4 + cpb - 1) / cpb;
 	size_t gy = (rows + (size_t)rpi * 32 - 1) / ((size_t)rpi * 32);
@@ -1268,6 +1290,42 @@ int colsum_any(cudaStream_t s, int g_kind, const void* g, size_t rows, int cols,
 		return -1;
 	colsum_partials_any_kernel<<<(cols + 31) / 32, 1024, 0, s>>>(part, (int)gy, cols, out, out_kind, accumulate);
 	return check("colsum_partials_any");
+}
+
+// strided [rows, cols] matrix of element kind `kind` <-> dense fp32 [rows, cols]: the operands of 16-bit GEMMs whose strides the
+// tensor-core path cannot take (TMA wants 16-byte multiples) are widened, multiplied on the CUDA cores and narrowed back
+__global__ void widen_matrix_kernel(const void* __restrict__ src, const int kind, const long long rs, const long long cs, float* __restrict__ dst, const int rows, const int cols)
+{
+	const size_t total = (size_t)rows * cols;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const size_t r = i / cols, c = i - r * cols;
+		dst[i] = ld_kind(src, r * rs + c * cs, kind);
+	}
+}
+__global__ void narrow_matrix_kernel(const float* __restrict__ src, void* __restrict__ dst, const int kind, const long long rs, const long long cs, const int rows, const int cols, const int accumulate)
+{
+	const size_t total = (size_t)rows * cols;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const size_t r = i / cols, c = i - r * cols;
+		const size_t at = r * rs + c * cs;
+		st_kind(dst, at, accumulate ? ld_kind(dst, at, kind) + src[i] : src[i], kind);
+	}
+}
+int widen_matrix(cudaStream_t s, const void* src, int kind, long long rs, long long cs, float* dst, int rows, int cols)
+{
+	if (rows <= 0 || cols <= 0)
+		return 0;
+	widen_matrix_kernel<<<grid_for((size_t)rows * cols, 256), 256, 0, s>>>(src, kind, rs, cs, dst, rows, cols);
+	return check("widen_matrix");
+}
+int narrow_matrix(cudaStream_t s, const float* src, void* dst, int kind, long long rs, long long cs, int rows, int cols, int accumulate)
+{
+	if (rows <= 0 || cols <= 0)
+		return 0;
+	narrow_matrix_kernel<<<grid_for((size_t)rows * cols, 256), 256, 0, s>>>(src, dst, kind, rs, cs, rows, cols, accumulate);
+	return check("narrow_matrix");
 }
 
 // =============================================================================================== dtype conversion

@@ -91,6 +91,10 @@ int sgd_multi_any(cudaStream_t s, int tensors, int g_kind, const void* const* g,
 // `tensors` independent SGD updates with the same hyper-parameters in ceil(tensors / 32) launches
 int sgd_multi_f32(cudaStream_t s, int tensors, const float* const* g, const float* const* a, const float* const* m, float* const* b, float* const* n, const size_t* counts, int nesterov, float rate, float scale, float decay, float momentum, float dampening);
 
+// strided matrix of element kind `kind` (0 fp32, 1 bf16, 2 fp16) <-> dense fp32 (16-bit GEMM operands with strides TMA cannot take)
+int widen_matrix(cudaStream_t s, const void* src, int kind, long long rs, long long cs, float* dst, int rows, int cols);
+int narrow_matrix(cudaStream_t s, const float* src, void* dst, int kind, long long rs, long long cs, int rows, int cols, int accumulate);
+
 // ---- datatype / layout ----------------------------------------------------------------------------------------
 // dtype codes: 0 = f32, 1 = f16 (CPU_REF semantics: f32 -> f16 truncates, lib/ccv_util.c:1434-1440), 2 = f64, 3 = bf16 (RNE)
 int convert_dtype(cudaStream_t s, const void* a, int a_dtype, void* b, int b_dtype, size_t n);

@@ -15,7 +15,8 @@ TOL = 1e-2
 
 
 @pytest.mark.parametrize("kind", KINDS)
-@pytest.mark.parametrize("M,N,K,ta,tb,with_bias", [(128, 128, 64, 0, 0, 0), (256, 192, 160, 0, 1, 1), (200, 136, 104, 1, 0, 1), (96, 72, 48, 1, 1, 0), (64, 1000, 2048, 0, 1, 1), (8, 64, 128, 0, 1, 0)])
+@pytest.mark.parametrize("M,N,K,ta,tb,with_bias", [(128, 128, 64, 0, 0, 0), (256, 192, 160, 0, 1, 1), (200, 136, 104, 1, 0, 1), (96, 72, 48, 1, 1, 0), (64, 1000, 2048, 0, 1, 1), (8, 64, 128, 0, 1, 0),
+                                                      (4, 10, 2048, 0, 1, 1), (33, 17, 21, 0, 1, 1)])  # strides TMA cannot take: widened, multiplied in fp32, narrowed
 def test_gemm_16bit_forward_backward(gpu, ref, kind, M, N, K, ta, tb, with_bias):
     nnc = gpu
     a = round16(seeded((K, M) if ta else (M, K), 11, -1, 1), kind)
