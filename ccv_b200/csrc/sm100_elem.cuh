@@ -61,6 +61,59 @@ __device__ __forceinline__ void st_kind(void* p, const size_t i, const float v, 
 		reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
 }
 
+// One 16-byte access = W elements (4 fp32, 8 bf16 / fp16): the widest single load / store, what the streaming kernels use when
+// the channel count allows it
+template <typename T> struct Vec16 { static constexpr int W = 16 / sizeof(T); };
+__device__ __forceinline__ void ldv(const float* p, float (&v)[4])
+{
+	const float4 t = *reinterpret_cast<const float4*>(p);
+	v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+__device__ __forceinline__ void stv(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void ldv(const __nv_bfloat16* p, float (&v)[8])
+{
+	const uint4 u = *reinterpret_cast<const uint4*>(p);
+	const uint32_t w[4] = { u.x, u.y, u.z, u.w };
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+		v[2 * i] = __uint_as_float(w[i] << 16), v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+}
+__device__ __forceinline__ void stv(__nv_bfloat16* p, const float (&v)[8])
+{
+	uint32_t w[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+		w[i] = *reinterpret_cast<const uint32_t*>(&t);
+	}
+	*reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void ldv(const __half* p, float (&v)[8])
+{
+	const uint4 u = *reinterpret_cast<const uint4*>(p);
+	const uint32_t w[4] = { u.x, u.y, u.z, u.w };
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+		v[2 * i] = t.x, v[2 * i + 1] = t.y;
+	}
+}
+__device__ __forceinline__ void stv(__half* p, const float (&v)[8])
+{
+	uint32_t w[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		const __half2 t = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+		w[i] = *reinterpret_cast<const uint32_t*>(&t);
+	}
+	*reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <typename T>
+static inline bool aligned_v16(const T* p) { return (((uintptr_t)p) & 15) == 0; }
+
 // a pointer is usable by ld4 / st4 when it is aligned to 4 elements
 template <typename T>
 static inline bool aligned_v4(const T* p) { return (((uintptr_t)p) & (4 * sizeof(T) - 1)) == 0; }

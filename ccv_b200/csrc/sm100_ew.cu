@@ -731,12 +731,46 @@ static int pool_max_bwd_t(cudaStream_t s, const PoolGeom& g, const T* grad_b, co
 		pool_bwd_kernel<T, 1, 1><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
 	return check("pool_max_bwd");
 }
+// Average-pool backward when the windows tile the input exactly (window = stride, no padding, H = P * R, W = Q * S: the 2 x 2 / 2
+// shortcut pools and the global pool of a ResNet): one thread per OUTPUT gradient group -- one 16-byte load, one multiply per
+// element, R * S 16-byte stores -- instead of one thread (and three integer divisions) per input group.
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_bwd_tiles_kernel(const PoolGeom g, const T* __restrict__ gb, T* __restrict__ ga)
+{
+	constexpr int W = Vec16<T>::W;
+	const unsigned CW = (unsigned)g.C / W;
+	const size_t total = (size_t)g.N * g.P * g.Q * CW;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const size_t r = i / CW;
+		const int c = (int)(i - r * CW) * W;
+		const size_t r2 = r / (unsigned)g.Q;
+		const int q = (int)(r - r2 * (unsigned)g.Q);
+		const int n = (int)(r2 / (unsigned)g.P), p = (int)(r2 - (size_t)n * (unsigned)g.P);
+		float v[W];
+		ldv(gb + n * g.bn + p * g.bh + q * g.bw + c, v);
+#pragma unroll
+		for (int k = 0; k < W; k++)
+			v[k] = v[k] / (float)(g.R * g.S); // the reference divides (pool/ccv_nnc_avg_pool_cpu_ref.c:60-110); keep its rounding
+		T* const base = ga + n * g.an + (long long)p * g.R * g.ah + (long long)q * g.S * g.aw + c;
+		for (int dh = 0; dh < g.R; dh++)
+			for (int dw = 0; dw < g.S; dw++)
+				stv(base + dh * g.ah + dw * g.aw, v);
+	}
+}
 template <typename T>
 static int pool_avg_bwd_t(cudaStream_t s, const PoolGeom& g, const T* grad_b, T* grad_a)
 {
 	const size_t total = (size_t)g.N * g.H * g.W * g.C;
 	if (total == 0)
 		return 0;
+	constexpr int W = Vec16<T>::W;
+	if (g.R == g.stride_h && g.S == g.stride_w && g.pad_h == 0 && g.pad_w == 0 && g.H == g.P * g.R && g.W == g.Q * g.S && g.C % W == 0 && aligned_v16(grad_b) && aligned_v16(grad_a) &&
+		g.aw % W == 0 && g.ah % W == 0 && g.an % W == 0 && g.bw % W == 0 && g.bh % W == 0 && g.bn % W == 0)
+	{
+		avgpool_bwd_tiles_kernel<T><<<grid_for((size_t)g.N * g.P * g.Q * (g.C / W), 256), 256, 0, s>>>(g, grad_b, grad_a);
+		return check("pool_avg_bwd");
+	}
 	if (pool_vec_ok(g, (const T*)grad_a, grad_b))
 		pool_bwd_kernel<T, 4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, (const T*)0, (const T*)0, grad_a);
 	else
