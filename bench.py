@@ -377,7 +377,7 @@ def main():
     ap.add_argument("--algorithm", type=int, default=-1, help="fp32 contraction algorithm: -1 default (convolutions TF32, GEMM 3xTF32), 0 TF32, 1 3xTF32, 2 FFMA")
     ap.add_argument("--workload", default="resnet50", choices=["resnet50", "sdpa_cfg5"])
     ap.add_argument("--no-variants", action="store_true", help="only the headline configuration")
-    ap.add_argument("--exchange", default="overlap", choices=["overlap", "between"], help="N > 1: bucketed allreduce inside the backward graph on a side stream, or one allreduce between the graphs")
+    ap.add_argument("--exchange", default="between", choices=["overlap", "between"], help="N > 1: one allreduce command between the backward and the optimizer graph (default), or bucketed allreduce nodes inside the backward graph on its side stream")
     ap.add_argument("--buckets", type=int, default=4, help="gradient buckets of the overlapped exchange")
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="run every reference command as its own kernel sequence (no peephole fusion)")

@@ -781,8 +781,9 @@ int ccv_nnc_sm100_graph_exec_new(ccv_nnc_sm100_graph_t* const graph, const uint3
 }
 
 // Marks node `i` as asynchronous to the main stream: when the runner reaches it, the side stream waits for everything issued
-// on the main stream so far, the node is issued on the side stream, and the main stream carries on; the end of the run (or of
-// the captured CUDA graph) waits for the side stream.  For commands whose results are only needed after the run -- the
+// on the main stream so far, the node is issued on the side stream, and the main stream carries on; the main stream waits for the
+// side stream in front of the first later node that reads or writes memory the side node writes, and at the end of the run (or
+// of the captured CUDA graph) at the latest.  For commands whose results are only needed after the run -- the
 // COMM_ALLREDUCE of a gradient bucket that is complete while the rest of the backward pass still computes
 // (lib/nnc/ccv_nnc_symbolic_graph_parallel.c:546-575 places its allreduce nodes the same way, one stream per device).
 int ccv_nnc_sm100_graph_exec_set_side_stream(ccv_nnc_sm100_graph_t* const graph, const int i, const int side)
@@ -804,10 +805,46 @@ int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin,
 	int status = 0, i;
 	const int last = end < 0 || end > (int)graph->nodes.size() ? (int)graph->nodes.size() : end;
 	bool side_pending = false;
+	// byte ranges written by side-stream nodes that have not been joined yet: a main-stream node that touches one of them is a
+	// consumer (or an overwriter) of that result, so the join is issued in front of it instead of at the end of the run
+	std::vector<std::pair<const unsigned char*, const unsigned char*> > side_writes;
+	auto range_of = [](const ccv_nnc_tensor_t* const t) {
+		size_t elems = 1;
+		if (CCV_IS_TENSOR_VIEW(t))
+		{
+			const ccv_nnc_tensor_view_t* const tv = (const ccv_nnc_tensor_view_t*)t;
+			for (int d = 0; d < CCV_NNC_MAX_DIM_ALLOC && t->info.dim[d] > 0; d++)
+				elems += (size_t)(t->info.dim[d] - 1) * (size_t)tv->stride[d];
+		} else
+			for (int d = 0; d < CCV_NNC_MAX_DIM_ALLOC && t->info.dim[d] > 0; d++)
+				elems *= (size_t)t->info.dim[d];
+		return std::make_pair((const unsigned char*)t->data.u8, (const unsigned char*)t->data.u8 + elems * datatype_size(t->info.datatype));
+	};
+	auto join = [&]() {
+		ccv_nnc_stream_context_emit_signal(graph->side_stream, graph->join_signal);
+		ccv_nnc_stream_context_wait_signal(stream_context, graph->join_signal);
+		side_pending = false;
+		side_writes.clear();
+	};
 	for (i = begin < 0 ? 0 : begin; i < last; i++)
 	{
 		ccv_nnc_sm100_graph_node_t& n = graph->nodes[i];
 		ccv_nnc_stream_context_t* sc = stream_context;
+		if (side_pending && !n.side)
+		{
+			bool touches = false;
+			for (int pass = 0; pass < 2 && !touches; pass++)
+				for (ccv_nnc_tensor_t* t : (pass ? n.outputs : n.inputs))
+					if (t && t->data.u8)
+					{
+						const auto r = range_of(t);
+						for (const auto& w : side_writes)
+							if (r.first < w.second && w.first < r.second)
+								touches = true;
+					}
+			if (touches)
+				join();
+		}
 		if (n.side && stream_context && CCV_STREAM_GET_CONTEXT(stream_context->type) == CCV_STREAM_CONTEXT_GPU)
 		{
 			if (!graph->side_stream || graph->side_stream->device != stream_context->device)
@@ -827,6 +864,9 @@ int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin,
 				ccv_nnc_stream_context_wait_signal(graph->side_stream, graph->fork_signal);
 				sc = graph->side_stream;
 				side_pending = true;
+				for (ccv_nnc_tensor_t* t : n.outputs)
+					if (t && t->data.u8)
+						side_writes.push_back(range_of(t));
 			}
 		}
 		const int ret = n.fused ? n.fused(n.cmd, n.hint, n.flags, n.inputs.data(), (int)n.inputs.size(), n.outputs.data(), (int)n.outputs.size(), sc) :
@@ -838,11 +878,7 @@ int ccv_nnc_sm100_graph_run(ccv_nnc_sm100_graph_t* const graph, const int begin,
 		}
 	}
 	if (side_pending)
-	{
-		// join: whatever runs after this graph on the main stream is ordered behind the side stream's commands
-		ccv_nnc_stream_context_emit_signal(graph->side_stream, graph->join_signal);
-		ccv_nnc_stream_context_wait_signal(stream_context, graph->join_signal);
-	}
+		join(); // whatever runs after this graph on the main stream is ordered behind the side stream's commands
 	return status;
 }
 
