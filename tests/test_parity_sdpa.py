@@ -157,3 +157,61 @@ def test_attention_bf16_backward(gpu, ref, B, Sq, Sk, Hq, Hk, causal):
         assert_close(_from_bf16(t.download()), want, 1e-2, "bf16 " + name)
     for t in [x for x in ins if x is not None] + outs + [stream]:
         t.free()
+
+
+@pytest.mark.parametrize("D,masked,causal", [(40, 0, 0), (64, 0, 1), (160, 0, 0), (224, 0, 1), (128, 1, 0)])
+def test_attention_16bit_forward_other_head_dims_and_masks(gpu, ref, D, masked, causal):
+    """Head dimensions the reference trials (40, 64, 160, 224: test/int/nnc/cublas.tests.c:2752-2833) and additive masks on bf16
+    tensors: the tcgen05 flash kernel does not cover them, the command still runs (widen -> fp32 path -> narrow) instead of
+    returning NO_KERNEL.  Against CPU_REF on the bf16-rounded operands, 1e-2 of max|ref|."""
+    nnc = gpu
+    B, S, H = 2, 48, 4
+    scale = 1.0 / np.sqrt(D)
+    bits = [_to_bf16(seeded((B, S, H, D), i + 1, -1, 1)) for i in range(3)]
+    q, k, v = (_from_bf16(b) for b in bits)
+    fwd = _cmd(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD, scale, causal)
+    mask = None
+    if masked:
+        mask = np.where(np.random.RandomState(5).rand(1, 1, S, S) < 0.3, -1e9, 0.0).astype(np.float32)
+        mask[..., np.arange(S), np.arange(S)] = 0
+    ins_r = [q, k, v] + ([mask] if masked else [])
+    st_r, (o_r, _) = ref_exec(ref, fwd, None, 0, ins_r, [np.zeros((B, S, H, D), np.float32), None])
+    assert st_r == 0
+    stream = nnc.Stream(0)
+    tq, tk, tv = (nnc.gpu_tensor([B, S, H, D], datatype=abi.CCV_16BF).upload(b) for b in bits)
+    to = nnc.gpu_tensor([B, S, H, D], datatype=abi.CCV_16BF)
+    tm = nnc.gpu_tensor(list(mask.shape)).upload(mask) if masked else None
+    assert nnc.cmd_exec(fwd, None, 0, [tq, tk, tv] + ([tm] if masked else []), [to], stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+    stream.wait()
+    assert_close(_from_bf16(to.download()), o_r, 1e-2, "bf16 attention D=%d" % D)
+    for t in (tq, tk, tv, to, stream) + ((tm,) if masked else ()):
+        t.free()
+
+
+def test_baseline_config5_slices_vs_compiled_reference(gpu, ref):
+    """BASELINE.json configs[4] at FULL size on the GPU (bf16, B=32 H=16 S=2048 D=128, non-causal and causal, the reference's
+    i / count ramps of test/int/nnc/cublas.tests.c:2786-2794) with four (b, h) slices of the result checked against the compiled
+    reference itself (CPU_REF run per slice on the bf16-rounded values: O(S^2) scratch per slice is what makes the whole tensor
+    unaffordable on the CPU), 1e-2 of max|ref|."""
+    nnc = gpu
+    B, H, S, D = 32, 16, 2048, 128
+    n = B * S * H * D
+    bits = _to_bf16((np.arange(n, dtype=np.float64) / n).astype(np.float32)).reshape(B, S, H, D)
+    vals = _from_bf16(bits)
+    stream = nnc.Stream(0)
+    tq, tk, tv, to = (nnc.gpu_tensor([B, S, H, D], datatype=abi.CCV_16BF) for _ in range(4))
+    for t in (tq, tk, tv):
+        t.upload(bits)
+    tl = nnc.gpu_tensor([B, H, S])
+    for causal in (0, 1):
+        fwd = _cmd(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD, 1.0 / np.sqrt(D), causal)
+        assert nnc.cmd_exec(fwd, None, 0, [tq, tk, tv], [to, tl], stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+        stream.wait()
+        got = _from_bf16(to.download())
+        for b, h in ((0, 0), (7, 3), (19, 15), (31, 8)):
+            sl = np.ascontiguousarray(vals[b:b + 1, :, h:h + 1, :])
+            st_r, (o_r, _) = ref_exec(ref, fwd, None, 0, [sl, sl, sl], [np.zeros((1, S, 1, D), np.float32), None])
+            assert st_r == 0
+            assert_close(got[b:b + 1, :, h:h + 1, :], o_r, 1e-2, "configs[4] slice (b=%d, h=%d) causal=%d" % (b, h, causal))
+    for t in (tq, tk, tv, to, tl, stream):
+        t.free()
