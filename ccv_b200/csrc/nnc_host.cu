@@ -991,7 +991,7 @@ int ccv_nnc_sm100_graph_fuse(ccv_nnc_sm100_graph_t* const graph)
 				bool g_read_later = false;
 				for (size_t j = i + 2; j < n && !g_read_later; j++)
 					for (ccv_nnc_tensor_t* t : nodes[j].inputs)
-						if (t == a.outputs[0])
+						if (t == a.outputs[0] || (t && a.outputs[0] && t->data.u8 && t->data.u8 == a.outputs[0]->data.u8)) // the same memory through another tensor / view counts
 						{
 							// a later node that overwrites g before reading it would be fine, but keep the rule simple
 							g_read_later = true;

@@ -61,70 +61,86 @@ static inline float* ws_part(void* ws, int C) { return (float*)(((uintptr_t)(ws_
 template <typename T, int MODE, int MASK>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ coef, const size_t rows, const int C, float* __restrict__ part, const int cpb)
 {
-	__shared__ float4 sh[2][256];
-	const int CV = C >> 2;
+	// one 16-byte access = W channels (4 fp32 / 8 bf16 or fp16); thread = (channel group tx, row lane ty)
+	constexpr int W = Vec16<T>::W;
+	__shared__ float sh[2][256][W + 1];
+	const int CW = C / W;
 	const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb, rpi = 256 / cpb;
-	const int cv = blockIdx.x * cpb + tx;
-	float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
-	if (ty < rpi && cv < CV)
+	const int cw = blockIdx.x * cpb + tx;
+	float s1[W], s2[W];
+#pragma unroll
+	for (int k = 0; k < W; k++)
+		s1[k] = s2[k] = 0.f;
+	if (ty < rpi && cw < CW)
 	{
-		const float4 k = MODE == 0 ? ld4(x + cv * 4) : ld4(mean + cv * 4);
-		float4 a = make_float4(0, 0, 0, 0), b = a;
-		if (MASK)
-			a = ld4(coef + cv * 4), b = ld4(coef + C + cv * 4);
+		float kk[W], a[W], b[W];
+		if (MODE == 0)
+			ldv(x + cw * W, kk);
+		else {
+#pragma unroll
+			for (int k = 0; k < W; k++)
+				kk[k] = mean[cw * W + k];
+		}
+#pragma unroll
+		for (int k = 0; k < W; k++)
+			a[k] = MASK ? coef[cw * W + k] : 0.f, b[k] = MASK ? coef[C + cw * W + k] : 0.f;
 		const size_t step = (size_t)gridDim.y * rpi;
 		size_t r = (size_t)blockIdx.y * rpi + ty;
-#define BN_ACC(xv, gv) \
-		{ \
-			if (MODE == 0) \
-			{ \
-				const float d0 = xv.x - k.x, d1 = xv.y - k.y, d2 = xv.z - k.z, d3 = xv.w - k.w; \
-				s1.x += d0, s1.y += d1, s1.z += d2, s1.w += d3; \
-				s2.x += d0 * d0, s2.y += d1 * d1, s2.z += d2 * d2, s2.w += d3 * d3; \
-			} else { \
-				float m0_ = gv.x, m1_ = gv.y, m2_ = gv.z, m3_ = gv.w; \
-				if (MASK) \
-				{ \
-					m0_ = fmaf(xv.x, a.x, b.x) > 0.f ? m0_ : 0.f, m1_ = fmaf(xv.y, a.y, b.y) > 0.f ? m1_ : 0.f; \
-					m2_ = fmaf(xv.z, a.z, b.z) > 0.f ? m2_ : 0.f, m3_ = fmaf(xv.w, a.w, b.w) > 0.f ? m3_ : 0.f; \
-				} \
-				s1.x += m0_, s1.y += m1_, s1.z += m2_, s1.w += m3_; \
-				s2.x += m0_ * (xv.x - k.x), s2.y += m1_ * (xv.y - k.y), s2.z += m2_ * (xv.z - k.z), s2.w += m3_ * (xv.w - k.w); \
-			} \
-		}
+		auto acc = [&](const float (&xv)[W], const float (&gv)[W]) {
+#pragma unroll
+			for (int k = 0; k < W; k++)
+			{
+				if (MODE == 0)
+				{
+					const float d = xv[k] - kk[k];
+					s1[k] += d, s2[k] += d * d;
+				} else {
+					float m = gv[k];
+					if (MASK)
+						m = fmaf(xv[k], a[k], b[k]) > 0.f ? m : 0.f;
+					s1[k] += m, s2[k] += m * (xv[k] - kk[k]);
+				}
+			}
+		};
 		for (; r + 3 * step < rows; r += 4 * step)
 		{
-			const float4 x0 = ld4(x + r * C + cv * 4), x1 = ld4(x + (r + step) * C + cv * 4), x2 = ld4(x + (r + 2 * step) * C + cv * 4), x3 = ld4(x + (r + 3 * step) * C + cv * 4);
-			float4 g0 = x0, g1 = x0, g2 = x0, g3 = x0;
-			if (MODE == 1)
-				g0 = ld4(g + r * C + cv * 4), g1 = ld4(g + (r + step) * C + cv * 4), g2 = ld4(g + (r + 2 * step) * C + cv * 4), g3 = ld4(g + (r + 3 * step) * C + cv * 4);
-			BN_ACC(x0, g0) BN_ACC(x1, g1) BN_ACC(x2, g2) BN_ACC(x3, g3)
+			float xv[4][W], gv[4][W];
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+			{
+				ldv(x + (r + u * step) * C + cw * W, xv[u]);
+				if (MODE == 1)
+					ldv(g + (r + u * step) * C + cw * W, gv[u]);
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+				acc(xv[u], MODE == 1 ? gv[u] : xv[u]);
 		}
 		for (; r < rows; r += step)
 		{
-			const float4 x0 = ld4(x + r * C + cv * 4);
-			float4 g0 = x0;
+			float xv[W], gv[W];
+			ldv(x + r * C + cw * W, xv);
 			if (MODE == 1)
-				g0 = ld4(g + r * C + cv * 4);
-			BN_ACC(x0, g0)
+				ldv(g + r * C + cw * W, gv);
+			acc(xv, MODE == 1 ? gv : xv);
 		}
-#undef BN_ACC
 	}
-	sh[0][threadIdx.x] = s1, sh[1][threadIdx.x] = s2;
+#pragma unroll
+	for (int k = 0; k < W; k++)
+		sh[0][threadIdx.x][k] = s1[k], sh[1][threadIdx.x][k] = s2[k];
 	__syncthreads();
-	if (ty == 0 && cv < CV)
+	if (ty == 0 && cw < CW)
 	{
 		for (int t = 1; t < rpi; t++)
-		{
-			const float4 u = sh[0][t * cpb + tx], v = sh[1][t * cpb + tx];
-			s1.x += u.x, s1.y += u.y, s1.z += u.z, s1.w += u.w;
-			s2.x += v.x, s2.y += v.y, s2.z += v.z, s2.w += v.w;
-		}
+#pragma unroll
+			for (int k = 0; k < W; k++)
+				s1[k] += sh[0][t * cpb + tx][k], s2[k] += sh[1][t * cpb + tx][k];
 		// per-block partial sums; bn_finalize_partials_kernel adds the gridDim.y rows in a fixed order (no atomics: 600 same-address
 		// fp64 atomics per channel cost ~15 us per launch, profiles/r01_ncu_bn_reduce_apply.txt, and made the result run-dependent)
 		float* const row = part + (size_t)blockIdx.y * 2 * C;
-		st4(row + cv * 4, s1);
-		st4(row + C + cv * 4, s2);
+#pragma unroll
+		for (int k = 0; k < W; k++)
+			row[cw * W + k] = s1[k], row[C + cw * W + k] = s2[k];
 	}
 }
 
@@ -620,11 +636,12 @@ static int run_reduce(cudaStream_t s, const T* x, const T* g, const float* mean,
 {
 	// NHWC vector path: leaves *part_rows > 0 rows of per-block partial sums in `part` (finished by bn_finalize_partials_kernel);
 	// generic path: one block per channel writes the sums to ws directly (*part_rows = 0)
-	if (inner == 1 && C % 4 == 0 && aligned_v4(x) && (MODE == 0 || aligned_v4(g)))
+	constexpr int W = Vec16<T>::W;
+	if (inner == 1 && C % W == 0 && aligned_v16(x) && (MODE == 0 || aligned_v16(g)))
 	{
 		int cpb;
 		dim3 grid;
-		reduce_config(outer, C / 4, cpb, grid);
+		reduce_config(outer, C / W, cpb, grid);
 		bn_reduce_kernel<T, MODE, MASK><<<grid, 256, 0, s>>>(x, g, mean, coef, outer, C, part, cpb);
 		*part_rows = (int)grid.y;
 		return check("bn_reduce");
@@ -730,7 +747,7 @@ static int bn_bwd_t(cudaStream_t s, const T* g, const T* x, const float* scale, 
 	double* ws = ws_sums(workspace);
 	float* coef = ws_coef(workspace, C);
 	const int mask = bias != 0;
-	const bool vec = inner == 1 && C % 4 == 0 && aligned_v4(x) && aligned_v4(g);
+	const bool vec = inner == 1 && C % Vec16<T>::W == 0 && aligned_v16(x) && aligned_v16(g); // = the condition under which run_reduce leaves partial rows
 	if (mask)
 	{
 		bn_mask_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, scale, bias, saved_mean, saved_inv_std, coef);
@@ -806,20 +823,23 @@ int bn_bwd_16(cudaStream_t s, int kind, const void* g, const void* x, const floa
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) add_relu_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ y, T* __restrict__ out, const size_t n, const int vec)
 {
-	const size_t n4 = vec ? n >> 2 : 0;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+	constexpr int W = Vec16<T>::W; // one 16-byte access per operand and iteration
+	const size_t nw = vec ? n / W : 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nw; i += (size_t)gridDim.x * blockDim.x)
 	{
-		const float4 u = ld4(a + i * 4), v = ld4(b + i * 4);
-		float4 o = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
-		if (MODE == 0)
-			o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-		else {
-			const float4 m = ld4(y + i * 4);
-			o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
+		float u[W], v[W], m[W], o[W];
+		ldv(a + i * W, u), ldv(b + i * W, v);
+		if (MODE == 1)
+			ldv(y + i * W, m);
+#pragma unroll
+		for (int k = 0; k < W; k++)
+		{
+			o[k] = u[k] + v[k];
+			o[k] = MODE == 0 ? fmaxf(o[k], 0.f) : (m[k] > 0.f ? o[k] : 0.f);
 		}
-		st4(out + i * 4, o);
+		stv(out + i * W, o);
 	}
-	for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	for (size_t i = nw * W + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 	{
 		const float o = ldf(a + i) + ldf(b + i);
 		stf(out + i, MODE == 0 ? fmaxf(o, 0.f) : (ldf(y + i) > 0.f ? o : 0.f));
@@ -830,8 +850,8 @@ static int add_relu_fwd_t(cudaStream_t s, const T* a, const T* b, T* out, size_t
 {
 	if (n == 0)
 		return 0;
-	const int vec = aligned_v4(a) && aligned_v4(b) && aligned_v4(out);
-	add_relu_kernel<T, 0><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, (const T*)0, out, n, vec);
+	const int vec = aligned_v16(a) && aligned_v16(b) && aligned_v16(out);
+	add_relu_kernel<T, 0><<<grid_for(vec ? n / Vec16<T>::W + 1 : n, 256), 256, 0, s>>>(a, b, (const T*)0, out, n, vec);
 	return check("add_relu_fwd");
 }
 template <typename T>
@@ -839,8 +859,8 @@ static int add_relu_bwd_t(cudaStream_t s, const T* a, const T* b, const T* y, T*
 {
 	if (n == 0)
 		return 0;
-	const int vec = aligned_v4(a) && aligned_v4(b) && aligned_v4(out) && aligned_v4(y);
-	add_relu_kernel<T, 1><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, b, y, out, n, vec);
+	const int vec = aligned_v16(a) && aligned_v16(b) && aligned_v16(out) && aligned_v16(y);
+	add_relu_kernel<T, 1><<<grid_for(vec ? n / Vec16<T>::W + 1 : n, 256), 256, 0, s>>>(a, b, y, out, n, vec);
 	return check("add_relu_bwd");
 }
 int ew_add_relu_fwd_f32(cudaStream_t s, const float* a, const float* b, float* out, size_t n) { return add_relu_fwd_t<float>(s, a, b, out, n); }

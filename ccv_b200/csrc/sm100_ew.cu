@@ -524,6 +524,23 @@ int reduce_sum_bcast_f32(cudaStream_t s, const float* a, const int* adim, const 
 // =============================================================================================== pooling (NHWC)
 // pool/ccv_nnc_max_pool_cpu_ref.c:13-59, pool/ccv_nnc_avg_pool_cpu_ref.c:13-58: the window is clipped to the input
 // (SET_BORDER_OFFSET_SIZE_FOR, ccv_nnc_internal.h:209-213); the average divides by the clipped window size.
+// VEC channels of one pixel: one 16-byte access when VEC is the type's vector width, a scalar access when VEC == 1
+template <typename T, int VEC>
+__device__ __forceinline__ void pool_load(const T* p, float (&v)[VEC])
+{
+	if constexpr (VEC == 1)
+		v[0] = ldf(p);
+	else
+		ldv(p, v);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void pool_store(T* p, const float (&v)[VEC])
+{
+	if constexpr (VEC == 1)
+		stf(p, v[0]);
+	else
+		stv(p, v);
+}
 template <typename T, int VEC, int IS_MAX>
 __global__ void pool_fwd_kernel(const PoolGeom g, const T* __restrict__ a, T* __restrict__ b)
 {
@@ -561,12 +578,7 @@ __global__ void pool_fwd_kernel(const PoolGeom g, const T* __restrict__ a, T* __
 			{
 				const T* ap = a + n * g.an + h * g.ah + w * g.aw + c;
 				float x[VEC];
-				if (VEC == 4)
-				{
-					const float4 t = ld4(ap);
-					x[0] = t.x, x[1 % VEC] = t.y, x[2 % VEC] = t.z, x[3 % VEC] = t.w;
-				} else
-					x[0] = ldf(ap);
+				pool_load<T, VEC>(ap, x);
 #pragma unroll
 				for (int k = 0; k < VEC; k++)
 					v[k] = IS_MAX ? fmaxf(v[k], x[k]) : v[k] + x[k];
@@ -579,16 +591,14 @@ __global__ void pool_fwd_kernel(const PoolGeom g, const T* __restrict__ a, T* __
 				v[k] = v[k] / inv;
 		}
 		T* bp = b + n * g.bn + p * g.bh + q * g.bw + c;
-		if (VEC == 4)
-			st4(bp, make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
-		else
-			stf(bp, v[0]);
+		pool_store<T, VEC>(bp, v);
 	}
 }
 template <typename T>
 static bool pool_vec_ok(const PoolGeom& g, const T* a, const T* b)
 {
-	return g.C % 4 == 0 && aligned_v4(a) && aligned_v4(b) && g.aw % 4 == 0 && g.ah % 4 == 0 && g.an % 4 == 0 && g.bw % 4 == 0 && g.bh % 4 == 0 && g.bn % 4 == 0;
+	constexpr int W = Vec16<T>::W; // channels per 16-byte access
+	return g.C % W == 0 && aligned_v16(a) && aligned_v16(b) && g.aw % W == 0 && g.ah % W == 0 && g.an % W == 0 && g.bw % W == 0 && g.bh % W == 0 && g.bn % W == 0;
 }
 template <typename T, int IS_MAX>
 static int pool_fwd_t(cudaStream_t s, const PoolGeom& g, const T* a, T* b)
@@ -597,7 +607,7 @@ static int pool_fwd_t(cudaStream_t s, const PoolGeom& g, const T* a, T* b)
 	if (total == 0)
 		return 0;
 	if (pool_vec_ok(g, a, (const T*)b))
-		pool_fwd_kernel<T, 4, IS_MAX><<<grid_for(total / 4, 256), 256, 0, s>>>(g, a, b);
+		pool_fwd_kernel<T, Vec16<T>::W, IS_MAX><<<grid_for(total / Vec16<T>::W, 256), 256, 0, s>>>(g, a, b);
 	else
 		pool_fwd_kernel<T, 1, IS_MAX><<<grid_for(total, 256), 256, 0, s>>>(g, a, b);
 	return check(IS_MAX ? "pool_max_fwd" : "pool_avg_fwd");
@@ -640,19 +650,24 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const T* __restrict__ gb, cons
 			h = (int)(r % g.H);
 			n = (int)(r / g.H);
 		}
-		if (!IS_MAX && VEC == 4 && g.R == g.stride_h && g.S == g.stride_w && g.pad_h == 0 && g.pad_w == 0)
+		if (!IS_MAX && VEC > 1 && g.R == g.stride_h && g.S == g.stride_w && g.pad_h == 0 && g.pad_w == 0)
 		{
 			// non-overlapping windows (the 2 x 2 / 2 shortcut pools, the global pool): every input position belongs to at most one
 			// window, whose size is never clipped -> one load, one divide per lane, one store
 			const int p = h / g.stride_h, q = w / g.stride_w;
-			float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+			float o[VEC];
+#pragma unroll
+			for (int k = 0; k < VEC; k++)
+				o[k] = 0.f;
 			if (p < g.P && q < g.Q)
 			{
-				const float4 t = ld4(gb + n * g.bn + p * g.bh + q * g.bw + c);
+				pool_load<T, VEC>(gb + n * g.bn + p * g.bh + q * g.bw + c, o);
 				const float inv = (float)(g.R * g.S);
-				o = make_float4(t.x / inv, t.y / inv, t.z / inv, t.w / inv);
+#pragma unroll
+				for (int k = 0; k < VEC; k++)
+					o[k] = o[k] / inv;
 			}
-			st4(ga + n * g.an + h * g.ah + w * g.aw + c, o);
+			pool_store<T, VEC>(ga + n * g.an + h * g.ah + w * g.aw + c, o);
 			continue;
 		}
 		// windows p with p * stride - pad <= h < p * stride - pad + R
@@ -664,13 +679,7 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const T* __restrict__ gb, cons
 			acc[k] = 0.f, x[k] = 0.f;
 		if (IS_MAX)
 		{
-			const T* ap = a + n * g.an + h * g.ah + w * g.aw + c;
-			if (VEC == 4)
-			{
-				const float4 t = ld4(ap);
-				x[0] = t.x, x[1 % VEC] = t.y, x[2 % VEC] = t.z, x[3 % VEC] = t.w;
-			} else
-				x[0] = ldf(ap);
+			pool_load<T, VEC>(a + n * g.an + h * g.ah + w * g.aw + c, x);
 		}
 		for (int p = p_lo; p <= p_hi; p++)
 		{
@@ -683,20 +692,9 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const T* __restrict__ gb, cons
 					continue;
 				const size_t o = n * g.bn + p * g.bh + q * g.bw + c;
 				float gv[VEC], bv[VEC];
-				if (VEC == 4)
-				{
-					const float4 t = ld4(gb + o);
-					gv[0] = t.x, gv[1 % VEC] = t.y, gv[2 % VEC] = t.z, gv[3 % VEC] = t.w;
-					if (IS_MAX)
-					{
-						const float4 u = ld4(b + o);
-						bv[0] = u.x, bv[1 % VEC] = u.y, bv[2 % VEC] = u.z, bv[3 % VEC] = u.w;
-					}
-				} else {
-					gv[0] = ldf(gb + o);
-					if (IS_MAX)
-						bv[0] = ldf(b + o);
-				}
+				pool_load<T, VEC>(gb + o, gv);
+				if (IS_MAX)
+					pool_load<T, VEC>(b + o, bv);
 				if (IS_MAX)
 				{
 #pragma unroll
@@ -713,10 +711,7 @@ __global__ void pool_bwd_kernel(const PoolGeom g, const T* __restrict__ gb, cons
 			}
 		}
 		T* hp = ga + n * g.an + h * g.ah + w * g.aw + c;
-		if (VEC == 4)
-			st4(hp, make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]));
-		else
-			stf(hp, acc[0]);
+		pool_store<T, VEC>(hp, acc);
 	}
 }
 template <typename T>
@@ -725,8 +720,8 @@ static int pool_max_bwd_t(cudaStream_t s, const PoolGeom& g, const T* grad_b, co
 	const size_t total = (size_t)g.N * g.H * g.W * g.C;
 	if (total == 0)
 		return 0;
-	if (pool_vec_ok(g, a, b) && aligned_v4(grad_b) && aligned_v4(grad_a))
-		pool_bwd_kernel<T, 4, 1><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
+	if (pool_vec_ok(g, a, b) && aligned_v16(grad_b) && aligned_v16(grad_a))
+		pool_bwd_kernel<T, Vec16<T>::W, 1><<<grid_for(total / Vec16<T>::W, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
 	else
 		pool_bwd_kernel<T, 1, 1><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, a, b, grad_a);
 	return check("pool_max_bwd");
@@ -772,7 +767,7 @@ static int pool_avg_bwd_t(cudaStream_t s, const PoolGeom& g, const T* grad_b, T*
 		return check("pool_avg_bwd");
 	}
 	if (pool_vec_ok(g, (const T*)grad_a, grad_b))
-		pool_bwd_kernel<T, 4, 0><<<grid_for(total / 4, 256), 256, 0, s>>>(g, grad_b, (const T*)0, (const T*)0, grad_a);
+		pool_bwd_kernel<T, Vec16<T>::W, 0><<<grid_for(total / Vec16<T>::W, 256), 256, 0, s>>>(g, grad_b, (const T*)0, (const T*)0, grad_a);
 	else
 		pool_bwd_kernel<T, 1, 0><<<grid_for(total, 256), 256, 0, s>>>(g, grad_b, (const T*)0, (const T*)0, grad_a);
 	return check("pool_avg_bwd");
@@ -1147,18 +1142,20 @@ int sgd_multi_any(cudaStream_t s, int tensors, int g_kind, const void* const* g,
 template <typename T, int BWD>
 __global__ void relu16_kernel(const T* __restrict__ g, const T* __restrict__ a, T* __restrict__ out, const size_t n, const int vec)
 {
-	const size_t n4 = vec ? n >> 2 : 0;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+	constexpr int W = Vec16<T>::W;
+	const size_t nw = vec ? n / W : 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nw; i += (size_t)gridDim.x * blockDim.x)
 	{
-		const float4 x = ld4(a + i * 4);
-		if (!BWD)
-			st4(out + i * 4, make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)));
-		else {
-			const float4 y = ld4(g + i * 4);
-			st4(out + i * 4, make_float4(x.x > 0 ? y.x : 0.f, x.y > 0 ? y.y : 0.f, x.z > 0 ? y.z : 0.f, x.w > 0 ? y.w : 0.f));
-		}
+		float x[W], y[W], o[W];
+		ldv(a + i * W, x);
+		if (BWD)
+			ldv(g + i * W, y);
+#pragma unroll
+		for (int k = 0; k < W; k++)
+			o[k] = BWD ? (x[k] > 0 ? y[k] : 0.f) : fmaxf(x[k], 0.f);
+		stv(out + i * W, o);
 	}
-	for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	for (size_t i = nw * W + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		stf(out + i, BWD ? (ldf(a + i) > 0 ? ldf(g + i) : 0.f) : fmaxf(ldf(a + i), 0.f));
 }
 template <typename T>
@@ -1166,11 +1163,11 @@ static int relu16_t(cudaStream_t s, const T* g, const T* a, T* out, size_t n, in
 {
 	if (n == 0)
 		return 0;
-	const int vec = aligned_v4(a) && aligned_v4(out) && (!bwd || aligned_v4(g));
+	const int vec = aligned_v16(a) && aligned_v16(out) && (!bwd || aligned_v16(g));
 	if (bwd)
-		relu16_kernel<T, 1><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(g, a, out, n, vec);
+		relu16_kernel<T, 1><<<grid_for(vec ? n / Vec16<T>::W + 1 : n, 256), 256, 0, s>>>(g, a, out, n, vec);
 	else
-		relu16_kernel<T, 0><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(g, a, out, n, vec);
+		relu16_kernel<T, 0><<<grid_for(vec ? n / Vec16<T>::W + 1 : n, 256), 256, 0, s>>>(g, a, out, n, vec);
 	return check("relu16");
 }
 int ew_relu_fwd_16(cudaStream_t s, int kind, const void* a, void* b, size_t n)
@@ -1188,19 +1185,26 @@ struct SumArgs16 {
 template <typename T>
 __global__ void sum16_kernel(const SumArgs16 a, T* __restrict__ out, const size_t n, const int vec)
 {
-	const size_t n4 = vec ? n >> 2 : 0;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+	constexpr int W = Vec16<T>::W;
+	const size_t nw = vec ? n / W : 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nw; i += (size_t)gridDim.x * blockDim.x)
 	{
-		float4 acc = make_float4(0, 0, 0, 0);
+		float acc[W];
+#pragma unroll
+		for (int k = 0; k < W; k++)
+			acc[k] = 0.f;
 #pragma unroll 8
 		for (int j = 0; j < a.k; j++)
 		{
-			const float4 v = ld4(reinterpret_cast<const T*>(a.in[j]) + i * 4);
-			acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+			float v[W];
+			ldv(reinterpret_cast<const T*>(a.in[j]) + i * W, v);
+#pragma unroll
+			for (int k = 0; k < W; k++)
+				acc[k] += v[k];
 		}
-		st4(out + i * 4, acc);
+		stv(out + i * W, acc);
 	}
-	for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	for (size_t i = nw * W + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 	{
 		float acc = 0.f;
 		for (int j = 0; j < a.k; j++)
@@ -1217,13 +1221,13 @@ int ew_sum_16(cudaStream_t s, int kind, const void* const* inputs, int k, void* 
 		return 1;
 	SumArgs16 a;
 	a.k = k;
-	bool vec = (((uintptr_t)out) & 7) == 0;
+	bool vec = (((uintptr_t)out) & 15) == 0;
 	for (int j = 0; j < k; j++)
-		a.in[j] = inputs[j], vec = vec && (((uintptr_t)inputs[j]) & 7) == 0;
+		a.in[j] = inputs[j], vec = vec && (((uintptr_t)inputs[j]) & 15) == 0;
 	if (kind == 1)
-		sum16_kernel<__nv_bfloat16><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, (__nv_bfloat16*)out, n, vec);
+		sum16_kernel<__nv_bfloat16><<<grid_for(vec ? (n >> 3) + 1 : n, 256), 256, 0, s>>>(a, (__nv_bfloat16*)out, n, vec);
 	else
-		sum16_kernel<__half><<<grid_for(vec ? (n >> 2) + 1 : n, 256), 256, 0, s>>>(a, (__half*)out, n, vec);
+		sum16_kernel<__half><<<grid_for(vec ? (n >> 3) + 1 : n, 256), 256, 0, s>>>(a, (__half*)out, n, vec);
 	return check("ew_sum16");
 }
 // column sums with any input / output element kind: per-block partial rows (fp32) in the workspace, combined in a fixed order

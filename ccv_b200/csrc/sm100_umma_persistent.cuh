@@ -345,12 +345,15 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 					// lane = row.  The 32 x 32 chunk goes (+bias) into one of this warp's two 4 KB buffers in the 128-byte-swizzled
 					// layout the output tensor map expects and leaves as ONE TMA tile store: ~60 instructions per chunk instead of
 					// ~400 (LDS / address checks / STG per row: the epilogue was issue-bound, profiles/r01_ncu_expand_1x1_*.txt)
+					const int col0 = n0 + c * 32;
+					if (col0 >= N)
+						continue; // a chunk wholly past the last column: nothing to store.  It must not take a buffer either -- the
+						          // two-buffer rotation below relies on exactly one bulk group being committed per buffer use
 					float* const buf = scratch + (chunk_no & 1) * 1024;
 					chunk_no++;
 					if (lane == 0)
 						bulk_wait_group_read<1>(); // the store issued two chunks ago has finished reading this buffer
 					__syncwarp();
-					const int col0 = n0 + c * 32;
 					float v[32];
 #pragma unroll
 					for (int i = 0; i < 32; i++)
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 						}
 						st_k[ci] = k, st_s1[ci] += s1, st_s2[ci] += s2;
 					}
-					if (lane == 0 && col0 < N)
+					if (lane == 0)
 					{
 						tma_store_2d(&tmC, buf, col0, m0 + quarter * 32);
 						bulk_commit_group();
