@@ -31,6 +31,7 @@ CMD_IDS = dict(
     MUL=0x24721a46, RELU=0xc51eaa80, RMSNORM=0x6889e9d0, SCALAR_MUL=0x8b4d86aa,
     SCALED_DOT_PRODUCT_ATTENTION=0x284ed926, SET=0x2b070804, SGD=0xe650ad26, SOFTMAX=0xc969a252,
     SOFTMAX_CROSSENTROPY=0xc26b7b5e, TRANSPOSE=0xb4d506e0, UPSAMPLE=0x73875556,
+    ADAMW=0x4f5d4870, GELU=0xb1527ab8, SWISH=0x583d90c2, INDEX_SELECT=0x7ee7771e,
 )
 for _k, _v in CMD_IDS.items():
     globals()["CCV_NNC_%s_FORWARD" % _k] = _v
@@ -83,6 +84,14 @@ class _Sgd(C.Structure):
     _fields_ = [("nesterov", C.c_int), ("rate", C.c_float), ("scale", C.c_float), ("decay", C.c_float), ("momentum", C.c_float), ("dampening", C.c_float)]
 
 
+class _Adam(C.Structure):
+    _fields_ = [("step", C.c_int), ("rate", C.c_float), ("scale", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("decay", C.c_float), ("epsilon", C.c_float), ("amsgrad", C.c_int)]
+
+
+class _Gelu(C.Structure):
+    _fields_ = [("tanh", C.c_int)]
+
+
 class _Blas(C.Structure):
     _fields_ = [("transpose_a", C.c_int * 2), ("transpose_b", C.c_int * 2), ("a", C.c_float * 3), ("flags", C.c_int)]
 
@@ -109,7 +118,7 @@ class _Sdpa(C.Structure):
 
 class _CmdUnion(C.Union):
     _fields_ = [("convolution", _Convolution), ("pool", _Pool), ("bnorm", _Bnorm), ("lnorm", _Lnorm), ("gnorm", _Gnorm), ("rmsnorm", _Rmsnorm),
-                ("sgd", _Sgd), ("blas", _Blas), ("label_smoothing", _LabelSmoothing), ("reduce", _Reduce), ("transpose", _Transpose),
+                ("sgd", _Sgd), ("adam", _Adam), ("gelu", _Gelu), ("blas", _Blas), ("label_smoothing", _LabelSmoothing), ("reduce", _Reduce), ("transpose", _Transpose),
                 ("upsample", _Upsample), ("scaled_dot_product_attention", _Sdpa), ("userdata", C.c_void_p)]
 
 

@@ -503,6 +503,41 @@ def CMD_SOFTMAX_CROSSENTROPY_BACKWARD(trim0=0.0, trim1=1.0, **kw):
     return _label_smoothing(abi.CCV_NNC_SOFTMAX_CROSSENTROPY_BACKWARD, trim0, trim1, **kw)
 
 
+def CMD_GELU_FORWARD(tanh=0, **kw):
+    c = _simple(abi.CCV_NNC_GELU_FORWARD, **kw)
+    c.info.gelu.tanh = tanh
+    return c
+
+
+def CMD_GELU_BACKWARD(tanh=0, **kw):
+    c = _simple(abi.CCV_NNC_GELU_BACKWARD, **kw)
+    c.info.gelu.tanh = tanh
+    return c
+
+
+def CMD_SWISH_FORWARD(**kw):
+    return _simple(abi.CCV_NNC_SWISH_FORWARD, **kw)
+
+
+def CMD_SWISH_BACKWARD(**kw):
+    return _simple(abi.CCV_NNC_SWISH_BACKWARD, **kw)
+
+
+def CMD_INDEX_SELECT_FORWARD(**kw):
+    return _simple(abi.CCV_NNC_INDEX_SELECT_FORWARD, **kw)
+
+
+def CMD_INDEX_SELECT_BACKWARD(**kw):
+    return _simple(abi.CCV_NNC_INDEX_SELECT_BACKWARD, **kw)
+
+
+def CMD_ADAMW_FORWARD(step, rate, beta1, beta2, decay, epsilon, amsgrad=0, scale=1.0, **kw):
+    c = _simple(abi.CCV_NNC_ADAMW_FORWARD, **kw)
+    a = c.info.adam
+    a.step, a.rate, a.scale, a.beta1, a.beta2, a.decay, a.epsilon, a.amsgrad = step, rate, scale, beta1, beta2, decay, epsilon, amsgrad
+    return c
+
+
 def CMD_SGD_FORWARD(nesterov, rate, scale, decay, momentum, dampening, **kw):
     c = _simple(abi.CCV_NNC_SGD_FORWARD, **kw)
     s = c.info.sgd

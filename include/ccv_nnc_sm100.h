@@ -217,6 +217,19 @@ typedef struct {
 			float dampening;
 		} sgd;
 		struct {
+			int step;
+			float rate;
+			float scale;
+			float beta1;
+			float beta2;
+			float decay;
+			float epsilon;
+			int amsgrad;
+		} adam;
+		struct {
+			int tanh;
+		} gelu;
+		struct {
 			int transpose_a[2];
 			int transpose_b[2];
 			float a[3];
@@ -356,6 +369,14 @@ enum {
 	CCV_NNC_SET_BACKWARD = 0x2b070805,
 	CCV_NNC_SGD_FORWARD = 0xe650ad26,
 	CCV_NNC_SGD_BACKWARD = 0xe650ad27,
+	CCV_NNC_ADAMW_FORWARD = 0x4f5d4870,
+	CCV_NNC_ADAMW_BACKWARD = 0x4f5d4871,
+	CCV_NNC_GELU_FORWARD = 0xb1527ab8,
+	CCV_NNC_GELU_BACKWARD = 0xb1527ab9,
+	CCV_NNC_SWISH_FORWARD = 0x583d90c2,
+	CCV_NNC_SWISH_BACKWARD = 0x583d90c3,
+	CCV_NNC_INDEX_SELECT_FORWARD = 0x7ee7771e,
+	CCV_NNC_INDEX_SELECT_BACKWARD = 0x7ee7771f,
 	CCV_NNC_SOFTMAX_FORWARD = 0xc969a252,
 	CCV_NNC_SOFTMAX_BACKWARD = 0xc969a253,
 	CCV_NNC_SOFTMAX_CROSSENTROPY_FORWARD = 0xc26b7b5e,
@@ -415,6 +436,9 @@ enum {
 	X(CCV_NNC_TRANSPOSE_FORWARD) X(CCV_NNC_TRANSPOSE_BACKWARD) \
 	X(CCV_NNC_DATATYPE_CONVERSION_FORWARD) X(CCV_NNC_DATATYPE_CONVERSION_BACKWARD) \
 	X(CCV_NNC_SGD_FORWARD) X(CCV_NNC_SGD_BACKWARD) \
+	X(CCV_NNC_ADAMW_FORWARD) X(CCV_NNC_ADAMW_BACKWARD) \
+	X(CCV_NNC_GELU_FORWARD) X(CCV_NNC_GELU_BACKWARD) X(CCV_NNC_SWISH_FORWARD) X(CCV_NNC_SWISH_BACKWARD) \
+	X(CCV_NNC_INDEX_SELECT_FORWARD) X(CCV_NNC_INDEX_SELECT_BACKWARD) \
 	X(CCV_NNC_CATEGORICAL_CROSSENTROPY_FORWARD) X(CCV_NNC_CATEGORICAL_CROSSENTROPY_BACKWARD) \
 	X(CCV_NNC_SOFTMAX_CROSSENTROPY_FORWARD) X(CCV_NNC_SOFTMAX_CROSSENTROPY_BACKWARD) \
 	X(CCV_NNC_COMM_ALLREDUCE_FORWARD) X(CCV_NNC_COMM_ALLREDUCE_BACKWARD)
