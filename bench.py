@@ -321,6 +321,7 @@ def run_sdpa_cfg5(args):
     for t in host[:3]:
         t.upload(ramp)
     lse = nnc.gpu_tensor([B, H, S])
+    grads = [nnc.gpu_tensor([B, S, H, D], datatype=abi.CCV_16BF) for _ in range(3)]
     xfer = nnc.CMD_DATA_TRANSFER_FORWARD()
     assert nnc.cmd_exec(xfer, None, 0, host[:3], dev[:3], stream) == 0
     sampler = ClockSampler(0)
@@ -349,18 +350,39 @@ def run_sdpa_cfg5(args):
                 fn()
             e1.record(stream)
             res[name] = e0.elapsed_ms(e1) / reps
+        # backward (dq, dk, dv from dout, q, k, v and the forward's saved o / lse: inputs[9], inputs[10]); dout = the q ramp
+        bcmd = nnc._simple(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD)
+        bcmd.info.scaled_dot_product_attention.scale = 1.0 / np.sqrt(D)
+        bcmd.info.scaled_dot_product_attention.is_causal = causal
+        bcmd.info.scaled_dot_product_attention.deterministic = 1
+        b_ins = [dev[0], None, None, dev[0], dev[1], dev[2], None, None, None, dev[3], lse]
+
+        def bwd():
+            assert nnc.cmd_exec(bcmd, None, 0, b_ins, grads, stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+        for _ in range(2):
+            bwd()
+        e0, e1 = nnc.Event(), nnc.Event()
+        stream.wait()
+        e0.record(stream)
+        for _ in range(10):
+            bwd()
+        e1.record(stream)
+        bms = e0.elapsed_ms(e1) / 10
+        bflops = 10.0 * B * H * S * S * D * (0.5 if causal else 1.0)  # the 5 GEMMs of the backward; the kernels issue 7 (S and dP twice)
         flops = 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
         byts = 4.0 * n * 2 + B * H * S * 4
         ms = res["device"]
         out["causal" if causal else "full"] = {
+            "backward": {"ms": bms, "tflops": bflops / bms * 1e-9, "frac_of_bf16_peak": bflops / bms * 1e-9 / pk["bf16_tflops"], "algorithmic_flops": bflops,
+                         "note": "fused deterministic tcgen05 backward (prep + dK/dV kernel + dQ kernel), 5-GEMM flop count"},
             "ms": ms, "tflops": flops / ms * 1e-9, "frac_of_bf16_peak": flops / ms * 1e-9 / pk["bf16_tflops"], "gbs": byts / ms * 1e-6, "frac_of_hbm_peak": byts / ms * 1e-6 / pk["hbm_gbs"],
             "algorithmic_flops": flops, "algorithmic_bytes": byts, "l2": "Q + K + V + O = 1.07 GB per launch: larger than the 126 MB L2",
             "e2e": {"ms": res["e2e"], "tflops": flops / res["e2e"] * 1e-9, "h2d_bytes_per_step": int(3 * n * 2), "d2h_bytes_per_step": int(n * 2)}}
     sampler.stop_flag = True
     sampler.join()
     out["clocks"] = sampler.summary()
-    out["workload"] = "CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD bf16 B=32 H=16 S=2048 D=128 (BASELINE.json configs[4]), tcgen05 flash-attention kernel, LSE written"
-    for t in dev + host + [lse, stream]:
+    out["workload"] = "CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD bf16 B=32 H=16 S=2048 D=128 (BASELINE.json configs[4]), tcgen05 flash-attention kernel, LSE written; `backward` = CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD on the same tensors"
+    for t in dev + host + grads + [lse, stream]:
         t.free()
     return out
 

@@ -212,9 +212,8 @@ int ccv_nnc_sm100_exec_sdpa_back(SM100_EXEC_ARGS)
 	const int dt = CCV_GET_DATA_TYPE(inputs[3]->info.datatype);
 	if (dt != CCV_32F)
 	{
-		// 16-bit backward, functional form: widen g, q, k, v to fp32 in the stream workspace, run the fp32 composed backward
-		// (TF32 tensor-core GEMMs per (b, h)), narrow dq, dk, dv back (round to nearest even).  A fused 16-bit flash
-		// backward kernel is the next step; this keeps the command usable for bf16 / fp16 training meanwhile.
+		// 16-bit backward.  Outside the fused kernel's shapes (below) the functional form: widen g, q, k, v to fp32 in the stream
+		// workspace, run the fp32 composed backward (TF32 tensor-core GEMMs per (b, h)), narrow dq, dk, dv back.
 		for (int i : { 0, 3, 4, 5 })
 			if (CCV_IS_TENSOR_VIEW(inputs[i]))
 				return CCV_NNC_EXEC_INVALID;
@@ -225,6 +224,32 @@ int ccv_nnc_sm100_exec_sdpa_back(SM100_EXEC_ARGS)
 			return CCV_NNC_EXEC_INVALID;
 		if (dg.B != g.B || dg.H != g.H || dg.Hk != g.Hk || dg.Sq != g.Sq || dg.Sk != g.Sk || dg.D != g.D || dg.Dv != g.Dv)
 			return CCV_NNC_EXEC_INVALID;
+		// the fused tcgen05 backward (sm100_fmha_bwd.cu) when it covers the call: head dimension 128, 16-byte aligned rows.  It works
+		// from the forward's saved output and log-sum-exp (inputs[9], inputs[10]: ...flash_attn.cu:240-241) and recomputes both itself
+		// when the caller does not pass them.
+		{
+			const ccv_nnc_tensor_t* const o_t = input_size > 9 ? inputs[9] : 0;
+			const ccv_nnc_tensor_t* const lse_t = input_size > 10 ? inputs[10] : 0;
+			const void* o_ptr = 0;
+			const float* lse_ptr = 0;
+			long long oo_b = 0, oo_s = 0, oo_h = 0;
+			if (o_t && lse_t && packed_f32(lse_t) && count_of(lse_t) == (size_t)g.B * g.H * g.Sq)
+			{
+				int oB, oS, oH, oD;
+				if (sdpa_axes(o_t, dt, oB, oS, oH, oD, oo_b, oo_s, oo_h) && oB == g.B && oS == g.Sq && oH == g.H && oD == g.Dv)
+					o_ptr = o_t->data.u8, lse_ptr = lse_t->data.f32;
+			}
+			const int need_forward = !o_ptr;
+			void* const fws = ccv_nnc_stream_context_get_workspace(stream_context, sdpa_backward_f16_workspace_bytes(g, need_forward), CCV_TENSOR_GPU_MEMORY);
+			if (!fws)
+				return CCV_NNC_EXEC_OOM;
+			const int rc = sdpa_backward_f16(stream_of(stream_context), g, dg, dt == CCV_16BF, inputs[0]->data.u8, inputs[3]->data.u8, inputs[4]->data.u8, inputs[5]->data.u8, o_ptr, oo_b, oo_s, oo_h, lse_ptr,
+				outputs[0]->data.u8, outputs[1]->data.u8, outputs[2]->data.u8, fws);
+			if (rc < 0)
+				return CCV_NNC_EXEC_INVALID;
+			if (rc == 0)
+				return CCV_NNC_EXEC_SUCCESS;
+		}
 		const size_t nq = count_of(inputs[3]), nk = count_of(inputs[4]), nv = count_of(inputs[5]), no = count_of(inputs[0]);
 		const size_t floats = no + 2 * nq + 2 * nk + 2 * nv;
 		const size_t ws_bytes = floats * sizeof(float) + 256 + sdpa_workspace_bytes(g.Sq, g.Sk, 1);

@@ -87,6 +87,13 @@ int sdpa_backward_f32(cudaStream_t s, const SdpaGeom& g, const float* dout, cons
 // returns 0 on success, 1 when the shape is not covered, < 0 on CUDA errors
 int sdpa_forward_f16(cudaStream_t s, const SdpaGeom& g, int is_bf16, const void* q, const void* k, const void* v, void* o, float* lse);
 
+// 16-bit flash attention backward on tcgen05 (sm100_fmha_bwd.cu), deterministic: D = Dv = 128.  g carries the strides of q / k / v and, in
+// o_*, of dout; dg the strides of dq / dk / dv in q_* / k_* / v_*.  out (strides oo_*) / lse = the forward's saved outputs, or NULL:
+// both are then recomputed into the workspace (sdpa_backward_f16_workspace_bytes(g, 1)).  Same return convention as the forward.
+size_t sdpa_backward_f16_workspace_bytes(const SdpaGeom& g, int need_forward);
+int sdpa_backward_f16(cudaStream_t s, const SdpaGeom& g, const SdpaGeom& dg, int is_bf16, const void* dout, const void* q, const void* k, const void* v, const void* out, long long oo_b, long long oo_s, long long oo_h,
+	const float* lse, void* dq, void* dk, void* dv, void* workspace);
+
 // bookkeeping shared by every launcher in the backend
 void count_launch(int n = 1);
 unsigned long long launch_count();

@@ -18,11 +18,7 @@
 //             Two warps per scheduler instead of one hide the tcgen05.ld / MUFU latency of the other.
 // TMEM: S0, S1, O0, O1 = 4 x 128 columns (O_j alternates so that folding O_{j-1} into the registers overlaps P_j V_j).  smem: Q 32 KB + K 2 x 32 KB + V 2 x 32 KB + P 32 KB = 192 KB.
 #include "sm100_contract.h"
-#include "sm100_ptx.cuh"
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <mutex>
-#include <stdlib.h>
+#include "sm100_fmha.cuh"
 #include <string.h>
 
 namespace sm100 {
@@ -56,32 +52,6 @@ struct FmhaSmem {
 	static constexpr int XCHG_OFF = BAR_OFF + 256; // float [6][128]: row maxima per (S buffer, half), final partial row sums per half
 	static constexpr int TOTAL = XCHG_OFF + 6 * FM_BLOCK * 4 + 1024;
 };
-
-__device__ __forceinline__ uint32_t pack2(const float a, const float b, const int is_bf16)
-{
-	if (is_bf16)
-	{
-		const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-		return *reinterpret_cast<const uint32_t*>(&v);
-	}
-	const __half2 v = __floats2half2_rn(a, b);
-	return *reinterpret_cast<const uint32_t*>(&v);
-}
-
-// sm_100 packed / 3-input fp32 instructions: FMNMX3 halves the row-max pass, FFMA2 halves the scale-and-shift in front of the exp2
-// and the running-output update (the softmax warps are issue-limited: profiles/r01_ncu_fmha_bf16_config5.txt)
-__device__ __forceinline__ float max3(const float a, const float b, const float c)
-{
-	float d;
-	asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-	return d;
-}
-__device__ __forceinline__ void fma2(float& d0, float& d1, const float a0, const float a1, const float b0, const float b1, const float c0, const float c1)
-{
-	asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\tfma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-		: "=f"(d0), "=f"(d1)
-		: "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
 
 template <int CL>
 __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const FmhaParams p)
@@ -403,44 +373,6 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 		tmem_dealloc(tmem_base, 512);
 }
 
-typedef CUresult (*encode_tiled_f)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-encode_tiled_f g_encode = 0;
-
-bool encode_init()
-{
-	static std::once_flag once;
-	std::call_once(once, []() {
-		void* fn = 0;
-		cudaDriverEntryPointQueryResult qres;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-			g_encode = (encode_tiled_f)fn;
-	});
-	return g_encode != 0;
-}
-
-// 16-bit [B, S, H, D] tensor with element strides (sb, ss, sh), D contiguous: box = {64 d, 1 head, 128 rows, 1 batch}
-bool make_map_bshd(CUtensorMap* map, const void* ptr, int B, int S, int H, int D, long long sb, long long ss, long long sh, int is_bf16)
-{
-	if ((((uintptr_t)ptr) & 15) || ((sb * 2) & 15) || ((ss * 2) & 15) || ((sh * 2) & 15))
-		return false;
-	// a stride of 0 is not encodable; extents of 1 never advance, any positive multiple of 16 bytes will do
-	if (H == 1 && sh <= 0)
-		sh = D;
-	if (B == 1 && sb <= 0)
-		sb = (long long)S * ss;
-	cuuint64_t dims[4] = { (cuuint64_t)D, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B };
-	cuuint64_t strides[3] = { (cuuint64_t)sh * 2, (cuuint64_t)ss * 2, (cuuint64_t)sb * 2 };
-	cuuint32_t box[4] = { 64, 1, FM_BLOCK, 1 };
-	cuuint32_t estr[4] = { 1, 1, 1, 1 };
-	return g_encode(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-int env_int(const char* name, int dflt)
-{
-	const char* e = getenv(name);
-	return e ? atoi(e) : dflt;
-}
-
 } // namespace
 
 // returns 0 on success, 1 when the shape is outside this kernel (D = Dv = 128, 16-byte aligned strides), < 0 on CUDA errors
@@ -451,8 +383,8 @@ int sdpa_forward_f16(cudaStream_t stream, const SdpaGeom& g, int is_bf16, const 
 	if ((((uintptr_t)o) & 15) || (g.o_b & 7) || (g.o_s & 7) || (g.o_h & 7))
 		return 1;
 	CUtensorMap tmQ, tmK, tmV;
-	if (!make_map_bshd(&tmQ, q, g.B, g.Sq, g.H, g.D, g.q_b, g.q_s, g.q_h, is_bf16) || !make_map_bshd(&tmK, k, g.B, g.Sk, g.Hk, g.D, g.k_b, g.k_s, g.k_h, is_bf16) ||
-		!make_map_bshd(&tmV, v, g.B, g.Sk, g.Hk, g.Dv, g.v_b, g.v_s, g.v_h, is_bf16))
+	if (!make_map_bshd(&tmQ, q, g.B, g.Sq, g.H, g.D, g.q_b, g.q_s, g.q_h, is_bf16, FM_BLOCK) || !make_map_bshd(&tmK, k, g.B, g.Sk, g.Hk, g.D, g.k_b, g.k_s, g.k_h, is_bf16, FM_BLOCK) ||
+		!make_map_bshd(&tmV, v, g.B, g.Sk, g.Hk, g.Dv, g.v_b, g.v_s, g.v_h, is_bf16, FM_BLOCK))
 		return 1;
 	FmhaParams p;
 	memset(&p, 0, sizeof(p));

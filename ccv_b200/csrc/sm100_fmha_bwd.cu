@@ -1,0 +1,504 @@
+// sm100_fmha_bwd.cu -- SCALED_DOT_PRODUCT_ATTENTION backward for 16-bit tensors (bf16 / fp16), head dimension 128: a fused
+// flash-attention backward on the tcgen05 tensor cores, deterministic (no atomics, every sum in one fixed order).
+// Semantics: scaled_dot_product_attention/ccv_nnc_scaled_dot_product_attention_cpu_ref.c:259-479 (dq, dk, dv of
+// O = softmax(scale * Q K^T [causal, bottom-right aligned]) V, GQA gradients summed over the query heads of a key head); the reference's
+// GPU form is gpu/ccv_nnc_scaled_dot_product_attention_flash_attn.cu:221-451 (recomputation from O and the saved log-sum-exp,
+// :410-440 its deterministic split accumulator, :444-449 the GQA sum).
+//
+//   P  = exp(scale * Q K^T - LSE)            recomputed per tile from the saved log-sum-exp
+//   dV = P^T dO
+//   dP = dO V^T,   dS = P o (dP - delta),    delta_i = sum_d dO_id O_id
+//   dQ = scale * dS K,   dK = scale * dS^T Q
+//
+// Three launches:
+//   fmha_bwd_prep_kernel    (lse * log2 e, delta) pairs per query row, padded to whole tiles (padding rows: lse = +inf -> P = 0)
+//   fmha_bwd_kernel<0>      one CTA per 128 keys of one (batch, KEY head): K, V tiles resident in shared memory, Q_i / dO_i blocks of
+//                           64 queries streamed for every query head of the group; dV, dK accumulate in TMEM over the whole loop
+//   fmha_bwd_kernel<1>      one CTA per 128 queries of one (batch, query head): Q, dO resident, K_j / V_j blocks of 64 keys streamed;
+//                           dQ accumulates in TMEM
+// Both recompute S and dP (7 GEMMs instead of 5) so that no gradient is ever accumulated across CTAs: that is what makes the result
+// run-to-run identical without the reference's per-split fp32 dq_accum buffers.
+//
+// One kernel body serves both (MODE 0 = dK/dV, 1 = dQ).  R1 / R2 = the resident 128-row tiles, T1 / T2 = the streamed 64-row blocks:
+//   MODE 0: R1 = K, R2 = V, T1 = Q_i, T2 = dO_i:  X = R1 T1^T = S^T,  Y = R2 T2^T = dP^T,  acc1 += P^T T2 (dV),  acc2 += dS^T T1 (dK)
+//   MODE 1: R1 = Q, R2 = dO, T1 = K_j, T2 = V_j:  X = R1 T1^T = S,    Y = R2 T2^T = dP,    acc2 += dS T1 (dQ)
+// 320 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-9 = the element-wise stage (two warps per TMEM lane
+// quarter, 32 of the 64 columns each): X, Y from TMEM -> P, dS as bf16 / fp16 K-major 128-byte-swizzled smem tiles the accumulating
+// MMAs read as their A operand; T1 / T2 are the B operand twice -- K-major for X / Y, MN-major for the accumulation.
+// TMEM: X[2] 2 x 64 + Y[2] 2 x 64 + acc1 128 + acc2 128 = 512 columns.  smem: R 64 KB + T 2 x 32 KB + (P, dS) 2 x 32 KB = 192 KB.
+#include "sm100_contract.h"
+#include "sm100_fmha.cuh"
+#include <string.h>
+
+namespace sm100 {
+
+namespace {
+
+constexpr int FB_R = 128;                     // resident rows per CTA
+constexpr int FB_T = 64;                      // streamed rows per block
+constexpr int FB_D = 128;                     // head dimension
+constexpr int FB_R_ATOM = FB_R * 128;         // 16 KB: 128 rows x 64 features
+constexpr int FB_R_BYTES = 2 * FB_R_ATOM;     // 32 KB
+constexpr int FB_T_ATOM = FB_T * 128;         // 8 KB
+constexpr int FB_T_BYTES = 2 * FB_T_ATOM;     // 16 KB
+constexpr int FB_P_BYTES = FB_R * FB_T * 2;   // 16 KB: 128 rows x 64 columns, one swizzle atom wide
+constexpr int FB_STAT_BYTES = FB_T * 8;       // (lse2, delta) per streamed query
+
+struct FmhaBwdParams {
+	int H, Hk, Sq, Sk, Sq_r;
+	int causal;
+	int is_bf16;
+	float scale, scale_log2;
+	const float2* stat;          // [B, H, Sq_r] (lse * log2 e, delta)
+	void* out1;                  // MODE 0: dV
+	void* out2;                  // MODE 0: dK, MODE 1: dQ
+	long long o1_b, o1_s, o1_h;  // element strides
+	long long o2_b, o2_s, o2_h;
+	uint32_t idesc_xy, idesc_acc;
+};
+
+template <int MODE>
+struct FmhaBwdSmem {
+	static constexpr int PBUF = MODE == 0 ? 2 * FB_P_BYTES : FB_P_BYTES; // dS (+ P) per buffer
+	static constexpr int R1_OFF = 0;
+	static constexpr int R2_OFF = R1_OFF + FB_R_BYTES;
+	static constexpr int T_OFF = R2_OFF + FB_R_BYTES; // stage s: T1 at + s * 2 * FB_T_BYTES, T2 right behind it
+	static constexpr int P_OFF = T_OFF + 2 * 2 * FB_T_BYTES; // buffer s: dS at + s * PBUF, P behind it (MODE 0)
+	static constexpr int STAT_OFF = P_OFF + 2 * PBUF;
+	static constexpr int BAR_OFF = STAT_OFF + 2 * FB_STAT_BYTES;
+	static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__device__ __forceinline__ float widen16(const uint16_t u, const int is_bf16)
+{
+	return is_bf16 ? __uint_as_float((uint32_t)u << 16) : __half2float(__ushort_as_half(u));
+}
+
+// (lse * log2 e, delta) per query row: 16 lanes per row, 8 features each
+__global__ void __launch_bounds__(256) fmha_bwd_prep_kernel(const uint16_t* __restrict__ dout, const uint16_t* __restrict__ out, const float* __restrict__ lse, float2* __restrict__ stat, int B, int H, int Sq, int Sq_r, int is_bf16,
+	long long do_b, long long do_s, long long do_h, long long o_b, long long o_s, long long o_h)
+{
+	const long long row = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
+	const int sub = threadIdx.x & 15;
+	const long long rows = (long long)B * H * Sq_r;
+	if (row >= rows)
+		return;
+	const int q = (int)(row % Sq_r);
+	const int h = (int)((row / Sq_r) % H);
+	const int b = (int)(row / ((long long)Sq_r * H));
+	float acc = 0.f;
+	if (q < Sq)
+	{
+		const uint4 a = *reinterpret_cast<const uint4*>(dout + b * do_b + (long long)q * do_s + h * do_h + sub * 8);
+		const uint4 c = *reinterpret_cast<const uint4*>(out + b * o_b + (long long)q * o_s + h * o_h + sub * 8);
+		const uint32_t aw[4] = { a.x, a.y, a.z, a.w }, cw[4] = { c.x, c.y, c.z, c.w };
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+		{
+			acc = fmaf(widen16((uint16_t)(aw[i] & 0xffff), is_bf16), widen16((uint16_t)(cw[i] & 0xffff), is_bf16), acc);
+			acc = fmaf(widen16((uint16_t)(aw[i] >> 16), is_bf16), widen16((uint16_t)(cw[i] >> 16), is_bf16), acc);
+		}
+	}
+	// fixed-order tree over the 16 lanes of the row
+#pragma unroll
+	for (int m = 8; m >= 1; m >>= 1)
+		acc += __shfl_xor_sync(0xffffffffu, acc, m);
+	if (sub == 0)
+	{
+		float l2 = INFINITY; // padding rows and fully masked rows (lse = -inf): P = exp2(x - inf) = 0
+		if (q < Sq)
+		{
+			const float l = lse[((long long)b * H + h) * Sq + q];
+			if (l != -INFINITY)
+				l2 = l * 1.4426950408889634f;
+		}
+		stat[row] = make_float2(l2, q < Sq ? acc : 0.f);
+	}
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2, const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2, const FmhaBwdParams p)
+{
+	typedef FmhaBwdSmem<MODE> L;
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	uint64_t* bars = (uint64_t*)(smem + L::BAR_OFF);
+	uint64_t* r_full = bars;
+	uint64_t* t_full = bars + 1;   // [2] TMA -> MMA (and the element-wise warps: the stat pairs ride on the same barrier)
+	uint64_t* t_empty = bars + 3;  // [2] MMA (accumulation done) -> TMA
+	uint64_t* x_full = bars + 5;   // [2] MMA -> element-wise: X and Y of this block are in TMEM
+	uint64_t* x_empty = bars + 7;  // [2] element-wise -> MMA (8 arrivals): X, Y buffers read
+	uint64_t* p_full = bars + 9;   // [2] element-wise -> MMA (8 arrivals): P / dS tiles written
+	uint64_t* p_empty = bars + 11; // [2] MMA (accumulation done) -> element-wise
+	uint64_t* acc_full = bars + 13;
+	uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int r0 = blockIdx.x * FB_R;
+	const int hr = blockIdx.y, b = blockIdx.z; // MODE 0: key head, MODE 1: query head
+	const int G = p.H / p.Hk;
+	const int shift = p.Sk - p.Sq; // query i sees keys <= i + shift
+	// streamed blocks this tile needs
+	int blk0 = 0, n_blk;
+	if (MODE == 0)
+	{
+		const int nq = (p.Sq + FB_T - 1) / FB_T;
+		if (p.causal)
+			blk0 = min(nq, max(r0 - shift, 0) / FB_T); // queries below r0 - shift see none of this tile's keys
+		n_blk = nq - blk0;
+	} else {
+		const int kv_end = p.causal ? min(p.Sk, max(r0 + FB_R + shift, 0)) : p.Sk;
+		n_blk = (kv_end + FB_T - 1) / FB_T;
+	}
+	const int n_it = MODE == 0 ? n_blk * G : n_blk;
+
+	if (warp == 0 && lane == 0)
+	{
+		tma_prefetch_desc(&tmR1);
+		tma_prefetch_desc(&tmR2);
+		tma_prefetch_desc(&tmT1);
+		tma_prefetch_desc(&tmT2);
+		mbar_init(r_full, 1);
+		for (int s = 0; s < 2; s++)
+		{
+			mbar_init(&t_full[s], 1), mbar_init(&t_empty[s], 1);
+			mbar_init(&x_full[s], 1), mbar_init(&x_empty[s], 8);
+			mbar_init(&p_full[s], 8), mbar_init(&p_empty[s], 1);
+		}
+		mbar_init(acc_full, 1);
+		fence_mbar_init();
+	}
+	if (warp == 1)
+	{
+		tmem_alloc(tmem_slot, 512);
+		tmem_relinquish();
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+	const uint32_t tmem_x = tmem_base;        // X[s] at + 64 s
+	const uint32_t tmem_y = tmem_base + 128;  // Y[s] at + 64 s
+	const uint32_t tmem_a1 = tmem_base + 256; // dV
+	const uint32_t tmem_a2 = tmem_base + 384; // dK | dQ
+
+	if (warp == 0)
+	{
+		if (lane == 0 && n_it > 0)
+		{
+			mbar_expect_tx(r_full, 2 * FB_R_BYTES);
+			tma_load_4d(smem + L::R1_OFF, &tmR1, r_full, 0, hr, r0, b);
+			tma_load_4d(smem + L::R1_OFF + FB_R_ATOM, &tmR1, r_full, 64, hr, r0, b);
+			tma_load_4d(smem + L::R2_OFF, &tmR2, r_full, 0, hr, r0, b);
+			tma_load_4d(smem + L::R2_OFF + FB_R_ATOM, &tmR2, r_full, 64, hr, r0, b);
+			for (int it = 0; it < n_it; it++)
+			{
+				const int s = it & 1;
+				const uint32_t ph = (uint32_t)(it >> 1) & 1;
+				const int ht = MODE == 0 ? hr * G + it / n_blk : hr / G;
+				const int t0 = (MODE == 0 ? blk0 + it % n_blk : it) * FB_T;
+				uint8_t* const t1 = smem + L::T_OFF + s * 2 * FB_T_BYTES;
+				uint8_t* const t2 = t1 + FB_T_BYTES;
+				mbar_wait(&t_empty[s], ph ^ 1);
+				mbar_expect_tx(&t_full[s], 2 * FB_T_BYTES + (MODE == 0 ? FB_STAT_BYTES : 0));
+				tma_load_4d(t1, &tmT1, &t_full[s], 0, ht, t0, b);
+				tma_load_4d(t1 + FB_T_ATOM, &tmT1, &t_full[s], 64, ht, t0, b);
+				tma_load_4d(t2, &tmT2, &t_full[s], 0, ht, t0, b);
+				tma_load_4d(t2 + FB_T_ATOM, &tmT2, &t_full[s], 64, ht, t0, b);
+				if (MODE == 0)
+					bulk_load_1d(smem + L::STAT_OFF + s * FB_STAT_BYTES, p.stat + ((long long)b * p.H + ht) * p.Sq_r + t0, FB_STAT_BYTES, &t_full[s]);
+			}
+		}
+	} else if (warp == 1) {
+		if (n_it > 0)
+		{
+			const uint32_t r1_addr = smem_u32(smem + L::R1_OFF);
+			const uint32_t r2_addr = smem_u32(smem + L::R2_OFF);
+			// X = R1 T1^T, Y = R2 T2^T into buffer it & 1: both operands K-major, 8 steps of 16 features over the two 64-wide atoms
+			auto issue_xy = [&](const int it) {
+				const int s = it & 1;
+				const uint32_t ph = (uint32_t)(it >> 1) & 1;
+				mbar_wait(&x_empty[s], ph ^ 1); // the element-wise warps have read what block it - 2 left here
+				mbar_wait(&t_full[s], ph);
+				tc_fence_after();
+				if (lane == 0)
+				{
+					const uint32_t t1_addr = smem_u32(smem + L::T_OFF + s * 2 * FB_T_BYTES);
+					const uint32_t t2_addr = t1_addr + FB_T_BYTES;
+#pragma unroll
+					for (int k = 0; k < FB_D / 16; k++)
+					{
+						const uint32_t ro = (uint32_t)(k >> 2) * FB_R_ATOM + (uint32_t)(k & 3) * 32;
+						const uint32_t to = (uint32_t)(k >> 2) * FB_T_ATOM + (uint32_t)(k & 3) * 32;
+						umma_f16(tmem_x + s * 64, umma_smem_desc(r1_addr + ro, 16, 1024, 2), umma_smem_desc(t1_addr + to, 16, 1024, 2), p.idesc_xy, k > 0 ? 1u : 0u);
+					}
+#pragma unroll
+					for (int k = 0; k < FB_D / 16; k++)
+					{
+						const uint32_t ro = (uint32_t)(k >> 2) * FB_R_ATOM + (uint32_t)(k & 3) * 32;
+						const uint32_t to = (uint32_t)(k >> 2) * FB_T_ATOM + (uint32_t)(k & 3) * 32;
+						umma_f16(tmem_y + s * 64, umma_smem_desc(r2_addr + ro, 16, 1024, 2), umma_smem_desc(t2_addr + to, 16, 1024, 2), p.idesc_xy, k > 0 ? 1u : 0u);
+					}
+					umma_commit(&x_full[s]);
+				}
+				__syncwarp();
+			};
+			mbar_wait(r_full, 0);
+			issue_xy(0);
+			for (int it = 0; it < n_it; it++)
+			{
+				if (it + 1 < n_it)
+					issue_xy(it + 1); // one block ahead: overlaps the element-wise stage of block it
+				const int s = it & 1;
+				const uint32_t ph = (uint32_t)(it >> 1) & 1;
+				mbar_wait(&p_full[s], ph);
+				tc_fence_after();
+				if (lane == 0)
+				{
+					const uint32_t t1_addr = smem_u32(smem + L::T_OFF + s * 2 * FB_T_BYTES);
+					const uint32_t t2_addr = t1_addr + FB_T_BYTES;
+					const uint32_t ds_addr = smem_u32(smem + L::P_OFF + s * L::PBUF);
+					// A = the 128 x 64 tile just written (K-major, one atom), B = the streamed block as an MN-major operand: two 64-wide
+					// feature atoms 8 KB apart (LBO), 8-row groups 1 KB apart (SBO), one MMA consumes 16 rows = 2 KB
+#pragma unroll
+					for (int k = 0; k < FB_T / 16; k++)
+					{
+						const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+						if (MODE == 0)
+							umma_f16(tmem_a1, umma_smem_desc(ds_addr + FB_P_BYTES + k * 32, 16, 1024, 2), umma_smem_desc(t2_addr + k * 2048, FB_T_ATOM, 1024, 2), p.idesc_acc, acc);
+						umma_f16(tmem_a2, umma_smem_desc(ds_addr + k * 32, 16, 1024, 2), umma_smem_desc(t1_addr + k * 2048, FB_T_ATOM, 1024, 2), p.idesc_acc, acc);
+					}
+					umma_commit(&t_empty[s]);
+					umma_commit(&p_empty[s]);
+					if (it + 1 == n_it)
+						umma_commit(acc_full);
+				}
+				__syncwarp();
+			}
+		}
+	} else {
+		// ------------------------------------------------------------------ element-wise stage and epilogue (warps 2..9)
+		const int quarter = warp & 3;     // TMEM lanes [32 * quarter, +32) are the ones this warp may touch
+		const int half = (warp - 2) >> 2; // columns [32 * half, +32) of a 64-wide block; [64 * half, +64) of the accumulators
+		const int row = quarter * 32 + lane;
+		const int rr = r0 + row; // MODE 0: key index, MODE 1: query index
+		const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+		float lse2 = INFINITY, delta = 0.f;
+		if (MODE == 1)
+		{
+			const float2 st = p.stat[((long long)b * p.H + hr) * p.Sq_r + rr]; // Sq_r is a whole number of tiles
+			lse2 = st.x, delta = st.y;
+		}
+		for (int it = 0; it < n_it; it++)
+		{
+			const int s = it & 1;
+			const uint32_t ph = (uint32_t)(it >> 1) & 1;
+			const int t0 = (MODE == 0 ? blk0 + it % n_blk : it) * FB_T;
+			// columns [cmin, cmax) of this row are visible
+			int cmin = 0, cmax = FB_T;
+			if (MODE == 0)
+			{
+				if (p.causal)
+					cmin = rr - shift - t0; // key rr is seen by queries >= rr - shift
+			} else
+				cmax = (p.causal ? min(p.Sk, rr + shift + 1) : p.Sk) - t0;
+			const int c0 = half * 32;
+			const bool edge = cmin > c0 || cmax < c0 + 32;
+			mbar_wait(&x_full[s], ph);
+			if (MODE == 0)
+				mbar_wait(&t_full[s], ph); // the stat pairs of this block (the MMA warp has observed this phase already)
+			tc_fence_after();
+			uint32_t xr[32], yr[32];
+			tmem_ld_32x32(tmem_x + s * 64 + c0 + lane_sel, xr);
+			tmem_ld_32x32(tmem_y + s * 64 + c0 + lane_sel, yr);
+			tmem_ld_wait();
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(&x_empty[s]);
+			const float2* const st = (const float2*)(smem + L::STAT_OFF + s * FB_STAT_BYTES) + c0;
+			uint32_t pk[16], dk[16];
+#pragma unroll
+			for (int i = 0; i < 32; i += 2)
+			{
+				float l0 = lse2, l1 = lse2, d0 = delta, d1 = delta;
+				if (MODE == 0)
+				{
+					const float4 sv = *reinterpret_cast<const float4*>(st + i); // two (lse2, delta) pairs, the same address for the whole warp
+					l0 = sv.x, d0 = sv.y, l1 = sv.z, d1 = sv.w;
+				}
+				float e0 = ex2_approx(fmaf(__uint_as_float(xr[i]), p.scale_log2, -l0));
+				float e1 = ex2_approx(fmaf(__uint_as_float(xr[i + 1]), p.scale_log2, -l1));
+				if (edge)
+				{
+					if (c0 + i < cmin || c0 + i >= cmax)
+						e0 = 0.f;
+					if (c0 + i + 1 < cmin || c0 + i + 1 >= cmax)
+						e1 = 0.f;
+				}
+				const float g0 = e0 * (__uint_as_float(yr[i]) - d0);
+				const float g1 = e1 * (__uint_as_float(yr[i + 1]) - d1);
+				if (MODE == 0)
+					pk[i >> 1] = pack2(e0, e1, p.is_bf16);
+				dk[i >> 1] = pack2(g0, g1, p.is_bf16);
+			}
+			// the accumulation of block it - 2 has finished reading this P / dS buffer
+			mbar_wait(&p_empty[s], ph ^ 1);
+			uint8_t* const ds_row = smem + L::P_OFF + s * L::PBUF + row * 128;
+#pragma unroll
+			for (int c = 0; c < 4; c++)
+			{
+				const int chunk = ((half * 4 + c) ^ (row & 7)) << 4;
+				*reinterpret_cast<uint4*>(ds_row + chunk) = make_uint4(dk[c * 4], dk[c * 4 + 1], dk[c * 4 + 2], dk[c * 4 + 3]);
+				if (MODE == 0)
+					*reinterpret_cast<uint4*>(ds_row + FB_P_BYTES + chunk) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+			}
+			fence_proxy_async(); // generic-proxy smem writes -> the tensor core's async proxy
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(&p_full[s]);
+		}
+		// epilogue: the accumulators -> 16-bit gradients (this thread: one row, 64 of the 128 features)
+		if (n_it > 0)
+		{
+			mbar_wait(acc_full, 0);
+			tc_fence_after();
+		}
+		const int limit = MODE == 0 ? p.Sk : p.Sq;
+#pragma unroll
+		for (int a = MODE == 0 ? 0 : 1; a < 2; a++)
+		{
+			uint32_t r[64];
+			if (n_it > 0)
+			{
+				const uint32_t ta = (a == 0 ? tmem_a1 : tmem_a2) + lane_sel + half * 64;
+				tmem_ld_32x32(ta, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+				tmem_ld_32x32(ta + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+				tmem_ld_wait();
+			} else {
+#pragma unroll
+				for (int i = 0; i < 64; i++)
+					r[i] = 0;
+			}
+			if (rr < limit)
+			{
+				const float f = a == 0 ? 1.f : p.scale;
+				uint16_t* const orow = a == 0 ? (uint16_t*)p.out1 + b * p.o1_b + (long long)rr * p.o1_s + hr * p.o1_h + half * 64 : (uint16_t*)p.out2 + b * p.o2_b + (long long)rr * p.o2_s + hr * p.o2_h + half * 64;
+#pragma unroll
+				for (int i = 0; i < 64; i += 8)
+				{
+					const uint4 v = make_uint4(pack2(__uint_as_float(r[i]) * f, __uint_as_float(r[i + 1]) * f, p.is_bf16), pack2(__uint_as_float(r[i + 2]) * f, __uint_as_float(r[i + 3]) * f, p.is_bf16),
+						pack2(__uint_as_float(r[i + 4]) * f, __uint_as_float(r[i + 5]) * f, p.is_bf16), pack2(__uint_as_float(r[i + 6]) * f, __uint_as_float(r[i + 7]) * f, p.is_bf16));
+					*reinterpret_cast<uint4*>(orow + i) = v;
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1)
+		tmem_dealloc(tmem_base, 512);
+}
+
+template <int MODE>
+int launch_bwd(cudaStream_t stream, const CUtensorMap& r1, const CUtensorMap& r2, const CUtensorMap& t1, const CUtensorMap& t2, const FmhaBwdParams& p, int tiles, int heads, int B)
+{
+	static bool configured_on[64]; // the attribute is per device
+	int dev = 0;
+	cudaGetDevice(&dev);
+	bool& configured = configured_on[dev & 63];
+	if (!configured)
+	{
+		const cudaError_t e = cudaFuncSetAttribute(fmha_bwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaBwdSmem<MODE>::TOTAL);
+		if (e != cudaSuccess)
+		{
+			set_last_error("cudaFuncSetAttribute(fmha_bwd_kernel)", e);
+			return -1;
+		}
+		configured = true;
+	}
+	fmha_bwd_kernel<MODE><<<dim3(tiles, heads, B), 320, FmhaBwdSmem<MODE>::TOTAL, stream>>>(r1, r2, t1, t2, p);
+	count_launch();
+	const cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		set_last_error("fmha_bwd_kernel launch", e);
+		return -1;
+	}
+	return 0;
+}
+
+} // namespace
+
+size_t sdpa_backward_f16_workspace_bytes(const SdpaGeom& g, int need_forward)
+{
+	const size_t sq_r = (size_t)(g.Sq + FB_R - 1) / FB_R * FB_R;
+	size_t bytes = (size_t)g.B * g.H * sq_r * sizeof(float2) + 256;
+	if (need_forward) // O (16-bit, packed [B, Sq, H, D]) and the log-sum-exp [B, H, Sq]
+		bytes += (size_t)g.B * g.Sq * g.H * g.Dv * 2 + 256 + (size_t)g.B * g.H * g.Sq * sizeof(float) + 256;
+	return bytes;
+}
+
+// g: q / k / v strides, o_* = the strides of dout; dg: the strides of dq / dk / dv in its q_* / k_* / v_* fields.  `out` (strides oo_*)
+// and `lse` are the forward's saved outputs; when either is NULL both are recomputed into the workspace with the forward kernel.
+// returns 0 on success, 1 when the shape is outside these kernels (D = Dv = 128, 16-byte aligned strides), < 0 on CUDA errors
+int sdpa_backward_f16(cudaStream_t stream, const SdpaGeom& g, const SdpaGeom& dg, int is_bf16, const void* dout, const void* q, const void* k, const void* v, const void* out, long long oo_b, long long oo_s, long long oo_h,
+	const float* lse, void* dq, void* dk, void* dv, void* workspace)
+{
+	if (g.D != FB_D || g.Dv != FB_D || g.B <= 0 || g.H <= 0 || g.Hk <= 0 || g.H % g.Hk != 0 || g.Sq <= 0 || g.Sk <= 0 || !encode_init())
+		return 1;
+	for (const void* ptr : { (const void*)dq, (const void*)dk, (const void*)dv, dout })
+		if (((uintptr_t)ptr) & 15)
+			return 1;
+	for (const long long st : { dg.q_b, dg.q_s, dg.q_h, dg.k_b, dg.k_s, dg.k_h, dg.v_b, dg.v_s, dg.v_h, g.o_b, g.o_s, g.o_h })
+		if (st & 7)
+			return 1;
+	CUtensorMap tmQr, tmQt, tmKr, tmKt, tmVr, tmVt, tmGr, tmGt;
+	if (!make_map_bshd(&tmQr, q, g.B, g.Sq, g.H, g.D, g.q_b, g.q_s, g.q_h, is_bf16, FB_R) || !make_map_bshd(&tmQt, q, g.B, g.Sq, g.H, g.D, g.q_b, g.q_s, g.q_h, is_bf16, FB_T) ||
+		!make_map_bshd(&tmKr, k, g.B, g.Sk, g.Hk, g.D, g.k_b, g.k_s, g.k_h, is_bf16, FB_R) || !make_map_bshd(&tmKt, k, g.B, g.Sk, g.Hk, g.D, g.k_b, g.k_s, g.k_h, is_bf16, FB_T) ||
+		!make_map_bshd(&tmVr, v, g.B, g.Sk, g.Hk, g.Dv, g.v_b, g.v_s, g.v_h, is_bf16, FB_R) || !make_map_bshd(&tmVt, v, g.B, g.Sk, g.Hk, g.Dv, g.v_b, g.v_s, g.v_h, is_bf16, FB_T) ||
+		!make_map_bshd(&tmGr, dout, g.B, g.Sq, g.H, g.Dv, g.o_b, g.o_s, g.o_h, is_bf16, FB_R) || !make_map_bshd(&tmGt, dout, g.B, g.Sq, g.H, g.Dv, g.o_b, g.o_s, g.o_h, is_bf16, FB_T))
+		return 1;
+	const int sq_r = (g.Sq + FB_R - 1) / FB_R * FB_R;
+	uint8_t* ws = (uint8_t*)workspace;
+	float2* const stat = (float2*)ws;
+	ws += (((size_t)g.B * g.H * sq_r * sizeof(float2)) + 255) & ~(size_t)255;
+	if (!out || !lse)
+	{
+		void* const o_ws = ws;
+		ws += (((size_t)g.B * g.Sq * g.H * g.Dv * 2) + 255) & ~(size_t)255;
+		float* const lse_ws = (float*)ws;
+		SdpaGeom fg = g;
+		fg.o_h = g.Dv, fg.o_s = (long long)g.H * g.Dv, fg.o_b = (long long)g.Sq * g.H * g.Dv;
+		const int rc = sdpa_forward_f16(stream, fg, is_bf16, q, k, v, o_ws, lse_ws);
+		if (rc != 0)
+			return rc;
+		out = o_ws, lse = lse_ws;
+		oo_b = fg.o_b, oo_s = fg.o_s, oo_h = fg.o_h;
+	}
+	if ((((uintptr_t)out) & 15) || (oo_b & 7) || (oo_s & 7) || (oo_h & 7))
+		return 1;
+	const long long rows = (long long)g.B * g.H * sq_r;
+	fmha_bwd_prep_kernel<<<(unsigned)((rows + 15) / 16), 256, 0, stream>>>((const uint16_t*)dout, (const uint16_t*)out, lse, stat, g.B, g.H, g.Sq, sq_r, is_bf16, g.o_b, g.o_s, g.o_h, oo_b, oo_s, oo_h);
+	count_launch();
+	FmhaBwdParams p;
+	memset(&p, 0, sizeof(p));
+	p.H = g.H, p.Hk = g.Hk, p.Sq = g.Sq, p.Sk = g.Sk, p.Sq_r = sq_r;
+	p.causal = g.is_causal, p.is_bf16 = is_bf16;
+	p.scale = g.scale, p.scale_log2 = g.scale * 1.4426950408889634f;
+	p.stat = stat;
+	p.idesc_xy = umma_instr_desc(is_bf16 ? 1 : 0, 0, 0, FB_R, FB_T);
+	p.idesc_acc = umma_instr_desc(is_bf16 ? 1 : 0, 0, 1, FB_R, FB_D);
+	// dK, dV: one CTA per 128 keys of a (batch, key head)
+	p.out1 = dv, p.o1_b = dg.v_b, p.o1_s = dg.v_s, p.o1_h = dg.v_h;
+	p.out2 = dk, p.o2_b = dg.k_b, p.o2_s = dg.k_s, p.o2_h = dg.k_h;
+	int rc = launch_bwd<0>(stream, tmKr, tmVr, tmQt, tmGt, p, (g.Sk + FB_R - 1) / FB_R, g.Hk, g.B);
+	if (rc != 0)
+		return rc;
+	// dQ: one CTA per 128 queries of a (batch, query head)
+	p.out1 = 0;
+	p.out2 = dq, p.o2_b = dg.q_b, p.o2_s = dg.q_s, p.o2_h = dg.q_h;
+	return launch_bwd<1>(stream, tmQr, tmGr, tmKt, tmVt, p, (g.Sq + FB_R - 1) / FB_R, g.H, g.B);
+}
+
+} // namespace sm100

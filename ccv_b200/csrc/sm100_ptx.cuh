@@ -89,6 +89,11 @@ __device__ __forceinline__ void tma_load_4d_multicast(void* dst, const CUtensorM
 		"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
 		: "memory");
 }
+// plain 1-D bulk copy global -> shared (16-byte aligned on both sides, bytes a multiple of 16), completing on an mbarrier like the tile loads
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // shared -> global tile store (bulk async group): the box at smem `src` is written at tensor coordinates (c0, c1); rows / columns
 // outside the tensor are clipped by the TMA unit
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* desc, const void* src, int c0, int c1)

@@ -135,26 +135,62 @@ def test_flash_attention_16bit_forward(gpu, ref, B, Sq, Sk, Hq, Hk, causal, dtyp
         t.free()
 
 
-@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,causal", [(1, 128, 128, 2, 2, 0), (2, 64, 96, 4, 2, 1)])
-def test_attention_bf16_backward(gpu, ref, B, Sq, Sk, Hq, Hk, causal):
-    """bf16 SDPA backward (functional form: widened to fp32, composed from the TF32 GEMMs, narrowed with RNE) against CPU_REF's
-    fp32 backward on the bf16-rounded operands; 1e-2 of max|ref| (bf16 output rounding alone is 4e-3)."""
+BWD16 = [
+    # B, Sq, Sk, Hq, Hk, causal, dtype, saved (pass the forward's o / lse as inputs[9], [10])
+    (1, 128, 128, 2, 2, 0, "bf16", 0), (2, 64, 96, 4, 2, 1, "bf16", 0), (1, 256, 256, 2, 2, 1, "bf16", 1), (2, 200, 328, 4, 1, 0, "bf16", 1),
+    (1, 328, 200, 2, 2, 1, "bf16", 0), (1, 96, 160, 8, 2, 1, "f16", 1), (1, 1024, 1024, 2, 1, 0, "bf16", 1), (1, 40, 24, 2, 2, 1, "f16", 0),
+]
+
+
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,causal,dtype,saved", BWD16)
+def test_attention_16bit_backward_fused(gpu, ref, B, Sq, Sk, Hq, Hk, causal, dtype, saved):
+    """bf16 / fp16 SDPA backward, D = 128: the fused deterministic tcgen05 kernels (sm100_fmha_bwd.cu) against CPU_REF's fp32 backward
+    (…attention_cpu_ref.c:259-479) on the rounded operands; 1e-2 of max|ref| (P and dS are rounded to 16 bits on the way, like the
+    reference's flash-attention backward).  Covers GQA (dk / dv summed over the query heads), causal with Sq != Sk (bottom-right
+    aligned, Sq > Sk leaves fully masked rows), ragged tiles, with and without the forward's saved output / log-sum-exp, and that two
+    runs are bit-identical."""
     nnc = gpu
     D = 128
     scale = 1.0 / np.sqrt(D)
     arrs = [seeded((B, Sq, Hq, D), 4, -1, 1), None, None, seeded((B, Sq, Hq, D), 1, -1, 1), seeded((B, Sk, Hk, D), 2, -1, 1), seeded((B, Sk, Hk, D), 3, -1, 1)]
-    bits = [None if a is None else _to_bf16(a) for a in arrs]
-    vals = [None if b is None else _from_bf16(b) for b in bits]
+    if dtype == "bf16":
+        ccv_dt = abi.CCV_16BF
+        bits = [None if a is None else _to_bf16(a) for a in arrs]
+        vals = [None if b is None else _from_bf16(b) for b in bits]
+        back = _from_bf16
+    else:
+        ccv_dt = abi.CCV_16F
+        bits = [None if a is None else a.astype(np.float16) for a in arrs]
+        vals = [None if b is None else b.astype(np.float32) for b in bits]
+        back = lambda x: x.astype(np.float32)
     bwd = _cmd(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD, scale, causal)
+    bwd.info.scaled_dot_product_attention.deterministic = 1
     st_r, (dq_r, dk_r, dv_r) = ref_exec(ref, bwd, None, 0, vals, [np.zeros_like(vals[3]), np.zeros_like(vals[4]), np.zeros_like(vals[5])])
     assert st_r == 0
     stream = nnc.Stream(0)
-    ins = [None if b is None else nnc.gpu_tensor(list(b.shape), datatype=abi.CCV_16BF).upload(b) for b in bits]
-    outs = [nnc.gpu_tensor(list(vals[i].shape), datatype=abi.CCV_16BF) for i in (3, 4, 5)]
+    ins = [None if b is None else nnc.gpu_tensor(list(b.shape), datatype=ccv_dt).upload(b) for b in bits]
+    extra = []
+    if saved:
+        to = nnc.gpu_tensor([B, Sq, Hq, D], datatype=ccv_dt)
+        tl = nnc.gpu_tensor([B, Hq, Sq])
+        fwd = _cmd(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD, scale, causal)
+        assert nnc.cmd_exec(fwd, None, 0, [ins[3], ins[4], ins[5]], [to, tl], stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+        ins = ins + [None, None, None, to, tl]
+        extra = [to, tl]
+    outs = [nnc.gpu_tensor(list(vals[i].shape), datatype=ccv_dt) for i in (3, 4, 5)]
+    launches = nnc.lib().ccv_nnc_sm100_launch_count()
     assert nnc.cmd_exec(bwd, None, 0, ins, outs, stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
     stream.wait()
+    assert nnc.lib().ccv_nnc_sm100_launch_count() - launches == (3 if saved else 4), "the fused path is prep + dK/dV + dQ (+ the forward when o / lse are not passed)"
+    first = [t.download().copy() for t in outs]
     for t, want, name in zip(outs, (dq_r, dk_r, dv_r), ("dq", "dk", "dv")):
-        assert_close(_from_bf16(t.download()), want, 1e-2, "bf16 " + name)
+        assert_close(back(t.download()), want, 1e-2, "%s %s" % (dtype, name))
+    for t in outs:
+        t.upload(np.zeros(t.dims, np.uint16 if ccv_dt == abi.CCV_16BF else np.float16))
+    assert nnc.cmd_exec(bwd, None, 0, ins, outs, stream) == 0
+    stream.wait()
+    for t, a in zip(outs, first):
+        assert np.array_equal(t.download().view(np.uint16), a.view(np.uint16)), "the backward must be run-to-run identical"
     for t in [x for x in ins if x is not None] + outs + [stream]:
         t.free()
 
