@@ -23,9 +23,13 @@
 //   MODE 0: R1 = K, R2 = V, T1 = Q_i, T2 = dO_i:  X = R1 T1^T = S^T,  Y = R2 T2^T = dP^T,  acc1 += P^T T2 (dV),  acc2 += dS^T T1 (dK)
 //   MODE 1: R1 = Q, R2 = dO, T1 = K_j, T2 = V_j:  X = R1 T1^T = S,    Y = R2 T2^T = dP,    acc2 += dS T1 (dQ)
 // 320 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-9 = the element-wise stage (two warps per TMEM lane
-// quarter, 32 of the 64 columns each): X, Y from TMEM -> P, dS as bf16 / fp16 K-major 128-byte-swizzled smem tiles the accumulating
-// MMAs read as their A operand; T1 / T2 are the B operand twice -- K-major for X / Y, MN-major for the accumulation.
-// TMEM: X[2] 2 x 64 + Y[2] 2 x 64 + acc1 128 + acc2 128 = 512 columns.  smem: R 64 KB + T 2 x 32 KB + (P, dS) 2 x 32 KB = 192 KB.
+// quarter, 32 of the 64 columns each; measured faster than giving alternate blocks to two sets of four warps, which puts the
+// accumulate -> X / Y round trip of the tensor core on each set's critical path).  X, Y from TMEM -> P, dS as bf16 / fp16 K-major
+// 128-byte-swizzled smem tiles the accumulating MMAs read as their A operand; T1 / T2 are the B operand twice -- K-major for X / Y,
+// MN-major for the accumulation.  The streamed blocks sit in a ring of 3 (MODE 0) / 4 (MODE 1) stages: a stage is only free once the accumulation of its
+// block has completed, and the next X / Y is issued one block ahead, so two stages would expose the whole TMA latency every block.
+// TMEM: X[2] 2 x 64 + Y[2] 2 x 64 + acc1 128 + acc2 128 = 512 columns.  smem: R 64 KB + T 3 x 32 KB + (P, dS) 2 x 32 KB = 224 KB
+// (MODE 0), R 64 KB + T 4 x 32 KB + dS 2 x 16 KB = 224 KB (MODE 1).
 #include "sm100_contract.h"
 #include "sm100_fmha.cuh"
 #include <string.h>
@@ -42,14 +46,14 @@ constexpr int FB_R_BYTES = 2 * FB_R_ATOM;     // 32 KB
 constexpr int FB_T_ATOM = FB_T * 128;         // 8 KB
 constexpr int FB_T_BYTES = 2 * FB_T_ATOM;     // 16 KB
 constexpr int FB_P_BYTES = FB_R * FB_T * 2;   // 16 KB: 128 rows x 64 columns, one swizzle atom wide
-constexpr int FB_STAT_BYTES = FB_T * 8;       // (lse2, delta) per streamed query
+constexpr int FB_STAT_BYTES = FB_T * 8;       // (-lse2, -delta) per streamed query, as float4 (-l0, -l1, -d0, -d1) per query pair
 
 struct FmhaBwdParams {
 	int H, Hk, Sq, Sk, Sq_r;
 	int causal;
 	int is_bf16;
 	float scale, scale_log2;
-	const float2* stat;          // [B, H, Sq_r] (lse * log2 e, delta)
+	const float4* stat;          // [B, H, Sq_r / 2] (-lse2_0, -lse2_1, -delta_0, -delta_1) per query pair, lse2 = lse * log2 e
 	void* out1;                  // MODE 0: dV
 	void* out2;                  // MODE 0: dK, MODE 1: dQ
 	long long o1_b, o1_s, o1_h;  // element strides
@@ -59,14 +63,16 @@ struct FmhaBwdParams {
 
 template <int MODE>
 struct FmhaBwdSmem {
+	static constexpr int NST = MODE == 0 ? 3 : 4; // stages of the streamed ring
 	static constexpr int PBUF = MODE == 0 ? 2 * FB_P_BYTES : FB_P_BYTES; // dS (+ P) per buffer
 	static constexpr int R1_OFF = 0;
 	static constexpr int R2_OFF = R1_OFF + FB_R_BYTES;
 	static constexpr int T_OFF = R2_OFF + FB_R_BYTES; // stage s: T1 at + s * 2 * FB_T_BYTES, T2 right behind it
-	static constexpr int P_OFF = T_OFF + 2 * 2 * FB_T_BYTES; // buffer s: dS at + s * PBUF, P behind it (MODE 0)
+	static constexpr int P_OFF = T_OFF + NST * 2 * FB_T_BYTES; // buffer s: dS at + s * PBUF, P behind it (MODE 0)
 	static constexpr int STAT_OFF = P_OFF + 2 * PBUF;
-	static constexpr int BAR_OFF = STAT_OFF + 2 * FB_STAT_BYTES;
+	static constexpr int BAR_OFF = STAT_OFF + (MODE == 0 ? NST * FB_STAT_BYTES : 0);
 	static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+	static_assert(TOTAL <= 232448, "227 KB of shared memory per CTA");
 };
 
 __device__ __forceinline__ float widen16(const uint16_t u, const int is_bf16)
@@ -74,8 +80,8 @@ __device__ __forceinline__ float widen16(const uint16_t u, const int is_bf16)
 	return is_bf16 ? __uint_as_float((uint32_t)u << 16) : __half2float(__ushort_as_half(u));
 }
 
-// (lse * log2 e, delta) per query row: 16 lanes per row, 8 features each
-__global__ void __launch_bounds__(256) fmha_bwd_prep_kernel(const uint16_t* __restrict__ dout, const uint16_t* __restrict__ out, const float* __restrict__ lse, float2* __restrict__ stat, int B, int H, int Sq, int Sq_r, int is_bf16,
+// (-lse * log2 e, -delta) per query row: 16 lanes per row, 8 features each
+__global__ void __launch_bounds__(256) fmha_bwd_prep_kernel(const uint16_t* __restrict__ dout, const uint16_t* __restrict__ out, const float* __restrict__ lse, float* __restrict__ stat, int B, int H, int Sq, int Sq_r, int is_bf16,
 	long long do_b, long long do_s, long long do_h, long long o_b, long long o_s, long long o_h)
 {
 	const long long row = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
@@ -112,7 +118,10 @@ __global__ void __launch_bounds__(256) fmha_bwd_prep_kernel(const uint16_t* __re
 			if (l != -INFINITY)
 				l2 = l * 1.4426950408889634f;
 		}
-		stat[row] = make_float2(l2, q < Sq ? acc : 0.f);
+		// query pair (2j, 2j + 1) -> (-l, -l', -d, -d'): Sq_r is even, so a pair never straddles two heads
+		float* const dst = stat + (row >> 1) * 4 + (row & 1);
+		dst[0] = -l2;
+		dst[2] = q < Sq ? -acc : 0.f;
 	}
 }
 
@@ -120,18 +129,19 @@ template <int MODE>
 __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2, const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2, const FmhaBwdParams p)
 {
 	typedef FmhaBwdSmem<MODE> L;
+	constexpr int NST = L::NST;
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint64_t* bars = (uint64_t*)(smem + L::BAR_OFF);
 	uint64_t* r_full = bars;
-	uint64_t* t_full = bars + 1;   // [2] TMA -> MMA (and the element-wise warps: the stat pairs ride on the same barrier)
-	uint64_t* t_empty = bars + 3;  // [2] MMA (accumulation done) -> TMA
-	uint64_t* x_full = bars + 5;   // [2] MMA -> element-wise: X and Y of this block are in TMEM
-	uint64_t* x_empty = bars + 7;  // [2] element-wise -> MMA (8 arrivals): X, Y buffers read
-	uint64_t* p_full = bars + 9;   // [2] element-wise -> MMA (8 arrivals): P / dS tiles written
-	uint64_t* p_empty = bars + 11; // [2] MMA (accumulation done) -> element-wise
-	uint64_t* acc_full = bars + 13;
-	uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+	uint64_t* t_full = bars + 1;          // [NST] TMA -> MMA (and the element-wise warps: the stat pairs ride on the same barrier)
+	uint64_t* t_empty = t_full + NST;     // [NST] MMA (accumulation done) -> TMA
+	uint64_t* x_full = t_empty + NST;     // [2] MMA -> element-wise: X and Y of this block are in TMEM
+	uint64_t* x_empty = x_full + 2;       // [2] element-wise -> MMA (8 arrivals): X, Y buffers read
+	uint64_t* p_full = x_empty + 2;       // [2] element-wise -> MMA (8 arrivals): P / dS tiles written
+	uint64_t* p_empty = p_full + 2;       // [2] MMA (accumulation done) -> element-wise
+	uint64_t* acc_full = p_empty + 2;
+	uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int r0 = blockIdx.x * FB_R;
@@ -159,9 +169,10 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 		tma_prefetch_desc(&tmT1);
 		tma_prefetch_desc(&tmT2);
 		mbar_init(r_full, 1);
+		for (int s = 0; s < NST; s++)
+			mbar_init(&t_full[s], 1), mbar_init(&t_empty[s], 1);
 		for (int s = 0; s < 2; s++)
 		{
-			mbar_init(&t_full[s], 1), mbar_init(&t_empty[s], 1);
 			mbar_init(&x_full[s], 1), mbar_init(&x_empty[s], 8);
 			mbar_init(&p_full[s], 8), mbar_init(&p_empty[s], 1);
 		}
@@ -191,22 +202,24 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 			tma_load_4d(smem + L::R1_OFF + FB_R_ATOM, &tmR1, r_full, 64, hr, r0, b);
 			tma_load_4d(smem + L::R2_OFF, &tmR2, r_full, 0, hr, r0, b);
 			tma_load_4d(smem + L::R2_OFF + FB_R_ATOM, &tmR2, r_full, 64, hr, r0, b);
+			int st = 0;
+			uint32_t ph = 0;
 			for (int it = 0; it < n_it; it++)
 			{
-				const int s = it & 1;
-				const uint32_t ph = (uint32_t)(it >> 1) & 1;
 				const int ht = MODE == 0 ? hr * G + it / n_blk : hr / G;
 				const int t0 = (MODE == 0 ? blk0 + it % n_blk : it) * FB_T;
-				uint8_t* const t1 = smem + L::T_OFF + s * 2 * FB_T_BYTES;
+				uint8_t* const t1 = smem + L::T_OFF + st * 2 * FB_T_BYTES;
 				uint8_t* const t2 = t1 + FB_T_BYTES;
-				mbar_wait(&t_empty[s], ph ^ 1);
-				mbar_expect_tx(&t_full[s], 2 * FB_T_BYTES + (MODE == 0 ? FB_STAT_BYTES : 0));
-				tma_load_4d(t1, &tmT1, &t_full[s], 0, ht, t0, b);
-				tma_load_4d(t1 + FB_T_ATOM, &tmT1, &t_full[s], 64, ht, t0, b);
-				tma_load_4d(t2, &tmT2, &t_full[s], 0, ht, t0, b);
-				tma_load_4d(t2 + FB_T_ATOM, &tmT2, &t_full[s], 64, ht, t0, b);
+				mbar_wait(&t_empty[st], ph ^ 1);
+				mbar_expect_tx(&t_full[st], 2 * FB_T_BYTES + (MODE == 0 ? FB_STAT_BYTES : 0));
+				tma_load_4d(t1, &tmT1, &t_full[st], 0, ht, t0, b);
+				tma_load_4d(t1 + FB_T_ATOM, &tmT1, &t_full[st], 64, ht, t0, b);
+				tma_load_4d(t2, &tmT2, &t_full[st], 0, ht, t0, b);
+				tma_load_4d(t2 + FB_T_ATOM, &tmT2, &t_full[st], 64, ht, t0, b);
 				if (MODE == 0)
-					bulk_load_1d(smem + L::STAT_OFF + s * FB_STAT_BYTES, p.stat + ((long long)b * p.H + ht) * p.Sq_r + t0, FB_STAT_BYTES, &t_full[s]);
+					bulk_load_1d(smem + L::STAT_OFF + st * FB_STAT_BYTES, p.stat + (((long long)b * p.H + ht) * p.Sq_r + t0) / 2, FB_STAT_BYTES, &t_full[st]);
+				if (++st == NST)
+					st = 0, ph ^= 1;
 			}
 		}
 	} else if (warp == 1) {
@@ -214,16 +227,17 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 		{
 			const uint32_t r1_addr = smem_u32(smem + L::R1_OFF);
 			const uint32_t r2_addr = smem_u32(smem + L::R2_OFF);
+			int xst = 0, ast = 0; // ring stage of the next X / Y block and of the next accumulation
+			uint32_t xph = 0;
 			// X = R1 T1^T, Y = R2 T2^T into buffer it & 1: both operands K-major, 8 steps of 16 features over the two 64-wide atoms
 			auto issue_xy = [&](const int it) {
 				const int s = it & 1;
-				const uint32_t ph = (uint32_t)(it >> 1) & 1;
-				mbar_wait(&x_empty[s], ph ^ 1); // the element-wise warps have read what block it - 2 left here
-				mbar_wait(&t_full[s], ph);
+				mbar_wait(&x_empty[s], ((uint32_t)(it >> 1) & 1) ^ 1); // the element-wise warps have read what block it - 2 left here
+				mbar_wait(&t_full[xst], xph);
 				tc_fence_after();
 				if (lane == 0)
 				{
-					const uint32_t t1_addr = smem_u32(smem + L::T_OFF + s * 2 * FB_T_BYTES);
+					const uint32_t t1_addr = smem_u32(smem + L::T_OFF + xst * 2 * FB_T_BYTES);
 					const uint32_t t2_addr = t1_addr + FB_T_BYTES;
 #pragma unroll
 					for (int k = 0; k < FB_D / 16; k++)
@@ -242,6 +256,8 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 					umma_commit(&x_full[s]);
 				}
 				__syncwarp();
+				if (++xst == NST)
+					xst = 0, xph ^= 1;
 			};
 			mbar_wait(r_full, 0);
 			issue_xy(0);
@@ -250,12 +266,11 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 				if (it + 1 < n_it)
 					issue_xy(it + 1); // one block ahead: overlaps the element-wise stage of block it
 				const int s = it & 1;
-				const uint32_t ph = (uint32_t)(it >> 1) & 1;
-				mbar_wait(&p_full[s], ph);
+				mbar_wait(&p_full[s], (uint32_t)(it >> 1) & 1);
 				tc_fence_after();
 				if (lane == 0)
 				{
-					const uint32_t t1_addr = smem_u32(smem + L::T_OFF + s * 2 * FB_T_BYTES);
+					const uint32_t t1_addr = smem_u32(smem + L::T_OFF + ast * 2 * FB_T_BYTES);
 					const uint32_t t2_addr = t1_addr + FB_T_BYTES;
 					const uint32_t ds_addr = smem_u32(smem + L::P_OFF + s * L::PBUF);
 					// A = the 128 x 64 tile just written (K-major, one atom), B = the streamed block as an MN-major operand: two 64-wide
@@ -268,27 +283,33 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 							umma_f16(tmem_a1, umma_smem_desc(ds_addr + FB_P_BYTES + k * 32, 16, 1024, 2), umma_smem_desc(t2_addr + k * 2048, FB_T_ATOM, 1024, 2), p.idesc_acc, acc);
 						umma_f16(tmem_a2, umma_smem_desc(ds_addr + k * 32, 16, 1024, 2), umma_smem_desc(t1_addr + k * 2048, FB_T_ATOM, 1024, 2), p.idesc_acc, acc);
 					}
-					umma_commit(&t_empty[s]);
+					umma_commit(&t_empty[ast]);
 					umma_commit(&p_empty[s]);
 					if (it + 1 == n_it)
 						umma_commit(acc_full);
 				}
 				__syncwarp();
+				if (++ast == NST)
+					ast = 0;
 			}
 		}
 	} else {
 		// ------------------------------------------------------------------ element-wise stage and epilogue (warps 2..9)
 		const int quarter = warp & 3;     // TMEM lanes [32 * quarter, +32) are the ones this warp may touch
 		const int half = (warp - 2) >> 2; // columns [32 * half, +32) of a 64-wide block; [64 * half, +64) of the accumulators
+		const int set = half;
 		const int row = quarter * 32 + lane;
 		const int rr = r0 + row; // MODE 0: key index, MODE 1: query index
 		const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-		float lse2 = INFINITY, delta = 0.f;
+		const int c0 = half * 32;
+		float nl = -INFINITY, nd = 0.f; // MODE 1: -lse2 and -delta of this thread's query
 		if (MODE == 1)
 		{
-			const float2 st = p.stat[((long long)b * p.H + hr) * p.Sq_r + rr]; // Sq_r is a whole number of tiles
-			lse2 = st.x, delta = st.y;
+			const float4 sv = p.stat[(((long long)b * p.H + hr) * p.Sq_r + rr) >> 1]; // Sq_r is a whole number of tiles
+			nl = (rr & 1) ? sv.y : sv.x, nd = (rr & 1) ? sv.w : sv.z;
 		}
+		int st = 0;
+		uint32_t tph = 0;
 		for (int it = 0; it < n_it; it++)
 		{
 			const int s = it & 1;
@@ -302,33 +323,35 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 					cmin = rr - shift - t0; // key rr is seen by queries >= rr - shift
 			} else
 				cmax = (p.causal ? min(p.Sk, rr + shift + 1) : p.Sk) - t0;
-			const int c0 = half * 32;
 			const bool edge = cmin > c0 || cmax < c0 + 32;
 			mbar_wait(&x_full[s], ph);
 			if (MODE == 0)
-				mbar_wait(&t_full[s], ph); // the stat pairs of this block (the MMA warp has observed this phase already)
+				mbar_wait(&t_full[st], tph); // the stat pairs of this block (the MMA warp has observed this phase already)
 			tc_fence_after();
 			uint32_t xr[32], yr[32];
 			tmem_ld_32x32(tmem_x + s * 64 + c0 + lane_sel, xr);
 			tmem_ld_32x32(tmem_y + s * 64 + c0 + lane_sel, yr);
 			tmem_ld_wait();
+			// X[s], Y[s] are in registers: the tensor core may overwrite them with block it + 2
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0)
 				mbar_arrive(&x_empty[s]);
-			const float2* const st = (const float2*)(smem + L::STAT_OFF + s * FB_STAT_BYTES) + c0;
+			const float4* const sp = (const float4*)(smem + L::STAT_OFF + st * FB_STAT_BYTES) + (c0 >> 1);
 			uint32_t pk[16], dk[16];
 #pragma unroll
 			for (int i = 0; i < 32; i += 2)
 			{
-				float l0 = lse2, l1 = lse2, d0 = delta, d1 = delta;
+				float l0 = nl, l1 = nl, d0 = nd, d1 = nd;
 				if (MODE == 0)
 				{
-					const float4 sv = *reinterpret_cast<const float4*>(st + i); // two (lse2, delta) pairs, the same address for the whole warp
-					l0 = sv.x, d0 = sv.y, l1 = sv.z, d1 = sv.w;
+					const float4 sv = sp[i >> 1]; // (-l, -l', -d, -d') of two queries, the same address for the whole warp
+					l0 = sv.x, l1 = sv.y, d0 = sv.z, d1 = sv.w;
 				}
-				float e0 = ex2_approx(fmaf(__uint_as_float(xr[i]), p.scale_log2, -l0));
-				float e1 = ex2_approx(fmaf(__uint_as_float(xr[i + 1]), p.scale_log2, -l1));
+				float t0f, t1f, u0, u1, g0, g1;
+				fma2(t0f, t1f, __uint_as_float(xr[i]), __uint_as_float(xr[i + 1]), p.scale_log2, p.scale_log2, l0, l1);
+				float e0 = ex2_approx(t0f);
+				float e1 = ex2_approx(t1f);
 				if (edge)
 				{
 					if (c0 + i < cmin || c0 + i >= cmax)
@@ -336,8 +359,8 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 					if (c0 + i + 1 < cmin || c0 + i + 1 >= cmax)
 						e1 = 0.f;
 				}
-				const float g0 = e0 * (__uint_as_float(yr[i]) - d0);
-				const float g1 = e1 * (__uint_as_float(yr[i + 1]) - d1);
+				fma2(u0, u1, __uint_as_float(yr[i]), __uint_as_float(yr[i + 1]), 1.f, 1.f, d0, d1);
+				fma2(g0, g1, e0, e1, u0, u1, 0.f, 0.f);
 				if (MODE == 0)
 					pk[i >> 1] = pack2(e0, e1, p.is_bf16);
 				dk[i >> 1] = pack2(g0, g1, p.is_bf16);
@@ -357,6 +380,8 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 			__syncwarp();
 			if (lane == 0)
 				mbar_arrive(&p_full[s]);
+			if (++st == NST)
+				st = 0, tph ^= 1;
 		}
 		// epilogue: the accumulators -> 16-bit gradients (this thread: one row, 64 of the 128 features)
 		if (n_it > 0)
@@ -371,7 +396,7 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 			uint32_t r[64];
 			if (n_it > 0)
 			{
-				const uint32_t ta = (a == 0 ? tmem_a1 : tmem_a2) + lane_sel + half * 64;
+				const uint32_t ta = (a == 0 ? tmem_a1 : tmem_a2) + lane_sel + set * 64;
 				tmem_ld_32x32(ta, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
 				tmem_ld_32x32(ta + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
 				tmem_ld_wait();
@@ -383,7 +408,7 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 			if (rr < limit)
 			{
 				const float f = a == 0 ? 1.f : p.scale;
-				uint16_t* const orow = a == 0 ? (uint16_t*)p.out1 + b * p.o1_b + (long long)rr * p.o1_s + hr * p.o1_h + half * 64 : (uint16_t*)p.out2 + b * p.o2_b + (long long)rr * p.o2_s + hr * p.o2_h + half * 64;
+				uint16_t* const orow = a == 0 ? (uint16_t*)p.out1 + b * p.o1_b + (long long)rr * p.o1_s + hr * p.o1_h + set * 64 : (uint16_t*)p.out2 + b * p.o2_b + (long long)rr * p.o2_s + hr * p.o2_h + set * 64;
 #pragma unroll
 				for (int i = 0; i < 64; i += 8)
 				{
@@ -433,7 +458,7 @@ int launch_bwd(cudaStream_t stream, const CUtensorMap& r1, const CUtensorMap& r2
 size_t sdpa_backward_f16_workspace_bytes(const SdpaGeom& g, int need_forward)
 {
 	const size_t sq_r = (size_t)(g.Sq + FB_R - 1) / FB_R * FB_R;
-	size_t bytes = (size_t)g.B * g.H * sq_r * sizeof(float2) + 256;
+	size_t bytes = (size_t)g.B * g.H * sq_r * 2 * sizeof(float) + 256;
 	if (need_forward) // O (16-bit, packed [B, Sq, H, D]) and the log-sum-exp [B, H, Sq]
 		bytes += (size_t)g.B * g.Sq * g.H * g.Dv * 2 + 256 + (size_t)g.B * g.H * g.Sq * sizeof(float) + 256;
 	return bytes;
@@ -461,8 +486,8 @@ int sdpa_backward_f16(cudaStream_t stream, const SdpaGeom& g, const SdpaGeom& dg
 		return 1;
 	const int sq_r = (g.Sq + FB_R - 1) / FB_R * FB_R;
 	uint8_t* ws = (uint8_t*)workspace;
-	float2* const stat = (float2*)ws;
-	ws += (((size_t)g.B * g.H * sq_r * sizeof(float2)) + 255) & ~(size_t)255;
+	float* const stat = (float*)ws;
+	ws += (((size_t)g.B * g.H * sq_r * 2 * sizeof(float)) + 255) & ~(size_t)255;
 	if (!out || !lse)
 	{
 		void* const o_ws = ws;
@@ -486,7 +511,7 @@ int sdpa_backward_f16(cudaStream_t stream, const SdpaGeom& g, const SdpaGeom& dg
 	p.H = g.H, p.Hk = g.Hk, p.Sq = g.Sq, p.Sk = g.Sk, p.Sq_r = sq_r;
 	p.causal = g.is_causal, p.is_bf16 = is_bf16;
 	p.scale = g.scale, p.scale_log2 = g.scale * 1.4426950408889634f;
-	p.stat = stat;
+	p.stat = (const float4*)stat;
 	p.idesc_xy = umma_instr_desc(is_bf16 ? 1 : 0, 0, 0, FB_R, FB_T);
 	p.idesc_acc = umma_instr_desc(is_bf16 ? 1 : 0, 0, 1, FB_R, FB_D);
 	// dK, dV: one CTA per 128 keys of a (batch, key head)
