@@ -23,13 +23,14 @@
 //   MODE 0: R1 = K, R2 = V, T1 = Q_i, T2 = dO_i:  X = R1 T1^T = S^T,  Y = R2 T2^T = dP^T,  acc1 += P^T T2 (dV),  acc2 += dS^T T1 (dK)
 //   MODE 1: R1 = Q, R2 = dO, T1 = K_j, T2 = V_j:  X = R1 T1^T = S,    Y = R2 T2^T = dP,    acc2 += dS T1 (dQ)
 // 320 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-9 = the element-wise stage (two warps per TMEM lane
-// quarter, 32 of the 64 columns each; measured faster than giving alternate blocks to two sets of four warps, which puts the
-// accumulate -> X / Y round trip of the tensor core on each set's critical path).  X, Y from TMEM -> P, dS as bf16 / fp16 K-major
-// 128-byte-swizzled smem tiles the accumulating MMAs read as their A operand; T1 / T2 are the B operand twice -- K-major for X / Y,
-// MN-major for the accumulation.  The streamed blocks sit in a ring of 3 (MODE 0) / 4 (MODE 1) stages: a stage is only free once the accumulation of its
+// quarter, 32 of the 64 columns each).  X, Y from TMEM -> P, dS as bf16 / fp16 pairs written straight back into TMEM (over the
+// columns just read), where the accumulating MMAs take them as their A operand: an MMA whose two operands come from shared memory
+// is bound by the operand fetch, not by the tensor core (profiles/r02_ncu_fmha_bwd.txt).  T1 / T2 are the B operand twice --
+// K-major for X / Y, MN-major for the accumulation.  The streamed blocks sit in a ring of 4 (MODE 0) / 7 (MODE 1) stages: a stage is only free once the accumulation of its
 // block has completed, and the next X / Y is issued one block ahead, so two stages would expose the whole TMA latency every block.
-// TMEM: X[2] 2 x 64 + Y[2] 2 x 64 + acc1 128 + acc2 128 = 512 columns.  smem: R 64 KB + T 3 x 32 KB + (P, dS) 2 x 32 KB = 224 KB
-// (MODE 0), R 64 KB + T 4 x 32 KB + dS 2 x 16 KB = 224 KB (MODE 1).
+// MODE 1 also keeps its resident tiles (Q, dout) in tensor memory, so every one of its MMAs reads only the streamed block from
+// shared memory.  TMEM: X[2] 2 x 64 + Y[2] 2 x 64 + dV 128 (MODE 0) | Q 64 + dout 64 (MODE 1) + dK | dQ 128 = 512 columns.
+// smem: R 64 KB + T 4 x 32 KB = 192 KB (MODE 0), T 7 x 32 KB = 224 KB (MODE 1).
 #include "sm100_contract.h"
 #include "sm100_fmha.cuh"
 #include <string.h>
@@ -45,7 +46,6 @@ constexpr int FB_R_ATOM = FB_R * 128;         // 16 KB: 128 rows x 64 features
 constexpr int FB_R_BYTES = 2 * FB_R_ATOM;     // 32 KB
 constexpr int FB_T_ATOM = FB_T * 128;         // 8 KB
 constexpr int FB_T_BYTES = 2 * FB_T_ATOM;     // 16 KB
-constexpr int FB_P_BYTES = FB_R * FB_T * 2;   // 16 KB: 128 rows x 64 columns, one swizzle atom wide
 constexpr int FB_STAT_BYTES = FB_T * 8;       // (-lse2, -delta) per streamed query, as float4 (-l0, -l1, -d0, -d1) per query pair
 
 struct FmhaBwdParams {
@@ -59,17 +59,19 @@ struct FmhaBwdParams {
 	long long o1_b, o1_s, o1_h;  // element strides
 	long long o2_b, o2_s, o2_h;
 	uint32_t idesc_xy, idesc_acc;
+	// MODE 1: the resident tiles (Q, dout) are read straight from global memory into tensor memory
+	const void* r1;
+	const void* r2;
+	long long r1_b, r1_s, r1_h, r2_b, r2_s, r2_h;
 };
 
 template <int MODE>
 struct FmhaBwdSmem {
-	static constexpr int NST = MODE == 0 ? 3 : 4; // stages of the streamed ring
-	static constexpr int PBUF = MODE == 0 ? 2 * FB_P_BYTES : FB_P_BYTES; // dS (+ P) per buffer
-	static constexpr int R1_OFF = 0;
+	static constexpr int NST = MODE == 0 ? 4 : 7; // stages of the streamed ring
+	static constexpr int R1_OFF = 0;              // MODE 0 only: MODE 1 keeps its resident tiles in tensor memory
 	static constexpr int R2_OFF = R1_OFF + FB_R_BYTES;
-	static constexpr int T_OFF = R2_OFF + FB_R_BYTES; // stage s: T1 at + s * 2 * FB_T_BYTES, T2 right behind it
-	static constexpr int P_OFF = T_OFF + NST * 2 * FB_T_BYTES; // buffer s: dS at + s * PBUF, P behind it (MODE 0)
-	static constexpr int STAT_OFF = P_OFF + 2 * PBUF;
+	static constexpr int T_OFF = MODE == 0 ? R2_OFF + FB_R_BYTES : 0; // stage s: T1 at + s * 2 * FB_T_BYTES, T2 right behind it
+	static constexpr int STAT_OFF = T_OFF + NST * 2 * FB_T_BYTES;
 	static constexpr int BAR_OFF = STAT_OFF + (MODE == 0 ? NST * FB_STAT_BYTES : 0);
 	static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 	static_assert(TOTAL <= 232448, "227 KB of shared memory per CTA");
@@ -137,10 +139,8 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 	uint64_t* t_full = bars + 1;          // [NST] TMA -> MMA (and the element-wise warps: the stat pairs ride on the same barrier)
 	uint64_t* t_empty = t_full + NST;     // [NST] MMA (accumulation done) -> TMA
 	uint64_t* x_full = t_empty + NST;     // [2] MMA -> element-wise: X and Y of this block are in TMEM
-	uint64_t* x_empty = x_full + 2;       // [2] element-wise -> MMA (8 arrivals): X, Y buffers read
-	uint64_t* p_full = x_empty + 2;       // [2] element-wise -> MMA (8 arrivals): P / dS tiles written
-	uint64_t* p_empty = p_full + 2;       // [2] MMA (accumulation done) -> element-wise
-	uint64_t* acc_full = p_empty + 2;
+	uint64_t* p_full = x_full + 2;        // [2] element-wise -> MMA (8 arrivals): P / dS written back into TMEM
+	uint64_t* acc_full = p_full + 2;
 	uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,13 +168,12 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 		tma_prefetch_desc(&tmR2);
 		tma_prefetch_desc(&tmT1);
 		tma_prefetch_desc(&tmT2);
-		mbar_init(r_full, 1);
+		mbar_init(r_full, MODE == 0 ? 1 : 8);
 		for (int s = 0; s < NST; s++)
 			mbar_init(&t_full[s], 1), mbar_init(&t_empty[s], 1);
 		for (int s = 0; s < 2; s++)
 		{
-			mbar_init(&x_full[s], 1), mbar_init(&x_empty[s], 8);
-			mbar_init(&p_full[s], 8), mbar_init(&p_empty[s], 1);
+			mbar_init(&x_full[s], 1), mbar_init(&p_full[s], 8);
 		}
 		mbar_init(acc_full, 1);
 		fence_mbar_init();
@@ -190,18 +189,23 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 	const uint32_t tmem_base = *tmem_slot;
 	const uint32_t tmem_x = tmem_base;        // X[s] at + 64 s
 	const uint32_t tmem_y = tmem_base + 128;  // Y[s] at + 64 s
-	const uint32_t tmem_a1 = tmem_base + 256; // dV
+	const uint32_t tmem_a1 = tmem_base + 256; // dV (MODE 0)
 	const uint32_t tmem_a2 = tmem_base + 384; // dK | dQ
+	const uint32_t tmem_r1 = tmem_base + 256; // MODE 1: Q and dout as 16-bit pairs, 64 columns each
+	const uint32_t tmem_r2 = tmem_base + 320;
 
 	if (warp == 0)
 	{
-		if (lane == 0 && n_it > 0)
+		if (n_it > 0 && elect_one())
 		{
-			mbar_expect_tx(r_full, 2 * FB_R_BYTES);
-			tma_load_4d(smem + L::R1_OFF, &tmR1, r_full, 0, hr, r0, b);
-			tma_load_4d(smem + L::R1_OFF + FB_R_ATOM, &tmR1, r_full, 64, hr, r0, b);
-			tma_load_4d(smem + L::R2_OFF, &tmR2, r_full, 0, hr, r0, b);
-			tma_load_4d(smem + L::R2_OFF + FB_R_ATOM, &tmR2, r_full, 64, hr, r0, b);
+			if (MODE == 0)
+			{
+				mbar_expect_tx(r_full, 2 * FB_R_BYTES);
+				tma_load_4d(smem + L::R1_OFF, &tmR1, r_full, 0, hr, r0, b);
+				tma_load_4d(smem + L::R1_OFF + FB_R_ATOM, &tmR1, r_full, 64, hr, r0, b);
+				tma_load_4d(smem + L::R2_OFF, &tmR2, r_full, 0, hr, r0, b);
+				tma_load_4d(smem + L::R2_OFF + FB_R_ATOM, &tmR2, r_full, 64, hr, r0, b);
+			}
 			int st = 0;
 			uint32_t ph = 0;
 			for (int it = 0; it < n_it; it++)
@@ -223,43 +227,54 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 			}
 		}
 	} else if (warp == 1) {
-		if (n_it > 0)
+		// One elected thread issues every MMA of the CTA.  `elect_one()` rather than `lane == 0`, and descriptors as base + constant:
+		// with a lane test ptxas cannot prove the operands uniform and wraps every tcgen05.mma in an elect / broadcast / branch loop plus the
+		// descriptor arithmetic -- about 12 dependent instructions per MMA, which made the issue rate, not the tensor core, the bound of the
+		// first version of this kernel (profiles/r02_ncu_fmha_bwd.txt).
+		if (n_it > 0 && elect_one())
 		{
-			const uint32_t r1_addr = smem_u32(smem + L::R1_OFF);
-			const uint32_t r2_addr = smem_u32(smem + L::R2_OFF);
+			const uint64_t r1_desc = umma_smem_desc(smem_u32(smem + L::R1_OFF), 16, 1024, 2);
+			const uint64_t r2_desc = umma_smem_desc(smem_u32(smem + L::R2_OFF), 16, 1024, 2);
+			const uint64_t t_kmajor = umma_smem_desc(smem_u32(smem + L::T_OFF), 16, 1024, 2);       // a streamed block as the K-major B operand of X / Y
+			const uint64_t t_mnmajor = umma_smem_desc(smem_u32(smem + L::T_OFF), FB_T_ATOM, 1024, 2); // and as the MN-major B operand of the accumulation
+			constexpr uint32_t STAGE16 = (2 * FB_T_BYTES) >> 4, T2_16 = FB_T_BYTES >> 4; // descriptor address units (16 bytes)
 			int xst = 0, ast = 0; // ring stage of the next X / Y block and of the next accumulation
 			uint32_t xph = 0;
 			// X = R1 T1^T, Y = R2 T2^T into buffer it & 1: both operands K-major, 8 steps of 16 features over the two 64-wide atoms
 			auto issue_xy = [&](const int it) {
 				const int s = it & 1;
-				mbar_wait(&x_empty[s], ((uint32_t)(it >> 1) & 1) ^ 1); // the element-wise warps have read what block it - 2 left here
+				// X[s] / Y[s] also hold P / dS of block it - 2 (below): the accumulation that reads them was issued before this point, and the
+				// tensor core executes its MMAs in issue order, so no barrier is needed before overwriting them
 				mbar_wait(&t_full[xst], xph);
 				tc_fence_after();
-				if (lane == 0)
+				const uint64_t t1 = t_kmajor + (uint32_t)xst * STAGE16;
+				const uint64_t t2 = t1 + T2_16;
+#pragma unroll
+				for (int k = 0; k < FB_D / 16; k++)
 				{
-					const uint32_t t1_addr = smem_u32(smem + L::T_OFF + xst * 2 * FB_T_BYTES);
-					const uint32_t t2_addr = t1_addr + FB_T_BYTES;
-#pragma unroll
-					for (int k = 0; k < FB_D / 16; k++)
-					{
-						const uint32_t ro = (uint32_t)(k >> 2) * FB_R_ATOM + (uint32_t)(k & 3) * 32;
-						const uint32_t to = (uint32_t)(k >> 2) * FB_T_ATOM + (uint32_t)(k & 3) * 32;
-						umma_f16(tmem_x + s * 64, umma_smem_desc(r1_addr + ro, 16, 1024, 2), umma_smem_desc(t1_addr + to, 16, 1024, 2), p.idesc_xy, k > 0 ? 1u : 0u);
-					}
-#pragma unroll
-					for (int k = 0; k < FB_D / 16; k++)
-					{
-						const uint32_t ro = (uint32_t)(k >> 2) * FB_R_ATOM + (uint32_t)(k & 3) * 32;
-						const uint32_t to = (uint32_t)(k >> 2) * FB_T_ATOM + (uint32_t)(k & 3) * 32;
-						umma_f16(tmem_y + s * 64, umma_smem_desc(r2_addr + ro, 16, 1024, 2), umma_smem_desc(t2_addr + to, 16, 1024, 2), p.idesc_xy, k > 0 ? 1u : 0u);
-					}
-					umma_commit(&x_full[s]);
+					const uint32_t ro = ((uint32_t)(k >> 2) * FB_R_ATOM + (uint32_t)(k & 3) * 32) >> 4;
+					const uint32_t to = ((uint32_t)(k >> 2) * FB_T_ATOM + (uint32_t)(k & 3) * 32) >> 4;
+					if (MODE == 0)
+						umma_f16(tmem_x + s * 64, r1_desc + ro, t1 + to, p.idesc_xy, k > 0 ? 1u : 0u);
+					else // the resident operand from tensor memory: 8 columns per 16 features
+						umma_f16_ts(tmem_x + s * 64, tmem_r1 + k * 8, t1 + to, p.idesc_xy, k > 0 ? 1u : 0u);
 				}
-				__syncwarp();
+#pragma unroll
+				for (int k = 0; k < FB_D / 16; k++)
+				{
+					const uint32_t ro = ((uint32_t)(k >> 2) * FB_R_ATOM + (uint32_t)(k & 3) * 32) >> 4;
+					const uint32_t to = ((uint32_t)(k >> 2) * FB_T_ATOM + (uint32_t)(k & 3) * 32) >> 4;
+					if (MODE == 0)
+						umma_f16(tmem_y + s * 64, r2_desc + ro, t2 + to, p.idesc_xy, k > 0 ? 1u : 0u);
+					else
+						umma_f16_ts(tmem_y + s * 64, tmem_r2 + k * 8, t2 + to, p.idesc_xy, k > 0 ? 1u : 0u);
+				}
+				umma_commit(&x_full[s]);
 				if (++xst == NST)
 					xst = 0, xph ^= 1;
 			};
 			mbar_wait(r_full, 0);
+			tc_fence_after();
 			issue_xy(0);
 			for (int it = 0; it < n_it; it++)
 			{
@@ -268,27 +283,23 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 				const int s = it & 1;
 				mbar_wait(&p_full[s], (uint32_t)(it >> 1) & 1);
 				tc_fence_after();
-				if (lane == 0)
-				{
-					const uint32_t t1_addr = smem_u32(smem + L::T_OFF + ast * 2 * FB_T_BYTES);
-					const uint32_t t2_addr = t1_addr + FB_T_BYTES;
-					const uint32_t ds_addr = smem_u32(smem + L::P_OFF + s * L::PBUF);
-					// A = the 128 x 64 tile just written (K-major, one atom), B = the streamed block as an MN-major operand: two 64-wide
-					// feature atoms 8 KB apart (LBO), 8-row groups 1 KB apart (SBO), one MMA consumes 16 rows = 2 KB
+				const uint64_t t1 = t_mnmajor + (uint32_t)ast * STAGE16;
+				const uint64_t t2 = t1 + T2_16;
+				// A = P / dS from tensor memory (written over the first 16 columns of each 32-column half of X[s] / Y[s]: 8 columns per
+				// 16 rows of the streamed block), B = the streamed block as an MN-major operand: two 64-wide feature atoms 8 KB apart
+				// (LBO), 8-row groups 1 KB apart (SBO), one MMA consumes 16 rows = 2 KB
 #pragma unroll
-					for (int k = 0; k < FB_T / 16; k++)
-					{
-						const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-						if (MODE == 0)
-							umma_f16(tmem_a1, umma_smem_desc(ds_addr + FB_P_BYTES + k * 32, 16, 1024, 2), umma_smem_desc(t2_addr + k * 2048, FB_T_ATOM, 1024, 2), p.idesc_acc, acc);
-						umma_f16(tmem_a2, umma_smem_desc(ds_addr + k * 32, 16, 1024, 2), umma_smem_desc(t1_addr + k * 2048, FB_T_ATOM, 1024, 2), p.idesc_acc, acc);
-					}
-					umma_commit(&t_empty[ast]);
-					umma_commit(&p_empty[s]);
-					if (it + 1 == n_it)
-						umma_commit(acc_full);
+				for (int k = 0; k < FB_T / 16; k++)
+				{
+					const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+					const uint32_t a_col = (uint32_t)s * 64 + (uint32_t)(k >> 1) * 32 + (uint32_t)(k & 1) * 8;
+					if (MODE == 0)
+						umma_f16_ts(tmem_a1, tmem_x + a_col, t2 + k * (2048 >> 4), p.idesc_acc, acc);
+					umma_f16_ts(tmem_a2, tmem_y + a_col, t1 + k * (2048 >> 4), p.idesc_acc, acc);
 				}
-				__syncwarp();
+				umma_commit(&t_empty[ast]);
+				if (it + 1 == n_it)
+					umma_commit(acc_full);
 				if (++ast == NST)
 					ast = 0;
 			}
@@ -307,6 +318,36 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 		{
 			const float4 sv = p.stat[(((long long)b * p.H + hr) * p.Sq_r + rr) >> 1]; // Sq_r is a whole number of tiles
 			nl = (rr & 1) ? sv.y : sv.x, nd = (rr & 1) ? sv.w : sv.z;
+		}
+		if (MODE == 1 && n_it > 0)
+		{
+			// the resident tiles: this thread's row of Q and of dout, 64 of the 128 features each, global -> registers -> tensor memory
+			// (two 16-bit elements per column in memory order = the K-major A operand layout); rows past the end are zero
+#pragma unroll
+			for (int a = 0; a < 2; a++)
+			{
+				uint32_t r[32];
+				if (rr < p.Sq)
+				{
+					const uint16_t* const src = a == 0 ? (const uint16_t*)p.r1 + b * p.r1_b + (long long)rr * p.r1_s + hr * p.r1_h + half * 64 : (const uint16_t*)p.r2 + b * p.r2_b + (long long)rr * p.r2_s + hr * p.r2_h + half * 64;
+#pragma unroll
+					for (int i = 0; i < 8; i++)
+					{
+						const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+						r[i * 4] = v.x, r[i * 4 + 1] = v.y, r[i * 4 + 2] = v.z, r[i * 4 + 3] = v.w;
+					}
+				} else {
+#pragma unroll
+					for (int i = 0; i < 32; i++)
+						r[i] = 0;
+				}
+				tmem_st_32x32((a == 0 ? tmem_r1 : tmem_r2) + half * 32 + lane_sel, r);
+			}
+			tmem_st_wait();
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(r_full);
 		}
 		int st = 0;
 		uint32_t tph = 0;
@@ -332,11 +373,6 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 			tmem_ld_32x32(tmem_x + s * 64 + c0 + lane_sel, xr);
 			tmem_ld_32x32(tmem_y + s * 64 + c0 + lane_sel, yr);
 			tmem_ld_wait();
-			// X[s], Y[s] are in registers: the tensor core may overwrite them with block it + 2
-			tc_fence_before();
-			__syncwarp();
-			if (lane == 0)
-				mbar_arrive(&x_empty[s]);
 			const float4* const sp = (const float4*)(smem + L::STAT_OFF + st * FB_STAT_BYTES) + (c0 >> 1);
 			uint32_t pk[16], dk[16];
 #pragma unroll
@@ -365,18 +401,13 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 					pk[i >> 1] = pack2(e0, e1, p.is_bf16);
 				dk[i >> 1] = pack2(g0, g1, p.is_bf16);
 			}
-			// the accumulation of block it - 2 has finished reading this P / dS buffer
-			mbar_wait(&p_empty[s], ph ^ 1);
-			uint8_t* const ds_row = smem + L::P_OFF + s * L::PBUF + row * 128;
-#pragma unroll
-			for (int c = 0; c < 4; c++)
-			{
-				const int chunk = ((half * 4 + c) ^ (row & 7)) << 4;
-				*reinterpret_cast<uint4*>(ds_row + chunk) = make_uint4(dk[c * 4], dk[c * 4 + 1], dk[c * 4 + 2], dk[c * 4 + 3]);
-				if (MODE == 0)
-					*reinterpret_cast<uint4*>(ds_row + FB_P_BYTES + chunk) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-			}
-			fence_proxy_async(); // generic-proxy smem writes -> the tensor core's async proxy
+			// P / dS go back into tensor memory as the A operand of the accumulating MMAs (16-bit pairs per column, K-major): over the first
+			// 16 columns of this thread's own 32 of X[s] / Y[s], which it has just read -- no shared-memory round trip
+			if (MODE == 0)
+				tmem_st_32x16(tmem_x + s * 64 + c0 + lane_sel, pk);
+			tmem_st_32x16(tmem_y + s * 64 + c0 + lane_sel, dk);
+			tmem_st_wait();
+			tc_fence_before();
 			__syncwarp();
 			if (lane == 0)
 				mbar_arrive(&p_full[s]);
@@ -523,6 +554,8 @@ int sdpa_backward_f16(cudaStream_t stream, const SdpaGeom& g, const SdpaGeom& dg
 	// dQ: one CTA per 128 queries of a (batch, query head)
 	p.out1 = 0;
 	p.out2 = dq, p.o2_b = dg.q_b, p.o2_s = dg.q_s, p.o2_h = dg.q_h;
+	p.r1 = q, p.r1_b = g.q_b, p.r1_s = g.q_s, p.r1_h = g.q_h;
+	p.r2 = dout, p.r2_b = g.o_b, p.r2_s = g.o_s, p.r2_h = g.o_h;
 	return launch_bwd<1>(stream, tmQr, tmGr, tmKt, tmVt, p, (g.Sq + FB_R - 1) / FB_R, g.H, g.B);
 }
 
