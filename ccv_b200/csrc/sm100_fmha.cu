@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 
 	if (warp == 0)
 	{
-		if (lane == 0 && n_max > 0)
+		if (n_max > 0 && elect_one())
 		{
 			if (n_blk > 0)
 			{
@@ -161,10 +161,16 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 			}
 		}
 	} else if (warp == 1) {
-		if (n_max > 0)
+		// one elected thread issues every MMA, descriptors as base + constant: operands stay in uniform registers (with a `lane == 0` test
+		// ptxas wraps each tcgen05.mma in an elect / broadcast / branch loop and rebuilds the descriptors, ~12 dependent instructions per MMA)
+		if (n_max > 0 && elect_one())
 		{
-			const uint32_t q_addr = smem_u32(smem + FmhaSmem::Q_OFF);
-			const uint32_t p_addr = smem_u32(smem + FmhaSmem::P_OFF);
+			const uint64_t q_desc = umma_smem_desc(smem_u32(smem + FmhaSmem::Q_OFF), 16, 1024, 2);
+			const uint64_t p_desc = umma_smem_desc(smem_u32(smem + FmhaSmem::P_OFF), 16, 1024, 2);
+			const uint64_t k_desc0 = umma_smem_desc(smem_u32(smem + FmhaSmem::K_OFF), 16, 1024, 2);
+			const uint64_t v_desc0 = umma_smem_desc(smem_u32(smem + FmhaSmem::V_OFF), p.v_lbo, p.v_sbo, p.v_layout);
+			const uint32_t v_kstep16 = p.v_kstep >> 4;
+			const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
 			auto release = [&](uint64_t* bar) {
 				if (CL == 1)
 					umma_commit(bar);
@@ -179,23 +185,19 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 					mbar_wait(&s_empty[s], ph ^ 1); // softmax has finished reading what block j - 2 left in this buffer
 				mbar_wait(&k_full[s], ph);
 				tc_fence_after();
-				if (lane == 0)
+				if (j < n_blk)
 				{
-					if (j < n_blk)
-					{
-						const uint32_t k_addr = smem_u32(smem + FmhaSmem::K_OFF + s * FM_TILE_BYTES);
+					const uint64_t k_desc = k_desc0 + (uint32_t)s * (uint32_t)(FM_TILE_BYTES >> 4);
 #pragma unroll
-						for (int k = 0; k < FM_D / 16; k++)
-						{
-							const uint32_t off = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
-							umma_f16(tmem_base + s * 128, umma_smem_desc(q_addr + off, 16, 1024, 2), umma_smem_desc(k_addr + off, 16, 1024, 2), p.idesc_qk, k > 0 ? 1u : 0u);
-						}
+					for (int k = 0; k < FM_D / 16; k++)
+					{
+						const uint32_t off = ((uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32) >> 4;
+						umma_f16(tmem_base + s * 128, q_desc + off, k_desc + off, idesc_qk, k > 0 ? 1u : 0u);
 					}
-					release(&k_empty[s]);
-					if (j < n_blk)
-						umma_commit(&s_full[s]);
 				}
-				__syncwarp();
+				release(&k_empty[s]);
+				if (j < n_blk)
+					umma_commit(&s_full[s]);
 			};
 			if (n_blk > 0)
 				mbar_wait(q_full, 0);
@@ -210,23 +212,19 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 					mbar_wait(p_full, (uint32_t)j & 1);
 				mbar_wait(&v_full[s], ph);
 				tc_fence_after();
-				if (lane == 0)
+				if (j < n_blk)
 				{
-					if (j < n_blk)
-					{
-						const uint32_t v_addr = smem_u32(smem + FmhaSmem::V_OFF + s * FM_TILE_BYTES);
+					const uint64_t v_desc = v_desc0 + (uint32_t)s * (uint32_t)(FM_TILE_BYTES >> 4);
 #pragma unroll
-						for (int k = 0; k < FM_BLOCK / 16; k++)
-						{
-							const uint32_t poff = (uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32;
-							umma_f16(tmem_o + (uint32_t)(j & 1) * 128, umma_smem_desc(p_addr + poff, 16, 1024, 2), umma_smem_desc(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo, p.v_layout), p.idesc_pv, k > 0 ? 1u : 0u);
-						}
+					for (int k = 0; k < FM_BLOCK / 16; k++)
+					{
+						const uint32_t poff = ((uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32) >> 4;
+						umma_f16(tmem_o + (uint32_t)(j & 1) * 128, p_desc + poff, v_desc + k * v_kstep16, idesc_pv, k > 0 ? 1u : 0u);
 					}
-					release(&v_empty[s]);
-					if (j < n_blk)
-						umma_commit(o_full);
 				}
-				__syncwarp();
+				release(&v_empty[s]);
+				if (j < n_blk)
+					umma_commit(o_full);
 			}
 		}
 	} else {

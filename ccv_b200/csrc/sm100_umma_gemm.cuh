@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
 	if (warp == 0)
 	{
 		// ------------------------------------------------------------------ TMA producer
-		if (lane == 0 && n_it > 0)
+		if (n_it > 0 && elect_one())
 		{
 			// im2col base coordinates of this tile's first row (A side); fixed for the whole loop
 			int a_w = 0, a_h = 0, a_n = 0;
@@ -186,34 +186,32 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
 			}
 		}
 	} else if (warp == 1) {
-		// ------------------------------------------------------------------ MMA issuer
-		if (n_it > 0)
+		// ------------------------------------------------------------------ MMA issuer: one elected thread, operands in uniform registers
+		// (sm100_umma_persistent.cuh explains why not `lane == 0`)
+		if (n_it > 0 && elect_one())
 		{
+			const uint32_t smem_base = smem_u32(smem);
+			// K-major (SWIZZLE_128B): 8 fp32 = 32 bytes along the swizzled row per MMA; SBO = 8 rows x 128 B.
+			// MN-major tf32 (SWIZZLE_128B_BASE32B is the only legal layout): 8 k-rows x 128 B = 1024 bytes per MMA;
+			// LBO = stride between 32-wide MN groups, SBO = stride between 4-row k atoms.  The start-address field counts 16-byte units.
+			const uint64_t a_desc0 = (AMODE == OP_MN2D) ? umma_smem_desc(smem_base, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(smem_base, 16, 1024, 2);
+			const uint64_t b_desc0 = (BMODE == OP_K2D) ? umma_smem_desc(smem_base + S::A_BYTES, 16, 1024, 2) : umma_smem_desc(smem_base + S::A_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+			constexpr uint32_t A_STEP = (AMODE == OP_MN2D ? 1024 : 32) >> 4, B_STEP = (BMODE == OP_K2D ? 32 : 1024) >> 4;
+			const uint32_t idesc = p.idesc;
 			int stage = 0;
 			uint32_t phase = 0;
 			for (int it = 0; it < n_it; it++)
 			{
 				mbar_wait(&full_bar[stage], phase);
 				tc_fence_after();
-				if (lane == 0)
-				{
-					const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-					const uint32_t b_addr = a_addr + S::A_BYTES;
+				const uint64_t da0 = a_desc0 + (uint32_t)stage * (uint32_t)(S::STAGE_BYTES >> 4);
+				const uint64_t db0 = b_desc0 + (uint32_t)stage * (uint32_t)(S::STAGE_BYTES >> 4);
 #pragma unroll
-					for (int k = 0; k < UMMA_BLOCK_K / 8; k++)
-					{
-						// K-major (SWIZZLE_128B): 8 fp32 = 32 bytes along the swizzled row; SBO = 8 rows x 128 B.
-						// MN-major tf32 (SWIZZLE_128B_BASE32B is the only legal layout): 8 k-rows x 128 B = 1024 bytes per MMA;
-						// LBO = stride between 32-wide MN groups, SBO = stride between 4-row k atoms.
-						const uint64_t da = (AMODE == OP_MN2D) ? umma_smem_desc(a_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
-						const uint64_t db = (BMODE == OP_K2D) ? umma_smem_desc(b_addr + k * 32, 16, 1024, 2) : umma_smem_desc(b_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout);
-						umma_tf32(tmem_base, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
-					}
-					umma_commit(&empty_bar[stage]); // frees the smem stage once these MMAs have read it
-					if (it == n_it - 1)
-						umma_commit(tmem_full_bar);
-				}
-				__syncwarp();
+				for (int k = 0; k < UMMA_BLOCK_K / 8; k++)
+					umma_tf32(tmem_base, da0 + k * A_STEP, db0 + k * B_STEP, idesc, (it > 0 || k > 0) ? 1u : 0u);
+				umma_commit(&empty_bar[stage]); // frees the smem stage once these MMAs have read it
+				if (it == n_it - 1)
+					umma_commit(tmem_full_bar);
 				if (++stage == STAGES) { stage = 0; phase ^= 1; }
 			}
 		}

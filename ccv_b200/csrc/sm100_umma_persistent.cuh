@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 
 	if (warp == 0)
 	{
-		// ------------------------------------------------------------------ TMA producer
-		if (lane == 0)
+		// ------------------------------------------------------------------ TMA producer (one elected thread, see the MMA issuer)
+		if (elect_one())
 		{
 			int stage = 0;
 			uint32_t phase = 0;
@@ -180,55 +180,60 @@ __global__ void __launch_bounds__(64 + EPIW * 32 + (X3 ? 128 : 0), 1) umma_gemm_
 		}
 	} else if (warp == 1) {
 		// ------------------------------------------------------------------ MMA issuer
-		int stage = 0;
-		uint32_t phase = 0;
-		int t = 0;
-		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++)
+		// One elected thread runs the whole role.  `elect_one()` (not a lane test) and descriptors as base + constant keep every operand in
+		// uniform registers: with `if (lane == 0)` around each issue ptxas wraps every tcgen05.mma in an elect / broadcast / branch loop and
+		// rebuilds the descriptors -- about 12 dependent instructions per MMA, more than a 128 x 64 MMA takes to execute.
+		if (elect_one())
 		{
-			const int zz = (tile / tiles_n) / tiles_m;
-			const int split = zz % p.splits;
-			const int it_begin = split * per;
-			const int n_it = min(p.k_iters, it_begin + per) - it_begin;
-			const int acc = t & 1;
-			const uint32_t acc_phase = (t >> 1) & 1;
-			mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1); // the epilogue has drained this accumulator
-			tc_fence_after();
-			const uint32_t tmem_d = tmem_base + acc * BN;
-			for (int it = 0; it < n_it; it++)
+			const uint32_t smem_base = smem_u32(smem);
+			const uint64_t a_desc0 = (AMODE == OP_MN2D) ? umma_smem_desc(smem_base, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(smem_base, 16, 1024, 2);
+			const uint64_t b_desc0 = (BMODE == OP_K2D) ? umma_smem_desc(smem_base + S::A_BYTES, 16, 1024, 2) : umma_smem_desc(smem_base + S::A_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+			// one MMA covers 32 bytes of K (8 fp32 / 16 16-bit): K-major operands advance 32 B inside the swizzled row, MN-major ones by
+			// UMMA_K k-rows of 128 B; the start-address field counts 16-byte units
+			constexpr uint32_t A_STEP = (AMODE == OP_MN2D ? MN_STEP : 32) >> 4, B_STEP = (BMODE == OP_K2D ? 32 : MN_STEP) >> 4;
+			const uint32_t idesc = p.idesc;
+			int stage = 0;
+			uint32_t phase = 0;
+			int t = 0;
+			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++)
 			{
-				mbar_wait(X3 ? &xform_bar[stage] : &full_bar[stage], phase);
+				const int zz = (tile / tiles_n) / tiles_m;
+				const int split = zz % p.splits;
+				const int it_begin = split * per;
+				const int n_it = min(p.k_iters, it_begin + per) - it_begin;
+				const int acc = t & 1;
+				const uint32_t acc_phase = (t >> 1) & 1;
+				mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1); // the epilogue has drained this accumulator
 				tc_fence_after();
-				if (lane == 0)
+				const uint32_t tmem_d = tmem_base + acc * BN;
+				for (int it = 0; it < n_it; it++)
 				{
-					const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-					const uint32_t b_addr = a_addr + S::A_BYTES;
+					mbar_wait(X3 ? &xform_bar[stage] : &full_bar[stage], phase);
+					tc_fence_after();
+					const uint64_t da0 = a_desc0 + (uint32_t)stage * (uint32_t)(S::STAGE_BYTES >> 4);
+					const uint64_t db0 = b_desc0 + (uint32_t)stage * (uint32_t)(S::STAGE_BYTES >> 4);
 #pragma unroll
 					for (int k = 0; k < UMMA_BLOCK_K / 8; k++)
 					{
-						// one MMA covers 32 bytes of K (8 fp32 / 16 16-bit): K-major operands advance 32 B inside the swizzled row,
-						// MN-major ones by UMMA_K k-rows of 128 B (p.mn_step)
-						const uint64_t da = (AMODE == OP_MN2D) ? umma_smem_desc(a_addr + k * MN_STEP, p.mn_lbo, p.mn_sbo, p.mn_layout) : umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
-						const uint64_t db = (BMODE == OP_K2D) ? umma_smem_desc(b_addr + k * 32, 16, 1024, 2) : umma_smem_desc(b_addr + k * MN_STEP, p.mn_lbo, p.mn_sbo, p.mn_layout);
+						const uint64_t da = da0 + k * A_STEP;
+						const uint64_t db = db0 + k * B_STEP;
 						if (K16)
-							umma_f16(tmem_d, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+							umma_f16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
 						else if (X3)
 						{
 							// the lo tiles sit RAW_BYTES behind their hi tiles (same layout): small terms first, then hi * hi
-							constexpr uint64_t LO = (uint64_t)(S::RAW_BYTES >> 4); // start-address field is in 16-byte units
-							umma_tf32(tmem_d, da + LO, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
-							umma_tf32(tmem_d, da, db + LO, p.idesc, 1u);
-							umma_tf32(tmem_d, da, db, p.idesc, 1u);
+							constexpr uint64_t LO = (uint64_t)(S::RAW_BYTES >> 4);
+							umma_tf32(tmem_d, da + LO, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+							umma_tf32(tmem_d, da, db + LO, idesc, 1u);
+							umma_tf32(tmem_d, da, db, idesc, 1u);
 						} else
-							umma_tf32(tmem_d, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+							umma_tf32(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
 					}
 					umma_commit(&empty_bar[stage]);
+					if (++stage == STAGES) { stage = 0; phase ^= 1; }
 				}
-				__syncwarp();
-				if (++stage == STAGES) { stage = 0; phase ^= 1; }
-			}
-			if (lane == 0)
 				umma_commit(&tmem_full_bar[acc]); // fires once every MMA of this tile has completed
-			__syncwarp();
+			}
 		}
 	} else if (X3 && warp >= 2 + EPIW) {
 		// ------------------------------------------------------------------ hi / lo split of every staged operand element (X3)

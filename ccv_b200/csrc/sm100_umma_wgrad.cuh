@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(192, 2) umma_wgrad_taps_kernel(const __grid_co
 
 	if (warp == 0)
 	{
-		if (lane == 0)
+		if (elect_one())
 		{
 			int stage = 0;
 			uint32_t phase = 0;
@@ -117,29 +117,29 @@ __global__ void __launch_bounds__(192, 2) umma_wgrad_taps_kernel(const __grid_co
 			}
 		}
 	} else if (warp == 1) {
-		int stage = 0;
-		uint32_t phase = 0;
-		for (int it = 0; it < n_it; it++)
+		// one elected thread issues the MMAs, operands in uniform registers (see sm100_umma_persistent.cuh)
+		if (elect_one())
 		{
-			mbar_wait(&full_bar[stage], phase);
-			tc_fence_after();
-			if (lane == 0)
+			const uint32_t smem_base = smem_u32(smem);
+			const uint64_t a_desc0 = umma_smem_desc(smem_base, p.mn_lbo, p.mn_sbo, p.mn_layout);
+			const uint64_t b_desc0 = umma_smem_desc(smem_base + S::A_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+			const uint32_t idesc = p.idesc;
+			int stage = 0;
+			uint32_t phase = 0;
+			for (int it = 0; it < n_it; it++)
 			{
-				const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-				const uint32_t b_addr = a_addr + S::A_BYTES;
+				mbar_wait(&full_bar[stage], phase);
+				tc_fence_after();
+				const uint64_t da0 = a_desc0 + (uint32_t)stage * (uint32_t)(S::STAGE_BYTES >> 4);
+				const uint64_t db0 = b_desc0 + (uint32_t)stage * (uint32_t)(S::STAGE_BYTES >> 4);
 #pragma unroll
 				for (int k = 0; k < UMMA_BLOCK_K / 8; k++)
-				{
-					const uint64_t da = umma_smem_desc(a_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout);
-					const uint64_t db = umma_smem_desc(b_addr + k * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout);
-					umma_tf32(tmem_base, da, db, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
-				}
+					umma_tf32(tmem_base, da0 + k * (1024 >> 4), db0 + k * (1024 >> 4), idesc, (it > 0 || k > 0) ? 1u : 0u);
 				umma_commit(&empty_bar[stage]);
 				if (it == n_it - 1)
 					umma_commit(tmem_full_bar);
+				if (++stage == STAGES) { stage = 0; phase ^= 1; }
 			}
-			__syncwarp();
-			if (++stage == STAGES) { stage = 0; phase ^= 1; }
 		}
 	} else {
 		const int quarter = warp & 3;
