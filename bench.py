@@ -523,12 +523,15 @@ def profile_nodes(nnc, net, graphs, stream, pk, dtype="f32", algorithm=-1):
     tc = [r for r in rows if r["flops"] > 0]
     tc_flops, tc_ms = sum(r["flops"] for r in tc), sum(r["ms"] for r in tc)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    # DRAM bytes of the same launches from one `ncu --set full` capture (tools/run_ncu_traffic.sh -> profiles/): all
+    # every contraction command against ITS OWN bound, max(flops / tensor peak, algorithmic bytes / HBM peak): the 1x1 convolutions and the
+    # stem move more bytes than they have flops for (half of the 110 convolution commands of ResNet-50 at N = 256 are HBM-bound)
+    bound_ms = sum(max(r["flops"] / (tf32_peak * 1e12), r["bytes"] / (pk["hbm_gbs"] * 1e9)) for r in tc) * 1e3
+    # DRAM bytes of the same launches from one ncu capture (tools/run_ncu_profiles.sh -> profiles/): all
     # contraction launches of one step, to be read against the algorithmic operand + result bytes of those commands
     traffic, traffic_note = None, None
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_contraction_traffic.json")))
-        traffic, traffic_note = float(t["dram_bytes_per_step"]), "dram__bytes_read.sum + dram__bytes_write.sum over the %d contraction launches of one step (ncu --set full, profiles/r01_contraction_traffic.json)" % t["launches"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_contraction_traffic.json")))
+        traffic, traffic_note = float(t["dram_bytes_per_step"]), "dram__bytes_read.sum + dram__bytes_write.sum over the %d contraction launches of one step (ncu, tools/run_ncu_profiles.sh -> profiles/r02_contraction_traffic.json)" % t["launches"]
     except Exception:
         pass
     if dtype != "f32" or algorithm == 1:
@@ -536,7 +539,9 @@ def profile_nodes(nnc, net, graphs, stream, pk, dtype="f32", algorithm=-1):
     roofline = {"bound": "tensor", "kernel": "umma_* (tcgen05 GEMM / implicit-GEMM convolution kernels; all convolution + GEMM commands of one step)", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": achieved / tf32_peak, "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes_per_step": sum(r["bytes"] for r in tc),
                 "peak_source": "%s %s" % (pk["source"], peak_note),
-                "launch_ms_total": tc_ms, "algorithmic_flops_per_step": tc_flops, "total_ms_all_commands": sum(r["ms"] for r in rows)}
+                "launch_ms_total": tc_ms, "algorithmic_flops_per_step": tc_flops, "total_ms_all_commands": sum(r["ms"] for r in rows),
+                "per_command_bound_ms": bound_ms, "frac_of_per_command_bound": bound_ms / tc_ms if tc_ms > 0 else None,
+                "hbm_bound_commands": sum(1 for r in tc if r["bytes"] / (pk["hbm_gbs"] * 1e9) > r["flops"] / (tf32_peak * 1e12)), "contraction_commands": len(tc)}
     return dict(roofline=roofline, summary=summary, rows=rows)
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Sum DRAM traffic and duration over the tensor-core contraction launches of ONE bench step from an `ncu --set full` report
-(tools/run_ncu_traffic.sh) -> profiles/r01_contraction_traffic.json, which bench.py reports as roofline.traffic."""
+(tools/run_ncu_profiles.sh; launches_per_step 0 = autodetect the period) -> profiles/r0N_contraction_traffic.json, which bench.py reports as roofline.traffic."""
 import csv, json, subprocess, sys
 rep, launches_per_step, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], stderr=subprocess.DEVNULL).decode()
@@ -9,6 +9,10 @@ hdr, units = rows[0], rows[1]
 col = {n: hdr.index(n) for n in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+names = [r[col["Kernel Name"]] for r in rows[2:]]
+if launches_per_step <= 0:
+    # autodetect: the smallest period of the kernel-name sequence (every step launches the same contraction kernels in the same order)
+    launches_per_step = next((P for P in range(8, len(names) // 2 + 1) if names[:P] == names[P:2 * P]), len(names))
 body = rows[2:][:launches_per_step]
 tot_b = tot_ms = 0.0
 per = {}
