@@ -30,6 +30,9 @@ constexpr int FM_D = 128;     // head dimension (q/k and v)
 constexpr int FM_TILE_BYTES = FM_BLOCK * FM_D * 2; // 32 KB: two 128 x 64 swizzle atoms
 constexpr int FM_ATOM_BYTES = FM_BLOCK * 128;      // 16 KB
 constexpr int FM_KV_STAGES = 2;
+// P_j goes back into tensor memory (16-bit pairs over the first 32 columns of each 64-column half of S[j & 1]) and is the A operand of
+// O_j = P_j V_j from there: no shared-memory write / fence / operand fetch for P.  0 = the shared-memory P tile of round 1.
+constexpr int FM_P_IN_TMEM = 1;
 
 struct FmhaParams {
 	int H, Hk, Sq, Sk;
@@ -181,8 +184,10 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 			auto issue_qk = [&](const int j) {
 				const int s = j & 1;
 				const uint32_t ph = (uint32_t)(j >> 1) & 1;
-				if (j < n_blk)
-					mbar_wait(&s_empty[s], ph ^ 1); // softmax has finished reading what block j - 2 left in this buffer
+				// S[s] still holds block j - 2: the softmax warps have read it (shared-memory P), or P_{j-2} lives in it and the P V MMA that
+				// reads it was issued before this point -- the tensor core executes in issue order, no barrier needed (P in TMEM)
+				if (!FM_P_IN_TMEM && j < n_blk)
+					mbar_wait(&s_empty[s], ph ^ 1);
 				mbar_wait(&k_full[s], ph);
 				tc_fence_after();
 				if (j < n_blk)
@@ -219,7 +224,10 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 					for (int k = 0; k < FM_BLOCK / 16; k++)
 					{
 						const uint32_t poff = ((uint32_t)(k >> 2) * FM_ATOM_BYTES + (uint32_t)(k & 3) * 32) >> 4;
-						umma_f16(tmem_o + (uint32_t)(j & 1) * 128, p_desc + poff, v_desc + k * v_kstep16, idesc_pv, k > 0 ? 1u : 0u);
+						if (FM_P_IN_TMEM) // 16 keys = 8 columns; keys [64 h, 64 h + 64) sit in columns [64 h, 64 h + 32) of S[s]
+							umma_f16_ts(tmem_o + (uint32_t)(j & 1) * 128, tmem_base + s * 128 + (uint32_t)(k >> 2) * 64 + (uint32_t)(k & 3) * 8, v_desc + k * v_kstep16, idesc_pv, k > 0 ? 1u : 0u);
+						else
+							umma_f16(tmem_o + (uint32_t)(j & 1) * 128, p_desc + poff, v_desc + k * v_kstep16, idesc_pv, k > 0 ? 1u : 0u);
 					}
 				}
 				release(&v_empty[s]);
@@ -294,24 +302,40 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 				sum += e0 + e1;
 				pk[i >> 1] = pack2(e0, e1, p.is_bf16);
 			}
-			// o_full flips when O_{j-1} = P_{j-1} V_{j-1} is complete: the P tile may be overwritten
-			if (j > 0)
+			if (FM_P_IN_TMEM)
 			{
-				mbar_wait(o_full, (uint32_t)(j - 1) & 1);
-				tc_fence_after();
-			}
-			// P tile in smem (K-major, 128-byte swizzle; this half = one 64-key atom)
+				// P_j over the first 32 columns of this thread's own 64 of S[s] (which it has just read), as the K-major A operand
+				tmem_st_32x32(ts, pk);
+				tmem_st_wait();
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0)
+					mbar_arrive(p_full);
+				if (j > 0)
+				{
+					mbar_wait(o_full, (uint32_t)(j - 1) & 1); // O_{j-1} = P_{j-1} V_{j-1} is complete
+					tc_fence_after();
+				}
+			} else {
+				// o_full flips when O_{j-1} = P_{j-1} V_{j-1} is complete: the P tile may be overwritten
+				if (j > 0)
+				{
+					mbar_wait(o_full, (uint32_t)(j - 1) & 1);
+					tc_fence_after();
+				}
+				// P tile in smem (K-major, 128-byte swizzle; this half = one 64-key atom)
 #pragma unroll
-			for (int c = 0; c < 8; c++)
-				*reinterpret_cast<uint4*>(p_row + ((c ^ (row & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-			// hand S[s] back and publish P_j to the tensor core (generic-proxy smem writes -> async proxy)
-			fence_proxy_async();
-			tc_fence_before();
-			__syncwarp();
-			if (lane == 0)
-			{
-				mbar_arrive(&s_empty[s]);
-				mbar_arrive(p_full);
+				for (int c = 0; c < 8; c++)
+					*reinterpret_cast<uint4*>(p_row + ((c ^ (row & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+				// hand S[s] back and publish P_j to the tensor core (generic-proxy smem writes -> async proxy)
+				fence_proxy_async();
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0)
+				{
+					mbar_arrive(&s_empty[s]);
+					mbar_arrive(p_full);
+				}
 			}
 			// O_{j-1} sits in the other output buffer (O_j goes to O[j & 1]): fold it into the running output off the critical
 			// path, while the tensor core already works on P_j V_j
