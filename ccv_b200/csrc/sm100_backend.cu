@@ -1568,6 +1568,18 @@ int autotune_contraction(const ccv_nnc_cmd_t cmd, const size_t max_workspace_siz
 
 } // namespace
 
+namespace sm100 {
+int backend_gemm_nt_bias(void* stream_context, int kind, int M, int N, int K, const void* a, const void* w, void* c, const void* bias, int bias_is_f32)
+{
+	ccv_nnc_stream_context_t* const ctx = (ccv_nnc_stream_context_t*)stream_context;
+	const Scratch scratch = scratch_of(ctx);
+	cudaStream_t s = stream_of(ctx);
+	if (kind == 0)
+		return gemm_dispatch(s, scratch, CCV_NNC_SM100_ALGO_3XTF32, M, N, K, (const float*)a, K, 1, (const float*)w, 1, K, (float*)c, N, 1, (const float*)bias, 0);
+	return gemm_dispatch16(s, scratch, kind, M, N, K, a, K, 1, w, 1, K, c, N, 1, bias && bias_is_f32 ? (const float*)bias : 0, bias && !bias_is_f32 ? bias : 0, 0);
+}
+} // namespace sm100
+
 // implemented in sm100_backend_ext.cu (attention, layer / rms norm, upsample, allreduce)
 extern "C" {
 int ccv_nnc_sm100_exec_sdpa_forw(const ccv_nnc_cmd_t, const ccv_nnc_hint_t, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_tensor_t* const*, const int, ccv_nnc_stream_context_t*);

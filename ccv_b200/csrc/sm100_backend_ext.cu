@@ -121,13 +121,10 @@ static bool sdpa_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_tensor_t* const q,
 }
 
 // scaled_dot_product_attention/ccv_nnc_scaled_dot_product_attention_cpu_ref.c:16-183: inputs (q, k, v, [attn_mask]) ->
-// outputs (y, [softmax_lse]).  The fused "unify head" projection (inputs 4, 5) is not offered (CCV_NNC_EXEC_INVALID), the
-// same restriction the reference's flash-attention backend has for its backward (…flash_attn.cu:247-248).
-int ccv_nnc_sm100_exec_sdpa_forw(SM100_EXEC_ARGS)
+// outputs (y, [softmax_lse]); `outputs` here already has the per-head attention tensor in slot 0 (see the entry point below)
+static int sdpa_forw_core(SM100_EXEC_ARGS)
 {
 	if (input_size < 3 || output_size < 1 || !inputs[0] || !inputs[1] || !inputs[2] || !outputs[0])
-		return CCV_NNC_EXEC_INVALID;
-	if (input_size > 4 && inputs[4])
 		return CCV_NNC_EXEC_INVALID;
 	SdpaGeom g;
 	if (!sdpa_geom(cmd, inputs[0], inputs[1], inputs[2], outputs[0], g))
@@ -197,6 +194,54 @@ int ccv_nnc_sm100_exec_sdpa_forw(SM100_EXEC_ARGS)
 	if (!ws)
 		return CCV_NNC_EXEC_OOM;
 	if (sdpa_forward_f32(stream_of(stream_context), g, inputs[0]->data.f32, inputs[1]->data.f32, inputs[2]->data.f32, mask, outputs[0]->data.f32, ws))
+		return CCV_NNC_EXEC_INVALID;
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+
+// The command's entry point.  With "unify head" weights (inputs[4] = w [H Dv, H Dv], inputs[5] = bias, :26-27,:184-255) the per-head
+// attention goes to outputs[2] and outputs[0] = that tensor seen as [B, Sq, H Dv], times w^T, plus bias: the attention above followed
+// by one dense projection on the tensor cores (fp32: the GEMM command's default 3xTF32; 16-bit: kind::f16).
+int ccv_nnc_sm100_exec_sdpa_forw(SM100_EXEC_ARGS)
+{
+	ccv_nnc_tensor_t* const w = input_size > 4 ? inputs[4] : 0;
+	ccv_nnc_tensor_t* const bias = input_size > 5 ? inputs[5] : 0;
+	if (!w)
+	{
+		if (bias) // a bias always requires a weight matrix (:27-28)
+			return CCV_NNC_EXEC_INVALID;
+		return sdpa_forw_core(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	}
+	if (input_size < 3 || output_size < 3 || !outputs[0] || !outputs[2] || !inputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	ccv_nnc_tensor_t* const c = outputs[2];
+	ccv_nnc_tensor_t* const d = outputs[0];
+	const int dt = CCV_GET_DATA_TYPE(inputs[0]->info.datatype);
+	const int c_nd = nd_of(c), d_nd = nd_of(d);
+	if (CCV_IS_TENSOR_VIEW(c) || CCV_IS_TENSOR_VIEW(d) || CCV_IS_TENSOR_VIEW(w) || (c_nd != 3 && c_nd != 4) || d_nd != 3 || nd_of(w) != 2)
+		return CCV_NNC_EXEC_INVALID;
+	if (CCV_GET_DATA_TYPE(c->info.datatype) != dt || CCV_GET_DATA_TYPE(d->info.datatype) != dt || CCV_GET_DATA_TYPE(w->info.datatype) != dt)
+		return CCV_NNC_EXEC_INVALID;
+	const int B = c->info.dim[0], S = c->info.dim[1];
+	const long long hd = c_nd == 4 ? (long long)c->info.dim[2] * c->info.dim[3] : c->info.dim[2];
+	if (d->info.dim[0] != B || d->info.dim[1] != S || d->info.dim[2] != hd || w->info.dim[0] != hd || w->info.dim[1] != hd || hd > 0x7fffffff || (long long)B * S > 0x7fffffff)
+		return CCV_NNC_EXEC_INVALID;
+	int bias_f32 = 0;
+	if (bias)
+	{
+		const int bdt = CCV_GET_DATA_TYPE(bias->info.datatype);
+		if (CCV_IS_TENSOR_VIEW(bias) || count_of(bias) != (size_t)hd || (bdt != dt && bdt != CCV_32F))
+			return CCV_NNC_EXEC_INVALID;
+		bias_f32 = bdt == CCV_32F;
+	}
+	// the attention proper, into c: inputs (q, k, v, mask), outputs (c, lse)
+	ccv_nnc_tensor_t* core_in[4] = { inputs[0], inputs[1], inputs[2], input_size > 3 ? inputs[3] : 0 };
+	ccv_nnc_tensor_t* core_out[2] = { c, output_size > 1 ? outputs[1] : 0 };
+	const int st = sdpa_forw_core(cmd, hint, flags, core_in, 4, core_out, 2, stream_context);
+	if (st != CCV_NNC_EXEC_SUCCESS)
+		return st;
+	const int kind = dt == CCV_32F ? 0 : (dt == CCV_16BF ? 1 : 2);
+	if (backend_gemm_nt_bias(stream_context, kind, B * S, (int)hd, (int)hd, c->data.u8, w->data.u8, d->data.u8, bias ? bias->data.u8 : 0, bias_f32))
 		return CCV_NNC_EXEC_INVALID;
 	return CCV_NNC_EXEC_SUCCESS;
 }

@@ -94,6 +94,11 @@ size_t sdpa_backward_f16_workspace_bytes(const SdpaGeom& g, int need_forward);
 int sdpa_backward_f16(cudaStream_t s, const SdpaGeom& g, const SdpaGeom& dg, int is_bf16, const void* dout, const void* q, const void* k, const void* v, const void* out, long long oo_b, long long oo_s, long long oo_h,
 	const float* lse, void* dq, void* dk, void* dv, void* workspace);
 
+// c[M, N] = a[M, K] w[N, K]^T (+ bias[N]) on the stream context's contraction scratch, all operands packed row-major; kind 0 = fp32
+// (the GEMM command's default algorithm, 3xTF32), 1 = bf16, 2 = fp16; bias in the operands' type or fp32 (bias_is_f32).  Used by
+// commands that end in a dense projection (the attention "unify head" output).  Returns 0, or non-zero like the GEMM launchers.
+int backend_gemm_nt_bias(void* stream_context, int kind, int M, int N, int K, const void* a, const void* w, void* c, const void* bias, int bias_is_f32);
+
 // bookkeeping shared by every launcher in the backend
 void count_launch(int n = 1);
 unsigned long long launch_count();

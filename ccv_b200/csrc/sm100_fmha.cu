@@ -36,6 +36,7 @@ constexpr int FM_P_IN_TMEM = 1;
 
 struct FmhaParams {
 	int H, Hk, Sq, Sk;
+	int D; // actual head dimension (<= 128, a multiple of 8): the tiles are always 128 wide, TMA zero-fills the rest
 	int causal;
 	int is_bf16;
 	float scale_log2; // scale * log2(e)
@@ -381,7 +382,8 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 			{
 				const uint4 v = make_uint4(pack2(acc[i] * inv, acc[i + 1] * inv, p.is_bf16), pack2(acc[i + 2] * inv, acc[i + 3] * inv, p.is_bf16),
 					pack2(acc[i + 4] * inv, acc[i + 5] * inv, p.is_bf16), pack2(acc[i + 6] * inv, acc[i + 7] * inv, p.is_bf16));
-				*reinterpret_cast<uint4*>(orow + i) = v;
+				if (half * 64 + i < p.D) // head dimensions below 128: the padded feature columns are not part of the tensor
+					*reinterpret_cast<uint4*>(orow + i) = v;
 			}
 			if (p.lse && half == 0)
 				p.lse[((long long)b * p.H + h) * p.Sq + qi] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
@@ -397,10 +399,11 @@ __global__ void __launch_bounds__(320, 1) fmha_fwd_kernel(const __grid_constant_
 
 } // namespace
 
-// returns 0 on success, 1 when the shape is outside this kernel (D = Dv = 128, 16-byte aligned strides), < 0 on CUDA errors
+// returns 0 on success, 1 when the shape is outside this kernel (D = Dv <= 128 and a multiple of 8 -- head dimensions below 128 run on the
+// same 128-wide tiles, the TMA unit zero-fills the missing features; 16-byte aligned strides), < 0 on CUDA errors
 int sdpa_forward_f16(cudaStream_t stream, const SdpaGeom& g, int is_bf16, const void* q, const void* k, const void* v, void* o, float* lse)
 {
-	if (g.D != FM_D || g.Dv != FM_D || g.B <= 0 || g.H <= 0 || g.Hk <= 0 || g.H % g.Hk != 0 || g.Sq <= 0 || g.Sk <= 0 || !encode_init())
+	if (g.D > FM_D || g.D < 8 || (g.D & 7) || g.Dv != g.D || g.B <= 0 || g.H <= 0 || g.Hk <= 0 || g.H % g.Hk != 0 || g.Sq <= 0 || g.Sk <= 0 || !encode_init())
 		return 1;
 	if ((((uintptr_t)o) & 15) || (g.o_b & 7) || (g.o_s & 7) || (g.o_h & 7))
 		return 1;
@@ -410,7 +413,7 @@ int sdpa_forward_f16(cudaStream_t stream, const SdpaGeom& g, int is_bf16, const 
 		return 1;
 	FmhaParams p;
 	memset(&p, 0, sizeof(p));
-	p.H = g.H, p.Hk = g.Hk, p.Sq = g.Sq, p.Sk = g.Sk;
+	p.H = g.H, p.Hk = g.Hk, p.Sq = g.Sq, p.Sk = g.Sk, p.D = g.D;
 	p.causal = g.is_causal, p.is_bf16 = is_bf16;
 	p.scale_log2 = g.scale * 1.4426950408889634f;
 	p.o = o, p.o_b = g.o_b, p.o_s = g.o_s, p.o_h = g.o_h;

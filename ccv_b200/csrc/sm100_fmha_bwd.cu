@@ -1,4 +1,5 @@
-// sm100_fmha_bwd.cu -- SCALED_DOT_PRODUCT_ATTENTION backward for 16-bit tensors (bf16 / fp16), head dimension 128: a fused
+// sm100_fmha_bwd.cu -- SCALED_DOT_PRODUCT_ATTENTION backward for 16-bit tensors (bf16 / fp16), head dimension <= 128 (multiples of 8;
+// the tiles are always 128 features wide, missing features are zero-filled by the TMA unit and never stored): a fused
 // flash-attention backward on the tcgen05 tensor cores, deterministic (no atomics, every sum in one fixed order).
 // Semantics: scaled_dot_product_attention/ccv_nnc_scaled_dot_product_attention_cpu_ref.c:259-479 (dq, dk, dv of
 // O = softmax(scale * Q K^T [causal, bottom-right aligned]) V, GQA gradients summed over the query heads of a key head); the reference's
@@ -50,6 +51,7 @@ constexpr int FB_STAT_BYTES = FB_T * 8;       // (-lse2, -delta) per streamed qu
 
 struct FmhaBwdParams {
 	int H, Hk, Sq, Sk, Sq_r;
+	int D; // actual head dimension (<= 128, a multiple of 8): tiles are 128 wide, missing features are zero-filled and never stored
 	int causal;
 	int is_bf16;
 	float scale, scale_log2;
@@ -83,7 +85,7 @@ __device__ __forceinline__ float widen16(const uint16_t u, const int is_bf16)
 }
 
 // (-lse * log2 e, -delta) per query row: 16 lanes per row, 8 features each
-__global__ void __launch_bounds__(256) fmha_bwd_prep_kernel(const uint16_t* __restrict__ dout, const uint16_t* __restrict__ out, const float* __restrict__ lse, float* __restrict__ stat, int B, int H, int Sq, int Sq_r, int is_bf16,
+__global__ void __launch_bounds__(256) fmha_bwd_prep_kernel(const uint16_t* __restrict__ dout, const uint16_t* __restrict__ out, const float* __restrict__ lse, float* __restrict__ stat, int B, int H, int Sq, int Sq_r, int D, int is_bf16,
 	long long do_b, long long do_s, long long do_h, long long o_b, long long o_s, long long o_h)
 {
 	const long long row = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(256) fmha_bwd_prep_kernel(const uint16_t* __re
 	const int h = (int)((row / Sq_r) % H);
 	const int b = (int)(row / ((long long)Sq_r * H));
 	float acc = 0.f;
-	if (q < Sq)
+	if (q < Sq && sub * 8 < D)
 	{
 		const uint4 a = *reinterpret_cast<const uint4*>(dout + b * do_b + (long long)q * do_s + h * do_h + sub * 8);
 		const uint4 c = *reinterpret_cast<const uint4*>(out + b * o_b + (long long)q * o_s + h * o_h + sub * 8);
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 #pragma unroll
 					for (int i = 0; i < 8; i++)
 					{
-						const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+						const uint4 v = half * 64 + i * 8 < p.D ? __ldg(reinterpret_cast<const uint4*>(src) + i) : make_uint4(0, 0, 0, 0);
 						r[i * 4] = v.x, r[i * 4 + 1] = v.y, r[i * 4 + 2] = v.z, r[i * 4 + 3] = v.w;
 					}
 				} else {
@@ -445,7 +447,8 @@ __global__ void __launch_bounds__(320, 1) fmha_bwd_kernel(const __grid_constant_
 				{
 					const uint4 v = make_uint4(pack2(__uint_as_float(r[i]) * f, __uint_as_float(r[i + 1]) * f, p.is_bf16), pack2(__uint_as_float(r[i + 2]) * f, __uint_as_float(r[i + 3]) * f, p.is_bf16),
 						pack2(__uint_as_float(r[i + 4]) * f, __uint_as_float(r[i + 5]) * f, p.is_bf16), pack2(__uint_as_float(r[i + 6]) * f, __uint_as_float(r[i + 7]) * f, p.is_bf16));
-					*reinterpret_cast<uint4*>(orow + i) = v;
+					if (set * 64 + i < p.D)
+						*reinterpret_cast<uint4*>(orow + i) = v;
 				}
 			}
 		}
@@ -497,11 +500,11 @@ size_t sdpa_backward_f16_workspace_bytes(const SdpaGeom& g, int need_forward)
 
 // g: q / k / v strides, o_* = the strides of dout; dg: the strides of dq / dk / dv in its q_* / k_* / v_* fields.  `out` (strides oo_*)
 // and `lse` are the forward's saved outputs; when either is NULL both are recomputed into the workspace with the forward kernel.
-// returns 0 on success, 1 when the shape is outside these kernels (D = Dv = 128, 16-byte aligned strides), < 0 on CUDA errors
+// returns 0 on success, 1 when the shape is outside these kernels (D = Dv <= 128 and a multiple of 8, 16-byte aligned strides), < 0 on CUDA errors
 int sdpa_backward_f16(cudaStream_t stream, const SdpaGeom& g, const SdpaGeom& dg, int is_bf16, const void* dout, const void* q, const void* k, const void* v, const void* out, long long oo_b, long long oo_s, long long oo_h,
 	const float* lse, void* dq, void* dk, void* dv, void* workspace)
 {
-	if (g.D != FB_D || g.Dv != FB_D || g.B <= 0 || g.H <= 0 || g.Hk <= 0 || g.H % g.Hk != 0 || g.Sq <= 0 || g.Sk <= 0 || !encode_init())
+	if (g.D > FB_D || g.D < 8 || (g.D & 7) || g.Dv != g.D || g.B <= 0 || g.H <= 0 || g.Hk <= 0 || g.H % g.Hk != 0 || g.Sq <= 0 || g.Sk <= 0 || !encode_init())
 		return 1;
 	for (const void* ptr : { (const void*)dq, (const void*)dk, (const void*)dv, dout })
 		if (((uintptr_t)ptr) & 15)
@@ -535,11 +538,11 @@ int sdpa_backward_f16(cudaStream_t stream, const SdpaGeom& g, const SdpaGeom& dg
 	if ((((uintptr_t)out) & 15) || (oo_b & 7) || (oo_s & 7) || (oo_h & 7))
 		return 1;
 	const long long rows = (long long)g.B * g.H * sq_r;
-	fmha_bwd_prep_kernel<<<(unsigned)((rows + 15) / 16), 256, 0, stream>>>((const uint16_t*)dout, (const uint16_t*)out, lse, stat, g.B, g.H, g.Sq, sq_r, is_bf16, g.o_b, g.o_s, g.o_h, oo_b, oo_s, oo_h);
+	fmha_bwd_prep_kernel<<<(unsigned)((rows + 15) / 16), 256, 0, stream>>>((const uint16_t*)dout, (const uint16_t*)out, lse, stat, g.B, g.H, g.Sq, sq_r, g.D, is_bf16, g.o_b, g.o_s, g.o_h, oo_b, oo_s, oo_h);
 	count_launch();
 	FmhaBwdParams p;
 	memset(&p, 0, sizeof(p));
-	p.H = g.H, p.Hk = g.Hk, p.Sq = g.Sq, p.Sk = g.Sk, p.Sq_r = sq_r;
+	p.H = g.H, p.Hk = g.Hk, p.Sq = g.Sq, p.Sk = g.Sk, p.Sq_r = sq_r, p.D = g.D;
 	p.causal = g.is_causal, p.is_bf16 = is_bf16;
 	p.scale = g.scale, p.scale_log2 = g.scale * 1.4426950408889634f;
 	p.stat = (const float4*)stat;

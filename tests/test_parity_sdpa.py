@@ -57,6 +57,54 @@ def test_sdpa_with_additive_mask(gpu, ref):
     assert_close(o_g, o_r, 2e-3, "masked attention")
 
 
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,D,causal,with_bias", [(2, 24, 36, 4, 2, 32, 0, 1), (1, 40, 40, 8, 8, 16, 1, 0), (2, 32, 32, 2, 2, 64, 0, 1)])
+def test_sdpa_unify_head_projection_vs_cpu_ref(gpu, ref, B, Sq, Sk, Hq, Hk, D, causal, with_bias):
+    """The fused "unify head" output (…attention_cpu_ref.c:26-27,184-255; test/unit/nnc/attention.tests.c): inputs (q, k, v, mask, w,
+    bias) -> outputs (d = concat_heads(attention) w^T + bias, lse, c = per-head attention).  fp32 against CPU_REF: c to the attention
+    bound, d to the GEMM command's 3xTF32 bound."""
+    nnc = gpu
+    scale = 1.0 / np.sqrt(D)
+    q, k, v = seeded((B, Sq, Hq, D), 1, -1, 1), seeded((B, Sk, Hk, D), 2, -1, 1), seeded((B, Sk, Hk, D), 3, -1, 1)
+    w = seeded((Hq * D, Hq * D), 4, -0.5, 0.5)
+    bias = seeded((Hq * D,), 5, -1, 1) if with_bias else None
+    fwd = _cmd(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD, scale, causal)
+    ins = [q, k, v, None, w, bias]
+    mk = lambda: [np.zeros((B, Sq, Hq * D), np.float32), None, np.zeros((B, Sq, Hq, D), np.float32)]
+    st_r, (d_r, _, c_r) = ref_exec(ref, fwd, None, 0, ins, mk())
+    st_g, (d_g, _, c_g) = gpu_exec(nnc, fwd, None, 0, ins, mk())
+    assert st_r == 0 and st_g == 0
+    assert_close(c_g, c_r, 2e-3, "per-head attention")
+    assert_close(d_g, d_r, 2e-3, "unified output")
+    # a bias without a weight matrix is refused, as the reference asserts (:27-28)
+    if with_bias:
+        st, _ = gpu_exec(nnc, fwd, None, 0, [q, k, v, None, None, bias], [np.zeros((B, Sq, Hq, D), np.float32), None])
+        assert st == abi.CCV_NNC_EXEC_INVALID
+
+
+def test_sdpa_unify_head_projection_bf16(gpu, ref):
+    """The same on bf16 tensors, D = 128 (flash kernel + kind::f16 projection), fp32 bias: CPU_REF on the rounded operands, 1e-2."""
+    nnc = gpu
+    B, S, H, D = 2, 128, 2, 128
+    scale = 1.0 / np.sqrt(D)
+    arrs = [seeded((B, S, H, D), 1, -1, 1), seeded((B, S, H, D), 2, -1, 1), seeded((B, S, H, D), 3, -1, 1), seeded((H * D, H * D), 4, -0.1, 0.1)]
+    bits = [_to_bf16(a) for a in arrs]
+    q, k, v, w = (_from_bf16(b) for b in bits)
+    bias = seeded((H * D,), 5, -1, 1)
+    fwd = _cmd(abi.CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD, scale, 0)
+    st_r, (d_r, _, c_r) = ref_exec(ref, fwd, None, 0, [q, k, v, None, w, bias], [np.zeros((B, S, H * D), np.float32), None, np.zeros((B, S, H, D), np.float32)])
+    assert st_r == 0
+    stream = nnc.Stream(0)
+    tq, tk, tv, tw = (nnc.gpu_tensor(list(b.shape), datatype=abi.CCV_16BF).upload(b) for b in bits)
+    tb = nnc.gpu_tensor([H * D]).upload(bias)
+    td, tc = nnc.gpu_tensor([B, S, H * D], datatype=abi.CCV_16BF), nnc.gpu_tensor([B, S, H, D], datatype=abi.CCV_16BF)
+    assert nnc.cmd_exec(fwd, None, 0, [tq, tk, tv, None, tw, tb], [td, None, tc], stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
+    stream.wait()
+    assert_close(_from_bf16(tc.download()), c_r, 1e-2, "bf16 per-head attention")
+    assert_close(_from_bf16(td.download()), d_r, 1e-2, "bf16 unified output")
+    for t in (tq, tk, tv, tw, tb, td, tc, stream):
+        t.free()
+
+
 # ---- 16-bit flash attention (ccv_b200/csrc/sm100_fmha.cu) --------------------------------------------------------------
 def _to_bf16(a):
     u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
@@ -136,21 +184,22 @@ def test_flash_attention_16bit_forward(gpu, ref, B, Sq, Sk, Hq, Hk, causal, dtyp
 
 
 BWD16 = [
-    # B, Sq, Sk, Hq, Hk, causal, dtype, saved (pass the forward's o / lse as inputs[9], [10])
-    (1, 128, 128, 2, 2, 0, "bf16", 0), (2, 64, 96, 4, 2, 1, "bf16", 0), (1, 256, 256, 2, 2, 1, "bf16", 1), (2, 200, 328, 4, 1, 0, "bf16", 1),
-    (1, 328, 200, 2, 2, 1, "bf16", 0), (1, 96, 160, 8, 2, 1, "f16", 1), (1, 1024, 1024, 2, 1, 0, "bf16", 1), (1, 40, 24, 2, 2, 1, "f16", 0),
+    # B, Sq, Sk, Hq, Hk, causal, dtype, saved (pass the forward's o / lse as inputs[9], [10]), D
+    (1, 128, 128, 2, 2, 0, "bf16", 0, 128), (2, 64, 96, 4, 2, 1, "bf16", 0, 128), (1, 256, 256, 2, 2, 1, "bf16", 1, 128), (2, 200, 328, 4, 1, 0, "bf16", 1, 128),
+    (1, 328, 200, 2, 2, 1, "bf16", 0, 128), (1, 96, 160, 8, 2, 1, "f16", 1, 128), (1, 1024, 1024, 2, 1, 0, "bf16", 1, 128), (1, 40, 24, 2, 2, 1, "f16", 0, 128),
+    # head dimensions below 128 (the reference trials 40 and 64, test/int/nnc/cublas.tests.c:2752-2833): same kernels, zero-filled features
+    (2, 160, 224, 4, 2, 1, "bf16", 1, 64), (1, 136, 136, 2, 2, 0, "bf16", 0, 40), (1, 192, 128, 4, 4, 1, "f16", 1, 96),
 ]
 
 
-@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,causal,dtype,saved", BWD16)
-def test_attention_16bit_backward_fused(gpu, ref, B, Sq, Sk, Hq, Hk, causal, dtype, saved):
-    """bf16 / fp16 SDPA backward, D = 128: the fused deterministic tcgen05 kernels (sm100_fmha_bwd.cu) against CPU_REF's fp32 backward
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,causal,dtype,saved,D", BWD16)
+def test_attention_16bit_backward_fused(gpu, ref, B, Sq, Sk, Hq, Hk, causal, dtype, saved, D):
+    """bf16 / fp16 SDPA backward, D <= 128: the fused deterministic tcgen05 kernels (sm100_fmha_bwd.cu) against CPU_REF's fp32 backward
     (…attention_cpu_ref.c:259-479) on the rounded operands; 1e-2 of max|ref| (P and dS are rounded to 16 bits on the way, like the
     reference's flash-attention backward).  Covers GQA (dk / dv summed over the query heads), causal with Sq != Sk (bottom-right
     aligned, Sq > Sk leaves fully masked rows), ragged tiles, with and without the forward's saved output / log-sum-exp, and that two
     runs are bit-identical."""
     nnc = gpu
-    D = 128
     scale = 1.0 / np.sqrt(D)
     arrs = [seeded((B, Sq, Hq, D), 4, -1, 1), None, None, seeded((B, Sq, Hq, D), 1, -1, 1), seeded((B, Sk, Hk, D), 2, -1, 1), seeded((B, Sk, Hk, D), 3, -1, 1)]
     if dtype == "bf16":
@@ -195,11 +244,12 @@ def test_attention_16bit_backward_fused(gpu, ref, B, Sq, Sk, Hq, Hk, causal, dty
         t.free()
 
 
-@pytest.mark.parametrize("D,masked,causal", [(40, 0, 0), (64, 0, 1), (160, 0, 0), (224, 0, 1), (128, 1, 0)])
+@pytest.mark.parametrize("D,masked,causal", [(40, 0, 0), (64, 0, 1), (96, 0, 0), (160, 0, 0), (224, 0, 1), (128, 1, 0)])
 def test_attention_16bit_forward_other_head_dims_and_masks(gpu, ref, D, masked, causal):
     """Head dimensions the reference trials (40, 64, 160, 224: test/int/nnc/cublas.tests.c:2752-2833) and additive masks on bf16
-    tensors: the tcgen05 flash kernel does not cover them, the command still runs (widen -> fp32 path -> narrow) instead of
-    returning NO_KERNEL.  Against CPU_REF on the bf16-rounded operands, 1e-2 of max|ref|."""
+    tensors.  D <= 128 without a mask runs on the tcgen05 flash kernel (one launch: the tiles stay 128 features wide, the TMA unit
+    zero-fills the rest); D > 128 and masks take the functional form (widen -> fp32 path -> narrow) instead of returning NO_KERNEL.
+    Against CPU_REF on the bf16-rounded operands, 1e-2 of max|ref|."""
     nnc = gpu
     B, S, H = 2, 48, 4
     scale = 1.0 / np.sqrt(D)
@@ -217,8 +267,11 @@ def test_attention_16bit_forward_other_head_dims_and_masks(gpu, ref, D, masked, 
     tq, tk, tv = (nnc.gpu_tensor([B, S, H, D], datatype=abi.CCV_16BF).upload(b) for b in bits)
     to = nnc.gpu_tensor([B, S, H, D], datatype=abi.CCV_16BF)
     tm = nnc.gpu_tensor(list(mask.shape)).upload(mask) if masked else None
+    launches = nnc.lib().ccv_nnc_sm100_launch_count()
     assert nnc.cmd_exec(fwd, None, 0, [tq, tk, tv] + ([tm] if masked else []), [to], stream) == 0, nnc.lib().ccv_nnc_sm100_last_error()
     stream.wait()
+    if D <= 128 and not masked:
+        assert nnc.lib().ccv_nnc_sm100_launch_count() - launches == 1, "the flash kernel covers this head dimension"
     assert_close(_from_bf16(to.download()), o_r, 1e-2, "bf16 attention D=%d" % D)
     for t in (tq, tk, tv, to, stream) + ((tm,) if masked else ()):
         t.free()
