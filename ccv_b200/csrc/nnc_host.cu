@@ -27,6 +27,7 @@ struct ccv_nnc_stream_context_s {
 	size_t cpu_workspace_size;
 	ccv_nnc_stream_context_neighbor_discovery_f neighbor_discovery;
 	void* neighbor_discovery_context;
+	uint64_t rng_state; // the per-context generator of ccv_nnc_stream.c:247-281 (there an sfmt_t): 0 = not seeded yet
 };
 
 namespace {
@@ -403,6 +404,35 @@ ccv_nnc_stream_context_t* ccv_nnc_stream_context_new(const int type)
 		}
 	}
 	return s;
+}
+
+// ccv_nnc_stream.c:247-281: a generator per stream context, seeded lazily from the calling thread's generator; the random-fill
+// commands draw ONE 32-bit seed per launch from it.  (The reference keeps an SFMT state; any well-mixed 64-bit generator serves
+// the contract -- the drop-in build uses the reference's own function, this is the stand-alone host's.)
+static inline uint32_t splitmix_next(uint64_t* const state)
+{
+	uint64_t z = (*state += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return (uint32_t)((z ^ (z >> 31)) >> 16);
+}
+static thread_local uint64_t t_rng_state = 0;
+void ccv_nnc_stream_context_set_seed(ccv_nnc_stream_context_t* const stream_context, uint32_t seed)
+{
+	uint64_t* const st = stream_context ? &stream_context->rng_state : &t_rng_state;
+	*st = ((uint64_t)seed << 1) | 1; // never 0 (0 = unseeded)
+}
+uint32_t ccv_nnc_stream_context_genrand_uint32(ccv_nnc_stream_context_t* const stream_context)
+{
+	if (!stream_context)
+	{
+		if (!t_rng_state)
+			t_rng_state = ((uint64_t)(uintptr_t)&t_rng_state << 1) | 1;
+		return splitmix_next(&t_rng_state);
+	}
+	if (!stream_context->rng_state)
+		stream_context->rng_state = ((uint64_t)ccv_nnc_stream_context_genrand_uint32(0) << 1) | 1;
+	return splitmix_next(&stream_context->rng_state);
 }
 
 int ccv_nnc_stream_context_type(const ccv_nnc_stream_context_t* const stream_context)

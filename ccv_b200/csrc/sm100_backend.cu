@@ -10,6 +10,7 @@
 #include "sm100_ew.h"
 #include <cuda_runtime.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 using namespace sm100;
@@ -116,6 +117,7 @@ inline int kind_of(const ccv_nnc_tensor_t* const t)
 	return -1;
 }
 inline size_t kind_size(const int kind) { return kind == 0 ? 4 : 2; }
+inline uint16_t f32_to_16(const float v, const int kind); // host-side rounding of a fill value (defined with exec_via_f32)
 
 bool same_shape(const TV& a, const TV& b)
 {
@@ -411,6 +413,116 @@ int exec_gemm_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
+// ------------------------------------------------------------------------------------------------ GEMM with two batch axes
+// ccv_nnc_tensor_get_matrix_params (lib/nnc/ccv_nnc_easy.h:421-444) and the reference GEMMs take up to 4-d operands
+// [b0, b1, rows, cols] (attention-style "batch (2, 4)" products, test/int/nnc/cublas.tests.c:1801-2100), any of them possibly a
+// view, an operand with fewer axes being shared by every outer batch.  The 3-d commands above are run once per outer index on
+// sub-views; an output that is shared across the outer axis accumulates from the second index on (in a call of its own, so
+// that per-index outputs are still overwritten).
+struct Slice4 {
+	ccv_nnc_tensor_view_t v;
+	int is4;
+};
+inline void slice4_make(ccv_nnc_tensor_t* const t, Slice4& sl)
+{
+	sl.is4 = t && tensor_nd(t->info.dim) == 4;
+	if (!sl.is4)
+		return;
+	const TV tv = view_of(t);
+	memset(&sl.v, 0, sizeof(sl.v));
+	memcpy(&sl.v, t, sizeof(ccv_nnc_tensor_t));
+	sl.v.type |= CCV_TENSOR_VIEW;
+	memset(sl.v.info.dim, 0, sizeof(sl.v.info.dim));
+	int packed = 1, contiguous = 1;
+	for (int i = 2; i >= 0; i--)
+	{
+		sl.v.info.dim[i] = tv.dim[i + 1], sl.v.stride[i] = tv.stride[i + 1];
+		if (tv.dim[i + 1] != 1 && tv.stride[i + 1] != packed)
+			contiguous = 0;
+		packed *= tv.dim[i + 1];
+	}
+	sl.v.contiguous = contiguous;
+}
+template <ccv_nnc_cmd_exec_f F>
+int exec_gemm_nd4(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	enum { MAXT = 4 };
+	int outer = 0;
+	for (int i = 0; i < input_size; i++)
+		if (inputs[i] && tensor_nd(inputs[i]->info.dim) == 4)
+			outer = std::max(outer, inputs[i]->info.dim[0]);
+	for (int i = 0; i < output_size; i++)
+		if (outputs[i] && tensor_nd(outputs[i]->info.dim) == 4)
+			outer = std::max(outer, outputs[i]->info.dim[0]);
+	if (outer == 0)
+		return F(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	if (input_size > MAXT || output_size > MAXT)
+		return CCV_NNC_EXEC_INVALID;
+	Slice4 si[MAXT], so[MAXT];
+	ccv_nnc_tensor_t* in[MAXT];
+	ccv_nnc_tensor_t* out[MAXT];
+	ccv_nnc_tensor_t* out_shared[MAXT];
+	int any_shared = 0, any_sliced = 0;
+	for (int i = 0; i < input_size; i++)
+	{
+		slice4_make(inputs[i], si[i]);
+		if (si[i].is4 && inputs[i]->info.dim[0] != outer && inputs[i]->info.dim[0] != 1)
+			return CCV_NNC_EXEC_INVALID;
+	}
+	for (int i = 0; i < output_size; i++)
+	{
+		slice4_make(outputs[i], so[i]);
+		if (so[i].is4 && outputs[i]->info.dim[0] != outer && outputs[i]->info.dim[0] != 1)
+			return CCV_NNC_EXEC_INVALID;
+		if (outputs[i])
+		{
+			const int shared = !so[i].is4 || outputs[i]->info.dim[0] == 1;
+			any_shared |= shared, any_sliced |= !shared;
+		}
+	}
+	for (int o = 0; o < outer; o++)
+	{
+		for (int i = 0; i < input_size; i++)
+		{
+			in[i] = inputs[i];
+			if (si[i].is4)
+			{
+				const size_t step = inputs[i]->info.dim[0] == 1 ? 0 : (size_t)o * view_of(inputs[i]).stride[0];
+				si[i].v.data.u8 = inputs[i]->data.u8 + step * dtype_size(inputs[i]->info.datatype);
+				in[i] = (ccv_nnc_tensor_t*)&si[i].v;
+			}
+		}
+		for (int i = 0; i < output_size; i++)
+		{
+			out[i] = outputs[i], out_shared[i] = 0;
+			if (!outputs[i])
+				continue;
+			const int shared = !so[i].is4 || outputs[i]->info.dim[0] == 1;
+			if (so[i].is4)
+			{
+				const size_t step = outputs[i]->info.dim[0] == 1 ? 0 : (size_t)o * view_of(outputs[i]).stride[0];
+				so[i].v.data.u8 = outputs[i]->data.u8 + step * dtype_size(outputs[i]->info.datatype);
+				out[i] = (ccv_nnc_tensor_t*)&so[i].v;
+			}
+			if (shared && o > 0 && any_sliced)
+				out_shared[i] = out[i], out[i] = 0; // second call, accumulating
+		}
+		if (o == 0 || any_sliced)
+		{
+			const int rc = F(cmd, hint, (o > 0 && !any_sliced) ? (flags | CCV_NNC_ACCUMULATE_OUTPUT) : flags, in, input_size, out, output_size, stream_context);
+			if (rc != CCV_NNC_EXEC_SUCCESS)
+				return rc;
+		}
+		if (o > 0 && any_shared)
+		{
+			const int rc = F(cmd, hint, flags | CCV_NNC_ACCUMULATE_OUTPUT, in, input_size, any_sliced ? out_shared : out, output_size, stream_context);
+			if (rc != CCV_NNC_EXEC_SUCCESS)
+				return rc;
+		}
+	}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
 // ================================================================================================ CONVOLUTION
 // NHWC activations ([N,] H, W, C), filters [K, R, S, C / groups] (convolution/ccv_nnc_conv_cpu_ref.c:47-65)
 bool conv_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, const TV& a, const TV& w, const TV& b, ConvGeom& g)
@@ -450,7 +562,7 @@ bool conv_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, const TV& a
 	return true;
 }
 
-int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+int conv_forw_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1] || !outputs[0])
 		return CCV_NNC_EXEC_INVALID;
@@ -487,59 +599,11 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	const float* w = inputs[1]->data.f32;
 	const float* bias = bias_t ? bias_t->data.f32 : 0;
 	float* b = outputs[0]->data.f32;
-	float* nchw_out = 0; // NCHW call: the NHWC result is staged here and transposed back at the end
-	Scratch nchw_scratch = { 0, 0 };
-	TV ta = view_of(inputs[0]), tw = view_of(inputs[1]), tb = view_of(outputs[0]);
-	if (ta.format == CCV_TENSOR_FORMAT_NCHW && tb.format == CCV_TENSOR_FORMAT_NCHW)
-	{
-		// NCHW activations [N, C, H, W] and filters [K, C / g, kh, kw] (convolution/ccv_nnc_conv_cpu_ref.c:66-120): the kernels are
-		// NHWC, so x and w are re-laid out into the stream workspace (two strided copies), the convolution runs there and the
-		// result is transposed back.  Forward only, like CPU_REF (its backward is NHWC-only, :358).
-		if (ta.nd != 4 || tb.nd != 4 || tw.nd != 4 || !ta.contiguous || !tb.contiguous || !tw.contiguous)
-			return CCV_NNC_EXEC_INVALID;
-		const int N = ta.dim[0], C = ta.dim[1], H = ta.dim[2], W = ta.dim[3], K = tb.dim[1], P = tb.dim[2], Q = tb.dim[3], Cg = tw.dim[1], R = tw.dim[2], S = tw.dim[3];
-		if (tb.dim[0] != N || tw.dim[0] != K)
-			return CCV_NNC_EXEC_INVALID;
-		const size_t nx = ta.count, nw = tw.count, ny = tb.count;
-		float* const ws = (float*)ccv_nnc_stream_context_get_workspace(stream_context, (nx + nw + ny) * sizeof(float) + 1024 + CONTRACT_SCRATCH_BYTES, CCV_TENSOR_GPU_MEMORY);
-		if (!ws)
-			return CCV_NNC_EXEC_OOM;
-		float* const xh = ws;
-		float* const wh = (float*)(((uintptr_t)(xh + nx) + 255) & ~(uintptr_t)255);
-		float* const yh = (float*)(((uintptr_t)(wh + nw) + 255) & ~(uintptr_t)255);
-		nchw_scratch = scratch_at((void*)(((uintptr_t)(yh + ny) + 255) & ~(uintptr_t)255), CONTRACT_SCRATCH_BYTES);
-		const int xd[4] = { N, H, W, C }, xs[4] = { C * H * W, W, 1, H * W }, xt[4] = { H * W * C, W * C, C, 1 };
-		const int wd[4] = { K, R, S, Cg }, wsrc[4] = { Cg * R * S, S, 1, R * S }, wdst[4] = { R * S * Cg, S * Cg, Cg, 1 };
-		RC(copy_strided(s, a, xs, xh, xt, xd, 4));
-		RC(copy_strided(s, w, wsrc, wh, wdst, wd, 4));
-		memset(&ta, 0, sizeof(ta)), memset(&tw, 0, sizeof(tw)), memset(&tb, 0, sizeof(tb));
-		ta.nd = tw.nd = tb.nd = 4, ta.format = tw.format = tb.format = CCV_TENSOR_FORMAT_NHWC, ta.contiguous = tw.contiguous = tb.contiguous = 1;
-		const int yd[4] = { N, P, Q, K };
-		for (int i = 3, px = 1, pw = 1, py = 1; i >= 0; i--)
-		{
-			ta.dim[i] = xd[i], ta.stride[i] = px, px *= xd[i];
-			tw.dim[i] = wd[i], tw.stride[i] = pw, pw *= wd[i];
-			tb.dim[i] = yd[i], tb.stride[i] = py, py *= yd[i];
-		}
-		ta.count = nx, tw.count = nw, tb.count = ny;
-		a = xh, w = wh, b = yh, nchw_out = outputs[0]->data.f32;
-	}
+	const TV ta = view_of(inputs[0]), tw = view_of(inputs[1]), tb = view_of(outputs[0]);
 	if (!conv_geom(cmd, hint, ta, tw, tb, g))
 		return CCV_NNC_EXEC_INVALID;
 	if (bias_t && bias_t->info.dim[0] != g.K)
 		return CCV_NNC_EXEC_INVALID;
-	if (nchw_out)
-	{
-		// the staged convolution, then [N, P, Q, K] -> [N, K, P, Q]
-		int rc = groups == 1 && algo != CCV_NNC_SM100_ALGO_FFMA ? conv_fprop_tf32(s, g, a, w, bias, b, nchw_scratch, x3) : 1;
-		if (rc < 0)
-			return CCV_NNC_EXEC_INVALID;
-		if (rc > 0)
-			RC(conv_fprop_ffma(s, g, groups, a, w, bias, b));
-		const int yd[4] = { g.N, g.K, g.P, g.Q }, ysrc[4] = { g.P * g.Q * g.K, 1, g.Q * g.K, g.K }, ydst[4] = { g.K * g.P * g.Q, g.P * g.Q, g.Q, 1 };
-		RC(copy_strided(s, b, ysrc, nchw_out, ydst, yd, 4));
-		return CCV_NNC_EXEC_SUCCESS;
-	}
 	if (groups == 1 && algo != CCV_NNC_SM100_ALGO_FFMA)
 	{
 		int rc = conv_fprop_tf32(s, g, a, w, bias, b, scratch_of(stream_context), x3);
@@ -561,7 +625,7 @@ int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 
 // convolution/ccv_nnc_conv_cpu_ref.c:174-345: inputs (g, a, w), outputs (h, dw, dbias); dw / dbias honour
 // CCV_NNC_ACCUMULATE_OUTPUT, h is always overwritten (:286)
-int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+int conv_back_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1])
 		return CCV_NNC_EXEC_INVALID;
@@ -662,6 +726,176 @@ int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	}
 	return CCV_NNC_EXEC_SUCCESS;
 }
+
+// ------------------------------------------------------------------------------------------------ NCHW / mixed formats
+// The kernels are NHWC.  The reference's GPU convolution takes any mix of formats -- its tests run NHWC activations against NCHW
+// filters and all-NCHW forward and backward (convolution/gpu/ccv_nnc_conv_gpu_cudnn.cu:204-357; test/int/nnc/cudnn.tests.c:24-85,
+// 87-140, 417-497) -- so every NCHW operand is re-laid out into the stream workspace (one strided copy each way), the NHWC
+// command runs on shadow tensors, and NCHW results are copied back.  The workspace is one grow-only buffer per stream: this
+// layer asks for [inner | staging] in ONE request, `inner` being the most the NHWC command will ask for, so that the nested
+// requests (smaller) return the same base and never move the staged tensors.
+struct Staged {
+	ccv_nnc_tensor_t shadow;
+	ccv_nnc_tensor_t* orig;
+	int d[4], src[4], dst[4]; // index space N, H, W, C with the NCHW and the NHWC strides
+	size_t bytes;
+	int elem;
+};
+
+inline bool is_nchw(const ccv_nnc_tensor_t* const t) { return t && t->info.format == CCV_TENSOR_FORMAT_NCHW && tensor_nd(t->info.dim) >= 3; }
+
+bool stage_plan(ccv_nnc_tensor_t* const t, Staged& st)
+{
+	const TV v = view_of(t);
+	const size_t elem = dtype_size(t->info.datatype);
+	if (!v.contiguous || (v.nd != 3 && v.nd != 4) || elem == 0)
+		return false;
+	const int N = v.nd == 4 ? v.dim[0] : 1, C = v.dim[v.nd - 3], H = v.dim[v.nd - 2], W = v.dim[v.nd - 1];
+	const int d[4] = { N, H, W, C }, src[4] = { C * H * W, W, 1, H * W }, dst[4] = { H * W * C, W * C, C, 1 };
+	memcpy(st.d, d, sizeof(d)), memcpy(st.src, src, sizeof(src)), memcpy(st.dst, dst, sizeof(dst));
+	st.orig = t;
+	st.elem = (int)elem;
+	st.bytes = (v.count * elem + 255) & ~(size_t)255;
+	memcpy(&st.shadow, t, sizeof(ccv_nnc_tensor_t));
+	st.shadow.type &= ~CCV_TENSOR_VIEW;
+	st.shadow.info.format = CCV_TENSOR_FORMAT_NHWC;
+	memset(st.shadow.info.dim, 0, sizeof(st.shadow.info.dim));
+	if (v.nd == 4)
+		st.shadow.info.dim[0] = N, st.shadow.info.dim[1] = H, st.shadow.info.dim[2] = W, st.shadow.info.dim[3] = C;
+	else
+		st.shadow.info.dim[0] = H, st.shadow.info.dim[1] = W, st.shadow.info.dim[2] = C;
+	return true;
+}
+
+// upper bound of what the NHWC command requests from the workspace for this geometry
+size_t conv_inner_workspace(const ConvGeom& g, const int kind)
+{
+	size_t need = CONTRACT_SCRATCH_BYTES;
+	if (g.C % (kind == 0 ? 4 : 8) != 0)
+		need = std::max(need, kind == 0 ? conv_im2col_workspace_bytes(g) : conv_im2col_workspace_bytes(g, kind));
+	need = std::max(need, colsum_workspace_bytes(g.K));
+	return (need + 255) & ~(size_t)255;
+}
+
+// `exec` = the NHWC command, `inner_of` = the most it requests from the workspace given the shadow tensor lists; `accumulating`
+// = outputs[1..] may be read before they are written (CCV_NNC_ACCUMULATE_OUTPUT), so they are staged in as well
+typedef size_t (*staged_inner_f)(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, ccv_nnc_tensor_t* const* in, int input_size, ccv_nnc_tensor_t* const* out, int output_size);
+int nchw_staged(const ccv_nnc_cmd_exec_f exec, const staged_inner_f inner_of, const int accumulating, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	enum { MAXT = 6 };
+	if (input_size > 3 || output_size > 3)
+		return CCV_NNC_EXEC_INVALID;
+	Staged st[MAXT];
+	ccv_nnc_tensor_t* in[3] = { 0, 0, 0 };
+	ccv_nnc_tensor_t* out[3] = { 0, 0, 0 };
+	int n = 0, slot_in[3] = { -1, -1, -1 }, slot_out[3] = { -1, -1, -1 };
+	size_t staging = 0;
+	for (int i = 0; i < input_size; i++)
+	{
+		in[i] = inputs[i];
+		if (is_nchw(inputs[i]))
+		{
+			if (!stage_plan(inputs[i], st[n]))
+				return CCV_NNC_EXEC_INVALID;
+			staging += st[n].bytes, slot_in[i] = n++;
+		}
+	}
+	for (int i = 0; i < output_size; i++)
+	{
+		out[i] = outputs[i];
+		if (is_nchw(outputs[i]))
+		{
+			if (!stage_plan(outputs[i], st[n]))
+				return CCV_NNC_EXEC_INVALID;
+			staging += st[n].bytes, slot_out[i] = n++;
+		}
+	}
+	for (int i = 0; i < 3; i++)
+	{
+		if (slot_in[i] >= 0)
+			in[i] = &st[slot_in[i]].shadow;
+		if (slot_out[i] >= 0)
+			out[i] = &st[slot_out[i]].shadow;
+	}
+	const size_t inner = inner_of(cmd, hint, in, input_size, out, output_size);
+	if (inner == (size_t)-1)
+		return CCV_NNC_EXEC_INVALID;
+	unsigned char* const ws = (unsigned char*)ccv_nnc_stream_context_get_workspace(stream_context, inner + staging, CCV_TENSOR_GPU_MEMORY);
+	if (!ws)
+		return CCV_NNC_EXEC_OOM;
+	cudaStream_t s = stream_of(stream_context);
+	unsigned char* p = ws + inner;
+	for (int i = 0; i < n; i++)
+		st[i].shadow.data.u8 = p, p += st[i].bytes;
+	// operands in; outputs that accumulate come in too
+	for (int i = 0; i < 3; i++)
+		if (slot_in[i] >= 0)
+		{
+			const Staged& t = st[slot_in[i]];
+			RC(copy_strided(s, t.orig->data.u8, t.src, t.shadow.data.u8, t.dst, t.d, t.elem));
+		}
+	if (accumulating && (flags & CCV_NNC_ACCUMULATE_OUTPUT))
+		for (int i = 1; i < 3; i++)
+			if (slot_out[i] >= 0)
+			{
+				const Staged& t = st[slot_out[i]];
+				RC(copy_strided(s, t.orig->data.u8, t.src, t.shadow.data.u8, t.dst, t.d, t.elem));
+			}
+	const int rc = exec(cmd, hint, flags, in, input_size, out, output_size, stream_context);
+	if (rc != CCV_NNC_EXEC_SUCCESS)
+		return rc;
+	for (int i = 0; i < 3; i++)
+		if (slot_out[i] >= 0)
+		{
+			const Staged& t = st[slot_out[i]];
+			RC(copy_strided(s, t.shadow.data.u8, t.dst, t.orig->data.u8, t.src, t.d, t.elem));
+		}
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+template <int BACKWARD>
+size_t conv_staged_inner(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, ccv_nnc_tensor_t* const* const in, const int input_size, ccv_nnc_tensor_t* const* const out, const int output_size)
+{
+	// geometry on the shadows: activations, filter, output of the forward convolution
+	ccv_nnc_tensor_t* const act = BACKWARD ? in[1] : in[0];
+	ccv_nnc_tensor_t* const filt = BACKWARD ? (output_size > 1 && out[1] ? out[1] : (input_size > 2 ? in[2] : 0)) : in[1];
+	ccv_nnc_tensor_t* const res = BACKWARD ? in[0] : out[0];
+	ConvGeom g;
+	if (!act || !filt || !res || kind_of(act) < 0 || !conv_geom(cmd, hint, view_of(act), view_of(filt), view_of(res), g))
+		return (size_t)-1;
+	return conv_inner_workspace(g, kind_of(act));
+}
+template <int BACKWARD>
+int conv_staged(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return nchw_staged(BACKWARD ? conv_back_nhwc : conv_forw_nhwc, conv_staged_inner<BACKWARD>, BACKWARD, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
+inline bool any_nchw(ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size)
+{
+	for (int i = 0; i < input_size; i++)
+		if (is_nchw(inputs[i]))
+			return true;
+	for (int i = 0; i < output_size; i++)
+		if (is_nchw(outputs[i]))
+			return true;
+	return false;
+}
+
+int exec_conv_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (any_nchw(inputs, input_size, outputs, output_size))
+		return conv_staged<0>(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	return conv_forw_nhwc(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
+int exec_conv_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (any_nchw(inputs, input_size, outputs, output_size))
+		return conv_staged<1>(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	return conv_back_nhwc(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
 
 // ================================================================================================ BATCH NORM
 // norm/ccv_nnc_batch_norm_cpu_ref.c:16-250.  Supported reduction shapes: per-channel statistics of an NHWC
@@ -852,6 +1086,22 @@ int exec_relu_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 // ew/ccv_nnc_ew_cpu_ref.c:15-110,207-214
 int exec_ewsum_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
+	if (input_size >= 1 && output_size >= 1 && outputs[0] && CCV_GET_DATA_TYPE(outputs[0]->info.datatype) == CCV_32S)
+	{
+		// int32 tensors (ew/gpu/ccv_nnc_ew_gpu_cudnn.cu registers CCV_32S; test/int/nnc/cudnn.tests.c:4817-4850)
+		const TV ci = view_of(outputs[0]);
+		const int* iptrs[64];
+		if (!ci.contiguous || input_size > 64)
+			return CCV_NNC_EXEC_INVALID;
+		for (int i = 0; i < input_size; i++)
+		{
+			if (!inputs[i] || CCV_GET_DATA_TYPE(inputs[i]->info.datatype) != CCV_32S || !view_of(inputs[i]).contiguous || view_of(inputs[i]).count != ci.count)
+				return CCV_NNC_EXEC_INVALID;
+			iptrs[i] = inputs[i]->data.i32;
+		}
+		RC(ew_sum_i32(stream_of(stream_context), iptrs, input_size, outputs[0]->data.i32, ci.count));
+		return CCV_NNC_EXEC_SUCCESS;
+	}
 	if (input_size < 1 || output_size < 1 || !outputs[0] || kind_of(outputs[0]) < 0)
 		return CCV_NNC_EXEC_INVALID;
 	const TV c = view_of(outputs[0]);
@@ -1031,7 +1281,9 @@ int exec_mul_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int 
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
-// d(p a b)/da = p g b, d/db = p g a; only the same-shape (no broadcast) gradient is provided here
+// blas/ccv_nnc_mul_cpu_ref.c:192-330: d(p a b)/da = p g b, d/db = p g a, each summed over the axes along which that operand was
+// broadcast (g == NULL reads as ones).  Same shapes: one fused pass; otherwise the product is formed over the full index space in
+// the stream workspace and reduced onto the operand's shape in a fixed order.
 int exec_mul_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (input_size < 3)
@@ -1043,21 +1295,56 @@ int exec_mul_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int 
 		if (!outputs[i])
 			continue;
 		const ccv_nnc_tensor_t* const other = inputs[2 - i]; // ha needs b (inputs[2]), hb needs a (inputs[1])
-		if (!other)
+		if (!other || !is_f32(other) || !is_f32(outputs[i]) || (inputs[0] && !is_f32(inputs[0])))
 			return CCV_NNC_EXEC_INVALID;
 		const TV o = view_of(outputs[i]), x = view_of(other);
-		if (!o.contiguous || !x.contiguous || !same_shape(o, x))
+		if (!o.contiguous || o.nd > 4 || x.nd > 4)
 			return CCV_NNC_EXEC_INVALID;
-		if (!inputs[0])
-			RC(ew_axpby_f32(s, p, other->data.f32, 0.f, 0, outputs[i]->data.f32, o.count));
-		else {
-			const TV g = view_of(inputs[0]);
-			if (!g.contiguous || !same_shape(g, o))
-				return CCV_NNC_EXEC_INVALID;
-			int d[4], st[4];
-			dims4(o, d, st);
-			RC(ew_mul_bcast_f32(s, p, inputs[0]->data.f32, st, other->data.f32, st, outputs[i]->data.f32, st, d));
+		if (x.contiguous && same_shape(o, x) && (!inputs[0] || (view_of(inputs[0]).contiguous && same_shape(view_of(inputs[0]), o))))
+		{
+			if (!inputs[0])
+				RC(ew_axpby_f32(s, p, other->data.f32, 0.f, 0, outputs[i]->data.f32, o.count));
+			else {
+				int d[4], st[4];
+				dims4(o, d, st);
+				RC(ew_mul_bcast_f32(s, p, inputs[0]->data.f32, st, other->data.f32, st, outputs[i]->data.f32, st, d));
+			}
+			continue;
 		}
+		// the full index space: the gradient's shape, or (no gradient) the broadcast of the two operands
+		int fd[4], od[4], os[4], xd[4], xs[4], gd[4] = { 1, 1, 1, 1 }, gs[4] = { 0, 0, 0, 0 };
+		dims4(o, od, os);
+		dims4(x, xd, xs);
+		if (inputs[0])
+		{
+			const TV g = view_of(inputs[0]);
+			if (g.nd > 4)
+				return CCV_NNC_EXEC_INVALID;
+			dims4(g, gd, gs);
+		}
+		size_t fcount = 1;
+		for (int k = 0; k < 4; k++)
+		{
+			fd[k] = std::max(std::max(od[k], xd[k]), gd[k]);
+			if ((od[k] != fd[k] && od[k] != 1) || (xd[k] != fd[k] && xd[k] != 1) || (gd[k] != fd[k] && gd[k] != 1))
+				return CCV_NNC_EXEC_INVALID;
+			if (xd[k] == 1)
+				xs[k] = 0;
+			if (gd[k] == 1)
+				gs[k] = 0;
+			fcount *= (size_t)fd[k];
+		}
+		float* const t = (float*)ccv_nnc_stream_context_get_workspace(stream_context, fcount * sizeof(float), CCV_TENSOR_GPU_MEMORY);
+		if (!t)
+			return CCV_NNC_EXEC_OOM;
+		int fs[4];
+		for (int k = 3, packed = 1; k >= 0; k--)
+			fs[k] = packed, packed *= fd[k];
+		if (inputs[0])
+			RC(ew_mul_bcast_f32(s, p, inputs[0]->data.f32, gs, other->data.f32, xs, t, fs, fd));
+		else
+			RC(ew_axpby_bcast_f32(s, p, other->data.f32, xs, 0.f, 0, 0, t, fs, fd));
+		RC(reduce_sum_bcast_f32(s, t, fd, fs, outputs[i]->data.f32, od, 1.f, 0));
 	}
 	return CCV_NNC_EXEC_SUCCESS;
 }
@@ -1368,7 +1655,13 @@ int exec_set_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int 
 			float fv;
 			memcpy(&fv, &iv, 4);
 			RC(ew_set_f32(s, outputs[i]->data.f32, o.count, fv));
-		} else
+		} else if (dt == CCV_64F) {
+			// a double is two 32-bit words: fill the word pairs (o.count * 2 words, even / odd word pattern)
+			const double dv = (double)v;
+			RC(ew_set_u64(s, (uint64_t*)outputs[i]->data.u8, o.count, *(const uint64_t*)&dv));
+		} else if (dt == CCV_16F || dt == CCV_16BF)
+			RC(ew_set_u16(s, (uint16_t*)outputs[i]->data.u8, o.count, f32_to_16(v, dt == CCV_16BF ? 1 : 2)));
+		else
 			return CCV_NNC_EXEC_INVALID;
 	}
 	return CCV_NNC_EXEC_SUCCESS;
@@ -1410,6 +1703,11 @@ int exec_data_transfer(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const
 	for (int i = 0; i < n; i++)
 		if (inputs[i] && outputs[i] && inputs[i] != outputs[i])
 			RC(copy_tensor(s, inputs[i], outputs[i]));
+	// Without a stream context the reference's transfer is the BLOCKING cudaMemcpy (util/gpu/ccv_nnc_util_gpu_ref.cu:44-60): the
+	// caller reads a pinned host tensor right after the call (test/int/nnc/schedule.tests.c:56-59).  The copies above were enqueued
+	// on the default stream; wait for them.
+	if (!stream_context && cudaStreamSynchronize(s) != cudaSuccess)
+		return CCV_NNC_EXEC_INVALID;
 	return CCV_NNC_EXEC_SUCCESS;
 }
 
@@ -1510,6 +1808,122 @@ int exec_datatype_conversion(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint,
 		RC(convert_dtype(s, a.p, dtype_code(a.datatype), b.p, dtype_code(b.datatype), a.count));
 	}
 	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// ================================================================================================ 16-bit tensors on fp32-only commands
+// The commands below have fp32 kernels only; the reference's GPU backends register them for CCV_16F as well (e.g.
+// softmax/gpu/ccv_nnc_softmax_gpu_cudnn.cu, blas/gpu/ccv_nnc_add_gpu_cudnn.cu) and its half-precision tests run them
+// (test/int/nnc/cudnn.tests.c:3504-3678, 4151-4323, 4363-4735).  For bf16 / fp16 tensors the command runs in its functional form:
+// every 16-bit operand is widened into the stream workspace, the fp32 command runs on shadow tensors, every 16-bit result is
+// rounded once (to nearest even) on the way back.  One workspace request [inner | staging], as in conv_staged.
+inline uint16_t f32_to_16(const float v, const int kind)
+{
+	uint32_t u;
+	memcpy(&u, &v, 4);
+	if (kind == 1)
+		return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16); // bf16, round to nearest even
+	// fp16, round to nearest even (finite range; the fill values this is used for are small)
+	const uint32_t sign = (u >> 16) & 0x8000u;
+	const int32_t e = (int32_t)((u >> 23) & 0xff) - 127 + 15;
+	uint32_t m = u & 0x7fffffu;
+	if (e >= 31)
+		return (uint16_t)(sign | 0x7c00u);
+	if (e <= 0)
+	{
+		if (e < -10)
+			return (uint16_t)sign;
+		m |= 0x800000u;
+		const int shift = 14 - e;
+		const uint32_t r = m >> shift, rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+		return (uint16_t)(sign | (r + (rem > half || (rem == half && (r & 1)))));
+	}
+	const uint32_t r = (uint32_t)(e << 10) | (m >> 13), rem = m & 0x1fffu;
+	return (uint16_t)(sign | (r + (rem > 0x1000u || (rem == 0x1000u && (r & 1)))));
+}
+
+template <ccv_nnc_cmd_exec_f F32>
+int exec_via_f32(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	enum { MAXT = 16 };
+	bool any16 = false;
+	for (int i = 0; i < input_size; i++)
+		any16 = any16 || (inputs[i] && kind_of(inputs[i]) > 0);
+	for (int i = 0; i < output_size; i++)
+		any16 = any16 || (outputs[i] && kind_of(outputs[i]) > 0);
+	if (!any16)
+		return F32(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	if (input_size > MAXT || output_size > MAXT)
+		return CCV_NNC_EXEC_INVALID;
+	struct Shadow { ccv_nnc_tensor_t t; ccv_nnc_tensor_t* orig; size_t n; int kind; int is_out; } sh[2 * MAXT];
+	ccv_nnc_tensor_t* in[MAXT];
+	ccv_nnc_tensor_t* out[MAXT];
+	int n = 0;
+	size_t staging = 0;
+	const auto shadow_of = [&](ccv_nnc_tensor_t* const t, const int is_out) -> ccv_nnc_tensor_t* {
+		if (!t || kind_of(t) <= 0)
+			return t;
+		for (int j = 0; j < n; j++)
+			if (sh[j].orig == t || sh[j].orig->data.u8 == t->data.u8)
+			{
+				sh[j].is_out |= is_out;
+				return &sh[j].t;
+			}
+		const TV v = view_of(t);
+		if (!v.contiguous || v.count > 0x7fffffffull)
+			return 0;
+		Shadow& x = sh[n++];
+		memcpy(&x.t, t, sizeof(ccv_nnc_tensor_t));
+		x.t.type &= ~CCV_TENSOR_VIEW;
+		x.t.info.datatype = CCV_32F;
+		x.orig = t, x.n = v.count, x.kind = kind_of(t), x.is_out = is_out;
+		staging += (v.count * sizeof(float) + 255) & ~(size_t)255;
+		return &x.t;
+	};
+	for (int i = 0; i < input_size; i++)
+		if (!(in[i] = shadow_of(inputs[i], 0)) && inputs[i])
+			return CCV_NNC_EXEC_INVALID;
+	for (int i = 0; i < output_size; i++)
+		if (!(out[i] = shadow_of(outputs[i], 1)) && outputs[i])
+			return CCV_NNC_EXEC_INVALID;
+	const size_t inner = (size_t)4 << 20; // the fp32 forms of these commands ask for at most a few partial rows
+	unsigned char* const ws = (unsigned char*)ccv_nnc_stream_context_get_workspace(stream_context, inner + staging, CCV_TENSOR_GPU_MEMORY);
+	if (!ws)
+		return CCV_NNC_EXEC_OOM;
+	cudaStream_t s = stream_of(stream_context);
+	unsigned char* p = ws + inner;
+	for (int j = 0; j < n; j++)
+	{
+		sh[j].t.data.u8 = p, p += (sh[j].n * sizeof(float) + 255) & ~(size_t)255;
+		// every shadow is filled: inputs carry data, and an output may be read by the command (in-place forms)
+		RC(widen_matrix(s, sh[j].orig->data.u8, sh[j].kind, (long long)sh[j].n, 1, sh[j].t.data.f32, 1, (int)sh[j].n));
+	}
+	const int rc = F32(cmd, hint, flags, in, input_size, out, output_size, stream_context);
+	if (rc != CCV_NNC_EXEC_SUCCESS)
+		return rc;
+	for (int j = 0; j < n; j++)
+		if (sh[j].is_out)
+			RC(narrow_matrix(s, sh[j].t.data.f32, sh[j].orig->data.u8, sh[j].kind, (long long)sh[j].n, 1, 1, (int)sh[j].n, 0));
+	return CCV_NNC_EXEC_SUCCESS;
+}
+
+// SGD: fp32 parameters / momenta with gradients of any type run natively (the mixed-precision form); 16-bit PARAMETERS
+// (sgd/gpu/ccv_nnc_sgd_gpu_ref.cu:75-77, test/int/nnc/sgd.tests.c:73-137) go through the functional form
+int exec_sgd_any(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size >= 2 && inputs[1] && kind_of(inputs[1]) > 0)
+		return exec_via_f32<exec_sgd_forw>(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	return exec_sgd_forw(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+
+// pooling on NCHW tensors ([N,] C, H, W: pool/gpu/ccv_nnc_max_pool_gpu_cudnn.cu takes both formats; test/int/nnc/cudnn.tests.c:2772-2870):
+// the kernels are NHWC (channel-contiguous 16-byte accesses), NCHW operands are staged like the convolution's
+size_t pool_staged_inner(const ccv_nnc_cmd_t&, const ccv_nnc_hint_t&, ccv_nnc_tensor_t* const*, int, ccv_nnc_tensor_t* const*, int) { return 256; }
+template <ccv_nnc_cmd_exec_f F>
+int exec_pool_any(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (any_nchw(inputs, input_size, outputs, output_size))
+		return nchw_staged(F, pool_staged_inner, 0, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	return F(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 
 void fill(ccv_nnc_cmd_backend_registry_t* const registry, const int formats, const int datatypes, const int algorithms, const ccv_nnc_cmd_exec_f exec)
@@ -1680,14 +2094,14 @@ extern "C" int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_
 // ================================================================================================ registration
 #define REGISTER_SM100(cmd) extern "C" void _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(ccv_nnc_cmd_backend_registry_t* const registry)
 
-REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_forw); registry->autotune = autotune_contraction<exec_gemm_forw>; }
-REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_back); registry->autotune = autotune_contraction<exec_gemm_back>; }
+REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_nd4<exec_gemm_forw>); registry->autotune = autotune_contraction<exec_gemm_nd4<exec_gemm_forw> >; }
+REGISTER_SM100(CCV_NNC_GEMM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_nd4<exec_gemm_back>); registry->autotune = autotune_contraction<exec_gemm_nd4<exec_gemm_back> >; }
 REGISTER_SM100(CCV_NNC_CONVOLUTION_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_conv_forw); registry->autotune = autotune_contraction<exec_conv_forw>; }
-REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); registry->autotune = autotune_contraction<exec_conv_back>; }
+REGISTER_SM100(CCV_NNC_CONVOLUTION_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_conv_back); registry->autotune = autotune_contraction<exec_conv_back>; }
 REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_forw); }
 REGISTER_SM100(CCV_NNC_SCALED_DOT_PRODUCT_ATTENTION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_sdpa_back); }
-REGISTER_SM100(CCV_NNC_SOFTMAX_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_forw); }
-REGISTER_SM100(CCV_NNC_SOFTMAX_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_softmax_back); }
+REGISTER_SM100(CCV_NNC_SOFTMAX_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<exec_softmax_forw>); }
+REGISTER_SM100(CCV_NNC_SOFTMAX_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<exec_softmax_back>); }
 REGISTER_SM100(CCV_NNC_BATCH_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_bnorm_forw); }
 REGISTER_SM100(CCV_NNC_BATCH_NORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_bnorm_back); }
 REGISTER_SM100(CCV_NNC_LAYER_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_lnorm_forw); }
@@ -1696,20 +2110,20 @@ REGISTER_SM100(CCV_NNC_GROUP_NORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F
 REGISTER_SM100(CCV_NNC_GROUP_NORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_gnorm_back); }
 REGISTER_SM100(CCV_NNC_RMSNORM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_rmsnorm_forw); }
 REGISTER_SM100(CCV_NNC_RMSNORM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, ccv_nnc_sm100_exec_rmsnorm_back); }
-REGISTER_SM100(CCV_NNC_EWSUM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_ewsum_forw); }
+REGISTER_SM100(CCV_NNC_EWSUM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_ewsum_forw); }
 REGISTER_SM100(CCV_NNC_EWSUM_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_ewsum_back); }
-REGISTER_SM100(CCV_NNC_ADD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_add_forw); }
-REGISTER_SM100(CCV_NNC_ADD_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_add_back); }
-REGISTER_SM100(CCV_NNC_MUL_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_mul_forw); }
-REGISTER_SM100(CCV_NNC_MUL_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_mul_back); }
-REGISTER_SM100(CCV_NNC_SCALAR_MUL_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_scalar_mul_forw); }
-REGISTER_SM100(CCV_NNC_SCALAR_MUL_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_scalar_mul_back); }
+REGISTER_SM100(CCV_NNC_ADD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<exec_add_forw>); }
+REGISTER_SM100(CCV_NNC_ADD_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<exec_add_back>); }
+REGISTER_SM100(CCV_NNC_MUL_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<exec_mul_forw>); }
+REGISTER_SM100(CCV_NNC_MUL_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<exec_mul_back>); }
+REGISTER_SM100(CCV_NNC_SCALAR_MUL_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<exec_scalar_mul_forw>); }
+REGISTER_SM100(CCV_NNC_SCALAR_MUL_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<exec_scalar_mul_back>); }
 REGISTER_SM100(CCV_NNC_RELU_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_relu_forw); }
 REGISTER_SM100(CCV_NNC_RELU_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_relu_back); }
-REGISTER_SM100(CCV_NNC_MAX_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_forw<1>); }
-REGISTER_SM100(CCV_NNC_MAX_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_back<1>); }
-REGISTER_SM100(CCV_NNC_AVERAGE_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_forw<0>); }
-REGISTER_SM100(CCV_NNC_AVERAGE_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_back<0>); }
+REGISTER_SM100(CCV_NNC_MAX_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_any<exec_pool_forw<1> >); }
+REGISTER_SM100(CCV_NNC_MAX_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_any<exec_pool_back<1> >); }
+REGISTER_SM100(CCV_NNC_AVERAGE_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_any<exec_pool_forw<0> >); }
+REGISTER_SM100(CCV_NNC_AVERAGE_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_any<exec_pool_back<0> >); }
 REGISTER_SM100(CCV_NNC_UPSAMPLE_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, 1, ccv_nnc_sm100_exec_upsample_forw); }
 REGISTER_SM100(CCV_NNC_UPSAMPLE_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, 1, ccv_nnc_sm100_exec_upsample_back); }
 REGISTER_SM100(CCV_NNC_SET_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_set_forw); }
@@ -1722,11 +2136,11 @@ REGISTER_SM100(CCV_NNC_TRANSPOSE_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F 
 REGISTER_SM100(CCV_NNC_TRANSPOSE_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_transpose); }
 REGISTER_SM100(CCV_NNC_DATATYPE_CONVERSION_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF, 1, exec_datatype_conversion); }
 REGISTER_SM100(CCV_NNC_DATATYPE_CONVERSION_BACKWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF, 1, exec_datatype_conversion); }
-REGISTER_SM100(CCV_NNC_SGD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_sgd_forw); }
+REGISTER_SM100(CCV_NNC_SGD_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, exec_sgd_any); }
 REGISTER_SM100(CCV_NNC_SGD_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F, 1, exec_invalid); }
-REGISTER_SM100(CCV_NNC_CATEGORICAL_CROSSENTROPY_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_cce_forw); }
-REGISTER_SM100(CCV_NNC_CATEGORICAL_CROSSENTROPY_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_cce_back); }
-REGISTER_SM100(CCV_NNC_SOFTMAX_CROSSENTROPY_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_softmax_cce_forw); }
-REGISTER_SM100(CCV_NNC_SOFTMAX_CROSSENTROPY_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_32S, 1, exec_softmax_cce_back); }
+REGISTER_SM100(CCV_NNC_CATEGORICAL_CROSSENTROPY_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_via_f32<exec_cce_forw>); }
+REGISTER_SM100(CCV_NNC_CATEGORICAL_CROSSENTROPY_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_via_f32<exec_cce_back>); }
+REGISTER_SM100(CCV_NNC_SOFTMAX_CROSSENTROPY_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_via_f32<exec_softmax_cce_forw>); }
+REGISTER_SM100(CCV_NNC_SOFTMAX_CROSSENTROPY_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_via_f32<exec_softmax_cce_back>); }
 REGISTER_SM100(CCV_NNC_COMM_ALLREDUCE_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_allreduce); }
 REGISTER_SM100(CCV_NNC_COMM_ALLREDUCE_BACKWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, 1, ccv_nnc_sm100_exec_allreduce); }

@@ -426,7 +426,12 @@ int ccv_nnc_sm100_exec_gnorm_forw(SM100_EXEC_ARGS)
 	GroupNormGeom g;
 	if (!gn_geom(inputs[0], outputs[0], 0, outputs[1], affine ? inputs[1] : 0, g) || !packed_f32(outputs[2]) || count_of(outputs[2]) != count_of(outputs[1]) || (affine && !packed_f32(inputs[2])))
 		return CCV_NNC_EXEC_INVALID;
-	if (group_norm_fwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, affine ? inputs[1]->data.f32 : 0, affine ? inputs[2]->data.f32 : 0, outputs[0]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, cmd.info.gnorm.epsilon))
+	// Both reference implementations read the epsilon through the LAYER-norm arm of the parameter union
+	// (norm/ccv_nnc_group_norm_cpu_ref.c:46, norm/gpu/ccv_nnc_group_norm_gpu_cudnn.cu:117: `cmd.info.lnorm.epsilon`), which aliases
+	// gnorm.reduce_count -- a small integer whose bits read as a denormal float (~0), NOT gnorm.epsilon.  Parity is with what the
+	// reference computes, so the same word is read here (its own tests hold the two backends to 1e-5 on statistics over 4 values,
+	// test/int/nnc/cudnn.tests.c:1491-1560, where a 1e-5 epsilon would show).
+	if (group_norm_fwd_f32(stream_of(stream_context), g, inputs[0]->data.f32, affine ? inputs[1]->data.f32 : 0, affine ? inputs[2]->data.f32 : 0, outputs[0]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, cmd.info.lnorm.epsilon))
 		return CCV_NNC_EXEC_INVALID;
 	return CCV_NNC_EXEC_SUCCESS;
 }

@@ -126,6 +126,46 @@ int ew_set_u16(cudaStream_t s, uint16_t* p, size_t n, uint16_t v)
 	set_u16_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, v);
 	return check("set_u16");
 }
+__global__ void set_u64_kernel(uint64_t* __restrict__ p, const size_t n, const uint64_t v)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		p[i] = v;
+}
+int ew_set_u64(cudaStream_t s, uint64_t* p, size_t n, uint64_t v)
+{
+	if (n == 0)
+		return 0;
+	set_u64_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, v);
+	return check("set_u64");
+}
+// int32 n-ary sum (label / index arithmetic in graphs: small tensors, scalar accesses)
+struct SumArgsI32 {
+	const int* in[64];
+	int k;
+};
+__global__ void sum_i32_kernel(const SumArgsI32 a, int* __restrict__ out, const size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+	{
+		int v = 0;
+		for (int j = 0; j < a.k; j++)
+			v += a.in[j][i];
+		out[i] = v;
+	}
+}
+int ew_sum_i32(cudaStream_t s, const int* const* inputs, int k, int* out, size_t n)
+{
+	if (n == 0)
+		return 0;
+	if (k < 1 || k > 64)
+		return 1;
+	SumArgsI32 a;
+	for (int j = 0; j < k; j++)
+		a.in[j] = inputs[j];
+	a.k = k;
+	sum_i32_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, out, n);
+	return check("sum_i32");
+}
 
 struct SumArgs {
 	const float* in[8];

@@ -10,6 +10,8 @@ namespace sm100 {
 // ---- fill / n-ary sum / axpby / relu --------------------------------------------------------------------------
 int ew_set_f32(cudaStream_t s, float* p, size_t n, float v);
 int ew_set_u16(cudaStream_t s, uint16_t* p, size_t n, uint16_t v);
+int ew_set_u64(cudaStream_t s, uint64_t* p, size_t n, uint64_t v);
+int ew_sum_i32(cudaStream_t s, const int* const* inputs, int k, int* out, size_t n); // k <= 64
 int ew_sum_f32(cudaStream_t s, const float* const* inputs, int k, float* out, size_t n); // out = sum_k inputs[k] (out may alias any input)
 // c = p * a + q * b (b may be NULL: c = p * a); all contiguous and same shape
 int ew_axpby_f32(cudaStream_t s, float p, const float* a, float q, const float* b, float* c, size_t n);

@@ -599,3 +599,94 @@ def CMD_TRANSPOSE_FORWARD(axis_a, axis_b, **kw):
     c = _simple(abi.CCV_NNC_TRANSPOSE_FORWARD, **kw)
     c.info.transpose.axis[0], c.info.transpose.axis[1] = axis_a, axis_b
     return c
+
+
+# ---- element-wise family, reductions, masked fill (cmd/ew/ccv_nnc_ew.c, cmd/sigmoid, cmd/tanh, cmd/leaky_relu, cmd/reduce, cmd/util) ----
+def _make_simple(name):
+    def fwd(**kw):
+        return _simple(getattr(abi, "CCV_NNC_%s_FORWARD" % name), **kw)
+
+    def bwd(**kw):
+        return _simple(getattr(abi, "CCV_NNC_%s_BACKWARD" % name), **kw)
+    return fwd, bwd
+
+
+CMD_SIGMOID_FORWARD, CMD_SIGMOID_BACKWARD = _make_simple("SIGMOID")
+CMD_TANH_FORWARD, CMD_TANH_BACKWARD = _make_simple("TANH")
+CMD_EWEXP_FORWARD, CMD_EWEXP_BACKWARD = _make_simple("EWEXP")
+CMD_EWLOG_FORWARD, CMD_EWLOG_BACKWARD = _make_simple("EWLOG")
+CMD_EWSQRT_FORWARD, CMD_EWSQRT_BACKWARD = _make_simple("EWSQRT")
+CMD_EWDIV_FORWARD, CMD_EWDIV_BACKWARD = _make_simple("EWDIV")
+
+
+def CMD_LEAKY_RELU_FORWARD(negative_slope, **kw):
+    c = _simple(abi.CCV_NNC_LEAKY_RELU_FORWARD, **kw)
+    c.info.leaky_relu.negative_slope = negative_slope
+    return c
+
+
+def CMD_LEAKY_RELU_BACKWARD(negative_slope, **kw):
+    c = _simple(abi.CCV_NNC_LEAKY_RELU_BACKWARD, **kw)
+    c.info.leaky_relu.negative_slope = negative_slope
+    return c
+
+
+def CMD_CLAMP_FORWARD(lo, hi, **kw):
+    """lo / hi may be float('nan') for an open side (CMD_CLAMP_FORWARD(min, max), cmd/ew/ccv_nnc_ew.c)"""
+    c = _simple(abi.CCV_NNC_CLAMP_FORWARD, **kw)
+    c.info.clamp.min, c.info.clamp.max = lo, hi
+    return c
+
+
+def CMD_CLAMP_BACKWARD(lo, hi, **kw):
+    c = _simple(abi.CCV_NNC_CLAMP_BACKWARD, **kw)
+    c.info.clamp.min, c.info.clamp.max = lo, hi
+    return c
+
+
+def _reduce(cmd_id, axes, **kw):
+    c = _simple(cmd_id, **kw)
+    for i, a in enumerate(axes):
+        c.info.reduce.axis[i] = a
+    c.info.reduce.count = len(axes)
+    return c
+
+
+def _make_reduce(name):
+    def fwd(*axes, **kw):
+        return _reduce(getattr(abi, "CCV_NNC_REDUCE_%s_FORWARD" % name), axes, **kw)
+
+    def bwd(*axes, **kw):
+        return _reduce(getattr(abi, "CCV_NNC_REDUCE_%s_BACKWARD" % name), axes, **kw)
+    return fwd, bwd
+
+
+CMD_REDUCE_SUM_FORWARD, CMD_REDUCE_SUM_BACKWARD = _make_reduce("SUM")
+CMD_REDUCE_MEAN_FORWARD, CMD_REDUCE_MEAN_BACKWARD = _make_reduce("MEAN")
+CMD_REDUCE_MAX_FORWARD, CMD_REDUCE_MAX_BACKWARD = _make_reduce("MAX")
+CMD_REDUCE_MIN_FORWARD, CMD_REDUCE_MIN_BACKWARD = _make_reduce("MIN")
+CMD_REDUCE_NORM2_FORWARD, CMD_REDUCE_NORM2_BACKWARD = _make_reduce("NORM2")
+
+
+def CMD_MASKED_FILL_FORWARD(eq, fill, **kw):
+    c = _simple(abi.CCV_NNC_MASKED_FILL_FORWARD, **kw)
+    c.info.blas.a[0], c.info.blas.a[1] = eq, fill
+    return c
+
+
+def CMD_MASKED_FILL_BACKWARD(eq, fill, **kw):
+    c = _simple(abi.CCV_NNC_MASKED_FILL_BACKWARD, **kw)
+    c.info.blas.a[0], c.info.blas.a[1] = eq, fill
+    return c
+
+
+def CMD_RANDOM_UNIFORM_FORWARD(lb, ub, **kw):
+    c = _simple(abi.CCV_NNC_RANDOM_UNIFORM_FORWARD, **kw)
+    c.info.blas.a[0], c.info.blas.a[1] = lb, ub
+    return c
+
+
+def CMD_RANDOM_NORMAL_FORWARD(std, mean, **kw):
+    c = _simple(abi.CCV_NNC_RANDOM_NORMAL_FORWARD, **kw)
+    c.info.blas.a[0], c.info.blas.a[1] = std, mean
+    return c

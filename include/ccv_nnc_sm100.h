@@ -257,6 +257,9 @@ typedef struct {
 			float max;
 		} clamp;
 		struct {
+			float negative_slope;
+		} leaky_relu;
+		struct {
 			float scale;
 			int is_causal;
 			int flags;
@@ -385,6 +388,38 @@ enum {
 	CCV_NNC_TRANSPOSE_BACKWARD = 0xb4d506e1,
 	CCV_NNC_UPSAMPLE_FORWARD = 0x73875556,
 	CCV_NNC_UPSAMPLE_BACKWARD = 0x73875557,
+	CCV_NNC_SIGMOID_FORWARD = 0xf2f69650,
+	CCV_NNC_SIGMOID_BACKWARD = 0xf2f69651,
+	CCV_NNC_TANH_FORWARD = 0x6a62be30,
+	CCV_NNC_TANH_BACKWARD = 0x6a62be31,
+	CCV_NNC_LEAKY_RELU_FORWARD = 0x507144e0,
+	CCV_NNC_LEAKY_RELU_BACKWARD = 0x507144e1,
+	CCV_NNC_EWEXP_FORWARD = 0xd784b170,
+	CCV_NNC_EWEXP_BACKWARD = 0xd784b171,
+	CCV_NNC_EWLOG_FORWARD = 0xf4191bf2,
+	CCV_NNC_EWLOG_BACKWARD = 0xf4191bf3,
+	CCV_NNC_EWSQRT_FORWARD = 0x8870a61e,
+	CCV_NNC_EWSQRT_BACKWARD = 0x8870a61f,
+	CCV_NNC_CLAMP_FORWARD = 0x2640d854,
+	CCV_NNC_CLAMP_BACKWARD = 0x2640d855,
+	CCV_NNC_EWDIV_FORWARD = 0x1cd2fa18,
+	CCV_NNC_EWDIV_BACKWARD = 0x1cd2fa19,
+	CCV_NNC_REDUCE_SUM_FORWARD = 0x52970f06,
+	CCV_NNC_REDUCE_SUM_BACKWARD = 0x52970f07,
+	CCV_NNC_REDUCE_MEAN_FORWARD = 0xf23556c6,
+	CCV_NNC_REDUCE_MEAN_BACKWARD = 0xf23556c7,
+	CCV_NNC_REDUCE_MAX_FORWARD = 0x80f1a506,
+	CCV_NNC_REDUCE_MAX_BACKWARD = 0x80f1a507,
+	CCV_NNC_REDUCE_MIN_FORWARD = 0x6785ef96,
+	CCV_NNC_REDUCE_MIN_BACKWARD = 0x6785ef97,
+	CCV_NNC_REDUCE_NORM2_FORWARD = 0xb3034e16,
+	CCV_NNC_REDUCE_NORM2_BACKWARD = 0xb3034e17,
+	CCV_NNC_MASKED_FILL_FORWARD = 0x7f992d84,
+	CCV_NNC_MASKED_FILL_BACKWARD = 0x7f992d85,
+	CCV_NNC_RANDOM_UNIFORM_FORWARD = 0xa0cd1d5e,
+	CCV_NNC_RANDOM_UNIFORM_BACKWARD = 0xa0cd1d5f,
+	CCV_NNC_RANDOM_NORMAL_FORWARD = 0x7062c8b4,
+	CCV_NNC_RANDOM_NORMAL_BACKWARD = 0x7062c8b5,
 };
 
 enum {
@@ -441,7 +476,10 @@ enum {
 	X(CCV_NNC_INDEX_SELECT_FORWARD) X(CCV_NNC_INDEX_SELECT_BACKWARD) \
 	X(CCV_NNC_CATEGORICAL_CROSSENTROPY_FORWARD) X(CCV_NNC_CATEGORICAL_CROSSENTROPY_BACKWARD) \
 	X(CCV_NNC_SOFTMAX_CROSSENTROPY_FORWARD) X(CCV_NNC_SOFTMAX_CROSSENTROPY_BACKWARD) \
-	X(CCV_NNC_COMM_ALLREDUCE_FORWARD) X(CCV_NNC_COMM_ALLREDUCE_BACKWARD)
+	X(CCV_NNC_COMM_ALLREDUCE_FORWARD) X(CCV_NNC_COMM_ALLREDUCE_BACKWARD) \
+	X(CCV_NNC_SIGMOID_FORWARD) X(CCV_NNC_SIGMOID_BACKWARD) X(CCV_NNC_TANH_FORWARD) X(CCV_NNC_TANH_BACKWARD) X(CCV_NNC_LEAKY_RELU_FORWARD) X(CCV_NNC_LEAKY_RELU_BACKWARD) X(CCV_NNC_EWEXP_FORWARD) X(CCV_NNC_EWEXP_BACKWARD) X(CCV_NNC_EWLOG_FORWARD) X(CCV_NNC_EWLOG_BACKWARD) X(CCV_NNC_EWSQRT_FORWARD) X(CCV_NNC_EWSQRT_BACKWARD) X(CCV_NNC_CLAMP_FORWARD) X(CCV_NNC_CLAMP_BACKWARD) \
+	X(CCV_NNC_EWDIV_FORWARD) X(CCV_NNC_EWDIV_BACKWARD) X(CCV_NNC_REDUCE_SUM_FORWARD) X(CCV_NNC_REDUCE_SUM_BACKWARD) X(CCV_NNC_REDUCE_MEAN_FORWARD) X(CCV_NNC_REDUCE_MEAN_BACKWARD) X(CCV_NNC_REDUCE_MAX_FORWARD) X(CCV_NNC_REDUCE_MAX_BACKWARD) X(CCV_NNC_REDUCE_MIN_FORWARD) X(CCV_NNC_REDUCE_MIN_BACKWARD) X(CCV_NNC_REDUCE_NORM2_FORWARD) X(CCV_NNC_REDUCE_NORM2_BACKWARD) X(CCV_NNC_MASKED_FILL_FORWARD) X(CCV_NNC_MASKED_FILL_BACKWARD) \
+	X(CCV_NNC_RANDOM_UNIFORM_FORWARD) X(CCV_NNC_RANDOM_UNIFORM_BACKWARD) X(CCV_NNC_RANDOM_NORMAL_FORWARD) X(CCV_NNC_RANDOM_NORMAL_BACKWARD)
 
 #define CCV_SM100_DECLARE_REGISTER(cmd) void _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(ccv_nnc_cmd_backend_registry_t* const registry);
 CCV_NNC_SM100_COMMANDS(CCV_SM100_DECLARE_REGISTER)
@@ -452,6 +490,9 @@ CCV_NNC_SM100_COMMANDS(CCV_SM100_DECLARE_REGISTER)
 void* ccv_nnc_stream_context_get_stream(const ccv_nnc_stream_context_t* const stream_context);
 int ccv_nnc_stream_context_get_device(const ccv_nnc_stream_context_t* const stream_context);
 void* ccv_nnc_stream_context_get_workspace(ccv_nnc_stream_context_t* const stream_context, const size_t workspace_size, const int mem);
+/* lib/nnc/ccv_nnc.h / ccv_nnc_stream.c:247-281: the per-stream-context generator the random-fill commands draw their seed from */
+uint32_t ccv_nnc_stream_context_genrand_uint32(ccv_nnc_stream_context_t* const stream_context);
+void ccv_nnc_stream_context_set_seed(ccv_nnc_stream_context_t* const stream_context, uint32_t seed);
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* (B) HOST side, reference names and semantics.                                                                 */

@@ -266,6 +266,71 @@ def test_convolution_forward_nchw(gpu, ref, N, C, H, K, R, st, groups):
     assert_close(y_g, y_r, 1e-3, "NCHW convolution")
 
 
+@pytest.mark.ref
+@pytest.mark.parametrize("C,K,st,which", [(32, 64, 1, "filters"), (3, 24, 2, "filters"), (16, 32, 1, "activations")])
+def test_convolution_forward_mixed_formats(gpu, ref, C, K, st, which):
+    """NHWC activations against NCHW filters -- what the reference's own GPU tests run (test/int/nnc/cudnn.tests.c:24-85:
+    `gwo` is GPU_TENSOR_NCHW while `ga` / `gc` are NHWC) -- and the converse; CPU_REF has no mixed path, so the check is the
+    all-NHWC CPU_REF result on the transposed arrays."""
+    nnc = gpu
+    N, H, R = 2, 12, 3
+    pad = R // 2
+    P = (H + 2 * pad - R) // st + 1
+    x, w, bias = seeded((N, H, H, C), 1, -1, 1), seeded((K, R, R, C), 2, -1, 1) / (R * R * C) ** 0.5, seeded((K,), 3, -1, 1)
+    cmd = nnc.CMD_CONVOLUTION_FORWARD(1, K, R, R, C)
+    hint = nnc.hint((st, st), (pad, pad))
+    st_r, (y_r,) = ref_exec(ref, cmd, hint, 0, [x, w, bias], [np.zeros((N, P, P, K), np.float32)])
+    if which == "filters":
+        ins, fm = [x, np.ascontiguousarray(w.transpose(0, 3, 1, 2)), bias], dict(in_fmts=[NHWC, NCHW, NHWC], out_fmts=[NHWC])
+        st_g, (y_g,) = gpu_exec(nnc, cmd, hint, 0, ins, [np.zeros((N, P, P, K), np.float32)], **fm)
+    else:
+        ins, fm = [np.ascontiguousarray(x.transpose(0, 3, 1, 2)), w, bias], dict(in_fmts=[NCHW, NHWC, NHWC], out_fmts=[NCHW])
+        st_g, (y_g,) = gpu_exec(nnc, cmd, hint, 0, ins, [np.zeros((N, K, P, P), np.float32)], **fm)
+        y_g = y_g.transpose(0, 2, 3, 1)
+    assert st_r == 0 and st_g == 0
+    assert_close(y_g, y_r, 1e-3, "mixed-format convolution")
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("C,K,st,layout", [(32, 64, 1, "nchw"), (3, 16, 2, "nchw"), (16, 32, 1, "filters"), (16, 32, 2, "nchw16")])
+def test_convolution_backward_nchw_and_mixed(gpu, ref, C, K, st, layout):
+    """CONVOLUTION_BACKWARD with NCHW tensors (all of them, or only the filter / its gradient as in test/int/nnc/cudnn.tests.c:
+    348-497), also accumulating and in half precision: staged through NHWC; checked against CPU_REF's NHWC backward on the transposed arrays
+    (CPU_REF's own backward is NHWC-only, convolution/ccv_nnc_conv_cpu_ref.c:358)."""
+    nnc = gpu
+    N, H, R = 2, 10, 3
+    pad = R // 2
+    P = (H + 2 * pad - R) // st + 1
+    g, x, w = seeded((N, P, P, K), 1, -1, 1), seeded((N, H, H, C), 2, -1, 1), seeded((K, R, R, C), 3, -1, 1) / (R * R * C) ** 0.5
+    half = layout == "nchw16"
+    if half:
+        from tests.util import round16
+        g, x, w = round16(g, abi.CCV_16F), round16(x, abi.CCV_16F), round16(w, abi.CCV_16F)
+    cmd = nnc.CMD_CONVOLUTION_BACKWARD(1, K, R, R, C)
+    hint = nnc.hint((st, st), (pad, pad))
+    st_r, (h_r, dw_r, db_r) = ref_exec(ref, cmd, hint, 0, [g, x, w], [np.zeros_like(x), np.zeros_like(w), np.zeros((K,), np.float32)])
+    t = lambda a: np.ascontiguousarray(a.transpose(0, 3, 1, 2))
+    if layout == "filters":
+        ins, outs = [g, x, t(w)], [np.zeros_like(x), np.ones_like(t(w)), np.zeros((K,), np.float32)]
+        fm = dict(in_fmts=[NHWC, NHWC, NCHW], out_fmts=[NHWC, NCHW, NHWC])
+        st_g, (h_g, dw_g, db_g) = gpu_exec(nnc, cmd, hint, abi.CCV_NNC_ACCUMULATE_OUTPUT, ins, outs, **fm)
+        dw_g = dw_g.transpose(0, 2, 3, 1) - 1.0  # accumulated onto ones
+    else:
+        ins, outs = [t(g), t(x), t(w)], [np.zeros_like(t(x)), np.zeros_like(t(w)), np.zeros((K,), np.float32)]
+        fm = dict(in_fmts=[NCHW, NCHW, NCHW], out_fmts=[NCHW, NCHW, NHWC])
+        if half:
+            from tests.util import gpu_exec16
+            st_g, (h_g, dw_g, db_g) = gpu_exec16(nnc, cmd, hint, 0, ins, outs, abi.CCV_16F, keep32=(id(outs[2]),), **fm)
+        else:
+            st_g, (h_g, dw_g, db_g) = gpu_exec(nnc, cmd, hint, 0, ins, outs, **fm)
+        h_g, dw_g = h_g.transpose(0, 2, 3, 1), dw_g.transpose(0, 2, 3, 1)
+    assert st_r == 0 and st_g == 0
+    tol = 1e-2 if half else 1e-3
+    assert_close(h_g, h_r, tol, "dgrad " + layout)
+    assert_close(dw_g, dw_r, tol, "wgrad " + layout)
+    assert_close(db_g, db_r, tol, "dbias " + layout)
+
+
 # ------------------------------------------------------------------------------------------------ BASELINE configs at full size
 def _report(name, got, want, tol):
     from tests.util import elem_rel_err, rel_err

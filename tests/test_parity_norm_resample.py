@@ -62,16 +62,18 @@ def _gnorm(cmd_id, group_axis, groups, eps, affine, reduce_axes):
     ((2, 6, 5, 16), 3, 4, (1, 2), 1),      # NHWC
     ((3, 32, 7, 7), 1, 8, (2, 3), 0),      # no affine
     ((4, 24, 10), 1, 3, (2,), 1),          # 3-d
+    ((2, 16, 2, 10), 1, 4, (), 1),         # test/int/nnc/cudnn.tests.c:1491-1560: statistics over the 4 channels of a group only (small variances: the epsilon word matters)
 ])
 def test_group_norm_forward_backward(gpu, ref, shape, group_axis, groups, reduce_axes, affine):
-    """norm/ccv_nnc_group_norm_cpu_ref.c: statistics per (sample, group); per-channel scale / bias.  CPU_REF reads its
-    epsilon through the lnorm arm of the parameter union (:46), i.e. the integer reduce_count reinterpreted as a float
-    (a denormal ~ 0) instead of gnorm.epsilon; this backend uses gnorm.epsilon as documented (lib/nnc/ccv_nnc.h:163) and
-    the inputs here have O(0.3) variance, so the 1e-5 epsilon moves inv_std by ~2e-5 relative, inside the tolerance."""
+    """norm/ccv_nnc_group_norm_cpu_ref.c: statistics per (sample, group); per-channel scale / bias.  CPU_REF (and the
+    reference's GPU implementation) read the epsilon through the lnorm arm of the parameter union (:46), i.e. the integer
+    reduce_count reinterpreted as a float (a denormal ~ 0) instead of gnorm.epsilon; the backend reads the same word."""
     nnc = gpu
     x = seeded(shape, 1, -1, 1)
     rshape = tuple(groups if i == group_axis else (1 if i in reduce_axes else d) for i, d in enumerate(shape))
     pshape = tuple(d if i == group_axis else 1 for i, d in enumerate(shape))
+    if not reduce_axes:
+        pshape = (1,) + tuple(shape[1:])  # the reference's own test shape: scale / bias per element of a sample
     scale, bias = seeded(pshape, 2), seeded(pshape, 3)
     fwd = _gnorm(abi.CCV_NNC_GROUP_NORM_FORWARD, group_axis, groups, 1e-5, affine, reduce_axes)
     mk = lambda: [np.zeros(shape, np.float32), np.zeros(rshape, np.float32), np.zeros(rshape, np.float32)]

@@ -109,27 +109,27 @@ def unpack16(u, kind):
     return from_bf16(u) if kind == abi.CCV_16BF else np.asarray(u, np.float16).astype(np.float32)
 
 
-def gpu_exec16(nnc, cmd, hint, flags, in_arrays, out_arrays, kind, keep32=(), stream=None):
+def gpu_exec16(nnc, cmd, hint, flags, in_arrays, out_arrays, kind, keep32=(), stream=None, in_fmts=None, out_fmts=None):
     """gpu_exec with fp32 numpy arrays travelling as 16-bit tensors of `kind`.  `keep32`: ids (id(array)) of operands that stay
     fp32 (batch-norm parameters / statistics, fp32 master weights of SGD).  Integer arrays travel unchanged.  The same array
     object in both lists is the same GPU tensor.  Returns (status, [fp32 output arrays])."""
     cache = {}
 
-    def tensor_for(a):
+    def tensor_for(a, f=NHWC):
         if a is None:
             return None
         if id(a) not in cache:
             if a.dtype != np.float32 or id(a) in keep32:
-                t = nnc.gpu_tensor(list(a.shape), NHWC, NP_TO_CCV[a.dtype])
+                t = nnc.gpu_tensor(list(a.shape), f, NP_TO_CCV[a.dtype])
                 t.upload(a)
             else:
-                t = nnc.gpu_tensor(list(a.shape), NHWC, kind)
+                t = nnc.gpu_tensor(list(a.shape), f, kind)
                 t.upload(pack16(a, kind))
             cache[id(a)] = t
         return cache[id(a)]
 
-    ins = [tensor_for(a) for a in in_arrays]
-    outs = [tensor_for(a) for a in out_arrays]
+    ins = [tensor_for(a, in_fmts[i] if in_fmts else NHWC) for i, a in enumerate(in_arrays)]
+    outs = [tensor_for(a, out_fmts[i] if out_fmts else NHWC) for i, a in enumerate(out_arrays)]
     status = nnc.cmd_exec(cmd, hint, flags, ins, outs, stream)
     if stream is not None:
         stream.wait()
