@@ -317,15 +317,31 @@ int exec_gemm_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		a.batch_inc = 0;
 	if (w.batch == 1)
 		w.batch_inc = 0;
+	bool matrix_bias = false;
 	if (bias_t)
 	{
-		if (!mat_of(view_of(bias_t), no_transpose, bias) || bias.cols != b.cols || bias.cs != 1 || (bias.rows != 1))
+		if (!mat_of(view_of(bias_t), no_transpose, bias) || bias.cols != b.cols || bias.cs != 1)
+			return CCV_NNC_EXEC_INVALID;
+		// the third operand is a row vector added to every row, or (blas/gpu/ccv_nnc_gemm_gpu_cublas.cu; test/int/nnc/cublas.tests.c:164-211)
+		// a full [M, N] matrix: then c = a w + d, applied as a second pass
+		matrix_bias = bias.rows == b.rows && bias.rows != 1;
+		if ((bias.rows != 1 && !matrix_bias) || (matrix_bias && (kind != 0 || b.cs != 1)))
 			return CCV_NNC_EXEC_INVALID;
 		if (bias.batch == 1)
 			bias.batch_inc = 0;
 	}
 	cudaStream_t s = stream_of(stream_context);
 	const Scratch scratch = scratch_of(stream_context);
+	if (matrix_bias)
+	{
+		for (int i = 0; i < b.batch; i++)
+		{
+			RC(gemm_dispatch(s, scratch, gemm_algorithm(cmd), b.rows, b.cols, a.cols, a.p + i * a.batch_inc, a.rs, a.cs, w.p + i * w.batch_inc, w.rs, w.cs, b.p + i * b.batch_inc, b.rs, b.cs, 0, 0));
+			const int d4[4] = { 1, 1, b.rows, b.cols }, cs4[4] = { 0, 0, (int)b.rs, 1 }, ds4[4] = { 0, 0, (int)bias.rs, 1 };
+			RC(ew_axpby_bcast_f32(s, 1.f, b.p + i * b.batch_inc, cs4, 1.f, bias.p + i * bias.batch_inc, ds4, b.p + i * b.batch_inc, cs4, d4));
+		}
+		return CCV_NNC_EXEC_SUCCESS;
+	}
 	if (kind != 0)
 	{
 		// 16-bit operands: tcgen05 kind::f16, fp32 accumulate; the bias may be fp32 or in the operands' type
@@ -562,6 +578,92 @@ bool conv_geom(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, const TV& a
 	return true;
 }
 
+// ------------------------------------------------------------------------------------------------ grouped convolution on tensor cores
+// groups > 1 (convolution/ccv_nnc_conv_cpu_ref.c:47-65; the reference's GPU path hands groups to cuDNN,
+// convolution/gpu/ccv_nnc_conv_gpu_cudnn.cu:204-357): group i contracts channels [i C/g, (i+1) C/g) against filters
+// [i K/g, (i+1) K/g) -- `groups` independent dense convolutions whose operands are channel SLICES of the NHWC tensors (pixel stride
+// C, not C/g) except for the filters, whose rows are contiguous per group.  When a group is wide enough to fill tensor-core tiles
+// (C/g and K/g multiples of the 16-byte vector and >= 16) each group's slices are made dense in the stream workspace (one strided
+// copy in, one out), and the dense tcgen05 kernels above do the arithmetic; narrower groups (depthwise and the like) stay on the
+// FFMA kernels, where the contraction is too short for a 64-deep MMA anyway.  PASS 0 = fprop, 1 = wgrad, 2 = dgrad.
+// returns 0 done, 1 not applicable (caller falls back), < 0 error
+template <int PASS>
+int conv_grouped_tc(ccv_nnc_stream_context_t* const stream_context, const int kind, const ConvGeom& g, const int groups, const int x3, const int accumulate,
+	const void* const act, const void* const filt, const float* const bias32, const void* const bias16, const void* const res, void* const out)
+{
+	const int align = kind == 0 ? 4 : 8;
+	const size_t es = kind_size(kind);
+	if (groups <= 1 || g.C % groups || g.K % groups)
+		return 1;
+	const int Cg = g.C / groups, Kg = g.K / groups;
+	if (Cg % align || Kg % align || Cg < 16 || Kg < 16)
+		return 1;
+	const long long lim = 0x7fffffffll;
+	if ((long long)g.N * g.an > lim || (long long)g.N * g.bn > lim)
+		return 1; // copy_strided walks int strides
+	ConvGeom gg = g;
+	gg.C = Cg, gg.K = Kg;
+	gg.aw = Cg, gg.ah = (long long)g.W * Cg, gg.an = (long long)g.H * g.W * Cg;
+	gg.bw = Kg, gg.bh = (long long)g.Q * Kg, gg.bn = (long long)g.P * g.Q * Kg;
+	const size_t nx = (size_t)g.N * g.H * g.W * Cg, ny = (size_t)g.N * g.P * g.Q * Kg;
+	const size_t xb = (nx * es + 255) & ~(size_t)255, yb = (ny * es + 255) & ~(size_t)255;
+	unsigned char* const ws = (unsigned char*)ccv_nnc_stream_context_get_workspace(stream_context, CONTRACT_SCRATCH_BYTES + xb + yb, CCV_TENSOR_GPU_MEMORY);
+	if (!ws)
+		return 1;
+	const Scratch scratch = scratch_at(ws, CONTRACT_SCRATCH_BYTES);
+	unsigned char* const xg = ws + CONTRACT_SCRATCH_BYTES;
+	unsigned char* const yg = xg + xb;
+	cudaStream_t s = stream_of(stream_context);
+	const int xd[4] = { g.N, g.H, g.W, Cg }, xs_t[4] = { (int)g.an, (int)g.ah, (int)g.aw, 1 }, xs_d[4] = { g.H * g.W * Cg, g.W * Cg, Cg, 1 };
+	const int yd[4] = { g.N, g.P, g.Q, Kg }, ys_t[4] = { (int)g.bn, (int)g.bh, (int)g.bw, 1 }, ys_d[4] = { g.P * g.Q * Kg, g.Q * Kg, Kg, 1 };
+	const size_t wstep = (size_t)Kg * g.R * g.S * Cg * es;
+	for (int i = 0; i < groups; i++)
+	{
+		const unsigned char* const act_i = (const unsigned char*)act + (size_t)i * Cg * es;
+		const unsigned char* const res_i = (const unsigned char*)res + (size_t)i * Kg * es;
+		const unsigned char* const w_i = (const unsigned char*)filt + (size_t)i * wstep;
+		int rc;
+		if (PASS == 0)
+		{
+			// y_i = conv(x_i, w_i) + bias_i
+			if (copy_strided(s, act_i, xs_t, xg, xs_d, xd, (int)es))
+				return -1;
+			if (kind == 0)
+				rc = conv_fprop_tf32(s, gg, (const float*)xg, (const float*)w_i, bias32 ? bias32 + (size_t)i * Kg : 0, (float*)yg, scratch, x3);
+			else
+				rc = conv_fprop_16(s, kind, gg, xg, w_i, bias32 ? bias32 + (size_t)i * Kg : 0, bias16 ? (const unsigned char*)bias16 + (size_t)i * Kg * 2 : 0, yg, scratch);
+			if (rc)
+				return i == 0 ? rc : -1;
+			if (copy_strided(s, yg, ys_d, (unsigned char*)out + (size_t)i * Kg * es, ys_t, yd, (int)es))
+				return -1;
+		} else if (PASS == 1) {
+			// dw_i (+)= wgrad(g_i, x_i): the filter gradient's rows of a group are contiguous
+			if (copy_strided(s, act_i, xs_t, xg, xs_d, xd, (int)es) || copy_strided(s, res_i, ys_t, yg, ys_d, yd, (int)es))
+				return -1;
+			unsigned char* const dw_i = (unsigned char*)out + (size_t)i * wstep;
+			if (kind == 0)
+				rc = conv_wgrad_tf32(s, gg, (const float*)yg, (const float*)xg, (float*)dw_i, accumulate, scratch, x3);
+			else
+				rc = conv_wgrad_16(s, kind, gg, yg, xg, dw_i, accumulate, scratch);
+			if (rc)
+				return i == 0 ? rc : -1;
+		} else {
+			// h_i = dgrad(g_i, w_i)
+			if (copy_strided(s, res_i, ys_t, yg, ys_d, yd, (int)es))
+				return -1;
+			if (kind == 0)
+				rc = conv_dgrad_tf32(s, gg, (const float*)yg, (const float*)w_i, (float*)xg, scratch, x3);
+			else
+				rc = conv_dgrad_16(s, kind, gg, yg, w_i, xg, scratch);
+			if (rc)
+				return i == 0 ? rc : -1;
+			if (copy_strided(s, xg, xs_d, (unsigned char*)out + (size_t)i * Cg * es, xs_t, xd, (int)es))
+				return -1;
+		}
+	}
+	return 0;
+}
+
 int conv_forw_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (input_size < 2 || output_size < 1 || !inputs[0] || !inputs[1] || !outputs[0])
@@ -574,11 +676,13 @@ int conv_forw_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		if (kind_of(inputs[1]) != kind || kind_of(outputs[0]) != kind || (bias_t && ((kind_of(bias_t) != kind && !is_f32(bias_t)) || CCV_IS_TENSOR_VIEW(bias_t))))
 			return CCV_NNC_EXEC_INVALID;
 		ConvGeom g16;
-		if ((cmd.info.convolution.groups > 1) || !conv_geom(cmd, hint, view_of(inputs[0]), view_of(inputs[1]), view_of(outputs[0]), g16) || (bias_t && bias_t->info.dim[0] != g16.K))
+		if (!conv_geom(cmd, hint, view_of(inputs[0]), view_of(inputs[1]), view_of(outputs[0]), g16) || (bias_t && bias_t->info.dim[0] != g16.K))
 			return CCV_NNC_EXEC_INVALID;
 		cudaStream_t s16 = stream_of(stream_context);
 		const float* const bias32 = bias_t && is_f32(bias_t) ? bias_t->data.f32 : 0;
 		const void* const bias16 = bias_t && !is_f32(bias_t) ? (const void*)bias_t->data.u8 : 0;
+		if (cmd.info.convolution.groups > 1) // wide groups only: there is no 16-bit FFMA kernel to fall back to
+			return conv_grouped_tc<0>(stream_context, kind, g16, cmd.info.convolution.groups, 0, 0, inputs[0]->data.u8, inputs[1]->data.u8, bias32, bias16, 0, outputs[0]->data.u8) == 0 ? CCV_NNC_EXEC_SUCCESS : CCV_NNC_EXEC_INVALID;
 		int rc = conv_fprop_16(s16, kind, g16, inputs[0]->data.u8, inputs[1]->data.u8, bias32, bias16, outputs[0]->data.u8, scratch_of(stream_context));
 		if (rc > 0 && g16.C % 8 != 0)
 		{
@@ -619,6 +723,14 @@ int conv_forw_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		if (rc < 0)
 			return CCV_NNC_EXEC_INVALID;
 	}
+	if (groups > 1 && algo != CCV_NNC_SM100_ALGO_FFMA)
+	{
+		const int rc = conv_grouped_tc<0>(stream_context, 0, g, groups, x3, 0, a, w, bias, 0, 0, b);
+		if (rc == 0)
+			return CCV_NNC_EXEC_SUCCESS;
+		if (rc < 0)
+			return CCV_NNC_EXEC_INVALID;
+	}
 	RC(conv_fprop_ffma(s, g, groups, a, w, bias, b));
 	return CCV_NNC_EXEC_SUCCESS;
 }
@@ -638,8 +750,9 @@ int conv_back_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 	if (kind > 0 && filt)
 	{
 		// bf16 / fp16: the same three products on the kind::f16 kernels; dbias in fp32 or the tensors' type
-		if (kind_of(inputs[1]) != kind || kind_of(filt) != kind || (h_t && kind_of(h_t) != kind) || (w_t && kind_of(w_t) != kind) || cmd.info.convolution.groups > 1)
+		if (kind_of(inputs[1]) != kind || kind_of(filt) != kind || (h_t && kind_of(h_t) != kind) || (w_t && kind_of(w_t) != kind))
 			return CCV_NNC_EXEC_INVALID;
+		const int groups16 = cmd.info.convolution.groups > 1 ? cmd.info.convolution.groups : 1;
 		ConvGeom g16;
 		if (!conv_geom(cmd, hint, view_of(inputs[1]), view_of(filt), view_of(inputs[0]), g16))
 			return CCV_NNC_EXEC_INVALID;
@@ -652,8 +765,11 @@ int conv_back_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 				return CCV_NNC_EXEC_INVALID;
 			RC(colsum_any(s16, kind, inputs[0]->data.u8, (size_t)g16.N * g16.P * g16.Q, g16.K, g16.bw, dbias_t->data.u8, db_kind, acc16, ccv_nnc_stream_context_get_workspace(stream_context, colsum_workspace_bytes(g16.K), CCV_TENSOR_GPU_MEMORY)));
 		}
-		if (dw_t)
+		if (dw_t && groups16 > 1)
 		{
+			if (conv_grouped_tc<1>(stream_context, kind, g16, groups16, 0, acc16, inputs[1]->data.u8, 0, 0, 0, inputs[0]->data.u8, dw_t->data.u8))
+				return CCV_NNC_EXEC_INVALID;
+		} else if (dw_t) {
 			int rc = conv_wgrad_16(s16, kind, g16, inputs[0]->data.u8, inputs[1]->data.u8, dw_t->data.u8, acc16, scratch_of(stream_context));
 			if (rc > 0 && g16.C % 8 != 0)
 			{
@@ -669,8 +785,32 @@ int conv_back_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 			ConvGeom gh16;
 			if (!w_t || !conv_geom(cmd, hint, view_of(h_t), view_of(w_t), view_of(inputs[0]), gh16))
 				return CCV_NNC_EXEC_INVALID;
-			if (conv_dgrad_16(s16, kind, gh16, inputs[0]->data.u8, w_t->data.u8, h_t->data.u8, scratch_of(stream_context)))
-				return CCV_NNC_EXEC_INVALID;
+			if (groups16 > 1)
+			{
+				if (conv_grouped_tc<2>(stream_context, kind, gh16, groups16, 0, 0, 0, w_t->data.u8, 0, 0, inputs[0]->data.u8, h_t->data.u8))
+					return CCV_NNC_EXEC_INVALID;
+			} else {
+				const int rc = conv_dgrad_16(s16, kind, gh16, inputs[0]->data.u8, w_t->data.u8, h_t->data.u8, scratch_of(stream_context));
+				if (rc < 0)
+					return CCV_NNC_EXEC_INVALID;
+				if (rc > 0)
+				{
+					// shapes the tensor-core path cannot take (3-channel pixels: the image gradient of a stem, test/int/nnc/cudnn.tests.c:499-577):
+					// functional form -- widen g and w, fp32 FFMA data gradient, one rounding on the way back.  Dense tensors only.
+					const size_t ng = (size_t)gh16.N * gh16.P * gh16.Q * gh16.K, nw = (size_t)gh16.K * gh16.R * gh16.S * gh16.C, nh = (size_t)gh16.N * gh16.H * gh16.W * gh16.C;
+					if (gh16.bw != gh16.K || gh16.bh != (long long)gh16.Q * gh16.K || gh16.bn != (long long)gh16.P * gh16.Q * gh16.K || gh16.aw != gh16.C || gh16.ah != (long long)gh16.W * gh16.C || gh16.an != (long long)gh16.H * gh16.W * gh16.C || ng > 0x7fffffffull || nh > 0x7fffffffull)
+						return CCV_NNC_EXEC_INVALID;
+					float* const g32 = (float*)ccv_nnc_stream_context_get_workspace(stream_context, (ng + nw + nh) * sizeof(float) + 1024, CCV_TENSOR_GPU_MEMORY);
+					if (!g32)
+						return CCV_NNC_EXEC_OOM;
+					float* const w32 = (float*)(((uintptr_t)(g32 + ng) + 255) & ~(uintptr_t)255);
+					float* const h32 = (float*)(((uintptr_t)(w32 + nw) + 255) & ~(uintptr_t)255);
+					RC(widen_matrix(s16, inputs[0]->data.u8, kind, (long long)ng, 1, g32, 1, (int)ng));
+					RC(widen_matrix(s16, w_t->data.u8, kind, (long long)nw, 1, w32, 1, (int)nw));
+					RC(conv_dgrad_ffma(s16, gh16, 1, g32, w32, h32));
+					RC(narrow_matrix(s16, h32, h_t->data.u8, kind, (long long)nh, 1, 1, (int)nh, 0));
+				}
+			}
 		}
 		return CCV_NNC_EXEC_SUCCESS;
 	}
@@ -704,6 +844,8 @@ int conv_back_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 					rc = conv_wgrad_im2col_tf32(s, g, gb, a, dw_t->data.f32, accumulate, ws, x3);
 			}
 		}
+		if (groups > 1 && algo != CCV_NNC_SM100_ALGO_FFMA)
+			rc = conv_grouped_tc<1>(stream_context, 0, g, groups, x3, accumulate, a, 0, 0, 0, gb, dw_t->data.f32);
 		if (rc < 0)
 			return CCV_NNC_EXEC_INVALID;
 		if (rc > 0)
@@ -719,6 +861,8 @@ int conv_back_nhwc(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int
 		int rc = 1;
 		if (groups == 1 && algo != CCV_NNC_SM100_ALGO_FFMA)
 			rc = conv_dgrad_tf32(s, gh, gb, w_t->data.f32, h_t->data.f32, scratch_of(stream_context), x3);
+		if (groups > 1 && algo != CCV_NNC_SM100_ALGO_FFMA)
+			rc = conv_grouped_tc<2>(stream_context, 0, gh, groups, x3, 0, 0, w_t->data.f32, 0, 0, gb, h_t->data.f32);
 		if (rc < 0)
 			return CCV_NNC_EXEC_INVALID;
 		if (rc > 0)
@@ -1727,6 +1871,12 @@ int exec_format_transform(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, co
 			RC(copy_tensor(s, inputs[i], outputs[i]));
 			continue;
 		}
+		if (a.nd == b.nd && a.nd < 3)
+		{
+			// a vector / matrix tagged with another format (the bias gradient of an NCHW convolution, test/int/nnc/cudnn.tests.c:455-471): plain copy
+			RC(copy_tensor(s, inputs[i], outputs[i]));
+			continue;
+		}
 		if (a.datatype != b.datatype || a.nd != b.nd || (a.nd != 3 && a.nd != 4))
 			return CCV_NNC_EXEC_INVALID;
 		// express both in (n, c, h, w) index order
@@ -1841,8 +1991,7 @@ inline uint16_t f32_to_16(const float v, const int kind)
 	return (uint16_t)(sign | (r + (rem > 0x1000u || (rem == 0x1000u && (r & 1)))));
 }
 
-template <ccv_nnc_cmd_exec_f F32>
-int exec_via_f32(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+int via_f32(const ccv_nnc_cmd_exec_f F32, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	enum { MAXT = 16 };
 	bool any16 = false;
@@ -1904,6 +2053,11 @@ int exec_via_f32(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int f
 		if (sh[j].is_out)
 			RC(narrow_matrix(s, sh[j].t.data.f32, sh[j].orig->data.u8, sh[j].kind, (long long)sh[j].n, 1, 1, (int)sh[j].n, 0));
 	return CCV_NNC_EXEC_SUCCESS;
+}
+template <ccv_nnc_cmd_exec_f F32>
+int exec_via_f32(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return via_f32(F32, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 
 // SGD: fp32 parameters / momenta with gradients of any type run natively (the mixed-precision form); 16-bit PARAMETERS
@@ -2092,6 +2246,13 @@ extern "C" int ccv_nnc_sm100_fused_sgd_multi(const ccv_nnc_cmd_t cmd, const ccv_
 }
 
 // ================================================================================================ registration
+namespace sm100 {
+int exec_via_f32_rt(ccv_nnc_cmd_exec_f f32, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	return via_f32(f32, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+}
+}
+
 #define REGISTER_SM100(cmd) extern "C" void _register_command_ ## cmd ## _backend_CCV_NNC_BACKEND_GPU_SM100(ccv_nnc_cmd_backend_registry_t* const registry)
 
 REGISTER_SM100(CCV_NNC_GEMM_FORWARD) { fill(registry, ALL_FORMATS, CCV_32F | CCV_16F | CCV_16BF, CCV_NNC_SM100_ALGO_COUNT, exec_gemm_nd4<exec_gemm_forw>); registry->autotune = autotune_contraction<exec_gemm_nd4<exec_gemm_forw> >; }
@@ -2124,8 +2285,8 @@ REGISTER_SM100(CCV_NNC_MAX_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC
 REGISTER_SM100(CCV_NNC_MAX_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_any<exec_pool_back<1> >); }
 REGISTER_SM100(CCV_NNC_AVERAGE_POOL_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_any<exec_pool_forw<0> >); }
 REGISTER_SM100(CCV_NNC_AVERAGE_POOL_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_pool_any<exec_pool_back<0> >); }
-REGISTER_SM100(CCV_NNC_UPSAMPLE_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, 1, ccv_nnc_sm100_exec_upsample_forw); }
-REGISTER_SM100(CCV_NNC_UPSAMPLE_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F, 1, ccv_nnc_sm100_exec_upsample_back); }
+REGISTER_SM100(CCV_NNC_UPSAMPLE_FORWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<ccv_nnc_sm100_exec_upsample_forw>); }
+REGISTER_SM100(CCV_NNC_UPSAMPLE_BACKWARD) { fill(registry, CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_NCHW, CCV_32F | CCV_16F | CCV_16BF, 1, exec_via_f32<ccv_nnc_sm100_exec_upsample_back>); }
 REGISTER_SM100(CCV_NNC_SET_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_set_forw); }
 REGISTER_SM100(CCV_NNC_SET_BACKWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S, 1, exec_set_forw); }
 REGISTER_SM100(CCV_NNC_DATA_TRANSFER_FORWARD) { fill(registry, ALL_FORMATS, CCV_64F | CCV_32F | CCV_16F | CCV_16BF | CCV_32S | CCV_8U, 1, exec_data_transfer); registry->tensor_memory = CCV_TENSOR_CPU_MEMORY | CCV_TENSOR_GPU_MEMORY; }

@@ -282,7 +282,7 @@ template <int MODE> __device__ __forceinline__ float red_identity() { return MOD
 template <int MODE> __device__ __forceinline__ float red_combine(const float x, const float y) { return MODE == RED_MAX ? fmaxf(x, y) : MODE == RED_MIN ? fminf(x, y) : x + y; }
 template <int MODE> __device__ __forceinline__ float red_map(const float v) { return MODE == RED_NORM2 ? v * v : v; }
 template <typename T, int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS) reduce_kernel(const T* __restrict__ a, T* __restrict__ b, const Red4 r, const size_t outputs, const float scale)
+__global__ void __launch_bounds__(256) reduce_kernel(const T* __restrict__ a, T* __restrict__ b, const Red4 r, const size_t outputs, const float scale)
 {
 	// one group of THREADS (a warp or the block) per output element
 	constexpr int GROUPS = 256 / THREADS;

@@ -14,6 +14,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+// functional form of an fp32-only command on bf16 / fp16 tensors (sm100_backend.cu: widen into the workspace, run `f32`, round back once)
+namespace sm100 {
+int exec_via_f32_rt(ccv_nnc_cmd_exec_f f32, const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context);
+}
 using namespace sm100;
 
 namespace {
@@ -297,13 +301,16 @@ int exec_index_select_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, c
 
 // ------------------------------------------------------------------------------------------------ AdamW
 // inputs (g, a, m, v, [vm]) -> outputs (b, n, u, [um]); g fp32 / bf16 / fp16, everything else fp32; contiguous
+template <int L2>
 __global__ void __launch_bounds__(256) adamw_kernel(const void* __restrict__ g, const int g_kind, const float* __restrict__ a, const float* __restrict__ m, const float* __restrict__ v, const float* __restrict__ vm,
 	float* __restrict__ b, float* __restrict__ n, float* __restrict__ u, float* __restrict__ um, const size_t count, const float scale, const float beta1, const float beta2, const float rate_inv_bias_correction1,
 	const float inv_bias_correction2, const float rate_decay, const float epsilon)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
 	{
-		const float grad = scale * ld_kind(g, i, g_kind);
+		float grad = scale * ld_kind(g, i, g_kind);
+		if (L2)
+			grad += rate_decay * a[i]; // ADAM: the decay is an L2 term of the gradient (adam/ccv_nnc_adam_cpu_ref.c:117-118); rate_decay carries `decay` itself
 		const float mom = beta1 * m[i] + (1.f - beta1) * grad;
 		const float vel = beta2 * v[i] + (1.f - beta2) * grad * grad;
 		n[i] = mom, u[i] = vel;
@@ -314,10 +321,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const void* __restrict__ g, 
 			um[i] = vel_hat;
 		}
 		const float av = a[i];
-		b[i] = av - rate_decay * av - (mom * rate_inv_bias_correction1) / (sqrtf(vel_hat) + epsilon);
+		b[i] = (L2 ? av : av - rate_decay * av) - (mom * rate_inv_bias_correction1) / (sqrtf(vel_hat) + epsilon);
 	}
 }
-int exec_adamw_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+template <int L2>
+int exec_adam_f32(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
 	if (input_size < 4 || output_size < 3 || cmd.info.adam.step < 1)
 		return CCV_NNC_EXEC_INVALID;
@@ -347,9 +355,17 @@ int exec_adamw_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const in
 	const float rate = cmd.info.adam.rate, beta1 = cmd.info.adam.beta1, beta2 = cmd.info.adam.beta2;
 	const float rate_inv_bias_correction1 = rate / (1 - powf(beta1, cmd.info.adam.step));
 	const float inv_bias_correction2 = 1.f / (1 - powf(beta2, cmd.info.adam.step));
-	adamw_kernel<<<grid_for(count, 256), 256, 0, stream_of(stream_context)>>>(inputs[0]->data.u8, g_kind, inputs[1]->data.f32, inputs[2]->data.f32, inputs[3]->data.f32, ams ? vm->data.f32 : 0,
-		outputs[0]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, ams ? um->data.f32 : 0, count, cmd.info.adam.scale, beta1, beta2, rate_inv_bias_correction1, inv_bias_correction2, rate * cmd.info.adam.decay, cmd.info.adam.epsilon);
+	adamw_kernel<L2><<<grid_for(count, 256), 256, 0, stream_of(stream_context)>>>(inputs[0]->data.u8, g_kind, inputs[1]->data.f32, inputs[2]->data.f32, inputs[3]->data.f32, ams ? vm->data.f32 : 0,
+		outputs[0]->data.f32, outputs[1]->data.f32, outputs[2]->data.f32, ams ? um->data.f32 : 0, count, cmd.info.adam.scale, beta1, beta2, rate_inv_bias_correction1, inv_bias_correction2, L2 ? cmd.info.adam.decay : rate * cmd.info.adam.decay, cmd.info.adam.epsilon);
 	return check("adamw") ? CCV_NNC_EXEC_INVALID : CCV_NNC_EXEC_SUCCESS;
+}
+// parameters / moments in half precision (adam/gpu/ccv_nnc_adamw_gpu_ref.cu registers CCV_16F; test/int/nnc/adam.tests.c:300-360): functional form
+template <int L2>
+int exec_adam_any(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size >= 2 && inputs[1] && kind_of(inputs[1]) > 0)
+		return exec_via_f32_rt(exec_adam_f32<L2>, cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
+	return exec_adam_f32<L2>(cmd, hint, flags, inputs, input_size, outputs, output_size, stream_context);
 }
 int exec_no_backward(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
 {
@@ -376,5 +392,7 @@ REGISTER_SM100(CCV_NNC_SWISH_FORWARD) { fill(registry, CCV_32F | CCV_16F | CCV_1
 REGISTER_SM100(CCV_NNC_SWISH_BACKWARD) { fill(registry, CCV_32F | CCV_16F | CCV_16BF, exec_act<1, 1>); }
 REGISTER_SM100(CCV_NNC_INDEX_SELECT_FORWARD) { fill(registry, CCV_32F | CCV_16F | CCV_16BF | CCV_32S, exec_index_select_forw); }
 REGISTER_SM100(CCV_NNC_INDEX_SELECT_BACKWARD) { fill(registry, CCV_32F | CCV_16F | CCV_16BF | CCV_32S, exec_index_select_back); }
-REGISTER_SM100(CCV_NNC_ADAMW_FORWARD) { fill(registry, CCV_32F | CCV_16F | CCV_16BF, exec_adamw_forw); }
+REGISTER_SM100(CCV_NNC_ADAMW_FORWARD) { fill(registry, CCV_32F | CCV_16F | CCV_16BF, exec_adam_any<0>); }
+REGISTER_SM100(CCV_NNC_ADAM_FORWARD) { fill(registry, CCV_32F | CCV_16F | CCV_16BF, exec_adam_any<1>); }
+REGISTER_SM100(CCV_NNC_ADAM_BACKWARD) { fill(registry, CCV_32F | CCV_16F | CCV_16BF, exec_no_backward); }
 REGISTER_SM100(CCV_NNC_ADAMW_BACKWARD) { fill(registry, CCV_32F | CCV_16F | CCV_16BF, exec_no_backward); }

@@ -690,3 +690,9 @@ def CMD_RANDOM_NORMAL_FORWARD(std, mean, **kw):
     c = _simple(abi.CCV_NNC_RANDOM_NORMAL_FORWARD, **kw)
     c.info.blas.a[0], c.info.blas.a[1] = std, mean
     return c
+
+
+def CMD_ADAM_FORWARD(step, rate, beta1, beta2, decay, epsilon, amsgrad=0, scale=1.0, **kw):
+    c = CMD_ADAMW_FORWARD(step, rate, beta1, beta2, decay, epsilon, amsgrad, scale, **kw)
+    c.cmd = abi.CCV_NNC_ADAM_FORWARD
+    return c

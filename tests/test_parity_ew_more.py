@@ -44,8 +44,9 @@ def test_unary_forward_backward(gpu, ref, name):
     st, (h_g,) = gpu_exec(nnc, bwd, None, 0, ins, [_z()])
     assert st == 0
     assert_close(h_g, h_r, 1e-5, name + " backward")
-    if name in ("SIGMOID", "TANH", "EWEXP"):
-        # no incoming gradient = all ones (e.g. sigmoid_cpu_ref.c:57-62)
+    if name == "EWEXP":
+        # no incoming gradient = all ones (ew_cpu_ref.c:1043-1044; CPU_REF's sigmoid / tanh backward dereference g before testing it,
+        # sigmoid_cpu_ref.c:44, so that form has no oracle there)
         ins0 = [None, x, y_r]
         _, (h0_r,) = ref_exec(ref, bwd, None, 0, ins0, [_z()])
         st, (h0_g,) = gpu_exec(nnc, bwd, None, 0, ins0, [_z()])
@@ -157,3 +158,23 @@ def test_masked_fill(gpu, ref, mask_dtype):
     _, (h_r,) = ref_exec(ref, bwd, None, 0, [g, None, mask], [_z(shape)])
     st, (h_g,) = gpu_exec(nnc, bwd, None, 0, [g, None, mask], [_z(shape)])
     assert st == 0 and np.array_equal(h_g, h_r)
+
+
+@pytest.mark.parametrize("n", [100003, 4096])
+def test_random_uniform_and_normal(gpu, n):
+    """RANDOM_UNIFORM / RANDOM_NORMAL (rand/gpu/ccv_nnc_rand_uniform_gpu_ref.cu:33-66): the contract is the distribution and a fresh seed
+    per call from the stream context's generator (the protocol of test/int/nnc/random.tests.c: moments of a large sample)."""
+    nnc = gpu
+    st, (u1,) = gpu_exec(nnc, nnc.CMD_RANDOM_UNIFORM_FORWARD(-2.0, 3.0), None, 0, [], [np.zeros((n,), np.float32)])
+    st2, (u2,) = gpu_exec(nnc, nnc.CMD_RANDOM_UNIFORM_FORWARD(-2.0, 3.0), None, 0, [], [np.zeros((n,), np.float32)])
+    assert st == 0 and st2 == 0
+    assert u1.min() >= -2.0 and u1.max() <= 3.0 and not np.array_equal(u1, u2)
+    tol = 6.0 / np.sqrt(n)
+    assert abs(u1.mean() - 0.5) <= 5 * tol / np.sqrt(12) * 1.0 + 1e-3 and abs(u1.std() - 5 / np.sqrt(12)) <= 0.05
+    assert len(np.unique(u1)) > 0.95 * n
+    st, (g1,) = gpu_exec(nnc, nnc.CMD_RANDOM_NORMAL_FORWARD(2.0, 1.0), None, 0, [], [np.zeros((n,), np.float32)])
+    assert st == 0 and np.isfinite(g1).all()
+    assert abs(g1.mean() - 1.0) <= 2 * tol + 1e-3 and abs(g1.std() - 2.0) <= 0.1
+    # bf16 tensors
+    st, (ub,) = gpu_exec16(nnc, nnc.CMD_RANDOM_UNIFORM_FORWARD(0.0, 1.0), None, 0, [], [np.zeros((n,), np.float32)], abi.CCV_16BF)
+    assert st == 0 and ub.min() >= 0.0 and ub.max() <= 1.0 and abs(ub.mean() - 0.5) <= 0.02
