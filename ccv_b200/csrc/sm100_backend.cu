@@ -912,9 +912,15 @@ bool stage_plan(ccv_nnc_tensor_t* const t, Staged& st)
 }
 
 // upper bound of what the NHWC command requests from the workspace for this geometry
-size_t conv_inner_workspace(const ConvGeom& g, const int kind)
+size_t conv_inner_workspace(const ConvGeom& g, const int kind, const int groups)
 {
 	size_t need = CONTRACT_SCRATCH_BYTES;
+	if (groups > 1 && g.C % groups == 0 && g.K % groups == 0)
+	{
+		// conv_grouped_tc: split-K scratch + one group's dense activations and results
+		const size_t es = kind_size(kind), nx = (size_t)g.N * g.H * g.W * (g.C / groups), ny = (size_t)g.N * g.P * g.Q * (g.K / groups);
+		need += ((nx * es + 255) & ~(size_t)255) + ((ny * es + 255) & ~(size_t)255);
+	}
 	if (g.C % (kind == 0 ? 4 : 8) != 0)
 		need = std::max(need, kind == 0 ? conv_im2col_workspace_bytes(g) : conv_im2col_workspace_bytes(g, kind));
 	need = std::max(need, colsum_workspace_bytes(g.K));
@@ -1007,7 +1013,7 @@ size_t conv_staged_inner(const ccv_nnc_cmd_t& cmd, const ccv_nnc_hint_t& hint, c
 	ConvGeom g;
 	if (!act || !filt || !res || kind_of(act) < 0 || !conv_geom(cmd, hint, view_of(act), view_of(filt), view_of(res), g))
 		return (size_t)-1;
-	return conv_inner_workspace(g, kind_of(act));
+	return conv_inner_workspace(g, kind_of(act), cmd.info.convolution.groups > 1 ? cmd.info.convolution.groups : 1);
 }
 template <int BACKWARD>
 int conv_staged(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
