@@ -994,6 +994,12 @@ int nchw_staged(const ccv_nnc_cmd_exec_f exec, const staged_inner_f inner_of, co
 	const int rc = exec(cmd, hint, flags, in, input_size, out, output_size, stream_context);
 	if (rc != CCV_NNC_EXEC_SUCCESS)
 		return rc;
+	if (ccv_nnc_stream_context_get_workspace(stream_context, 1, CCV_TENSOR_GPU_MEMORY) != (void*)ws)
+	{
+		// the NHWC command asked for more than `inner`: the workspace moved and the staged tensors with it (a bound above is wrong)
+		set_last_error("staged convolution / pooling: workspace moved under the staged tensors", cudaErrorInvalidValue);
+		return CCV_NNC_EXEC_INVALID;
+	}
 	for (int i = 0; i < 3; i++)
 		if (slot_out[i] >= 0)
 		{
@@ -2040,7 +2046,12 @@ int via_f32(const ccv_nnc_cmd_exec_f F32, const ccv_nnc_cmd_t cmd, const ccv_nnc
 	for (int i = 0; i < output_size; i++)
 		if (!(out[i] = shadow_of(outputs[i], 1)) && outputs[i])
 			return CCV_NNC_EXEC_INVALID;
-	const size_t inner = (size_t)4 << 20; // the fp32 forms of these commands ask for at most a few partial rows
+	// what the fp32 command itself may ask the workspace for: partial rows, or (MUL backward with broadcasting) one temporary of
+	// the full index space, which is the size of its largest operand
+	size_t largest = 0;
+	for (int j = 0; j < n; j++)
+		largest = std::max(largest, (sh[j].n * sizeof(float) + 255) & ~(size_t)255);
+	const size_t inner = ((size_t)4 << 20) + largest;
 	unsigned char* const ws = (unsigned char*)ccv_nnc_stream_context_get_workspace(stream_context, inner + staging, CCV_TENSOR_GPU_MEMORY);
 	if (!ws)
 		return CCV_NNC_EXEC_OOM;
@@ -2055,6 +2066,11 @@ int via_f32(const ccv_nnc_cmd_exec_f F32, const ccv_nnc_cmd_t cmd, const ccv_nnc
 	const int rc = F32(cmd, hint, flags, in, input_size, out, output_size, stream_context);
 	if (rc != CCV_NNC_EXEC_SUCCESS)
 		return rc;
+	if (ccv_nnc_stream_context_get_workspace(stream_context, 1, CCV_TENSOR_GPU_MEMORY) != (void*)ws)
+	{
+		set_last_error("functional 16-bit form: the fp32 command moved the workspace under the widened tensors", cudaErrorInvalidValue);
+		return CCV_NNC_EXEC_INVALID;
+	}
 	for (int j = 0; j < n; j++)
 		if (sh[j].is_out)
 			RC(narrow_matrix(s, sh[j].t.data.f32, sh[j].orig->data.u8, sh[j].kind, (long long)sh[j].n, 1, 1, (int)sh[j].n, 0));

@@ -1,0 +1,60 @@
+"""SURVEY.md 8f-1, the drop-in proof as tests.  integration/Makefile (run by __graft_entry__.build() where /root/reference exists) builds
+the UNMODIFIED reference -- every layer of lib/nnc above the backends, its CPU backends and its own CUDA compatibility layer --
+with the 8-backend registry files, links it with this repository's backend objects (no nnc_host.o: ccv_nnc_cmd_exec, tensors,
+stream contexts, the graph runner and ccv_cnnp_model are the reference's) and compiles the reference's own test programs unmodified
+with the GPU backend names reading CCV_NNC_BACKEND_GPU_SM100.  The binaries travel with the tree; nothing here reads /root/reference.
+
+CPU: the reference's unit programs (gemm / forward / backward / attention known answers) pass against the patched registry, i.e. the
+8-slot backend hash and the re-slotted registration calls leave the CPU backends where ccv_nnc_cmd_exec finds them.
+GPU: the reference's integration programs whose cases are deterministic and quick -- ccv_cnnp_model training (cnnp.core),
+statically scheduled multi-stream graphs with while / case-of (schedule), SGD / ADAM(W) in float, half and mixed precision, index
+select, tensor transfer, datatype conversion, concat, leaky relu, GELU, SWISH, transforms, reductions, upsample -- pass on this
+backend as the only GPU backend of the library.  (cudnn.tests / cublas.tests, minutes of CPU_REF convolutions, are run by
+integration/run_reference_tests.py: profiles/r02_dropin_reference_tests.md.)"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "integration", "_build")
+RUNNER = os.path.join(ROOT, "integration", "run_reference_tests.py")
+
+
+def _built(programs):
+    return os.path.exists(os.path.join(BUILD, "libccv_dropin.so")) and os.path.exists(os.path.join(BUILD, "cases.json")) and all(os.path.exists(os.path.join(BUILD, p + ".tests")) for p in programs)
+
+
+def _run(only, budget, tmp_path):
+    out = str(tmp_path / "report.json")
+    p = subprocess.run([sys.executable, RUNNER, "--only", ",".join(only), "--budget-s", str(budget), "--case-timeout", "60", "--out", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=budget + 60)
+    assert p.returncode == 0, p.stdout.decode()[-2000:]
+    return json.load(open(out))
+
+
+def test_reference_unit_programs_pass_on_the_8_backend_registry(tmp_path):
+    programs = ["unit.gemm", "unit.forward", "unit.backward", "unit.attention"]
+    if not _built(programs):
+        pytest.skip("integration/_build is not built (make -C integration; needs the reference sources)")
+    rep = _run(programs, 240, tmp_path)
+    assert rep["total"]["FAIL"] == 0 and rep["total"]["CRASH"] == 0, rep
+    assert rep["total"]["PASS"] == 44, rep["total"]  # 18 + 17 + 3 + 6 known-answer cases
+
+
+# program -> cases that passed on a B200 with this build (profiles/r02_dropin_reference_tests.md)
+GPU_PROGRAMS = {"int.cnnp.core": 4, "int.schedule": 5, "int.sgd": 6, "int.index": 9, "int.tensor": 7, "int.datatype": 1, "int.concat": 2, "int.leaky_relu": 4,
+                "int.gelu": 8, "int.swish": 4, "int.transform": 9, "int.adam": 12, "int.reduce": 9, "int.upsample": 9}
+
+
+@pytest.mark.gpu
+def test_reference_integration_programs_pass_on_the_dropin_build(gpu, tmp_path):
+    if not _built(list(GPU_PROGRAMS)):
+        pytest.skip("integration/_build is not built (make -C integration; needs the reference sources)")
+    rep = _run(list(GPU_PROGRAMS), 300, tmp_path)
+    bad = {p: (r["failed"], list(r["crashed"])) for p, r in rep["programs"].items() if r["failed"] or r["crashed"]}
+    assert not bad, json.dumps({p: {"failed": r.get("fail_detail"), "crashed": r.get("crashed")} for p, r in rep["programs"].items() if p in bad}, indent=1)[-3000:]
+    for prog, want in GPU_PROGRAMS.items():
+        got = rep["programs"][prog + ".tests"]["tally"]["PASS"]
+        assert got >= want, (prog, got, want, rep["programs"][prog + ".tests"]["skipped"])
