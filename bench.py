@@ -387,6 +387,37 @@ def run_sdpa_cfg5(args):
     return out
 
 
+def run_reference_cnnp(args):
+    """BASELINE.json configs[2] through the REFERENCE'S OWN public API: integration/cnnp_resnet50_bench.c builds the same ResNet-50 v1d
+    with ccv_cnnp_* and trains it with ccv_cnnp_model_fit; linked against integration/_build/libccv_dropin.so every layer above the
+    backend is the unmodified reference (model zoo, symbolic graph, autograd, memory planner, graph runner: one ccv_nnc_cmd_exec per node,
+    no fusion pass, no CUDA graph) and every GPU command is served by CCV_NNC_BACKEND_GPU_SM100.  Runs as a child process after this
+    process has finished its own measurements; whatever goes wrong there is reported as `unavailable`, never raised."""
+    import subprocess
+    exe = os.path.join(ROOT, "integration", "_build", "cnnp_resnet50_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "integration/_build/cnnp_resnet50_bench is not built (make -C integration; needs the reference sources)"}
+    steps = max(1, min(int(args.steps), 5))
+    cmd = [exe, "--device", "gpu", "--batch", str(args.batch), "--image", str(args.image), "--steps", str(steps), "--warmup", "2"]
+    try:
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=150)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "timed out after 150 s"}
+    except Exception as e:  # noqa: BLE001 -- a side measurement must not take the benchmark line down
+        return {"unavailable": repr(e)[:300]}
+    lines = [ln for ln in p.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
+    if p.returncode != 0 or not lines:
+        return {"unavailable": "exit %d: %s" % (p.returncode, p.stderr.decode(errors="replace").strip()[-400:])}
+    try:
+        r = json.loads(lines[-1])
+    except ValueError:
+        return {"unavailable": "unparsable output: " + lines[-1][:200]}
+    r["note"] = ("the unmodified reference L2-L5 (ccv_cnnp_model_fit -> its symbolic graph / autograd / graph runner) on this backend as the only GPU "
+                 "backend of the library; host-timed around ccv_nnc_stream_context_wait; inputs resident on the device")
+    return r
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -451,6 +482,7 @@ def main():
                 variants[name]["roofline"], variants[name]["per_op"] = v["roofline"], v["per_op"]
         if world == 1 and rank == 0:
             variants["sdpa_cfg5"] = run_sdpa_cfg5(args)
+            variants["reference_cnnp_resnet50"] = run_reference_cnnp(args)
         out["variants"] = variants
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -60,3 +60,29 @@ def test_reference_integration_programs_pass_on_the_dropin_build(gpu, tmp_path):
     for prog, want in GPU_PROGRAMS.items():
         got = rep["programs"][prog + ".tests"]["tally"]["PASS"]
         assert got >= want, (prog, got, want, rep["programs"][prog + ".tests"]["skipped"])
+
+
+def test_cnnp_resnet50_program_trains_on_the_cpu_backends():
+    """integration/cnnp_resnet50_bench.c (a ccv_cnnp_model ResNet-50 v1d through ccv_cnnp_model_compile / _fit, the reference's public API)
+    on CPU tensors: the program's own logic -- model definition, compile, fit loop, loss read-back -- checked where no GPU is needed."""
+    exe = os.path.join(BUILD, "cnnp_resnet50_bench")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build is not built (make -C integration; needs the reference sources)")
+    p = subprocess.run([exe, "--device", "cpu", "--batch", "2", "--image", "32", "--steps", "3", "--warmup", "1", "--classes", "10"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert p.returncode == 0, p.stderr.decode()[-1000:]
+    r = json.loads(p.stdout.decode().strip().splitlines()[-1])
+    assert r["device"] == "cpu" and r["images_per_sec"] > 0
+    assert 0 < r["last_loss"] < r["first_loss"], r  # four SGD steps on one fixed batch lower its loss
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first hardware run of this program: it was written after the builder's GPU budget was spent (its logic is checked on the "
+                   "CPU backends above); bench.py reports it as variants.reference_cnnp_resnet50")
+def test_cnnp_resnet50_program_trains_on_the_dropin_build(gpu):
+    exe = os.path.join(BUILD, "cnnp_resnet50_bench")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build is not built")
+    p = subprocess.run([exe, "--device", "gpu", "--batch", "8", "--image", "64", "--steps", "3", "--warmup", "1", "--classes", "100"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240)
+    assert p.returncode == 0, p.stderr.decode()[-1500:]
+    r = json.loads(p.stdout.decode().strip().splitlines()[-1])
+    assert r["device"] == "gpu" and 0 < r["last_loss"] < r["first_loss"], r
