@@ -6,7 +6,7 @@
  * GPU backend in that library).  It is a user program of ccv, not part of the backend: what `bin/nnc/imagenet.c` would do without its
  * data pipeline.
  *
- *   cnnp_resnet50_bench --device gpu|cpu --batch N --image S --steps K --warmup W [--classes C] [--half]
+ *   cnnp_resnet50_bench --device gpu|cpu --batch N --image S --steps K --warmup W [--classes C] [--lr R] [--seed S]
  *
  * Prints one JSON object: images/s over K timed steps (ccv_nnc_stream_context_wait on both sides), ms/step, the first and last
  * losses (-log p[label] averaged over the batch, from the model's softmax output) and ccv_cnnp_model_memory_size.  --device cpu runs
@@ -92,7 +92,8 @@ static double batch_loss(ccv_nnc_tensor_t* const device_out, ccv_nnc_tensor_t* c
 
 int main(int argc, char** argv)
 {
-	int gpu = 1, batch = 256, image = 224, steps = 10, warmup = 3, classes = 1000, i;
+	int gpu = 1, batch = 256, image = 224, steps = 10, warmup = 3, classes = 1000, seed = 0, i;
+	float lr = 0.01f;
 	for (i = 1; i < argc; i++)
 	{
 		if (!strcmp(argv[i], "--device") && i + 1 < argc) gpu = strcmp(argv[++i], "cpu") != 0;
@@ -101,9 +102,13 @@ int main(int argc, char** argv)
 		else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--classes") && i + 1 < argc) classes = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--lr") && i + 1 < argc) lr = (float)atof(argv[++i]);
+		else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = atoi(argv[++i]);
 		else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
 	}
 	ccv_nnc_init();
+	if (seed) /* the parameter initialisers draw from the calling thread's generator (lib/nnc/ccv_nnc_stream.c:247-281) */
+		ccv_nnc_stream_context_set_seed(0, (uint32_t)seed);
 	if (gpu && ccv_nnc_device_count(CCV_STREAM_CONTEXT_GPU) < 1)
 	{
 		printf("{\"unavailable\": \"no GPU device\"}\n");
@@ -114,7 +119,7 @@ int main(int argc, char** argv)
 	const ccv_nnc_tensor_param_t x_params = gpu ? GPU_TENSOR_NHWC(000, 32F, batch, image, image, 3) : CPU_TENSOR_NHWC(32F, batch, image, image, 3);
 	const ccv_nnc_tensor_param_t fit_params = gpu ? GPU_TENSOR_NHWC(000, 32F, batch, classes) : CPU_TENSOR_NHWC(32F, batch, classes);
 	/* nesterov SGD with the 1 / batch gradient scale, as bin/nnc/imagenet.c:316 */
-	ccv_cnnp_model_compile(model, &x_params, 1, CMD_SGD_FORWARD(1, 0.01, 1. / batch, 1e-4, 0.9, 0), CMD_CATEGORICAL_CROSSENTROPY_FORWARD());
+	ccv_cnnp_model_compile(model, &x_params, 1, CMD_SGD_FORWARD(1, lr, 1. / batch, 1e-4, 0.9, 0), CMD_CATEGORICAL_CROSSENTROPY_FORWARD());
 	ccv_cnnp_model_set_workspace_size(model, 1llu * 1024 * 1024 * 1024);
 	/* synthetic batch: U(0, 1) pixels, one-hot labels; built on the host, moved once */
 	ccv_nnc_tensor_t* const hx = ccv_nnc_tensor_new(0, CPU_TENSOR_NHWC(32F, batch, image, image, 3), 0);

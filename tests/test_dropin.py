@@ -68,7 +68,9 @@ def test_cnnp_resnet50_program_trains_on_the_cpu_backends():
     exe = os.path.join(BUILD, "cnnp_resnet50_bench")
     if not os.path.exists(exe):
         pytest.skip("integration/_build is not built (make -C integration; needs the reference sources)")
-    p = subprocess.run([exe, "--device", "cpu", "--batch", "2", "--image", "32", "--steps", "3", "--warmup", "1", "--classes", "10"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    # 64 x 64 images: at 32 x 32 the last stage is 1 x 1 and its batch norms see 8 values; some random initialisations diverge there on
+    # the reference's CPU backends (loss -> -log 1e-30), which says nothing about this program
+    p = subprocess.run([exe, "--device", "cpu", "--batch", "8", "--image", "64", "--steps", "3", "--warmup", "1", "--classes", "10", "--lr", "0.002", "--seed", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert p.returncode == 0, p.stderr.decode()[-1000:]
     r = json.loads(p.stdout.decode().strip().splitlines()[-1])
     assert r["device"] == "cpu" and r["images_per_sec"] > 0
@@ -82,7 +84,7 @@ def test_cnnp_resnet50_program_trains_on_the_dropin_build(gpu):
     exe = os.path.join(BUILD, "cnnp_resnet50_bench")
     if not os.path.exists(exe):
         pytest.skip("integration/_build is not built")
-    p = subprocess.run([exe, "--device", "gpu", "--batch", "8", "--image", "64", "--steps", "3", "--warmup", "1", "--classes", "100"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240)
+    p = subprocess.run([exe, "--device", "gpu", "--batch", "32", "--image", "64", "--steps", "3", "--warmup", "1", "--classes", "100", "--lr", "0.002", "--seed", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240)
     assert p.returncode == 0, p.stderr.decode()[-1500:]
     r = json.loads(p.stdout.decode().strip().splitlines()[-1])
     assert r["device"] == "gpu" and 0 < r["last_loss"] < r["first_loss"], r
