@@ -40,3 +40,36 @@ def test_host_dispatch_goes_through_the_generated_tables():
         text = open(os.path.join(ROOT, "integration", f)).read()
         assert "CCV_NNC_BACKEND_GPU_SM100" in text
     assert "CCV_NNC_BACKEND_COUNT = 8" in open(os.path.join(ROOT, "integration", "ccv_nnc_backend.h")).read()
+
+
+def test_patched_cmd_inc_reslots_every_registration_call(tmp_path):
+    """integration/patch_cmd_inc.py (what build-cmd.rb would regenerate for an 8th backend): every `_register_command_X_backend_Y` call of the
+    reference's generated file lands on the slot the 8-slot hash gives Y, the command slot is untouched, backend_init_map is ordered by
+    slot (lib/nnc/ccv_nnc_cmd.c:61-66 requires backend_init_map[ph(b)].backend == b) and the 92 SM100 registrations are present."""
+    import re
+    src = "/root/reference/lib/nnc/cmd/ccv_nnc_cmd.inc"
+    if not os.path.exists(src):
+        pytest.skip("the reference tree is only present in the build container")
+    dst = str(tmp_path / "ccv_nnc_cmd.inc")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "patch_cmd_inc.py"), src, dst], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout
+    text, ref = open(dst).read(), open(src).read()
+    backends = re.findall(r'\{\.name = "(CCV_NNC_BACKEND_[A-Z0-9_]+)", \.backend = (0x[0-9a-f]+)\}', text)
+    assert len(backends) == 8
+
+    def ph8(b):  # integration/ccv_nnc_cmd_backend.inc
+        return ((b >> 2) % 8) if (b % 2 == 0) else ((b >> 9) % 8)
+    for slot, (name, ident) in enumerate(backends):
+        assert ph8(int(ident, 16)) == slot, (name, slot)
+    slot_of = {name: i for i, (name, _) in enumerate(backends)}
+    call = re.compile(r"_register_command_(CCV_NNC_[A-Z0-9_]+?)_backend_(CCV_NNC_BACKEND_[A-Z0-9_]+)\(&\(init_map\[(\d+)\]\.backends\[(\d+)\]\)\);")
+    new_calls, old_calls = call.findall(text), call.findall(ref)
+    assert len(old_calls) == 334 and len(new_calls) == 334 + 92
+    for cmd, backend, i, j in new_calls:
+        assert int(j) == slot_of[backend], (cmd, backend, j)
+    # the command slot of every pre-existing call is the reference's
+    assert sorted((c, b, i) for c, b, i, _ in old_calls) == sorted((c, b, i) for c, b, i, _ in new_calls if b != "CCV_NNC_BACKEND_GPU_SM100")
+    # an SM100 call uses the command slot its command already has
+    cmd_slot = {c: i for c, _, i, _ in old_calls}
+    sm100 = [(c, i) for c, b, i, _ in new_calls if b == "CCV_NNC_BACKEND_GPU_SM100"]
+    assert len(sm100) == 92 and all(cmd_slot[c] == i for c, i in sm100)
