@@ -34,7 +34,7 @@ CMD_IDS = dict(
     ADAMW=0x4f5d4870, GELU=0xb1527ab8, SWISH=0x583d90c2, INDEX_SELECT=0x7ee7771e,
     SIGMOID=0xf2f69650, TANH=0x6a62be30, LEAKY_RELU=0x507144e0, EWEXP=0xd784b170, EWLOG=0xf4191bf2, EWSQRT=0x8870a61e, CLAMP=0x2640d854,
     EWDIV=0x1cd2fa18, REDUCE_SUM=0x52970f06, REDUCE_MEAN=0xf23556c6, REDUCE_MAX=0x80f1a506, REDUCE_MIN=0x6785ef96, REDUCE_NORM2=0xb3034e16,
-    MASKED_FILL=0x7f992d84, ADAM=0xe30099dc, RANDOM_UNIFORM=0xa0cd1d5e, RANDOM_NORMAL=0x7062c8b4,
+    MASKED_FILL=0x7f992d84, DROPOUT=0x7f2dc3e4, ADAM=0xe30099dc, RANDOM_UNIFORM=0xa0cd1d5e, RANDOM_NORMAL=0x7062c8b4,
 )
 for _k, _v in CMD_IDS.items():
     globals()["CCV_NNC_%s_FORWARD" % _k] = _v
@@ -127,10 +127,14 @@ class _LeakyRelu(C.Structure):
     _fields_ = [("negative_slope", C.c_float)]
 
 
+class _Dropout(C.Structure):
+    _fields_ = [("p", C.c_float), ("entirety", C.c_int)]
+
+
 class _CmdUnion(C.Union):
     _fields_ = [("convolution", _Convolution), ("pool", _Pool), ("bnorm", _Bnorm), ("lnorm", _Lnorm), ("gnorm", _Gnorm), ("rmsnorm", _Rmsnorm),
                 ("sgd", _Sgd), ("adam", _Adam), ("gelu", _Gelu), ("blas", _Blas), ("label_smoothing", _LabelSmoothing), ("reduce", _Reduce), ("transpose", _Transpose),
-                ("upsample", _Upsample), ("clamp", _Clamp), ("leaky_relu", _LeakyRelu), ("scaled_dot_product_attention", _Sdpa), ("userdata", C.c_void_p)]
+                ("upsample", _Upsample), ("clamp", _Clamp), ("leaky_relu", _LeakyRelu), ("dropout", _Dropout), ("scaled_dot_product_attention", _Sdpa), ("userdata", C.c_void_p)]
 
 
 class CmdParam(C.Structure):

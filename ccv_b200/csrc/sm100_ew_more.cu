@@ -615,6 +615,107 @@ int exec_random(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int fl
 	return check("random fill") ? CCV_NNC_EXEC_INVALID : CCV_NNC_EXEC_SUCCESS;
 }
 
+// ------------------------------------------------------------------------------------------------ dropout
+// dropout/ccv_nnc_dropout_cpu_ref.c:16-215: b = mask ? 0 : a / (1 - p), mask[i] = (u_i <= p) as one byte per element in the reserved
+// second output (dropout/ccv_nnc_dropout.c:21-44 sizes it in 128-byte lines, never below one byte per element); `entirety` = one
+// decision for the whole tensor, kept as an int32 in mask[0].  Backward (g, -, -, -, mask): h = mask ? 0 : g / (1 - p).  The
+// uniforms are the Philox stream of the random-fill commands above, keyed by the stream context's seed: as for those, the contract
+// is the distribution and the forward / backward consistency of the mask (there is no bit-level parity to define
+// against the reference's dSFMT / cuDNN generator states).
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(const T* __restrict__ a, T* __restrict__ b, uint8_t* __restrict__ mask, const size_t n, const uint32_t seed, const float p, const float inv_p, const int entirety)
+{
+	if (entirety)
+	{
+		uint32_t r[4];
+		philox4x32_10(0, seed, r);
+		const int drop = u01(r[0]) <= p;
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+			*reinterpret_cast<int32_t*>(mask) = drop;
+		for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+			stf(b + i, drop ? 0.f : ldf(a + i) * inv_p);
+		return;
+	}
+	const size_t quads = (n + 3) / 4;
+	for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < quads; q += (size_t)gridDim.x * blockDim.x)
+	{
+		uint32_t r[4];
+		philox4x32_10(q, seed, r);
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			const size_t i = q * 4 + j;
+			if (i < n)
+			{
+				const int drop = u01(r[j]) <= p;
+				mask[i] = (uint8_t)drop;
+				stf(b + i, drop ? 0.f : ldf(a + i) * inv_p);
+			}
+		}
+	}
+}
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(const T* __restrict__ g, const uint8_t* __restrict__ mask, T* __restrict__ h, const size_t n, const float inv_p, const int entirety)
+{
+	const int all = entirety ? *reinterpret_cast<const int32_t*>(mask) : 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		stf(h + i, (entirety ? all : mask[i]) ? 0.f : ldf(g + i) * inv_p);
+}
+size_t bytes_of(const ccv_nnc_tensor_t* const t)
+{
+	const int dt = CCV_GET_DATA_TYPE(t->info.datatype);
+	return count_of(t) * (dt == CCV_64F || dt == CCV_64S ? 8 : dt == CCV_16F || dt == CCV_16BF ? 2 : dt == CCV_8U ? 1 : 4);
+}
+int exec_dropout_forw(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 1 || output_size < 2 || !inputs[0] || !outputs[0] || !outputs[1])
+		return CCV_NNC_EXEC_INVALID;
+	const int kind = kind_of(inputs[0]), entirety = cmd.info.dropout.entirety;
+	if (kind < 0 || !ok_operand(outputs[0], inputs[0], kind) || !CCV_IS_TENSOR_CONTIGUOUS(inputs[0]) || !CCV_IS_TENSOR_CONTIGUOUS(outputs[1]))
+		return CCV_NNC_EXEC_INVALID;
+	const size_t n = count_of(inputs[0]);
+	if (bytes_of(outputs[1]) < (entirety ? sizeof(int32_t) : n))
+		return CCV_NNC_EXEC_INVALID;
+	if (n == 0)
+		return CCV_NNC_EXEC_SUCCESS;
+	const float p = cmd.info.dropout.p, inv_p = 1.f / (1.f - p);
+	const uint32_t seed = ccv_nnc_stream_context_genrand_uint32(stream_context);
+	cudaStream_t s = stream_of(stream_context);
+	const int grid = grid_for(entirety ? n : (n + 3) / 4, 256);
+	uint8_t* const mask = outputs[1]->data.u8;
+	if (kind == 0)
+		dropout_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)inputs[0]->data.u8, (float*)outputs[0]->data.u8, mask, n, seed, p, inv_p, entirety);
+	else if (kind == 1)
+		dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)inputs[0]->data.u8, (__nv_bfloat16*)outputs[0]->data.u8, mask, n, seed, p, inv_p, entirety);
+	else
+		dropout_fwd_kernel<__half><<<grid, 256, 0, s>>>((const __half*)inputs[0]->data.u8, (__half*)outputs[0]->data.u8, mask, n, seed, p, inv_p, entirety);
+	return check("dropout") ? CCV_NNC_EXEC_INVALID : CCV_NNC_EXEC_SUCCESS;
+}
+int exec_dropout_back(const ccv_nnc_cmd_t cmd, const ccv_nnc_hint_t hint, const int flags, ccv_nnc_tensor_t* const* const inputs, const int input_size, ccv_nnc_tensor_t* const* const outputs, const int output_size, ccv_nnc_stream_context_t* const stream_context)
+{
+	if (input_size < 5 || output_size < 1 || !inputs[0] || !inputs[4] || !outputs[0])
+		return CCV_NNC_EXEC_INVALID;
+	const int kind = kind_of(inputs[0]), entirety = cmd.info.dropout.entirety;
+	if (kind < 0 || !ok_operand(outputs[0], inputs[0], kind) || !CCV_IS_TENSOR_CONTIGUOUS(inputs[0]) || !CCV_IS_TENSOR_CONTIGUOUS(inputs[4]))
+		return CCV_NNC_EXEC_INVALID;
+	const size_t n = count_of(inputs[0]);
+	if (bytes_of(inputs[4]) < (entirety ? sizeof(int32_t) : n))
+		return CCV_NNC_EXEC_INVALID;
+	if (n == 0)
+		return CCV_NNC_EXEC_SUCCESS;
+	const float inv_p = 1.f / (1.f - cmd.info.dropout.p);
+	cudaStream_t s = stream_of(stream_context);
+	const int grid = grid_for(n, 256);
+	const uint8_t* const mask = inputs[4]->data.u8;
+	if (kind == 0)
+		dropout_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)inputs[0]->data.u8, mask, (float*)outputs[0]->data.u8, n, inv_p, entirety);
+	else if (kind == 1)
+		dropout_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)inputs[0]->data.u8, mask, (__nv_bfloat16*)outputs[0]->data.u8, n, inv_p, entirety);
+	else
+		dropout_bwd_kernel<__half><<<grid, 256, 0, s>>>((const __half*)inputs[0]->data.u8, mask, (__half*)outputs[0]->data.u8, n, inv_p, entirety);
+	return check("dropout backward") ? CCV_NNC_EXEC_INVALID : CCV_NNC_EXEC_SUCCESS;
+}
+
 void fill(ccv_nnc_cmd_backend_registry_t* const registry, const int datatypes, const ccv_nnc_cmd_exec_f exec)
 {
 	registry->tensor_formats = CCV_TENSOR_FORMAT_NCHW | CCV_TENSOR_FORMAT_NHWC | CCV_TENSOR_FORMAT_CHWN;
@@ -662,3 +763,5 @@ REGISTER_SM100(CCV_NNC_RANDOM_UNIFORM_FORWARD) { fill(registry, F3, exec_random<
 REGISTER_SM100(CCV_NNC_RANDOM_UNIFORM_BACKWARD) { fill(registry, F3, exec_random<0>); }
 REGISTER_SM100(CCV_NNC_RANDOM_NORMAL_FORWARD) { fill(registry, F3, exec_random<1>); }
 REGISTER_SM100(CCV_NNC_RANDOM_NORMAL_BACKWARD) { fill(registry, F3, exec_random<1>); }
+REGISTER_SM100(CCV_NNC_DROPOUT_FORWARD) { fill(registry, F3, exec_dropout_forw); }
+REGISTER_SM100(CCV_NNC_DROPOUT_BACKWARD) { fill(registry, F3, exec_dropout_back); }

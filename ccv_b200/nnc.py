@@ -696,3 +696,15 @@ def CMD_ADAM_FORWARD(step, rate, beta1, beta2, decay, epsilon, amsgrad=0, scale=
     c = CMD_ADAMW_FORWARD(step, rate, beta1, beta2, decay, epsilon, amsgrad, scale, **kw)
     c.cmd = abi.CCV_NNC_ADAM_FORWARD
     return c
+
+
+def CMD_DROPOUT_FORWARD(p, entirety=0, **kw):
+    c = _simple(abi.CCV_NNC_DROPOUT_FORWARD, **kw)
+    c.info.dropout.p, c.info.dropout.entirety = p, entirety
+    return c
+
+
+def CMD_DROPOUT_BACKWARD(p, entirety=0, **kw):
+    c = _simple(abi.CCV_NNC_DROPOUT_BACKWARD, **kw)
+    c.info.dropout.p, c.info.dropout.entirety = p, entirety
+    return c

@@ -4,8 +4,9 @@ with the 8-backend registry files, links it with this repository's backend objec
 stream contexts, the graph runner and ccv_cnnp_model are the reference's) and compiles the reference's own test programs unmodified
 with the GPU backend names reading CCV_NNC_BACKEND_GPU_SM100.  The binaries travel with the tree; nothing here reads /root/reference.
 
-CPU: the reference's unit programs (gemm / forward / backward / attention known answers) pass against the patched registry, i.e. the
-8-slot backend hash and the re-slotted registration calls leave the CPU backends where ccv_nnc_cmd_exec finds them.
+CPU: the reference's 55 unit programs (386 cases: known-answer GEMM / convolution / attention, autograd, symbolic-graph compile and
+simplification, while / case-of, dynamic graphs, cnnp core, dataframe, tensor IO) pass against the patched registry, i.e. the 8-slot
+backend hash and the re-slotted registration calls leave every CPU backend where ccv_nnc_cmd_exec and the upper layers find it.
 GPU: the reference's integration programs whose cases are deterministic and quick -- ccv_cnnp_model training (cnnp.core),
 statically scheduled multi-stream graphs with while / case-of (schedule), SGD / ADAM(W) in float, half and mixed precision, index
 select, tensor transfer, datatype conversion, concat, leaky relu, GELU, SWISH, transforms, reductions, upsample -- pass on this
@@ -34,13 +35,25 @@ def _run(only, budget, tmp_path):
     return json.load(open(out))
 
 
+# unit cases that cannot pass here for reasons unrelated to the registry: they read files under test/unit/nnc/data by a relative path (the
+# programs run from integration/_build) or map a file they wrote there; and one cnnp case that segfaults identically when the same test
+# source is linked against the pristine 7-backend CPU build of the reference (oracle/_ref/libccv_ref.so) in this toolchain
+UNIT_KNOWN = {"read long text from csv", "read Windows csv", "read csv include header", "read a larger csv file", "read a csv file", "tensor mapped from file",
+              "LoRA fine-tuning MLP with GELU, set is_trainable to false and with gradient checkpointing"}
+
+
 def test_reference_unit_programs_pass_on_the_8_backend_registry(tmp_path):
-    programs = ["unit.gemm", "unit.forward", "unit.backward", "unit.attention"]
-    if not _built(programs):
+    """all 55 unit programs of the reference (test/unit/nnc/makefile TARGETS minus cblas): autograd, symbolic graph compile / simplify /
+    while / case-of, dynamic graph, cnnp core, dataframe, tensor IO, every CPU command family"""
+    if not _built(["unit.gemm", "unit.cnnp.core", "unit.symbolic.graph", "unit.dynamic.graph", "unit.while"]):
         pytest.skip("integration/_build is not built (make -C integration; needs the reference sources)")
-    rep = _run(programs, 240, tmp_path)
-    assert rep["total"]["FAIL"] == 0 and rep["total"]["CRASH"] == 0, rep
-    assert rep["total"]["PASS"] == 44, rep["total"]  # 18 + 17 + 3 + 6 known-answer cases
+    rep = _run(["unit."], 600, tmp_path)
+    crashed = {k for r in rep["programs"].values() for k in r["crashed"]}
+    assert rep["total"]["FAIL"] == 0, {p: r["fail_detail"] for p, r in rep["programs"].items() if r["failed"]}
+    assert crashed <= UNIT_KNOWN, crashed - UNIT_KNOWN
+    assert rep["total"]["PASS"] >= 380, rep["total"]  # 386 on the build container
+    for prog, want in (("unit.gemm", 18), ("unit.forward", 17), ("unit.backward", 3), ("unit.attention", 6), ("unit.dynamic.graph", 36), ("unit.while", 12)):
+        assert rep["programs"][prog + ".tests"]["tally"]["PASS"] == want, (prog, rep["programs"][prog + ".tests"]["tally"])
 
 
 # program -> least number of cases that must PASS (none may FAIL or crash).  The counts are those of the whole-program B200 run of this

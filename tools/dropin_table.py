@@ -24,7 +24,7 @@ def main(out, paths):
             for k, v in r.get("crashed", {}).items():
                 m[k] = ("CRASH", v)
     total = {}
-    lines = ["| program (test/int/nnc/*.tests.c of the reference, unmodified) | PASS | SKIP | FAIL | CRASH |", "|---|---|---|---|---|"]
+    lines = ["| program (test/{int,unit}/nnc/*.tests.c of the reference, unmodified) | PASS | SKIP | FAIL | CRASH |", "|---|---|---|---|---|"]
     for prog in sorted(merged):
         t = {s: sum(1 for v in merged[prog].values() if v[0] == s) for s in ("PASS", "SKIP", "FAIL", "CRASH")}
         for s, n in t.items():
