@@ -100,13 +100,15 @@ def test_cnnp_resnet50_program_trains_on_the_cpu_backends():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run of this program: it was written after the builder's GPU budget was spent (its logic is checked on the "
-                   "CPU backends above); bench.py reports it as variants.reference_cnnp_resnet50")
 def test_cnnp_resnet50_program_trains_on_the_dropin_build(gpu):
     exe = os.path.join(BUILD, "cnnp_resnet50_bench")
     if not os.path.exists(exe):
         pytest.skip("integration/_build is not built")
-    p = subprocess.run([exe, "--device", "gpu", "--batch", "32", "--image", "64", "--steps", "3", "--warmup", "1", "--classes", "100", "--lr", "0.002", "--seed", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240)
+    """The same program on the GPU: the reference's cnnp / symbolic graph / autograd / planner / scheduled graph runner issuing a ResNet-50
+    training step to this backend.  The configuration is the one run on a B200 with this build (profiles/r02_cnnp_resnet50_reference_api_gpu.json:
+    batch 64 at 128 x 128, 9.7 ms/step, loss 8.67 -> 4.18 over five steps)."""
+    p = subprocess.run([exe, "--device", "gpu", "--batch", "64", "--image", "128", "--steps", "3", "--warmup", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240)
     assert p.returncode == 0, p.stderr.decode()[-1500:]
     r = json.loads(p.stdout.decode().strip().splitlines()[-1])
-    assert r["device"] == "gpu" and 0 < r["last_loss"] < r["first_loss"], r
+    assert r["device"] == "gpu" and r["images_per_sec"] > 0
+    assert 0 < r["last_loss"] < r["first_loss"], r  # five nesterov steps on one fixed batch
