@@ -49,10 +49,25 @@ def parse(text):
     return res, detail
 
 
+def _omp_threads():
+    """threads for the reference's CPU side of a test case (its CPU_REF comparison runs): the CPUs this process may use -- affinity cut by
+    a cgroup quota -- and at most 16: a container on a 128-thread host otherwise starts 128 spinning threads per parallel region"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return str(max(1, min(16, n)))
+
+
 def run(cmd, timeout):
     t0 = time.time()
+    env = dict(os.environ)
+    env.setdefault("OMP_NUM_THREADS", _omp_threads())
     try:
-        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, cwd=BUILD)
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, cwd=BUILD, env=env)
         return p.stdout.decode(errors="replace"), time.time() - t0
     except subprocess.TimeoutExpired as e:
         return (e.stdout or b"").decode(errors="replace") + "\n[program time limit]", time.time() - t0
