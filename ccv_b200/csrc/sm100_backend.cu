@@ -619,9 +619,10 @@ int conv_grouped_tc(ccv_nnc_stream_context_t* const stream_context, const int ki
 	const size_t wstep = (size_t)Kg * g.R * g.S * Cg * es;
 	for (int i = 0; i < groups; i++)
 	{
-		const unsigned char* const act_i = (const unsigned char*)act + (size_t)i * Cg * es;
-		const unsigned char* const res_i = (const unsigned char*)res + (size_t)i * Kg * es;
-		const unsigned char* const w_i = (const unsigned char*)filt + (size_t)i * wstep;
+		// (an operand a pass does not use is NULL: no arithmetic on it)
+		const unsigned char* const act_i = act ? (const unsigned char*)act + (size_t)i * Cg * es : 0;
+		const unsigned char* const res_i = res ? (const unsigned char*)res + (size_t)i * Kg * es : 0;
+		const unsigned char* const w_i = filt ? (const unsigned char*)filt + (size_t)i * wstep : 0;
 		int rc;
 		if (PASS == 0)
 		{
