@@ -396,6 +396,9 @@ enum {
 	CCV_NNC_TRANSPOSE_BACKWARD = 0xb4d506e1,
 	CCV_NNC_UPSAMPLE_FORWARD = 0x73875556,
 	CCV_NNC_UPSAMPLE_BACKWARD = 0x73875557,
+	/* feeder commands added with the drop-in proof (same rule; each value checked against lib/nnc/cmd/ccv_nnc_cmd.inc when it was added):
+	 * cmd/sigmoid, cmd/tanh, cmd/leaky_relu, cmd/ew (EWEXP / EWLOG / EWSQRT / CLAMP / EWDIV), cmd/reduce, cmd/util (MASKED_FILL), cmd/rand,
+	 * cmd/dropout, cmd/adam */
 	CCV_NNC_SIGMOID_FORWARD = 0xf2f69650,
 	CCV_NNC_SIGMOID_BACKWARD = 0xf2f69651,
 	CCV_NNC_TANH_FORWARD = 0x6a62be30,
